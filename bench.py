@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Benchmark of the EqF vision-update hot path: vision-updates/sec at N landmarks.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--landmarks 256] [--impl b200|reference]
+
+One *step* = one `processVisionData` call including the IMU integration since the previous image
+(10 IMU samples), preceded -- as eqvio_sim does (src/main_sim.cpp:136-142) -- by
+`augmentLandmarkStates`, on a synthetic VIOSimulator stream (simdata/, wave trajectory, 200/20 Hz,
+pinhole 752x480, fastRiccati, Euclidean chart, discrete lifts, equivariant output).  The default
+workload is BASELINE.json configs[1]: N = 256 landmarks, fp64 Sigma, one sequence per GPU.
+
+What is timed (CUDA events, after W warm-up steps, L2 flushed between steps outside the brackets):
+  value  updates/s from the device time of each update, measured with CUDA events recorded on the
+         filter's own stream from just after the step's pixels are staged in HBM to the last kernel
+         of the correction (propagation + preprocessing + correction, the reference's LoopTimer
+         labels).  Whole-job: sum over ranks of K / max over ranks of the summed device time.
+  e2e    updates/s through the host API with HOST buffers: per step 10x processIMUData,
+         augmentLandmarkStates, processVisionData (H2D of pixels / ids / IMU inside), and a D2H read
+         of the state estimate; events recorded on the current stream around each step (every call
+         ends synchronised, so device time == host time for the bracket).
+Multi-GPU (torchrun, one rank per GPU): independent sequences (seed = rank), no collective on the
+data path; one NCCL all-gather of the trajectories at the end (timed into e2e).  scaling = weak.
+
+--impl reference times the CPU restatement of the reference's dense Eigen path (oracle/, numpy fp64,
+same evaluation order incl. the doubly evaluated gain) on the host cores with the same stream.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--landmarks", type=int, default=256)
+    ap.add_argument("--coord", type=int, default=0)
+    ap.add_argument("--no-l2-flush", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="updates in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--profile-steps", type=int, default=10, help="extra untimed-for-throughput steps with per-kernel events")
+    return ap.parse_args()
+
+
+def settings_dict(coord):
+    """Benchmark filter settings: struct defaults of VIOFilter::Settings with fastRiccati on."""
+    return dict(fastRiccati=1, coordinateChoice=coord)
+
+
+def workload_name(N, coord):
+    return (f"VIOSimulator wave, N={N} landmarks, fp64 Sigma (dim {21 + 3 * N}), {'Euclidean' if coord == 0 else 'InvDepth'} chart, "
+            "fastRiccati, 10 IMU samples per update")
+
+
+# ---- algorithmic work per update (DESIGN.md "Roofline bookkeeping") -------------------------
+def alg_counts(N, n):
+    dim, m = 21 + 3 * N, 2 * n
+    return dict(
+        dim=dim, m=m,
+        syrk_flops=float(dim) * dim * m,  # Sigma -= Y^T Y on the lower triangle (2 m dim^2 / 2)
+        trail_flops=float(m) * m * m / 3 + float(m) * m * dim,  # Cholesky of S + trsm of W
+        prop_bytes=2.0 * 8 * dim * dim,  # read + write Sigma once
+        upd_flops=float(m) ** 3 / 3 + float(m) * m * dim + 2.0 * m * dim * dim / 2 + 72.0 * dim * dim,
+        upd_bytes=8.0 * (4 * dim * dim + 4 * m * dim))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi-equivalent sampling of SM clocks and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=self.max_mhz, reasons=[], samples=0)
+        return dict(sm_mhz=float(np.median(self.samples)), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                    samples=len(self.samples))
+
+
+def oracle_stream(stream, settings_kw):
+    """simdata stream -> the oracle's containers (cpu_baseline / reference arm only)."""
+    from oracle import eqf
+    from oracle.camera import PinholeCamera
+    from oracle.liegroups import SE3
+
+    st = eqf.Settings()
+    for k, v in settings_kw.items():
+        cur = getattr(st, k)
+        setattr(st, k, bool(v) if isinstance(cur, bool) else v)
+    c = stream.camera
+    cam = PinholeCamera(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"])
+    init = eqf.VIOState(eqf.VIOSensorState.fromFlat(stream.init_sensor), stream.init_p, stream.init_ids)
+    st.cameraOffset = SE3(stream.init_sensor[16:20], stream.init_sensor[20:23])
+    return st, cam, init
+
+
+def time_cpu(stream, settings_kw, warmup, steps):
+    """The reference's dense evaluation order on the host cores: returns (updates/s, per-stage seconds)."""
+    from oracle import eqf
+
+    st, cam, init = oracle_stream(stream, settings_kw)
+    flt = eqf.VIOFilter(st, init, 0.0)
+    flt.filterState.mirrorLazyEvaluation = True
+    t_total = 0.0
+    done = 0
+    for k, fr in enumerate(stream.frames[: 1 + warmup + steps]):
+        if k == 1 + warmup:
+            flt.timing = {"propagation": 0.0, "preprocessing": 0.0, "correction": 0.0}
+        t0 = time.perf_counter()
+        for row in fr.imu:
+            flt.processIMUData(eqf.IMUVelocity(row[0], row[1:4], row[4:7], row[7:10], row[10:13]))
+        meas = eqf.VisionMeasurement.fromArrays(fr.stamp, fr.ids, fr.y, cam)
+        flt.augmentLandmarkStates(meas.getIds(), eqf.VIOState(None, fr.provided_p, fr.ids))
+        flt.processVisionData(meas)
+        flt.stateEstimate()
+        if k >= 1 + warmup:
+            t_total += time.perf_counter() - t0
+            done += 1
+    return done / t_total, dict(flt.timing), done
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from simdata import SimConfig, record_stream
+
+    N = args.landmarks
+    skw = settings_dict(args.coord)
+    stream = record_stream(SimConfig.benchmark(N, 0), 1 + args.warmup + args.steps)
+    ups, stages, done = time_cpu(stream, skw, args.warmup, args.steps)
+    cores = blas_threads()
+    sample = f"{done} consecutive updates of the same stream after {args.warmup} warm-up updates"
+    line = dict(impl="reference", metric="vision-updates/sec", value=ups, unit="updates/s", n_gpus=args.gpus, steps=done,
+                warmup=args.warmup, ms_per_step=1000.0 / ups, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64", data="synthetic",
+                config=dict(workload=workload_name(N, args.coord), landmarks=N, impl_detail="oracle port of the dense Eigen path "
+                            "(numpy fp64 + OpenBLAS, reference evaluation order incl. doubly evaluated gain); the reference "
+                            "itself cannot be built here (Eigen3/OpenCV/yaml-cpp absent)"),
+                cpu_baseline=dict(value=ups, unit="updates/s", cores=cores, kind="port", sample=sample,
+                                  stage_ms={k: 1000.0 * v / done for k, v in stages.items()}),
+                e2e=dict(value=ups, unit="updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, local_rank, world):
+    import torch
+
+    import __graft_entry__ as entry
+
+    entry.build()
+    import eqvio_b200 as eb
+    from simdata import SimConfig, record_stream
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    N, K, W, P = args.landmarks, args.steps, args.warmup, args.profile_steps
+    skw = settings_dict(args.coord)
+    total_frames = 1 + W + K + P
+    if total_frames > 399:
+        raise SystemExit("bench.py: warmup + steps exceeds the 20 s simulated lap (399 updates)")
+    stream = record_stream(SimConfig.benchmark(N, rank), total_frames)
+    st = eb.Settings(**skw)
+    xi0 = eb.VIOState(eb.VIOSensorState.fromFlat(stream.init_sensor), stream.init_p, stream.init_ids)
+    flt = eb.VIOFilter(st, xi0, 0.0, capacity=N + 8, device=local_rank)
+    cam = eb.Camera(**stream.camera)
+    flt.enableStageTiming(True)
+
+    flush_buf = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def step(fr):
+        flt.processIMUArray(fr.imu)
+        flt.augmentLandmarkStates(fr.ids, eb.VIOState(eb.VIOSensorState(), fr.provided_p, fr.ids))
+        flt.processVisionArrays(fr.stamp, fr.ids, fr.y, cam)
+        return flt.stateEstimate()
+
+    def h2d_bytes(fr):
+        return fr.imu.nbytes + 2 * 4 * len(fr.ids) + fr.y.nbytes + 4 * len(fr.ids)  # imu + measIdx/lmOf + pixels (+ids of new lms)
+
+    frames = stream.frames
+    step(frames[0])  # t = 0 image: augments only
+    for fr in frames[1: 1 + W]:
+        step(fr)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = flt.launchCount()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    dev_ms = 0.0
+    stage_acc = dict(propagation=0.0, preprocessing=0.0, correction=0.0)
+    traj = np.zeros((K, 11))
+    h2d = d2h = 0
+    wall0 = time.perf_counter()
+    for k, fr in enumerate(frames[1 + W: 1 + W + K]):
+        if flush_buf is not None:
+            flush_buf.fill_(k & 0xFF)
+            torch.cuda.synchronize()
+        ev[k][0].record()
+        est = step(fr)
+        ev[k][1].record()
+        sm = flt.stageMs()
+        for key in stage_acc:
+            stage_acc[key] += sm[key]
+        dev_ms += sm["propagation"] + sm["preprocessing"] + sm["correction"]
+        traj[k, 0] = fr.stamp
+        traj[k, 1:4], traj[k, 4:8], traj[k, 8:11] = est.sensor.pose_x, est.sensor.pose_q, est.sensor.velocity
+        h2d += h2d_bytes(fr)
+        d2h += 8 * (23 + 3 * len(est.ids)) + 8 * 3 * N + 4 * (1 + N)  # state estimate + gate scalars + status
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    launches = flt.launchCount() - launches0
+    e2e_ms = sum(a.elapsed_time(b) for a, b in ev)
+    # the single collective of the path: all-gather of the trajectories at the end
+    if dist:
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tt = torch.from_numpy(traj).cuda()
+        out = [torch.empty_like(tt) for _ in range(world)]
+        g0.record()
+        dist.all_gather(out, tt)
+        g1.record()
+        torch.cuda.synchronize()
+        e2e_ms += g0.elapsed_time(g1)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # per-kernel profile on extra steps (event pairs around every launch of the four kernel classes)
+    flt.enableKernelProfile(True)
+    flt.kernelProfile(reset=True)
+    nprof = 0
+    for fr in frames[1 + W + K: 1 + W + K + P]:
+        if flush_buf is not None:
+            flush_buf.fill_(1)
+            torch.cuda.synchronize()
+        step(fr)
+        nprof += 1
+    prof = flt.kernelProfile(reset=True)
+    flt.enableKernelProfile(False)
+    n_meas = len(frames[1 + W].ids)
+    n_state = flt.numLandmarks()
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        # fp64 has no entry in MEASURED_PEAKS.json (tcgen05 has no fp64 kind; the path runs on the FP64
+        # DMMA pipe): calibrate a cuBLAS DGEMM here and use it as the tensor-bound denominator.
+        a = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
+        b = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            a @ b
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        f64_peak = 2.0 * 4096**3 / (best * 1e-3) / 1e12
+
+        cnt = alg_counts(n_state, n_meas)
+        kern = {}
+        for name, d in prof.items():
+            if d["launches"] == 0:
+                continue
+            per_update_ms = d["ms"] / max(nprof, 1)
+            e = dict(ms_per_update=per_update_ms, launches_per_update=d["launches"] / max(nprof, 1),
+                     avg_launch_us=1000.0 * d["ms"] / d["launches"])
+            if name == "syrk":
+                e.update(bound="tensor", achieved=cnt["syrk_flops"] / (per_update_ms * 1e-3) / 1e12, peak=f64_peak, unit="TFLOP/s")
+            elif name == "chol_trail":
+                e.update(bound="tensor", achieved=cnt["trail_flops"] / (per_update_ms * 1e-3) / 1e12, peak=f64_peak, unit="TFLOP/s")
+            elif name == "prop_ll":
+                e.update(bound="hbm", achieved=cnt["prop_bytes"] / (per_update_ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s")
+            if "achieved" in e:
+                e["frac"] = e["achieved"] / e["peak"]
+            kern[name] = e
+        dom = max(kern, key=lambda k_: kern[k_]["ms_per_update"]) if kern else None
+        # the dominant kernel must carry a roofline; the serial panel kernel is latency-bound, report the
+        # heaviest kernel that has a bound and keep the panel's share visible in `kernels`
+        dom_r = max((k_ for k_ in kern if "achieved" in kern[k_]), key=lambda k_: kern[k_]["ms_per_update"], default=None)
+        roofline = None
+        if dom_r:
+            d = kern[dom_r]
+            roofline = dict(kernel=dom_r, bound=d["bound"], achieved=d["achieved"], peak=d["peak"], unit=d["unit"], frac=d["frac"],
+                            traffic=None, avg_launch_us=d["avg_launch_us"],
+                            peak_source=(hbm_src if d["bound"] == "hbm" else
+                                         f"cuBLAS DGEMM 4096^3 measured in this run ({f64_peak:.1f} TFLOP/s); MEASURED_PEAKS.json "
+                                         "has no fp64 figure"),
+                            dominant_by_time=dom, kernels=kern,
+                            update=dict(flops=cnt["upd_flops"], bytes=cnt["upd_bytes"],
+                                        flops_frac=cnt["upd_flops"] * K / (dev_ms / 1e3) / 1e12 / f64_peak,
+                                        hbm_frac=cnt["upd_bytes"] * K / (dev_ms / 1e3) / 1e9 / hbm_peak))
+        value = world * K / (dev_ms_max * 1e-3)
+        e2e = world * K / (e2e_ms_max * 1e-3)
+        line = dict(metric="vision-updates/sec", value=value, unit="updates/s", n_gpus=world, steps=K, warmup=W,
+                    ms_per_step=dev_ms_max / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                    data="synthetic",
+                    config=dict(workload=workload_name(N, args.coord), landmarks=N, measured_per_update=n_meas, state_dim=cnt["dim"],
+                                sequences_per_gpu=1, l2="not flushed" if args.no_l2_flush else
+                                "flushed between steps (256 MiB write) outside the per-step event brackets",
+                                value_timing="CUDA events on the filter stream: pixels staged -> last correction kernel",
+                                parallelism=f"replicas x{world}, one sequence per GPU, all-gather of trajectories at the end"),
+                    e2e=dict(value=e2e, unit="updates/s", h2d_bytes_per_step=h2d // K, d2h_bytes_per_step=d2h // K,
+                             ms_per_step=e2e_ms_max / K, wall_ms_per_step=1000.0 * wall / K),
+                    gpu_launches=int(launches), launches_per_step=launches / K,
+                    stage_ms={k_: v / K for k_, v in stage_acc.items()}, clocks=sampler.result(), roofline=roofline)
+        if not args.no_cpu_baseline:
+            est_s = 17.0 * cnt["dim"] ** 3 / 50e9 + 0.02  # ~17 dim^3 flops of the dense path at a conservative 50 GFLOP/s
+            sample_n = args.cpu_sample or int(max(3, min(K, 20.0 / est_s)))
+            ups, stages, done = time_cpu(stream, skw, min(W, 2), sample_n)
+            line["cpu_baseline"] = dict(value=ups, unit="updates/s", cores=blas_threads(), kind="port",
+                                        sample=f"{done} consecutive updates of rank 0's stream (same inputs) after {min(W, 2)} warm-up "
+                                        "updates; oracle port of the dense Eigen path, reference evaluation order",
+                                        stage_ms={k_: 1000.0 * v / done for k_, v in stages.items()})
+        print(json.dumps(line), flush=True)
+    flt.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,1333 @@
+// Host side of the B200 EqF path: the filter driver of the reference's VIOFilter
+// (src/VIOFilter.cpp) re-bodied over device-resident state, exported through the C ABI declared in
+// include/eqvio_b200.h.  Everything numerical runs in the kernels of kernels.cuh; the host keeps
+// only the IMU buffer, the landmark id list and the discrete bookkeeping decisions
+// (which landmarks to drop / add), made in fp64 from per-landmark scalars the gate kernel returns.
+//
+// There is no CPU fallback: every entry point that touches filter state needs a CUDA device and
+// returns EQVIO_ERR_CUDA otherwise.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/eqvio_b200.h"
+#include "kernels.cuh"
+
+using namespace eqvio;
+
+#define EQVIO_STR2(x) #x
+#define EQVIO_STR(x) EQVIO_STR2(x)
+
+namespace {
+
+std::string g_createError;
+
+struct ImuSample {
+    double stamp;
+    double v[12];  // gyr, acc, gyrBiasVel, accBiasVel
+};
+
+enum { PROF_PROP_LL = 0, PROF_PANEL, PROF_TRAIL, PROF_SYRK, PROF_CLASSES };
+
+struct EventPair {
+    cudaEvent_t a, b;
+    int cls;
+};
+
+}  // namespace
+
+struct eqvio_filter {
+    eqvio_settings st;
+    int device = 0, cap = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    std::string err;
+
+    // host-side filter state
+    bool initialised = false;
+    double time = -1.0;
+    std::deque<ImuSample> buf;
+    std::vector<int> ids;  // state order
+    double xi0s[23];       // host mirror of xi0.sensor
+    std::vector<int> lastOutliers;
+
+    // device state
+    int ld = 0;
+    double* Sig[2] = {nullptr, nullptr};
+    int cur = 0;
+    double* lm[2] = {nullptr, nullptr};
+    int* dids[2] = {nullptr, nullptr};
+    int lmcur = 0;
+    double *d_xi0s = nullptr, *d_Xs = nullptr;
+    RiccatiCtx* d_ctx = nullptr;
+    ObsStep* d_steps = nullptr;
+    double* d_imu = nullptr;
+    int maxSteps = 0;
+    int yCap = 0;
+    double *d_rows = nullptr, *d_uv = nullptr, *d_Z = nullptr, *d_Lout = nullptr;
+    size_t zElems = 0;
+    double *d_Cblk = nullptr, *d_Gamma = nullptr, *d_gate = nullptr, *d_y = nullptr, *d_newP = nullptr, *d_out = nullptr;
+    int *d_measIdx = nullptr, *d_lmOf = nullptr, *d_map = nullptr, *d_newIds = nullptr, *d_status = nullptr;
+
+    // pinned staging arena (reset at the start of every API call; calls end synchronised)
+    std::vector<std::pair<char*, size_t>> arenas;
+    size_t arenaUsed = 0;
+
+    // measurement hooks
+    long long launches = 0;
+    bool stageTiming = false;
+    cudaEvent_t stageEv[4] = {nullptr, nullptr, nullptr, nullptr};
+    double stageMs[3] = {0, 0, 0};
+    double augMs = 0;  // device time of augment_landmark_states calls since the last process_vision
+    bool profiling = false;
+    std::vector<EventPair> evPool;
+    size_t evUsed = 0;
+    double profMs[PROF_CLASSES] = {0, 0, 0, 0};
+    long long profLaunches[PROF_CLASSES] = {0, 0, 0, 0};
+
+    // scratch of a process_vision call split in phases (batch API)
+    struct Pending {
+        bool active = false, gated = false;
+        int n = 0;
+        std::vector<int> mids;
+        std::vector<double> my;
+        std::vector<int> measIdx;  // per state landmark
+        std::vector<char> keep;
+        double* h_gate = nullptr;
+        int* h_status = nullptr;
+        int nStatus = 0;
+        Camera cam;
+        bool corrected = false;
+    } pend;
+};
+
+namespace {
+
+#define CUDA_TRY(f, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            (f)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                        \
+            return EQVIO_ERR_CUDA;                                                                \
+        }                                                                                         \
+    } while (0)
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline int dimp_of(int N) { return SOFF + 3 * N; }
+
+void* stage_alloc(eqvio_filter* f, size_t bytes) {
+    bytes = (bytes + 63) & ~size_t(63);
+    if (!f->arenas.empty()) {
+        auto& a = f->arenas.back();
+        if (f->arenaUsed + bytes <= a.second) {
+            void* p = a.first + f->arenaUsed;
+            f->arenaUsed += bytes;
+            return p;
+        }
+    }
+    size_t sz = std::max(bytes, size_t(1) << 20);
+    char* p = nullptr;
+    if (cudaMallocHost(&p, sz) != cudaSuccess) return nullptr;
+    f->arenas.emplace_back(p, sz);
+    f->arenaUsed = bytes;
+    return p;
+}
+void stage_reset(eqvio_filter* f) {
+    // keep only the largest arena
+    while (f->arenas.size() > 1) {
+        size_t smallest = 0;
+        for (size_t i = 1; i < f->arenas.size(); ++i)
+            if (f->arenas[i].second < f->arenas[smallest].second) smallest = i;
+        cudaFreeHost(f->arenas[smallest].first);
+        f->arenas.erase(f->arenas.begin() + smallest);
+    }
+    f->arenaUsed = 0;
+}
+
+template <class T>
+int upload(eqvio_filter* f, T* dst, const T* src, size_t count) {
+    if (count == 0) return EQVIO_OK;
+    T* h = static_cast<T*>(stage_alloc(f, count * sizeof(T)));
+    if (!h) {
+        f->err = "pinned staging allocation failed";
+        return EQVIO_ERR_CUDA;
+    }
+    std::memcpy(h, src, count * sizeof(T));
+    CUDA_TRY(f, cudaMemcpyAsync(dst, h, count * sizeof(T), cudaMemcpyHostToDevice, f->stream));
+    return EQVIO_OK;
+}
+template <class T>
+int download_async(eqvio_filter* f, T** hostOut, const T* src, size_t count) {
+    T* h = static_cast<T*>(stage_alloc(f, std::max<size_t>(count, 1) * sizeof(T)));
+    if (!h) {
+        f->err = "pinned staging allocation failed";
+        return EQVIO_ERR_CUDA;
+    }
+    if (count) CUDA_TRY(f, cudaMemcpyAsync(h, src, count * sizeof(T), cudaMemcpyDeviceToHost, f->stream));
+    *hostOut = h;
+    return EQVIO_OK;
+}
+
+int check_launch(eqvio_filter* f, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        f->err = std::string(what) + ": " + cudaGetErrorString(e);
+        return EQVIO_ERR_CUDA;
+    }
+    ++f->launches;
+    return EQVIO_OK;
+}
+#define LAUNCH_CHECK(f, what)                          \
+    do {                                               \
+        int rc_ = check_launch((f), (what));           \
+        if (rc_ != EQVIO_OK) return rc_;               \
+    } while (0)
+
+// profiling brackets -------------------------------------------------------------------------
+int prof_begin(eqvio_filter* f, int cls) {
+    if (!f->profiling) return -1;
+    if (f->evUsed == f->evPool.size()) {
+        EventPair p;
+        cudaEventCreate(&p.a);
+        cudaEventCreate(&p.b);
+        f->evPool.push_back(p);
+    }
+    int k = (int)f->evUsed++;
+    f->evPool[k].cls = cls;
+    cudaEventRecord(f->evPool[k].a, f->stream);
+    return k;
+}
+void prof_end(eqvio_filter* f, int k) {
+    if (k >= 0) cudaEventRecord(f->evPool[k].b, f->stream);
+}
+void prof_collect(eqvio_filter* f) {  // stream must be synchronised
+    for (size_t k = 0; k < f->evUsed; ++k) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, f->evPool[k].a, f->evPool[k].b) == cudaSuccess) {
+            f->profMs[f->evPool[k].cls] += ms;
+            f->profLaunches[f->evPool[k].cls] += 1;
+        }
+    }
+    f->evUsed = 0;
+}
+void stage_mark(eqvio_filter* f, int i) {
+    if (f->stageTiming) cudaEventRecord(f->stageEv[i], f->stream);
+}
+
+Camera to_camera(const eqvio_camera* c) {
+    Camera k;
+    k.model = c->model;
+    k.width = c->width;
+    k.height = c->height;
+    k.ndist = c->ndist;
+    k.fx = c->fx;
+    k.fy = c->fy;
+    k.cx = c->cx;
+    k.cy = c->cy;
+    for (int i = 0; i < 5; ++i) {
+        k.dist[i] = c->dist[i];
+        k.inv_dist[i] = c->inv_dist[i];
+    }
+    return k;
+}
+
+// Initial covariance diagonal in the internal (padded) order (VIOFilterSettings.h:208-229).
+void initial_diag(const eqvio_settings& s, int N, bool depthVariance, std::vector<double>& d) {
+    d.assign(dimp_of(N), 0.0);
+    const double v[7] = {s.initialBiasOmegaVariance,      s.initialBiasAccelVariance,     s.initialAttitudeVariance,
+                         s.initialPositionVariance,       s.initialVelocityVariance,      s.initialCameraAttitudeVariance,
+                         s.initialCameraPositionVariance};
+    for (int i = 0; i < SENSOR_DIM; ++i) d[i] = v[i / 3];
+    for (int i = 0; i < N; ++i)
+        for (int a = 0; a < 3; ++a)
+            d[SOFF + 3 * i + a] =
+                (a == 2 && depthVariance && s.initialPointDepthVariance > 0) ? s.initialPointDepthVariance : s.initialPointVariance;
+}
+
+int alloc_device(eqvio_filter* f) {
+    const int cap = f->cap;
+    const int dimpMax = dimp_of(cap);
+    f->ld = (dimpMax + 7) & ~7;
+    const size_t sigElems = (size_t)f->ld * f->ld;
+    for (int k = 0; k < 2; ++k) {
+        CUDA_TRY(f, cudaMalloc(&f->Sig[k], sigElems * sizeof(double)));
+        CUDA_TRY(f, cudaMemsetAsync(f->Sig[k], 0, sigElems * sizeof(double), f->stream));
+        CUDA_TRY(f, cudaMalloc(&f->lm[k], (size_t)LM_FIELDS * std::max(cap, 1) * sizeof(double)));
+        CUDA_TRY(f, cudaMemsetAsync(f->lm[k], 0, (size_t)LM_FIELDS * std::max(cap, 1) * sizeof(double), f->stream));
+        CUDA_TRY(f, cudaMalloc(&f->dids[k], std::max(cap, 1) * sizeof(int)));
+    }
+    CUDA_TRY(f, cudaMalloc(&f->d_xi0s, 23 * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&f->d_Xs, 23 * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&f->d_ctx, sizeof(RiccatiCtx)));
+    f->maxSteps = 64;
+    CUDA_TRY(f, cudaMalloc(&f->d_steps, f->maxSteps * sizeof(ObsStep)));
+    CUDA_TRY(f, cudaMalloc(&f->d_imu, f->maxSteps * 13 * sizeof(double)));
+    const size_t c1 = std::max(cap, 1);
+    CUDA_TRY(f, cudaMalloc(&f->d_rows, c1 * ROWS_STRIDE * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&f->d_uv, c1 * UV_STRIDE * sizeof(double)));
+    const size_t mMax = 2 * c1;
+    const size_t ldzMax = (mMax + dimpMax + 1 + 7) & ~size_t(7);
+    f->zElems = std::max(ldzMax * mMax, sigElems);
+    CUDA_TRY(f, cudaMalloc(&f->d_Z, f->zElems * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&f->d_Lout, (mMax + NB) * NB * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&f->d_Cblk, c1 * 6 * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&f->d_Gamma, (size_t)(dimpMax + 8) * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&f->d_gate, c1 * 3 * sizeof(double)));
+    f->yCap = (int)c1;
+    CUDA_TRY(f, cudaMalloc(&f->d_y, c1 * 2 * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&f->d_newP, c1 * 3 * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&f->d_out, (23 + 3 * c1) * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&f->d_measIdx, c1 * sizeof(int)));
+    CUDA_TRY(f, cudaMalloc(&f->d_lmOf, c1 * sizeof(int)));
+    CUDA_TRY(f, cudaMalloc(&f->d_map, c1 * sizeof(int)));
+    CUDA_TRY(f, cudaMalloc(&f->d_newIds, c1 * sizeof(int)));
+    CUDA_TRY(f, cudaMalloc(&f->d_status, (1 + c1) * sizeof(int)));
+    CUDA_TRY(f, cudaMemsetAsync(f->d_status, 0, (1 + c1) * sizeof(int), f->stream));
+    for (int i = 0; i < 4; ++i) CUDA_TRY(f, cudaEventCreate(&f->stageEv[i]));
+    return EQVIO_OK;
+}
+
+void group_identity_flat(double* g) {
+    for (int i = 0; i < 23; ++i) g[i] = 0.0;
+    g[6] = 1.0;
+    g[16] = 1.0;
+}
+
+// Replace the whole device state: xi0 sensor, X = identity, landmarks (ids, p) with Q = identity,
+// Sigma = diag(diagInternal).
+int reset_state(eqvio_filter* f, const double sensor[23], int n, const int* ids, const double* p,
+                const std::vector<double>& diag) {
+    if (n > f->cap) {
+        f->err = "landmark count exceeds the capacity the handle was created with";
+        return EQVIO_ERR_CAPACITY;
+    }
+    std::memcpy(f->xi0s, sensor, 23 * sizeof(double));
+    int rc;
+    if ((rc = upload(f, f->d_xi0s, sensor, 23)) != EQVIO_OK) return rc;
+    double gid[23];
+    group_identity_flat(gid);
+    if ((rc = upload(f, f->d_Xs, gid, 23)) != EQVIO_OK) return rc;
+    f->ids.assign(ids, ids + n);
+    if (n > 0) {
+        std::vector<double> soa((size_t)LM_FIELDS * n);
+        for (int i = 0; i < n; ++i) {
+            soa[F_Q0X * n + i] = p[3 * i];
+            soa[F_Q0Y * n + i] = p[3 * i + 1];
+            soa[F_Q0Z * n + i] = p[3 * i + 2];
+            soa[F_QW * n + i] = 1.0;
+            soa[F_QX * n + i] = 0.0;
+            soa[F_QY * n + i] = 0.0;
+            soa[F_QZ * n + i] = 0.0;
+            soa[F_QA * n + i] = 1.0;
+        }
+        double* h = static_cast<double*>(stage_alloc(f, soa.size() * sizeof(double)));
+        if (!h) return EQVIO_ERR_CUDA;
+        std::memcpy(h, soa.data(), soa.size() * sizeof(double));
+        for (int fld = 0; fld < LM_FIELDS; ++fld)
+            CUDA_TRY(f, cudaMemcpyAsync(f->lm[f->lmcur] + (size_t)fld * f->cap, h + (size_t)fld * n, n * sizeof(double),
+                                        cudaMemcpyHostToDevice, f->stream));
+        if ((rc = upload(f, f->dids[f->lmcur], ids, n)) != EQVIO_OK) return rc;
+    }
+    const int dimp = dimp_of(n);
+    double* d_diag = f->d_Gamma;  // scratch, dimp <= dimpMax
+    if ((rc = upload(f, d_diag, diag.data(), dimp)) != EQVIO_OK) return rc;
+    dim3 grid(cdiv(dimp, 128), dimp);
+    fill_diag_kernel<<<grid, 128, 0, f->stream>>>(f->Sig[f->cur], f->ld, dimp, d_diag);
+    LAUNCH_CHECK(f, "fill_diag_kernel");
+    CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+    return EQVIO_OK;
+}
+
+// Apply a landmark map (stable compaction + append) to lm / ids / Sigma.
+int apply_map(eqvio_filter* f, const std::vector<int>& map, const std::vector<int>& newIds, const std::vector<double>& newP,
+              double newVar, double newDepthVar) {
+    const int newN = (int)map.size();
+    if (newN > f->cap) {
+        f->err = "landmark count exceeds the capacity the handle was created with";
+        return EQVIO_ERR_CAPACITY;
+    }
+    bool identity = (newN == (int)f->ids.size());
+    for (int p = 0; identity && p < newN; ++p) identity = (map[p] == p);
+    if (identity) return EQVIO_OK;
+    int rc;
+    std::vector<int> nids(newN);
+    for (int p = 0; p < newN; ++p) nids[p] = map[p] >= 0 ? f->ids[map[p]] : newIds[-1 - map[p]];
+    if (newN > 0) {
+        if ((rc = upload(f, f->d_map, map.data(), newN)) != EQVIO_OK) return rc;
+        if (!newIds.empty()) {
+            if ((rc = upload(f, f->d_newIds, newIds.data(), newIds.size())) != EQVIO_OK) return rc;
+            if ((rc = upload(f, f->d_newP, newP.data(), newP.size())) != EQVIO_OK) return rc;
+        }
+        compact_landmarks_kernel<<<cdiv(newN, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->lm[1 - f->lmcur], f->cap,
+                                                                          f->dids[f->lmcur], f->dids[1 - f->lmcur], f->d_map,
+                                                                          newN, f->d_newP, f->d_newIds);
+        LAUNCH_CHECK(f, "compact_landmarks_kernel");
+        f->lmcur = 1 - f->lmcur;
+    }
+    {
+        const int nb = 8 + newN;
+        dim3 block(32, 8);
+        dim3 grid(cdiv(nb, 32), cdiv(nb, 8));
+        compact_sigma_kernel<<<grid, block, 0, f->stream>>>(f->Sig[f->cur], f->Sig[1 - f->cur], f->ld, f->d_map, newN, newVar,
+                                                            newDepthVar);
+        LAUNCH_CHECK(f, "compact_sigma_kernel");
+        f->cur = 1 - f->cur;
+    }
+    f->ids.swap(nids);
+    return EQVIO_OK;
+}
+
+// removeOldLandmarks (VIOFilter.cpp:280-302) followed by an append of `addIds` with positions `addP`.
+int remove_and_append(eqvio_filter* f, const std::vector<char>& keep, const std::vector<int>& addIds,
+                      const std::vector<double>& addP, double newVar, double newDepthVar) {
+    std::vector<int> map;
+    map.reserve(f->ids.size() + addIds.size());
+    for (int i = 0; i < (int)f->ids.size(); ++i)
+        if (keep[i]) map.push_back(i);
+    for (int k = 0; k < (int)addIds.size(); ++k) map.push_back(-1 - k);
+    return apply_map(f, map, addIds, addP, newVar, newDepthVar);
+}
+
+// integrateUpToTime (VIOFilter.cpp:134-192).  *advanced = 0 reproduces the reference's `return false`.
+int integrate_up_to_time(eqvio_filter* f, double newTime, int* advanced) {
+    *advanced = 0;
+    if (newTime <= f->time || f->time < 0 || f->buf.empty()) return EQVIO_OK;
+    const eqvio_settings& s = f->st;
+    if (!s.fastRiccati) {
+        f->err = "fastRiccati=false (integrateRiccatiStateAccurate/Discrete) has no CUDA path in this build";
+        return EQVIO_ERR_UNSUPPORTED;
+    }
+    const int n = (int)f->buf.size();
+    const int N = (int)f->ids.size();
+    std::vector<double> imu((size_t)13 * n);
+    double accT = 0.0, acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+        const double t0 = std::max(f->buf[i].stamp, f->time);
+        const double t1 = i + 1 < n ? std::min(f->buf[i + 1].stamp, newTime) : newTime;
+        const double dt = std::max(t1 - t0, 0.0);
+        imu[13 * i] = dt;
+        for (int k = 0; k < 12; ++k) imu[13 * i + 1 + k] = f->buf[i].v[k];
+        accT += dt;
+        for (int k = 0; k < 12; ++k) acc[k] = acc[k] + f->buf[i].v[k] * dt;
+    }
+    const double inv = 1.0 / accT;
+    for (int k = 0; k < 12; ++k) acc[k] = acc[k] * inv;
+
+    if (n > f->maxSteps) {
+        CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+        cudaFree(f->d_steps);
+        cudaFree(f->d_imu);
+        f->maxSteps = n * 2;
+        CUDA_TRY(f, cudaMalloc(&f->d_steps, f->maxSteps * sizeof(ObsStep)));
+        CUDA_TRY(f, cudaMalloc(&f->d_imu, f->maxSteps * 13 * sizeof(double)));
+    }
+    int rc;
+    if ((rc = upload(f, f->d_imu, imu.data(), imu.size())) != EQVIO_OK) return rc;
+
+    const int CH = 256;  // IMU segments per launch (ObsStep staging in shared memory)
+    for (int s0 = 0; s0 < n; s0 += CH) {
+        const int ns = std::min(CH, n - s0);
+        const int doRic = (s0 == 0) ? 1 : 0;
+        PrepArgs a;
+        a.xi0s = f->d_xi0s;
+        a.Xs = f->d_Xs;
+        a.ctx = f->d_ctx;
+        a.steps = f->d_steps + s0;
+        a.imu = f->d_imu + (size_t)13 * s0;
+        a.nsteps = ns;
+        for (int k = 0; k < 12; ++k) a.meanImu[k] = acc[k];
+        a.dtTotal = accT;
+        a.doRiccati = doRic;
+        a.discreteLift = s.useDiscreteVelocityLift ? 1 : 0;
+        a.qdiag[0] = s.velGyrNoise * s.velGyrNoise;
+        a.qdiag[1] = s.velAccNoise * s.velAccNoise;
+        a.qdiag[2] = s.velGyrBiasWalk * s.velGyrBiasWalk;
+        a.qdiag[3] = s.velAccBiasWalk * s.velAccBiasWalk;
+        a.pdiag[0] = s.biasOmegaProcessVariance;
+        a.pdiag[1] = s.biasAccelProcessVariance;
+        a.pdiag[2] = s.attitudeProcessVariance;
+        a.pdiag[3] = s.positionProcessVariance;
+        a.pdiag[4] = s.velocityProcessVariance;
+        a.pdiag[5] = s.cameraAttitudeProcessVariance;
+        a.pdiag[6] = s.cameraPositionProcessVariance;
+        a.pdiag[7] = s.pointProcessVariance;
+        sensor_prep_kernel<<<1, 32, 0, f->stream>>>(a);
+        LAUNCH_CHECK(f, "sensor_prep_kernel");
+        if (N > 0) {
+            landmark_propagate_kernel<<<cdiv(N, 128), 128, ns * sizeof(ObsStep), f->stream>>>(
+                f->lm[f->lmcur], f->cap, N, f->d_ctx, f->d_steps + s0, ns, doRic, s.coordinateChoice, f->d_rows);
+            LAUNCH_CHECK(f, "landmark_propagate_kernel");
+        }
+        if (doRic) {
+            const double* Sin = f->Sig[f->cur];
+            double* Sout = f->Sig[1 - f->cur];
+            prop_sensor_block_kernel<<<1, 448, 0, f->stream>>>(Sin, Sout, f->ld, f->d_ctx);
+            LAUNCH_CHECK(f, "prop_sensor_block_kernel");
+            if (N > 0) {
+                prop_strip_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv);
+                LAUNCH_CHECK(f, "prop_strip_kernel");
+                const int nt = cdiv(N, TP);
+                int pk = prof_begin(f, PROF_PROP_LL);
+                prop_ll_kernel<<<dim3(nt, nt), dim3(TP, TP), 0, f->stream>>>(Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv);
+                prof_end(f, pk);
+                LAUNCH_CHECK(f, "prop_ll_kernel");
+            }
+            f->cur = 1 - f->cur;
+        }
+    }
+    f->time = newTime;
+    // prune, keeping the last sample with stamp < currentTime (VIOFilter.cpp:183-189)
+    size_t k = 0;
+    while (k < f->buf.size() && !(f->buf[k].stamp >= f->time)) ++k;
+    if (k != 0) f->buf.erase(f->buf.begin(), f->buf.begin() + (k - 1));
+    *advanced = 1;
+    return EQVIO_OK;
+}
+
+// ---- process_vision, phase A: propagate, launch the gate, start its download ---------------------
+int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const double* y, const eqvio_camera* cam) {
+    auto& P = f->pend;
+    P = eqvio_filter::Pending();
+    stage_reset(f);
+    f->lastOutliers.clear();
+    if (n < 0 || (n > 0 && (!ids || !y)) || !cam) {
+        f->err = "invalid measurement arguments";
+        return EQVIO_ERR_INVALID_ARG;
+    }
+    for (int j = 1; j < n; ++j)
+        if (ids[j] <= ids[j - 1]) {
+            f->err = "measurement ids must be strictly ascending";
+            return EQVIO_ERR_INVALID_ARG;
+        }
+    if (cam->model != EQVIO_CAMERA_PINHOLE && cam->model != EQVIO_CAMERA_RADTAN) {
+        f->err = "unsupported camera model";
+        return EQVIO_ERR_UNSUPPORTED;
+    }
+    // inputs (pixels) are staged in HBM before the first timing event; the IMU samples follow inside
+    // integrate_up_to_time (1 KB) and are counted with the propagation stage
+    int rc;
+    if (n > f->yCap) {  // a measurement may list more ids than the state can hold (gated later)
+        CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+        cudaFree(f->d_y);
+        f->d_y = nullptr;
+        f->yCap = 2 * n;
+        CUDA_TRY(f, cudaMalloc(&f->d_y, (size_t)f->yCap * 2 * sizeof(double)));
+    }
+    if (n > 0 && (rc = upload(f, f->d_y, y, 2 * (size_t)n)) != EQVIO_OK) return rc;
+    stage_mark(f, 0);
+    int advanced = 0;
+    rc = integrate_up_to_time(f, stamp, &advanced);
+    if (rc != EQVIO_OK) return rc;
+    stage_mark(f, 1);
+    if (!advanced || !f->initialised) return EQVIO_OK;  // VIOFilter.cpp:198-199
+    P.active = true;
+    P.n = n;
+    P.mids.assign(ids, ids + n);
+    P.my.assign(y, y + 2 * n);
+    P.cam = to_camera(cam);
+    const int N = (int)f->ids.size();
+    std::unordered_map<int, int> pos;
+    pos.reserve(n * 2 + 1);
+    for (int j = 0; j < n; ++j) pos[ids[j]] = j;
+    P.measIdx.assign(N, -1);
+    P.keep.assign(N, 1);
+    for (int i = 0; i < N; ++i) {
+        auto it = pos.find(f->ids[i]);
+        if (it != pos.end())
+            P.measIdx[i] = it->second;
+        else if (f->st.removeLostLandmarks)
+            P.keep[i] = 0;  // removeOldLandmarks, VIOFilter.cpp:203-205
+    }
+    if (N > 0) {
+        if ((rc = upload(f, f->d_measIdx, P.measIdx.data(), N)) != EQVIO_OK) return rc;
+        gate_kernel<<<cdiv(N, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->Sig[f->cur], f->ld, f->d_measIdx,
+                                                          f->d_y, P.cam, f->st.coordinateChoice, f->d_gate);
+        LAUNCH_CHECK(f, "gate_kernel");
+        if ((rc = download_async(f, &P.h_gate, f->d_gate, 3 * (size_t)N)) != EQVIO_OK) return rc;
+        P.gated = true;
+    }
+    return EQVIO_OK;
+}
+
+// ---- phase B: bookkeeping decisions on the host, compaction, correction launches -------------------
+int vision_phase_b(eqvio_filter* f) {
+    auto& P = f->pend;
+    if (!P.active) return EQVIO_OK;
+    const eqvio_settings& s = f->st;
+    int rc;
+    if (P.gated) CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+    const int N = (int)f->ids.size();
+    const int n = P.n;
+    const double* errAbs = P.h_gate;
+    const double* errProb = P.h_gate ? P.h_gate + N : nullptr;
+    const double* depth2 = P.h_gate ? P.h_gate + 2 * N : nullptr;
+
+    // removeOutliers (VIOFilter.cpp:304-364): candidates are visited in ascending id like the
+    // reference's std::map iteration.
+    const size_t maxOutliers = (size_t)((1.0 - s.featureRetention) * n);
+    std::vector<int> order;  // state indices of measured, kept landmarks in ascending id
+    for (int i = 0; i < N; ++i)
+        if (P.keep[i] && P.measIdx[i] >= 0) order.push_back(i);
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return f->ids[a] < f->ids[b]; });
+    std::vector<int> proposed;
+    std::map<int, double> absOut, probOut;  // keyed by state index
+    for (int i : order)
+        if (errAbs[i] > s.outlierThresholdAbs) {
+            absOut[i] = errAbs[i];
+            proposed.push_back(i);
+        }
+    for (int i : order) {
+        if (absOut.count(i)) continue;
+        if (errProb[i] > s.outlierThresholdProb) {
+            probOut[i] = errProb[i];
+            proposed.push_back(i);
+        }
+    }
+    std::sort(proposed.begin(), proposed.end(), [&](int a, int b) {
+        if (absOut.count(a)) {
+            if (absOut.count(b)) return absOut.at(a) < absOut.at(b);
+            return false;
+        }
+        if (absOut.count(b)) return true;
+        return probOut.at(a) < probOut.at(b);
+    });
+    std::reverse(proposed.begin(), proposed.end());
+    if (proposed.size() > maxOutliers) proposed.resize(maxOutliers);
+    std::vector<char> measKept(n, 1);
+    for (int i : proposed) {
+        P.keep[i] = 0;
+        measKept[P.measIdx[i]] = 0;
+        f->lastOutliers.push_back(f->ids[i]);
+    }
+
+    // addNewLandmarks (VIOFilter.cpp:258-278)
+    std::vector<char> measInState(n, 0);
+    for (int i = 0; i < N; ++i)
+        if (P.measIdx[i] >= 0) measInState[P.measIdx[i]] = 1;
+    std::vector<int> addIds;
+    std::vector<double> addP;
+    for (int j = 0; j < n; ++j)
+        if (!measInState[j]) addIds.push_back(P.mids[j]);
+    if (!addIds.empty()) {
+        double depth = s.initialSceneDepth;
+        if (s.useMedianDepth) {  // getMedianSceneDepth, VIOFilter.cpp:366-380
+            std::vector<double> d2;
+            for (int i = 0; i < N; ++i)
+                if (P.keep[i]) d2.push_back(depth2[i]);
+            if (!d2.empty()) {
+                auto mid = d2.begin() + d2.size() / 2;
+                std::nth_element(d2.begin(), mid, d2.end());
+                depth = std::sqrt(*mid);
+            }
+        }
+        for (int j = 0; j < n; ++j)
+            if (!measInState[j]) {
+                V3 b = cam_undistort(P.cam, P.my[2 * j], P.my[2 * j + 1]);
+                addP.push_back(b.x * depth);
+                addP.push_back(b.y * depth);
+                addP.push_back(b.z * depth);
+            }
+    }
+    if ((rc = remove_and_append(f, P.keep, addIds, addP, s.initialPointVariance, -1.0)) != EQVIO_OK) return rc;
+    stage_mark(f, 2);
+
+    // measurement restricted to the kept ids (ascending)
+    std::vector<int> kmids;
+    std::vector<double> ky;
+    for (int j = 0; j < n; ++j)
+        if (measKept[j]) {
+            kmids.push_back(P.mids[j]);
+            ky.push_back(P.my[2 * j]);
+            ky.push_back(P.my[2 * j + 1]);
+        }
+    const int nm = (int)kmids.size();
+    if (nm == 0) {  // VIOFilter.cpp:223-224
+        stage_mark(f, 3);
+        return EQVIO_OK;
+    }
+    const int Nn = (int)f->ids.size();
+    std::unordered_map<int, int> spos;
+    spos.reserve(Nn * 2 + 1);
+    for (int i = 0; i < Nn; ++i) spos[f->ids[i]] = i;
+    std::vector<int> lmOf(nm);
+    for (int j = 0; j < nm; ++j) lmOf[j] = spos.at(kmids[j]);
+
+    // performVisionUpdate (VIO_eqf.cpp:105-135) in the symmetric Cholesky form
+    const int m = 2 * nm;
+    const int dimp = dimp_of(Nn);
+    const int Mz = m + dimp + 1;
+    const int ldz = (Mz + 7) & ~7;
+    double* Z = f->d_Z;
+    if ((rc = upload(f, f->d_lmOf, lmOf.data(), nm)) != EQVIO_OK) return rc;
+    if ((rc = upload(f, f->d_y, ky.data(), ky.size())) != EQVIO_OK) return rc;
+    CUDA_TRY(f, cudaMemsetAsync(f->d_status, 0, (1 + (size_t)Nn) * sizeof(int), f->stream));
+    meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, P.cam, s.coordinateChoice,
+                                                      s.useEquivariantOutput ? 1 : 0, f->d_Cblk, Z, ldz, m + dimp);
+    LAUNCH_CHECK(f, "meas_kernel");
+    zbuild_kernel<<<dim3(cdiv(dimp, 256), nm), 256, 0, f->stream>>>(f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, Z, ldz, m);
+    LAUNCH_CHECK(f, "zbuild_kernel");
+    sbuild_kernel<<<dim3(cdiv(m, 128), m), 128, 0, f->stream>>>(f->d_lmOf, f->d_Cblk, Z, ldz, m,
+                                                                s.measurementNoise * s.measurementNoise);
+    LAUNCH_CHECK(f, "sbuild_kernel");
+    for (int k = 0; k < m; k += NB) {
+        const int nbk = std::min(NB, m - k);
+        const int below = Mz - (k + nbk);
+        int pk = prof_begin(f, PROF_PANEL);
+        chol_panel_kernel<<<std::max(1, cdiv(below, PANEL_THREADS)), PANEL_THREADS, 0, f->stream>>>(Z, ldz, Mz, k, nbk,
+                                                                                                     f->d_status, f->d_Lout);
+        prof_end(f, pk);
+        LAUNCH_CHECK(f, "chol_panel_kernel");
+        if (k + nbk < m) {
+            const int o = k + nbk;
+            const int Mr = Mz - o, Nc = m - o;
+            int tk = prof_begin(f, PROF_TRAIL);
+            gemm_nt_sub_kernel<false><<<dim3(cdiv(Nc, GBN), cdiv(Mr, GBM)), 128, 0, f->stream>>>(
+                Z + (size_t)o * ldz + o, ldz, Z + (size_t)k * ldz + o, ldz, Z + (size_t)k * ldz + o, ldz, Mr, Nc, nbk);
+            prof_end(f, tk);
+            LAUNCH_CHECK(f, "gemm_nt_sub_kernel<trail>");
+        }
+    }
+    {
+        int sk = prof_begin(f, PROF_SYRK);
+        gemm_nt_sub_kernel<true><<<dim3(cdiv(dimp, GBN), cdiv(dimp, GBM)), 128, 0, f->stream>>>(f->Sig[f->cur], f->ld, Z + m, ldz,
+                                                                                                Z + m, ldz, dimp, dimp, m);
+        prof_end(f, sk);
+        LAUNCH_CHECK(f, "gemm_nt_sub_kernel<syrk>");
+    }
+    gamma_kernel<<<cdiv(dimp, 128), 128, m * sizeof(double), f->stream>>>(Z, ldz, m, dimp, f->d_Gamma);
+    LAUNCH_CHECK(f, "gamma_kernel");
+    lift_kernel<<<cdiv(std::max(Nn, 1), 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, Nn, f->d_xi0s, f->d_Xs, f->d_Gamma,
+                                                                   s.useDiscreteInnovationLift ? 1 : 0, s.coordinateChoice,
+                                                                   f->d_status, f->d_status + 1);
+    LAUNCH_CHECK(f, "lift_kernel");
+    stage_mark(f, 3);
+    P.nStatus = 1 + Nn;
+    if ((rc = download_async(f, &P.h_status, f->d_status, P.nStatus)) != EQVIO_OK) return rc;
+    P.corrected = true;
+    return EQVIO_OK;
+}
+
+// ---- phase C: wait, check the device status word, drop invalid landmarks ---------------------------
+int vision_phase_c(eqvio_filter* f, int* did_update) {
+    auto& P = f->pend;
+    if (did_update) *did_update = 0;
+    CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+    prof_collect(f);
+    if (f->stageTiming && P.active) {
+        for (int i = 0; i < 3; ++i) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, f->stageEv[i], f->stageEv[i + 1]) == cudaSuccess) f->stageMs[i] = ms;
+        }
+        f->stageMs[1] += f->augMs;
+        f->augMs = 0;
+    }
+    if (!P.active || !P.corrected) {
+        P.active = false;
+        return EQVIO_OK;
+    }
+    P.active = false;
+    const int st = P.h_status[0];
+    if (st & 1) {
+        f->err = "innovation covariance S is not positive definite";
+        return EQVIO_ERR_NUMERIC;
+    }
+    if (st & 2) {
+        f->err = "NaN detected in the correction";
+        return EQVIO_ERR_NUMERIC;
+    }
+    if (did_update) *did_update = 1;
+    if (st & 4) {  // removeInvalidLandmarks, VIO_eqf.cpp:213-223
+        const int Nn = (int)f->ids.size();
+        std::vector<char> keep(Nn, 1);
+        for (int i = 0; i < Nn; ++i)
+            if (P.h_status[1 + i]) keep[i] = 0;
+        int rc = remove_and_append(f, keep, {}, {}, 0.0, -1.0);
+        if (rc != EQVIO_OK) return rc;
+        CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+    }
+    return EQVIO_OK;
+}
+
+int make_filter(const eqvio_settings* s, int device, int capacity, void* stream, eqvio_filter** out) {
+    if (!s || !out || capacity < 0) {
+        g_createError = "invalid arguments";
+        return EQVIO_ERR_INVALID_ARG;
+    }
+    *out = nullptr;
+    if (s->coordinateChoice != EQVIO_COORD_EUCLIDEAN && s->coordinateChoice != EQVIO_COORD_INVDEPTH) {
+        g_createError = "coordinateChoice: only Euclidean and InvDepth have a CUDA path";
+        return EQVIO_ERR_UNSUPPORTED;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_createError = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return EQVIO_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        g_createError = "device index out of range";
+        return EQVIO_ERR_INVALID_ARG;
+    }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        g_createError = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return EQVIO_ERR_CUDA;
+    }
+    eqvio_filter* f = new eqvio_filter();
+    f->st = *s;
+    f->device = device;
+    f->cap = capacity;
+    if (stream) {
+        f->stream = static_cast<cudaStream_t>(stream);
+    } else {
+        e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            g_createError = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+            delete f;
+            return EQVIO_ERR_CUDA;
+        }
+        f->ownStream = true;
+    }
+    int rc = alloc_device(f);
+    if (rc != EQVIO_OK) {
+        g_createError = f->err;
+        eqvio_destroy(f);
+        return rc;
+    }
+    *out = f;
+    return EQVIO_OK;
+}
+
+#define ENTER(f)                                        \
+    if (!(f)) return EQVIO_ERR_INVALID_ARG;             \
+    {                                                   \
+        cudaError_t e_ = cudaSetDevice((f)->device);    \
+        if (e_ != cudaSuccess) {                        \
+            (f)->err = cudaGetErrorString(e_);          \
+            return EQVIO_ERR_CUDA;                      \
+        }                                               \
+    }
+
+}  // namespace
+
+extern "C" {
+
+void eqvio_settings_default(eqvio_settings* s) {  // VIOFilterSettings.h:59-98
+    if (!s) return;
+    s->biasOmegaProcessVariance = s->biasAccelProcessVariance = s->attitudeProcessVariance = s->positionProcessVariance =
+        s->velocityProcessVariance = s->cameraAttitudeProcessVariance = s->cameraPositionProcessVariance =
+            s->pointProcessVariance = 0.001;
+    s->velGyrNoise = 1e-4;
+    s->velAccNoise = 1e-3;
+    s->velGyrBiasWalk = 1e-5;
+    s->velAccBiasWalk = 1e-3;
+    s->measurementNoise = 2.0;
+    s->outlierThresholdAbs = 1e8;
+    s->outlierThresholdProb = 1e8;
+    s->featureRetention = 0.3;
+    s->initialAttitudeVariance = 1.0e-4;
+    s->initialPositionVariance = 1.0e-4;
+    s->initialVelocityVariance = 1.0e-2;
+    s->initialCameraAttitudeVariance = 1.0e-5;
+    s->initialCameraPositionVariance = 1.0e-4;
+    s->initialPointVariance = 1.0;
+    s->initialPointDepthVariance = -1.0;
+    s->initialBiasOmegaVariance = 0.1;
+    s->initialBiasAccelVariance = 0.1;
+    s->initialSceneDepth = 1.0;
+    s->useDiscreteInnovationLift = 1;
+    s->useDiscreteVelocityLift = 1;
+    s->useDiscreteStateMatrix = 0;
+    s->fastRiccati = 0;
+    s->useMedianDepth = 1;
+    s->useFeaturePredictions = 0;
+    s->useEquivariantOutput = 1;
+    s->removeLostLandmarks = 1;
+    s->coordinateChoice = EQVIO_COORD_EUCLIDEAN;
+    s->cameraOffset[0] = 1.0;
+    for (int i = 1; i < 7; ++i) s->cameraOffset[i] = 0.0;
+}
+
+// StandardCamera::computeInverseDistortion (StandardCamera.cpp:113-145): least-squares fit of five
+// inverse coefficients on a grid of normalised points, solved by Householder QR.
+int eqvio_camera_fit_inverse_distortion(eqvio_camera* cam) {
+    if (!cam) return EQVIO_ERR_INVALID_ARG;
+    int w = cam->width, h = cam->height;
+    if ((long long)w * h == 0) {
+        w = (int)std::lround(cam->cx * 2);
+        h = (int)std::lround(cam->cy * 2);
+    }
+    const int maxPoints = 30;
+    const int sx = w / maxPoints, sy = h / maxPoints;
+    if (sx <= 0 || sy <= 0) return EQVIO_ERR_INVALID_ARG;
+    std::vector<double> A, b;  // row-major rows x 5
+    for (int x = 0; x < w; x += sx)
+        for (int y = 0; y < h; y += sy) {
+            const double nx = (x - cam->cx) / cam->fx, ny = (y - cam->cy) / cam->fy;
+            double px, py;
+            distort_homogeneous(nx, ny, cam->dist, cam->ndist, px, py);
+            const double r2 = px * px + py * py;
+            const double r0[5] = {px * r2, px * r2 * r2, 2 * px * py, r2 + 2 * px * px, px * r2 * r2 * r2};
+            const double r1[5] = {py * r2, py * r2 * r2, r2 + 2 * py * py, 2 * px * py, py * r2 * r2 * r2};
+            A.insert(A.end(), r0, r0 + 5);
+            A.insert(A.end(), r1, r1 + 5);
+            b.push_back(nx - px);
+            b.push_back(ny - py);
+        }
+    const int rows = (int)b.size();
+    if (rows < 5) return EQVIO_ERR_INVALID_ARG;
+    // Householder QR with column pivoting on [A | b]
+    int perm[5] = {0, 1, 2, 3, 4};
+    for (int k = 0; k < 5; ++k) {
+        int best = k;
+        double bestN = -1;
+        for (int c = k; c < 5; ++c) {
+            double s = 0;
+            for (int r = k; r < rows; ++r) s += A[r * 5 + c] * A[r * 5 + c];
+            if (s > bestN) {
+                bestN = s;
+                best = c;
+            }
+        }
+        if (best != k) {
+            for (int r = 0; r < rows; ++r) std::swap(A[r * 5 + k], A[r * 5 + best]);
+            std::swap(perm[k], perm[best]);
+        }
+        double nrm = std::sqrt(bestN);
+        if (nrm == 0) continue;
+        const double alpha = A[k * 5 + k] > 0 ? -nrm : nrm;
+        std::vector<double> v(rows - k);
+        for (int r = k; r < rows; ++r) v[r - k] = A[r * 5 + k];
+        v[0] -= alpha;
+        double vn = 0;
+        for (double t : v) vn += t * t;
+        if (vn == 0) continue;
+        for (int c = k; c < 5; ++c) {
+            double d = 0;
+            for (int r = k; r < rows; ++r) d += v[r - k] * A[r * 5 + c];
+            d = 2 * d / vn;
+            for (int r = k; r < rows; ++r) A[r * 5 + c] -= d * v[r - k];
+        }
+        double d = 0;
+        for (int r = k; r < rows; ++r) d += v[r - k] * b[r];
+        d = 2 * d / vn;
+        for (int r = k; r < rows; ++r) b[r] -= d * v[r - k];
+    }
+    double xs[5] = {0, 0, 0, 0, 0};
+    for (int k = 4; k >= 0; --k) {
+        double s = b[k];
+        for (int c = k + 1; c < 5; ++c) s -= A[k * 5 + c] * xs[c];
+        xs[k] = (A[k * 5 + k] != 0) ? s / A[k * 5 + k] : 0.0;
+    }
+    for (int k = 0; k < 5; ++k) cam->inv_dist[perm[k]] = xs[k];
+    return EQVIO_OK;
+}
+
+int eqvio_create(const eqvio_settings* s, int device, int capacity, void* stream_or_null, eqvio_filter** out) {
+    int rc = make_filter(s, device, capacity, stream_or_null, out);
+    if (rc != EQVIO_OK) return rc;
+    eqvio_filter* f = *out;
+    double sensor[23];
+    for (int i = 0; i < 23; ++i) sensor[i] = 0.0;
+    sensor[6] = 1.0;  // identity pose
+    for (int i = 0; i < 7; ++i) sensor[16 + i] = s->cameraOffset[i];
+    std::vector<double> diag;
+    initial_diag(f->st, 0, true, diag);
+    rc = reset_state(f, sensor, 0, nullptr, nullptr, diag);
+    if (rc != EQVIO_OK) {
+        g_createError = f->err;
+        eqvio_destroy(f);
+        *out = nullptr;
+        return rc;
+    }
+    f->time = -1.0;
+    f->initialised = false;
+    return EQVIO_OK;
+}
+
+int eqvio_create_from_state(const eqvio_settings* s, int device, int capacity, void* stream_or_null, const double sensor[23],
+                            int n, const int* ids, const double* p, double time, eqvio_filter** out) {
+    if (!sensor || n < 0 || (n > 0 && (!ids || !p))) {
+        g_createError = "invalid arguments";
+        return EQVIO_ERR_INVALID_ARG;
+    }
+    if (n > capacity) {
+        g_createError = "initial landmark count exceeds capacity";
+        return EQVIO_ERR_CAPACITY;
+    }
+    int rc = make_filter(s, device, capacity, stream_or_null, out);
+    if (rc != EQVIO_OK) return rc;
+    eqvio_filter* f = *out;
+    std::vector<double> diag;
+    initial_diag(f->st, n, true, diag);
+    rc = reset_state(f, sensor, n, ids, p, diag);
+    if (rc != EQVIO_OK) {
+        g_createError = f->err;
+        eqvio_destroy(f);
+        *out = nullptr;
+        return rc;
+    }
+    f->time = time;
+    f->initialised = true;
+    return EQVIO_OK;
+}
+
+void eqvio_destroy(eqvio_filter* f) {
+    if (!f) return;
+    cudaSetDevice(f->device);
+    if (f->stream) cudaStreamSynchronize(f->stream);
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(f->Sig[k]);
+        cudaFree(f->lm[k]);
+        cudaFree(f->dids[k]);
+    }
+    cudaFree(f->d_xi0s);
+    cudaFree(f->d_Xs);
+    cudaFree(f->d_ctx);
+    cudaFree(f->d_steps);
+    cudaFree(f->d_imu);
+    cudaFree(f->d_rows);
+    cudaFree(f->d_uv);
+    cudaFree(f->d_Z);
+    cudaFree(f->d_Lout);
+    cudaFree(f->d_Cblk);
+    cudaFree(f->d_Gamma);
+    cudaFree(f->d_gate);
+    cudaFree(f->d_y);
+    cudaFree(f->d_newP);
+    cudaFree(f->d_out);
+    cudaFree(f->d_measIdx);
+    cudaFree(f->d_lmOf);
+    cudaFree(f->d_map);
+    cudaFree(f->d_newIds);
+    cudaFree(f->d_status);
+    for (auto& a : f->arenas) cudaFreeHost(a.first);
+    for (auto& p : f->evPool) {
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    for (int i = 0; i < 4; ++i)
+        if (f->stageEv[i]) cudaEventDestroy(f->stageEv[i]);
+    if (f->ownStream && f->stream) cudaStreamDestroy(f->stream);
+    delete f;
+}
+
+const char* eqvio_last_error(const eqvio_filter* f) { return f ? f->err.c_str() : g_createError.c_str(); }
+
+int eqvio_initialise_from_imu(eqvio_filter* f, double stamp, const double gyr[3], const double acc[3]) {
+    ENTER(f);
+    (void)gyr;
+    if (!acc) return EQVIO_ERR_INVALID_ARG;
+    stage_reset(f);
+    for (int i = 0; i < 6; ++i) f->xi0s[i] = 0.0;
+    Quat q = quat_from_two_vectors(normalized(V3{acc[0], acc[1], acc[2]}), V3{0, 0, 1});
+    f->xi0s[6] = q.w;
+    f->xi0s[7] = q.x;
+    f->xi0s[8] = q.y;
+    f->xi0s[9] = q.z;
+    for (int i = 10; i < 16; ++i) f->xi0s[i] = 0.0;
+    int rc = upload(f, f->d_xi0s, f->xi0s, 23);
+    if (rc != EQVIO_OK) return rc;
+    CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+    f->initialised = true;
+    f->time = stamp;
+    return EQVIO_OK;
+}
+
+int eqvio_set_state(eqvio_filter* f, const double sensor[23], int n, const int* ids, const double* p) {
+    ENTER(f);
+    if (!sensor || n < 0 || (n > 0 && (!ids || !p))) return EQVIO_ERR_INVALID_ARG;
+    stage_reset(f);
+    std::vector<double> diag;
+    initial_diag(f->st, n, false, diag);
+    int rc = reset_state(f, sensor, n, ids, p, diag);
+    if (rc != EQVIO_OK) return rc;
+    f->initialised = true;
+    return EQVIO_OK;
+}
+
+int eqvio_set_landmarks(eqvio_filter* f, int n, const int* ids, const double* p) {
+    ENTER(f);
+    if (n < 0 || (n > 0 && (!ids || !p))) return EQVIO_ERR_INVALID_ARG;
+    if (n != (int)f->ids.size()) {
+        // the reference overwrites a block of an unresized Sigma (VIOFilter.cpp:94-101); any other
+        // count leaves its state inconsistent, so it is rejected here
+        f->err = "set_landmarks: count must equal the current number of landmarks";
+        return EQVIO_ERR_INVALID_ARG;
+    }
+    stage_reset(f);
+    if (n == 0) return EQVIO_OK;
+    std::vector<double> soa((size_t)3 * n);
+    for (int i = 0; i < n; ++i) {
+        soa[i] = p[3 * i];
+        soa[n + i] = p[3 * i + 1];
+        soa[2 * n + i] = p[3 * i + 2];
+    }
+    double* h = static_cast<double*>(stage_alloc(f, (size_t)LM_FIELDS * n * sizeof(double)));
+    if (!h) return EQVIO_ERR_CUDA;
+    std::memcpy(h, soa.data(), soa.size() * sizeof(double));
+    for (int i = 0; i < n; ++i) {
+        h[F_QW * n + i] = 1.0;
+        h[F_QX * n + i] = 0.0;
+        h[F_QY * n + i] = 0.0;
+        h[F_QZ * n + i] = 0.0;
+        h[F_QA * n + i] = 1.0;
+    }
+    for (int fld = 0; fld < LM_FIELDS; ++fld)
+        CUDA_TRY(f, cudaMemcpyAsync(f->lm[f->lmcur] + (size_t)fld * f->cap, h + (size_t)fld * n, n * sizeof(double),
+                                    cudaMemcpyHostToDevice, f->stream));
+    int rc = upload(f, f->dids[f->lmcur], ids, n);
+    if (rc != EQVIO_OK) return rc;
+    f->ids.assign(ids, ids + n);
+    fill_ll_diag_kernel<<<dim3(cdiv(3 * n, 128), 3 * n), 128, 0, f->stream>>>(f->Sig[f->cur], f->ld, 3 * n, f->st.initialPointVariance,
+                                                                              f->st.initialPointDepthVariance);
+    LAUNCH_CHECK(f, "fill_ll_diag_kernel");
+    CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+    return EQVIO_OK;
+}
+
+int eqvio_augment_landmark_states(eqvio_filter* f, int n_new, const int* new_ids, int n_provided, const int* provided_ids,
+                                  const double* provided_p) {
+    ENTER(f);
+    if (n_new < 0 || n_provided < 0 || (n_new > 0 && !new_ids) || (n_provided > 0 && (!provided_ids || !provided_p)))
+        return EQVIO_ERR_INVALID_ARG;
+    stage_reset(f);
+    const int N = (int)f->ids.size();
+    std::unordered_map<int, int> want, prov, have;
+    for (int j = 0; j < n_new; ++j) want.emplace(new_ids[j], j);
+    for (int j = 0; j < n_provided; ++j) prov.emplace(provided_ids[j], j);
+    std::vector<char> keep(N, 1);
+    for (int i = 0; i < N; ++i) {
+        if (!want.count(f->ids[i])) keep[i] = 0;
+        have.emplace(f->ids[i], i);
+    }
+    std::vector<int> addIds;
+    std::vector<double> addP;
+    for (int j = 0; j < n_new; ++j) {
+        if (have.count(new_ids[j])) continue;
+        auto it = prov.find(new_ids[j]);
+        if (it == prov.end()) {
+            f->err = "augment_landmark_states: a new id is missing from the provided state";
+            return EQVIO_ERR_INVALID_ARG;
+        }
+        have.emplace(new_ids[j], -1);
+        addIds.push_back(new_ids[j]);
+        for (int a = 0; a < 3; ++a) addP.push_back(provided_p[3 * it->second + a]);
+    }
+    stage_mark(f, 0);
+    int rc = remove_and_append(f, keep, addIds, addP, f->st.initialPointVariance, -1.0);
+    if (rc != EQVIO_OK) return rc;
+    stage_mark(f, 1);
+    CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+    if (f->stageTiming) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, f->stageEv[0], f->stageEv[1]) == cudaSuccess) f->augMs += ms;
+    }
+    return EQVIO_OK;
+}
+
+int eqvio_process_imu(eqvio_filter* f, double stamp, const double gyr[3], const double acc[3], const double gyr_bias_vel[3],
+                      const double acc_bias_vel[3]) {
+    ENTER(f);
+    if (!gyr || !acc) return EQVIO_ERR_INVALID_ARG;
+    if (!f->initialised) {
+        int rc = eqvio_initialise_from_imu(f, stamp, gyr, acc);
+        if (rc != EQVIO_OK) return rc;
+    }
+    ImuSample u;
+    u.stamp = stamp;
+    for (int i = 0; i < 3; ++i) {
+        u.v[i] = gyr[i];
+        u.v[3 + i] = acc[i];
+        u.v[6 + i] = gyr_bias_vel ? gyr_bias_vel[i] : 0.0;
+        u.v[9 + i] = acc_bias_vel ? acc_bias_vel[i] : 0.0;
+    }
+    f->buf.push_back(u);
+    return EQVIO_OK;
+}
+
+int eqvio_process_vision(eqvio_filter* f, double stamp, int n, const int* ids, const double* y, const eqvio_camera* cam,
+                         int* did_update) {
+    ENTER(f);
+    if (did_update) *did_update = 0;
+    int rc = vision_phase_a(f, stamp, n, ids, y, cam);
+    if (rc == EQVIO_OK) rc = vision_phase_b(f);
+    int rc2 = vision_phase_c(f, did_update);
+    return rc != EQVIO_OK ? rc : rc2;
+}
+
+int eqvio_batch_process_vision(eqvio_filter* const* fs, int count, const double* stamps, const int* n, const int* const* ids,
+                               const double* const* y, const eqvio_camera* cam, int* did_update) {
+    if (!fs || count < 0 || !stamps || !n || !ids || !y || !cam) return EQVIO_ERR_INVALID_ARG;
+    int worst = EQVIO_OK;
+    std::vector<int> rc(count, EQVIO_OK);
+    for (int k = 0; k < count; ++k) {
+        if (!fs[k]) return EQVIO_ERR_INVALID_ARG;
+        if (cudaSetDevice(fs[k]->device) != cudaSuccess) return EQVIO_ERR_CUDA;
+        rc[k] = vision_phase_a(fs[k], stamps[k], n[k], ids[k], y[k], cam);
+    }
+    for (int k = 0; k < count; ++k) {
+        cudaSetDevice(fs[k]->device);
+        if (rc[k] == EQVIO_OK) rc[k] = vision_phase_b(fs[k]);
+    }
+    for (int k = 0; k < count; ++k) {
+        cudaSetDevice(fs[k]->device);
+        int d = 0;
+        int r2 = vision_phase_c(fs[k], &d);
+        if (rc[k] == EQVIO_OK) rc[k] = r2;
+        if (did_update) did_update[k] = (rc[k] == EQVIO_OK) ? d : 0;
+        if (rc[k] != EQVIO_OK && worst == EQVIO_OK) worst = rc[k];
+    }
+    return worst;
+}
+
+double eqvio_get_time(const eqvio_filter* f) { return f ? f->time : -1.0; }
+int eqvio_is_initialised(const eqvio_filter* f) { return f && f->initialised ? 1 : 0; }
+int eqvio_num_landmarks(const eqvio_filter* f) { return f ? (int)f->ids.size() : 0; }
+int eqvio_state_dim(const eqvio_filter* f) { return f ? SENSOR_DIM + 3 * (int)f->ids.size() : 0; }
+int eqvio_capacity(const eqvio_filter* f) { return f ? f->cap : 0; }
+
+int eqvio_get_state_estimate(eqvio_filter* f, double sensor[23], int* ids, double* p, int* n_out) {
+    ENTER(f);
+    stage_reset(f);
+    const int N = (int)f->ids.size();
+    state_estimate_kernel<<<cdiv(std::max(N, 1), 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_xi0s, f->d_Xs, f->d_out);
+    LAUNCH_CHECK(f, "state_estimate_kernel");
+    double* h = nullptr;
+    int rc = download_async(f, &h, f->d_out, 23 + 3 * (size_t)N);
+    if (rc != EQVIO_OK) return rc;
+    CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+    if (sensor) std::memcpy(sensor, h, 23 * sizeof(double));
+    if (ids && N) std::memcpy(ids, f->ids.data(), N * sizeof(int));
+    if (p && N) std::memcpy(p, h + 23, 3 * (size_t)N * sizeof(double));
+    if (n_out) *n_out = N;
+    return EQVIO_OK;
+}
+
+int eqvio_get_eqf_state(eqvio_filter* f, double xi0_sensor[23], int* ids, double* xi0_p, double X_group[23], double* X_Q,
+                        double* Sigma, int ld) {
+    ENTER(f);
+    stage_reset(f);
+    const int N = (int)f->ids.size();
+    const int dim = SENSOR_DIM + 3 * N;
+    if (xi0_sensor) std::memcpy(xi0_sensor, f->xi0s, 23 * sizeof(double));
+    if (ids && N) std::memcpy(ids, f->ids.data(), N * sizeof(int));
+    int rc;
+    double *hX = nullptr, *hlm = nullptr;
+    if ((rc = download_async(f, &hX, f->d_Xs, 23)) != EQVIO_OK) return rc;
+    if (N > 0 && (xi0_p || X_Q)) {
+        hlm = static_cast<double*>(stage_alloc(f, (size_t)LM_FIELDS * N * sizeof(double)));
+        if (!hlm) return EQVIO_ERR_CUDA;
+        for (int fld = 0; fld < LM_FIELDS; ++fld)
+            CUDA_TRY(f, cudaMemcpyAsync(hlm + (size_t)fld * N, f->lm[f->lmcur] + (size_t)fld * f->cap, N * sizeof(double),
+                                        cudaMemcpyDeviceToHost, f->stream));
+    }
+    if (Sigma) {
+        if (ld < dim) {
+            f->err = "get_eqf_state: ld < dim";
+            return EQVIO_ERR_INVALID_ARG;
+        }
+        pack_sigma_kernel<<<dim3(cdiv(dim, 128), dim), 128, 0, f->stream>>>(f->Sig[f->cur], f->ld, dim, f->d_Z, dim);
+        LAUNCH_CHECK(f, "pack_sigma_kernel");
+        CUDA_TRY(f, cudaMemcpy2DAsync(Sigma, (size_t)ld * sizeof(double), f->d_Z, (size_t)dim * sizeof(double),
+                                      (size_t)dim * sizeof(double), dim, cudaMemcpyDeviceToHost, f->stream));
+    }
+    CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+    if (X_group) std::memcpy(X_group, hX, 23 * sizeof(double));
+    if (hlm) {
+        for (int i = 0; i < N; ++i) {
+            if (xi0_p) {
+                xi0_p[3 * i] = hlm[F_Q0X * N + i];
+                xi0_p[3 * i + 1] = hlm[F_Q0Y * N + i];
+                xi0_p[3 * i + 2] = hlm[F_Q0Z * N + i];
+            }
+            if (X_Q) {
+                X_Q[5 * i] = hlm[F_QW * N + i];
+                X_Q[5 * i + 1] = hlm[F_QX * N + i];
+                X_Q[5 * i + 2] = hlm[F_QY * N + i];
+                X_Q[5 * i + 3] = hlm[F_QZ * N + i];
+                X_Q[5 * i + 4] = hlm[F_QA * N + i];
+            }
+        }
+    }
+    return EQVIO_OK;
+}
+
+int eqvio_get_landmark_cov_blocks(eqvio_filter* f, double* blocks) {
+    ENTER(f);
+    stage_reset(f);
+    const int N = (int)f->ids.size();
+    if (N == 0) return EQVIO_OK;
+    if (!blocks) return EQVIO_ERR_INVALID_ARG;
+    cov_blocks_kernel<<<cdiv(N, 128), 128, 0, f->stream>>>(f->Sig[f->cur], f->ld, N, f->d_Z);
+    LAUNCH_CHECK(f, "cov_blocks_kernel");
+    double* h = nullptr;
+    int rc = download_async(f, &h, f->d_Z, 9 * (size_t)N);
+    if (rc != EQVIO_OK) return rc;
+    CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+    std::memcpy(blocks, h, 9 * (size_t)N * sizeof(double));
+    return EQVIO_OK;
+}
+
+int eqvio_get_feature_predictions(eqvio_filter* f, const eqvio_camera* cam, double stamp, int* ids, double* y, int* n_out) {
+    ENTER(f);
+    (void)cam;
+    (void)stamp;
+    (void)ids;
+    (void)y;
+    if (n_out) *n_out = 0;
+    if (f->st.useFeaturePredictions) {
+        f->err = "useFeaturePredictions (VIO_eqf::predictState) has no CUDA path in this build";
+        return EQVIO_ERR_UNSUPPORTED;
+    }
+    return EQVIO_OK;  // VIOFilter.cpp:247-252: an empty measurement
+}
+
+int eqvio_get_last_outliers(const eqvio_filter* f, int* ids, int cap, int* n_out) {
+    if (!f) return EQVIO_ERR_INVALID_ARG;
+    const int k = (int)f->lastOutliers.size();
+    if (n_out) *n_out = k;
+    if (ids)
+        for (int i = 0; i < std::min(k, cap); ++i) ids[i] = f->lastOutliers[i];
+    return EQVIO_OK;
+}
+
+int eqvio_get_stage_ms(eqvio_filter* f, double ms[3]) {
+    if (!f || !ms) return EQVIO_ERR_INVALID_ARG;
+    for (int i = 0; i < 3; ++i) ms[i] = f->stageMs[i];
+    return EQVIO_OK;
+}
+int eqvio_enable_stage_timing(eqvio_filter* f, int on) {
+    if (!f) return EQVIO_ERR_INVALID_ARG;
+    f->stageTiming = on != 0;
+    return EQVIO_OK;
+}
+long long eqvio_get_launch_count(const eqvio_filter* f) { return f ? f->launches : 0; }
+
+int eqvio_enable_kernel_profile(eqvio_filter* f, int on) {
+    if (!f) return EQVIO_ERR_INVALID_ARG;
+    f->profiling = on != 0;
+    return EQVIO_OK;
+}
+int eqvio_get_kernel_profile(eqvio_filter* f, int reset, double ms[EQVIO_PROF_CLASSES], long long launches[EQVIO_PROF_CLASSES]) {
+    if (!f) return EQVIO_ERR_INVALID_ARG;
+    for (int i = 0; i < PROF_CLASSES; ++i) {
+        if (ms) ms[i] = f->profMs[i];
+        if (launches) launches[i] = f->profLaunches[i];
+        if (reset) {
+            f->profMs[i] = 0;
+            f->profLaunches[i] = 0;
+        }
+    }
+    return EQVIO_OK;
+}
+
+const char* eqvio_build_info(void) { return "eqvio_b200 sm_100a fp64 (CUDA " EQVIO_STR(__CUDACC_VER_MAJOR__) "." EQVIO_STR(__CUDACC_VER_MINOR__) ")"; }
+
+}  // extern "C"

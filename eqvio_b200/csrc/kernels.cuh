@@ -1,0 +1,922 @@
+// CUDA kernels of the EqF vision-update path (sm_100a).  fp64 throughout.
+//
+// Data layout in HBM (one filter):
+//   Sigma   : two ldS x ldS column-major buffers (ping-pong).  Internal row/col index of
+//             state component r:  r < 21 -> r ; landmark i component a -> SOFF + 3 i + a
+//             (SOFF = 24: the 21-wide sensor block is padded to 24 so that landmark rows
+//             start 64-byte aligned; pad rows/cols are kept zero).
+//   lm      : SoA landmark arrays, 8 fields x cap doubles: q0x q0y q0z | Qw Qx Qy Qz | Qa
+//   ids     : cap ints (state order)
+//   Z       : (m + dimp + 1) x m column-major work matrix of the correction,
+//             rows [0,m) = S, rows [m, m+dimp) = W^T = Sigma C^T, row m+dimp = ytilde^T.
+//             A blocked right-looking Cholesky sweep over its m columns leaves
+//             L (lower), Y^T = W^T L^-T and (L^-1 ytilde)^T in place, i.e. the partial
+//             Cholesky of [[S, W],[W^T, Sigma]] whose Schur complement is the updated Sigma.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "model.cuh"
+
+namespace eqvio {
+
+// landmark SoA field offsets (units of cap)
+enum { F_Q0X = 0, F_Q0Y, F_Q0Z, F_QW, F_QX, F_QY, F_QZ, F_QA, LM_FIELDS };
+
+__device__ __constant__ int c_sidx[12] = {0, 1, 2, 12, 13, 14, 15, 16, 17, 18, 19, 20};
+
+struct RiccatiCtx {
+    double Fs[21 * 21];   // I + dt * A_s (row-major)
+    double Ns[21 * 21];   // dt * (B_s Q B_s^T + P_s)
+    double BsG[21 * 3];   // dt * q_gyr * B_s[:, 0:3]
+    double RICt_RAt[9];   // R_IC^T R_Ahat^T                         (euclid.cpp:133-138)
+    double RT_IC[9];      // xi_hat.cameraOffset.R.inverse()         (euclid.cpp:221)
+    double common[36];    // Ad_{B^-1} ad(Ad_{T0^-1} Ad_A U_I)       (euclid.cpp:141-147)
+    double vC[3];         // linear part of Ad_{T_hat^-1} U_I        (euclid.cpp:150-151)
+    double xIC[3];        // xi_hat.cameraOffset.x
+    double dt, cg, plDiag;  // step, dt*velGyrNoise^2, dt*pointProcessVariance
+};
+
+struct ObsStep {  // one IMU segment of integrateObserverState, sensor part already resolved
+    int discrete;
+    double dt;
+    SE3 camChangeInv;  // T_hat^-1 A_Lambda^-1 T_hat              (VIOGroup.cpp:259)
+    V3 omegaC, vC;     // U_C of the continuous lift               (VIOGroup.cpp:211-220)
+};
+
+struct PrepArgs {
+    const double* xi0s;  // 23
+    double* Xs;          // 23, updated in place
+    RiccatiCtx* ctx;
+    ObsStep* steps;
+    const double* imu;  // nsteps x 13: dt, gyr3, acc3, gyrBiasVel3, accBiasVel3
+    int nsteps;
+    double meanImu[12];
+    double dtTotal;
+    int doRiccati, discreteLift;
+    double qdiag[4];  // gyr^2, acc^2, gyrBias^2, accBias^2       (VIOFilterSettings.h:192-201)
+    double pdiag[8];  // process variances per 3-block + point     (VIOFilterSettings.h:176-190)
+};
+
+// ------------------------------------------------------------------------------------------------
+// K1: sensor-sized preparation, one thread.  Builds the sensor blocks of A and B for the Riccati
+// step (euclid.cpp:99-160,186-233; identical for invdepth) from X *before* the observer
+// integration, then runs the sensor part of integrateObserverState for every IMU segment
+// (VIO_eqf.cpp:47-60, VIOGroup.cpp:190-271) and records what the landmark kernel needs.
+// ------------------------------------------------------------------------------------------------
+__global__ void sensor_prep_kernel(PrepArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    SensorState xi0 = unpack_sensor(a.xi0s);
+    GroupSensor X = unpack_group(a.Xs);
+
+    if (a.doRiccati) {
+        RiccatiCtx& c = *a.ctx;
+        const double dt = a.dtTotal;
+        SensorState xh = sensor_group_action(X, xi0);
+        double As[21 * 21], Bs[21 * 12];
+        for (int i = 0; i < 21 * 21; ++i) As[i] = 0;
+        for (int i = 0; i < 21 * 12; ++i) Bs[i] = 0;
+        // B sensor rows (euclid.cpp:206-218)
+        for (int i = 0; i < 6; ++i) Bs[i * 12 + 6 + i] = 1.0;
+        M3 RA = qmat(X.A.q);
+        M3 xRA = skew(X.A.x) * RA;
+        M3 RAv = RA * skew(xh.vel);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                Bs[(6 + i) * 12 + j] = RA(i, j);
+                Bs[(9 + i) * 12 + j] = xRA(i, j);
+                Bs[(12 + i) * 12 + j] = RAv(i, j);
+                Bs[(12 + i) * 12 + 3 + j] = RA(i, j);
+            }
+        // A sensor block (euclid.cpp:111-131)
+        for (int i = 0; i < 21; ++i)
+            for (int j = 0; j < 6; ++j) As[i * 21 + j] = -Bs[i * 12 + j];
+        for (int i = 0; i < 3; ++i) As[(9 + i) * 21 + 12 + i] = 1.0;
+        V3 gdir = qrot(qinv(xi0.pose.q), V3{0, 0, 1});
+        M3 gsk = (-GRAVITY_CONSTANT) * skew(gdir);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) As[(12 + i) * 21 + 6 + j] = gsk(i, j);
+        double UI[6] = {a.meanImu[0] - xh.bias[0], a.meanImu[1] - xh.bias[1], a.meanImu[2] - xh.bias[2],
+                        xh.vel.x, xh.vel.y, xh.vel.z};
+        double AdT0inv[36], AdA[36], t1[6], t2[6], adT[36];
+        se3_Adjoint(se3_inv(xi0.cam), AdT0inv);
+        se3_Adjoint(X.A, AdA);
+        mat6_vec(AdA, UI, t1);
+        mat6_vec(AdT0inv, t1, t2);
+        se3_adjoint(t2, adT);
+        for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j) As[(15 + i) * 21 + 15 + j] = adT[6 * i + j];
+        // landmark-row context
+        double AdBinv[36];
+        se3_Adjoint(se3_inv(X.B), AdBinv);
+        mat6_mul(AdBinv, adT, c.common);
+        M3 RIC = qmat(xh.cam.q);
+        M3 t = transpose(RIC) * transpose(RA);
+        M3 RTIC = qmat(qinv(xh.cam.q));
+        for (int i = 0; i < 9; ++i) {
+            c.RICt_RAt[i] = t.m[i];
+            c.RT_IC[i] = RTIC.m[i];
+        }
+        double AdThinv[36], UC[6];
+        se3_Adjoint(se3_inv(xh.cam), AdThinv);
+        mat6_vec(AdThinv, UI, UC);
+        c.vC[0] = UC[3]; c.vC[1] = UC[4]; c.vC[2] = UC[5];
+        c.xIC[0] = xh.cam.x.x; c.xIC[1] = xh.cam.x.y; c.xIC[2] = xh.cam.x.z;
+        c.dt = dt;
+        c.cg = dt * a.qdiag[0];
+        c.plDiag = dt * a.pdiag[7];
+        for (int i = 0; i < 21; ++i)
+            for (int j = 0; j < 21; ++j) c.Fs[i * 21 + j] = (i == j ? 1.0 : 0.0) + dt * As[i * 21 + j];
+        for (int i = 0; i < 21; ++i)
+            for (int j = 0; j < 21; ++j) {
+                double s = 0;
+                for (int k = 0; k < 12; ++k) s += Bs[i * 12 + k] * a.qdiag[k / 3] * Bs[j * 12 + k];
+                if (i == j) s += a.pdiag[i / 3];
+                c.Ns[i * 21 + j] = dt * s;
+            }
+        for (int i = 0; i < 21; ++i)
+            for (int j = 0; j < 3; ++j) c.BsG[i * 3 + j] = c.cg * Bs[i * 12 + j];
+    }
+
+    // observer integration, sensor part
+    for (int s = 0; s < a.nsteps; ++s) {
+        const double* u = a.imu + 13 * s;
+        const double dt = u[0];
+        SensorState xh = sensor_group_action(X, xi0);
+        V3 gyr = V3{u[1] - xh.bias[0], u[2] - xh.bias[1], u[3] - xh.bias[2]};
+        V3 acc = V3{u[4] - xh.bias[3], u[5] - xh.bias[4], u[6] - xh.bias[5]};
+        V3 gdir = qrot(qinv(xh.pose.q), V3{0, 0, 1});
+        GroupSensor L;
+        ObsStep st;
+        st.discrete = a.discreteLift;
+        st.dt = dt;
+        if (a.discreteLift) {  // VIOGroup.cpp:229-257
+            for (int i = 0; i < 6; ++i) L.beta[i] = dt * u[7 + i];
+            L.A.q = so3_exp(dt * gyr);
+            V3 x = dt * qrot(xh.pose.q, xh.vel) +
+                   (0.5 * dt * dt) * (qrot(xh.pose.q, acc) + V3{0, 0, -GRAVITY_CONSTANT});
+            L.A.x = qrot(qinv(xh.pose.q), x);
+            L.B = se3_mul(se3_mul(se3_inv(xh.cam), L.A), xh.cam);
+            V3 bvd = acc - GRAVITY_CONSTANT * gdir;
+            L.w = xh.vel - (xh.vel + dt * bvd);
+            st.camChangeInv = se3_mul(se3_mul(se3_inv(xh.cam), se3_inv(L.A)), xh.cam);
+            st.omegaC = V3{0, 0, 0};
+            st.vC = V3{0, 0, 0};
+        } else {  // VIOGroup.cpp:190-227 then VIOExp(dt * lambda) :273-290
+            double UA[6] = {gyr.x, gyr.y, gyr.z, xh.vel.x, xh.vel.y, xh.vel.z};
+            double AdTinv[36], UB[6];
+            se3_Adjoint(se3_inv(xh.cam), AdTinv);
+            mat6_vec(AdTinv, UA, UB);
+            V3 uw = -acc + GRAVITY_CONSTANT * gdir;
+            for (int i = 0; i < 6; ++i) L.beta[i] = dt * u[7 + i];
+            se23_exp(dt * gyr, dt * xh.vel, dt * uw, L.A.q, L.A.x, L.w);
+            L.B = se3_exp(dt * V3{UB[0], UB[1], UB[2]}, dt * V3{UB[3], UB[4], UB[5]});
+            st.omegaC = V3{UB[0], UB[1], UB[2]};
+            st.vC = V3{UB[3], UB[4], UB[5]};
+            st.camChangeInv = se3_identity();
+        }
+        a.steps[s] = st;
+        // X <- X * Lambda (VIOGroup.cpp:71-92)
+        GroupSensor Xn;
+        for (int i = 0; i < 6; ++i) Xn.beta[i] = X.beta[i] + L.beta[i];
+        Xn.A = se3_mul(X.A, L.A);
+        Xn.B = se3_mul(X.B, L.B);
+        Xn.w = X.w + qrot(X.A.q, L.w);
+        X = Xn;
+    }
+    if (a.nsteps > 0) pack_group(X, a.Xs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: one thread per landmark.  (a) landmark rows of A and B (euclid.cpp:133-155,219-228;
+// invdepth.cpp:83-118,170-178) condensed to D_i = I + dt A_qi (3x3), G_i = dt [ -B_l | A_vel | A_cam ]
+// (3x12, columns c_sidx) and Bl_i (3x3); (b) the landmark part of every buffered IMU segment
+// (VIOGroup.cpp:258-269 / :211-220), Q_i <- Q_i * Lambda_Qi.
+// rows[i] = D(9) | G(36) | Bl(9), row-major.
+// ------------------------------------------------------------------------------------------------
+constexpr int ROWS_STRIDE = 54;
+
+__global__ void landmark_propagate_kernel(double* __restrict__ lm, int cap, int N, const RiccatiCtx* __restrict__ ctx,
+                                          const ObsStep* __restrict__ steps, int nsteps, int doRiccati, int coord,
+                                          double* __restrict__ rows) {
+    extern __shared__ unsigned char smem_raw[];
+    ObsStep* s_steps = reinterpret_cast<ObsStep*>(smem_raw);
+    for (int i = threadIdx.x; i < nsteps * (int)(sizeof(ObsStep) / 8); i += blockDim.x)
+        reinterpret_cast<double*>(s_steps)[i] = reinterpret_cast<const double*>(steps)[i];
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
+    Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
+    double a = lm[F_QA * cap + i];
+
+    if (doRiccati) {
+        const double dt = ctx->dt;
+        M3 RQ = qmat(Q);
+        M3 Qhat = a * RQ;
+        V3 qh = landmark_action(Q, a, q0);
+        M3 T, RTIC;
+        for (int k = 0; k < 9; ++k) {
+            T.m[k] = ctx->RICt_RAt[k];
+            RTIC.m[k] = ctx->RT_IC[k];
+        }
+        V3 vC = V3{ctx->vC[0], ctx->vC[1], ctx->vC[2]};
+        V3 xIC = V3{ctx->xIC[0], ctx->xIC[1], ctx->xIC[2]};
+        M3 velB = (-1.0) * (Qhat * T);
+        // [skew(q0) R_Q, -a R_Q] * common  (3x6)
+        M3 t0 = skew(q0) * RQ;
+        M3 t1 = (-a) * RQ;
+        double camB[18];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 6; ++c) {
+                double s = 0;
+                for (int k = 0; k < 3; ++k) s += t0(r, k) * ctx->common[6 * k + c] + t1(r, k) * ctx->common[6 * (3 + k) + c];
+                camB[6 * r + c] = s;
+            }
+        M3 inner = skew(qh) * skew(vC) - 2.0 * outer(vC, qh) + outer(qh, vC);
+        M3 Aq = (-1.0 / norm2(qh)) * (Qhat * inner * inverse(Qhat));
+        M3 Bl = Qhat * (skew(qh) * RTIC + RTIC * skew(xIC));
+        if (coord == COORD_INVDEPTH) {
+            M3 cv = conv_euc2ind(q0), cvi = conv_ind2euc(q0);
+            velB = cv * velB;
+            double tmp[18];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 6; ++c) tmp[6 * r + c] = cv(r, 0) * camB[c] + cv(r, 1) * camB[6 + c] + cv(r, 2) * camB[12 + c];
+            for (int k = 0; k < 18; ++k) camB[k] = tmp[k];
+            Aq = cv * Aq * cvi;
+            Bl = cv * Bl;
+        }
+        double* o = rows + (size_t)i * ROWS_STRIDE;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) o[3 * r + c] = (r == c ? 1.0 : 0.0) + dt * Aq(r, c);
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) o[9 + 12 * r + c] = -dt * Bl(r, c);
+            for (int c = 0; c < 3; ++c) o[9 + 12 * r + 3 + c] = dt * velB(r, c);
+            for (int c = 0; c < 6; ++c) o[9 + 12 * r + 6 + c] = dt * camB[6 * r + c];
+        }
+        for (int k = 0; k < 9; ++k) o[45 + k] = Bl.m[k];
+    }
+
+    for (int s = 0; s < nsteps; ++s) {
+        const ObsStep& st = s_steps[s];
+        V3 p0 = landmark_action(Q, a, q0);
+        Quat LQ;
+        double La;
+        if (st.discrete) {
+            V3 p1 = se3_apply(st.camChangeInv, p0);
+            LQ = quat_from_two_vectors(normalized(p1), normalized(p0));
+            La = norm(p0) / norm(p1);
+        } else {
+            double n2 = norm2(p0);
+            V3 wv = st.omegaC + cross(p0, st.vC) / n2;
+            LQ = so3_exp(st.dt * wv);               // SOT3::exp(dt * W) (SOT3.h:48-53)
+            La = exp(st.dt * (dot(p0, st.vC) / n2));
+        }
+        Q = qmul(Q, LQ);
+        a = a * La;
+    }
+    if (nsteps > 0) {
+        lm[F_QW * cap + i] = Q.w;
+        lm[F_QX * cap + i] = Q.x;
+        lm[F_QY * cap + i] = Q.y;
+        lm[F_QZ * cap + i] = Q.z;
+        lm[F_QA * cap + i] = a;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3a: sensor-sensor block  Sigma'_ss = F_s Sigma_ss F_s^T + N_s   (one block, 21x21 threads)
+// ------------------------------------------------------------------------------------------------
+__global__ void prop_sensor_block_kernel(const double* __restrict__ Sin, double* __restrict__ Sout, int ld,
+                                         const RiccatiCtx* __restrict__ ctx) {
+    __shared__ double sF[21 * 21], sS[21 * 21], sT[21 * 21];
+    int t = threadIdx.x;
+    if (t < 441) {
+        int r = t / 21, c = t % 21;
+        sF[t] = ctx->Fs[t];
+        sS[t] = Sin[(size_t)c * ld + r];  // sS[r*21+c] = Sigma[r,c]
+    }
+    __syncthreads();
+    if (t < 441) {
+        int r = t / 21, c = t % 21;
+        double s = 0;
+        for (int k = 0; k < 21; ++k) s += sF[r * 21 + k] * sS[k * 21 + c];
+        sT[t] = s;
+    }
+    __syncthreads();
+    if (t < 441) {
+        int r = t / 21, c = t % 21;
+        double s = ctx->Ns[t];
+        for (int k = 0; k < 21; ++k) s += sT[r * 21 + k] * sF[c * 21 + k];
+        Sout[(size_t)c * ld + r] = s;
+    }
+    // keep the 3 pad rows/cols of the sensor block zero
+    if (t < 3 * SOFF) {
+        int p = SENSOR_DIM + t / SOFF, q = t % SOFF;
+        Sout[(size_t)q * ld + p] = 0.0;
+        Sout[(size_t)p * ld + q] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3b: one thread per landmark.  With L_i = Sigma[rows of i, 0:21] (3x21):
+//   E_i = D_i L_i[:, sidx]                       (3x12)
+//   H_i = G_i Sigma[sidx, sidx] + E_i            (3x12) = (F Sigma)[rows of i, sidx]
+//   U_i = [ G_i | H_i | cg Bl_i ],  V_i = [ E_i | G_i | Bl_i ]   (3x27 each), so that
+//   Sigma'_ij = D_i Sigma_ij D_j^T + U_i V_j^T (+ plDiag I for i = j)
+// and the sensor-landmark block
+//   Sigma'_{s,i} = F_s ( Sigma[s, sidx] G_i^T + Sigma_{s,i} D_i^T ) + BsG Bl_i^T   (21x3)
+// is written to both triangles of Sout.  uv[i] = U(81) | V(81) row-major 3x27.
+// ------------------------------------------------------------------------------------------------
+constexpr int UV_STRIDE = 162;
+
+__global__ void prop_strip_kernel(const double* __restrict__ Sin, double* __restrict__ Sout, int ld, int N,
+                                  const RiccatiCtx* __restrict__ ctx, const double* __restrict__ rows,
+                                  double* __restrict__ uv) {
+    __shared__ double sF[21 * 21], sS[21 * 21], sBG[63];
+    for (int t = threadIdx.x; t < 441; t += blockDim.x) {
+        int r = t / 21, c = t % 21;
+        sF[t] = ctx->Fs[t];
+        sS[t] = Sin[(size_t)c * ld + r];
+    }
+    for (int t = threadIdx.x; t < 63; t += blockDim.x) sBG[t] = ctx->BsG[t];
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double cg = ctx->cg;
+    const double* ro = rows + (size_t)i * ROWS_STRIDE;
+    double D[9], G[36], Bl[9];
+    for (int k = 0; k < 9; ++k) D[k] = ro[k];
+    for (int k = 0; k < 36; ++k) G[k] = ro[9 + k];
+    for (int k = 0; k < 9; ++k) Bl[k] = ro[45 + k];
+    double L[63];  // L[a*21 + c] = Sigma[SOFF+3i+a, c]
+    const int r0 = SOFF + 3 * i;
+    for (int c = 0; c < 21; ++c)
+        for (int a = 0; a < 3; ++a) L[a * 21 + c] = Sin[(size_t)c * ld + r0 + a];
+    double* U = uv + (size_t)i * UV_STRIDE;
+    double* V = U + 81;
+    for (int a = 0; a < 3; ++a)
+        for (int c = 0; c < 12; ++c) {
+            int sc = c_sidx[c];
+            double e = D[3 * a] * L[sc] + D[3 * a + 1] * L[21 + sc] + D[3 * a + 2] * L[42 + sc];
+            double h = e;
+            for (int k = 0; k < 12; ++k) h += G[12 * a + k] * sS[c_sidx[k] * 21 + sc];
+            U[27 * a + c] = G[12 * a + c];
+            U[27 * a + 12 + c] = h;
+            V[27 * a + c] = e;
+            V[27 * a + 12 + c] = G[12 * a + c];
+        }
+    for (int a = 0; a < 3; ++a)
+        for (int c = 0; c < 3; ++c) {
+            U[27 * a + 24 + c] = cg * Bl[3 * a + c];
+            V[27 * a + 24 + c] = Bl[3 * a + c];
+        }
+    // sensor-landmark block
+    double tmp[63];  // tmp[r*3 + b]
+    for (int r = 0; r < 21; ++r)
+        for (int b = 0; b < 3; ++b) {
+            double s = L[r] * D[3 * b] + L[21 + r] * D[3 * b + 1] + L[42 + r] * D[3 * b + 2];
+            for (int k = 0; k < 12; ++k) s += sS[r * 21 + c_sidx[k]] * G[12 * b + k];
+            tmp[r * 3 + b] = s;
+        }
+    for (int r = 0; r < 21; ++r)
+        for (int b = 0; b < 3; ++b) {
+            double s = sBG[r * 3] * Bl[3 * b] + sBG[r * 3 + 1] * Bl[3 * b + 1] + sBG[r * 3 + 2] * Bl[3 * b + 2];
+            for (int k = 0; k < 21; ++k) s += sF[r * 21 + k] * tmp[k * 3 + b];
+            Sout[(size_t)(r0 + b) * ld + r] = s;
+            Sout[(size_t)r * ld + r0 + b] = s;
+        }
+    for (int p = SENSOR_DIM; p < SOFF; ++p)
+        for (int b = 0; b < 3; ++b) {
+            Sout[(size_t)(r0 + b) * ld + p] = 0.0;
+            Sout[(size_t)p * ld + r0 + b] = 0.0;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: landmark-landmark block of the Riccati step, HBM-bound: one read of Sigma_in, one write of
+// Sigma_out.  A CTA owns a TP x TP tile of landmark pairs; a thread owns one 3x3 block.
+//   Sigma'_ij = D_i Sigma_ij D_j^T + U_i V_j^T (+ plDiag I)
+// Only tiles on or below the diagonal are computed; the mirror tile is written transposed.
+// ------------------------------------------------------------------------------------------------
+constexpr int TP = 16;
+
+__global__ void __launch_bounds__(TP* TP)
+    prop_ll_kernel(const double* __restrict__ Sin, double* __restrict__ Sout, int ld, int N,
+                   const RiccatiCtx* __restrict__ ctx, const double* __restrict__ rows,
+                   const double* __restrict__ uv) {
+    const int ti = blockIdx.y, tj = blockIdx.x;
+    if (tj > ti) return;
+    __shared__ double sU[TP][82], sV[TP][82], sDi[TP][9], sDj[TP][9];
+    const int tid = threadIdx.y * TP + threadIdx.x;
+    const int i0 = ti * TP, j0 = tj * TP;
+    for (int t = tid; t < TP * 81; t += TP * TP) {
+        int l = t / 81, k = t % 81;
+        sU[l][k] = (i0 + l < N) ? uv[(size_t)(i0 + l) * UV_STRIDE + k] : 0.0;
+        sV[l][k] = (j0 + l < N) ? uv[(size_t)(j0 + l) * UV_STRIDE + 81 + k] : 0.0;
+    }
+    for (int t = tid; t < TP * 9; t += TP * TP) {
+        int l = t / 9, k = t % 9;
+        sDi[l][k] = (i0 + l < N) ? rows[(size_t)(i0 + l) * ROWS_STRIDE + k] : 0.0;
+        sDj[l][k] = (j0 + l < N) ? rows[(size_t)(j0 + l) * ROWS_STRIDE + k] : 0.0;
+    }
+    __syncthreads();
+    const int li = threadIdx.x, lj = threadIdx.y;  // threadIdx.x walks rows (contiguous in memory)
+    const int i = i0 + li, j = j0 + lj;
+    if (i >= N || j >= N) return;
+    const int r0 = SOFF + 3 * i, c0 = SOFF + 3 * j;
+    double S[9];  // S[a*3+b] = Sigma[r0+a, c0+b]
+    for (int b = 0; b < 3; ++b)
+        for (int a = 0; a < 3; ++a) S[a * 3 + b] = Sin[(size_t)(c0 + b) * ld + r0 + a];
+    double T[9];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b)
+            T[a * 3 + b] = sDi[li][3 * a] * S[b] + sDi[li][3 * a + 1] * S[3 + b] + sDi[li][3 * a + 2] * S[6 + b];
+    double O[9];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            double s = T[3 * a] * sDj[lj][3 * b] + T[3 * a + 1] * sDj[lj][3 * b + 1] + T[3 * a + 2] * sDj[lj][3 * b + 2];
+#pragma unroll
+            for (int k = 0; k < 27; ++k) s += sU[li][27 * a + k] * sV[lj][27 * b + k];
+            O[a * 3 + b] = s;
+        }
+    if (i == j) {
+        const double pl = ctx->plDiag;
+        O[0] += pl;
+        O[4] += pl;
+        O[8] += pl;
+    }
+    for (int b = 0; b < 3; ++b)
+        for (int a = 0; a < 3; ++a) Sout[(size_t)(c0 + b) * ld + r0 + a] = O[a * 3 + b];
+    if (ti != tj) {
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) Sout[(size_t)(r0 + a) * ld + c0 + b] = O[a * 3 + b];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gate: per state landmark, pixel error, marginal Mahalanobis error and squared depth
+// (VIOFilter.cpp:304-336, VIO_eqf.cpp:196-211, VIOFilter.cpp:366-380).
+// measIdx[i] = index of landmark i's pixel in y, or -1.   out: errAbs[N] | errProb[N] | depth2[N]
+// ------------------------------------------------------------------------------------------------
+__global__ void gate_kernel(const double* __restrict__ lm, int cap, int N, const double* __restrict__ Sig, int ld,
+                            const int* __restrict__ measIdx, const double* __restrict__ y, Camera cam, int coord,
+                            double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
+    Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
+    double a = lm[F_QA * cap + i];
+    V3 qh = landmark_action(Q, a, q0);
+    out[2 * N + i] = norm2(qh);
+    int mi = measIdx[i];
+    if (mi < 0) {
+        out[i] = -1.0;
+        out[N + i] = -1.0;
+        return;
+    }
+    double u, v;
+    cam_project(cam, qh, u, v);
+    double d0 = y[2 * mi] - u, d1 = y[2 * mi + 1] - v;
+    out[i] = sqrt(d0 * d0 + d1 * d1);
+    double C[6];
+    output_block(cam, coord, q0, Q, a, false, 0.0, 0.0, C);
+    const int r0 = SOFF + 3 * i;
+    double P[9];
+    for (int b = 0; b < 3; ++b)
+        for (int aa = 0; aa < 3; ++aa) P[aa * 3 + b] = Sig[(size_t)(r0 + b) * ld + r0 + aa];
+    double CP[6];
+    for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 3; ++c) CP[3 * r + c] = C[3 * r] * P[c] + C[3 * r + 1] * P[3 + c] + C[3 * r + 2] * P[6 + c];
+    double c00 = CP[0] * C[0] + CP[1] * C[1] + CP[2] * C[2];
+    double c01 = CP[0] * C[3] + CP[1] * C[4] + CP[2] * C[5];
+    double c10 = CP[3] * C[0] + CP[4] * C[1] + CP[5] * C[2];
+    double c11 = CP[3] * C[3] + CP[4] * C[4] + CP[5] * C[5];
+    double det = c00 * c11 - c01 * c10;
+    // y^T cov^-1 y with the 2x2 adjugate inverse (Eigen fixed-size inverse)
+    double i00 = c11 / det, i01 = -c01 / det, i10 = -c10 / det, i11 = c00 / det;
+    out[N + i] = d0 * (i00 * d0 + i01 * d1) + d1 * (i10 * d0 + i11 * d1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stable compaction / append of landmarks (removeLandmarkByIndex + addNewLandmarks,
+// VIO_eqf.cpp:172-178,225-245).  map[p] = source landmark index of destination landmark p, or
+// -1-k for the k-th new landmark (identity Q, covariance newVar[0] I, newVar[1] on the depth
+// coordinate when >0).
+// ------------------------------------------------------------------------------------------------
+__global__ void compact_landmarks_kernel(const double* __restrict__ src, double* __restrict__ dst, int cap,
+                                         const int* __restrict__ srcIds, int* __restrict__ dstIds,
+                                         const int* __restrict__ map, int newN, const double* __restrict__ newP,
+                                         const int* __restrict__ newIds) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= newN) return;
+    int s = map[p];
+    if (s >= 0) {
+        for (int f = 0; f < LM_FIELDS; ++f) dst[f * cap + p] = src[f * cap + s];
+        dstIds[p] = srcIds[s];
+    } else {
+        int k = -1 - s;
+        dst[F_Q0X * cap + p] = newP[3 * k];
+        dst[F_Q0Y * cap + p] = newP[3 * k + 1];
+        dst[F_Q0Z * cap + p] = newP[3 * k + 2];
+        dst[F_QW * cap + p] = 1.0;
+        dst[F_QX * cap + p] = 0.0;
+        dst[F_QY * cap + p] = 0.0;
+        dst[F_QZ * cap + p] = 0.0;
+        dst[F_QA * cap + p] = 1.0;
+        dstIds[p] = newIds[k];
+    }
+}
+
+// rows/cols in units of 3 (block index 0..7 = sensor block incl. pad, 8+p = landmark p)
+__global__ void compact_sigma_kernel(const double* __restrict__ Sin, double* __restrict__ Sout, int ld,
+                                     const int* __restrict__ map, int newN, double newVar, double newDepthVar) {
+    // thread (x: row block, y: col block); each handles a 3x3 block
+    int pb = blockIdx.x * blockDim.x + threadIdx.x;
+    int qb = blockIdx.y * blockDim.y + threadIdx.y;
+    const int nb = 8 + newN;
+    if (pb >= nb || qb >= nb) return;
+    int sp = pb < 8 ? pb : (map[pb - 8] >= 0 ? 8 + map[pb - 8] : -1);
+    int sq = qb < 8 ? qb : (map[qb - 8] >= 0 ? 8 + map[qb - 8] : -1);
+    for (int b = 0; b < 3; ++b)
+        for (int a = 0; a < 3; ++a) {
+            double v;
+            if (sp >= 0 && sq >= 0)
+                v = Sin[(size_t)(3 * sq + b) * ld + 3 * sp + a];
+            else if (pb == qb && a == b)
+                v = (a == 2 && newDepthVar > 0) ? newDepthVar : newVar;
+            else
+                v = 0.0;
+            Sout[(size_t)(3 * qb + b) * ld + 3 * pb + a] = v;
+        }
+}
+
+// Fill Sigma with a diagonal (initial covariance): diag[] has dimp entries in internal order.
+__global__ void fill_diag_kernel(double* __restrict__ S, int ld, int dimp, const double* __restrict__ diag) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = blockIdx.y;
+    if (r >= dimp || c >= dimp) return;
+    S[(size_t)c * ld + r] = (r == c) ? diag[r] : 0.0;
+}
+// Overwrite the landmark-landmark block with a diagonal (setLandmarks, VIOFilter.cpp:94-101)
+__global__ void fill_ll_diag_kernel(double* __restrict__ S, int ld, int n3, double var, double depthVar) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = blockIdx.y;
+    if (r >= n3 || c >= n3) return;
+    double v = 0.0;
+    if (r == c) v = (r % 3 == 2 && depthVar > 0) ? depthVar : var;
+    S[(size_t)(SOFF + c) * ld + SOFF + r] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Correction, step 1: per measured landmark j (state index lmOf[j]): residual and C*_j
+// (VIOState.cpp:70-78, VisionMeasurement.cpp:60-79, EqFMatrices.cpp:43-82).
+// Writes Cblk[j] (2x3 row-major) and the ytilde row of Z.
+// ------------------------------------------------------------------------------------------------
+__global__ void meas_kernel(const double* __restrict__ lm, int cap, const int* __restrict__ lmOf, int n,
+                            const double* __restrict__ y, Camera cam, int coord, int useStar,
+                            double* __restrict__ Cblk, double* __restrict__ Z, int ldz, int yrow) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int i = lmOf[j];
+    V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
+    Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
+    double a = lm[F_QA * cap + i];
+    V3 qh = landmark_action(Q, a, q0);
+    double u, v;
+    cam_project(cam, qh, u, v);
+    double yu = y[2 * j], yv = y[2 * j + 1];
+    Z[(size_t)(2 * j) * ldz + yrow] = yu - u;
+    Z[(size_t)(2 * j + 1) * ldz + yrow] = yv - v;
+    double C[6];
+    output_block(cam, coord, q0, Q, a, useStar != 0, yu, yv, C);
+    for (int k = 0; k < 6; ++k) Cblk[6 * j + k] = C[k];
+}
+
+// Step 2: W^T = Sigma C^T into Z rows [m, m+dimp).  grid (ceil(dimp/256), n).
+__global__ void zbuild_kernel(const double* __restrict__ Sig, int ld, int dimp, const int* __restrict__ lmOf,
+                              const double* __restrict__ Cblk, double* __restrict__ Z, int ldz, int m) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y;
+    if (r >= dimp) return;
+    int c0 = SOFF + 3 * lmOf[j];
+    double s0 = Sig[(size_t)c0 * ld + r], s1 = Sig[(size_t)(c0 + 1) * ld + r], s2 = Sig[(size_t)(c0 + 2) * ld + r];
+    const double* C = Cblk + 6 * j;
+    Z[(size_t)(2 * j) * ldz + m + r] = C[0] * s0 + C[1] * s1 + C[2] * s2;
+    Z[(size_t)(2 * j + 1) * ldz + m + r] = C[3] * s0 + C[4] * s1 + C[5] * s2;
+}
+
+// Step 3: S = C W^T... + sigma^2 I into Z rows [0,m).  thread per entry.
+__global__ void sbuild_kernel(const int* __restrict__ lmOf, const double* __restrict__ Cblk, double* __restrict__ Z,
+                              int ldz, int m, double r2) {
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    int col = blockIdx.y;
+    if (row >= m) return;
+    int k = row >> 1, e = row & 1;
+    int w0 = m + SOFF + 3 * lmOf[k];
+    const double* C = Cblk + 6 * k + 3 * e;
+    const double* zc = Z + (size_t)col * ldz;
+    double s = C[0] * zc[w0] + C[1] * zc[w0 + 1] + C[2] * zc[w0 + 2];
+    if (row == col) s += r2;
+    Z[(size_t)col * ldz + row] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cholesky sweep, panel step: factor the NB x NB diagonal block (every CTA redundantly, one warp),
+// then solve rows below against L^T.  One thread per row; grid = ceil(rowsBelow / PANEL_THREADS)
+// (>= 1).  The factored diagonal block is NOT written back into Z (other CTAs are still reading the
+// unfactored block); CTA 0 stores it to Lout (NB x NB column-major per panel) instead.
+// ------------------------------------------------------------------------------------------------
+constexpr int NB = 32;
+constexpr int PANEL_THREADS = 128;
+
+__global__ void __launch_bounds__(PANEL_THREADS)
+    chol_panel_kernel(double* __restrict__ Z, int ldz, int Mz, int kcol, int nbk, int* __restrict__ status,
+                      double* __restrict__ Lout) {
+    __shared__ double L[NB][NB + 1];
+    __shared__ double invd[NB];
+    const int tid = threadIdx.x;
+    for (int t = tid; t < NB * NB; t += PANEL_THREADS) {
+        int r = t % NB, c = t / NB;
+        double v = (r == c) ? 1.0 : 0.0;
+        if (r < nbk && c < nbk && r >= c) v = Z[(size_t)(kcol + c) * ldz + kcol + r];
+        L[r][c] = v;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const int i = tid;
+        for (int j = 0; j < nbk; ++j) {
+            double s0 = (i >= j) ? L[i][j] : 0.0, s1 = 0.0;
+            int k = 0;
+            for (; k + 1 < j; k += 2) {
+                s0 -= L[i][k] * L[j][k];
+                s1 -= L[i][k + 1] * L[j][k + 1];
+            }
+            if (k < j) s0 -= L[i][k] * L[j][k];
+            double s = s0 + s1;
+            double d = __shfl_sync(0xffffffffu, s, j);
+            if (!(d > 0.0)) {
+                if (i == 0 && blockIdx.x == 0) atomicOr(status, 1);
+                d = 1.0;
+            }
+            d = sqrt(d);
+            if (i == j) {
+                L[j][j] = d;
+                invd[j] = 1.0 / d;
+            } else if (i > j) {
+                L[i][j] = s / d;
+            }
+            __syncwarp();
+        }
+        for (int j = nbk + i; j < NB; j += 32) invd[j] = 1.0;
+        if (i >= nbk) invd[i] = 1.0;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        double* lo = Lout + (size_t)kcol * NB;
+        for (int t = tid; t < NB * NB; t += PANEL_THREADS) {
+            int r = t % NB, c = t / NB;
+            lo[c * NB + r] = (r >= c && r < nbk && c < nbk) ? L[r][c] : 0.0;
+        }
+    }
+    const int row = kcol + nbk + blockIdx.x * PANEL_THREADS + tid;
+    if (row >= Mz) return;
+    double x[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) x[c] = (c < nbk) ? Z[(size_t)(kcol + c) * ldz + row] : 0.0;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        double s = x[c];
+#pragma unroll
+        for (int k = 0; k < c; ++k) s -= x[k] * L[c][k];
+        x[c] = s * invd[c];
+    }
+#pragma unroll
+    for (int c = 0; c < NB; ++c)
+        if (c < nbk) Z[(size_t)(kcol + c) * ldz + row] = x[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 tensor-core tile GEMM:  C[i,j] -= sum_k A[i,k] B[j,k]   (all column-major), used for the
+// trailing update of the sweep and for the Sigma downdate  Sigma -= Y^T Y  (A = B = Y^T, MIRROR).
+// Tiles strictly above the diagonal (max i < min j) are skipped; with MIRROR the transposed tile is
+// stored as well so that Sigma stays stored in full.  mma.sync.m8n8k4.f64 (DMMA): tcgen05 has no
+// fp64 kind, so the fp64 path runs on the FP64 tensor pipe through the legacy warp-level MMA.
+// CTA = 4 warps (2x2), CTA tile 64x64, warp tile 32x32, BK = 16, register-staged double buffering.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int GBM = 64, GBN = 64, GBK = 16, GLD = 72;  // GLD % 16 == 8 -> conflict-free fragment loads
+
+template <bool MIRROR>
+__global__ void __launch_bounds__(128)
+    gemm_nt_sub_kernel(double* __restrict__ C, int ldc, const double* __restrict__ A, int lda,
+                       const double* __restrict__ B, int ldb, int M, int N, int K) {
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    const int i0 = bi * GBM, j0 = bj * GBN;
+    if (i0 + GBM - 1 < j0) return;  // strictly above the diagonal
+    __shared__ double As[2][GBK][GLD];
+    __shared__ double Bs[2][GBK][GLD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int lr = tid & 63, lk = (tid >> 6) * 8;  // loader: row lr, k columns lk..lk+7
+    double ra[8], rb[8];
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            int k = k0 + lk + q;
+            ra[q] = (i0 + lr < M && k < K) ? A[(size_t)k * lda + i0 + lr] : 0.0;
+            rb[q] = (j0 + lr < N && k < K) ? B[(size_t)k * ldb + j0 + lr] : 0.0;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            As[buf][lk + q][lr] = ra[q];
+            Bs[buf][lk + q][lr] = rb[q];
+        }
+    };
+    const int nk = (K + GBK - 1) / GBK;
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) gload((kt + 1) * GBK);
+#pragma unroll
+        for (int k4 = 0; k4 < GBK; k4 += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) af[a] = As[buf][k4 + (lane & 3)][wm + a * 8 + (lane >> 2)];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bf[b] = Bs[buf][k4 + (lane & 3)][wn + b * 8 + (lane >> 2)];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+        if (kt + 1 < nk) {
+            sstore(buf ^ 1);
+            __syncthreads();
+        }
+    }
+    const bool offdiag = MIRROR && (i0 != j0);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            int r = i0 + wm + a * 8 + (lane >> 2);
+            int c = j0 + wn + b * 8 + (lane & 3) * 2;
+            if (r < M) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (c + e < N) {
+                        double v = C[(size_t)(c + e) * ldc + r] - acc[a][b][e];
+                        C[(size_t)(c + e) * ldc + r] = v;
+                        if (offdiag) C[(size_t)r * ldc + c + e] = v;
+                    }
+            }
+        }
+}
+
+// Gamma = Y^T (L^-1 ytilde):  Gamma[r] = sum_k Z[m + r, k] * Z[yrow, k].  One thread per r.
+__global__ void gamma_kernel(const double* __restrict__ Z, int ldz, int m, int dimp, double* __restrict__ Gamma) {
+    extern __shared__ double szy[];
+    const int yrow = m + dimp;
+    for (int k = threadIdx.x; k < m; k += blockDim.x) szy[k] = Z[(size_t)k * ldz + yrow];
+    __syncthreads();
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= dimp) return;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int k = 0;
+    for (; k + 3 < m; k += 4) {
+        s0 += Z[(size_t)k * ldz + m + r] * szy[k];
+        s1 += Z[(size_t)(k + 1) * ldz + m + r] * szy[k + 1];
+        s2 += Z[(size_t)(k + 2) * ldz + m + r] * szy[k + 2];
+        s3 += Z[(size_t)(k + 3) * ldz + m + r] * szy[k + 3];
+    }
+    for (; k < m; ++k) s0 += Z[(size_t)k * ldz + m + r] * szy[k];
+    Gamma[r] = (s0 + s1) + (s2 + s3);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Innovation lift and X <- Delta * X (euclid.cpp:36-97, invdepth.cpp:183-253, VIOGroup.cpp:71-92,
+// VIO_eqf.cpp:119-130), followed by the validity test of removeInvalidLandmarks
+// (VIO_eqf.cpp:213-223).  status: bit0 = non-SPD S, bit1 = NaN, invalidFlag[i] = 1 if Q.a is out of
+// (1e-8, 1e8].  Gamma uses the internal index (landmark i at SOFF + 3 i).
+// ------------------------------------------------------------------------------------------------
+__global__ void lift_kernel(double* __restrict__ lm, int cap, int N, const double* __restrict__ xi0s,
+                            double* __restrict__ Xs, const double* __restrict__ Gamma, int discrete, int coord,
+                            int* __restrict__ status, int* __restrict__ invalidFlag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        SensorState xi0 = unpack_sensor(xi0s);
+        GroupSensor X = unpack_group(Xs);
+        GroupSensor D;
+        bool bad = false;
+        for (int k = 0; k < 21; ++k) bad |= !isfinite(Gamma[k]);
+        V3 gw = V3{Gamma[6], Gamma[7], Gamma[8]}, gx = V3{Gamma[9], Gamma[10], Gamma[11]};
+        V3 gv = V3{Gamma[12], Gamma[13], Gamma[14]};
+        V3 bw = V3{Gamma[15], Gamma[16], Gamma[17]}, bx = V3{Gamma[18], Gamma[19], Gamma[20]};
+        for (int k = 0; k < 6; ++k) D.beta[k] = Gamma[k];
+        if (discrete) {  // euclid.cpp:71-79
+            D.A = se3_exp(gw, gx);
+            D.w = xi0.vel - qrot(D.A.q, xi0.vel + gv);
+            D.B = se3_mul(se3_mul(se3_mul(se3_inv(xi0.cam), D.A), xi0.cam), se3_exp(bw, bx));
+        } else {  // euclid.cpp:36-50 + VIOExp
+            V3 uw = -gv - cross(gw, xi0.vel);
+            double Ad[36], UA[6] = {gw.x, gw.y, gw.z, gx.x, gx.y, gx.z}, t[6];
+            se3_Adjoint(se3_inv(xi0.cam), Ad);
+            mat6_vec(Ad, UA, t);
+            se23_exp(gw, gx, uw, D.A.q, D.A.x, D.w);
+            D.B = se3_exp(V3{bw.x + t[0], bw.y + t[1], bw.z + t[2]}, V3{bx.x + t[3], bx.y + t[4], bx.z + t[5]});
+        }
+        GroupSensor Xn;
+        for (int k = 0; k < 6; ++k) Xn.beta[k] = D.beta[k] + X.beta[k];
+        Xn.A = se3_mul(D.A, X.A);
+        Xn.B = se3_mul(D.B, X.B);
+        Xn.w = D.w + qrot(D.A.q, X.w);
+        pack_group(Xn, Xs);
+        if (bad) atomicOr(status, 2);
+    }
+    if (i >= N) return;
+    V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
+    Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
+    double a = lm[F_QA * cap + i];
+    V3 g = V3{Gamma[SOFF + 3 * i], Gamma[SOFF + 3 * i + 1], Gamma[SOFF + 3 * i + 2]};
+    Quat DQ;
+    double Da;
+    if (discrete) {
+        V3 q1 = (coord == COORD_INVDEPTH) ? invdepth_chart_inv(g, q0) : q0 + g;
+        DQ = quat_from_two_vectors(normalized(q1), normalized(q0));
+        Da = norm(q0) / norm(q1);
+    } else {
+        if (coord == COORD_INVDEPTH) g = ind2euc_lift(q0) * g;
+        double n2 = norm2(q0);
+        V3 wv = (-1.0 / n2) * cross(q0, g);
+        DQ = so3_exp(wv);
+        Da = exp(-dot(q0, g) / n2);
+    }
+    Q = qmul(DQ, Q);
+    a = Da * a;
+    lm[F_QW * cap + i] = Q.w;
+    lm[F_QX * cap + i] = Q.x;
+    lm[F_QY * cap + i] = Q.y;
+    lm[F_QZ * cap + i] = Q.z;
+    lm[F_QA * cap + i] = a;
+    bool nan = !(isfinite(Q.w) && isfinite(Q.x) && isfinite(Q.y) && isfinite(Q.z) && isfinite(a));
+    if (nan) atomicOr(status, 2);
+    int inv = (a <= 1e-8 || a > 1e8) ? 1 : 0;
+    invalidFlag[i] = inv;
+    if (inv) atomicOr(status, 4);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Output helpers
+// ------------------------------------------------------------------------------------------------
+// stateEstimate (VIOGroup.cpp:34-55): out = sensor(23) | p(3N)
+__global__ void state_estimate_kernel(const double* __restrict__ lm, int cap, int N, const double* __restrict__ xi0s,
+                                      const double* __restrict__ Xs, double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        SensorState r = sensor_group_action(unpack_group(Xs), unpack_sensor(xi0s));
+        pack_sensor(r, out);
+    }
+    if (i >= N) return;
+    V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
+    Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
+    V3 p = landmark_action(Q, lm[F_QA * cap + i], q0);
+    out[23 + 3 * i] = p.x;
+    out[23 + 3 * i + 1] = p.y;
+    out[23 + 3 * i + 2] = p.z;
+}
+
+// Sigma in the reference's layout (dim x dim, column-major, no pad)
+__global__ void pack_sigma_kernel(const double* __restrict__ S, int ld, int dim, double* __restrict__ out, int ldo) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = blockIdx.y;
+    if (r >= dim || c >= dim) return;
+    int ri = r < SENSOR_DIM ? r : r + (SOFF - SENSOR_DIM);
+    int ci = c < SENSOR_DIM ? c : c + (SOFF - SENSOR_DIM);
+    out[(size_t)c * ldo + r] = S[(size_t)ci * ld + ri];
+}
+
+__global__ void cov_blocks_kernel(const double* __restrict__ S, int ld, int N, double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int r0 = SOFF + 3 * i;
+    for (int b = 0; b < 3; ++b)
+        for (int a = 0; a < 3; ++a) out[9 * i + 3 * b + a] = S[(size_t)(r0 + b) * ld + r0 + a];
+}
+
+}  // namespace eqvio

@@ -1,0 +1,303 @@
+// Sensor-state algebra, camera models, point charts and the per-landmark output
+// block of the EqF -- shared by host and device code.
+//
+// Reference functions restated here (path:line relative to the reference):
+//   sensorStateGroupAction            src/mathematical/VIOGroup.cpp:25-32
+//   GIFT pinhole / radtan camera      external/GIFT/GIFT/src/camera/PinholeCamera.cpp:57-74,
+//                                     external/GIFT/GIFT/src/camera/StandardCamera.cpp:41-111
+//   stereographic sphere chart        src/mathematical/VIOState.cpp:246-307
+//   pointChart_invdepth.inv           src/mathematical/VIOState.cpp:174-188
+//   conv_euc2ind / conv_ind2euc       src/mathematical/coordinateSuite/invdepth.cpp:65-81
+//   ind2euc (lift / C*)               src/mathematical/coordinateSuite/invdepth.cpp:203-209, 259-263
+//   EqFoutputMatrixCiStar_{euclid,invdepth}, outputMatrixCi
+//                                     coordinateSuite/euclid.cpp:162-184, invdepth.cpp:255-266,
+//                                     src/mathematical/EqFMatrices.cpp:84-89
+#pragma once
+#include "lie.cuh"
+
+namespace eqvio {
+
+constexpr int SENSOR_DIM = 21;  // VIOSensorState::CompDim
+constexpr int SOFF = 24;        // internal row offset of landmark 0 in Sigma (sensor block padded 21 -> 24)
+
+enum { COORD_EUCLIDEAN = 0, COORD_INVDEPTH = 1 };
+enum { CAM_PINHOLE = 0, CAM_RADTAN = 1 };
+
+struct Camera {
+    int model, width, height, ndist;
+    double fx, fy, cx, cy;
+    double dist[5];
+    double inv_dist[5];
+};
+
+struct SensorState {  // VIOSensorState (VIOState.h:41-62)
+    double bias[6];
+    SE3 pose;
+    V3 vel;
+    SE3 cam;
+};
+struct GroupSensor {  // sensor part of VIOGroup (VIOGroup.h:32-38)
+    double beta[6];
+    SE3 A;
+    V3 w;
+    SE3 B;
+};
+
+HD SE3 unpack_se3(const double* f) { return SE3{Quat{f[0], f[1], f[2], f[3]}, V3{f[4], f[5], f[6]}}; }
+HD void pack_se3(const SE3& s, double* f) {
+    f[0] = s.q.w; f[1] = s.q.x; f[2] = s.q.y; f[3] = s.q.z; f[4] = s.x.x; f[5] = s.x.y; f[6] = s.x.z;
+}
+HD SensorState unpack_sensor(const double* f) {
+    SensorState s;
+    for (int i = 0; i < 6; ++i) s.bias[i] = f[i];
+    s.pose = unpack_se3(f + 6);
+    s.vel = V3{f[13], f[14], f[15]};
+    s.cam = unpack_se3(f + 16);
+    return s;
+}
+HD void pack_sensor(const SensorState& s, double* f) {
+    for (int i = 0; i < 6; ++i) f[i] = s.bias[i];
+    pack_se3(s.pose, f + 6);
+    f[13] = s.vel.x; f[14] = s.vel.y; f[15] = s.vel.z;
+    pack_se3(s.cam, f + 16);
+}
+HD GroupSensor unpack_group(const double* f) {
+    GroupSensor g;
+    for (int i = 0; i < 6; ++i) g.beta[i] = f[i];
+    g.A = unpack_se3(f + 6);
+    g.w = V3{f[13], f[14], f[15]};
+    g.B = unpack_se3(f + 16);
+    return g;
+}
+HD void pack_group(const GroupSensor& g, double* f) {
+    for (int i = 0; i < 6; ++i) f[i] = g.beta[i];
+    pack_se3(g.A, f + 6);
+    f[13] = g.w.x; f[14] = g.w.y; f[15] = g.w.z;
+    pack_se3(g.B, f + 16);
+}
+HD GroupSensor group_identity() {
+    GroupSensor g;
+    for (int i = 0; i < 6; ++i) g.beta[i] = 0;
+    g.A = se3_identity();
+    g.w = V3{0, 0, 0};
+    g.B = se3_identity();
+    return g;
+}
+
+// VIOGroup.cpp:25-32
+HD SensorState sensor_group_action(const GroupSensor& X, const SensorState& s) {
+    SensorState r;
+    for (int i = 0; i < 6; ++i) r.bias[i] = s.bias[i] + X.beta[i];
+    r.pose = se3_mul(s.pose, X.A);
+    r.vel = qrot(qinv(X.A.q), s.vel - X.w);
+    r.cam = se3_mul(se3_mul(se3_inv(X.A), s.cam), X.B);
+    return r;
+}
+// landmark part of stateGroupAction: Q^-1 q0 = (1/a) R_Q^-1 q0 (VIOGroup.cpp:44-52, SOT3.h:95-103)
+HD V3 landmark_action(Quat Qq, double Qa, V3 q0) { return (1.0 / Qa) * qrot(qinv(Qq), q0); }
+
+// ---------------------------------------------------------------- cameras
+HD void distort_homogeneous(double x, double y, const double* d, int n, double& ox, double& oy) {
+    double r2 = x * x + y * y;  // StandardCamera.cpp:57-75
+    ox = x;
+    oy = y;
+    if (n >= 2) {
+        ox += x * (d[0] * r2 + d[1] * r2 * r2);
+        oy += y * (d[0] * r2 + d[1] * r2 * r2);
+    }
+    if (n >= 4) {
+        ox += 2 * d[2] * x * y + d[3] * (r2 + 2 * x * x);
+        oy += 2 * d[3] * x * y + d[2] * (r2 + 2 * y * y);
+    }
+    if (n >= 5) {
+        ox += x * d[4] * r2 * r2 * r2;
+        oy += y * d[4] * r2 * r2 * r2;
+    }
+}
+HD void cam_project(const Camera& c, V3 p, double& u, double& v) {
+    if (c.model == CAM_RADTAN) {  // StandardCamera.cpp:41-48
+        double dx, dy;
+        distort_homogeneous(p.x / p.z, p.y / p.z, c.dist, c.ndist, dx, dy);
+        u = c.fx * dx / 1.0 + c.cx;
+        v = c.fy * dy / 1.0 + c.cy;
+    } else {  // PinholeCamera.cpp:70-74
+        u = c.fx * p.x / p.z + c.cx;
+        v = c.fy * p.y / p.z + c.cy;
+    }
+}
+HD V3 cam_undistort(const Camera& c, double u, double v) {
+    V3 b = normalized(V3{(u - c.cx) / c.fx, (v - c.cy) / c.fy, 1.0});  // PinholeCamera.cpp:57-61
+    if (c.model == CAM_RADTAN) {                                        // StandardCamera.cpp:50-56
+        double dx, dy;
+        distort_homogeneous(b.x / b.z, b.y / b.z, c.inv_dist, c.ndist, dx, dy);
+        b = normalized(V3{dx, dy, 1.0});
+    }
+    return b;
+}
+// J: 2x3 row-major
+HD void cam_jacobian(const Camera& c, V3 p, double* J) {
+    double iz = 1.0 / p.z;
+    if (c.model == CAM_RADTAN) {  // StandardCamera.cpp:77-111
+        double Jh[6] = {1.0 / p.z, 0, -1.0 * p.x / (p.z * p.z), 0, 1.0 / p.z, -1.0 * p.y / (p.z * p.z)};
+        double px = p.x / p.z, py = p.y / p.z;
+        double r2 = px * px + py * py;
+        const double* d = c.dist;
+        double D00 = 1, D01 = 0, D10 = 0, D11 = 1;
+        if (c.ndist >= 2) {
+            double s = d[0] * r2 + d[1] * r2 * r2;
+            D00 += s;
+            D11 += s;
+            double k = d[0] + 2 * r2 * d[1];
+            D00 += px * k * 2 * px; D01 += px * k * 2 * py; D10 += py * k * 2 * px; D11 += py * k * 2 * py;
+        }
+        if (c.ndist >= 4) {
+            D00 += 2.0 * d[2] * py + 6.0 * d[3] * px;
+            D01 += 2.0 * d[2] * px + 2.0 * d[3] * py;
+            D10 += 2.0 * d[2] * px + 2.0 * d[3] * py;
+            D11 += 6.0 * d[2] * py + 2.0 * d[3] * px;
+        }
+        if (c.ndist >= 5) {
+            double s = d[4] * r2 * r2 * r2;
+            D00 += s;
+            D11 += s;
+            double k = d[4] * 3 * r2 * r2;
+            D00 += px * k * 2 * px; D01 += px * k * 2 * py; D10 += py * k * 2 * px; D11 += py * k * 2 * py;
+        }
+        for (int j = 0; j < 3; ++j) {
+            J[j] = c.fx * (D00 * Jh[j] + D01 * Jh[3 + j]);
+            J[3 + j] = c.fy * (D10 * Jh[j] + D11 * Jh[3 + j]);
+        }
+    } else {  // PinholeCamera.cpp:63-68
+        J[0] = c.fx / p.z; J[1] = 0; J[2] = -c.fx * p.x / (p.z * p.z);
+        J[3] = 0; J[4] = c.fy / p.z; J[5] = -c.fy * p.y / (p.z * p.z);
+    }
+    (void)iz;
+}
+
+// ---------------------------------------------------------------- stereographic chart about a pole
+// rot = SO3FromVectors(-pole, e3)  (VIOState.cpp:286-307)
+HD Quat stereo_rot(V3 pole) { return quat_from_two_vectors(-pole, V3{0, 0, 1}); }
+// chartDiff0(pole): 2x3 row-major  = e3ProjectSphereDiff(rot*pole) * R(rot)
+HD void stereo_diff0(V3 pole, double* D) {
+    Quat rot = stereo_rot(pole);
+    V3 eta = qrot(rot, pole);
+    M3 R = qmat(rot);
+    double s = 1.0 - eta.z;
+    double f = 1.0 / (s * s);  // pow(1 - e3.eta, -2)
+    // I23 * (I*(1-eta.z) + (eta - e3) e3^T): rows 0,1: [s,0,eta.x],[0,s,eta.y]
+    double P[6] = {f * s, 0, f * eta.x, 0, f * s, f * eta.y};
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 3; ++j) D[3 * i + j] = P[3 * i] * R(0, j) + P[3 * i + 1] * R(1, j) + P[3 * i + 2] * R(2, j);
+}
+// chartInvDiff0(pole): 3x2 row-major = R(rot^-1) * e3ProjectSphereInvDiff(0),  e3ProjectSphereInvDiff(0) = 2*[I2;0]
+HD void stereo_inv_diff0(V3 pole, double* D) {
+    M3 Ri = qmat(qinv(stereo_rot(pole)));
+    for (int i = 0; i < 3; ++i) {
+        D[2 * i] = 2.0 * Ri(i, 0);
+        D[2 * i + 1] = 2.0 * Ri(i, 1);
+    }
+}
+// sphereChart_stereo.inv(y, pole)
+HD V3 stereo_inv(double y0, double y1, V3 pole) {
+    double k = 2.0 / (y0 * y0 + y1 * y1 + 1.0);
+    V3 eta = V3{k * y0, k * y1, 1.0 + k * (0.0 - 1.0)};
+    return qrot(qinv(stereo_rot(pole)), eta);
+}
+// pointChart_invdepth.inv (VIOState.cpp:174-188)
+HD V3 invdepth_chart_inv(V3 eps, V3 q0) {
+    double rho0 = 1.0 / norm(q0);
+    V3 y0 = q0 * rho0;
+    V3 y = stereo_inv(eps.x, eps.y, y0);
+    double rho = eps.z + rho0;
+    if (rho <= 0.0) rho = 1e-6;
+    return y / rho;
+}
+// conv_euc2ind(q0) (invdepth.cpp:65-73): rows 0,1 = rho0 * DPhi(y0) (I - y0 y0^T); row 2 = -rho0^2 y0^T
+HD M3 conv_euc2ind(V3 q0) {
+    double rho0 = 1.0 / norm(q0);
+    V3 y0 = q0 * rho0;
+    double D[6];
+    stereo_diff0(y0, D);
+    M3 P = m3_identity() - outer(y0, y0);
+    M3 M;
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 3; ++j) M(i, j) = rho0 * (D[3 * i] * P(0, j) + D[3 * i + 1] * P(1, j) + D[3 * i + 2] * P(2, j));
+    M(2, 0) = -rho0 * rho0 * y0.x;
+    M(2, 1) = -rho0 * rho0 * y0.y;
+    M(2, 2) = -rho0 * rho0 * y0.z;
+    return M;
+}
+// conv_ind2euc(q0) (invdepth.cpp:74-81): cols 0,1 = DPhi^-1(y0)/rho0; col 2 = -y0/rho0^2
+HD M3 conv_ind2euc(V3 q0) {
+    double rho0 = 1.0 / norm(q0);
+    V3 y0 = q0 * rho0;
+    double D[6];
+    stereo_inv_diff0(y0, D);
+    M3 M;
+    for (int i = 0; i < 3; ++i) {
+        M(i, 0) = D[2 * i] / rho0;
+        M(i, 1) = D[2 * i + 1] / rho0;
+    }
+    M(0, 2) = -y0.x / (rho0 * rho0);
+    M(1, 2) = -y0.y / (rho0 * rho0);
+    M(2, 2) = -y0.z / (rho0 * rho0);
+    return M;
+}
+// ind2euc of the innovation lift and of C* (invdepth.cpp:203-209, 259-263): [r0 * DPhi^-1(y0), -r0 * q0]
+HD M3 ind2euc_lift(V3 q0) {
+    double r0 = norm(q0);
+    V3 y0 = q0 / r0;
+    double D[6];
+    stereo_inv_diff0(y0, D);
+    M3 M;
+    for (int i = 0; i < 3; ++i) {
+        M(i, 0) = r0 * D[2 * i];
+        M(i, 1) = r0 * D[2 * i + 1];
+    }
+    M(0, 2) = -r0 * q0.x;
+    M(1, 2) = -r0 * q0.y;
+    M(2, 2) = -r0 * q0.z;
+    return M;
+}
+
+// ---------------------------------------------------------------- output block C*_i (2x3 row-major)
+// DRho(v)[:, 0:3] = J_pi(v) * skew(v); the 4th column of DRho is zero, so only the rotation block
+// of Ad_{Q^-1} and the first three rows of m2g contribute (euclid.cpp:166-183).
+HD void drho3(const Camera& cam, V3 v, double* out /*2x3*/) {
+    double J[6];
+    cam_jacobian(cam, v, J);
+    M3 S = skew(v);
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 3; ++j) out[3 * i + j] = J[3 * i] * S(0, j) + J[3 * i + 1] * S(1, j) + J[3 * i + 2] * S(2, j);
+}
+// useStar: y = measured pixel; otherwise y := project(qHat) (outputMatrixCi, EqFMatrices.cpp:84-89)
+HD void output_block(const Camera& cam, int coord, V3 q0, Quat Qq, double Qa, bool useStar, double yu, double yv,
+                     double* C /*2x3*/) {
+    V3 qHat = landmark_action(Qq, Qa, q0);
+    V3 yHat = normalized(qHat);
+    if (!useStar) cam_project(cam, qHat, yu, yv);
+    V3 yTru = cam_undistort(cam, yu, yv);
+    double Da[6], Db[6];
+    drho3(cam, yTru, Da);
+    drho3(cam, yHat, Db);
+    M3 Rinv = qmat(qinv(Qq));
+    double n2 = norm2(q0);
+    M3 m2g = (-1.0 / n2) * skew(q0);  // -skew(q0)/|q0|^2
+    M3 T = Rinv * m2g;
+    double Ce[6];
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double a0 = 0.5 * (Da[3 * i] + Db[3 * i]), a1 = 0.5 * (Da[3 * i + 1] + Db[3 * i + 1]),
+                   a2 = 0.5 * (Da[3 * i + 2] + Db[3 * i + 2]);
+            Ce[3 * i + j] = a0 * T(0, j) + a1 * T(1, j) + a2 * T(2, j);
+        }
+    if (coord == COORD_INVDEPTH) {
+        M3 L = ind2euc_lift(q0);
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 3; ++j) C[3 * i + j] = Ce[3 * i] * L(0, j) + Ce[3 * i + 1] * L(1, j) + Ce[3 * i + 2] * L(2, j);
+    } else {
+        for (int i = 0; i < 6; ++i) C[i] = Ce[i];
+    }
+}
+
+}  // namespace eqvio

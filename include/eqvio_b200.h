@@ -1,0 +1,179 @@
+/*
+ * eqvio_b200 -- C ABI of the B200-native EqF vision-update path.
+ *
+ * This is the drop-in boundary for the hot path of pvangoor/eqvio: everything
+ * the reference's `VIOFilter` (include/eqvio/VIOFilter.h:36-192) does between
+ * `processIMUData` / `processVisionData` and `stateEstimate`, executed on one
+ * B200 with the Riccati matrix Sigma resident in HBM.  The reference has no FFI
+ * of its own; each entry point below names the C++ member it replaces so that a
+ * re-bodied `VIOFilter` can forward to it one-to-one.
+ *
+ * Conventions
+ *   - plain C types only; all pointers are HOST pointers unless a name ends in
+ *     `_dev`; arrays are caller-owned, sizes are explicit.
+ *   - return value: 0 = EQVIO_OK.  Conditions on which the reference returns
+ *     silently (filter not initialised, time not advanced, empty measurement;
+ *     src/VIOFilter.cpp:135-136,198-199,223-224) are NOT errors: the call
+ *     returns EQVIO_OK and sets *did_update = 0.  Negative values are errors;
+ *     `eqvio_last_error` gives the message.  Nothing throws across the ABI.
+ *   - one handle = one filter = one CUDA stream; a handle is not thread-safe,
+ *     distinct handles are independent (Monte-Carlo replicas).
+ *   - sensor state, flat `sensor[23]`:
+ *       [0,6) inputBias (gyr, acc) | [6,10) pose quaternion (w,x,y,z) |
+ *       [10,13) pose position | [13,16) body velocity |
+ *       [16,20) camera-offset quaternion | [20,23) camera-offset position
+ *     group element X, flat `group[23]`:
+ *       [0,6) beta | [6,10) A quaternion | [10,13) A translation | [13,16) w |
+ *       [16,20) B quaternion | [20,23) B translation
+ *   - landmark order is the reference's state order (insertion order of
+ *     xi0.cameraLandmarks / X.id); measurements are given in ascending id like
+ *     the reference's std::map (src/mathematical/VisionMeasurement.cpp:24-28).
+ *   - Sigma is exported column-major, dim x dim, dim = 21 + 3 N, in the
+ *     reference's state-vector order (coordinateSuite/euclid.cpp:103-109).
+ */
+#ifndef EQVIO_B200_H
+#define EQVIO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EQVIO_OK 0
+#define EQVIO_ERR_INVALID_ARG (-1)
+#define EQVIO_ERR_CUDA (-2)
+#define EQVIO_ERR_NUMERIC (-3)     /* NaN / non-SPD innovation covariance detected on device */
+#define EQVIO_ERR_CAPACITY (-4)    /* more landmarks than the handle was created for */
+#define EQVIO_ERR_UNSUPPORTED (-5) /* a Settings switch this build has no CUDA path for */
+
+#define EQVIO_COORD_EUCLIDEAN 0
+#define EQVIO_COORD_INVDEPTH 1
+#define EQVIO_COORD_NORMAL 2 /* not implemented on device: EQVIO_ERR_UNSUPPORTED */
+
+#define EQVIO_CAMERA_PINHOLE 0
+#define EQVIO_CAMERA_RADTAN 1
+
+typedef struct eqvio_filter eqvio_filter;
+
+/* POD mirror of VIOFilter::Settings (include/eqvio/VIOFilterSettings.h:58-99);
+ * field names and defaults are the reference's. */
+typedef struct eqvio_settings {
+    double biasOmegaProcessVariance, biasAccelProcessVariance, attitudeProcessVariance, positionProcessVariance,
+        velocityProcessVariance, cameraAttitudeProcessVariance, cameraPositionProcessVariance, pointProcessVariance;
+    double velGyrNoise, velAccNoise, velGyrBiasWalk, velAccBiasWalk;
+    double measurementNoise, outlierThresholdAbs, outlierThresholdProb, featureRetention;
+    double initialAttitudeVariance, initialPositionVariance, initialVelocityVariance, initialCameraAttitudeVariance,
+        initialCameraPositionVariance, initialPointVariance, initialPointDepthVariance, initialBiasOmegaVariance,
+        initialBiasAccelVariance, initialSceneDepth;
+    int useDiscreteInnovationLift, useDiscreteVelocityLift, useDiscreteStateMatrix, fastRiccati, useMedianDepth,
+        useFeaturePredictions, useEquivariantOutput, removeLostLandmarks;
+    int coordinateChoice;   /* EQVIO_COORD_* */
+    double cameraOffset[7]; /* quaternion (w,x,y,z), position -- Settings::cameraOffset */
+} eqvio_settings;
+
+/* Flattened GIFT::GICamera (external/GIFT/GIFT/include/GIFT/camera/GICamera.h:29-71).
+ * For RADTAN the caller supplies inv_dist, i.e. StandardCamera::invDist; use
+ * eqvio_camera_fit_inverse_distortion to recompute it (the member is protected in GIFT). */
+typedef struct eqvio_camera {
+    int model; /* EQVIO_CAMERA_* */
+    int width, height;
+    int ndist; /* number of valid entries of dist / inv_dist: 0, 2, 4 or 5 */
+    double fx, fy, cx, cy;
+    double dist[5];
+    double inv_dist[5];
+} eqvio_camera;
+
+/* --- settings / camera helpers ------------------------------------------------ */
+/* VIOFilter::Settings() defaults (VIOFilterSettings.h:59-98). */
+void eqvio_settings_default(eqvio_settings* s);
+/* StandardCamera::computeInverseDistortion (external/GIFT/GIFT/src/camera/StandardCamera.cpp:113-145). */
+int eqvio_camera_fit_inverse_distortion(eqvio_camera* cam);
+
+/* --- lifetime ------------------------------------------------------------------- */
+/* VIOFilter(const Settings&) (src/VIOFilter.cpp:31-41).  `capacity` = the largest
+ * landmark count the handle will ever hold (Sigma is allocated capacity-padded in
+ * HBM once).  `stream_or_null`: a cudaStream_t to run on, or NULL for a private one. */
+int eqvio_create(const eqvio_settings* s, int device, int capacity, void* stream_or_null, eqvio_filter** out);
+/* VIOFilter(const VIOState& xi0, const Settings&, const double& time) (src/VIOFilter.cpp:43-56). */
+int eqvio_create_from_state(const eqvio_settings* s, int device, int capacity, void* stream_or_null,
+                            const double sensor[23], int n, const int* ids, const double* p /* 3n, xyz per landmark */,
+                            double time, eqvio_filter** out);
+void eqvio_destroy(eqvio_filter* f);
+const char* eqvio_last_error(const eqvio_filter* f); /* f may be NULL: last create error */
+
+/* --- state setters ---------------------------------------------------------------- */
+int eqvio_initialise_from_imu(eqvio_filter* f, double stamp, const double gyr[3],
+                              const double acc[3]); /* initialiseFromIMUData, VIOFilter.cpp:65-78 */
+int eqvio_set_state(eqvio_filter* f, const double sensor[23], int n, const int* ids,
+                    const double* p); /* setState, VIOFilter.cpp:80-92 */
+int eqvio_set_landmarks(eqvio_filter* f, int n, const int* ids,
+                        const double* p); /* setLandmarks, VIOFilter.cpp:94-110 */
+/* augmentLandmarkStates (VIOFilter.cpp:112-132): keep only landmarks whose id is in
+ * new_ids, then append the ids that are new with the position found in the provided state. */
+int eqvio_augment_landmark_states(eqvio_filter* f, int n_new, const int* new_ids, int n_provided,
+                                  const int* provided_ids, const double* provided_p);
+
+/* --- input --------------------------------------------------------------------------- */
+/* processIMUData (VIOFilter.cpp:58-63): buffers the sample; first sample initialises attitude. */
+int eqvio_process_imu(eqvio_filter* f, double stamp, const double gyr[3], const double acc[3],
+                      const double gyr_bias_vel[3] /* may be NULL = 0 */, const double acc_bias_vel[3] /* may be NULL */);
+/* processVisionData (VIOFilter.cpp:194-241): propagate to `stamp`, prune lost landmarks, gate
+ * outliers, add new landmarks, EqF correction, drop invalid landmarks.  ids ascending. */
+int eqvio_process_vision(eqvio_filter* f, double stamp, int n, const int* ids, const double* y /* 2n pixels */,
+                         const eqvio_camera* cam, int* did_update /* may be NULL */);
+/* Same update for `count` independent filters at once (Monte-Carlo replicas on one GPU):
+ * kernels of different filters overlap on their streams.  Arrays are indexed per filter. */
+int eqvio_batch_process_vision(eqvio_filter* const* fs, int count, const double* stamps, const int* n,
+                               const int* const* ids, const double* const* y, const eqvio_camera* cam,
+                               int* did_update /* count entries or NULL */);
+
+/* --- output ------------------------------------------------------------------------------ */
+double eqvio_get_time(const eqvio_filter* f);       /* getTime, VIOFilter.cpp:256 */
+int eqvio_is_initialised(const eqvio_filter* f);    /* isInitialised, VIOFilter.h:170 */
+int eqvio_num_landmarks(const eqvio_filter* f);     /* filterState.X.id.size() */
+int eqvio_state_dim(const eqvio_filter* f);         /* xi0.Dim() = 21 + 3N */
+int eqvio_capacity(const eqvio_filter* f);
+/* stateEstimate (VIOFilter.cpp:243): xi_hat = stateGroupAction(X, xi0).  ids/p sized >= N. */
+int eqvio_get_state_estimate(eqvio_filter* f, double sensor[23], int* ids, double* p, int* n_out);
+/* viewEqFState (VIOFilter.cpp:245): xi0, X and Sigma.  Any output pointer may be NULL.
+ * X_Q holds 5 doubles per landmark: quaternion (w,x,y,z), scale a.  Sigma is dim x dim, column-major, ld >= dim. */
+int eqvio_get_eqf_state(eqvio_filter* f, double xi0_sensor[23], int* ids, double* xi0_p, double X_group[23],
+                        double* X_Q, double* Sigma, int ld);
+/* VIO_eqf::getLandmarkCovById for every landmark: 9 doubles (column-major 3x3) per landmark
+ * (VIO_eqf.cpp:188-194; what VIOWriter::writeConsistency reads, src/VIOWriter.cpp:162-222). */
+int eqvio_get_landmark_cov_blocks(eqvio_filter* f, double* blocks /* 9N */);
+/* getFeaturePredictions (VIOFilter.cpp:247-252): pixel predictions at `stamp`; n_out = 0 unless
+ * Settings::useFeaturePredictions. */
+int eqvio_get_feature_predictions(eqvio_filter* f, const eqvio_camera* cam, double stamp, int* ids, double* y,
+                                  int* n_out);
+/* ids removed as outliers by the last eqvio_process_vision (VIOFilter.cpp:304-364), in removal order. */
+int eqvio_get_last_outliers(const eqvio_filter* f, int* ids, int cap, int* n_out);
+
+/* --- measurement hooks (bench / tests only) ------------------------------------------------- */
+/* Device time in ms of the stages of the last eqvio_process_vision, measured with CUDA events on
+ * the handle's stream: [0] propagation, [1] preprocessing (gate + compaction, plus the device time of
+ * eqvio_augment_landmark_states calls made since the previous update), [2] correction -- the
+ * reference's LoopTimer labels (src/VIOFilter.cpp:196-236). */
+int eqvio_get_stage_ms(eqvio_filter* f, double ms[3]);
+/* Enable per-stage event timing (adds two event records per stage); off by default. */
+int eqvio_enable_stage_timing(eqvio_filter* f, int on);
+/* Number of kernel launches issued by this handle since creation. */
+long long eqvio_get_launch_count(const eqvio_filter* f);
+/* Per-kernel-class device time, measured with CUDA events recorded on the handle's stream around
+ * every launch of the class (adds two event records per launch; off by default, not meant to be on
+ * while whole-update throughput is timed).  Classes: */
+#define EQVIO_PROF_PROP_LL 0 /* Riccati propagation, landmark-landmark block (HBM-bound) */
+#define EQVIO_PROF_PANEL 1   /* Cholesky sweep: panel factor + triangular solve */
+#define EQVIO_PROF_TRAIL 2   /* Cholesky sweep: trailing update (FP64 tensor-core GEMM) */
+#define EQVIO_PROF_SYRK 3    /* Sigma downdate Sigma -= Y^T Y (FP64 tensor-core syrk) */
+#define EQVIO_PROF_CLASSES 4
+int eqvio_enable_kernel_profile(eqvio_filter* f, int on);
+/* Accumulated ms and launch counts per class since the last reset. */
+int eqvio_get_kernel_profile(eqvio_filter* f, int reset, double ms[EQVIO_PROF_CLASSES],
+                             long long launches[EQVIO_PROF_CLASSES]);
+/* Version / build info string (arch the kernels were compiled for). */
+const char* eqvio_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EQVIO_B200_H */

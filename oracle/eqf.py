@@ -1404,17 +1404,26 @@ class VIOFilter:
                 proposed.append(lmId)
         probabilisticOutliers = {}
         residual = measurement - yHat
-        for lmId in residual.getIds():
-            if lmId in absoluteOutliers:
-                continue
-            yT = residual.camCoordinates[lmId]
-            cov = fs.getOutputCovById(lmId, measurement.camCoordinates[lmId], measurement.cameraPtr)
-            det = cov[0, 0] * cov[1, 1] - cov[0, 1] * cov[1, 0]
-            inv = np.array([[cov[1, 1], -cov[0, 1]], [-cov[1, 0], cov[0, 0]]]) / det
-            err = float(yT @ inv @ yT)
-            if err > st.outlierThresholdProb:
-                probabilisticOutliers[lmId] = err
-                proposed.append(lmId)
+        cand = [lmId for lmId in residual.getIds() if lmId not in absoluteOutliers]
+        if cand:
+            # getOutputCovById for every candidate at once (VIO_eqf.cpp:196-211): C0i Sigma_ii C0i^T with the
+            # non-star C0i; same arithmetic as the per-id calls, vectorised over landmarks
+            order = {int(i): k for k, i in enumerate(fs.xi0.ids)}
+            idx = np.array([order[lmId] for lmId in cand], dtype=np.int64)
+            C0 = fs.coordinateSuite.outputMatrixCi(fs.xi0.p[idx], fs.X.Qq[idx], fs.X.Qa[idx], measurement.cameraPtr)
+            s0 = SENSOR_DIM + 3 * idx
+            rows = s0[:, None] + np.arange(3)[None, :]
+            lmCov = fs.Sigma[rows[:, :, None], rows[:, None, :]]
+            covs = C0 @ lmCov @ np.swapaxes(C0, -1, -2)
+            for k, lmId in enumerate(cand):
+                yT = residual.camCoordinates[lmId]
+                cov = covs[k]
+                det = cov[0, 0] * cov[1, 1] - cov[0, 1] * cov[1, 0]
+                inv = np.array([[cov[1, 1], -cov[0, 1]], [-cov[1, 0], cov[0, 0]]]) / det
+                err = float(yT @ inv @ yT)
+                if err > st.outlierThresholdProb:
+                    probabilisticOutliers[lmId] = err
+                    proposed.append(lmId)
 
         # absolute outliers outrank probabilistic ones; larger error first (:338-358)
         def key(lmId):

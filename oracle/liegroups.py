@@ -55,6 +55,15 @@ def norm(v):
     return np.sqrt(np.sum(np.asarray(v) ** 2, -1))
 
 
+def cross3(a, b):
+    """a x b on the last axis (same arithmetic as np.cross, without its axis-shuffling overhead)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    a0, a1, a2 = a[..., 0], a[..., 1], a[..., 2]
+    b0, b1, b2 = b[..., 0], b[..., 1], b[..., 2]
+    return np.stack([a1 * b2 - a2 * b1, a2 * b0 - a0 * b2, a0 * b1 - a1 * b0], -1)
+
+
 # ----------------------------------------------------------------------------
 # Eigen quaternion arithmetic, (w, x, y, z)
 # ----------------------------------------------------------------------------
@@ -87,9 +96,9 @@ def quat_rotate(q, v):
     """Eigen ``_transformVector``: v + w*(2 u x v) + u x (2 u x v)."""
     u = q[..., 1:]
     w = q[..., :1]
-    uv = np.cross(u, v)
+    uv = cross3(u, v)
     uv = uv + uv
-    return v + w * uv + np.cross(u, uv)
+    return v + w * uv + cross3(u, uv)
 
 
 def quat_to_matrix(q):
@@ -149,7 +158,7 @@ def quat_from_two_vectors(a, b):
     v0 = normalized(a)
     v1 = normalized(b)
     c = np.sum(v1 * v0, -1)
-    axis = np.cross(v0, v1)
+    axis = cross3(v0, v1)
     s = np.sqrt((1.0 + c) * 2.0)
     with np.errstate(divide="ignore", invalid="ignore"):
         invs = 1.0 / s

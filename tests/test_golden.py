@@ -1,0 +1,48 @@
+"""Golden fixtures: (CPU) the oracle reproduces its committed outputs bit-for-bit-ish (1e-12);
+(GPU) the CUDA path matches them within the parity tolerance."""
+import numpy as np
+import pytest
+
+from golden_utils import CASES, load
+from parity_utils import compare_states, run_gpu, run_oracle
+
+# BASELINE.json: pose / Sigma within 1e-6 relative Frobenius of the reference path.  The CUDA path
+# is fp64 end to end, so the tests hold it to a much tighter figure.
+TOL_GPU = 1e-9
+TOL_ORACLE = 1e-12
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_reproduces_golden(name):
+    stream, outs = load(name)
+    got = run_oracle(stream)
+    assert len(got) == len(outs)
+    for g, r in zip(got, outs):
+        e = compare_states(g, r)
+        assert e["ids_equal"]
+        assert e["sigma"] < TOL_ORACLE and e["state"] < TOL_ORACLE
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_dense_lazy_order_matches(name):
+    """The reference-order evaluation (K and S^-1 evaluated twice) gives the same numbers."""
+    stream, outs = load(name)
+    got = run_oracle(stream, dense_lazy=True)
+    for g, r in zip(got, outs):
+        e = compare_states(g, r)
+        assert e["ids_equal"] and e["sigma"] < TOL_ORACLE and e["state"] < TOL_ORACLE
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_matches_golden(name):
+    stream, outs = load(name)
+    got = run_gpu(stream)
+    assert len(got) == len(outs)
+    for k, (g, r) in enumerate(zip(got, outs)):
+        e = compare_states(g, r)
+        assert e["ids_equal"], f"update {k}: landmark ids differ: {g['ids']} vs {r['ids']}"
+        assert e["sigma"] < TOL_GPU, f"update {k}: Sigma rel-Frobenius {e['sigma']:.3e}"
+        assert e["state"] < TOL_GPU, f"update {k}: state rel-Frobenius {e['state']:.3e}"
+        assert e["time"] == 0.0
+        assert np.allclose(g["Sigma"], g["Sigma"].T, rtol=0, atol=1e-12 * np.abs(g["Sigma"]).max())

