@@ -110,7 +110,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.2)
 
     def result(self):
         if not self.samples:

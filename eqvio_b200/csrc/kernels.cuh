@@ -64,8 +64,7 @@ struct PrepArgs {
 // integration, then runs the sensor part of integrateObserverState for every IMU segment
 // (VIO_eqf.cpp:47-60, VIOGroup.cpp:190-271) and records what the landmark kernel needs.
 // ------------------------------------------------------------------------------------------------
-__global__ void sensor_prep_kernel(PrepArgs a) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+HD void sensor_prep_body(const PrepArgs& a) {
     SensorState xi0 = unpack_sensor(a.xi0s);
     GroupSensor X = unpack_group(a.Xs);
 
@@ -185,6 +184,11 @@ __global__ void sensor_prep_kernel(PrepArgs a) {
         X = Xn;
     }
     if (a.nsteps > 0) pack_group(X, a.Xs);
+}
+
+__global__ void sensor_prep_kernel(PrepArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    sensor_prep_body(a);
 }
 
 // ------------------------------------------------------------------------------------------------
