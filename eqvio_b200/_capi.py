@@ -92,6 +92,7 @@ SIGNATURES = {
     "eqvio_get_launch_count": (C.c_longlong, [_H]),
     "eqvio_enable_kernel_profile": (_I, [_H, _I]),
     "eqvio_get_kernel_profile": (_I, [_H, _I, _PD, C.POINTER(C.c_longlong)]),
+    "eqvio_set_tuning": (_I, [_H, _I, _I]),
     "eqvio_build_info": (C.c_char_p, []),
 }
 

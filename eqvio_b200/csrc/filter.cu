@@ -72,6 +72,9 @@ struct eqvio_filter {
     int yCap = 0;
     double *d_rows = nullptr, *d_uv = nullptr, *d_Z = nullptr, *d_Lout = nullptr;
     size_t zElems = 0;
+    double *d_Gamma2 = nullptr, *d_ytilde = nullptr;
+    int corrMode = 0;    // 0: sequential chunks (default), 1: batch Cholesky sweep over Z
+    int chunkLm = 32;    // landmarks per chunk (<= CH_R / 2)
     double *d_Cblk = nullptr, *d_Gamma = nullptr, *d_gate = nullptr, *d_y = nullptr, *d_newP = nullptr, *d_out = nullptr;
     int *d_measIdx = nullptr, *d_lmOf = nullptr, *d_map = nullptr, *d_newIds = nullptr, *d_status = nullptr;
 
@@ -253,7 +256,7 @@ void initial_diag(const eqvio_settings& s, int N, bool depthVariance, std::vecto
 int alloc_device(eqvio_filter* f) {
     const int cap = f->cap;
     const int dimpMax = dimp_of(cap);
-    f->ld = (dimpMax + 7) & ~7;
+    f->ld = (dimpMax + 63) & ~63;  // whole 64x64 tiles are moved by the downdate kernel
     const size_t sigElems = (size_t)f->ld * f->ld;
     for (int k = 0; k < 2; ++k) {
         CUDA_TRY(f, cudaMalloc(&f->Sig[k], sigElems * sizeof(double)));
@@ -273,11 +276,13 @@ int alloc_device(eqvio_filter* f) {
     CUDA_TRY(f, cudaMalloc(&f->d_uv, c1 * UV_STRIDE * sizeof(double)));
     const size_t mMax = 2 * c1;
     const size_t ldzMax = (mMax + dimpMax + 1 + 7) & ~size_t(7);
-    f->zElems = std::max(ldzMax * mMax, sigElems);
+    f->zElems = std::max(std::max(ldzMax * mMax, sigElems), (size_t)(f->ld / YB_T) * YB_TILE);
     CUDA_TRY(f, cudaMalloc(&f->d_Z, f->zElems * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Lout, (mMax + NB) * NB * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Cblk, c1 * 6 * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Gamma, (size_t)(dimpMax + 8) * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&f->d_Gamma2, (size_t)(dimpMax + 8) * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&f->d_ytilde, 2 * c1 * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_gate, c1 * 3 * sizeof(double)));
     f->yCap = (int)c1;
     CUDA_TRY(f, cudaMalloc(&f->d_y, c1 * 2 * sizeof(double)));
@@ -667,13 +672,41 @@ int vision_phase_b(eqvio_filter* f) {
     if ((rc = upload(f, f->d_lmOf, lmOf.data(), nm)) != EQVIO_OK) return rc;
     if ((rc = upload(f, f->d_y, ky.data(), ky.size())) != EQVIO_OK) return rc;
     CUDA_TRY(f, cudaMemsetAsync(f->d_status, 0, (1 + (size_t)Nn) * sizeof(int), f->stream));
+    const double r2 = s.measurementNoise * s.measurementNoise;
+    const double* gammaFinal = f->d_Gamma;
+    if (f->corrMode == 0) {
+        // sequential chunks: see chunk_factor_kernel
+        const int ldy = (dimp + 63) & ~63;
+        const int T = ldy / DD_T;
+        double* Y = f->d_Z;
+        meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, P.cam, s.coordinateChoice,
+                                                          s.useEquivariantOutput ? 1 : 0, f->d_Cblk, f->d_ytilde, 1, 0);
+        LAUNCH_CHECK(f, "meas_kernel");
+        double* gin = f->d_Gamma;
+        double* gout = f->d_Gamma2;
+        CUDA_TRY(f, cudaMemsetAsync(gin, 0, (size_t)dimp * sizeof(double), f->stream));
+        const int bcMax = std::max(1, std::min(f->chunkLm, CH_R / 2));
+        for (int j0 = 0; j0 < nm; j0 += bcMax) {
+            const int bc = std::min(bcMax, nm - j0);
+            int pk = prof_begin(f, PROF_PANEL);
+            chunk_factor_kernel<<<ldy / CH_COLS, CH_THREADS, sizeof(ChunkSmem), f->stream>>>(
+                f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Y, f->d_status);
+            prof_end(f, pk);
+            LAUNCH_CHECK(f, "chunk_factor_kernel");
+            int sk = prof_begin(f, PROF_SYRK);
+            chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->ld, Y);
+            prof_end(f, sk);
+            LAUNCH_CHECK(f, "chunk_downdate_kernel");
+            std::swap(gin, gout);
+        }
+        gammaFinal = gin;
+    } else {
     meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, P.cam, s.coordinateChoice,
                                                       s.useEquivariantOutput ? 1 : 0, f->d_Cblk, Z, ldz, m + dimp);
     LAUNCH_CHECK(f, "meas_kernel");
     zbuild_kernel<<<dim3(cdiv(dimp, 256), nm), 256, 0, f->stream>>>(f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, Z, ldz, m);
     LAUNCH_CHECK(f, "zbuild_kernel");
-    sbuild_kernel<<<dim3(cdiv(m, 128), m), 128, 0, f->stream>>>(f->d_lmOf, f->d_Cblk, Z, ldz, m,
-                                                                s.measurementNoise * s.measurementNoise);
+    sbuild_kernel<<<dim3(cdiv(m, 128), m), 128, 0, f->stream>>>(f->d_lmOf, f->d_Cblk, Z, ldz, m, r2);
     LAUNCH_CHECK(f, "sbuild_kernel");
     for (int k = 0; k < m; k += NB) {
         const int nbk = std::min(NB, m - k);
@@ -702,7 +735,8 @@ int vision_phase_b(eqvio_filter* f) {
     }
     gamma_kernel<<<cdiv(dimp, 128), 128, m * sizeof(double), f->stream>>>(Z, ldz, m, dimp, f->d_Gamma);
     LAUNCH_CHECK(f, "gamma_kernel");
-    lift_kernel<<<cdiv(std::max(Nn, 1), 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, Nn, f->d_xi0s, f->d_Xs, f->d_Gamma,
+    }
+    lift_kernel<<<cdiv(std::max(Nn, 1), 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, Nn, f->d_xi0s, f->d_Xs, gammaFinal,
                                                                    s.useDiscreteInnovationLift ? 1 : 0, s.coordinateChoice,
                                                                    f->d_status, f->d_status + 1);
     LAUNCH_CHECK(f, "lift_kernel");
@@ -777,6 +811,12 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
     e = cudaSetDevice(device);
     if (e != cudaSuccess) {
         g_createError = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return EQVIO_ERR_CUDA;
+    }
+    e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChunkSmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM);
+    if (e != cudaSuccess) {
+        g_createError = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
         return EQVIO_ERR_CUDA;
     }
     eqvio_filter* f = new eqvio_filter();
@@ -998,6 +1038,8 @@ void eqvio_destroy(eqvio_filter* f) {
     cudaFree(f->d_Lout);
     cudaFree(f->d_Cblk);
     cudaFree(f->d_Gamma);
+    cudaFree(f->d_Gamma2);
+    cudaFree(f->d_ytilde);
     cudaFree(f->d_gate);
     cudaFree(f->d_y);
     cudaFree(f->d_newP);
@@ -1326,6 +1368,22 @@ int eqvio_get_kernel_profile(eqvio_filter* f, int reset, double ms[EQVIO_PROF_CL
         }
     }
     return EQVIO_OK;
+}
+
+int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
+    if (!f) return EQVIO_ERR_INVALID_ARG;
+    switch (key) {
+        case EQVIO_TUNE_CORRECTION:
+            if (value != 0 && value != 1) return EQVIO_ERR_INVALID_ARG;
+            f->corrMode = value;
+            return EQVIO_OK;
+        case EQVIO_TUNE_CHUNK_LANDMARKS:
+            if (value < 1 || value > CH_R / 2) return EQVIO_ERR_INVALID_ARG;
+            f->chunkLm = value;
+            return EQVIO_OK;
+        default:
+            return EQVIO_ERR_INVALID_ARG;
+    }
 }
 
 const char* eqvio_build_info(void) { return "eqvio_b200 sm_100a fp64 (CUDA " EQVIO_STR(__CUDACC_VER_MAJOR__) "." EQVIO_STR(__CUDACC_VER_MINOR__) ")"; }

@@ -775,22 +775,475 @@ __global__ void __launch_bounds__(128)
         }
     }
     const bool offdiag = MIRROR && (i0 != j0);
+    // epilogue: all loads of the C tile are issued before the first store (loads and stores through the
+    // same pointer may alias, so interleaving them serialises one L2 round trip per element)
+    double cv[4][4][2];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            int r = i0 + wm + a * 8 + (lane >> 2);
-            int c = j0 + wn + b * 8 + (lane & 3) * 2;
+            const int r = i0 + wm + a * 8 + (lane >> 2);
+            const int c = j0 + wn + b * 8 + (lane & 3) * 2;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) cv[a][b][e] = (r < M && c + e < N) ? C[(size_t)(c + e) * ldc + r] : 0.0;
+        }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int r = i0 + wm + a * 8 + (lane >> 2);
+            const int c = j0 + wn + b * 8 + (lane & 3) * 2;
             if (r < M) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
                     if (c + e < N) {
-                        double v = C[(size_t)(c + e) * ldc + r] - acc[a][b][e];
+                        const double v = cv[a][b][e] - acc[a][b][e];
                         C[(size_t)(c + e) * ldc + r] = v;
                         if (offdiag) C[(size_t)r * ldc + c + e] = v;
                     }
             }
         }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Correction, sequential-chunk form.  R = sigma^2 I is diagonal, so with C and ytilde fixed at the
+// prior the batch update  Sigma - Sigma C^T (C Sigma C^T + R)^-1 C Sigma  equals the composition of
+// the updates of consecutive row chunks of C (exact arithmetic).  C has one 2x3 block per measured
+// landmark and no sensor columns (EqFMatrices.cpp:57,74-76), so for a chunk c of bc landmarks
+//   W_c = C_c Sigma   (2bc x dim)  is a 2x3-weighted gather of the CURRENT Sigma,
+//   S_c = W_c[:, L_c] C_c^T + sigma^2 I  only needs the (3bc)^2 block Sigma[L_c, L_c],
+// and the m^3/3 + m^2 dim flops of factoring the full S and solving for the full W disappear:
+//   L_c L_c^T = S_c,  Y_c = L_c^-1 W_c,  z_c = L_c^-1 (ytilde_c - C_c Gamma),
+//   Gamma += Y_c^T z_c,   Sigma -= Y_c^T Y_c                      (m dim^2 flops in total).
+//
+// chunk_factor_kernel: every CTA builds and factors S_c redundantly in shared memory (it is at most
+// 64 x 64), then each thread owns one state column s of W_c: gathers it, forward-substitutes it in
+// registers and writes Y_c[:, s]; warp 4 / lane 0 does the same for the residual column.  Grid =
+// ceil(dimp / 128) CTAs of 160 threads.  Y is R x ldy, row k contiguous in s.
+// ------------------------------------------------------------------------------------------------
+constexpr int CH_R = 64;        // max rows of a chunk (32 landmarks)
+constexpr int CH_COLS = 32;     // state columns per CTA (one warp substitutes, the residual rides on warp 1)
+constexpr int CH_THREADS = 160;
+constexpr int CH_WARPS = CH_THREADS / 32;
+constexpr int CH_T = 4;                                   // register tile edge of the elimination
+constexpr int CH_NT = CH_R / CH_T;                        // 16 tile rows
+constexpr int CH_TILES = CH_NT * (CH_NT + 1) / 2;         // 136 lower tiles, one thread each
+constexpr int CH_LDL = CH_R + 2;                          // row stride of sL (16-byte multiple)
+constexpr int CH_SB = 16;                                 // substitution block
+// Y is stored tile-blocked for the downdate kernel: tile t = 64 consecutive state columns, stored as 64 rows
+// (k) of 68 doubles (the last 4 are padding) so that a whole panel is ONE contiguous bulk copy that lands in
+// shared memory with a bank-conflict-free row stride.
+constexpr int YB_T = 64, YB_LD = 68;
+constexpr size_t YB_TILE = (size_t)YB_T * YB_LD;
+__host__ __device__ __forceinline__ size_t yb_index(int k, int s) { return (size_t)(s >> 6) * YB_TILE + (size_t)k * YB_LD + (s & 63); }
+
+struct ChunkSmem {
+    double L[CH_R][CH_LDL];       // L[k][c] = entry (row c, col k), c >= k: column k contiguous in c
+    double X[CH_R][CH_COLS + 1];  // X[k][lane]: right-hand sides being substituted (+1: the residual column)
+    double Pn[CH_NT][CH_T][CH_T];  // finished panel of the current block column: Pn[I][r][j]
+    double D[2][CH_T][CH_T];       // diagonal tile of the current block column (unscaled), double-buffered
+    double Dc[2][CH_T];            // reciprocal pivots
+    double C[CH_R / 2][6];
+    double Inv[CH_R];
+    double Z[CH_R];
+    int Idx[CH_R / 2];
+};
+
+// reciprocal to <= 1 ulp: hardware approximation + two Newton steps (a correctly rounded division is
+// ~3x longer and sits on the critical path of every elimination step)
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+// index t of a lower-triangular enumeration (row-major: (0,0),(1,0),(1,1),(2,0),...) -> (row, col)
+__device__ __forceinline__ void tri_decode(int t, int& row, int& col) {
+    int r = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((r + 1) * (r + 2) / 2 <= t) ++r;
+    while (r * (r + 1) / 2 > t) --r;
+    row = r;
+    col = t - r * (r + 1) / 2;
+}
+
+__global__ void __launch_bounds__(CH_THREADS)
+    chunk_factor_kernel(const double* __restrict__ Sig, int ld, int dimp, const int* __restrict__ lmOf,
+                        const double* __restrict__ Cblk, const double* __restrict__ ytilde, int j0, int bc, double r2,
+                        const double* __restrict__ GammaIn, double* __restrict__ GammaOut, double* __restrict__ Y,
+                        int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char chunk_smem_raw[];
+    ChunkSmem& sm = *reinterpret_cast<ChunkSmem*>(chunk_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rc = 2 * bc;
+    for (int t = tid; t < bc * 6; t += CH_THREADS) sm.C[t / 6][t % 6] = Cblk[6 * (size_t)j0 + t];
+    for (int t = tid; t < bc; t += CH_THREADS) sm.Idx[t] = SOFF + 3 * lmOf[j0 + t];
+    for (int t = tid; t < CH_R * CH_LDL; t += CH_THREADS) (&sm.L[0][0])[t] = 0.0;
+    for (int t = tid; t < CH_R * (CH_COLS + 1); t += CH_THREADS) (&sm.X[0][0])[t] = 0.0;
+    __syncthreads();
+
+    // ---- gathers: all global loads of a thread are issued before their first use (one L2 round trip) ----
+    // S_c = C_c Sigma[L_c, L_c] C_c^T + r2 I, lower triangle by landmark pairs (j >= k), <= 4 pairs per thread
+    {
+        const int npairs = bc * (bc + 1) / 2;
+        double P[4][9];
+        int pj[4], pk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = tid + u * CH_THREADS;
+            pj[u] = pk[u] = 0;
+            if (t < npairs) {
+                tri_decode(t, pj[u], pk[u]);
+                const double* sp = Sig + (size_t)sm.Idx[pk[u]] * ld + sm.Idx[pj[u]];  // Sigma[rows of j, cols of k]
+#pragma unroll
+                for (int b = 0; b < 3; ++b)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) P[u][a * 3 + b] = sp[(size_t)b * ld + a];
+            }
+        }
+        // W_c columns: warp w takes landmarks w, w+5, ... for state column s = 32 blockIdx + lane
+        const int s = blockIdx.x * CH_COLS + lane;
+        double w0[7], w1[7], w2[7];
+#pragma unroll
+        for (int u = 0; u < 7; ++u) {
+            const int j = warp + u * CH_WARPS;
+            w0[u] = w1[u] = w2[u] = 0.0;
+            if (j < bc && s < dimp) {
+                const double* sp = Sig + (size_t)sm.Idx[j] * ld + s;  // Sigma[s, cols of j] (symmetric storage)
+                w0[u] = sp[0];
+                w1[u] = sp[ld];
+                w2[u] = sp[2 * (size_t)ld];
+            }
+        }
+        // residual: lane j of warp 1 takes landmark j
+        double g0 = 0, g1 = 0, g2 = 0, y0 = 0, y1 = 0;
+        if (warp == 1 && lane < bc) {
+            const int g = sm.Idx[lane];
+            g0 = GammaIn[g];
+            g1 = GammaIn[g + 1];
+            g2 = GammaIn[g + 2];
+            y0 = ytilde[2 * (j0 + lane)];
+            y1 = ytilde[2 * (j0 + lane) + 1];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = tid + u * CH_THREADS;
+            if (t < npairs) {
+                const int j = pj[u], k = pk[u];
+                double T[6];
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b)
+                        T[e * 3 + b] = sm.C[j][3 * e] * P[u][b] + sm.C[j][3 * e + 1] * P[u][3 + b] + sm.C[j][3 * e + 2] * P[u][6 + b];
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+#pragma unroll
+                    for (int f = 0; f < 2; ++f) {
+                        double v = T[e * 3] * sm.C[k][3 * f] + T[e * 3 + 1] * sm.C[k][3 * f + 1] + T[e * 3 + 2] * sm.C[k][3 * f + 2];
+                        const int p = 2 * j + e, q = 2 * k + f;
+                        if (p == q) v += r2;
+                        if (p >= q) sm.L[q][p] = v;
+                    }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 7; ++u) {
+            const int j = warp + u * CH_WARPS;
+            if (j < bc) {
+                sm.X[2 * j][lane] = sm.C[j][0] * w0[u] + sm.C[j][1] * w1[u] + sm.C[j][2] * w2[u];
+                sm.X[2 * j + 1][lane] = sm.C[j][3] * w0[u] + sm.C[j][4] * w1[u] + sm.C[j][5] * w2[u];
+            }
+        }
+        if (warp == 1 && lane < bc) {
+            sm.X[2 * lane][CH_COLS] = y0 - (sm.C[lane][0] * g0 + sm.C[lane][1] * g1 + sm.C[lane][2] * g2);
+            sm.X[2 * lane + 1][CH_COLS] = y1 - (sm.C[lane][3] * g0 + sm.C[lane][4] * g1 + sm.C[lane][5] * g2);
+        }
+        for (int t = rc + tid; t < CH_R; t += CH_THREADS) sm.L[t][t] = 1.0;  // identity padding of a short last chunk
+    }
+    __syncthreads();
+
+    // ---- blocked right-looking elimination with unscaled columns (after it, column j holds v_ij = L_ij L_jj).
+    // Thread t < 136 keeps one 4x4 tile (TI >= TK) of the lower triangle in registers throughout.  Per block
+    // column J: the diagonal owner eliminates inside its tile and publishes it, the panel owners (TI > J, TK = J)
+    // finish their four columns and publish them, everybody else applies the rank-4 update: 2 barriers per 4 columns.
+    int TI = 0, TK = 0;
+    tri_decode(tid < CH_TILES ? tid : 0, TI, TK);
+    const bool owner = tid < CH_TILES;
+    double a[CH_T][CH_T];
+    if (owner) {
+#pragma unroll
+        for (int r = 0; r < CH_T; ++r)
+#pragma unroll
+            for (int c = 0; c < CH_T; ++c) a[r][c] = sm.L[CH_T * TK + c][CH_T * TI + r];  // upper entries of diagonal tiles: 0
+    }
+    const int nJ = (rc + CH_T - 1) / CH_T;
+    for (int J = 0; J < nJ; ++J) {
+        const int buf = J & 1;
+        if (owner && TI == J && TK == J) {
+#pragma unroll
+            for (int j = 0; j < CH_T; ++j) {
+                const double c = fast_rcp(a[j][j]);
+                sm.Dc[buf][j] = c;
+#pragma unroll
+                for (int i = j + 1; i < CH_T; ++i) {
+                    const double li = a[i][j] * c;
+#pragma unroll
+                    for (int k = j + 1; k <= i; ++k) a[i][k] -= li * a[k][j];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < CH_T; ++i)
+#pragma unroll
+                for (int j = 0; j < CH_T; ++j) sm.D[buf][i][j] = a[i][j];
+        }
+        __syncthreads();
+        if (owner && TK == J && TI > J) {
+            double c[CH_T], d[CH_T][CH_T];
+#pragma unroll
+            for (int j = 0; j < CH_T; ++j) c[j] = sm.Dc[buf][j];
+#pragma unroll
+            for (int i = 0; i < CH_T; ++i)
+#pragma unroll
+                for (int j = 0; j < CH_T; ++j) d[i][j] = sm.D[buf][i][j];
+#pragma unroll
+            for (int j = 0; j < CH_T; ++j)
+#pragma unroll
+                for (int k = j + 1; k < CH_T; ++k)
+#pragma unroll
+                    for (int r = 0; r < CH_T; ++r) a[r][k] -= (a[r][j] * c[j]) * d[k][j];
+#pragma unroll
+            for (int r = 0; r < CH_T; ++r)
+#pragma unroll
+                for (int j = 0; j < CH_T; ++j) sm.Pn[TI][r][j] = a[r][j];
+        }
+        __syncthreads();
+        if (owner && TK > J) {
+            double li[CH_T][CH_T], pk[CH_T][CH_T];
+#pragma unroll
+            for (int j = 0; j < CH_T; ++j) {
+                const double c = sm.Dc[buf][j];
+#pragma unroll
+                for (int r = 0; r < CH_T; ++r) li[r][j] = sm.Pn[TI][r][j] * c;
+            }
+#pragma unroll
+            for (int cc = 0; cc < CH_T; ++cc)
+#pragma unroll
+                for (int j = 0; j < CH_T; ++j) pk[cc][j] = sm.Pn[TK][cc][j];
+#pragma unroll
+            for (int r = 0; r < CH_T; ++r)
+#pragma unroll
+                for (int cc = 0; cc < CH_T; ++cc) {
+                    double acc = a[r][cc];
+#pragma unroll
+                    for (int j = 0; j < CH_T; ++j) acc -= li[r][j] * pk[cc][j];
+                    a[r][cc] = acc;
+                }
+        }
+    }
+    // publish the diagonal, then the scaled factor
+    if (owner && TI == TK) {
+#pragma unroll
+        for (int c = 0; c < CH_T; ++c) {
+            const double piv = a[c][c];
+            const int k = CH_T * TK + c;
+            if (!(piv > 0.0)) {
+                if (blockIdx.x == 0) atomicOr(status, 1);
+                sm.Inv[k] = 1.0;
+            } else {
+                sm.Inv[k] = 1.0 / sqrt(piv);
+            }
+        }
+    }
+    __syncthreads();
+    if (owner) {
+#pragma unroll
+        for (int c = 0; c < CH_T; ++c) {
+            const double sc = sm.Inv[CH_T * TK + c];
+#pragma unroll
+            for (int r = 0; r < CH_T; ++r) sm.L[CH_T * TK + c][CH_T * TI + r] = a[r][c] * sc;  // L[row][col] = v / L_colcol
+        }
+    }
+    __syncthreads();
+
+    // ---- blocked forward substitution L x = w: x lives in shared memory, 16-row blocks in registers ----
+    const bool isResid = tid == CH_COLS;
+    const int xcol = isResid ? CH_COLS : lane;
+    if (warp == 0 || isResid) {
+#pragma unroll 1
+        for (int kb = 0; kb < CH_R / CH_SB; ++kb) {
+            const int k0 = kb * CH_SB;
+            double xb[CH_SB];
+#pragma unroll
+            for (int q = 0; q < CH_SB; ++q) xb[q] = sm.X[k0 + q][xcol];
+#pragma unroll
+            for (int q = 0; q < CH_SB; ++q) {
+                const double xq = xb[q] * sm.Inv[k0 + q];
+                xb[q] = xq;
+#pragma unroll
+                for (int c = q + 1; c < CH_SB; ++c) xb[c] -= sm.L[k0 + q][k0 + c] * xq;
+            }
+#pragma unroll
+            for (int q = 0; q < CH_SB; ++q) sm.X[k0 + q][xcol] = xb[q];
+#pragma unroll 1
+            for (int cb = kb + 1; cb < CH_R / CH_SB; ++cb) {
+                const int c0 = cb * CH_SB;
+                double xc[CH_SB];
+#pragma unroll
+                for (int c = 0; c < CH_SB; ++c) xc[c] = sm.X[c0 + c][xcol];
+#pragma unroll
+                for (int q = 0; q < CH_SB; ++q) {
+                    const double2* lp = reinterpret_cast<const double2*>(&sm.L[k0 + q][c0]);
+#pragma unroll
+                    for (int c = 0; c < CH_SB; c += 2) {
+                        const double2 l2 = lp[c / 2];
+                        xc[c] -= l2.x * xb[q];
+                        xc[c + 1] -= l2.y * xb[q];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < CH_SB; ++c) sm.X[c0 + c][xcol] = xc[c];
+            }
+        }
+    }
+    if (isResid) {
+        for (int k = 0; k < CH_R; ++k) sm.Z[k] = sm.X[k][CH_COLS];
+    }
+    __syncthreads();
+    // ---- Y rows (all CH_R of them: zero beyond rc and for the pad columns s >= dimp) and the running correction
+    if (warp == 0) {
+        const int s = blockIdx.x * CH_COLS + lane;
+        double g = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < CH_R; ++k) {
+            const double v = sm.X[k][lane];
+            Y[yb_index(k, s)] = v;
+            g += v * sm.Z[k];
+        }
+        if (s < dimp) GammaOut[s] = GammaIn[s] + g;  // ping-pong: other CTAs may still be reading GammaIn
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sigma <- Sigma - Y^T Y for one chunk (K = 64 rows of Y), one 64x64 tile of Sigma per CTA, tiles on
+// or below the diagonal; the transposed tile is written too so that Sigma stays stored in full.
+// The two Y panels arrive through the TMA unit as ONE bulk copy each (cp.async.bulk, SASS UBLKCP,
+// 34 KB, mbarrier-signalled) straight into their padded shared-memory layout; the Sigma tile is read and
+// written with 16-byte coalesced loads/stores (one 512-byte column per warp instruction), the mirror
+// tile goes through a shared-memory transpose.  Math: mma.sync.m8n8k4.f64 (DMMA), 4 warps x 32x32.
+// Sigma must be allocated with ld and row count padded to a multiple of 64 (whole tiles are moved).
+// ------------------------------------------------------------------------------------------------
+constexpr int DD_T = 64, DD_LD = YB_LD, DD_THREADS = 128;
+constexpr int DD_SMEM = 3 * DD_T * DD_LD * 8 + 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(DD_THREADS)
+    chunk_downdate_kernel(double* __restrict__ Sig, int ld, const double* __restrict__ Y) {
+    int ti, tj;
+    tri_decode(blockIdx.x, ti, tj);  // lower-triangular tile index -> (ti, tj), ti >= tj
+    extern __shared__ __align__(16) unsigned char dd_smem_raw[];
+    double(*sA)[DD_LD] = reinterpret_cast<double(*)[DD_LD]>(dd_smem_raw);
+    double(*sB)[DD_LD] = sA + DD_T;
+    double(*sC)[DD_LD] = sB + DD_T;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dd_smem_raw + 3 * DD_T * DD_LD * 8);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i0 = ti * DD_T, j0 = tj * DD_T;
+    const bool diag = ti == tj;
+    constexpr uint32_t PANEL_BYTES = DD_T * DD_LD * 8;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar, diag ? PANEL_BYTES : 2 * PANEL_BYTES);
+        bulk_g2s(&sA[0][0], Y + (size_t)ti * YB_TILE, PANEL_BYTES, bar);
+        if (!diag) bulk_g2s(&sB[0][0], Y + (size_t)tj * YB_TILE, PANEL_BYTES, bar);
+    }
+    // Sigma tile: column j0+c, rows i0..i0+63 -> sC[c][0..63]; 32 lanes x 16 bytes = one column per instruction
+    double2 cv[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        const int c = warp * 16 + u;
+        cv[u] = *reinterpret_cast<const double2*>(Sig + (size_t)(j0 + c) * ld + i0 + 2 * lane);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        const int c = warp * 16 + u;
+        *reinterpret_cast<double2*>(&sC[c][2 * lane]) = cv[u];
+    }
+    __syncthreads();  // sC complete, barrier initialised for everyone
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    mbar_wait(bar, 0);
+    double(*sBB)[DD_LD] = diag ? sA : sB;
+#pragma unroll 4
+    for (int k4 = 0; k4 < DD_T; k4 += 4) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) af[a] = sA[k4 + (lane & 3)][wm + a * 8 + (lane >> 2)];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bf[b] = sBB[k4 + (lane & 3)][wn + b * 8 + (lane >> 2)];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+    __syncthreads();  // every warp is done reading the panels: sA can take the transposed tile
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int r = wm + a * 8 + (lane >> 2);
+            const int c = wn + b * 8 + (lane & 3) * 2;
+            const double v0 = sC[c][r] - acc[a][b][0];
+            const double v1 = sC[c + 1][r] - acc[a][b][1];
+            sC[c][r] = v0;
+            sC[c + 1][r] = v1;
+            if (!diag) {
+                sA[r][c] = v0;  // transposed tile
+                sA[r][c + 1] = v1;
+            }
+        }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        const int c = warp * 16 + u;
+        *reinterpret_cast<double2*>(Sig + (size_t)(j0 + c) * ld + i0 + 2 * lane) = *reinterpret_cast<const double2*>(&sC[c][2 * lane]);
+    }
+    if (!diag) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int c = warp * 16 + u;  // column i0+c of the mirror tile, rows j0..j0+63
+            *reinterpret_cast<double2*>(Sig + (size_t)(i0 + c) * ld + j0 + 2 * lane) = *reinterpret_cast<const double2*>(&sA[c][2 * lane]);
+        }
+    }
 }
 
 // Gamma = Y^T (L^-1 ytilde):  Gamma[r] = sum_k Z[m + r, k] * Z[yrow, k].  One thread per r.

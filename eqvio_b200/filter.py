@@ -333,6 +333,13 @@ class VIOFilter:
         self._check(lib.eqvio_get_stage_ms(self._h, _pd(ms)))
         return dict(propagation=ms[0], preprocessing=ms[1], correction=ms[2])
 
+    def setTuning(self, correction=None, chunkLandmarks=None):
+        """Evaluation-order knobs (eqvio_set_tuning): correction 0 = sequential chunks, 1 = batch sweep."""
+        if correction is not None:
+            self._check(lib.eqvio_set_tuning(self._h, 0, int(correction)))
+        if chunkLandmarks is not None:
+            self._check(lib.eqvio_set_tuning(self._h, 1, int(chunkLandmarks)))
+
     def launchCount(self):
         return int(lib.eqvio_get_launch_count(self._h))
 

@@ -170,6 +170,13 @@ int eqvio_enable_kernel_profile(eqvio_filter* f, int on);
 /* Accumulated ms and launch counts per class since the last reset. */
 int eqvio_get_kernel_profile(eqvio_filter* f, int reset, double ms[EQVIO_PROF_CLASSES],
                              long long launches[EQVIO_PROF_CLASSES]);
+/* Evaluation-order knobs of the correction (results agree to rounding; tests run both).
+ *   EQVIO_TUNE_CORRECTION: 0 = sequential landmark chunks exploiting C's block sparsity (default),
+ *                          1 = batch form: Cholesky sweep over [S; W^T; ytilde^T], then Sigma -= Y^T Y.
+ *   EQVIO_TUNE_CHUNK_LANDMARKS: landmarks per chunk in mode 0 (1..32, default 32). */
+#define EQVIO_TUNE_CORRECTION 0
+#define EQVIO_TUNE_CHUNK_LANDMARKS 1
+int eqvio_set_tuning(eqvio_filter* f, int key, int value);
 /* Version / build info string (arch the kernels were compiled for). */
 const char* eqvio_build_info(void);
 

@@ -73,8 +73,10 @@ def replay_gpu(flt, cam, frames, on_update=None):
             on_update(k, flt)
 
 
-def run_gpu(stream, capacity=None):
+def run_gpu(stream, capacity=None, tuning=None):
     flt, cam = gpu_filter(stream, capacity)
+    if tuning:
+        flt.setTuning(**tuning)
     out = []
     replay_gpu(flt, cam, stream["frames"], lambda k, f: out.append(snapshot_gpu(f)))
     flt.close()

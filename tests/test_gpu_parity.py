@@ -35,6 +35,15 @@ def test_sequence_matches_oracle(N, coord):
     _check(run_gpu(stream), run_oracle(stream))
 
 
+@pytest.mark.parametrize("tuning", [dict(correction=1), dict(correction=0, chunkLandmarks=5), dict(correction=0, chunkLandmarks=16),
+                                    dict(correction=0, chunkLandmarks=1)])
+def test_correction_evaluation_orders_agree(tuning):
+    """Batch Cholesky sweep vs sequential chunks of any size: same result to rounding, both match the oracle."""
+    stream = make_stream(N=40, frames=6, coord=1)
+    ref = run_oracle(stream)
+    _check(run_gpu(stream, tuning=tuning), ref)
+
+
 @pytest.mark.parametrize("coord", [0, 1])
 def test_continuous_lifts(coord):
     """useDiscreteVelocityLift = useDiscreteInnovationLift = false (the EuRoC config's innovation lift)."""
@@ -125,8 +134,9 @@ def test_radtan_camera():
 def test_config2_n256():
     """BASELINE configs[1]: N=256 landmarks, fp64 Sigma, correctness vs the CPU reference path."""
     stream = make_stream(N=256, frames=4, coord=0)
-    worst = _check(run_gpu(stream), run_oracle(stream, dense_lazy=True))
-    assert worst < 1e-9
+    ref = run_oracle(stream, dense_lazy=True)
+    assert _check(run_gpu(stream), ref) < 1e-9
+    assert _check(run_gpu(stream, tuning=dict(correction=1)), ref) < 1e-9
 
 
 def test_silent_returns_and_errors():
