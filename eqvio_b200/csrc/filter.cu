@@ -64,7 +64,11 @@ struct eqvio_filter {
     double* lm[2] = {nullptr, nullptr};
     int* dids[2] = {nullptr, nullptr};
     int lmcur = 0;
-    double *d_xi0s = nullptr, *d_Xs = nullptr;
+    double* d_xi0s = nullptr;
+    double* d_Xs[2] = {nullptr, nullptr};  // X sensor part, ping-pong across the observer integration
+    int xcur = 0;
+    cudaStream_t stream2 = nullptr;  // observer chain of the propagation runs beside the Riccati chain
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     RiccatiCtx* d_ctx = nullptr;
     ObsStep* d_steps = nullptr;
     double* d_imu = nullptr;
@@ -266,7 +270,11 @@ int alloc_device(eqvio_filter* f) {
         CUDA_TRY(f, cudaMalloc(&f->dids[k], std::max(cap, 1) * sizeof(int)));
     }
     CUDA_TRY(f, cudaMalloc(&f->d_xi0s, 23 * sizeof(double)));
-    CUDA_TRY(f, cudaMalloc(&f->d_Xs, 23 * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&f->d_Xs[0], 23 * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&f->d_Xs[1], 23 * sizeof(double)));
+    CUDA_TRY(f, cudaStreamCreateWithFlags(&f->stream2, cudaStreamNonBlocking));
+    CUDA_TRY(f, cudaEventCreateWithFlags(&f->evFork, cudaEventDisableTiming));
+    CUDA_TRY(f, cudaEventCreateWithFlags(&f->evJoin, cudaEventDisableTiming));
     CUDA_TRY(f, cudaMalloc(&f->d_ctx, sizeof(RiccatiCtx)));
     f->maxSteps = 64;
     CUDA_TRY(f, cudaMalloc(&f->d_steps, f->maxSteps * sizeof(ObsStep)));
@@ -317,7 +325,7 @@ int reset_state(eqvio_filter* f, const double sensor[23], int n, const int* ids,
     if ((rc = upload(f, f->d_xi0s, sensor, 23)) != EQVIO_OK) return rc;
     double gid[23];
     group_identity_flat(gid);
-    if ((rc = upload(f, f->d_Xs, gid, 23)) != EQVIO_OK) return rc;
+    if ((rc = upload(f, f->d_Xs[f->xcur], gid, 23)) != EQVIO_OK) return rc;
     f->ids.assign(ids, ids + n);
     if (n > 0) {
         std::vector<double> soa((size_t)LM_FIELDS * n);
@@ -435,57 +443,63 @@ int integrate_up_to_time(eqvio_filter* f, double newTime, int* advanced) {
     int rc;
     if ((rc = upload(f, f->d_imu, imu.data(), imu.size())) != EQVIO_OK) return rc;
 
-    const int CH = 256;  // IMU segments per launch (ObsStep staging in shared memory)
-    for (int s0 = 0; s0 < n; s0 += CH) {
-        const int ns = std::min(CH, n - s0);
-        const int doRic = (s0 == 0) ? 1 : 0;
-        PrepArgs a;
-        a.xi0s = f->d_xi0s;
-        a.Xs = f->d_Xs;
-        a.ctx = f->d_ctx;
-        a.steps = f->d_steps + s0;
-        a.imu = f->d_imu + (size_t)13 * s0;
-        a.nsteps = ns;
-        for (int k = 0; k < 12; ++k) a.meanImu[k] = acc[k];
-        a.dtTotal = accT;
-        a.doRiccati = doRic;
-        a.discreteLift = s.useDiscreteVelocityLift ? 1 : 0;
-        a.qdiag[0] = s.velGyrNoise * s.velGyrNoise;
-        a.qdiag[1] = s.velAccNoise * s.velAccNoise;
-        a.qdiag[2] = s.velGyrBiasWalk * s.velGyrBiasWalk;
-        a.qdiag[3] = s.velAccBiasWalk * s.velAccBiasWalk;
-        a.pdiag[0] = s.biasOmegaProcessVariance;
-        a.pdiag[1] = s.biasAccelProcessVariance;
-        a.pdiag[2] = s.attitudeProcessVariance;
-        a.pdiag[3] = s.positionProcessVariance;
-        a.pdiag[4] = s.velocityProcessVariance;
-        a.pdiag[5] = s.cameraAttitudeProcessVariance;
-        a.pdiag[6] = s.cameraPositionProcessVariance;
-        a.pdiag[7] = s.pointProcessVariance;
-        sensor_prep_kernel<<<1, 32, 0, f->stream>>>(a);
-        LAUNCH_CHECK(f, "sensor_prep_kernel");
-        if (N > 0) {
-            landmark_propagate_kernel<<<cdiv(N, 128), 128, ns * sizeof(ObsStep), f->stream>>>(
-                f->lm[f->lmcur], f->cap, N, f->d_ctx, f->d_steps + s0, ns, doRic, s.coordinateChoice, f->d_rows);
-            LAUNCH_CHECK(f, "landmark_propagate_kernel");
-        }
-        if (doRic) {
-            const double* Sin = f->Sig[f->cur];
-            double* Sout = f->Sig[1 - f->cur];
-            prop_sensor_block_kernel<<<1, 448, 0, f->stream>>>(Sin, Sout, f->ld, f->d_ctx);
-            LAUNCH_CHECK(f, "prop_sensor_block_kernel");
-            if (N > 0) {
-                prop_strip_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv);
-                LAUNCH_CHECK(f, "prop_strip_kernel");
-                const int nt = cdiv(N, TP);
-                int pk = prof_begin(f, PROF_PROP_LL);
-                prop_ll_kernel<<<dim3(nt, nt), dim3(TP, TP), 0, f->stream>>>(Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv);
-                prof_end(f, pk);
-                LAUNCH_CHECK(f, "prop_ll_kernel");
-            }
-            f->cur = 1 - f->cur;
-        }
+    PrepArgs a;
+    a.xi0s = f->d_xi0s;
+    a.Xs = f->d_Xs[f->xcur];
+    a.XsOut = f->d_Xs[1 - f->xcur];
+    a.ctx = f->d_ctx;
+    a.steps = f->d_steps;
+    a.imu = f->d_imu;
+    a.nsteps = n;
+    for (int k = 0; k < 12; ++k) a.meanImu[k] = acc[k];
+    a.dtTotal = accT;
+    a.discreteLift = s.useDiscreteVelocityLift ? 1 : 0;
+    a.qdiag[0] = s.velGyrNoise * s.velGyrNoise;
+    a.qdiag[1] = s.velAccNoise * s.velAccNoise;
+    a.qdiag[2] = s.velGyrBiasWalk * s.velGyrBiasWalk;
+    a.qdiag[3] = s.velAccBiasWalk * s.velAccBiasWalk;
+    a.pdiag[0] = s.biasOmegaProcessVariance;
+    a.pdiag[1] = s.biasAccelProcessVariance;
+    a.pdiag[2] = s.attitudeProcessVariance;
+    a.pdiag[3] = s.positionProcessVariance;
+    a.pdiag[4] = s.velocityProcessVariance;
+    a.pdiag[5] = s.cameraAttitudeProcessVariance;
+    a.pdiag[6] = s.cameraPositionProcessVariance;
+    a.pdiag[7] = s.pointProcessVariance;
+    // Two independent chains (VIOFilter.cpp:138 "the Riccati propagation ... does not affect the state propagation"):
+    //   stream : Riccati  -- context + Sigma_ss, landmark rows, strips, landmark-landmark block (reads X, Q *before*)
+    //   stream2: observer -- sensor part of every IMU segment, then the landmark part (writes the other X / lm buffers)
+    CUDA_TRY(f, cudaEventRecord(f->evFork, f->stream));
+    CUDA_TRY(f, cudaStreamWaitEvent(f->stream2, f->evFork, 0));
+    observer_sensor_kernel<<<1, 32, 0, f->stream2>>>(a);
+    LAUNCH_CHECK(f, "observer_sensor_kernel");
+    if (N > 0) {
+        observer_landmark_kernel<<<cdiv(N, 64), 64, 0, f->stream2>>>(f->lm[f->lmcur], f->lm[1 - f->lmcur], f->dids[f->lmcur],
+                                                                     f->dids[1 - f->lmcur], f->cap, N, f->d_steps, n);
+        LAUNCH_CHECK(f, "observer_landmark_kernel");
     }
+    CUDA_TRY(f, cudaEventRecord(f->evJoin, f->stream2));
+    {
+        const double* Sin = f->Sig[f->cur];
+        double* Sout = f->Sig[1 - f->cur];
+        riccati_prep_kernel<<<1, 448, 0, f->stream>>>(a, Sin, Sout, f->ld);
+        LAUNCH_CHECK(f, "riccati_prep_kernel");
+        if (N > 0) {
+            landmark_rows_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_ctx, s.coordinateChoice, f->d_rows);
+            LAUNCH_CHECK(f, "landmark_rows_kernel");
+            prop_strip_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv);
+            LAUNCH_CHECK(f, "prop_strip_kernel");
+            const int nt = cdiv(N, TP);
+            int pk = prof_begin(f, PROF_PROP_LL);
+            prop_ll_kernel<<<dim3(nt, nt), dim3(TP, TP), 0, f->stream>>>(Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv);
+            prof_end(f, pk);
+            LAUNCH_CHECK(f, "prop_ll_kernel");
+        }
+        f->cur = 1 - f->cur;
+    }
+    CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->evJoin, 0));
+    f->xcur = 1 - f->xcur;
+    if (N > 0) f->lmcur = 1 - f->lmcur;
     f->time = newTime;
     // prune, keeping the last sample with stamp < currentTime (VIOFilter.cpp:183-189)
     size_t k = 0;
@@ -736,7 +750,7 @@ int vision_phase_b(eqvio_filter* f) {
     gamma_kernel<<<cdiv(dimp, 128), 128, m * sizeof(double), f->stream>>>(Z, ldz, m, dimp, f->d_Gamma);
     LAUNCH_CHECK(f, "gamma_kernel");
     }
-    lift_kernel<<<cdiv(std::max(Nn, 1), 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, Nn, f->d_xi0s, f->d_Xs, gammaFinal,
+    lift_kernel<<<cdiv(std::max(Nn, 1), 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, Nn, f->d_xi0s, f->d_Xs[f->xcur], gammaFinal,
                                                                    s.useDiscreteInnovationLift ? 1 : 0, s.coordinateChoice,
                                                                    f->d_status, f->d_status + 1);
     LAUNCH_CHECK(f, "lift_kernel");
@@ -1028,7 +1042,11 @@ void eqvio_destroy(eqvio_filter* f) {
         cudaFree(f->dids[k]);
     }
     cudaFree(f->d_xi0s);
-    cudaFree(f->d_Xs);
+    cudaFree(f->d_Xs[0]);
+    cudaFree(f->d_Xs[1]);
+    if (f->stream2) cudaStreamDestroy(f->stream2);
+    if (f->evFork) cudaEventDestroy(f->evFork);
+    if (f->evJoin) cudaEventDestroy(f->evJoin);
     cudaFree(f->d_ctx);
     cudaFree(f->d_steps);
     cudaFree(f->d_imu);
@@ -1239,7 +1257,7 @@ int eqvio_get_state_estimate(eqvio_filter* f, double sensor[23], int* ids, doubl
     ENTER(f);
     stage_reset(f);
     const int N = (int)f->ids.size();
-    state_estimate_kernel<<<cdiv(std::max(N, 1), 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_xi0s, f->d_Xs, f->d_out);
+    state_estimate_kernel<<<cdiv(std::max(N, 1), 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_xi0s, f->d_Xs[f->xcur], f->d_out);
     LAUNCH_CHECK(f, "state_estimate_kernel");
     double* h = nullptr;
     int rc = download_async(f, &h, f->d_out, 23 + 3 * (size_t)N);
@@ -1262,7 +1280,7 @@ int eqvio_get_eqf_state(eqvio_filter* f, double xi0_sensor[23], int* ids, double
     if (ids && N) std::memcpy(ids, f->ids.data(), N * sizeof(int));
     int rc;
     double *hX = nullptr, *hlm = nullptr;
-    if ((rc = download_async(f, &hX, f->d_Xs, 23)) != EQVIO_OK) return rc;
+    if ((rc = download_async(f, &hX, f->d_Xs[f->xcur], 23)) != EQVIO_OK) return rc;
     if (N > 0 && (xi0_p || X_Q)) {
         hlm = static_cast<double*>(stage_alloc(f, (size_t)LM_FIELDS * N * sizeof(double)));
         if (!hlm) return EQVIO_ERR_CUDA;

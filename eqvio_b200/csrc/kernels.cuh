@@ -46,98 +46,105 @@ struct ObsStep {  // one IMU segment of integrateObserverState, sensor part alre
 
 struct PrepArgs {
     const double* xi0s;  // 23
-    double* Xs;          // 23, updated in place
+    const double* Xs;    // 23, X before the observer integration
+    double* XsOut;       // 23, X after it (a different buffer: the Riccati chain still reads Xs)
     RiccatiCtx* ctx;
     ObsStep* steps;
     const double* imu;  // nsteps x 13: dt, gyr3, acc3, gyrBiasVel3, accBiasVel3
     int nsteps;
     double meanImu[12];
     double dtTotal;
-    int doRiccati, discreteLift;
+    int discreteLift;
     double qdiag[4];  // gyr^2, acc^2, gyrBias^2, accBias^2       (VIOFilterSettings.h:192-201)
     double pdiag[8];  // process variances per 3-block + point     (VIOFilterSettings.h:176-190)
 };
 
 // ------------------------------------------------------------------------------------------------
-// K1: sensor-sized preparation, one thread.  Builds the sensor blocks of A and B for the Riccati
-// step (euclid.cpp:99-160,186-233; identical for invdepth) from X *before* the observer
-// integration, then runs the sensor part of integrateObserverState for every IMU segment
-// (VIO_eqf.cpp:47-60, VIOGroup.cpp:190-271) and records what the landmark kernel needs.
+// Riccati context, part 1 (sensor-sized, serial): the sensor blocks of A and B (euclid.cpp:99-160,
+// 186-233; identical for invdepth) from X *before* the observer integration, and the quantities the
+// landmark rows need.  As is 21x21, Bs 21x12, row-major.
 // ------------------------------------------------------------------------------------------------
-HD void sensor_prep_body(const PrepArgs& a) {
+HD void riccati_small(const PrepArgs& a, double* As, double* Bs) {
     SensorState xi0 = unpack_sensor(a.xi0s);
     GroupSensor X = unpack_group(a.Xs);
-
-    if (a.doRiccati) {
-        RiccatiCtx& c = *a.ctx;
-        const double dt = a.dtTotal;
-        SensorState xh = sensor_group_action(X, xi0);
-        double As[21 * 21], Bs[21 * 12];
-        for (int i = 0; i < 21 * 21; ++i) As[i] = 0;
-        for (int i = 0; i < 21 * 12; ++i) Bs[i] = 0;
-        // B sensor rows (euclid.cpp:206-218)
-        for (int i = 0; i < 6; ++i) Bs[i * 12 + 6 + i] = 1.0;
-        M3 RA = qmat(X.A.q);
-        M3 xRA = skew(X.A.x) * RA;
-        M3 RAv = RA * skew(xh.vel);
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) {
-                Bs[(6 + i) * 12 + j] = RA(i, j);
-                Bs[(9 + i) * 12 + j] = xRA(i, j);
-                Bs[(12 + i) * 12 + j] = RAv(i, j);
-                Bs[(12 + i) * 12 + 3 + j] = RA(i, j);
-            }
-        // A sensor block (euclid.cpp:111-131)
-        for (int i = 0; i < 21; ++i)
-            for (int j = 0; j < 6; ++j) As[i * 21 + j] = -Bs[i * 12 + j];
-        for (int i = 0; i < 3; ++i) As[(9 + i) * 21 + 12 + i] = 1.0;
-        V3 gdir = qrot(qinv(xi0.pose.q), V3{0, 0, 1});
-        M3 gsk = (-GRAVITY_CONSTANT) * skew(gdir);
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) As[(12 + i) * 21 + 6 + j] = gsk(i, j);
-        double UI[6] = {a.meanImu[0] - xh.bias[0], a.meanImu[1] - xh.bias[1], a.meanImu[2] - xh.bias[2],
-                        xh.vel.x, xh.vel.y, xh.vel.z};
-        double AdT0inv[36], AdA[36], t1[6], t2[6], adT[36];
-        se3_Adjoint(se3_inv(xi0.cam), AdT0inv);
-        se3_Adjoint(X.A, AdA);
-        mat6_vec(AdA, UI, t1);
-        mat6_vec(AdT0inv, t1, t2);
-        se3_adjoint(t2, adT);
-        for (int i = 0; i < 6; ++i)
-            for (int j = 0; j < 6; ++j) As[(15 + i) * 21 + 15 + j] = adT[6 * i + j];
-        // landmark-row context
-        double AdBinv[36];
-        se3_Adjoint(se3_inv(X.B), AdBinv);
-        mat6_mul(AdBinv, adT, c.common);
-        M3 RIC = qmat(xh.cam.q);
-        M3 t = transpose(RIC) * transpose(RA);
-        M3 RTIC = qmat(qinv(xh.cam.q));
-        for (int i = 0; i < 9; ++i) {
-            c.RICt_RAt[i] = t.m[i];
-            c.RT_IC[i] = RTIC.m[i];
+    RiccatiCtx& c = *a.ctx;
+    const double dt = a.dtTotal;
+    SensorState xh = sensor_group_action(X, xi0);
+    for (int i = 0; i < 21 * 21; ++i) As[i] = 0;
+    for (int i = 0; i < 21 * 12; ++i) Bs[i] = 0;
+    // B sensor rows (euclid.cpp:206-218)
+    for (int i = 0; i < 6; ++i) Bs[i * 12 + 6 + i] = 1.0;
+    M3 RA = qmat(X.A.q);
+    M3 xRA = skew(X.A.x) * RA;
+    M3 RAv = RA * skew(xh.vel);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            Bs[(6 + i) * 12 + j] = RA(i, j);
+            Bs[(9 + i) * 12 + j] = xRA(i, j);
+            Bs[(12 + i) * 12 + j] = RAv(i, j);
+            Bs[(12 + i) * 12 + 3 + j] = RA(i, j);
         }
-        double AdThinv[36], UC[6];
-        se3_Adjoint(se3_inv(xh.cam), AdThinv);
-        mat6_vec(AdThinv, UI, UC);
-        c.vC[0] = UC[3]; c.vC[1] = UC[4]; c.vC[2] = UC[5];
-        c.xIC[0] = xh.cam.x.x; c.xIC[1] = xh.cam.x.y; c.xIC[2] = xh.cam.x.z;
-        c.dt = dt;
-        c.cg = dt * a.qdiag[0];
-        c.plDiag = dt * a.pdiag[7];
-        for (int i = 0; i < 21; ++i)
-            for (int j = 0; j < 21; ++j) c.Fs[i * 21 + j] = (i == j ? 1.0 : 0.0) + dt * As[i * 21 + j];
-        for (int i = 0; i < 21; ++i)
-            for (int j = 0; j < 21; ++j) {
-                double s = 0;
-                for (int k = 0; k < 12; ++k) s += Bs[i * 12 + k] * a.qdiag[k / 3] * Bs[j * 12 + k];
-                if (i == j) s += a.pdiag[i / 3];
-                c.Ns[i * 21 + j] = dt * s;
-            }
-        for (int i = 0; i < 21; ++i)
-            for (int j = 0; j < 3; ++j) c.BsG[i * 3 + j] = c.cg * Bs[i * 12 + j];
+    // A sensor block (euclid.cpp:111-131)
+    for (int i = 0; i < 21; ++i)
+        for (int j = 0; j < 6; ++j) As[i * 21 + j] = -Bs[i * 12 + j];
+    for (int i = 0; i < 3; ++i) As[(9 + i) * 21 + 12 + i] = 1.0;
+    V3 gdir = qrot(qinv(xi0.pose.q), V3{0, 0, 1});
+    M3 gsk = (-GRAVITY_CONSTANT) * skew(gdir);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) As[(12 + i) * 21 + 6 + j] = gsk(i, j);
+    double UI[6] = {a.meanImu[0] - xh.bias[0], a.meanImu[1] - xh.bias[1], a.meanImu[2] - xh.bias[2],
+                    xh.vel.x, xh.vel.y, xh.vel.z};
+    double AdT0inv[36], AdA[36], t1[6], t2[6], adT[36];
+    se3_Adjoint(se3_inv(xi0.cam), AdT0inv);
+    se3_Adjoint(X.A, AdA);
+    mat6_vec(AdA, UI, t1);
+    mat6_vec(AdT0inv, t1, t2);
+    se3_adjoint(t2, adT);
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) As[(15 + i) * 21 + 15 + j] = adT[6 * i + j];
+    // landmark-row context
+    double AdBinv[36];
+    se3_Adjoint(se3_inv(X.B), AdBinv);
+    mat6_mul(AdBinv, adT, c.common);
+    M3 RIC = qmat(xh.cam.q);
+    M3 t = transpose(RIC) * transpose(RA);
+    M3 RTIC = qmat(qinv(xh.cam.q));
+    for (int i = 0; i < 9; ++i) {
+        c.RICt_RAt[i] = t.m[i];
+        c.RT_IC[i] = RTIC.m[i];
     }
+    double AdThinv[36], UC[6];
+    se3_Adjoint(se3_inv(xh.cam), AdThinv);
+    mat6_vec(AdThinv, UI, UC);
+    c.vC[0] = UC[3]; c.vC[1] = UC[4]; c.vC[2] = UC[5];
+    c.xIC[0] = xh.cam.x.x; c.xIC[1] = xh.cam.x.y; c.xIC[2] = xh.cam.x.z;
+    c.dt = dt;
+    c.cg = dt * a.qdiag[0];
+    c.plDiag = dt * a.pdiag[7];
+}
+// part 2, one call per entry t = 21 i + j of the sensor block: F_s = I + dt A_s, N_s = dt (B_s Q B_s^T + P_s),
+// and dt q_gyr B_s[:, 0:3] for t < 63.
+HD void riccati_entry(const PrepArgs& a, const double* As, const double* Bs, int t, double& Fs, double& Ns) {
+    const double dt = a.dtTotal;
+    const int i = t / 21, j = t % 21;
+    Fs = (i == j ? 1.0 : 0.0) + dt * As[t];
+    double s = 0;
+    for (int k = 0; k < 12; ++k) s += Bs[i * 12 + k] * a.qdiag[k / 3] * Bs[j * 12 + k];
+    if (i == j) s += a.pdiag[i / 3];
+    Ns = dt * s;
+    a.ctx->Fs[t] = Fs;
+    a.ctx->Ns[t] = Ns;
+    if (t < 63) a.ctx->BsG[t] = (dt * a.qdiag[0]) * Bs[(t / 3) * 12 + (t % 3)];
+}
 
-    // observer integration, sensor part
+// ------------------------------------------------------------------------------------------------
+// Observer integration, sensor part: integrateObserverState for every buffered IMU segment
+// (VIO_eqf.cpp:47-60, VIOGroup.cpp:190-271), X <- X * Lambda; records per segment what the landmark
+// part needs.  Serial by nature (each segment starts from the previous estimate).
+// ------------------------------------------------------------------------------------------------
+HD void observer_sensor_body(const PrepArgs& a) {
+    SensorState xi0 = unpack_sensor(a.xi0s);
+    GroupSensor X = unpack_group(a.Xs);
     for (int s = 0; s < a.nsteps; ++s) {
         const double* u = a.imu + 13 * s;
         const double dt = u[0];
@@ -183,142 +190,169 @@ HD void sensor_prep_body(const PrepArgs& a) {
         Xn.w = X.w + qrot(X.A.q, L.w);
         X = Xn;
     }
-    if (a.nsteps > 0) pack_group(X, a.Xs);
+    pack_group(X, a.XsOut);
 }
 
-__global__ void sensor_prep_kernel(PrepArgs a) {
+__global__ void observer_sensor_kernel(PrepArgs a) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    sensor_prep_body(a);
+    observer_sensor_body(a);
 }
 
-// ------------------------------------------------------------------------------------------------
-// K2: one thread per landmark.  (a) landmark rows of A and B (euclid.cpp:133-155,219-228;
-// invdepth.cpp:83-118,170-178) condensed to D_i = I + dt A_qi (3x3), G_i = dt [ -B_l | A_vel | A_cam ]
-// (3x12, columns c_sidx) and Bl_i (3x3); (b) the landmark part of every buffered IMU segment
-// (VIOGroup.cpp:258-269 / :211-220), Q_i <- Q_i * Lambda_Qi.
-// rows[i] = D(9) | G(36) | Bl(9), row-major.
-// ------------------------------------------------------------------------------------------------
-constexpr int ROWS_STRIDE = 54;
-
-__global__ void landmark_propagate_kernel(double* __restrict__ lm, int cap, int N, const RiccatiCtx* __restrict__ ctx,
-                                          const ObsStep* __restrict__ steps, int nsteps, int doRiccati, int coord,
-                                          double* __restrict__ rows) {
-    extern __shared__ unsigned char smem_raw[];
-    ObsStep* s_steps = reinterpret_cast<ObsStep*>(smem_raw);
-    for (int i = threadIdx.x; i < nsteps * (int)(sizeof(ObsStep) / 8); i += blockDim.x)
-        reinterpret_cast<double*>(s_steps)[i] = reinterpret_cast<const double*>(steps)[i];
-    __syncthreads();
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
-    Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
-    double a = lm[F_QA * cap + i];
-
-    if (doRiccati) {
-        const double dt = ctx->dt;
-        M3 RQ = qmat(Q);
-        M3 Qhat = a * RQ;
-        V3 qh = landmark_action(Q, a, q0);
-        M3 T, RTIC;
-        for (int k = 0; k < 9; ++k) {
-            T.m[k] = ctx->RICt_RAt[k];
-            RTIC.m[k] = ctx->RT_IC[k];
-        }
-        V3 vC = V3{ctx->vC[0], ctx->vC[1], ctx->vC[2]};
-        V3 xIC = V3{ctx->xIC[0], ctx->xIC[1], ctx->xIC[2]};
-        M3 velB = (-1.0) * (Qhat * T);
-        // [skew(q0) R_Q, -a R_Q] * common  (3x6)
-        M3 t0 = skew(q0) * RQ;
-        M3 t1 = (-a) * RQ;
-        double camB[18];
-        for (int r = 0; r < 3; ++r)
-            for (int c = 0; c < 6; ++c) {
-                double s = 0;
-                for (int k = 0; k < 3; ++k) s += t0(r, k) * ctx->common[6 * k + c] + t1(r, k) * ctx->common[6 * (3 + k) + c];
-                camB[6 * r + c] = s;
-            }
-        M3 inner = skew(qh) * skew(vC) - 2.0 * outer(vC, qh) + outer(qh, vC);
-        M3 Aq = (-1.0 / norm2(qh)) * (Qhat * inner * inverse(Qhat));
-        M3 Bl = Qhat * (skew(qh) * RTIC + RTIC * skew(xIC));
-        if (coord == COORD_INVDEPTH) {
-            M3 cv = conv_euc2ind(q0), cvi = conv_ind2euc(q0);
-            velB = cv * velB;
-            double tmp[18];
-            for (int r = 0; r < 3; ++r)
-                for (int c = 0; c < 6; ++c) tmp[6 * r + c] = cv(r, 0) * camB[c] + cv(r, 1) * camB[6 + c] + cv(r, 2) * camB[12 + c];
-            for (int k = 0; k < 18; ++k) camB[k] = tmp[k];
-            Aq = cv * Aq * cvi;
-            Bl = cv * Bl;
-        }
-        double* o = rows + (size_t)i * ROWS_STRIDE;
-        for (int r = 0; r < 3; ++r)
-            for (int c = 0; c < 3; ++c) o[3 * r + c] = (r == c ? 1.0 : 0.0) + dt * Aq(r, c);
-        for (int r = 0; r < 3; ++r) {
-            for (int c = 0; c < 3; ++c) o[9 + 12 * r + c] = -dt * Bl(r, c);
-            for (int c = 0; c < 3; ++c) o[9 + 12 * r + 3 + c] = dt * velB(r, c);
-            for (int c = 0; c < 6; ++c) o[9 + 12 * r + 6 + c] = dt * camB[6 * r + c];
-        }
-        for (int k = 0; k < 9; ++k) o[45 + k] = Bl.m[k];
-    }
-
-    for (int s = 0; s < nsteps; ++s) {
-        const ObsStep& st = s_steps[s];
-        V3 p0 = landmark_action(Q, a, q0);
-        Quat LQ;
-        double La;
-        if (st.discrete) {
-            V3 p1 = se3_apply(st.camChangeInv, p0);
-            LQ = quat_from_two_vectors(normalized(p1), normalized(p0));
-            La = norm(p0) / norm(p1);
-        } else {
-            double n2 = norm2(p0);
-            V3 wv = st.omegaC + cross(p0, st.vC) / n2;
-            LQ = so3_exp(st.dt * wv);               // SOT3::exp(dt * W) (SOT3.h:48-53)
-            La = exp(st.dt * (dot(p0, st.vC) / n2));
-        }
-        Q = qmul(Q, LQ);
-        a = a * La;
-    }
-    if (nsteps > 0) {
-        lm[F_QW * cap + i] = Q.w;
-        lm[F_QX * cap + i] = Q.x;
-        lm[F_QY * cap + i] = Q.y;
-        lm[F_QZ * cap + i] = Q.z;
-        lm[F_QA * cap + i] = a;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K3a: sensor-sensor block  Sigma'_ss = F_s Sigma_ss F_s^T + N_s   (one block, 21x21 threads)
-// ------------------------------------------------------------------------------------------------
-__global__ void prop_sensor_block_kernel(const double* __restrict__ Sin, double* __restrict__ Sout, int ld,
-                                         const RiccatiCtx* __restrict__ ctx) {
-    __shared__ double sF[21 * 21], sS[21 * 21], sT[21 * 21];
-    int t = threadIdx.x;
+// One CTA: Riccati context (thread 0 builds the sparse A_s, B_s; 441 threads fill F_s, N_s) and, fused, the
+// sensor-sensor block  Sigma'_ss = F_s Sigma_ss F_s^T + N_s  plus the zero pad rows/cols of the sensor block.
+__global__ void __launch_bounds__(448) riccati_prep_kernel(PrepArgs a, const double* __restrict__ Sin, double* __restrict__ Sout, int ld) {
+    __shared__ double sAs[441], sBs[252], sF[441], sS[441], sT[441];
+    const int t = threadIdx.x;
+    if (t == 0) riccati_small(a, sAs, sBs);
     if (t < 441) {
-        int r = t / 21, c = t % 21;
-        sF[t] = ctx->Fs[t];
+        const int r = t / 21, c = t % 21;
         sS[t] = Sin[(size_t)c * ld + r];  // sS[r*21+c] = Sigma[r,c]
     }
     __syncthreads();
+    double ns = 0.0;
     if (t < 441) {
-        int r = t / 21, c = t % 21;
+        double fs;
+        riccati_entry(a, sAs, sBs, t, fs, ns);
+        sF[t] = fs;
+    }
+    __syncthreads();
+    if (t < 441) {
+        const int r = t / 21, c = t % 21;
         double s = 0;
         for (int k = 0; k < 21; ++k) s += sF[r * 21 + k] * sS[k * 21 + c];
         sT[t] = s;
     }
     __syncthreads();
     if (t < 441) {
-        int r = t / 21, c = t % 21;
-        double s = ctx->Ns[t];
+        const int r = t / 21, c = t % 21;
+        double s = ns;
         for (int k = 0; k < 21; ++k) s += sT[r * 21 + k] * sF[c * 21 + k];
         Sout[(size_t)c * ld + r] = s;
     }
-    // keep the 3 pad rows/cols of the sensor block zero
     if (t < 3 * SOFF) {
-        int p = SENSOR_DIM + t / SOFF, q = t % SOFF;
+        const int p = SENSOR_DIM + t / SOFF, q = t % SOFF;
         Sout[(size_t)q * ld + p] = 0.0;
         Sout[(size_t)p * ld + q] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per landmark, Riccati rows: the landmark rows of A and B (euclid.cpp:133-155,219-228; invdepth.cpp:83-118,
+// 170-178) condensed to D_i = I + dt A_qi (3x3), G_i = dt [ -B_l | A_vel | A_cam ] (3x12, columns c_sidx)
+// and Bl_i (3x3).  rows[i] = D(9) | G(36) | Bl(9), row-major.  Uses Q before the observer integration.
+// ------------------------------------------------------------------------------------------------
+constexpr int ROWS_STRIDE = 54;
+
+__global__ void landmark_rows_kernel(const double* __restrict__ lm, int cap, int N, const RiccatiCtx* __restrict__ ctx, int coord,
+                                     double* __restrict__ rows) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
+    Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
+    double a = lm[F_QA * cap + i];
+    const double dt = ctx->dt;
+    M3 RQ = qmat(Q);
+    M3 Qhat = a * RQ;
+    V3 qh = landmark_action(Q, a, q0);
+    M3 T, RTIC;
+    for (int k = 0; k < 9; ++k) {
+        T.m[k] = ctx->RICt_RAt[k];
+        RTIC.m[k] = ctx->RT_IC[k];
+    }
+    V3 vC = V3{ctx->vC[0], ctx->vC[1], ctx->vC[2]};
+    V3 xIC = V3{ctx->xIC[0], ctx->xIC[1], ctx->xIC[2]};
+    M3 velB = (-1.0) * (Qhat * T);
+    // [skew(q0) R_Q, -a R_Q] * common  (3x6)
+    M3 t0 = skew(q0) * RQ;
+    M3 t1 = (-a) * RQ;
+    double camB[18];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 6; ++c) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += t0(r, k) * ctx->common[6 * k + c] + t1(r, k) * ctx->common[6 * (3 + k) + c];
+            camB[6 * r + c] = s;
+        }
+    M3 inner = skew(qh) * skew(vC) - 2.0 * outer(vC, qh) + outer(qh, vC);
+    M3 Aq = (-1.0 / norm2(qh)) * (Qhat * inner * inverse(Qhat));
+    M3 Bl = Qhat * (skew(qh) * RTIC + RTIC * skew(xIC));
+    if (coord == COORD_INVDEPTH) {
+        M3 cv = conv_euc2ind(q0), cvi = conv_ind2euc(q0);
+        velB = cv * velB;
+        double tmp[18];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 6; ++c) tmp[6 * r + c] = cv(r, 0) * camB[c] + cv(r, 1) * camB[6 + c] + cv(r, 2) * camB[12 + c];
+        for (int k = 0; k < 18; ++k) camB[k] = tmp[k];
+        Aq = cv * Aq * cvi;
+        Bl = cv * Bl;
+    }
+    double* o = rows + (size_t)i * ROWS_STRIDE;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) o[3 * r + c] = (r == c ? 1.0 : 0.0) + dt * Aq(r, c);
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) o[9 + 12 * r + c] = -dt * Bl(r, c);
+        for (int c = 0; c < 3; ++c) o[9 + 12 * r + 3 + c] = dt * velB(r, c);
+        for (int c = 0; c < 6; ++c) o[9 + 12 * r + 6 + c] = dt * camB[6 * r + c];
+    }
+    for (int k = 0; k < 9; ++k) o[45 + k] = Bl.m[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per landmark, observer integration: the landmark part of every buffered IMU segment
+// (VIOGroup.cpp:258-269 / :211-220), Q_i <- Q_i * Lambda_Qi.  Reads lmIn, writes every field of lmOut
+// (and the ids) so that the Riccati chain can keep reading lmIn concurrently.
+// ------------------------------------------------------------------------------------------------
+constexpr int OBS_STAGE = 64;  // IMU segments staged in shared memory at a time
+
+__global__ void observer_landmark_kernel(const double* __restrict__ lmIn, double* __restrict__ lmOut, const int* __restrict__ idsIn,
+                                         int* __restrict__ idsOut, int cap, int N, const ObsStep* __restrict__ steps, int nsteps) {
+    __shared__ ObsStep s_steps[OBS_STAGE];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < N;
+    V3 q0 = V3{0, 0, 1};
+    Quat Q = quat_identity();
+    double a = 1.0;
+    if (live) {
+        q0 = V3{lmIn[F_Q0X * cap + i], lmIn[F_Q0Y * cap + i], lmIn[F_Q0Z * cap + i]};
+        Q = Quat{lmIn[F_QW * cap + i], lmIn[F_QX * cap + i], lmIn[F_QY * cap + i], lmIn[F_QZ * cap + i]};
+        a = lmIn[F_QA * cap + i];
+    }
+    for (int s0 = 0; s0 < nsteps; s0 += OBS_STAGE) {
+        const int ns = min(OBS_STAGE, nsteps - s0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < ns * (int)(sizeof(ObsStep) / 8); t += blockDim.x)
+            reinterpret_cast<double*>(s_steps)[t] = reinterpret_cast<const double*>(steps + s0)[t];
+        __syncthreads();
+        if (live) {
+            for (int s = 0; s < ns; ++s) {
+                const ObsStep& st = s_steps[s];
+                V3 p0 = landmark_action(Q, a, q0);
+                Quat LQ;
+                double La;
+                if (st.discrete) {
+                    V3 p1 = se3_apply(st.camChangeInv, p0);
+                    LQ = quat_from_two_vectors(normalized(p1), normalized(p0));
+                    La = norm(p0) / norm(p1);
+                } else {
+                    double n2 = norm2(p0);
+                    V3 wv = st.omegaC + cross(p0, st.vC) / n2;
+                    LQ = so3_exp(st.dt * wv);               // SOT3::exp(dt * W) (SOT3.h:48-53)
+                    La = exp(st.dt * (dot(p0, st.vC) / n2));
+                }
+                Q = qmul(Q, LQ);
+                a = a * La;
+            }
+        }
+    }
+    if (live) {
+        lmOut[F_Q0X * cap + i] = q0.x;
+        lmOut[F_Q0Y * cap + i] = q0.y;
+        lmOut[F_Q0Z * cap + i] = q0.z;
+        lmOut[F_QW * cap + i] = Q.w;
+        lmOut[F_QX * cap + i] = Q.x;
+        lmOut[F_QY * cap + i] = Q.y;
+        lmOut[F_QZ * cap + i] = Q.z;
+        lmOut[F_QA * cap + i] = a;
+        idsOut[i] = idsIn[i];
     }
 }
 
@@ -1134,7 +1168,7 @@ __global__ void __launch_bounds__(CH_THREADS)
 // Sigma must be allocated with ld and row count padded to a multiple of 64 (whole tiles are moved).
 // ------------------------------------------------------------------------------------------------
 constexpr int DD_T = 64, DD_LD = YB_LD, DD_THREADS = 128;
-constexpr int DD_SMEM = 3 * DD_T * DD_LD * 8 + 16;
+constexpr int DD_SMEM = 2 * DD_T * DD_LD * 8 + 16;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -1162,15 +1196,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-__global__ void __launch_bounds__(DD_THREADS)
+__global__ void __launch_bounds__(DD_THREADS, 3)
     chunk_downdate_kernel(double* __restrict__ Sig, int ld, const double* __restrict__ Y) {
     int ti, tj;
     tri_decode(blockIdx.x, ti, tj);  // lower-triangular tile index -> (ti, tj), ti >= tj
     extern __shared__ __align__(16) unsigned char dd_smem_raw[];
     double(*sA)[DD_LD] = reinterpret_cast<double(*)[DD_LD]>(dd_smem_raw);
     double(*sB)[DD_LD] = sA + DD_T;
-    double(*sC)[DD_LD] = sB + DD_T;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(dd_smem_raw + 3 * DD_T * DD_LD * 8);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dd_smem_raw + 2 * DD_T * DD_LD * 8);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i0 = ti * DD_T, j0 = tj * DD_T;
     const bool diag = ti == tj;
@@ -1182,25 +1215,20 @@ __global__ void __launch_bounds__(DD_THREADS)
         bulk_g2s(&sA[0][0], Y + (size_t)ti * YB_TILE, PANEL_BYTES, bar);
         if (!diag) bulk_g2s(&sB[0][0], Y + (size_t)tj * YB_TILE, PANEL_BYTES, bar);
     }
-    // Sigma tile: column j0+c, rows i0..i0+63 -> sC[c][0..63]; 32 lanes x 16 bytes = one column per instruction
-    double2 cv[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-        const int c = warp * 16 + u;
-        cv[u] = *reinterpret_cast<const double2*>(Sig + (size_t)(j0 + c) * ld + i0 + 2 * lane);
-    }
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-        const int c = warp * 16 + u;
-        *reinterpret_cast<double2*>(&sC[c][2 * lane]) = cv[u];
-    }
-    __syncthreads();  // sC complete, barrier initialised for everyone
+    // The Sigma tile goes straight into the accumulator fragment layout: element (r, c) of the tile is
+    // Sigma[i0 + r, j0 + c]; for one (a, b, e) a warp touches 4 columns x 8 consecutive rows = whole sectors.
     const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int fr = wm + (lane >> 2), fc = wn + (lane & 3) * 2;
     double acc[4][4][2];
+    double* cbase = Sig + (size_t)(j0 + fc) * ld + i0 + fr;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        for (int b = 0; b < 4; ++b) {
+            acc[a][b][0] = -cbase[(size_t)(b * 8) * ld + a * 8];
+            acc[a][b][1] = -cbase[(size_t)(b * 8 + 1) * ld + a * 8];
+        }
+    __syncthreads();  // barrier initialised for everyone
     mbar_wait(bar, 0);
     double(*sBB)[DD_LD] = diag ? sA : sB;
 #pragma unroll 4
@@ -1215,35 +1243,21 @@ __global__ void __launch_bounds__(DD_THREADS)
 #pragma unroll
             for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
     }
-    __syncthreads();  // every warp is done reading the panels: sA can take the transposed tile
+    // acc = -(Sigma - Y^T Y): store negated.  Mirror tile: (c, c+1) are adjacent in memory -> 16-byte stores.
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const int r = wm + a * 8 + (lane >> 2);
-            const int c = wn + b * 8 + (lane & 3) * 2;
-            const double v0 = sC[c][r] - acc[a][b][0];
-            const double v1 = sC[c + 1][r] - acc[a][b][1];
-            sC[c][r] = v0;
-            sC[c + 1][r] = v1;
+            const double v0 = -acc[a][b][0], v1 = -acc[a][b][1];
+            cbase[(size_t)(b * 8) * ld + a * 8] = v0;
+            cbase[(size_t)(b * 8 + 1) * ld + a * 8] = v1;
             if (!diag) {
-                sA[r][c] = v0;  // transposed tile
-                sA[r][c + 1] = v1;
+                double2 t;
+                t.x = v0;
+                t.y = v1;
+                *reinterpret_cast<double2*>(Sig + (size_t)(i0 + fr + a * 8) * ld + j0 + fc + b * 8) = t;
             }
         }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-        const int c = warp * 16 + u;
-        *reinterpret_cast<double2*>(Sig + (size_t)(j0 + c) * ld + i0 + 2 * lane) = *reinterpret_cast<const double2*>(&sC[c][2 * lane]);
-    }
-    if (!diag) {
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int c = warp * 16 + u;  // column i0+c of the mirror tile, rows j0..j0+63
-            *reinterpret_cast<double2*>(Sig + (size_t)(i0 + c) * ld + j0 + 2 * lane) = *reinterpret_cast<const double2*>(&sA[c][2 * lane]);
-        }
-    }
 }
 
 // Gamma = Y^T (L^-1 ytilde):  Gamma[r] = sum_k Z[m + r, k] * Z[yrow, k].  One thread per r.

@@ -21,11 +21,19 @@ int hook_sensor_prep(const double* xi0s, double* Xs, const double* imu, int nste
     a.nsteps = nsteps;
     for (int k = 0; k < 12; ++k) a.meanImu[k] = meanImu[k];
     a.dtTotal = dtTotal;
-    a.doRiccati = 1;
     a.discreteLift = discreteLift;
     for (int k = 0; k < 4; ++k) a.qdiag[k] = qdiag[k];
     for (int k = 0; k < 8; ++k) a.pdiag[k] = pdiag[k];
-    sensor_prep_body(a);
+    double XsOut[23];
+    a.XsOut = XsOut;
+    double As[441], Bs[252];
+    riccati_small(a, As, Bs);
+    for (int t = 0; t < 441; ++t) {
+        double fs, ns;
+        riccati_entry(a, As, Bs, t, fs, ns);
+    }
+    observer_sensor_body(a);
+    for (int k = 0; k < 23; ++k) Xs[k] = XsOut[k];
     memcpy(ctx_out, &ctx, sizeof(ctx));
     memcpy(steps_out, steps, nsteps * sizeof(ObsStep));
     delete[] steps;
