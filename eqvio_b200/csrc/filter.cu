@@ -703,7 +703,7 @@ int vision_phase_b(eqvio_filter* f) {
         for (int j0 = 0; j0 < nm; j0 += bcMax) {
             const int bc = std::min(bcMax, nm - j0);
             int pk = prof_begin(f, PROF_PANEL);
-            chunk_factor_kernel<<<ldy / CH_COLS, CH_THREADS, sizeof(ChunkSmem), f->stream>>>(
+            chunk_factor_kernel<<<ldy / CH_COLS, CH_THREADS, 0, f->stream>>>(
                 f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Y, f->d_status);
             prof_end(f, pk);
             LAUNCH_CHECK(f, "chunk_factor_kernel");
@@ -827,8 +827,7 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
         g_createError = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
         return EQVIO_ERR_CUDA;
     }
-    e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChunkSmem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM);
+    e = cudaFuncSetAttribute(chunk_downdate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM);
     if (e != cudaSuccess) {
         g_createError = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
         return EQVIO_ERR_CUDA;

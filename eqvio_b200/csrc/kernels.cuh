@@ -856,14 +856,14 @@ __global__ void __launch_bounds__(128)
 // ceil(dimp / 128) CTAs of 160 threads.  Y is R x ldy, row k contiguous in s.
 // ------------------------------------------------------------------------------------------------
 constexpr int CH_R = 64;        // max rows of a chunk (32 landmarks)
-constexpr int CH_COLS = 32;     // state columns per CTA (one warp substitutes, the residual rides on warp 1)
-constexpr int CH_THREADS = 160;
-constexpr int CH_WARPS = CH_THREADS / 32;
-constexpr int CH_T = 4;                                   // register tile edge of the elimination
-constexpr int CH_NT = CH_R / CH_T;                        // 16 tile rows
-constexpr int CH_TILES = CH_NT * (CH_NT + 1) / 2;         // 136 lower tiles, one thread each
-constexpr int CH_LDL = CH_R + 2;                          // row stride of sL (16-byte multiple)
-constexpr int CH_SB = 16;                                 // substitution block
+constexpr int CH_COLS = 32;     // state columns per CTA
+constexpr int CH_T = 4;                                   // register tile edge
+constexpr int CH_NT = CH_R / CH_T;                        // 16 tile columns
+constexpr int CH_TILES = CH_NT * (CH_NT + 1) / 2;         // 136 lower tiles of S_c
+constexpr int CH_RHS_ROWS = (CH_COLS + 1 + CH_T - 1) / CH_T;  // 9 tile rows: 32 state columns + the residual (+ padding)
+constexpr int CH_RHS_TILES = CH_RHS_ROWS * CH_NT;         // 144
+constexpr int CH_THREADS = 288;                           // 136 + 144 = 280 tile owners
+constexpr int CH_PROWS = CH_NT + CH_RHS_ROWS;             // tile rows of the augmented matrix [S_c; W_c^T; r^T]
 // Y is stored tile-blocked for the downdate kernel: tile t = 64 consecutive state columns, stored as 64 rows
 // (k) of 68 doubles (the last 4 are padding) so that a whole panel is ONE contiguous bulk copy that lands in
 // shared memory with a bank-conflict-free row stride.
@@ -872,14 +872,12 @@ constexpr size_t YB_TILE = (size_t)YB_T * YB_LD;
 __host__ __device__ __forceinline__ size_t yb_index(int k, int s) { return (size_t)(s >> 6) * YB_TILE + (size_t)k * YB_LD + (s & 63); }
 
 struct ChunkSmem {
-    double L[CH_R][CH_LDL];       // L[k][c] = entry (row c, col k), c >= k: column k contiguous in c
-    double X[CH_R][CH_COLS + 1];  // X[k][lane]: right-hand sides being substituted (+1: the residual column)
-    double Pn[CH_NT][CH_T][CH_T];  // finished panel of the current block column: Pn[I][r][j]
-    double D[2][CH_T][CH_T];       // diagonal tile of the current block column (unscaled), double-buffered
-    double Dc[2][CH_T];            // reciprocal pivots
+    double Pn[CH_T][CH_T][CH_PROWS + 1];  // finished panel of the current block column: Pn[r][j][tile row]
+    double D[2][CH_T][CH_T];              // diagonal tile of the current block column (unscaled), double-buffered
+    double Dc[2][CH_T];                   // reciprocal pivots
     double C[CH_R / 2][6];
     double Inv[CH_R];
-    double Z[CH_R];
+    double Yt[CH_R][CH_RHS_ROWS * CH_T + 1];  // scaled rows of Y for this CTA's columns (+ the residual column z)
     int Idx[CH_R / 2];
 };
 
@@ -894,127 +892,145 @@ __device__ __forceinline__ double fast_rcp(double x) {
 }
 // index t of a lower-triangular enumeration (row-major: (0,0),(1,0),(1,1),(2,0),...) -> (row, col)
 __device__ __forceinline__ void tri_decode(int t, int& row, int& col) {
-    int r = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
     while ((r + 1) * (r + 2) / 2 <= t) ++r;
     while (r * (r + 1) / 2 > t) --r;
     row = r;
     col = t - r * (r + 1) / 2;
 }
 
+// chunk_factor_kernel: every CTA eliminates the augmented matrix [S_c; W_c^T(its 32 state columns); r^T] in
+// registers: one thread owns one 4x4 tile for the whole elimination (136 tiles of the lower triangle of S_c,
+// 144 tiles of right-hand-side rows), so the triangular solve Y_c = L_c^-1 W_c rides along with the
+// factorisation at no extra latency.  Right-looking, unscaled columns (after block column J its entries hold
+// v_ij = L_ij L_jj); per block column: the diagonal owner eliminates inside its tile and publishes it, the panel
+// owners finish their four columns and publish them, everybody to the right applies the rank-4 update --
+// two barriers per four columns.  Grid = (padded dimp) / 32 CTAs, each repeats the (tiny) S_c work.
 __global__ void __launch_bounds__(CH_THREADS)
     chunk_factor_kernel(const double* __restrict__ Sig, int ld, int dimp, const int* __restrict__ lmOf,
                         const double* __restrict__ Cblk, const double* __restrict__ ytilde, int j0, int bc, double r2,
                         const double* __restrict__ GammaIn, double* __restrict__ GammaOut, double* __restrict__ Y,
                         int* __restrict__ status) {
-    extern __shared__ __align__(16) unsigned char chunk_smem_raw[];
-    ChunkSmem& sm = *reinterpret_cast<ChunkSmem*>(chunk_smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ ChunkSmem sm;
+    const int tid = threadIdx.x;
     const int rc = 2 * bc;
     for (int t = tid; t < bc * 6; t += CH_THREADS) sm.C[t / 6][t % 6] = Cblk[6 * (size_t)j0 + t];
     for (int t = tid; t < bc; t += CH_THREADS) sm.Idx[t] = SOFF + 3 * lmOf[j0 + t];
-    for (int t = tid; t < CH_R * CH_LDL; t += CH_THREADS) (&sm.L[0][0])[t] = 0.0;
-    for (int t = tid; t < CH_R * (CH_COLS + 1); t += CH_THREADS) (&sm.X[0][0])[t] = 0.0;
     __syncthreads();
 
-    // ---- gathers: all global loads of a thread are issued before their first use (one L2 round trip) ----
-    // S_c = C_c Sigma[L_c, L_c] C_c^T + r2 I, lower triangle by landmark pairs (j >= k), <= 4 pairs per thread
-    {
-        const int npairs = bc * (bc + 1) / 2;
-        double P[4][9];
-        int pj[4], pk[4];
+    // tile ownership: TI = tile row in the augmented matrix, TK = tile column
+    const bool isS = tid < CH_TILES;
+    const bool isRhs = tid >= CH_TILES && tid < CH_TILES + CH_RHS_TILES;
+    const bool owner = isS || isRhs;
+    int TI = 0, TK = 0;
+    if (isS) {
+        tri_decode(tid, TI, TK);
+    } else if (isRhs) {
+        TI = CH_NT + (tid - CH_TILES) / CH_NT;
+        TK = (tid - CH_TILES) % CH_NT;
+    }
+    const int sbase = blockIdx.x * CH_COLS;
+    double a[CH_T][CH_T];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int t = tid + u * CH_THREADS;
-            pj[u] = pk[u] = 0;
-            if (t < npairs) {
-                tri_decode(t, pj[u], pk[u]);
-                const double* sp = Sig + (size_t)sm.Idx[pk[u]] * ld + sm.Idx[pj[u]];  // Sigma[rows of j, cols of k]
+    for (int r = 0; r < CH_T; ++r)
 #pragma unroll
-                for (int b = 0; b < 3; ++b)
+        for (int c = 0; c < CH_T; ++c) a[r][c] = 0.0;
+    if (isS) {
+        // S tile = 2x2 landmark pairs: rows from landmarks 2TI, 2TI+1; columns from 2TK, 2TK+1
+        double P[2][2][9];
 #pragma unroll
-                    for (int a = 0; a < 3; ++a) P[u][a * 3 + b] = sp[(size_t)b * ld + a];
-            }
-        }
-        // W_c columns: warp w takes landmarks w, w+5, ... for state column s = 32 blockIdx + lane
-        const int s = blockIdx.x * CH_COLS + lane;
-        double w0[7], w1[7], w2[7];
+        for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int u = 0; u < 7; ++u) {
-            const int j = warp + u * CH_WARPS;
-            w0[u] = w1[u] = w2[u] = 0.0;
-            if (j < bc && s < dimp) {
-                const double* sp = Sig + (size_t)sm.Idx[j] * ld + s;  // Sigma[s, cols of j] (symmetric storage)
-                w0[u] = sp[0];
-                w1[u] = sp[ld];
-                w2[u] = sp[2 * (size_t)ld];
-            }
-        }
-        // residual: lane j of warp 1 takes landmark j
-        double g0 = 0, g1 = 0, g2 = 0, y0 = 0, y1 = 0;
-        if (warp == 1 && lane < bc) {
-            const int g = sm.Idx[lane];
-            g0 = GammaIn[g];
-            g1 = GammaIn[g + 1];
-            g2 = GammaIn[g + 2];
-            y0 = ytilde[2 * (j0 + lane)];
-            y1 = ytilde[2 * (j0 + lane) + 1];
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int t = tid + u * CH_THREADS;
-            if (t < npairs) {
-                const int j = pj[u], k = pk[u];
-                double T[6];
-#pragma unroll
-                for (int e = 0; e < 2; ++e)
+            for (int v = 0; v < 2; ++v) {
+                const int j = 2 * TI + u, k = 2 * TK + v;
+                if (j < bc && k < bc) {
+                    const double* sp = Sig + (size_t)sm.Idx[k] * ld + sm.Idx[j];  // Sigma[rows of j, cols of k]
 #pragma unroll
                     for (int b = 0; b < 3; ++b)
-                        T[e * 3 + b] = sm.C[j][3 * e] * P[u][b] + sm.C[j][3 * e + 1] * P[u][3 + b] + sm.C[j][3 * e + 2] * P[u][6 + b];
 #pragma unroll
-                for (int e = 0; e < 2; ++e)
+                        for (int aa = 0; aa < 3; ++aa) P[u][v][aa * 3 + b] = sp[(size_t)b * ld + aa];
+                }
+            }
 #pragma unroll
-                    for (int f = 0; f < 2; ++f) {
-                        double v = T[e * 3] * sm.C[k][3 * f] + T[e * 3 + 1] * sm.C[k][3 * f + 1] + T[e * 3 + 2] * sm.C[k][3 * f + 2];
-                        const int p = 2 * j + e, q = 2 * k + f;
-                        if (p == q) v += r2;
-                        if (p >= q) sm.L[q][p] = v;
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const int j = 2 * TI + u, k = 2 * TK + v;
+                if (j < bc && k < bc) {
+                    double T[6];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+#pragma unroll
+                        for (int b = 0; b < 3; ++b)
+                            T[e * 3 + b] = sm.C[j][3 * e] * P[u][v][b] + sm.C[j][3 * e + 1] * P[u][v][3 + b] + sm.C[j][3 * e + 2] * P[u][v][6 + b];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+#pragma unroll
+                        for (int f = 0; f < 2; ++f)
+                            a[2 * u + e][2 * v + f] = T[e * 3] * sm.C[k][3 * f] + T[e * 3 + 1] * sm.C[k][3 * f + 1] + T[e * 3 + 2] * sm.C[k][3 * f + 2];
+                }
+            }
+        if (TI == TK) {
+#pragma unroll
+            for (int c = 0; c < CH_T; ++c) {
+                if (CH_T * TI + c < rc)
+                    a[c][c] += r2;
+                else
+                    a[c][c] = 1.0;  // identity padding of a short last chunk
+            }
+        }
+    } else if (isRhs) {
+        const int trow = TI - CH_NT;
+        if (trow < CH_COLS / CH_T) {
+            // rows s = sbase + 4 trow + r (state columns of W_c), columns k = 4TK + c from landmarks 2TK, 2TK+1
+            const int s0 = sbase + CH_T * trow;
+            double w[2][3][CH_T];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const int j = 2 * TK + v;
+                if (j < bc && s0 < dimp) {
+                    const double* sp = Sig + (size_t)sm.Idx[j] * ld + s0;  // Sigma[s0.., cols of j] (symmetric storage)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        const double2 p01 = *reinterpret_cast<const double2*>(sp + (size_t)b * ld);
+                        const double2 p23 = *reinterpret_cast<const double2*>(sp + (size_t)b * ld + 2);
+                        w[v][b][0] = p01.x;
+                        w[v][b][1] = p01.y;
+                        w[v][b][2] = p23.x;
+                        w[v][b][3] = p23.y;
                     }
+                }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < 7; ++u) {
-            const int j = warp + u * CH_WARPS;
-            if (j < bc) {
-                sm.X[2 * j][lane] = sm.C[j][0] * w0[u] + sm.C[j][1] * w1[u] + sm.C[j][2] * w2[u];
-                sm.X[2 * j + 1][lane] = sm.C[j][3] * w0[u] + sm.C[j][4] * w1[u] + sm.C[j][5] * w2[u];
+            for (int v = 0; v < 2; ++v) {
+                const int j = 2 * TK + v;
+                if (j < bc && s0 < dimp) {
+#pragma unroll
+                    for (int r = 0; r < CH_T; ++r)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                            a[r][2 * v + e] = (s0 + r < dimp) ? sm.C[j][3 * e] * w[v][0][r] + sm.C[j][3 * e + 1] * w[v][1][r] + sm.C[j][3 * e + 2] * w[v][2][r] : 0.0;
+                }
+            }
+        } else {
+            // residual row (r = 0 of the last tile row): ytilde_c - C_c Gamma
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const int j = 2 * TK + v;
+                if (j < bc) {
+                    const int g = sm.Idx[j];
+                    const double g0 = GammaIn[g], g1 = GammaIn[g + 1], g2 = GammaIn[g + 2];
+                    a[0][2 * v] = ytilde[2 * (j0 + j)] - (sm.C[j][0] * g0 + sm.C[j][1] * g1 + sm.C[j][2] * g2);
+                    a[0][2 * v + 1] = ytilde[2 * (j0 + j) + 1] - (sm.C[j][3] * g0 + sm.C[j][4] * g1 + sm.C[j][5] * g2);
+                }
             }
         }
-        if (warp == 1 && lane < bc) {
-            sm.X[2 * lane][CH_COLS] = y0 - (sm.C[lane][0] * g0 + sm.C[lane][1] * g1 + sm.C[lane][2] * g2);
-            sm.X[2 * lane + 1][CH_COLS] = y1 - (sm.C[lane][3] * g0 + sm.C[lane][4] * g1 + sm.C[lane][5] * g2);
-        }
-        for (int t = rc + tid; t < CH_R; t += CH_THREADS) sm.L[t][t] = 1.0;  // identity padding of a short last chunk
     }
-    __syncthreads();
 
-    // ---- blocked right-looking elimination with unscaled columns (after it, column j holds v_ij = L_ij L_jj).
-    // Thread t < 136 keeps one 4x4 tile (TI >= TK) of the lower triangle in registers throughout.  Per block
-    // column J: the diagonal owner eliminates inside its tile and publishes it, the panel owners (TI > J, TK = J)
-    // finish their four columns and publish them, everybody else applies the rank-4 update: 2 barriers per 4 columns.
-    int TI = 0, TK = 0;
-    tri_decode(tid < CH_TILES ? tid : 0, TI, TK);
-    const bool owner = tid < CH_TILES;
-    double a[CH_T][CH_T];
-    if (owner) {
-#pragma unroll
-        for (int r = 0; r < CH_T; ++r)
-#pragma unroll
-            for (int c = 0; c < CH_T; ++c) a[r][c] = sm.L[CH_T * TK + c][CH_T * TI + r];  // upper entries of diagonal tiles: 0
-    }
     const int nJ = (rc + CH_T - 1) / CH_T;
     for (int J = 0; J < nJ; ++J) {
         const int buf = J & 1;
-        if (owner && TI == J && TK == J) {
+        if (isS && TI == J && TK == J) {
 #pragma unroll
             for (int j = 0; j < CH_T; ++j) {
                 const double c = fast_rcp(a[j][j]);
@@ -1049,7 +1065,7 @@ __global__ void __launch_bounds__(CH_THREADS)
 #pragma unroll
             for (int r = 0; r < CH_T; ++r)
 #pragma unroll
-                for (int j = 0; j < CH_T; ++j) sm.Pn[TI][r][j] = a[r][j];
+                for (int j = 0; j < CH_T; ++j) sm.Pn[r][j][TI] = a[r][j];
         }
         __syncthreads();
         if (owner && TK > J) {
@@ -1058,12 +1074,12 @@ __global__ void __launch_bounds__(CH_THREADS)
             for (int j = 0; j < CH_T; ++j) {
                 const double c = sm.Dc[buf][j];
 #pragma unroll
-                for (int r = 0; r < CH_T; ++r) li[r][j] = sm.Pn[TI][r][j] * c;
+                for (int r = 0; r < CH_T; ++r) li[r][j] = sm.Pn[r][j][TI] * c;
             }
 #pragma unroll
             for (int cc = 0; cc < CH_T; ++cc)
 #pragma unroll
-                for (int j = 0; j < CH_T; ++j) pk[cc][j] = sm.Pn[TK][cc][j];
+                for (int j = 0; j < CH_T; ++j) pk[cc][j] = sm.Pn[cc][j][TK];
 #pragma unroll
             for (int r = 0; r < CH_T; ++r)
 #pragma unroll
@@ -1075,8 +1091,8 @@ __global__ void __launch_bounds__(CH_THREADS)
                 }
         }
     }
-    // publish the diagonal, then the scaled factor
-    if (owner && TI == TK) {
+    // 1 / L_kk from the diagonal tiles
+    if (isS && TI == TK) {
 #pragma unroll
         for (int c = 0; c < CH_T; ++c) {
             const double piv = a[c][c];
@@ -1090,71 +1106,27 @@ __global__ void __launch_bounds__(CH_THREADS)
         }
     }
     __syncthreads();
-    if (owner) {
+    // Y[k][s] = v_sk / L_kk, staged so that the global store and the Gamma dot products run in a fixed order
+    if (isRhs) {
+        const int trow = TI - CH_NT;
 #pragma unroll
         for (int c = 0; c < CH_T; ++c) {
             const double sc = sm.Inv[CH_T * TK + c];
 #pragma unroll
-            for (int r = 0; r < CH_T; ++r) sm.L[CH_T * TK + c][CH_T * TI + r] = a[r][c] * sc;  // L[row][col] = v / L_colcol
+            for (int r = 0; r < CH_T; ++r) sm.Yt[CH_T * TK + c][CH_T * trow + r] = a[r][c] * sc;
         }
     }
     __syncthreads();
-
-    // ---- blocked forward substitution L x = w: x lives in shared memory, 16-row blocks in registers ----
-    const bool isResid = tid == CH_COLS;
-    const int xcol = isResid ? CH_COLS : lane;
-    if (warp == 0 || isResid) {
-#pragma unroll 1
-        for (int kb = 0; kb < CH_R / CH_SB; ++kb) {
-            const int k0 = kb * CH_SB;
-            double xb[CH_SB];
-#pragma unroll
-            for (int q = 0; q < CH_SB; ++q) xb[q] = sm.X[k0 + q][xcol];
-#pragma unroll
-            for (int q = 0; q < CH_SB; ++q) {
-                const double xq = xb[q] * sm.Inv[k0 + q];
-                xb[q] = xq;
-#pragma unroll
-                for (int c = q + 1; c < CH_SB; ++c) xb[c] -= sm.L[k0 + q][k0 + c] * xq;
-            }
-#pragma unroll
-            for (int q = 0; q < CH_SB; ++q) sm.X[k0 + q][xcol] = xb[q];
-#pragma unroll 1
-            for (int cb = kb + 1; cb < CH_R / CH_SB; ++cb) {
-                const int c0 = cb * CH_SB;
-                double xc[CH_SB];
-#pragma unroll
-                for (int c = 0; c < CH_SB; ++c) xc[c] = sm.X[c0 + c][xcol];
-#pragma unroll
-                for (int q = 0; q < CH_SB; ++q) {
-                    const double2* lp = reinterpret_cast<const double2*>(&sm.L[k0 + q][c0]);
-#pragma unroll
-                    for (int c = 0; c < CH_SB; c += 2) {
-                        const double2 l2 = lp[c / 2];
-                        xc[c] -= l2.x * xb[q];
-                        xc[c + 1] -= l2.y * xb[q];
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < CH_SB; ++c) sm.X[c0 + c][xcol] = xc[c];
-            }
-        }
+    // all CH_R rows are written (zero beyond rc and for the pad columns s >= dimp): the downdate reads whole tiles
+    for (int t = tid; t < CH_R * CH_COLS; t += CH_THREADS) {
+        const int k = t / CH_COLS, sl = t % CH_COLS;
+        Y[yb_index(k, sbase + sl)] = sm.Yt[k][sl];
     }
-    if (isResid) {
-        for (int k = 0; k < CH_R; ++k) sm.Z[k] = sm.X[k][CH_COLS];
-    }
-    __syncthreads();
-    // ---- Y rows (all CH_R of them: zero beyond rc and for the pad columns s >= dimp) and the running correction
-    if (warp == 0) {
-        const int s = blockIdx.x * CH_COLS + lane;
+    if (tid < CH_COLS && sbase + tid < dimp) {
         double g = 0.0;
 #pragma unroll 8
-        for (int k = 0; k < CH_R; ++k) {
-            const double v = sm.X[k][lane];
-            Y[yb_index(k, s)] = v;
-            g += v * sm.Z[k];
-        }
-        if (s < dimp) GammaOut[s] = GammaIn[s] + g;  // ping-pong: other CTAs may still be reading GammaIn
+        for (int k = 0; k < CH_R; ++k) g += sm.Yt[k][tid] * sm.Yt[k][CH_COLS];
+        GammaOut[sbase + tid] = GammaIn[sbase + tid] + g;  // ping-pong: other CTAs may still be reading GammaIn
     }
 }
 
