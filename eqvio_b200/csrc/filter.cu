@@ -78,13 +78,24 @@ struct eqvio_filter {
     size_t zElems = 0;
     double *d_Gamma2 = nullptr, *d_ytilde = nullptr;
     int corrMode = 0;    // 0: sequential chunks (default), 1: batch Cholesky sweep over Z
+    int speculate = 1;   // launch the correction before the gate results reach the host (redone on a gate hit)
+    int* d_spec = nullptr;  // [0] set by the gate kernel when any measured landmark exceeds a threshold, [1] constant 0
+    cudaEvent_t augEv[2] = {nullptr, nullptr};
+    bool augTimed = false;
     int chunkLm = 32;    // landmarks per chunk (<= CH_R / 2)
     double *d_Cblk = nullptr, *d_Gamma = nullptr, *d_gate = nullptr, *d_y = nullptr, *d_newP = nullptr, *d_out = nullptr;
     int *d_measIdx = nullptr, *d_lmOf = nullptr, *d_map = nullptr, *d_newIds = nullptr, *d_status = nullptr;
 
-    // pinned staging arena (reset at the start of every API call; calls end synchronised)
-    std::vector<std::pair<char*, size_t>> arenas;
-    size_t arenaUsed = 0;
+    // pinned staging: NA arena sets used in rotation, one per API call, so that a call may return while its
+    // async copies are still in flight (the set is waited for, through its event, before it is reused)
+    static constexpr int NA = 4;
+    struct ArenaSet {
+        std::vector<std::pair<char*, size_t>> blocks;
+        size_t used = 0;
+        cudaEvent_t ev = nullptr;
+        bool pending = false;
+    } arenaSets[NA];
+    int arenaCur = 0;
 
     // measurement hooks
     long long launches = 0;
@@ -111,6 +122,10 @@ struct eqvio_filter {
         int nStatus = 0;
         Camera cam;
         bool corrected = false;
+        bool speculated = false;       // correction launched before the gate results were read
+        std::vector<int> oldIds;       // state ids when the gate ran (gate results are indexed like this)
+        std::vector<char> measKept;    // per measurement: survives gating
+        int* h_spec = nullptr;
     } pend;
 };
 
@@ -129,32 +144,46 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int dimp_of(int N) { return SOFF + 3 * N; }
 
 void* stage_alloc(eqvio_filter* f, size_t bytes) {
+    auto& A = f->arenaSets[f->arenaCur];
     bytes = (bytes + 63) & ~size_t(63);
-    if (!f->arenas.empty()) {
-        auto& a = f->arenas.back();
-        if (f->arenaUsed + bytes <= a.second) {
-            void* p = a.first + f->arenaUsed;
-            f->arenaUsed += bytes;
+    if (!A.blocks.empty()) {
+        auto& a = A.blocks.back();
+        if (A.used + bytes <= a.second) {
+            void* p = a.first + A.used;
+            A.used += bytes;
             return p;
         }
     }
     size_t sz = std::max(bytes, size_t(1) << 20);
     char* p = nullptr;
     if (cudaMallocHost(&p, sz) != cudaSuccess) return nullptr;
-    f->arenas.emplace_back(p, sz);
-    f->arenaUsed = bytes;
+    A.blocks.emplace_back(p, sz);
+    A.used = bytes;
     return p;
 }
+// start of an API call: mark the set used by the previous call as in flight, move to the next one
 void stage_reset(eqvio_filter* f) {
-    // keep only the largest arena
-    while (f->arenas.size() > 1) {
-        size_t smallest = 0;
-        for (size_t i = 1; i < f->arenas.size(); ++i)
-            if (f->arenas[i].second < f->arenas[smallest].second) smallest = i;
-        cudaFreeHost(f->arenas[smallest].first);
-        f->arenas.erase(f->arenas.begin() + smallest);
+    {
+        auto& prev = f->arenaSets[f->arenaCur];
+        if (!prev.ev) cudaEventCreateWithFlags(&prev.ev, cudaEventDisableTiming);
+        cudaEventRecord(prev.ev, f->stream);
+        prev.pending = true;
     }
-    f->arenaUsed = 0;
+    f->arenaCur = (f->arenaCur + 1) % eqvio_filter::NA;
+    auto& A = f->arenaSets[f->arenaCur];
+    if (A.pending) {
+        cudaEventSynchronize(A.ev);
+        A.pending = false;
+    }
+    // keep only the largest block
+    while (A.blocks.size() > 1) {
+        size_t smallest = 0;
+        for (size_t i = 1; i < A.blocks.size(); ++i)
+            if (A.blocks[i].second < A.blocks[smallest].second) smallest = i;
+        cudaFreeHost(A.blocks[smallest].first);
+        A.blocks.erase(A.blocks.begin() + smallest);
+    }
+    A.used = 0;
 }
 
 template <class T>
@@ -302,6 +331,9 @@ int alloc_device(eqvio_filter* f) {
     CUDA_TRY(f, cudaMalloc(&f->d_newIds, c1 * sizeof(int)));
     CUDA_TRY(f, cudaMalloc(&f->d_status, (1 + c1) * sizeof(int)));
     CUDA_TRY(f, cudaMemsetAsync(f->d_status, 0, (1 + c1) * sizeof(int), f->stream));
+    CUDA_TRY(f, cudaMalloc(&f->d_spec, 2 * sizeof(int)));
+    CUDA_TRY(f, cudaMemsetAsync(f->d_spec, 0, 2 * sizeof(int), f->stream));
+    for (int i = 0; i < 2; ++i) CUDA_TRY(f, cudaEventCreate(&f->augEv[i]));
     for (int i = 0; i < 4; ++i) CUDA_TRY(f, cudaEventCreate(&f->stageEv[i]));
     return EQVIO_OK;
 }
@@ -563,39 +595,41 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
         else if (f->st.removeLostLandmarks)
             P.keep[i] = 0;  // removeOldLandmarks, VIOFilter.cpp:203-205
     }
+    P.oldIds = f->ids;
     if (N > 0) {
         if ((rc = upload(f, f->d_measIdx, P.measIdx.data(), N)) != EQVIO_OK) return rc;
+        CUDA_TRY(f, cudaMemsetAsync(f->d_spec, 0, sizeof(int), f->stream));
         gate_kernel<<<cdiv(N, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->Sig[f->cur], f->ld, f->d_measIdx,
-                                                          f->d_y, P.cam, f->st.coordinateChoice, f->d_gate);
+                                                          f->d_y, P.cam, f->st.coordinateChoice, f->d_gate, f->st.outlierThresholdAbs,
+                                                          f->st.outlierThresholdProb, f->d_spec);
         LAUNCH_CHECK(f, "gate_kernel");
         if ((rc = download_async(f, &P.h_gate, f->d_gate, 3 * (size_t)N)) != EQVIO_OK) return rc;
+        if ((rc = download_async(f, &P.h_spec, f->d_spec, 1)) != EQVIO_OK) return rc;
         P.gated = true;
     }
     return EQVIO_OK;
 }
 
-// ---- phase B: bookkeeping decisions on the host, compaction, correction launches -------------------
-int vision_phase_b(eqvio_filter* f) {
+// ---- bookkeeping decisions on the host (indices refer to P.oldIds, the state when the gate ran) -----------
+// removeOutliers (VIOFilter.cpp:304-364) from the gate scalars; useGate = false assumes that no landmark is gated.
+void decide_outliers(eqvio_filter* f, bool useGate, std::vector<char>& outlier) {
     auto& P = f->pend;
-    if (!P.active) return EQVIO_OK;
     const eqvio_settings& s = f->st;
-    int rc;
-    if (P.gated) CUDA_TRY(f, cudaStreamSynchronize(f->stream));
-    const int N = (int)f->ids.size();
+    const int N = (int)P.oldIds.size();
     const int n = P.n;
+    outlier.assign(N, 0);
+    P.measKept.assign(n, 1);
+    f->lastOutliers.clear();
+    if (!useGate || !P.h_gate) return;
     const double* errAbs = P.h_gate;
-    const double* errProb = P.h_gate ? P.h_gate + N : nullptr;
-    const double* depth2 = P.h_gate ? P.h_gate + 2 * N : nullptr;
-
-    // removeOutliers (VIOFilter.cpp:304-364): candidates are visited in ascending id like the
-    // reference's std::map iteration.
+    const double* errProb = P.h_gate + N;
     const size_t maxOutliers = (size_t)((1.0 - s.featureRetention) * n);
-    std::vector<int> order;  // state indices of measured, kept landmarks in ascending id
+    std::vector<int> order;  // measured, kept landmarks in ascending id like the reference's std::map iteration
     for (int i = 0; i < N; ++i)
         if (P.keep[i] && P.measIdx[i] >= 0) order.push_back(i);
-    std::sort(order.begin(), order.end(), [&](int a, int b) { return f->ids[a] < f->ids[b]; });
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return P.oldIds[a] < P.oldIds[b]; });
     std::vector<int> proposed;
-    std::map<int, double> absOut, probOut;  // keyed by state index
+    std::map<int, double> absOut, probOut;
     for (int i : order)
         if (errAbs[i] > s.outlierThresholdAbs) {
             absOut[i] = errAbs[i];
@@ -618,27 +652,50 @@ int vision_phase_b(eqvio_filter* f) {
     });
     std::reverse(proposed.begin(), proposed.end());
     if (proposed.size() > maxOutliers) proposed.resize(maxOutliers);
-    std::vector<char> measKept(n, 1);
     for (int i : proposed) {
-        P.keep[i] = 0;
-        measKept[P.measIdx[i]] = 0;
-        f->lastOutliers.push_back(f->ids[i]);
+        outlier[i] = 1;
+        P.measKept[P.measIdx[i]] = 0;
+        f->lastOutliers.push_back(P.oldIds[i]);
     }
+}
 
-    // addNewLandmarks (VIOFilter.cpp:258-278)
+int launch_correction(eqvio_filter* f, const int* guard);
+
+// ---- phase B: compaction and correction launches ---------------------------------------------------------
+int vision_phase_b(eqvio_filter* f) {
+    auto& P = f->pend;
+    if (!P.active) return EQVIO_OK;
+    const eqvio_settings& s = f->st;
+    int rc;
+    const int N = (int)f->ids.size();
+    const int n = P.n;
     std::vector<char> measInState(n, 0);
     for (int i = 0; i < N; ++i)
         if (P.measIdx[i] >= 0) measInState[P.measIdx[i]] = 1;
+    bool anyNew = false;
+    for (int j = 0; j < n; ++j) anyNew |= !measInState[j];
+    const size_t maxOutliers = (size_t)((1.0 - s.featureRetention) * n);
+    // Speculation: with no new ids the only thing the host needs from the device is "did any landmark trip a
+    // gate".  The correction is launched right away, guarded on the device by that flag; phase C redoes it
+    // through the exact path in the (rare) case the flag came back set.
+    P.speculated = f->speculate && f->corrMode == 0 && P.gated && !anyNew && maxOutliers > 0;
+    const bool noGateNeeded = !P.gated || (maxOutliers == 0 && !(anyNew && s.useMedianDepth));
+    if (!P.speculated && !noGateNeeded) CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+    std::vector<char> outlier;
+    decide_outliers(f, !P.speculated && !noGateNeeded, outlier);
+    std::vector<char> keep(N);
+    for (int i = 0; i < N; ++i) keep[i] = P.keep[i] && !outlier[i];
+
+    // addNewLandmarks (VIOFilter.cpp:258-278)
     std::vector<int> addIds;
     std::vector<double> addP;
-    for (int j = 0; j < n; ++j)
-        if (!measInState[j]) addIds.push_back(P.mids[j]);
-    if (!addIds.empty()) {
+    if (anyNew) {
         double depth = s.initialSceneDepth;
-        if (s.useMedianDepth) {  // getMedianSceneDepth, VIOFilter.cpp:366-380
+        if (s.useMedianDepth && P.h_gate) {  // getMedianSceneDepth, VIOFilter.cpp:366-380
+            const double* depth2 = P.h_gate + 2 * N;
             std::vector<double> d2;
             for (int i = 0; i < N; ++i)
-                if (P.keep[i]) d2.push_back(depth2[i]);
+                if (keep[i]) d2.push_back(depth2[i]);
             if (!d2.empty()) {
                 auto mid = d2.begin() + d2.size() / 2;
                 std::nth_element(d2.begin(), mid, d2.end());
@@ -647,25 +704,35 @@ int vision_phase_b(eqvio_filter* f) {
         }
         for (int j = 0; j < n; ++j)
             if (!measInState[j]) {
+                addIds.push_back(P.mids[j]);
                 V3 b = cam_undistort(P.cam, P.my[2 * j], P.my[2 * j + 1]);
                 addP.push_back(b.x * depth);
                 addP.push_back(b.y * depth);
                 addP.push_back(b.z * depth);
             }
     }
-    if ((rc = remove_and_append(f, P.keep, addIds, addP, s.initialPointVariance, -1.0)) != EQVIO_OK) return rc;
+    if ((rc = remove_and_append(f, keep, addIds, addP, s.initialPointVariance, -1.0)) != EQVIO_OK) return rc;
     stage_mark(f, 2);
+    return launch_correction(f, P.speculated ? f->d_spec : f->d_spec + 1);
+}
 
-    // measurement restricted to the kept ids (ascending)
+// performVisionUpdate (VIO_eqf.cpp:105-135) on the measurement restricted to P.measKept.  Every kernel returns
+// at once when *guard != 0.
+int launch_correction(eqvio_filter* f, const int* guard) {
+    auto& P = f->pend;
+    const eqvio_settings& s = f->st;
+    int rc;
+    const int n = P.n;
     std::vector<int> kmids;
     std::vector<double> ky;
     for (int j = 0; j < n; ++j)
-        if (measKept[j]) {
+        if (P.measKept[j]) {
             kmids.push_back(P.mids[j]);
             ky.push_back(P.my[2 * j]);
             ky.push_back(P.my[2 * j + 1]);
         }
     const int nm = (int)kmids.size();
+    P.corrected = false;
     if (nm == 0) {  // VIOFilter.cpp:223-224
         stage_mark(f, 3);
         return EQVIO_OK;
@@ -694,7 +761,7 @@ int vision_phase_b(eqvio_filter* f) {
         const int T = ldy / DD_T;
         double* Y = f->d_Z;
         meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, P.cam, s.coordinateChoice,
-                                                          s.useEquivariantOutput ? 1 : 0, f->d_Cblk, f->d_ytilde, 1, 0);
+                                                          s.useEquivariantOutput ? 1 : 0, f->d_Cblk, f->d_ytilde, 1, 0, guard);
         LAUNCH_CHECK(f, "meas_kernel");
         double* gin = f->d_Gamma;
         double* gout = f->d_Gamma2;
@@ -704,11 +771,11 @@ int vision_phase_b(eqvio_filter* f) {
             const int bc = std::min(bcMax, nm - j0);
             int pk = prof_begin(f, PROF_PANEL);
             chunk_factor_kernel<<<ldy / CH_COLS, CH_THREADS, 0, f->stream>>>(
-                f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Y, f->d_status);
+                f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Y, f->d_status, guard);
             prof_end(f, pk);
             LAUNCH_CHECK(f, "chunk_factor_kernel");
             int sk = prof_begin(f, PROF_SYRK);
-            chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->ld, Y);
+            chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->ld, Y, guard);
             prof_end(f, sk);
             LAUNCH_CHECK(f, "chunk_downdate_kernel");
             std::swap(gin, gout);
@@ -716,7 +783,7 @@ int vision_phase_b(eqvio_filter* f) {
         gammaFinal = gin;
     } else {
     meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, P.cam, s.coordinateChoice,
-                                                      s.useEquivariantOutput ? 1 : 0, f->d_Cblk, Z, ldz, m + dimp);
+                                                      s.useEquivariantOutput ? 1 : 0, f->d_Cblk, Z, ldz, m + dimp, guard);
     LAUNCH_CHECK(f, "meas_kernel");
     zbuild_kernel<<<dim3(cdiv(dimp, 256), nm), 256, 0, f->stream>>>(f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, Z, ldz, m);
     LAUNCH_CHECK(f, "zbuild_kernel");
@@ -752,7 +819,7 @@ int vision_phase_b(eqvio_filter* f) {
     }
     lift_kernel<<<cdiv(std::max(Nn, 1), 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, Nn, f->d_xi0s, f->d_Xs[f->xcur], gammaFinal,
                                                                    s.useDiscreteInnovationLift ? 1 : 0, s.coordinateChoice,
-                                                                   f->d_status, f->d_status + 1);
+                                                                   f->d_status, f->d_status + 1, guard);
     LAUNCH_CHECK(f, "lift_kernel");
     stage_mark(f, 3);
     P.nStatus = 1 + Nn;
@@ -772,8 +839,26 @@ int vision_phase_c(eqvio_filter* f, int* did_update) {
             float ms = 0;
             if (cudaEventElapsedTime(&ms, f->stageEv[i], f->stageEv[i + 1]) == cudaSuccess) f->stageMs[i] = ms;
         }
-        f->stageMs[1] += f->augMs;
-        f->augMs = 0;
+        if (f->augTimed) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, f->augEv[0], f->augEv[1]) == cudaSuccess) f->stageMs[1] += ms;
+            f->augTimed = false;
+        }
+    }
+    if (P.active && P.speculated && P.h_spec && *P.h_spec != 0) {
+        // a gate tripped: the guarded correction did nothing.  Decide exactly (the gate scalars are on the host
+        // by now), remove the outliers from the already lost-compacted state and correct without a guard.
+        P.speculated = false;
+        std::vector<char> outlier;
+        decide_outliers(f, true, outlier);
+        std::vector<char> keepNow;
+        for (size_t i = 0; i < P.oldIds.size(); ++i)
+            if (P.keep[i]) keepNow.push_back(!outlier[i]);
+        int rc = remove_and_append(f, keepNow, {}, {}, 0.0, -1.0);
+        if (rc == EQVIO_OK) rc = launch_correction(f, f->d_spec + 1);
+        if (rc != EQVIO_OK) return rc;
+        CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+        prof_collect(f);
     }
     if (!P.active || !P.corrected) {
         P.active = false;
@@ -1066,7 +1151,13 @@ void eqvio_destroy(eqvio_filter* f) {
     cudaFree(f->d_map);
     cudaFree(f->d_newIds);
     cudaFree(f->d_status);
-    for (auto& a : f->arenas) cudaFreeHost(a.first);
+    cudaFree(f->d_spec);
+    for (int i = 0; i < 2; ++i)
+        if (f->augEv[i]) cudaEventDestroy(f->augEv[i]);
+    for (auto& A : f->arenaSets) {
+        for (auto& a : A.blocks) cudaFreeHost(a.first);
+        if (A.ev) cudaEventDestroy(A.ev);
+    }
     for (auto& p : f->evPool) {
         cudaEventDestroy(p.a);
         cudaEventDestroy(p.b);
@@ -1179,16 +1270,14 @@ int eqvio_augment_landmark_states(eqvio_filter* f, int n_new, const int* new_ids
         addIds.push_back(new_ids[j]);
         for (int a = 0; a < 3; ++a) addP.push_back(provided_p[3 * it->second + a]);
     }
-    stage_mark(f, 0);
+    if (f->stageTiming) cudaEventRecord(f->augEv[0], f->stream);
     int rc = remove_and_append(f, keep, addIds, addP, f->st.initialPointVariance, -1.0);
     if (rc != EQVIO_OK) return rc;
-    stage_mark(f, 1);
-    CUDA_TRY(f, cudaStreamSynchronize(f->stream));
     if (f->stageTiming) {
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, f->stageEv[0], f->stageEv[1]) == cudaSuccess) f->augMs += ms;
+        cudaEventRecord(f->augEv[1], f->stream);
+        f->augTimed = true;
     }
-    return EQVIO_OK;
+    return EQVIO_OK;  // asynchronous: the next call on this handle is ordered behind it on the stream
 }
 
 int eqvio_process_imu(eqvio_filter* f, double stamp, const double gyr[3], const double acc[3], const double gyr_bias_vel[3],
@@ -1393,6 +1482,9 @@ int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
         case EQVIO_TUNE_CORRECTION:
             if (value != 0 && value != 1) return EQVIO_ERR_INVALID_ARG;
             f->corrMode = value;
+            return EQVIO_OK;
+        case EQVIO_TUNE_SPECULATE:
+            f->speculate = value != 0;
             return EQVIO_OK;
         case EQVIO_TUNE_CHUNK_LANDMARKS:
             if (value < 1 || value > CH_R / 2) return EQVIO_ERR_INVALID_ARG;

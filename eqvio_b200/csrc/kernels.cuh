@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(TP* TP)
 // ------------------------------------------------------------------------------------------------
 __global__ void gate_kernel(const double* __restrict__ lm, int cap, int N, const double* __restrict__ Sig, int ld,
                             const int* __restrict__ measIdx, const double* __restrict__ y, Camera cam, int coord,
-                            double* __restrict__ out) {
+                            double* __restrict__ out, double thrAbs, double thrProb, int* __restrict__ tripped) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
@@ -533,7 +533,9 @@ __global__ void gate_kernel(const double* __restrict__ lm, int cap, int N, const
     double det = c00 * c11 - c01 * c10;
     // y^T cov^-1 y with the 2x2 adjugate inverse (Eigen fixed-size inverse)
     double i00 = c11 / det, i01 = -c01 / det, i10 = -c10 / det, i11 = c00 / det;
-    out[N + i] = d0 * (i00 * d0 + i01 * d1) + d1 * (i10 * d0 + i11 * d1);
+    const double eProb = d0 * (i00 * d0 + i01 * d1) + d1 * (i10 * d0 + i11 * d1);
+    out[N + i] = eProb;
+    if (out[i] > thrAbs || eProb > thrProb) atomicOr(tripped, 1);  // same comparisons as the host decision
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -613,9 +615,10 @@ __global__ void fill_ll_diag_kernel(double* __restrict__ S, int ld, int n3, doub
 // ------------------------------------------------------------------------------------------------
 __global__ void meas_kernel(const double* __restrict__ lm, int cap, const int* __restrict__ lmOf, int n,
                             const double* __restrict__ y, Camera cam, int coord, int useStar,
-                            double* __restrict__ Cblk, double* __restrict__ Z, int ldz, int yrow) {
+                            double* __restrict__ Cblk, double* __restrict__ Z, int ldz, int yrow,
+                            const int* __restrict__ guard) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+    if (j >= n || *guard) return;
     int i = lmOf[j];
     V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
     Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
@@ -910,7 +913,8 @@ __global__ void __launch_bounds__(CH_THREADS)
     chunk_factor_kernel(const double* __restrict__ Sig, int ld, int dimp, const int* __restrict__ lmOf,
                         const double* __restrict__ Cblk, const double* __restrict__ ytilde, int j0, int bc, double r2,
                         const double* __restrict__ GammaIn, double* __restrict__ GammaOut, double* __restrict__ Y,
-                        int* __restrict__ status) {
+                        int* __restrict__ status, const int* __restrict__ guard) {
+    if (*guard) return;
     __shared__ ChunkSmem sm;
     const int tid = threadIdx.x;
     const int rc = 2 * bc;
@@ -1169,7 +1173,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 __global__ void __launch_bounds__(DD_THREADS, 3)
-    chunk_downdate_kernel(double* __restrict__ Sig, int ld, const double* __restrict__ Y) {
+    chunk_downdate_kernel(double* __restrict__ Sig, int ld, const double* __restrict__ Y, const int* __restrict__ guard) {
+    if (*guard) return;
     int ti, tj;
     tri_decode(blockIdx.x, ti, tj);  // lower-triangular tile index -> (ti, tj), ti >= tj
     extern __shared__ __align__(16) unsigned char dd_smem_raw[];
@@ -1260,7 +1265,8 @@ __global__ void gamma_kernel(const double* __restrict__ Z, int ldz, int m, int d
 // ------------------------------------------------------------------------------------------------
 __global__ void lift_kernel(double* __restrict__ lm, int cap, int N, const double* __restrict__ xi0s,
                             double* __restrict__ Xs, const double* __restrict__ Gamma, int discrete, int coord,
-                            int* __restrict__ status, int* __restrict__ invalidFlag) {
+                            int* __restrict__ status, int* __restrict__ invalidFlag, const int* __restrict__ guard) {
+    if (*guard) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         SensorState xi0 = unpack_sensor(xi0s);

@@ -173,9 +173,14 @@ int eqvio_get_kernel_profile(eqvio_filter* f, int reset, double ms[EQVIO_PROF_CL
 /* Evaluation-order knobs of the correction (results agree to rounding; tests run both).
  *   EQVIO_TUNE_CORRECTION: 0 = sequential landmark chunks exploiting C's block sparsity (default),
  *                          1 = batch form: Cholesky sweep over [S; W^T; ytilde^T], then Sigma -= Y^T Y.
- *   EQVIO_TUNE_CHUNK_LANDMARKS: landmarks per chunk in mode 0 (1..32, default 32). */
+ *   EQVIO_TUNE_CHUNK_LANDMARKS: landmarks per chunk in mode 0 (1..32, default 32).
+ *   EQVIO_TUNE_SPECULATE: 1 (default) = when a frame brings no new ids, launch the correction before the
+ *                          gate scalars reach the host, guarded on the device by a "gate tripped" flag, and
+ *                          redo it through the exact host decision path if the flag came back set; 0 = always
+ *                          wait for the gate.  Same results either way. */
 #define EQVIO_TUNE_CORRECTION 0
 #define EQVIO_TUNE_CHUNK_LANDMARKS 1
+#define EQVIO_TUNE_SPECULATE 2
 int eqvio_set_tuning(eqvio_filter* f, int key, int value);
 /* Version / build info string (arch the kernels were compiled for). */
 const char* eqvio_build_info(void);

@@ -57,14 +57,16 @@ def test_non_equivariant_output():
     _check(run_gpu(stream), run_oracle(stream))
 
 
-def test_gating_and_noise_identical_indexing():
+@pytest.mark.parametrize("speculate", [1, 0])
+def test_gating_and_noise_identical_indexing(speculate):
     """Outlier gating (absolute + probabilistic, capped by featureRetention) with noisy inputs: the
-    discrete decisions must match the oracle's, update by update."""
+    discrete decisions must match the oracle's, update by update -- both when the correction is launched
+    speculatively (and redone after a gate hit) and when the host waits for the gate."""
     stream = make_stream(N=48, frames=10, coord=0,
                          settings_overrides=dict(outlierThresholdAbs=3.0, outlierThresholdProb=6.0, measurementNoise=0.5,
                                                  featureRetention=0.2),
                          sim_overrides=dict(outputNoise=True, inputNoise=True))
-    gpu, ref = run_gpu(stream), run_oracle(stream)
+    gpu, ref = run_gpu(stream, tuning=dict(speculate=speculate)), run_oracle(stream)
     _check(gpu, ref)
     assert any(len(r["ids"]) < 48 for r in ref), "the case is meant to exercise outlier removal"
 
