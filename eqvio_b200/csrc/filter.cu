@@ -71,9 +71,29 @@ struct eqvio_filter {
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     RiccatiCtx* d_ctx = nullptr;
     ObsStep* d_steps = nullptr;
+    // per-frame input block (FrameHeader | imu | y | measIdx | lmOf) at fixed device / pinned addresses
+    unsigned char* d_frame = nullptr;
+    unsigned char* h_frame = nullptr;
+    size_t frameBytes = 0, offImu = 0, offY = 0, offMeasIdx = 0, offLmOf = 0;
+    FrameHeader* d_hdr = nullptr;
     double* d_imu = nullptr;
     int maxSteps = 0;
     int yCap = 0;
+    // fixed pinned output block of the steady path: gate scalars | spec flag | status words
+    unsigned char* h_out = nullptr;
+    size_t outOffSpec = 0, outOffStatus = 0;
+    // CUDA graphs of the steady-state update, keyed by everything that shapes the launch sequence
+    struct GraphEntry {
+        cudaGraphExec_t exec = nullptr;
+        int cur2 = 0, lmcur2 = 0, xcur2 = 0;
+        long long launches = 0;
+        unsigned long long lastUse = 0;
+    };
+    std::map<std::vector<int>, GraphEntry> graphs;
+    unsigned long long graphClock = 0;
+    int useGraph = 1;
+    long long graphLaunches = 0, graphCaptures = 0;
+    double updateMs = 0;
     double *d_rows = nullptr, *d_uv = nullptr, *d_Z = nullptr, *d_Lout = nullptr;
     size_t zElems = 0;
     double *d_Gamma2 = nullptr, *d_ytilde = nullptr;
@@ -123,6 +143,8 @@ struct eqvio_filter {
         Camera cam;
         bool corrected = false;
         bool speculated = false;       // correction launched before the gate results were read
+        bool steady = false;           // phase A enqueued the whole update (possibly as a CUDA graph)
+        bool ignoreGate = false;       // featureRetention leaves no room for removals: the gate flag is moot
         std::vector<int> oldIds;       // state ids when the gate ran (gate results are indexed like this)
         std::vector<char> measKept;    // per measurement: survives gating
         int* h_spec = nullptr;
@@ -286,6 +308,38 @@ void initial_diag(const eqvio_settings& s, int N, bool depthVariance, std::vecto
                 (a == 2 && depthVariance && s.initialPointDepthVariance > 0) ? s.initialPointDepthVariance : s.initialPointVariance;
 }
 
+// (re)allocate the per-frame input block for `steps` IMU segments and `ycap` measured landmarks
+int alloc_frame(eqvio_filter* f, int steps, int ycap) {
+    for (auto& g : f->graphs)
+        if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    f->graphs.clear();
+    cudaFree(f->d_frame);
+    cudaFree(f->d_steps);
+    if (f->h_frame) cudaFreeHost(f->h_frame);
+    f->d_frame = nullptr;
+    f->h_frame = nullptr;
+    f->d_steps = nullptr;
+    f->maxSteps = steps;
+    f->yCap = ycap;
+    const size_t cap1 = std::max(f->cap, 1);
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    f->offImu = up(sizeof(FrameHeader));
+    f->offY = up(f->offImu + (size_t)steps * 13 * sizeof(double));
+    f->offMeasIdx = up(f->offY + (size_t)ycap * 2 * sizeof(double));
+    f->offLmOf = up(f->offMeasIdx + cap1 * sizeof(int));
+    f->frameBytes = up(f->offLmOf + cap1 * sizeof(int));
+    CUDA_TRY(f, cudaMalloc(&f->d_frame, f->frameBytes));
+    CUDA_TRY(f, cudaMallocHost(&f->h_frame, f->frameBytes));
+    std::memset(f->h_frame, 0, f->frameBytes);
+    CUDA_TRY(f, cudaMalloc(&f->d_steps, (size_t)steps * sizeof(ObsStep)));
+    f->d_hdr = reinterpret_cast<FrameHeader*>(f->d_frame);
+    f->d_imu = reinterpret_cast<double*>(f->d_frame + f->offImu);
+    f->d_y = reinterpret_cast<double*>(f->d_frame + f->offY);
+    f->d_measIdx = reinterpret_cast<int*>(f->d_frame + f->offMeasIdx);
+    f->d_lmOf = reinterpret_cast<int*>(f->d_frame + f->offLmOf);
+    return EQVIO_OK;
+}
+
 int alloc_device(eqvio_filter* f) {
     const int cap = f->cap;
     const int dimpMax = dimp_of(cap);
@@ -305,9 +359,10 @@ int alloc_device(eqvio_filter* f) {
     CUDA_TRY(f, cudaEventCreateWithFlags(&f->evFork, cudaEventDisableTiming));
     CUDA_TRY(f, cudaEventCreateWithFlags(&f->evJoin, cudaEventDisableTiming));
     CUDA_TRY(f, cudaMalloc(&f->d_ctx, sizeof(RiccatiCtx)));
-    f->maxSteps = 64;
-    CUDA_TRY(f, cudaMalloc(&f->d_steps, f->maxSteps * sizeof(ObsStep)));
-    CUDA_TRY(f, cudaMalloc(&f->d_imu, f->maxSteps * 13 * sizeof(double)));
+    {
+        int rcf = alloc_frame(f, 64, std::max(cap, 1));
+        if (rcf != EQVIO_OK) return rcf;
+    }
     const size_t c1 = std::max(cap, 1);
     CUDA_TRY(f, cudaMalloc(&f->d_rows, c1 * ROWS_STRIDE * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_uv, c1 * UV_STRIDE * sizeof(double)));
@@ -321,12 +376,11 @@ int alloc_device(eqvio_filter* f) {
     CUDA_TRY(f, cudaMalloc(&f->d_Gamma2, (size_t)(dimpMax + 8) * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_ytilde, 2 * c1 * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_gate, c1 * 3 * sizeof(double)));
-    f->yCap = (int)c1;
-    CUDA_TRY(f, cudaMalloc(&f->d_y, c1 * 2 * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_newP, c1 * 3 * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_out, (23 + 3 * c1) * sizeof(double)));
-    CUDA_TRY(f, cudaMalloc(&f->d_measIdx, c1 * sizeof(int)));
-    CUDA_TRY(f, cudaMalloc(&f->d_lmOf, c1 * sizeof(int)));
+    f->outOffSpec = ((3 * c1 * sizeof(double)) + 63) & ~size_t(63);
+    f->outOffStatus = f->outOffSpec + 64;
+    CUDA_TRY(f, cudaMallocHost(&f->h_out, f->outOffStatus + (1 + c1) * sizeof(int)));
     CUDA_TRY(f, cudaMalloc(&f->d_map, c1 * sizeof(int)));
     CUDA_TRY(f, cudaMalloc(&f->d_newIds, c1 * sizeof(int)));
     CUDA_TRY(f, cudaMalloc(&f->d_status, (1 + c1) * sizeof(int)));
@@ -439,8 +493,9 @@ int remove_and_append(eqvio_filter* f, const std::vector<char>& keep, const std:
     return apply_map(f, map, addIds, addP, newVar, newDepthVar);
 }
 
-// integrateUpToTime (VIOFilter.cpp:134-192).  *advanced = 0 reproduces the reference's `return false`.
-int integrate_up_to_time(eqvio_filter* f, double newTime, int* advanced) {
+// integrateUpToTime (VIOFilter.cpp:134-192), host part: segment lengths, time-weighted mean IMU, buffer pruning.
+// *advanced = 0 reproduces the reference's `return false`.  Fills the frame header / IMU rows in h_frame.
+int plan_integration(eqvio_filter* f, double newTime, int* advanced) {
     *advanced = 0;
     if (newTime <= f->time || f->time < 0 || f->buf.empty()) return EQVIO_OK;
     const eqvio_settings& s = f->st;
@@ -449,8 +504,13 @@ int integrate_up_to_time(eqvio_filter* f, double newTime, int* advanced) {
         return EQVIO_ERR_UNSUPPORTED;
     }
     const int n = (int)f->buf.size();
-    const int N = (int)f->ids.size();
-    std::vector<double> imu((size_t)13 * n);
+    if (n > f->maxSteps) {
+        CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+        int rc = alloc_frame(f, 2 * n, f->yCap);
+        if (rc != EQVIO_OK) return rc;
+    }
+    FrameHeader* hdr = reinterpret_cast<FrameHeader*>(f->h_frame);
+    double* imu = reinterpret_cast<double*>(f->h_frame + f->offImu);
     double accT = 0.0, acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < n; ++i) {
         const double t0 = std::max(f->buf[i].stamp, f->time);
@@ -462,29 +522,34 @@ int integrate_up_to_time(eqvio_filter* f, double newTime, int* advanced) {
         for (int k = 0; k < 12; ++k) acc[k] = acc[k] + f->buf[i].v[k] * dt;
     }
     const double inv = 1.0 / accT;
-    for (int k = 0; k < 12; ++k) acc[k] = acc[k] * inv;
+    for (int k = 0; k < 12; ++k) hdr->fs.meanImu[k] = acc[k] * inv;
+    hdr->fs.dtTotal = accT;
+    hdr->fs.nsteps = n;
+    hdr->fs.pad = 0;
+    f->time = newTime;
+    // prune, keeping the last sample with stamp < currentTime (VIOFilter.cpp:183-189)
+    size_t k = 0;
+    while (k < f->buf.size() && !(f->buf[k].stamp >= f->time)) ++k;
+    if (k != 0) f->buf.erase(f->buf.begin(), f->buf.begin() + (k - 1));
+    *advanced = 1;
+    return EQVIO_OK;
+}
 
-    if (n > f->maxSteps) {
-        CUDA_TRY(f, cudaStreamSynchronize(f->stream));
-        cudaFree(f->d_steps);
-        cudaFree(f->d_imu);
-        f->maxSteps = n * 2;
-        CUDA_TRY(f, cudaMalloc(&f->d_steps, f->maxSteps * sizeof(ObsStep)));
-        CUDA_TRY(f, cudaMalloc(&f->d_imu, f->maxSteps * 13 * sizeof(double)));
-    }
-    int rc;
-    if ((rc = upload(f, f->d_imu, imu.data(), imu.size())) != EQVIO_OK) return rc;
-
+// Device part of the propagation; the frame block must already be on its way to the device on f->stream.
+// Two independent chains (VIOFilter.cpp:138 "the Riccati propagation ... does not affect the state propagation"):
+//   stream : Riccati  -- context + Sigma_ss, landmark rows, strips, landmark-landmark block (reads X, Q *before*)
+//   stream2: observer -- sensor part of every IMU segment, then the landmark part (writes the other X / lm buffers)
+int enqueue_propagation(eqvio_filter* f) {
+    const eqvio_settings& s = f->st;
+    const int N = (int)f->ids.size();
     PrepArgs a;
     a.xi0s = f->d_xi0s;
     a.Xs = f->d_Xs[f->xcur];
     a.XsOut = f->d_Xs[1 - f->xcur];
     a.ctx = f->d_ctx;
     a.steps = f->d_steps;
+    a.fr = f->d_hdr;
     a.imu = f->d_imu;
-    a.nsteps = n;
-    for (int k = 0; k < 12; ++k) a.meanImu[k] = acc[k];
-    a.dtTotal = accT;
     a.discreteLift = s.useDiscreteVelocityLift ? 1 : 0;
     a.qdiag[0] = s.velGyrNoise * s.velGyrNoise;
     a.qdiag[1] = s.velAccNoise * s.velAccNoise;
@@ -498,16 +563,13 @@ int integrate_up_to_time(eqvio_filter* f, double newTime, int* advanced) {
     a.pdiag[5] = s.cameraAttitudeProcessVariance;
     a.pdiag[6] = s.cameraPositionProcessVariance;
     a.pdiag[7] = s.pointProcessVariance;
-    // Two independent chains (VIOFilter.cpp:138 "the Riccati propagation ... does not affect the state propagation"):
-    //   stream : Riccati  -- context + Sigma_ss, landmark rows, strips, landmark-landmark block (reads X, Q *before*)
-    //   stream2: observer -- sensor part of every IMU segment, then the landmark part (writes the other X / lm buffers)
     CUDA_TRY(f, cudaEventRecord(f->evFork, f->stream));
     CUDA_TRY(f, cudaStreamWaitEvent(f->stream2, f->evFork, 0));
     observer_sensor_kernel<<<1, 32, 0, f->stream2>>>(a);
     LAUNCH_CHECK(f, "observer_sensor_kernel");
     if (N > 0) {
         observer_landmark_kernel<<<cdiv(N, 64), 64, 0, f->stream2>>>(f->lm[f->lmcur], f->lm[1 - f->lmcur], f->dids[f->lmcur],
-                                                                     f->dids[1 - f->lmcur], f->cap, N, f->d_steps, n);
+                                                                     f->dids[1 - f->lmcur], f->cap, N, f->d_steps, f->d_hdr);
         LAUNCH_CHECK(f, "observer_landmark_kernel");
     }
     CUDA_TRY(f, cudaEventRecord(f->evJoin, f->stream2));
@@ -532,16 +594,37 @@ int integrate_up_to_time(eqvio_filter* f, double newTime, int* advanced) {
     CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->evJoin, 0));
     f->xcur = 1 - f->xcur;
     if (N > 0) f->lmcur = 1 - f->lmcur;
-    f->time = newTime;
-    // prune, keeping the last sample with stamp < currentTime (VIOFilter.cpp:183-189)
-    size_t k = 0;
-    while (k < f->buf.size() && !(f->buf[k].stamp >= f->time)) ++k;
-    if (k != 0) f->buf.erase(f->buf.begin(), f->buf.begin() + (k - 1));
-    *advanced = 1;
     return EQVIO_OK;
 }
 
-// ---- process_vision, phase A: propagate, launch the gate, start its download ---------------------
+int enqueue_gate(eqvio_filter* f, int N) {
+    CUDA_TRY(f, cudaMemsetAsync(f->d_spec, 0, sizeof(int), f->stream));
+    gate_kernel<<<cdiv(N, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->Sig[f->cur], f->ld, f->d_measIdx, f->d_y,
+                                                      f->d_hdr, f->st.coordinateChoice, f->d_gate, f->st.outlierThresholdAbs,
+                                                      f->st.outlierThresholdProb, f->d_spec);
+    LAUNCH_CHECK(f, "gate_kernel");
+    return EQVIO_OK;
+}
+
+int enqueue_correction(eqvio_filter* f, int nm, const int* guard);
+
+// The whole device side of a steady frame (no landmark enters or leaves before the gate): frame upload,
+// propagation, gate, guarded correction, result downloads into the fixed pinned block.  Issued either directly
+// or under stream capture (then replayed as one CUDA graph).
+int enqueue_steady_update(eqvio_filter* f, int N, int nm) {
+    int rc;
+    CUDA_TRY(f, cudaMemcpyAsync(f->d_frame, f->h_frame, f->frameBytes, cudaMemcpyHostToDevice, f->stream));
+    if ((rc = enqueue_propagation(f)) != EQVIO_OK) return rc;
+    if ((rc = enqueue_gate(f, N)) != EQVIO_OK) return rc;
+    CUDA_TRY(f, cudaMemcpyAsync(f->h_out, f->d_gate, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+    CUDA_TRY(f, cudaMemcpyAsync(f->h_out + f->outOffSpec, f->d_spec, sizeof(int), cudaMemcpyDeviceToHost, f->stream));
+    if ((rc = enqueue_correction(f, nm, f->d_spec)) != EQVIO_OK) return rc;
+    CUDA_TRY(f, cudaMemcpyAsync(f->h_out + f->outOffStatus, f->d_status, (1 + (size_t)N) * sizeof(int), cudaMemcpyDeviceToHost,
+                                f->stream));
+    return EQVIO_OK;
+}
+
+// ---- process_vision, phase A: plan, classify the frame, enqueue ---------------------------------------------
 int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const double* y, const eqvio_camera* cam) {
     auto& P = f->pend;
     P = eqvio_filter::Pending();
@@ -560,22 +643,13 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
         f->err = "unsupported camera model";
         return EQVIO_ERR_UNSUPPORTED;
     }
-    // inputs (pixels) are staged in HBM before the first timing event; the IMU samples follow inside
-    // integrate_up_to_time (1 KB) and are counted with the propagation stage
     int rc;
     if (n > f->yCap) {  // a measurement may list more ids than the state can hold (gated later)
         CUDA_TRY(f, cudaStreamSynchronize(f->stream));
-        cudaFree(f->d_y);
-        f->d_y = nullptr;
-        f->yCap = 2 * n;
-        CUDA_TRY(f, cudaMalloc(&f->d_y, (size_t)f->yCap * 2 * sizeof(double)));
+        if ((rc = alloc_frame(f, f->maxSteps, 2 * n)) != EQVIO_OK) return rc;
     }
-    if (n > 0 && (rc = upload(f, f->d_y, y, 2 * (size_t)n)) != EQVIO_OK) return rc;
-    stage_mark(f, 0);
     int advanced = 0;
-    rc = integrate_up_to_time(f, stamp, &advanced);
-    if (rc != EQVIO_OK) return rc;
-    stage_mark(f, 1);
+    if ((rc = plan_integration(f, stamp, &advanced)) != EQVIO_OK) return rc;
     if (!advanced || !f->initialised) return EQVIO_OK;  // VIOFilter.cpp:198-199
     P.active = true;
     P.n = n;
@@ -583,26 +657,111 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
     P.my.assign(y, y + 2 * n);
     P.cam = to_camera(cam);
     const int N = (int)f->ids.size();
+    // frame block: camera, pixels, per-landmark measurement index
+    FrameHeader* hdr = reinterpret_cast<FrameHeader*>(f->h_frame);
+    hdr->cam = P.cam;
+    if (n > 0) std::memcpy(f->h_frame + f->offY, y, 2 * (size_t)n * sizeof(double));
+    int* hMeasIdx = reinterpret_cast<int*>(f->h_frame + f->offMeasIdx);
+    int* hLmOf = reinterpret_cast<int*>(f->h_frame + f->offLmOf);
     std::unordered_map<int, int> pos;
     pos.reserve(n * 2 + 1);
     for (int j = 0; j < n; ++j) pos[ids[j]] = j;
     P.measIdx.assign(N, -1);
     P.keep.assign(N, 1);
+    bool anyLost = false;
+    int matched = 0;
     for (int i = 0; i < N; ++i) {
         auto it = pos.find(f->ids[i]);
-        if (it != pos.end())
+        if (it != pos.end()) {
             P.measIdx[i] = it->second;
-        else if (f->st.removeLostLandmarks)
+            hLmOf[it->second] = i;
+            ++matched;
+        } else if (f->st.removeLostLandmarks) {
             P.keep[i] = 0;  // removeOldLandmarks, VIOFilter.cpp:203-205
+            anyLost = true;
+        }
+        hMeasIdx[i] = P.measIdx[i];
     }
     P.oldIds = f->ids;
+    const bool anyNew = matched < n;
+    const size_t maxOutliers = (size_t)((1.0 - f->st.featureRetention) * n);
+    // steady frame: nothing enters or leaves before the gate, so the launch sequence is fully known now
+    P.steady = f->speculate && f->corrMode == 0 && N > 0 && n > 0 && !anyNew && !anyLost;
+    P.ignoreGate = maxOutliers == 0;
+    if (P.steady) {
+        P.speculated = true;
+        P.gated = true;
+        P.measKept.assign(n, 1);
+        P.h_gate = reinterpret_cast<double*>(f->h_out);
+        P.h_spec = reinterpret_cast<int*>(f->h_out + f->outOffSpec);
+        P.h_status = reinterpret_cast<int*>(f->h_out + f->outOffStatus);
+        P.nStatus = 1 + N;
+        stage_mark(f, 0);
+        const bool graphOk = f->useGraph && !f->profiling;
+        if (!graphOk) {
+            if ((rc = enqueue_steady_update(f, N, n)) != EQVIO_OK) return rc;
+            stage_mark(f, 3);
+        } else {
+            const eqvio_settings& st = f->st;
+            std::vector<int> key = {N, n, f->cur, f->lmcur, f->xcur, f->chunkLm, st.coordinateChoice, st.useDiscreteVelocityLift,
+                                    st.useDiscreteInnovationLift, st.useEquivariantOutput, f->maxSteps, f->yCap};
+            auto it = f->graphs.find(key);
+            if (it == f->graphs.end()) {
+                if (f->graphs.size() >= 32) {  // evict the least recently used
+                    auto victim = f->graphs.begin();
+                    for (auto g = f->graphs.begin(); g != f->graphs.end(); ++g)
+                        if (g->second.lastUse < victim->second.lastUse) victim = g;
+                    cudaGraphExecDestroy(victim->second.exec);
+                    f->graphs.erase(victim);
+                }
+                const int c0 = f->cur, l0 = f->lmcur, x0 = f->xcur;
+                const long long launches0 = f->launches;
+                cudaGraph_t graph = nullptr;
+                CUDA_TRY(f, cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal));
+                rc = enqueue_steady_update(f, N, n);
+                cudaError_t ce = cudaStreamEndCapture(f->stream, &graph);
+                eqvio_filter::GraphEntry ge;
+                ge.cur2 = f->cur;
+                ge.lmcur2 = f->lmcur;
+                ge.xcur2 = f->xcur;
+                ge.launches = f->launches - launches0;
+                f->cur = c0;  // capture only records: the state flips when the graph is launched below
+                f->lmcur = l0;
+                f->xcur = x0;
+                f->launches = launches0;
+                if (rc != EQVIO_OK) return rc;
+                if (ce != cudaSuccess || !graph) {
+                    f->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce);
+                    return EQVIO_ERR_CUDA;
+                }
+                ce = cudaGraphInstantiate(&ge.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) {
+                    f->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce);
+                    return EQVIO_ERR_CUDA;
+                }
+                ++f->graphCaptures;
+                it = f->graphs.emplace(key, ge).first;
+            }
+            it->second.lastUse = ++f->graphClock;
+            CUDA_TRY(f, cudaGraphLaunch(it->second.exec, f->stream));
+            stage_mark(f, 3);
+            f->cur = it->second.cur2;
+            f->lmcur = it->second.lmcur2;
+            f->xcur = it->second.xcur2;
+            f->launches += it->second.launches;
+            ++f->graphLaunches;
+        }
+        P.corrected = true;
+        return EQVIO_OK;
+    }
+    // general frame: upload, propagate, gate; decisions follow in phase B
+    CUDA_TRY(f, cudaMemcpyAsync(f->d_frame, f->h_frame, f->frameBytes, cudaMemcpyHostToDevice, f->stream));
+    stage_mark(f, 0);
+    if ((rc = enqueue_propagation(f)) != EQVIO_OK) return rc;
+    stage_mark(f, 1);
     if (N > 0) {
-        if ((rc = upload(f, f->d_measIdx, P.measIdx.data(), N)) != EQVIO_OK) return rc;
-        CUDA_TRY(f, cudaMemsetAsync(f->d_spec, 0, sizeof(int), f->stream));
-        gate_kernel<<<cdiv(N, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->Sig[f->cur], f->ld, f->d_measIdx,
-                                                          f->d_y, P.cam, f->st.coordinateChoice, f->d_gate, f->st.outlierThresholdAbs,
-                                                          f->st.outlierThresholdProb, f->d_spec);
-        LAUNCH_CHECK(f, "gate_kernel");
+        if ((rc = enqueue_gate(f, N)) != EQVIO_OK) return rc;
         if ((rc = download_async(f, &P.h_gate, f->d_gate, 3 * (size_t)N)) != EQVIO_OK) return rc;
         if ((rc = download_async(f, &P.h_spec, f->d_spec, 1)) != EQVIO_OK) return rc;
         P.gated = true;
@@ -664,7 +823,7 @@ int launch_correction(eqvio_filter* f, const int* guard);
 // ---- phase B: compaction and correction launches ---------------------------------------------------------
 int vision_phase_b(eqvio_filter* f) {
     auto& P = f->pend;
-    if (!P.active) return EQVIO_OK;
+    if (!P.active || P.steady) return EQVIO_OK;  // a steady frame was enqueued in full by phase A
     const eqvio_settings& s = f->st;
     int rc;
     const int N = (int)f->ids.size();
@@ -744,14 +903,28 @@ int launch_correction(eqvio_filter* f, const int* guard) {
     std::vector<int> lmOf(nm);
     for (int j = 0; j < nm; ++j) lmOf[j] = spos.at(kmids[j]);
 
-    // performVisionUpdate (VIO_eqf.cpp:105-135) in the symmetric Cholesky form
+    if ((rc = upload(f, f->d_lmOf, lmOf.data(), nm)) != EQVIO_OK) return rc;
+    if ((rc = upload(f, f->d_y, ky.data(), ky.size())) != EQVIO_OK) return rc;
+    if ((rc = enqueue_correction(f, nm, guard)) != EQVIO_OK) return rc;
+    stage_mark(f, 3);
+    P.nStatus = 1 + Nn;
+    if ((rc = download_async(f, &P.h_status, f->d_status, P.nStatus)) != EQVIO_OK) return rc;
+    P.corrected = true;
+    return EQVIO_OK;
+}
+
+// performVisionUpdate (VIO_eqf.cpp:105-135) in the symmetric form, for the nm measured landmarks whose pixels are
+// in d_y and state indices in d_lmOf.  Every kernel returns at once when *guard != 0.
+int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
+    auto& P = f->pend;
+    (void)P;
+    const eqvio_settings& s = f->st;
+    const int Nn = (int)f->ids.size();
     const int m = 2 * nm;
     const int dimp = dimp_of(Nn);
     const int Mz = m + dimp + 1;
     const int ldz = (Mz + 7) & ~7;
     double* Z = f->d_Z;
-    if ((rc = upload(f, f->d_lmOf, lmOf.data(), nm)) != EQVIO_OK) return rc;
-    if ((rc = upload(f, f->d_y, ky.data(), ky.size())) != EQVIO_OK) return rc;
     CUDA_TRY(f, cudaMemsetAsync(f->d_status, 0, (1 + (size_t)Nn) * sizeof(int), f->stream));
     const double r2 = s.measurementNoise * s.measurementNoise;
     const double* gammaFinal = f->d_Gamma;
@@ -760,7 +933,7 @@ int launch_correction(eqvio_filter* f, const int* guard) {
         const int ldy = (dimp + 63) & ~63;
         const int T = ldy / DD_T;
         double* Y = f->d_Z;
-        meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, P.cam, s.coordinateChoice,
+        meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
                                                           s.useEquivariantOutput ? 1 : 0, f->d_Cblk, f->d_ytilde, 1, 0, guard);
         LAUNCH_CHECK(f, "meas_kernel");
         double* gin = f->d_Gamma;
@@ -782,7 +955,7 @@ int launch_correction(eqvio_filter* f, const int* guard) {
         }
         gammaFinal = gin;
     } else {
-    meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, P.cam, s.coordinateChoice,
+    meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
                                                       s.useEquivariantOutput ? 1 : 0, f->d_Cblk, Z, ldz, m + dimp, guard);
     LAUNCH_CHECK(f, "meas_kernel");
     zbuild_kernel<<<dim3(cdiv(dimp, 256), nm), 256, 0, f->stream>>>(f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, Z, ldz, m);
@@ -821,10 +994,6 @@ int launch_correction(eqvio_filter* f, const int* guard) {
                                                                    s.useDiscreteInnovationLift ? 1 : 0, s.coordinateChoice,
                                                                    f->d_status, f->d_status + 1, guard);
     LAUNCH_CHECK(f, "lift_kernel");
-    stage_mark(f, 3);
-    P.nStatus = 1 + Nn;
-    if ((rc = download_async(f, &P.h_status, f->d_status, P.nStatus)) != EQVIO_OK) return rc;
-    P.corrected = true;
     return EQVIO_OK;
 }
 
@@ -835,9 +1004,15 @@ int vision_phase_c(eqvio_filter* f, int* did_update) {
     CUDA_TRY(f, cudaStreamSynchronize(f->stream));
     prof_collect(f);
     if (f->stageTiming && P.active) {
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 3; ++i) f->stageMs[i] = 0;
+        if (P.steady) {  // one bracket around the whole enqueued update
             float ms = 0;
-            if (cudaEventElapsedTime(&ms, f->stageEv[i], f->stageEv[i + 1]) == cudaSuccess) f->stageMs[i] = ms;
+            if (cudaEventElapsedTime(&ms, f->stageEv[0], f->stageEv[3]) == cudaSuccess) f->stageMs[2] = ms;
+        } else {
+            for (int i = 0; i < 3; ++i) {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, f->stageEv[i], f->stageEv[i + 1]) == cudaSuccess) f->stageMs[i] = ms;
+            }
         }
         if (f->augTimed) {
             float ms = 0;
@@ -845,7 +1020,7 @@ int vision_phase_c(eqvio_filter* f, int* did_update) {
             f->augTimed = false;
         }
     }
-    if (P.active && P.speculated && P.h_spec && *P.h_spec != 0) {
+    if (P.active && P.speculated && !P.ignoreGate && P.h_spec && *P.h_spec != 0) {
         // a gate tripped: the guarded correction did nothing.  Decide exactly (the gate scalars are on the host
         // by now), remove the outliers from the already lost-compacted state and correct without a guard.
         P.speculated = false;
@@ -1133,7 +1308,6 @@ void eqvio_destroy(eqvio_filter* f) {
     if (f->evJoin) cudaEventDestroy(f->evJoin);
     cudaFree(f->d_ctx);
     cudaFree(f->d_steps);
-    cudaFree(f->d_imu);
     cudaFree(f->d_rows);
     cudaFree(f->d_uv);
     cudaFree(f->d_Z);
@@ -1143,11 +1317,13 @@ void eqvio_destroy(eqvio_filter* f) {
     cudaFree(f->d_Gamma2);
     cudaFree(f->d_ytilde);
     cudaFree(f->d_gate);
-    cudaFree(f->d_y);
     cudaFree(f->d_newP);
     cudaFree(f->d_out);
-    cudaFree(f->d_measIdx);
-    cudaFree(f->d_lmOf);
+    cudaFree(f->d_frame);
+    if (f->h_frame) cudaFreeHost(f->h_frame);
+    if (f->h_out) cudaFreeHost(f->h_out);
+    for (auto& g : f->graphs)
+        if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     cudaFree(f->d_map);
     cudaFree(f->d_newIds);
     cudaFree(f->d_status);
@@ -1482,6 +1658,9 @@ int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
         case EQVIO_TUNE_CORRECTION:
             if (value != 0 && value != 1) return EQVIO_ERR_INVALID_ARG;
             f->corrMode = value;
+            return EQVIO_OK;
+        case EQVIO_TUNE_GRAPH:
+            f->useGraph = value != 0;
             return EQVIO_OK;
         case EQVIO_TUNE_SPECULATE:
             f->speculate = value != 0;

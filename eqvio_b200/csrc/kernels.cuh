@@ -44,16 +44,27 @@ struct ObsStep {  // one IMU segment of integrateObserverState, sensor part alre
     V3 omegaC, vC;     // U_C of the continuous lift               (VIOGroup.cpp:211-220)
 };
 
+// Per-frame inputs live in ONE device-resident block (uploaded with a single copy, at a fixed address so that the
+// whole update can be replayed as a CUDA graph): header below, then the IMU segments, pixels and index maps.
+struct FrameScalars {
+    double meanImu[12];  // time-weighted mean IMU over the frame (fastRiccati, VIOFilter.cpp:140-152)
+    double dtTotal;
+    int nsteps;          // buffered IMU segments
+    int pad;
+};
+struct FrameHeader {
+    FrameScalars fs;
+    Camera cam;
+};
+
 struct PrepArgs {
     const double* xi0s;  // 23
     const double* Xs;    // 23, X before the observer integration
     double* XsOut;       // 23, X after it (a different buffer: the Riccati chain still reads Xs)
     RiccatiCtx* ctx;
     ObsStep* steps;
+    const FrameHeader* fr;
     const double* imu;  // nsteps x 13: dt, gyr3, acc3, gyrBiasVel3, accBiasVel3
-    int nsteps;
-    double meanImu[12];
-    double dtTotal;
     int discreteLift;
     double qdiag[4];  // gyr^2, acc^2, gyrBias^2, accBias^2       (VIOFilterSettings.h:192-201)
     double pdiag[8];  // process variances per 3-block + point     (VIOFilterSettings.h:176-190)
@@ -68,7 +79,8 @@ HD void riccati_small(const PrepArgs& a, double* As, double* Bs) {
     SensorState xi0 = unpack_sensor(a.xi0s);
     GroupSensor X = unpack_group(a.Xs);
     RiccatiCtx& c = *a.ctx;
-    const double dt = a.dtTotal;
+    const double dt = a.fr->fs.dtTotal;
+    const double* meanImu = a.fr->fs.meanImu;
     SensorState xh = sensor_group_action(X, xi0);
     for (int i = 0; i < 21 * 21; ++i) As[i] = 0;
     for (int i = 0; i < 21 * 12; ++i) Bs[i] = 0;
@@ -92,7 +104,7 @@ HD void riccati_small(const PrepArgs& a, double* As, double* Bs) {
     M3 gsk = (-GRAVITY_CONSTANT) * skew(gdir);
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) As[(12 + i) * 21 + 6 + j] = gsk(i, j);
-    double UI[6] = {a.meanImu[0] - xh.bias[0], a.meanImu[1] - xh.bias[1], a.meanImu[2] - xh.bias[2],
+    double UI[6] = {meanImu[0] - xh.bias[0], meanImu[1] - xh.bias[1], meanImu[2] - xh.bias[2],
                     xh.vel.x, xh.vel.y, xh.vel.z};
     double AdT0inv[36], AdA[36], t1[6], t2[6], adT[36];
     se3_Adjoint(se3_inv(xi0.cam), AdT0inv);
@@ -125,7 +137,7 @@ HD void riccati_small(const PrepArgs& a, double* As, double* Bs) {
 // part 2, one call per entry t = 21 i + j of the sensor block: F_s = I + dt A_s, N_s = dt (B_s Q B_s^T + P_s),
 // and dt q_gyr B_s[:, 0:3] for t < 63.
 HD void riccati_entry(const PrepArgs& a, const double* As, const double* Bs, int t, double& Fs, double& Ns) {
-    const double dt = a.dtTotal;
+    const double dt = a.fr->fs.dtTotal;
     const int i = t / 21, j = t % 21;
     Fs = (i == j ? 1.0 : 0.0) + dt * As[t];
     double s = 0;
@@ -145,7 +157,8 @@ HD void riccati_entry(const PrepArgs& a, const double* As, const double* Bs, int
 HD void observer_sensor_body(const PrepArgs& a) {
     SensorState xi0 = unpack_sensor(a.xi0s);
     GroupSensor X = unpack_group(a.Xs);
-    for (int s = 0; s < a.nsteps; ++s) {
+    const int nsteps = a.fr->fs.nsteps;
+    for (int s = 0; s < nsteps; ++s) {
         const double* u = a.imu + 13 * s;
         const double dt = u[0];
         SensorState xh = sensor_group_action(X, xi0);
@@ -304,8 +317,10 @@ __global__ void landmark_rows_kernel(const double* __restrict__ lm, int cap, int
 constexpr int OBS_STAGE = 64;  // IMU segments staged in shared memory at a time
 
 __global__ void observer_landmark_kernel(const double* __restrict__ lmIn, double* __restrict__ lmOut, const int* __restrict__ idsIn,
-                                         int* __restrict__ idsOut, int cap, int N, const ObsStep* __restrict__ steps, int nsteps) {
+                                         int* __restrict__ idsOut, int cap, int N, const ObsStep* __restrict__ steps,
+                                         const FrameHeader* __restrict__ fr) {
     __shared__ ObsStep s_steps[OBS_STAGE];
+    const int nsteps = fr->fs.nsteps;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < N;
     V3 q0 = V3{0, 0, 1};
@@ -498,10 +513,11 @@ __global__ void __launch_bounds__(TP* TP)
 // measIdx[i] = index of landmark i's pixel in y, or -1.   out: errAbs[N] | errProb[N] | depth2[N]
 // ------------------------------------------------------------------------------------------------
 __global__ void gate_kernel(const double* __restrict__ lm, int cap, int N, const double* __restrict__ Sig, int ld,
-                            const int* __restrict__ measIdx, const double* __restrict__ y, Camera cam, int coord,
+                            const int* __restrict__ measIdx, const double* __restrict__ y, const FrameHeader* __restrict__ fr, int coord,
                             double* __restrict__ out, double thrAbs, double thrProb, int* __restrict__ tripped) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    const Camera cam = fr->cam;
     V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
     Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
     double a = lm[F_QA * cap + i];
@@ -614,11 +630,12 @@ __global__ void fill_ll_diag_kernel(double* __restrict__ S, int ld, int n3, doub
 // Writes Cblk[j] (2x3 row-major) and the ytilde row of Z.
 // ------------------------------------------------------------------------------------------------
 __global__ void meas_kernel(const double* __restrict__ lm, int cap, const int* __restrict__ lmOf, int n,
-                            const double* __restrict__ y, Camera cam, int coord, int useStar,
+                            const double* __restrict__ y, const FrameHeader* __restrict__ fr, int coord, int useStar,
                             double* __restrict__ Cblk, double* __restrict__ Z, int ldz, int yrow,
                             const int* __restrict__ guard) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n || *guard) return;
+    const Camera cam = fr->cam;
     int i = lmOf[j];
     V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
     Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};

@@ -181,6 +181,9 @@ int eqvio_get_kernel_profile(eqvio_filter* f, int reset, double ms[EQVIO_PROF_CL
 #define EQVIO_TUNE_CORRECTION 0
 #define EQVIO_TUNE_CHUNK_LANDMARKS 1
 #define EQVIO_TUNE_SPECULATE 2
+/*   EQVIO_TUNE_GRAPH: 1 (default) = replay the launch sequence of a steady frame (no landmark enters or leaves)
+ *                      as a cached CUDA graph; 0 = issue the launches one by one. */
+#define EQVIO_TUNE_GRAPH 3
 int eqvio_set_tuning(eqvio_filter* f, int key, int value);
 /* Version / build info string (arch the kernels were compiled for). */
 const char* eqvio_build_info(void);

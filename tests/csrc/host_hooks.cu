@@ -18,9 +18,11 @@ int hook_sensor_prep(const double* xi0s, double* Xs, const double* imu, int nste
     a.ctx = &ctx;
     a.steps = steps;
     a.imu = imu;
-    a.nsteps = nsteps;
-    for (int k = 0; k < 12; ++k) a.meanImu[k] = meanImu[k];
-    a.dtTotal = dtTotal;
+    FrameHeader fr;
+    fr.fs.nsteps = nsteps;
+    for (int k = 0; k < 12; ++k) fr.fs.meanImu[k] = meanImu[k];
+    fr.fs.dtTotal = dtTotal;
+    a.fr = &fr;
     a.discreteLift = discreteLift;
     for (int k = 0; k < 4; ++k) a.qdiag[k] = qdiag[k];
     for (int k = 0; k < 8; ++k) a.pdiag[k] = pdiag[k];

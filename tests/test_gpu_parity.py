@@ -44,6 +44,18 @@ def test_correction_evaluation_orders_agree(tuning):
     _check(run_gpu(stream, tuning=tuning), ref)
 
 
+@pytest.mark.parametrize("tuning", [dict(graph=0), dict(graph=0, speculate=0), dict(graph=1)])
+def test_steady_path_variants_agree(tuning):
+    """CUDA-graph replay, plain speculative launches and the wait-for-the-gate path give identical results
+    (same kernels, same order), over enough frames for graphs to be captured AND replayed."""
+    stream = make_stream(N=40, frames=12, coord=0)
+    ref = run_gpu(stream, tuning=dict(graph=0, speculate=0))
+    got = run_gpu(stream, tuning=tuning)
+    for g, r in zip(got, ref):
+        e = compare_states(g, r)
+        assert e["ids_equal"] and e["sigma"] == 0.0 and e["state"] == 0.0
+
+
 @pytest.mark.parametrize("coord", [0, 1])
 def test_continuous_lifts(coord):
     """useDiscreteVelocityLift = useDiscreteInnovationLift = false (the EuRoC config's innovation lift)."""
