@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--landmarks", type=int, default=256)
     ap.add_argument("--coord", type=int, default=0)
+    ap.add_argument("--sequences-per-gpu", type=int, default=1, help="independent sequences (replicas) run concurrently per GPU")
+    ap.add_argument("--no-graph", action="store_true", help="issue per-kernel launches instead of replaying CUDA graphs")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="updates in the cpu_baseline sample (0 = auto)")
@@ -200,6 +202,7 @@ def run_b200(args, rank, local_rank, world):
 
     entry.build()
     import eqvio_b200 as eb
+    from eqvio_b200.replicas import gather_trajectories, shard_instances, trajectory_row
     from simdata import SimConfig, record_stream
 
     if not torch.cuda.is_available():
@@ -211,90 +214,112 @@ def run_b200(args, rank, local_rank, world):
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    N, K, W, P = args.landmarks, args.steps, args.warmup, args.profile_steps
+    N, K, W, P, R = args.landmarks, args.steps, args.warmup, args.profile_steps, args.sequences_per_gpu
     skw = settings_dict(args.coord)
     total_frames = 1 + W + K + P
     if total_frames > 399:
         raise SystemExit("bench.py: warmup + steps exceeds the 20 s simulated lap (399 updates)")
-    stream = record_stream(SimConfig.benchmark(N, rank), total_frames)
+    # weak scaling: every rank owns R independent sequences (instance id = seed), contiguous blocks of ids
+    total_instances = R * world
+    mine = shard_instances(total_instances, world, rank)
+    streams = [record_stream(SimConfig.benchmark(N, inst), total_frames) for inst in mine]
     st = eb.Settings(**skw)
-    xi0 = eb.VIOState(eb.VIOSensorState.fromFlat(stream.init_sensor), stream.init_p, stream.init_ids)
-    flt = eb.VIOFilter(st, xi0, 0.0, capacity=N + 8, device=local_rank)
-    cam = eb.Camera(**stream.camera)
-    flt.enableStageTiming(True)
-
+    filters = []
+    for sm in streams:
+        xi0 = eb.VIOState(eb.VIOSensorState.fromFlat(sm.init_sensor), sm.init_p, sm.init_ids)
+        flt = eb.VIOFilter(st, xi0, 0.0, capacity=N + 8, device=local_rank)
+        flt.enableStageTiming(True)
+        if args.no_graph:
+            flt.setTuning(graph=0)
+        filters.append(flt)
+    cam = eb.Camera(**streams[0].camera)
     flush_buf = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-    def step(fr):
-        flt.processIMUArray(fr.imu)
-        flt.augmentLandmarkStates(fr.ids, eb.VIOState(eb.VIOSensorState(), fr.provided_p, fr.ids))
-        flt.processVisionArrays(fr.stamp, fr.ids, fr.y, cam)
-        return flt.stateEstimate()
+    def step(k):
+        """One vision update of every local sequence; returns the state estimates."""
+        frs = [sm.frames[k] for sm in streams]
+        for flt, fr in zip(filters, frs):
+            flt.processIMUArray(fr.imu)
+            flt.augmentLandmarkStates(fr.ids, eb.VIOState(eb.VIOSensorState(), fr.provided_p, fr.ids))
+        if len(filters) == 1:
+            filters[0].processVisionArrays(frs[0].stamp, frs[0].ids, frs[0].y, cam)
+        else:
+            eb.batchProcessVision(filters, [fr.stamp for fr in frs], [fr.ids for fr in frs], [fr.y for fr in frs], cam)
+        return [flt.stateEstimate() for flt in filters]
 
     def h2d_bytes(fr):
-        return fr.imu.nbytes + 2 * 4 * len(fr.ids) + fr.y.nbytes + 4 * len(fr.ids)  # imu + measIdx/lmOf + pixels (+ids of new lms)
+        return fr.imu.nbytes + fr.y.nbytes + 2 * 4 * len(fr.ids) + 8 * 13  # IMU rows, pixels, index maps, frame header scalars
 
-    frames = stream.frames
-    step(frames[0])  # t = 0 image: augments only
-    for fr in frames[1: 1 + W]:
-        step(fr)
+    step(0)  # t = 0 image: augments only
+    for k in range(1, 1 + W):
+        step(k)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = flt.launchCount()
+    launches0 = sum(f.launchCount() for f in filters)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     dev_ms = 0.0
     stage_acc = dict(propagation=0.0, preprocessing=0.0, correction=0.0)
-    traj = np.zeros((K, 11))
+    traj = {inst: np.zeros((K, 11)) for inst in mine}
     h2d = d2h = 0
-    wall0 = time.perf_counter()
-    for k, fr in enumerate(frames[1 + W: 1 + W + K]):
+    wall_in = 0.0
+    for kk in range(K):
+        k = 1 + W + kk
         if flush_buf is not None:
-            flush_buf.fill_(k & 0xFF)
+            flush_buf.fill_(kk & 0xFF)
             torch.cuda.synchronize()
-        ev[k][0].record()
-        est = step(fr)
-        ev[k][1].record()
-        sm = flt.stageMs()
-        for key in stage_acc:
-            stage_acc[key] += sm[key]
-        dev_ms += sm["propagation"] + sm["preprocessing"] + sm["correction"]
-        traj[k, 0] = fr.stamp
-        traj[k, 1:4], traj[k, 4:8], traj[k, 8:11] = est.sensor.pose_x, est.sensor.pose_q, est.sensor.velocity
-        h2d += h2d_bytes(fr)
-        d2h += 8 * (23 + 3 * len(est.ids)) + 8 * 3 * N + 4 * (1 + N)  # state estimate + gate scalars + status
+        t0 = time.perf_counter()
+        ev[kk][0].record()
+        ests = step(k)
+        ev[kk][1].record()
+        wall_in += time.perf_counter() - t0
+        per_filter = []
+        for flt in filters:
+            sm_ = flt.stageMs()
+            for key in stage_acc:
+                stage_acc[key] += sm_[key] / len(filters)
+            per_filter.append(sm_["propagation"] + sm_["preprocessing"] + sm_["correction"])
+        # sequences on one GPU run concurrently on their own streams: the step's device time is the slowest of them
+        dev_ms += max(per_filter)
+        for inst, est, sm in zip(mine, ests, streams):
+            traj[inst][kk] = trajectory_row(sm.frames[k].stamp, est)
+            h2d += h2d_bytes(sm.frames[k])
+            d2h += 8 * (23 + 3 * len(est.ids)) + 8 * 3 * N + 4 * (2 + N)  # state estimate + gate scalars + flag/status words
     torch.cuda.synchronize()
-    wall = time.perf_counter() - wall0
-    launches = flt.launchCount() - launches0
+    launches = sum(f.launchCount() for f in filters) - launches0
     e2e_ms = sum(a.elapsed_time(b) for a, b in ev)
-    # the single collective of the path: all-gather of the trajectories at the end
+    # the single collective of the path: all-gather of the trajectories at the end (timed into e2e)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    all_traj = gather_trajectories(traj, total_instances, device=torch.device("cuda", local_rank) if dist else None)
+    g1.record()
+    torch.cuda.synchronize()
     if dist:
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tt = torch.from_numpy(traj).cuda()
-        out = [torch.empty_like(tt) for _ in range(world)]
-        g0.record()
-        dist.all_gather(out, tt)
-        g1.record()
-        torch.cuda.synchronize()
         e2e_ms += g0.elapsed_time(g1)
+    assert all_traj.shape == (total_instances, K, 11) and np.isfinite(all_traj).all()
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    # per-kernel profile on extra steps (event pairs around every launch of the four kernel classes)
+    # per-kernel profile on extra steps of the first sequence (event pairs around every launch of a class; the
+    # graph path is off while profiling)
+    flt = filters[0]
     flt.enableKernelProfile(True)
     flt.kernelProfile(reset=True)
+    prof_stage = dict(propagation=0.0, preprocessing=0.0, correction=0.0)
     nprof = 0
-    for fr in frames[1 + W + K: 1 + W + K + P]:
+    for k in range(1 + W + K, 1 + W + K + P):
         if flush_buf is not None:
             flush_buf.fill_(1)
             torch.cuda.synchronize()
-        step(fr)
+        step(k)
+        for key, v in flt.stageMs().items():
+            prof_stage[key] += v
         nprof += 1
     prof = flt.kernelProfile(reset=True)
     flt.enableKernelProfile(False)
-    n_meas = len(frames[1 + W].ids)
+    n_meas = len(streams[0].frames[1 + W].ids)
     n_state = flt.numLandmarks()
 
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
@@ -327,6 +352,11 @@ def run_b200(args, rank, local_rank, world):
         f64_peak = 2.0 * 4096**3 / (best * 1e-3) / 1e12
 
         cnt = alg_counts(n_state, n_meas)
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        except Exception:
+            pass
         kern = {}
         for name, d in prof.items():
             if d["launches"] == 0:
@@ -334,8 +364,10 @@ def run_b200(args, rank, local_rank, world):
             per_update_ms = d["ms"] / max(nprof, 1)
             e = dict(ms_per_update=per_update_ms, launches_per_update=d["launches"] / max(nprof, 1),
                      avg_launch_us=1000.0 * d["ms"] / d["launches"])
-            if name == "syrk":
+            if name == "downdate":
                 e.update(bound="tensor", achieved=cnt["syrk_flops"] / (per_update_ms * 1e-3) / 1e12, peak=f64_peak, unit="TFLOP/s")
+            elif name == "chunk_factor":
+                e.update(bound="latency", note="64 sequential pivots per chunk; fp64 CUDA-core work, one 4x4 register tile per thread")
             elif name == "chol_trail":
                 e.update(bound="tensor", achieved=cnt["trail_flops"] / (per_update_ms * 1e-3) / 1e12, peak=f64_peak, unit="TFLOP/s")
             elif name == "prop_ll":
@@ -344,45 +376,50 @@ def run_b200(args, rank, local_rank, world):
                 e["frac"] = e["achieved"] / e["peak"]
             kern[name] = e
         dom = max(kern, key=lambda k_: kern[k_]["ms_per_update"]) if kern else None
-        # the dominant kernel must carry a roofline; the serial panel kernel is latency-bound, report the
-        # heaviest kernel that has a bound and keep the panel's share visible in `kernels`
         dom_r = max((k_ for k_ in kern if "achieved" in kern[k_]), key=lambda k_: kern[k_]["ms_per_update"], default=None)
         roofline = None
         if dom_r:
             d = kern[dom_r]
+            tr = traffic.get(dom_r, {}).get(str(N))
             roofline = dict(kernel=dom_r, bound=d["bound"], achieved=d["achieved"], peak=d["peak"], unit=d["unit"], frac=d["frac"],
-                            traffic=None, avg_launch_us=d["avg_launch_us"],
+                            traffic=tr, avg_launch_us=d["avg_launch_us"],
                             peak_source=(hbm_src if d["bound"] == "hbm" else
                                          f"cuBLAS DGEMM 4096^3 measured in this run ({f64_peak:.1f} TFLOP/s); MEASURED_PEAKS.json "
                                          "has no fp64 figure"),
-                            dominant_by_time=dom, kernels=kern,
+                            dominant_by_time=dom, kernels=kern, profile_stage_ms={k_: v / max(nprof, 1) for k_, v in prof_stage.items()},
                             update=dict(flops=cnt["upd_flops"], bytes=cnt["upd_bytes"],
-                                        flops_frac=cnt["upd_flops"] * K / (dev_ms / 1e3) / 1e12 / f64_peak,
-                                        hbm_frac=cnt["upd_bytes"] * K / (dev_ms / 1e3) / 1e9 / hbm_peak))
-        value = world * K / (dev_ms_max * 1e-3)
-        e2e = world * K / (e2e_ms_max * 1e-3)
+                                        flops_frac=cnt["upd_flops"] * K * R / (dev_ms / 1e3) / 1e12 / f64_peak,
+                                        hbm_frac=cnt["upd_bytes"] * K * R / (dev_ms / 1e3) / 1e9 / hbm_peak))
+        value = world * R * K / (dev_ms_max * 1e-3)
+        e2e = world * R * K / (e2e_ms_max * 1e-3)
         line = dict(metric="vision-updates/sec", value=value, unit="updates/s", n_gpus=world, steps=K, warmup=W,
                     ms_per_step=dev_ms_max / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                     data="synthetic",
                     config=dict(workload=workload_name(N, args.coord), landmarks=N, measured_per_update=n_meas, state_dim=cnt["dim"],
-                                sequences_per_gpu=1, l2="not flushed" if args.no_l2_flush else
+                                sequences_per_gpu=R, l2="not flushed" if args.no_l2_flush else
                                 "flushed between steps (256 MiB write) outside the per-step event brackets",
-                                value_timing="CUDA events on the filter stream: pixels staged -> last correction kernel",
-                                parallelism=f"replicas x{world}, one sequence per GPU, all-gather of trajectories at the end"),
+                                value_timing="CUDA events on each filter's stream around the device work of processVisionData "
+                                "(frame upload -> status download; + augmentLandmarkStates kernels); per step the slowest of the "
+                                "GPU's concurrent sequences counts",
+                                launch_mode="per-kernel launches" if args.no_graph else "steady frames replayed as a cached CUDA graph",
+                                parallelism=f"replicas: {R} sequence(s) per GPU x {world} GPU(s), no data-path collective, "
+                                "one all-gather of trajectories at the end"),
                     e2e=dict(value=e2e, unit="updates/s", h2d_bytes_per_step=h2d // K, d2h_bytes_per_step=d2h // K,
-                             ms_per_step=e2e_ms_max / K, wall_ms_per_step=1000.0 * wall / K),
+                             ms_per_step=e2e_ms_max / K, host_ms_per_step=1000.0 * wall_in / K),
                     gpu_launches=int(launches), launches_per_step=launches / K,
                     stage_ms={k_: v / K for k_, v in stage_acc.items()}, clocks=sampler.result(), roofline=roofline)
         if not args.no_cpu_baseline:
             est_s = 17.0 * cnt["dim"] ** 3 / 50e9 + 0.02  # ~17 dim^3 flops of the dense path at a conservative 50 GFLOP/s
             sample_n = args.cpu_sample or int(max(3, min(K, 20.0 / est_s)))
-            ups, stages, done = time_cpu(stream, skw, min(W, 2), sample_n)
+            ups, stages, done = time_cpu(streams[0], skw, min(W, 2), sample_n)
             line["cpu_baseline"] = dict(value=ups, unit="updates/s", cores=blas_threads(), kind="port",
-                                        sample=f"{done} consecutive updates of rank 0's stream (same inputs) after {min(W, 2)} warm-up "
-                                        "updates; oracle port of the dense Eigen path, reference evaluation order",
+                                        sample=f"{done} consecutive updates of sequence 0 (same inputs) after {min(W, 2)} warm-up "
+                                        "updates; oracle port of the dense Eigen path in the reference's evaluation order "
+                                        "(numpy + OpenBLAS; includes ~20 ms/update of Python overhead)",
                                         stage_ms={k_: 1000.0 * v / done for k_, v in stages.items()})
         print(json.dumps(line), flush=True)
-    flt.close()
+    for f in filters:
+        f.close()
     if dist:
         dist.barrier()
         dist.destroy_process_group()

@@ -24,7 +24,7 @@ ERROR_NAMES = {
     EQVIO_ERR_UNSUPPORTED: "EQVIO_ERR_UNSUPPORTED",
 }
 PROF_CLASSES = 4
-PROF_NAMES = ("prop_ll", "chol_panel", "chol_trail", "syrk")
+PROF_NAMES = ("prop_ll", "chunk_factor", "chol_trail", "downdate")
 
 _D = C.c_double
 _I = C.c_int
@@ -74,6 +74,7 @@ SIGNATURES = {
     "eqvio_set_landmarks": (_I, [_H, _I, _PI, _PD]),
     "eqvio_augment_landmark_states": (_I, [_H, _I, _PI, _I, _PI, _PD]),
     "eqvio_process_imu": (_I, [_H, _D, _PD, _PD, _PD, _PD]),
+    "eqvio_process_imu_rows": (_I, [_H, _I, _PD]),
     "eqvio_process_vision": (_I, [_H, _D, _I, _PI, _PD, C.POINTER(Camera), _PI]),
     "eqvio_batch_process_vision": (_I, [C.POINTER(_H), _I, _PD, _PI, C.POINTER(_PI), C.POINTER(_PD),
                                         C.POINTER(Camera), _PI]),

@@ -81,7 +81,8 @@ struct eqvio_filter {
     int yCap = 0;
     // fixed pinned output block of the steady path: gate scalars | spec flag | status words
     unsigned char* h_out = nullptr;
-    size_t outOffSpec = 0, outOffStatus = 0;
+    size_t outOffSpec = 0, outOffStatus = 0, outOffEst = 0;
+    bool estValid = false;  // h_out holds the state estimate of the current state (produced by the steady update)
     // CUDA graphs of the steady-state update, keyed by everything that shapes the launch sequence
     struct GraphEntry {
         cudaGraphExec_t exec = nullptr;
@@ -380,7 +381,8 @@ int alloc_device(eqvio_filter* f) {
     CUDA_TRY(f, cudaMalloc(&f->d_out, (23 + 3 * c1) * sizeof(double)));
     f->outOffSpec = ((3 * c1 * sizeof(double)) + 63) & ~size_t(63);
     f->outOffStatus = f->outOffSpec + 64;
-    CUDA_TRY(f, cudaMallocHost(&f->h_out, f->outOffStatus + (1 + c1) * sizeof(int)));
+    f->outOffEst = (f->outOffStatus + (1 + c1) * sizeof(int) + 63) & ~size_t(63);
+    CUDA_TRY(f, cudaMallocHost(&f->h_out, f->outOffEst + (23 + 3 * c1) * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_map, c1 * sizeof(int)));
     CUDA_TRY(f, cudaMalloc(&f->d_newIds, c1 * sizeof(int)));
     CUDA_TRY(f, cudaMalloc(&f->d_status, (1 + c1) * sizeof(int)));
@@ -621,6 +623,11 @@ int enqueue_steady_update(eqvio_filter* f, int N, int nm) {
     if ((rc = enqueue_correction(f, nm, f->d_spec)) != EQVIO_OK) return rc;
     CUDA_TRY(f, cudaMemcpyAsync(f->h_out + f->outOffStatus, f->d_status, (1 + (size_t)N) * sizeof(int), cudaMemcpyDeviceToHost,
                                 f->stream));
+    // stateEstimate() is what every caller asks for next (main_opt.cpp:225, main_sim.cpp:146): produce it here
+    state_estimate_kernel<<<cdiv(N, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_xi0s, f->d_Xs[f->xcur], f->d_out);
+    LAUNCH_CHECK(f, "state_estimate_kernel");
+    CUDA_TRY(f, cudaMemcpyAsync(f->h_out + f->outOffEst, f->d_out, (23 + 3 * (size_t)N) * sizeof(double), cudaMemcpyDeviceToHost,
+                                f->stream));
     return EQVIO_OK;
 }
 
@@ -630,6 +637,7 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
     P = eqvio_filter::Pending();
     stage_reset(f);
     f->lastOutliers.clear();
+    f->estValid = false;
     if (n < 0 || (n > 0 && (!ids || !y)) || !cam) {
         f->err = "invalid measurement arguments";
         return EQVIO_ERR_INVALID_ARG;
@@ -663,18 +671,17 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
     if (n > 0) std::memcpy(f->h_frame + f->offY, y, 2 * (size_t)n * sizeof(double));
     int* hMeasIdx = reinterpret_cast<int*>(f->h_frame + f->offMeasIdx);
     int* hLmOf = reinterpret_cast<int*>(f->h_frame + f->offLmOf);
-    std::unordered_map<int, int> pos;
-    pos.reserve(n * 2 + 1);
-    for (int j = 0; j < n; ++j) pos[ids[j]] = j;
     P.measIdx.assign(N, -1);
     P.keep.assign(N, 1);
     bool anyLost = false;
     int matched = 0;
     for (int i = 0; i < N; ++i) {
-        auto it = pos.find(f->ids[i]);
-        if (it != pos.end()) {
-            P.measIdx[i] = it->second;
-            hLmOf[it->second] = i;
+        // the measurement ids are strictly ascending: binary search instead of a hash map
+        const int* it = std::lower_bound(ids, ids + n, f->ids[i]);
+        if (it != ids + n && *it == f->ids[i]) {
+            const int j = (int)(it - ids);
+            P.measIdx[i] = j;
+            hLmOf[j] = i;
             ++matched;
         } else if (f->st.removeLostLandmarks) {
             P.keep[i] = 0;  // removeOldLandmarks, VIOFilter.cpp:203-205
@@ -1020,7 +1027,10 @@ int vision_phase_c(eqvio_filter* f, int* did_update) {
             f->augTimed = false;
         }
     }
+    const bool wasSteady = P.active && P.steady;
+    bool redone = false;
     if (P.active && P.speculated && !P.ignoreGate && P.h_spec && *P.h_spec != 0) {
+        redone = true;
         // a gate tripped: the guarded correction did nothing.  Decide exactly (the gate scalars are on the host
         // by now), remove the outliers from the already lost-compacted state and correct without a guard.
         P.speculated = false;
@@ -1050,6 +1060,7 @@ int vision_phase_c(eqvio_filter* f, int* did_update) {
         return EQVIO_ERR_NUMERIC;
     }
     if (did_update) *did_update = 1;
+    f->estValid = wasSteady && !redone && !(st & 4);
     if (st & 4) {  // removeInvalidLandmarks, VIO_eqf.cpp:213-223
         const int Nn = (int)f->ids.size();
         std::vector<char> keep(Nn, 1);
@@ -1348,6 +1359,7 @@ const char* eqvio_last_error(const eqvio_filter* f) { return f ? f->err.c_str() 
 
 int eqvio_initialise_from_imu(eqvio_filter* f, double stamp, const double gyr[3], const double acc[3]) {
     ENTER(f);
+    f->estValid = false;
     (void)gyr;
     if (!acc) return EQVIO_ERR_INVALID_ARG;
     stage_reset(f);
@@ -1368,6 +1380,7 @@ int eqvio_initialise_from_imu(eqvio_filter* f, double stamp, const double gyr[3]
 
 int eqvio_set_state(eqvio_filter* f, const double sensor[23], int n, const int* ids, const double* p) {
     ENTER(f);
+    f->estValid = false;
     if (!sensor || n < 0 || (n > 0 && (!ids || !p))) return EQVIO_ERR_INVALID_ARG;
     stage_reset(f);
     std::vector<double> diag;
@@ -1380,6 +1393,7 @@ int eqvio_set_state(eqvio_filter* f, const double sensor[23], int n, const int* 
 
 int eqvio_set_landmarks(eqvio_filter* f, int n, const int* ids, const double* p) {
     ENTER(f);
+    f->estValid = false;
     if (n < 0 || (n > 0 && (!ids || !p))) return EQVIO_ERR_INVALID_ARG;
     if (n != (int)f->ids.size()) {
         // the reference overwrites a block of an unresized Sigma (VIOFilter.cpp:94-101); any other
@@ -1425,28 +1439,44 @@ int eqvio_augment_landmark_states(eqvio_filter* f, int n_new, const int* new_ids
         return EQVIO_ERR_INVALID_ARG;
     stage_reset(f);
     const int N = (int)f->ids.size();
-    std::unordered_map<int, int> want, prov, have;
-    for (int j = 0; j < n_new; ++j) want.emplace(new_ids[j], j);
-    for (int j = 0; j < n_provided; ++j) prov.emplace(provided_ids[j], j);
+    // id lookups: binary search when the caller's lists are ascending (they come from std::map / getIds()), else sort a copy
+    auto make_index = [](int cnt, const int* v, std::vector<std::pair<int, int>>& out) {
+        out.resize(cnt);
+        for (int j = 0; j < cnt; ++j) out[j] = {v[j], j};
+        if (!std::is_sorted(out.begin(), out.end())) std::sort(out.begin(), out.end());
+    };
+    auto find_in = [](const std::vector<std::pair<int, int>>& idx, int id) -> int {
+        auto it = std::lower_bound(idx.begin(), idx.end(), std::make_pair(id, -1));
+        return (it != idx.end() && it->first == id) ? it->second : -1;
+    };
+    std::vector<std::pair<int, int>> want, prov, have;
+    make_index(n_new, new_ids, want);
+    make_index(n_provided, provided_ids, prov);
+    make_index(N, f->ids.data(), have);
     std::vector<char> keep(N, 1);
-    for (int i = 0; i < N; ++i) {
-        if (!want.count(f->ids[i])) keep[i] = 0;
-        have.emplace(f->ids[i], i);
-    }
+    for (int i = 0; i < N; ++i)
+        if (find_in(want, f->ids[i]) < 0) keep[i] = 0;
     std::vector<int> addIds;
     std::vector<double> addP;
     for (int j = 0; j < n_new; ++j) {
-        if (have.count(new_ids[j])) continue;
-        auto it = prov.find(new_ids[j]);
-        if (it == prov.end()) {
+        if (find_in(have, new_ids[j]) >= 0) continue;
+        bool dup = false;
+        for (int a : addIds) dup |= (a == new_ids[j]);
+        if (dup) continue;
+        const int pj = find_in(prov, new_ids[j]);
+        if (pj < 0) {
             f->err = "augment_landmark_states: a new id is missing from the provided state";
             return EQVIO_ERR_INVALID_ARG;
         }
-        have.emplace(new_ids[j], -1);
         addIds.push_back(new_ids[j]);
-        for (int a = 0; a < 3; ++a) addP.push_back(provided_p[3 * it->second + a]);
+        for (int a = 0; a < 3; ++a) addP.push_back(provided_p[3 * pj + a]);
     }
     if (f->stageTiming) cudaEventRecord(f->augEv[0], f->stream);
+    {
+        bool identity = addIds.empty();
+        for (int i = 0; identity && i < N; ++i) identity = keep[i] != 0;
+        if (!identity) f->estValid = false;
+    }
     int rc = remove_and_append(f, keep, addIds, addP, f->st.initialPointVariance, -1.0);
     if (rc != EQVIO_OK) return rc;
     if (f->stageTiming) {
@@ -1473,6 +1503,16 @@ int eqvio_process_imu(eqvio_filter* f, double stamp, const double gyr[3], const 
         u.v[9 + i] = acc_bias_vel ? acc_bias_vel[i] : 0.0;
     }
     f->buf.push_back(u);
+    return EQVIO_OK;
+}
+
+int eqvio_process_imu_rows(eqvio_filter* f, int count, const double* rows) {
+    if (!f || count < 0 || (count > 0 && !rows)) return EQVIO_ERR_INVALID_ARG;
+    for (int i = 0; i < count; ++i) {
+        const double* r = rows + 13 * (size_t)i;
+        int rc = eqvio_process_imu(f, r[0], r + 1, r + 4, r + 7, r + 10);
+        if (rc != EQVIO_OK) return rc;
+    }
     return EQVIO_OK;
 }
 
@@ -1519,8 +1559,16 @@ int eqvio_capacity(const eqvio_filter* f) { return f ? f->cap : 0; }
 
 int eqvio_get_state_estimate(eqvio_filter* f, double sensor[23], int* ids, double* p, int* n_out) {
     ENTER(f);
-    stage_reset(f);
     const int N = (int)f->ids.size();
+    if (f->estValid) {  // produced by the last steady update, state untouched since
+        const double* h = reinterpret_cast<const double*>(f->h_out + f->outOffEst);
+        if (sensor) std::memcpy(sensor, h, 23 * sizeof(double));
+        if (ids && N) std::memcpy(ids, f->ids.data(), N * sizeof(int));
+        if (p && N) std::memcpy(p, h + 23, 3 * (size_t)N * sizeof(double));
+        if (n_out) *n_out = N;
+        return EQVIO_OK;
+    }
+    stage_reset(f);
     state_estimate_kernel<<<cdiv(std::max(N, 1), 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_xi0s, f->d_Xs[f->xcur], f->d_out);
     LAUNCH_CHECK(f, "state_estimate_kernel");
     double* h = nullptr;

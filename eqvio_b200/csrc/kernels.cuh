@@ -1052,17 +1052,27 @@ __global__ void __launch_bounds__(CH_THREADS)
     for (int J = 0; J < nJ; ++J) {
         const int buf = J & 1;
         if (isS && TI == J && TK == J) {
-#pragma unroll
-            for (int j = 0; j < CH_T; ++j) {
-                const double c = fast_rcp(a[j][j]);
-                sm.Dc[buf][j] = c;
-#pragma unroll
-                for (int i = j + 1; i < CH_T; ++i) {
-                    const double li = a[i][j] * c;
-#pragma unroll
-                    for (int k = j + 1; k <= i; ++k) a[i][k] -= li * a[k][j];
-                }
-            }
+            // 4x4 diagonal tile: fraction-free elimination (products only, 6 dependent operations) and then the
+            // four pivot reciprocals side by side -- the serial pivot -> reciprocal -> multiplier chain of the
+            // textbook order costs ~4 x 200 cycles of fp64 latency here, with every other warp waiting on it.
+            const double a00 = a[0][0], a10 = a[1][0], a20 = a[2][0], a30 = a[3][0];
+            const double m11 = a[1][1] * a00 - a10 * a10, m21 = a[2][1] * a00 - a20 * a10, m22 = a[2][2] * a00 - a20 * a20;
+            const double m31 = a[3][1] * a00 - a30 * a10, m32 = a[3][2] * a00 - a30 * a20, m33 = a[3][3] * a00 - a30 * a30;
+            const double n22 = m22 * m11 - m21 * m21, n32 = m32 * m11 - m31 * m21, n33 = m33 * m11 - m31 * m31;
+            const double p33 = n33 * n22 - n32 * n32;
+            const double r0 = fast_rcp(a00), r1 = fast_rcp(m11), r2 = fast_rcp(n22), r3 = fast_rcp(p33);
+            const double s2 = r0 * r1, s3 = s2 * r2, e1 = a00 * m11;
+            // unscaled columns v_ij = L_ij L_jj (the Schur-complement values) and 1 / v_jj
+            a[1][1] = m11 * r0;
+            a[2][1] = m21 * r0;
+            a[3][1] = m31 * r0;
+            a[2][2] = n22 * s2;
+            a[3][2] = n32 * s2;
+            a[3][3] = p33 * s3;
+            sm.Dc[buf][0] = r0;
+            sm.Dc[buf][1] = a00 * r1;
+            sm.Dc[buf][2] = e1 * r2;
+            sm.Dc[buf][3] = (e1 * n22) * r3;
 #pragma unroll
             for (int i = 0; i < CH_T; ++i)
 #pragma unroll

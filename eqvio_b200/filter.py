@@ -237,8 +237,7 @@ class VIOFilter:
     def processIMUArray(self, rows):
         """rows (k,13): stamp, gyr3, acc3, gyrBiasVel3, accBiasVel3 -- k processIMUData calls."""
         rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, 13)
-        for r in rows:
-            self._check(lib.eqvio_process_imu(self._h, float(r[0]), _pd(r[1:4]), _pd(r[4:7]), _pd(r[7:10]), _pd(r[10:13])))
+        self._check(lib.eqvio_process_imu_rows(self._h, rows.shape[0], _pd(rows)))
 
     def initialiseFromIMUData(self, imu: IMUVelocity):  # VIOFilter.cpp:65-78
         self._check(lib.eqvio_initialise_from_imu(self._h, float(imu.stamp), _pd(_f64(imu.gyr, 3)), _pd(_f64(imu.acc, 3))))

@@ -116,6 +116,8 @@ int eqvio_augment_landmark_states(eqvio_filter* f, int n_new, const int* new_ids
 /* processIMUData (VIOFilter.cpp:58-63): buffers the sample; first sample initialises attitude. */
 int eqvio_process_imu(eqvio_filter* f, double stamp, const double gyr[3], const double acc[3],
                       const double gyr_bias_vel[3] /* may be NULL = 0 */, const double acc_bias_vel[3] /* may be NULL */);
+/* `count` processIMUData calls in one: rows of 13 doubles (stamp, gyr3, acc3, gyrBiasVel3, accBiasVel3). */
+int eqvio_process_imu_rows(eqvio_filter* f, int count, const double* rows);
 /* processVisionData (VIOFilter.cpp:194-241): propagate to `stamp`, prune lost landmarks, gate
  * outliers, add new landmarks, EqF correction, drop invalid landmarks.  ids ascending. */
 int eqvio_process_vision(eqvio_filter* f, double stamp, int n, const int* ids, const double* y /* 2n pixels */,
@@ -162,9 +164,9 @@ long long eqvio_get_launch_count(const eqvio_filter* f);
  * every launch of the class (adds two event records per launch; off by default, not meant to be on
  * while whole-update throughput is timed).  Classes: */
 #define EQVIO_PROF_PROP_LL 0 /* Riccati propagation, landmark-landmark block (HBM-bound) */
-#define EQVIO_PROF_PANEL 1   /* Cholesky sweep: panel factor + triangular solve */
-#define EQVIO_PROF_TRAIL 2   /* Cholesky sweep: trailing update (FP64 tensor-core GEMM) */
-#define EQVIO_PROF_SYRK 3    /* Sigma downdate Sigma -= Y^T Y (FP64 tensor-core syrk) */
+#define EQVIO_PROF_PANEL 1   /* chunk factorisation + solve (batch mode: panel of the Cholesky sweep) */
+#define EQVIO_PROF_TRAIL 2   /* batch mode only: trailing update of the sweep (FP64 tensor-core GEMM) */
+#define EQVIO_PROF_SYRK 3    /* Sigma downdate Sigma -= Y^T Y (FP64 tensor cores, DMMA) */
 #define EQVIO_PROF_CLASSES 4
 int eqvio_enable_kernel_profile(eqvio_filter* f, int on);
 /* Accumulated ms and launch counts per class since the last reset. */
