@@ -76,12 +76,13 @@ def alg_counts(N, n):
         upd_bytes=8.0 * (4 * dim * dim + 4 * m * dim))
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi-equivalent sampling of SM clocks and throttle reasons during the timed region (NVML)."""
+class ClockSampler:
+    """nvidia-smi-equivalent sampling of SM clocks and throttle reasons (NVML).  sample() is called from the
+    benchmark loop itself every few steps, right after a step's closing event (the GPU is still busy with the
+    tail of that step / the L2 flush, and NVML queries stay outside the timed brackets)."""
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
         try:
             import pynvml
 
@@ -92,7 +93,7 @@ class ClockSampler(threading.Thread):
         except Exception:
             self.nv = None
 
-    def run(self):
+    def sample(self):
         if self.nv is None:
             return
         nv = self.nv
@@ -103,16 +104,14 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
             getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
         }
-        while not self.stop_flag:
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in names.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
 
     def result(self):
         if not self.samples:
@@ -257,7 +256,8 @@ def run_b200(args, rank, local_rank, world):
     if dist:
         dist.barrier()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if dist:  # bring the collective path up (communicator, buffers) before anything is timed
+        gather_trajectories({inst: np.zeros((1, 11)) for inst in mine}, total_instances, device=torch.device("cuda", local_rank))
     launches0 = sum(f.launchCount() for f in filters)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     dev_ms = 0.0
@@ -275,6 +275,10 @@ def run_b200(args, rank, local_rank, world):
         ests = step(k)
         ev[kk][1].record()
         wall_in += time.perf_counter() - t0
+        if kk % max(1, K // 8) == 0:
+            if flush_buf is not None:
+                flush_buf.fill_(kk & 0xFF)  # keep the GPU busy while NVML is queried
+            sampler.sample()
         per_filter = []
         for flt in filters:
             sm_ = flt.stageMs()
@@ -299,8 +303,6 @@ def run_b200(args, rank, local_rank, world):
     if dist:
         e2e_ms += g0.elapsed_time(g1)
     assert all_traj.shape == (total_instances, K, 11) and np.isfinite(all_traj).all()
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
 
     # per-kernel profile on extra steps of the first sequence (event pairs around every launch of a class; the
     # graph path is off while profiling)

@@ -87,6 +87,7 @@ SIGNATURES = {
     "eqvio_get_eqf_state": (_I, [_H, _PD, _PI, _PD, _PD, _PD, _PD, _I]),
     "eqvio_get_landmark_cov_blocks": (_I, [_H, _PD]),
     "eqvio_get_feature_predictions": (_I, [_H, C.POINTER(Camera), _D, _PI, _PD, _PI]),
+    "eqvio_compute_nees": (_I, [_H, _PD, _I, _PI, _PD, _PD]),
     "eqvio_get_last_outliers": (_I, [_H, _PI, _I, _PI]),
     "eqvio_get_stage_ms": (_I, [_H, _PD]),
     "eqvio_enable_stage_timing": (_I, [_H, _I]),

@@ -74,7 +74,8 @@ struct eqvio_filter {
     // per-frame input block (FrameHeader | imu | y | measIdx | lmOf) at fixed device / pinned addresses
     unsigned char* d_frame = nullptr;
     unsigned char* h_frame = nullptr;
-    size_t frameBytes = 0, offImu = 0, offY = 0, offMeasIdx = 0, offLmOf = 0;
+    size_t frameBytes = 0, offImu = 0, offY = 0, offMeasIdx = 0, offLmOf = 0, offYIdx = 0;
+    int* d_yIdx = nullptr;
     FrameHeader* d_hdr = nullptr;
     double* d_imu = nullptr;
     int maxSteps = 0;
@@ -328,7 +329,8 @@ int alloc_frame(eqvio_filter* f, int steps, int ycap) {
     f->offY = up(f->offImu + (size_t)steps * 13 * sizeof(double));
     f->offMeasIdx = up(f->offY + (size_t)ycap * 2 * sizeof(double));
     f->offLmOf = up(f->offMeasIdx + cap1 * sizeof(int));
-    f->frameBytes = up(f->offLmOf + cap1 * sizeof(int));
+    f->offYIdx = up(f->offLmOf + cap1 * sizeof(int));
+    f->frameBytes = up(f->offYIdx + cap1 * sizeof(int));
     CUDA_TRY(f, cudaMalloc(&f->d_frame, f->frameBytes));
     CUDA_TRY(f, cudaMallocHost(&f->h_frame, f->frameBytes));
     std::memset(f->h_frame, 0, f->frameBytes);
@@ -338,6 +340,7 @@ int alloc_frame(eqvio_filter* f, int steps, int ycap) {
     f->d_y = reinterpret_cast<double*>(f->d_frame + f->offY);
     f->d_measIdx = reinterpret_cast<int*>(f->d_frame + f->offMeasIdx);
     f->d_lmOf = reinterpret_cast<int*>(f->d_frame + f->offLmOf);
+    f->d_yIdx = reinterpret_cast<int*>(f->d_frame + f->offYIdx);
     return EQVIO_OK;
 }
 
@@ -371,7 +374,7 @@ int alloc_device(eqvio_filter* f) {
     const size_t ldzMax = (mMax + dimpMax + 1 + 7) & ~size_t(7);
     f->zElems = std::max(std::max(ldzMax * mMax, sigElems), (size_t)(f->ld / YB_T) * YB_TILE);
     CUDA_TRY(f, cudaMalloc(&f->d_Z, f->zElems * sizeof(double)));
-    CUDA_TRY(f, cudaMalloc(&f->d_Lout, (mMax + NB) * NB * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&f->d_Lout, ((size_t)dimpMax + mMax + NB) * NB * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Cblk, c1 * 6 * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Gamma, (size_t)(dimpMax + 8) * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Gamma2, (size_t)(dimpMax + 8) * sizeof(double)));
@@ -671,6 +674,7 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
     if (n > 0) std::memcpy(f->h_frame + f->offY, y, 2 * (size_t)n * sizeof(double));
     int* hMeasIdx = reinterpret_cast<int*>(f->h_frame + f->offMeasIdx);
     int* hLmOf = reinterpret_cast<int*>(f->h_frame + f->offLmOf);
+    int* hYIdx = reinterpret_cast<int*>(f->h_frame + f->offYIdx);
     P.measIdx.assign(N, -1);
     P.keep.assign(N, 1);
     bool anyLost = false;
@@ -681,7 +685,10 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
         if (it != ids + n && *it == f->ids[i]) {
             const int j = (int)(it - ids);
             P.measIdx[i] = j;
-            hLmOf[j] = i;
+            // rows of the correction follow the STATE order (chunks then cover contiguous rows / columns of Sigma);
+            // the update does not depend on the row order (VIO_eqf.cpp:116-131 with R = sigma^2 I)
+            hLmOf[matched] = i;
+            hYIdx[matched] = j;
             ++matched;
         } else if (f->st.removeLostLandmarks) {
             P.keep[i] = 0;  // removeOldLandmarks, VIOFilter.cpp:203-205
@@ -907,10 +914,18 @@ int launch_correction(eqvio_filter* f, const int* guard) {
     std::unordered_map<int, int> spos;
     spos.reserve(Nn * 2 + 1);
     for (int i = 0; i < Nn; ++i) spos[f->ids[i]] = i;
-    std::vector<int> lmOf(nm);
-    for (int j = 0; j < nm; ++j) lmOf[j] = spos.at(kmids[j]);
-
+    std::vector<int> lmOf(nm), yIdx(nm);
+    {
+        std::vector<std::pair<int, int>> rows(nm);  // (state index, position in the kept measurement)
+        for (int j = 0; j < nm; ++j) rows[j] = {spos.at(kmids[j]), j};
+        if (f->corrMode == 0) std::sort(rows.begin(), rows.end());  // batch mode keeps the reference's ascending-id rows
+        for (int j = 0; j < nm; ++j) {
+            lmOf[j] = rows[j].first;
+            yIdx[j] = rows[j].second;
+        }
+    }
     if ((rc = upload(f, f->d_lmOf, lmOf.data(), nm)) != EQVIO_OK) return rc;
+    if ((rc = upload(f, f->d_yIdx, yIdx.data(), nm)) != EQVIO_OK) return rc;
     if ((rc = upload(f, f->d_y, ky.data(), ky.size())) != EQVIO_OK) return rc;
     if ((rc = enqueue_correction(f, nm, guard)) != EQVIO_OK) return rc;
     stage_mark(f, 3);
@@ -941,7 +956,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
         const int T = ldy / DD_T;
         double* Y = f->d_Z;
         meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
-                                                          s.useEquivariantOutput ? 1 : 0, f->d_Cblk, f->d_ytilde, 1, 0, guard);
+                                                          s.useEquivariantOutput ? 1 : 0, f->d_Cblk, f->d_ytilde, 1, 0, guard, f->d_yIdx);
         LAUNCH_CHECK(f, "meas_kernel");
         double* gin = f->d_Gamma;
         double* gout = f->d_Gamma2;
@@ -963,7 +978,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
         gammaFinal = gin;
     } else {
     meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
-                                                      s.useEquivariantOutput ? 1 : 0, f->d_Cblk, Z, ldz, m + dimp, guard);
+                                                      s.useEquivariantOutput ? 1 : 0, f->d_Cblk, Z, ldz, m + dimp, guard, f->d_yIdx);
     LAUNCH_CHECK(f, "meas_kernel");
     zbuild_kernel<<<dim3(cdiv(dimp, 256), nm), 256, 0, f->stream>>>(f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, Z, ldz, m);
     LAUNCH_CHECK(f, "zbuild_kernel");
@@ -1649,16 +1664,106 @@ int eqvio_get_landmark_cov_blocks(eqvio_filter* f, double* blocks) {
 
 int eqvio_get_feature_predictions(eqvio_filter* f, const eqvio_camera* cam, double stamp, int* ids, double* y, int* n_out) {
     ENTER(f);
-    (void)cam;
-    (void)stamp;
-    (void)ids;
-    (void)y;
     if (n_out) *n_out = 0;
-    if (f->st.useFeaturePredictions) {
-        f->err = "useFeaturePredictions (VIO_eqf::predictState) has no CUDA path in this build";
+    if (!f->st.useFeaturePredictions) return EQVIO_OK;  // VIOFilter.cpp:247-252: an empty measurement
+    if (!cam) return EQVIO_ERR_INVALID_ARG;
+    if (cam->model != EQVIO_CAMERA_PINHOLE && cam->model != EQVIO_CAMERA_RADTAN) {
+        f->err = "unsupported camera model";
         return EQVIO_ERR_UNSUPPORTED;
     }
-    return EQVIO_OK;  // VIOFilter.cpp:247-252: an empty measurement
+    stage_reset(f);
+    const int N = (int)f->ids.size();
+    if (n_out) *n_out = N;
+    if (N == 0) return EQVIO_OK;
+    // predictState (VIO_eqf.cpp:139-151): zero-order-hold segments of the buffered IMU samples up to `stamp`
+    const int n = (int)f->buf.size();
+    std::vector<double> rows((size_t)13 * std::max(n, 1), 0.0);
+    for (int i = 0; i < n; ++i) {
+        const double t0 = std::max(f->buf[i].stamp, f->time);
+        const double t1 = i + 1 < n ? std::min(f->buf[i + 1].stamp, stamp) : stamp;
+        rows[13 * i] = std::max(t1 - t0, 0.0);
+        for (int k = 0; k < 12; ++k) rows[13 * i + 1 + k] = f->buf[i].v[k];
+    }
+    int rc;
+    double* d_rows = f->d_Z;  // scratch
+    if (n > 0 && (rc = upload(f, d_rows, rows.data(), (size_t)13 * n)) != EQVIO_OK) return rc;
+    double* d_px = f->d_Z + (size_t)13 * std::max(n, 1);
+    predict_kernel<<<cdiv(N, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_xi0s, f->d_Xs[f->xcur], d_rows, n,
+                                                         to_camera(cam), d_px);
+    LAUNCH_CHECK(f, "predict_kernel");
+    double* h = nullptr;
+    if ((rc = download_async(f, &h, d_px, 2 * (size_t)N)) != EQVIO_OK) return rc;
+    CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+    if (ids) std::memcpy(ids, f->ids.data(), N * sizeof(int));
+    if (y) std::memcpy(y, h, 2 * (size_t)N * sizeof(double));
+    return EQVIO_OK;
+}
+
+// VIO_eqf::computeNEES (VIO_eqf.cpp:153-170): eps^T Sigma^-1 eps / dim with eps the chart coordinates of the true
+// state seen through X^-1.  Sigma^-1 is never formed: Sigma = L L^T by the blocked sweep, z = L^-1 eps, NEES = |z|^2 / dim.
+int eqvio_compute_nees(eqvio_filter* f, const double true_sensor[23], int n_true, const int* true_ids, const double* true_p,
+                       double* nees) {
+    ENTER(f);
+    if (!true_sensor || !nees || n_true < 0 || (n_true > 0 && (!true_ids || !true_p))) return EQVIO_ERR_INVALID_ARG;
+    stage_reset(f);
+    const int N = (int)f->ids.size();
+    const int dim = SENSOR_DIM + 3 * N;
+    // truncate / reorder the true landmarks to the state order (VIO_eqf.cpp:154-163)
+    std::vector<std::pair<int, int>> idx(n_true);
+    for (int j = 0; j < n_true; ++j) idx[j] = {true_ids[j], j};
+    std::sort(idx.begin(), idx.end());
+    std::vector<double> tp((size_t)3 * std::max(N, 1));
+    for (int i = 0; i < N; ++i) {
+        auto it = std::lower_bound(idx.begin(), idx.end(), std::make_pair(f->ids[i], -1));
+        if (it == idx.end() || it->first != f->ids[i]) {
+            f->err = "compute_nees: a state landmark is missing from the true state";
+            return EQVIO_ERR_INVALID_ARG;
+        }
+        for (int a = 0; a < 3; ++a) tp[3 * i + a] = true_p[3 * it->second + a];
+    }
+    int rc;
+    const int Mz = dim + 1;
+    const int ldz = (Mz + 7) & ~7;
+    double* Z = f->d_Z;
+    double* d_ts = f->d_Gamma;        // scratch: 23 doubles
+    double* d_tp = f->d_uv;           // scratch: 3N doubles (UV_STRIDE * cap available)
+    if ((rc = upload(f, d_ts, true_sensor, 23)) != EQVIO_OK) return rc;
+    if (N > 0 && (rc = upload(f, d_tp, tp.data(), (size_t)3 * N)) != EQVIO_OK) return rc;
+    CUDA_TRY(f, cudaMemsetAsync(f->d_status, 0, sizeof(int), f->stream));
+    pack_sigma_kernel<<<dim3(cdiv(dim, 128), dim), 128, 0, f->stream>>>(f->Sig[f->cur], f->ld, dim, Z, ldz);
+    LAUNCH_CHECK(f, "pack_sigma_kernel");
+    nees_eps_kernel<<<cdiv(std::max(N, 1), 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_xi0s, f->d_Xs[f->xcur], d_ts, d_tp,
+                                                                      f->st.coordinateChoice, Z, ldz, dim);
+    LAUNCH_CHECK(f, "nees_eps_kernel");
+    for (int k = 0; k < dim; k += NB) {
+        const int nbk = std::min(NB, dim - k);
+        const int below = Mz - (k + nbk);
+        chol_panel_kernel<<<std::max(1, cdiv(below, PANEL_THREADS)), PANEL_THREADS, 0, f->stream>>>(Z, ldz, Mz, k, nbk, f->d_status,
+                                                                                                     f->d_Lout);
+        LAUNCH_CHECK(f, "chol_panel_kernel");
+        if (k + nbk < dim) {
+            const int o = k + nbk;
+            gemm_nt_sub_kernel<false><<<dim3(cdiv(dim - o, GBN), cdiv(Mz - o, GBM)), 128, 0, f->stream>>>(
+                Z + (size_t)o * ldz + o, ldz, Z + (size_t)k * ldz + o, ldz, Z + (size_t)k * ldz + o, ldz, Mz - o, dim - o, nbk);
+            LAUNCH_CHECK(f, "gemm_nt_sub_kernel<trail>");
+        }
+    }
+    // z^T is the last row of Z: gather it (stride ldz) with a 2-D copy
+    double* hz = static_cast<double*>(stage_alloc(f, (size_t)dim * sizeof(double)));
+    int* hst = nullptr;
+    if (!hz) return EQVIO_ERR_CUDA;
+    CUDA_TRY(f, cudaMemcpy2DAsync(hz, sizeof(double), Z + dim, (size_t)ldz * sizeof(double), sizeof(double), dim,
+                                  cudaMemcpyDeviceToHost, f->stream));
+    if ((rc = download_async(f, &hst, f->d_status, 1)) != EQVIO_OK) return rc;
+    CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+    if (*hst & 1) {
+        f->err = "compute_nees: Sigma is not positive definite";
+        return EQVIO_ERR_NUMERIC;
+    }
+    double s2 = 0.0;
+    for (int k = 0; k < dim; ++k) s2 += hz[k] * hz[k];
+    *nees = s2 / dim;
+    return EQVIO_OK;
 }
 
 int eqvio_get_last_outliers(const eqvio_filter* f, int* ids, int cap, int* n_out) {
@@ -1721,6 +1826,12 @@ int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
             return EQVIO_ERR_INVALID_ARG;
     }
 }
+
+#ifdef EQVIO_CHUNK_TIMING
+int eqvio_debug_chunk_timing(long long out[16]) {
+    return cudaMemcpyFromSymbol(out, g_chunk_t, sizeof(long long) * 16) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 const char* eqvio_build_info(void) { return "eqvio_b200 sm_100a fp64 (CUDA " EQVIO_STR(__CUDACC_VER_MAJOR__) "." EQVIO_STR(__CUDACC_VER_MINOR__) ")"; }
 

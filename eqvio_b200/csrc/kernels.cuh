@@ -632,9 +632,10 @@ __global__ void fill_ll_diag_kernel(double* __restrict__ S, int ld, int n3, doub
 __global__ void meas_kernel(const double* __restrict__ lm, int cap, const int* __restrict__ lmOf, int n,
                             const double* __restrict__ y, const FrameHeader* __restrict__ fr, int coord, int useStar,
                             double* __restrict__ Cblk, double* __restrict__ Z, int ldz, int yrow,
-                            const int* __restrict__ guard) {
+                            const int* __restrict__ guard, const int* __restrict__ yIdx) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n || *guard) return;
+    const int jm = yIdx ? yIdx[j] : j;  // row pair j of the correction takes the pixel of measurement jm
     const Camera cam = fr->cam;
     int i = lmOf[j];
     V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
@@ -643,7 +644,7 @@ __global__ void meas_kernel(const double* __restrict__ lm, int cap, const int* _
     V3 qh = landmark_action(Q, a, q0);
     double u, v;
     cam_project(cam, qh, u, v);
-    double yu = y[2 * j], yv = y[2 * j + 1];
+    double yu = y[2 * jm], yv = y[2 * jm + 1];
     Z[(size_t)(2 * j) * ldz + yrow] = yu - u;
     Z[(size_t)(2 * j + 1) * ldz + yrow] = yv - v;
     double C[6];
@@ -880,10 +881,10 @@ constexpr int CH_COLS = 32;     // state columns per CTA
 constexpr int CH_T = 4;                                   // register tile edge
 constexpr int CH_NT = CH_R / CH_T;                        // 16 tile columns
 constexpr int CH_TILES = CH_NT * (CH_NT + 1) / 2;         // 136 lower tiles of S_c
+constexpr int CH_S_THREADS = 160;                         // warps 0-4 own the S_c tiles (24 threads idle)
 constexpr int CH_RHS_ROWS = (CH_COLS + 1 + CH_T - 1) / CH_T;  // 9 tile rows: 32 state columns + the residual (+ padding)
-constexpr int CH_RHS_TILES = CH_RHS_ROWS * CH_NT;         // 144
-constexpr int CH_THREADS = 288;                           // 136 + 144 = 280 tile owners
-constexpr int CH_PROWS = CH_NT + CH_RHS_ROWS;             // tile rows of the augmented matrix [S_c; W_c^T; r^T]
+constexpr int CH_RHS_THREADS = 160;                       // warps 5-9: one tile row per half-warp (lane % 16 = tile column)
+constexpr int CH_THREADS = CH_S_THREADS + CH_RHS_THREADS;
 // Y is stored tile-blocked for the downdate kernel: tile t = 64 consecutive state columns, stored as 64 rows
 // (k) of 68 doubles (the last 4 are padding) so that a whole panel is ONE contiguous bulk copy that lands in
 // shared memory with a bank-conflict-free row stride.
@@ -892,13 +893,15 @@ constexpr size_t YB_TILE = (size_t)YB_T * YB_LD;
 __host__ __device__ __forceinline__ size_t yb_index(int k, int s) { return (size_t)(s >> 6) * YB_TILE + (size_t)k * YB_LD + (s & 63); }
 
 struct ChunkSmem {
-    double Pn[CH_T][CH_T][CH_PROWS + 1];  // finished panel of the current block column: Pn[r][j][tile row]
-    double D[2][CH_T][CH_T];              // diagonal tile of the current block column (unscaled), double-buffered
-    double Dc[2][CH_T];                   // reciprocal pivots
+    union {
+        double Lp[CH_NT][CH_T][CH_T][CH_NT + 1];  // Lp[J][r][j][TI] = v(row 4TI+r, col 4J+j): every finished panel is kept
+        double Yt[CH_R][CH_RHS_ROWS * CH_T + 1];  // afterwards: scaled rows of Y for this CTA's columns (+ the residual z)
+    };
+    double Dc[CH_NT][CH_T];                   // reciprocal pivots of block column J
     double C[CH_R / 2][6];
     double Inv[CH_R];
-    double Yt[CH_R][CH_RHS_ROWS * CH_T + 1];  // scaled rows of Y for this CTA's columns (+ the residual column z)
     int Idx[CH_R / 2];
+    volatile int ready;                       // block columns of S_c whose panels are published
 };
 
 // reciprocal to <= 1 ulp: hardware approximation + two Newton steps (a correctly rounded division is
@@ -918,14 +921,24 @@ __device__ __forceinline__ void tri_decode(int t, int& row, int& col) {
     row = r;
     col = t - r * (r + 1) / 2;
 }
+#ifdef EQVIO_CHUNK_TIMING
+__device__ long long g_chunk_t[16];
+#define CH_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == (i < 100 ? 0 : CH_S_THREADS)) g_chunk_t[(i) % 100] = clock64(); } while (0)
+#else
+#define CH_STAMP(i) do { } while (0)
+#endif
+__device__ __forceinline__ void s_group_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(CH_S_THREADS) : "memory"); }
 
 // chunk_factor_kernel: every CTA eliminates the augmented matrix [S_c; W_c^T(its 32 state columns); r^T] in
-// registers: one thread owns one 4x4 tile for the whole elimination (136 tiles of the lower triangle of S_c,
-// 144 tiles of right-hand-side rows), so the triangular solve Y_c = L_c^-1 W_c rides along with the
-// factorisation at no extra latency.  Right-looking, unscaled columns (after block column J its entries hold
-// v_ij = L_ij L_jj); per block column: the diagonal owner eliminates inside its tile and publishes it, the panel
-// owners finish their four columns and publish them, everybody to the right applies the rank-4 update --
-// two barriers per four columns.  Grid = (padded dimp) / 32 CTAs, each repeats the (tiny) S_c work.
+// registers, one 4x4 tile per thread, right-looking with unscaled columns (after block column J its entries hold
+// v_ij = L_ij L_jj), so the triangular solve Y_c = L_c^-1 W_c rides along with the factorisation.
+//   S group   (warps 0-4, 136 tiles of the lower triangle of S_c): per block column the diagonal owner eliminates
+//             inside its tile (fraction-free, four reciprocals side by side), the panel owners finish their four
+//             columns, the tiles to the right apply the rank-4 update; two NAMED barriers per block column, every
+//             finished panel stays in shared memory.
+//   RHS group (warps 5-9, one tile row per half-warp): follows the S group through a progress flag, never joins its
+//             barriers -- the serial pivot chain of S_c is not slowed down by the 144 right-hand-side tiles.
+// Grid = (padded dimp) / 32 CTAs, each repeats the (tiny) S_c work.
 __global__ void __launch_bounds__(CH_THREADS)
     chunk_factor_kernel(const double* __restrict__ Sig, int ld, int dimp, const int* __restrict__ lmOf,
                         const double* __restrict__ Cblk, const double* __restrict__ ytilde, int j0, int bc, double r2,
@@ -935,74 +948,172 @@ __global__ void __launch_bounds__(CH_THREADS)
     __shared__ ChunkSmem sm;
     const int tid = threadIdx.x;
     const int rc = 2 * bc;
+    CH_STAMP(0);
     for (int t = tid; t < bc * 6; t += CH_THREADS) sm.C[t / 6][t % 6] = Cblk[6 * (size_t)j0 + t];
     for (int t = tid; t < bc; t += CH_THREADS) sm.Idx[t] = SOFF + 3 * lmOf[j0 + t];
+    if (tid == 0) sm.ready = 0;
     __syncthreads();
+    CH_STAMP(1);
 
-    // tile ownership: TI = tile row in the augmented matrix, TK = tile column
-    const bool isS = tid < CH_TILES;
-    const bool isRhs = tid >= CH_TILES && tid < CH_TILES + CH_RHS_TILES;
-    const bool owner = isS || isRhs;
-    int TI = 0, TK = 0;
-    if (isS) {
-        tri_decode(tid, TI, TK);
-    } else if (isRhs) {
-        TI = CH_NT + (tid - CH_TILES) / CH_NT;
-        TK = (tid - CH_TILES) % CH_NT;
-    }
+    const bool sGroup = tid < CH_S_THREADS;
     const int sbase = blockIdx.x * CH_COLS;
+    const int nJ = (rc + CH_T - 1) / CH_T;
     double a[CH_T][CH_T];
 #pragma unroll
     for (int r = 0; r < CH_T; ++r)
 #pragma unroll
         for (int c = 0; c < CH_T; ++c) a[r][c] = 0.0;
-    if (isS) {
-        // S tile = 2x2 landmark pairs: rows from landmarks 2TI, 2TI+1; columns from 2TK, 2TK+1
-        double P[2][2][9];
+
+    if (sGroup) {
+        // ================================ S group ================================
+        const bool owner = tid < CH_TILES;
+        int TI = 0, TK = 0;
+        if (owner) tri_decode(tid, TI, TK);
+        if (owner) {
+            // S tile = 2x2 landmark pairs: rows from landmarks 2TI, 2TI+1; columns from 2TK, 2TK+1.  All loads first.
+            double P[2][2][9];
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+            for (int u = 0; u < 2; ++u)
 #pragma unroll
-            for (int v = 0; v < 2; ++v) {
-                const int j = 2 * TI + u, k = 2 * TK + v;
-                if (j < bc && k < bc) {
-                    const double* sp = Sig + (size_t)sm.Idx[k] * ld + sm.Idx[j];  // Sigma[rows of j, cols of k]
+                for (int v = 0; v < 2; ++v) {
+                    const int j = 2 * TI + u, k = 2 * TK + v;
+                    if (j < bc && k < bc) {
+                        // Sigma[rows of j, cols of k] read through its mirror Sigma[rows of k, cols of j]: lanes walk k, and
+                        // chunks follow the state order, so a warp touches a few contiguous lines instead of 32
+                        const double* sp = Sig + (size_t)sm.Idx[j] * ld + sm.Idx[k];
 #pragma unroll
-                    for (int b = 0; b < 3; ++b)
+                        for (int aa = 0; aa < 3; ++aa)
 #pragma unroll
-                        for (int aa = 0; aa < 3; ++aa) P[u][v][aa * 3 + b] = sp[(size_t)b * ld + aa];
+                            for (int b = 0; b < 3; ++b) P[u][v][aa * 3 + b] = sp[(size_t)aa * ld + b];
+                    }
                 }
-            }
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+            for (int u = 0; u < 2; ++u)
 #pragma unroll
-            for (int v = 0; v < 2; ++v) {
-                const int j = 2 * TI + u, k = 2 * TK + v;
-                if (j < bc && k < bc) {
-                    double T[6];
+                for (int v = 0; v < 2; ++v) {
+                    const int j = 2 * TI + u, k = 2 * TK + v;
+                    if (j < bc && k < bc) {
+                        double T[6];
 #pragma unroll
-                    for (int e = 0; e < 2; ++e)
+                        for (int e = 0; e < 2; ++e)
 #pragma unroll
-                        for (int b = 0; b < 3; ++b)
-                            T[e * 3 + b] = sm.C[j][3 * e] * P[u][v][b] + sm.C[j][3 * e + 1] * P[u][v][3 + b] + sm.C[j][3 * e + 2] * P[u][v][6 + b];
+                            for (int b = 0; b < 3; ++b)
+                                T[e * 3 + b] = sm.C[j][3 * e] * P[u][v][b] + sm.C[j][3 * e + 1] * P[u][v][3 + b] + sm.C[j][3 * e + 2] * P[u][v][6 + b];
 #pragma unroll
-                    for (int e = 0; e < 2; ++e)
+                        for (int e = 0; e < 2; ++e)
 #pragma unroll
-                        for (int f = 0; f < 2; ++f)
-                            a[2 * u + e][2 * v + f] = T[e * 3] * sm.C[k][3 * f] + T[e * 3 + 1] * sm.C[k][3 * f + 1] + T[e * 3 + 2] * sm.C[k][3 * f + 2];
+                            for (int f = 0; f < 2; ++f)
+                                a[2 * u + e][2 * v + f] = T[e * 3] * sm.C[k][3 * f] + T[e * 3 + 1] * sm.C[k][3 * f + 1] + T[e * 3 + 2] * sm.C[k][3 * f + 2];
+                    }
                 }
-            }
-        if (TI == TK) {
+            if (TI == TK) {
 #pragma unroll
-            for (int c = 0; c < CH_T; ++c) {
-                if (CH_T * TI + c < rc)
-                    a[c][c] += r2;
-                else
-                    a[c][c] = 1.0;  // identity padding of a short last chunk
+                for (int c = 0; c < CH_T; ++c) {
+                    if (CH_T * TI + c < rc)
+                        a[c][c] += r2;
+                    else
+                        a[c][c] = 1.0;  // identity padding of a short last chunk
+                }
             }
         }
-    } else if (isRhs) {
-        const int trow = TI - CH_NT;
-        if (trow < CH_COLS / CH_T) {
+        CH_STAMP(2);
+        for (int J = 0; J < nJ; ++J) {
+            if (owner && TI == J && TK == J) {
+                // 4x4 diagonal tile: fraction-free elimination (products only, 6 dependent operations) and then the
+                // four pivot reciprocals side by side -- the serial pivot -> reciprocal -> multiplier chain of the
+                // textbook order costs ~4 x 200 cycles of fp64 latency, with every other warp waiting on it.
+                const double a00 = a[0][0], a10 = a[1][0], a20 = a[2][0], a30 = a[3][0];
+                const double m11 = a[1][1] * a00 - a10 * a10, m21 = a[2][1] * a00 - a20 * a10, m22 = a[2][2] * a00 - a20 * a20;
+                const double m31 = a[3][1] * a00 - a30 * a10, m32 = a[3][2] * a00 - a30 * a20, m33 = a[3][3] * a00 - a30 * a30;
+                const double n22 = m22 * m11 - m21 * m21, n32 = m32 * m11 - m31 * m21, n33 = m33 * m11 - m31 * m31;
+                const double p33 = n33 * n22 - n32 * n32;
+                const double r0 = fast_rcp(a00), r1 = fast_rcp(m11), r2_ = fast_rcp(n22), r3 = fast_rcp(p33);
+                const double s2 = r0 * r1, s3 = s2 * r2_, e1 = a00 * m11;
+                // unscaled columns v_ij = L_ij L_jj (the Schur-complement values) and 1 / v_jj
+                a[1][1] = m11 * r0;
+                a[2][1] = m21 * r0;
+                a[3][1] = m31 * r0;
+                a[2][2] = n22 * s2;
+                a[3][2] = n32 * s2;
+                a[3][3] = p33 * s3;
+                sm.Dc[J][0] = r0;
+                sm.Dc[J][1] = a00 * r1;
+                sm.Dc[J][2] = e1 * r2_;
+                sm.Dc[J][3] = (e1 * n22) * r3;
+#pragma unroll
+                for (int i = 0; i < CH_T; ++i)
+#pragma unroll
+                    for (int j = 0; j < CH_T; ++j) sm.Lp[J][i][j][J] = a[i][j];
+            }
+            s_group_barrier();
+            if (owner && TK == J && TI > J) {
+                double c[CH_T], d[CH_T][CH_T];
+#pragma unroll
+                for (int j = 0; j < CH_T; ++j) c[j] = sm.Dc[J][j];
+#pragma unroll
+                for (int i = 0; i < CH_T; ++i)
+#pragma unroll
+                    for (int j = 0; j < CH_T; ++j) d[i][j] = sm.Lp[J][i][j][J];
+#pragma unroll
+                for (int j = 0; j < CH_T; ++j)
+#pragma unroll
+                    for (int k = j + 1; k < CH_T; ++k)
+#pragma unroll
+                        for (int r = 0; r < CH_T; ++r) a[r][k] -= (a[r][j] * c[j]) * d[k][j];
+#pragma unroll
+                for (int r = 0; r < CH_T; ++r)
+#pragma unroll
+                    for (int j = 0; j < CH_T; ++j) sm.Lp[J][r][j][TI] = a[r][j];
+            }
+            s_group_barrier();
+            if (tid == 0) {
+                __threadfence_block();
+                sm.ready = J + 1;  // the right-hand-side warps may consume block column J
+            }
+            if (owner && TK > J) {
+                double li[CH_T][CH_T], pk[CH_T][CH_T];
+#pragma unroll
+                for (int j = 0; j < CH_T; ++j) {
+                    const double c = sm.Dc[J][j];
+#pragma unroll
+                    for (int r = 0; r < CH_T; ++r) li[r][j] = sm.Lp[J][r][j][TI] * c;
+                }
+#pragma unroll
+                for (int cc = 0; cc < CH_T; ++cc)
+#pragma unroll
+                    for (int j = 0; j < CH_T; ++j) pk[cc][j] = sm.Lp[J][cc][j][TK];
+#pragma unroll
+                for (int r = 0; r < CH_T; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < CH_T; ++cc) {
+                        double acc = a[r][cc];
+#pragma unroll
+                        for (int j = 0; j < CH_T; ++j) acc -= li[r][j] * pk[cc][j];
+                        a[r][cc] = acc;
+                    }
+            }
+        }
+        CH_STAMP(3);
+        // 1 / L_kk from the diagonal tiles
+        if (owner && TI == TK) {
+#pragma unroll
+            for (int c = 0; c < CH_T; ++c) {
+                const double piv = a[c][c];
+                const int k = CH_T * TK + c;
+                if (!(piv > 0.0)) {
+                    if (blockIdx.x == 0) atomicOr(status, 1);
+                    sm.Inv[k] = 1.0;
+                } else {
+                    sm.Inv[k] = 1.0 / sqrt(piv);
+                }
+            }
+        }
+    } else {
+        // ================================ RHS group ================================
+        const int q = tid - CH_S_THREADS;
+        const int trow = q / CH_NT, TK = q % CH_NT;
+        const bool isRhs = trow < CH_RHS_ROWS;
+        if (isRhs && trow < CH_COLS / CH_T) {
             // rows s = sbase + 4 trow + r (state columns of W_c), columns k = 4TK + c from landmarks 2TK, 2TK+1
             const int s0 = sbase + CH_T * trow;
             double w[2][3][CH_T];
@@ -1033,7 +1144,7 @@ __global__ void __launch_bounds__(CH_THREADS)
                             a[r][2 * v + e] = (s0 + r < dimp) ? sm.C[j][3 * e] * w[v][0][r] + sm.C[j][3 * e + 1] * w[v][1][r] + sm.C[j][3 * e + 2] * w[v][2][r] : 0.0;
                 }
             }
-        } else {
+        } else if (isRhs) {
             // residual row (r = 0 of the last tile row): ytilde_c - C_c Gamma
 #pragma unroll
             for (int v = 0; v < 2; ++v) {
@@ -1046,108 +1157,69 @@ __global__ void __launch_bounds__(CH_THREADS)
                 }
             }
         }
-    }
-
-    const int nJ = (rc + CH_T - 1) / CH_T;
-    for (int J = 0; J < nJ; ++J) {
-        const int buf = J & 1;
-        if (isS && TI == J && TK == J) {
-            // 4x4 diagonal tile: fraction-free elimination (products only, 6 dependent operations) and then the
-            // four pivot reciprocals side by side -- the serial pivot -> reciprocal -> multiplier chain of the
-            // textbook order costs ~4 x 200 cycles of fp64 latency here, with every other warp waiting on it.
-            const double a00 = a[0][0], a10 = a[1][0], a20 = a[2][0], a30 = a[3][0];
-            const double m11 = a[1][1] * a00 - a10 * a10, m21 = a[2][1] * a00 - a20 * a10, m22 = a[2][2] * a00 - a20 * a20;
-            const double m31 = a[3][1] * a00 - a30 * a10, m32 = a[3][2] * a00 - a30 * a20, m33 = a[3][3] * a00 - a30 * a30;
-            const double n22 = m22 * m11 - m21 * m21, n32 = m32 * m11 - m31 * m21, n33 = m33 * m11 - m31 * m31;
-            const double p33 = n33 * n22 - n32 * n32;
-            const double r0 = fast_rcp(a00), r1 = fast_rcp(m11), r2 = fast_rcp(n22), r3 = fast_rcp(p33);
-            const double s2 = r0 * r1, s3 = s2 * r2, e1 = a00 * m11;
-            // unscaled columns v_ij = L_ij L_jj (the Schur-complement values) and 1 / v_jj
-            a[1][1] = m11 * r0;
-            a[2][1] = m21 * r0;
-            a[3][1] = m31 * r0;
-            a[2][2] = n22 * s2;
-            a[3][2] = n32 * s2;
-            a[3][3] = p33 * s3;
-            sm.Dc[buf][0] = r0;
-            sm.Dc[buf][1] = a00 * r1;
-            sm.Dc[buf][2] = e1 * r2;
-            sm.Dc[buf][3] = (e1 * n22) * r3;
+        CH_STAMP(108);
+        for (int J = 0; J < nJ; ++J) {
+            while (sm.ready <= J) __nanosleep(64);
+            __threadfence_block();
+            // the lane holding tile column J finishes its four columns ...
+            double c[CH_T];
 #pragma unroll
-            for (int i = 0; i < CH_T; ++i)
+            for (int j = 0; j < CH_T; ++j) c[j] = sm.Dc[J][j];
+            if (TK == J) {
+                double d[CH_T][CH_T];
 #pragma unroll
-                for (int j = 0; j < CH_T; ++j) sm.D[buf][i][j] = a[i][j];
-        }
-        __syncthreads();
-        if (owner && TK == J && TI > J) {
-            double c[CH_T], d[CH_T][CH_T];
+                for (int i = 0; i < CH_T; ++i)
 #pragma unroll
-            for (int j = 0; j < CH_T; ++j) c[j] = sm.Dc[buf][j];
+                    for (int j = 0; j < CH_T; ++j) d[i][j] = sm.Lp[J][i][j][J];
 #pragma unroll
-            for (int i = 0; i < CH_T; ++i)
+                for (int j = 0; j < CH_T; ++j)
 #pragma unroll
-                for (int j = 0; j < CH_T; ++j) d[i][j] = sm.D[buf][i][j];
+                    for (int k = j + 1; k < CH_T; ++k)
 #pragma unroll
-            for (int j = 0; j < CH_T; ++j)
-#pragma unroll
-                for (int k = j + 1; k < CH_T; ++k)
-#pragma unroll
-                    for (int r = 0; r < CH_T; ++r) a[r][k] -= (a[r][j] * c[j]) * d[k][j];
+                        for (int r = 0; r < CH_T; ++r) a[r][k] -= (a[r][j] * c[j]) * d[k][j];
+            }
+            // ... and hands them to the rest of its half-warp (same tile row)
+            double li[CH_T][CH_T];
 #pragma unroll
             for (int r = 0; r < CH_T; ++r)
 #pragma unroll
-                for (int j = 0; j < CH_T; ++j) sm.Pn[r][j][TI] = a[r][j];
-        }
-        __syncthreads();
-        if (owner && TK > J) {
-            double li[CH_T][CH_T], pk[CH_T][CH_T];
+                for (int j = 0; j < CH_T; ++j) li[r][j] = __shfl_sync(0xffffffffu, a[r][j], J, CH_NT) * c[j];
+            if (TK > J) {
+                double pk[CH_T][CH_T];
 #pragma unroll
-            for (int j = 0; j < CH_T; ++j) {
-                const double c = sm.Dc[buf][j];
+                for (int cc = 0; cc < CH_T; ++cc)
 #pragma unroll
-                for (int r = 0; r < CH_T; ++r) li[r][j] = sm.Pn[r][j][TI] * c;
-            }
+                    for (int j = 0; j < CH_T; ++j) pk[cc][j] = sm.Lp[J][cc][j][TK];
 #pragma unroll
-            for (int cc = 0; cc < CH_T; ++cc)
+                for (int r = 0; r < CH_T; ++r)
 #pragma unroll
-                for (int j = 0; j < CH_T; ++j) pk[cc][j] = sm.Pn[cc][j][TK];
+                    for (int cc = 0; cc < CH_T; ++cc) {
+                        double acc = a[r][cc];
 #pragma unroll
-            for (int r = 0; r < CH_T; ++r)
-#pragma unroll
-                for (int cc = 0; cc < CH_T; ++cc) {
-                    double acc = a[r][cc];
-#pragma unroll
-                    for (int j = 0; j < CH_T; ++j) acc -= li[r][j] * pk[cc][j];
-                    a[r][cc] = acc;
-                }
-        }
-    }
-    // 1 / L_kk from the diagonal tiles
-    if (isS && TI == TK) {
-#pragma unroll
-        for (int c = 0; c < CH_T; ++c) {
-            const double piv = a[c][c];
-            const int k = CH_T * TK + c;
-            if (!(piv > 0.0)) {
-                if (blockIdx.x == 0) atomicOr(status, 1);
-                sm.Inv[k] = 1.0;
-            } else {
-                sm.Inv[k] = 1.0 / sqrt(piv);
+                        for (int j = 0; j < CH_T; ++j) acc -= li[r][j] * pk[cc][j];
+                        a[r][cc] = acc;
+                    }
             }
         }
     }
-    __syncthreads();
+    CH_STAMP(109);
+    __syncthreads();  // Inv published, every tile final
+    CH_STAMP(4);
     // Y[k][s] = v_sk / L_kk, staged so that the global store and the Gamma dot products run in a fixed order
-    if (isRhs) {
-        const int trow = TI - CH_NT;
+    if (!sGroup) {
+        const int q = tid - CH_S_THREADS;
+        const int trow = q / CH_NT, TK = q % CH_NT;
+        if (trow < CH_RHS_ROWS) {
 #pragma unroll
-        for (int c = 0; c < CH_T; ++c) {
-            const double sc = sm.Inv[CH_T * TK + c];
+            for (int c = 0; c < CH_T; ++c) {
+                const double sc = sm.Inv[CH_T * TK + c];
 #pragma unroll
-            for (int r = 0; r < CH_T; ++r) sm.Yt[CH_T * TK + c][CH_T * trow + r] = a[r][c] * sc;
+                for (int r = 0; r < CH_T; ++r) sm.Yt[CH_T * TK + c][CH_T * trow + r] = a[r][c] * sc;
+            }
         }
     }
     __syncthreads();
+    CH_STAMP(5);
     // all CH_R rows are written (zero beyond rc and for the pad columns s >= dimp): the downdate reads whole tiles
     for (int t = tid; t < CH_R * CH_COLS; t += CH_THREADS) {
         const int k = t / CH_COLS, sl = t % CH_COLS;
@@ -1159,6 +1231,7 @@ __global__ void __launch_bounds__(CH_THREADS)
         for (int k = 0; k < CH_R; ++k) g += sm.Yt[k][tid] * sm.Yt[k][CH_COLS];
         GammaOut[sbase + tid] = GammaIn[sbase + tid] + g;  // ping-pong: other CTAs may still be reading GammaIn
     }
+    CH_STAMP(6);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1375,6 +1448,64 @@ __global__ void state_estimate_kernel(const double* __restrict__ lm, int cap, in
     out[23 + 3 * i] = p.x;
     out[23 + 3 * i + 1] = p.y;
     out[23 + 3 * i + 2] = p.z;
+}
+
+// ------------------------------------------------------------------------------------------------
+// getFeaturePredictions (VIOFilter.cpp:247-252): predictState (VIO_eqf.cpp:139-151) = integrateSystemFunction over the
+// buffered IMU segments starting from the state estimate, then measureSystemState (VIOState.cpp:70-78).  Every CTA
+// repeats the (tiny) sensor chain; one thread per landmark.  imu rows: dt, gyr3, acc3, gyrBiasVel3, accBiasVel3.
+// ------------------------------------------------------------------------------------------------
+__global__ void predict_kernel(const double* __restrict__ lm, int cap, int N, const double* __restrict__ xi0s,
+                               const double* __restrict__ Xs, const double* __restrict__ imu, int nsteps, Camera cam,
+                               double* __restrict__ out) {
+    __shared__ SE3 sT;
+    if (threadIdx.x == 0) {
+        SensorState s = sensor_group_action(unpack_group(Xs), unpack_sensor(xi0s));
+        SE3 T = se3_identity();
+        for (int k = 0; k < nsteps; ++k) {
+            SE3 c = integrate_system_sensor(s, imu + 13 * k + 1, imu[13 * k]);
+            T = se3_mul(c, T);
+        }
+        sT = T;
+    }
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
+    Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
+    V3 p = se3_apply(sT, landmark_action(Q, lm[F_QA * cap + i], q0));
+    double u, v;
+    cam_project(cam, p, u, v);
+    out[2 * i] = u;
+    out[2 * i + 1] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// computeNEES, first half (VIO_eqf.cpp:153-166): the linearised state error
+//   eps = stateChart( stateGroupAction(X^-1, xi_true), xi0 )      (sensorChart_std + euclid / invdepth point charts)
+// written as the extra row `row` of the column-major work matrix Z (unpadded state order).  trueP is in state order.
+// ------------------------------------------------------------------------------------------------
+__global__ void nees_eps_kernel(const double* __restrict__ lm, int cap, int N, const double* __restrict__ xi0s,
+                                const double* __restrict__ Xs, const double* __restrict__ trueSensor,
+                                const double* __restrict__ trueP, int coord, double* __restrict__ Z, int ldz, int row) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        SensorState xi0 = unpack_sensor(xi0s);
+        SensorState err = sensor_group_action(group_inverse(unpack_group(Xs)), unpack_sensor(trueSensor));
+        double eps[21];
+        sensor_chart_std(err, xi0, eps);
+        for (int k = 0; k < 21; ++k) Z[(size_t)k * ldz + row] = eps[k];
+    }
+    if (i >= N) return;
+    V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
+    Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
+    const double a = lm[F_QA * cap + i];
+    V3 pt = V3{trueP[3 * i], trueP[3 * i + 1], trueP[3 * i + 2]};
+    V3 pe = a * qrot(Q, pt);  // (Q^-1)^-1 p = Q p = a R_Q p  (VIOGroup.cpp:44-52 with X^-1, SOT3.h:95-97)
+    V3 e = (coord == COORD_INVDEPTH) ? invdepth_chart(pe, q0) : pe - q0;
+    Z[(size_t)(21 + 3 * i) * ldz + row] = e.x;
+    Z[(size_t)(21 + 3 * i + 1) * ldz + row] = e.y;
+    Z[(size_t)(21 + 3 * i + 2) * ldz + row] = e.z;
 }
 
 // Sigma in the reference's layout (dim x dim, column-major, no pad)

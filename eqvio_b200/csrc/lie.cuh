@@ -194,6 +194,18 @@ HD SE3 se3_inv(const SE3& a) {                                                  
     return SE3{qi, -qrot(qi, a.x)};
 }
 HD V3 se3_apply(const SE3& a, V3 p) { return qrot(a.q, p) + a.x; }
+// SE3::log (SE3.h:85-104): out = (omega, v)
+HD void se3_log(const SE3& P, double* out) {
+    V3 om = so3_log(P.q);
+    M3 O = skew(om);
+    double theta = sqrt(om.x * om.x + om.y * om.y + om.z * om.z);
+    double coef = 1.0 / 12.0;
+    if (fabs(theta) > 1e-6) coef = 1.0 / (theta * theta) * (1.0 - (theta * sin(theta)) / (2.0 * (1.0 - cos(theta))));
+    M3 VInv = m3_identity() - 0.5 * O + coef * (O * O);
+    V3 v = VInv * P.x;
+    out[0] = om.x; out[1] = om.y; out[2] = om.z;
+    out[3] = v.x; out[4] = v.y; out[5] = v.z;
+}
 HD void rodrigues(V3 w, bool strict, M3& R, M3& V) {  // SE3.h:59-77 (strict: >1e-12), SEn3.h:66-87 (>=1e-12)
     double th = norm(w);
     double A, B, C;

@@ -203,6 +203,57 @@ HD V3 stereo_inv(double y0, double y1, V3 pole) {
     V3 eta = V3{k * y0, k * y1, 1.0 + k * (0.0 - 1.0)};
     return qrot(qinv(stereo_rot(pole)), eta);
 }
+// sphereChart_stereo(eta, pole) (VIOState.cpp:286-290) with e3ProjectSphere (:246-251)
+HD void stereo_chart(V3 eta, V3 pole, double& y0, double& y1) {
+    V3 r = qrot(stereo_rot(pole), eta);
+    y0 = (r.x - 0.0) / (1.0 - r.z);
+    y1 = (r.y - 0.0) / (1.0 - r.z);
+}
+// pointChart_invdepth (VIOState.cpp:160-173)
+HD V3 invdepth_chart(V3 p, V3 p0) {
+    double rho = 1.0 / norm(p), rho0 = 1.0 / norm(p0);
+    double a, b;
+    stereo_chart(p * rho, p0 * rho0, a, b);
+    return V3{a, b, rho - rho0};
+}
+// sensor part of VIOGroup::inverse (VIOGroup.cpp:108-121)
+HD GroupSensor group_inverse(const GroupSensor& X) {
+    GroupSensor r;
+    for (int i = 0; i < 6; ++i) r.beta[i] = -X.beta[i];
+    r.A = se3_inv(X.A);
+    r.B = se3_inv(X.B);
+    r.w = -qrot(qinv(X.A.q), X.w);
+    return r;
+}
+// sensorChart_std (VIOState.cpp:104-113): 21 coordinates of Xi about Xi0
+HD void sensor_chart_std(const SensorState& Xi, const SensorState& Xi0, double* eps) {
+    for (int i = 0; i < 6; ++i) eps[i] = Xi.bias[i] - Xi0.bias[i];
+    se3_log(se3_mul(se3_inv(Xi0.pose), Xi.pose), eps + 6);
+    eps[12] = Xi.vel.x - Xi0.vel.x;
+    eps[13] = Xi.vel.y - Xi0.vel.y;
+    eps[14] = Xi.vel.z - Xi0.vel.z;
+    se3_log(se3_mul(se3_inv(Xi0.cam), Xi.cam), eps + 15);
+}
+// integrateSystemFunction, sensor part (VIOState.cpp:27-68): advances s by one IMU segment u = (gyr, acc, gyrBiasVel,
+// accBiasVel) of length dt and returns the camera-frame change applied to every landmark.
+HD SE3 integrate_system_sensor(SensorState& s, const double* u, double dt) {
+    V3 gyr = V3{u[0] - s.bias[0], u[1] - s.bias[1], u[2] - s.bias[2]};
+    V3 acc = V3{u[3] - s.bias[3], u[4] - s.bias[4], u[5] - s.bias[5]};
+    SensorState n;
+    for (int i = 0; i < 6; ++i) n.bias[i] = s.bias[i] + dt * u[6 + i];
+    SE3 poseChange;
+    poseChange.q = so3_exp(dt * gyr);
+    V3 x = dt * qrot(s.pose.q, s.vel) + (0.5 * dt * dt) * (qrot(s.pose.q, acc) + V3{0, 0, -GRAVITY_CONSTANT});
+    poseChange.x = qrot(qinv(s.pose.q), x);
+    n.pose = se3_mul(s.pose, poseChange);
+    V3 inertialVelocityDiff = qmat(s.pose.q) * acc + V3{0, 0, -GRAVITY_CONSTANT};
+    n.vel = qrot(qinv(n.pose.q), qrot(s.pose.q, s.vel) + dt * inertialVelocityDiff);
+    n.cam = s.cam;
+    SE3 camChangeInv = se3_mul(se3_mul(se3_inv(s.cam), se3_inv(poseChange)), s.cam);
+    s = n;
+    return camChangeInv;
+}
+
 // pointChart_invdepth.inv (VIOState.cpp:174-188)
 HD V3 invdepth_chart_inv(V3 eps, V3 q0) {
     double rho0 = 1.0 / norm(q0);

@@ -313,9 +313,21 @@ class VIOFilter:
         return b[:9 * N].reshape(N, 3, 3).transpose(0, 2, 1).copy()
 
     def getFeaturePredictions(self, camera: Camera, stamp: float = -1.0) -> VisionMeasurement:  # VIOFilter.cpp:247-252
+        N = self.numLandmarks()
+        ids = np.zeros(max(N, 1), dtype=np.int32)
+        y = np.zeros(2 * max(N, 1))
         n = C.c_int(0)
-        self._check(lib.eqvio_get_feature_predictions(self._h, C.byref(camera.pod), float(stamp), None, None, C.byref(n)))
-        return VisionMeasurement()
+        self._check(lib.eqvio_get_feature_predictions(self._h, C.byref(camera.pod), float(stamp), _pi(ids), _pd(y), C.byref(n)))
+        k = n.value
+        return VisionMeasurement(float(stamp), {int(ids[j]): y[2 * j:2 * j + 2].copy() for j in range(k)}, camera)
+
+    def computeNEES(self, trueState: VIOState) -> float:
+        """viewEqFState().computeNEES(trueState) of the reference (VIO_eqf.cpp:153-170), evaluated on the device."""
+        ids = _i32(trueState.ids)
+        out = C.c_double(0.0)
+        self._check(lib.eqvio_compute_nees(self._h, _pd(_f64(trueState.sensor.flat(), 23)), len(ids), _pi(ids), _pd(_f64(trueState.p)),
+                                           C.byref(out)))
+        return out.value
 
     def lastOutliers(self):
         ids = np.zeros(max(self.capacity, 1), dtype=np.int32)

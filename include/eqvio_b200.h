@@ -143,10 +143,16 @@ int eqvio_get_eqf_state(eqvio_filter* f, double xi0_sensor[23], int* ids, double
 /* VIO_eqf::getLandmarkCovById for every landmark: 9 doubles (column-major 3x3) per landmark
  * (VIO_eqf.cpp:188-194; what VIOWriter::writeConsistency reads, src/VIOWriter.cpp:162-222). */
 int eqvio_get_landmark_cov_blocks(eqvio_filter* f, double* blocks /* 9N */);
-/* getFeaturePredictions (VIOFilter.cpp:247-252): pixel predictions at `stamp`; n_out = 0 unless
+/* getFeaturePredictions (VIOFilter.cpp:247-252): predictState (VIO_eqf.cpp:139-151) over the buffered IMU
+ * samples up to `stamp`, projected through `cam`; ids / y sized >= N, state order.  n_out = 0 unless
  * Settings::useFeaturePredictions. */
 int eqvio_get_feature_predictions(eqvio_filter* f, const eqvio_camera* cam, double stamp, int* ids, double* y,
                                   int* n_out);
+/* VIO_eqf::computeNEES (VIO_eqf.cpp:153-170), what eqvio_sim prints every frame (main_sim.cpp:146-148): the true
+ * state (sensor[23] + landmarks by id, any order, must contain every state landmark) -> NEES.  Solved on the device
+ * with a Cholesky sweep of Sigma instead of the reference's dense inverse. */
+int eqvio_compute_nees(eqvio_filter* f, const double true_sensor[23], int n_true, const int* true_ids, const double* true_p,
+                       double* nees);
 /* ids removed as outliers by the last eqvio_process_vision (VIOFilter.cpp:304-364), in removal order. */
 int eqvio_get_last_outliers(const eqvio_filter* f, int* ids, int cap, int* n_out);
 

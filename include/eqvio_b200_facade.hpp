@@ -183,11 +183,27 @@ public:
         return v;
     }
     VisionMeasurement getFeaturePredictions(const eqvio_camera& cam, const double& stamp = -1) {  // VIOFilter.cpp:247-252
+        const int N = eqvio_num_landmarks(h_);
+        std::vector<int> ids(N > 0 ? N : 1);
+        std::vector<double> px(2 * (N > 0 ? N : 1));
         int n = 0;
-        check(eqvio_get_feature_predictions(h_, &cam, stamp, nullptr, nullptr, &n));
+        check(eqvio_get_feature_predictions(h_, &cam, stamp, ids.data(), px.data(), &n));
         VisionMeasurement m;
+        m.stamp = stamp;
         m.camera = cam;
+        for (int j = 0; j < n; ++j) m.camCoordinates[ids[j]] = {px[2 * j], px[2 * j + 1]};
         return m;
+    }
+    // viewEqFState().computeNEES(trueState) (VIO_eqf.cpp:153-170) without moving Sigma to the host
+    double computeNEES(const VIOState& trueState) const {
+        double sensor[23];
+        pack(trueState.sensor, sensor);
+        std::vector<int> ids;
+        std::vector<double> p;
+        flatten(trueState.cameraLandmarks, ids, p);
+        double nees = 0;
+        check(eqvio_compute_nees(h_, sensor, (int)ids.size(), ids.data(), p.data(), &nees));
+        return nees;
     }
     eqvio_filter* handle() const { return h_; }
 

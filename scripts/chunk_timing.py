@@ -1,0 +1,39 @@
+"""Phase timestamps (clock64) of chunk_factor_kernel, CTA 0 -- needs a library built with -DEQVIO_CHUNK_TIMING
+at gpurun_out/libtiming.so.   python scripts/chunk_timing.py [N]"""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import shutil
+
+lib_dst = os.path.join(ROOT, "eqvio_b200", "lib", "libeqvio_b200.so")
+shutil.copy(os.path.join(ROOT, "eqvio_b200", "lib", "libtiming.so"), lib_dst)
+os.utime(lib_dst, None)
+import numpy as np
+
+import eqvio_b200 as eb
+from eqvio_b200 import _capi
+from simdata import SimConfig, record_stream
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+sm = record_stream(SimConfig.benchmark(N, 0), 12)
+flt = eb.VIOFilter(eb.Settings(fastRiccati=1), eb.VIOState(eb.VIOSensorState.fromFlat(sm.init_sensor), sm.init_p, sm.init_ids), 0.0,
+                   capacity=N + 8)
+flt.setTuning(graph=0)
+cam = eb.Camera(**sm.camera)
+for fr in sm.frames:
+    flt.processIMUArray(fr.imu)
+    flt.augmentLandmarkStates(fr.ids, eb.VIOState(eb.VIOSensorState(), fr.provided_p, fr.ids))
+    flt.processVisionArrays(fr.stamp, fr.ids, fr.y, cam)
+fn = _capi.lib.eqvio_debug_chunk_timing
+fn.restype = C.c_int
+out = (C.c_longlong * 16)()
+assert fn(out) == 0
+t = np.array(list(out), dtype=np.int64)
+names = {0: "start", 1: "C/Idx loaded", 2: "S gather done", 3: "S loop done", 4: "final barrier", 5: "Yt staged", 6: "end", 8: "RHS gather done",
+         9: "RHS loop done"}
+base = t[0]
+for i in sorted(names):
+    print(f"{names[i]:>18s}: {t[i] - base:8d} cycles")

@@ -290,3 +290,65 @@ def test_full_size_properties_n1024():
     assert flt.numLandmarks() == 1024
     assert traces[1] < traces[0] and traces[2] < traces[1] * 1.01
     flt.close()
+
+
+def test_feature_predictions_match_oracle():
+    """getFeaturePredictions / predictState (VIO_eqf.cpp:139-151) with useFeaturePredictions on."""
+    import eqvio_b200 as eb
+    from oracle import eqf
+    from parity_utils import snapshot_oracle
+
+    stream = make_stream(N=24, frames=4, coord=0, settings_overrides=dict(useFeaturePredictions=True))
+    o = eqf.VIOFilter(stream["settings"], stream["init"], 0.0)
+    g, cam = gpu_filter(stream)
+    for k, fr in enumerate(stream["frames"]):
+        for row in fr.imu:
+            o.processIMUData(eqf.IMUVelocity(row[0], row[1:4], row[4:7], row[7:10], row[10:13]))
+        g.processIMUArray(fr.imu)
+        if k > 0:
+            # the tracker asks for predictions at the new image stamp before the update (main_opt.cpp:205-206)
+            po = o.getFeaturePredictions(stream["cam"], fr.stamp)
+            pg = g.getFeaturePredictions(cam, fr.stamp)
+            assert sorted(po.camCoordinates) == sorted(pg.camCoordinates) and len(pg.camCoordinates) > 0
+            for i, px in po.camCoordinates.items():
+                assert np.abs(pg.camCoordinates[i] - px).max() < 1e-9 * max(1.0, np.abs(px).max())
+        o.augmentLandmarkStates(list(fr.ids), eqf.VIOState(None, fr.provided_p, fr.ids))
+        g.augmentLandmarkStates(fr.ids, eb.VIOState(eb.VIOSensorState(), fr.provided_p, fr.ids))
+        o.processVisionData(eqf.VisionMeasurement.fromArrays(fr.stamp, fr.ids, fr.y, stream["cam"]))
+        g.processVisionArrays(fr.stamp, fr.ids, fr.y, cam)
+        e = compare_states(snapshot_gpu(g), snapshot_oracle(o))
+        assert e["ids_equal"] and e["sigma"] < TOL and e["state"] < TOL
+    # switched off: an empty measurement, like the reference
+    g2, cam2 = gpu_filter(make_stream(N=8, frames=2, coord=0))
+    assert g2.getFeaturePredictions(cam2, 0.1).camCoordinates == {}
+    g.close()
+    g2.close()
+
+
+@pytest.mark.parametrize("coord", [0, 1])
+def test_nees_matches_oracle(coord):
+    """computeNEES (VIO_eqf.cpp:153-170): device Cholesky solve vs the oracle's dense inverse, along a sequence."""
+    import eqvio_b200 as eb
+    from oracle import eqf
+    from oracle.simulator import SimulationDataServer, benchmarkSim
+
+    stream = make_stream(N=20, frames=6, coord=coord)
+    server = SimulationDataServer(benchmarkSim(20, 0), stream["settings"])
+    o = eqf.VIOFilter(stream["settings"], stream["init"], 0.0)
+    g, cam = gpu_filter(stream)
+    for fr in stream["frames"]:
+        for row in fr.imu:
+            o.processIMUData(eqf.IMUVelocity(row[0], row[1:4], row[4:7], row[7:10], row[10:13]))
+        g.processIMUArray(fr.imu)
+        o.augmentLandmarkStates(list(fr.ids), eqf.VIOState(None, fr.provided_p, fr.ids))
+        g.augmentLandmarkStates(fr.ids, eb.VIOState(eb.VIOSensorState(), fr.provided_p, fr.ids))
+        o.processVisionData(eqf.VisionMeasurement.fromArrays(fr.stamp, fr.ids, fr.y, stream["cam"]))
+        g.processVisionArrays(fr.stamp, fr.ids, fr.y, cam)
+        true = server.getTrueState(o.getTime())
+        # perturb the truth a little so that the error vector is not ~0
+        true.sensor.inputBias = true.sensor.inputBias + 0.01
+        true.p = true.p * 1.01
+        no = o.viewEqFState().computeNEES(true)
+        ng = g.computeNEES(eb.VIOState(eb.VIOSensorState.fromFlat(true.sensor.flat()), true.p, true.ids))
+        assert np.isfinite(ng) and abs(ng - no) <= 1e-8 * max(1.0, abs(no)), (ng, no)
+    g.close()
