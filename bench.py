@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--coord", type=int, default=0)
     ap.add_argument("--sequences-per-gpu", type=int, default=1, help="independent sequences (replicas) run concurrently per GPU")
     ap.add_argument("--no-graph", action="store_true", help="issue per-kernel launches instead of replaying CUDA graphs")
+    ap.add_argument("--pipeline", action="store_true", help="experimental: overlap chunk c+1's factor kernel with chunk c's downdate")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="updates in the cpu_baseline sample (0 = auto)")
@@ -230,6 +231,8 @@ def run_b200(args, rank, local_rank, world):
         flt.enableStageTiming(True)
         if args.no_graph:
             flt.setTuning(graph=0)
+        if args.pipeline:
+            flt.setTuning(pipeline=1)
         filters.append(flt)
     cam = eb.Camera(**streams[0].camera)
     flush_buf = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")

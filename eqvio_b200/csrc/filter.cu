@@ -101,6 +101,9 @@ struct eqvio_filter {
     double *d_Gamma2 = nullptr, *d_ytilde = nullptr;
     int corrMode = 0;    // 0: sequential chunks (default), 1: batch Cholesky sweep over Z
     int speculate = 1;   // launch the correction before the gate results reach the host (redone on a gate hit)
+    int pipeline = 0;    // experimental: overlap chunk c+1's factor kernel with chunk c's (out-of-place) downdate
+    double* d_Y2 = nullptr;
+    std::vector<cudaEvent_t> chunkEv;
     int* d_spec = nullptr;  // [0] set by the gate kernel when any measured landmark exceeds a threshold, [1] constant 0
     cudaEvent_t augEv[2] = {nullptr, nullptr};
     bool augTimed = false;
@@ -374,6 +377,7 @@ int alloc_device(eqvio_filter* f) {
     const size_t ldzMax = (mMax + dimpMax + 1 + 7) & ~size_t(7);
     f->zElems = std::max(std::max(ldzMax * mMax, sigElems), (size_t)(f->ld / YB_T) * YB_TILE);
     CUDA_TRY(f, cudaMalloc(&f->d_Z, f->zElems * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&f->d_Y2, (size_t)(f->ld / YB_T) * YB_TILE * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Lout, ((size_t)dimpMax + mMax + NB) * NB * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Cblk, c1 * 6 * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Gamma, (size_t)(dimpMax + 8) * sizeof(double)));
@@ -962,18 +966,57 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
         double* gout = f->d_Gamma2;
         CUDA_TRY(f, cudaMemsetAsync(gin, 0, (size_t)dimp * sizeof(double), f->stream));
         const int bcMax = std::max(1, std::min(f->chunkLm, CH_R / 2));
-        for (int j0 = 0; j0 < nm; j0 += bcMax) {
-            const int bc = std::min(bcMax, nm - j0);
-            int pk = prof_begin(f, PROF_PANEL);
-            chunk_factor_kernel<<<ldy / CH_COLS, CH_THREADS, 0, f->stream>>>(
-                f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Y, f->d_status, guard);
-            prof_end(f, pk);
-            LAUNCH_CHECK(f, "chunk_factor_kernel");
-            int sk = prof_begin(f, PROF_SYRK);
-            chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->ld, Y, guard);
-            prof_end(f, sk);
-            LAUNCH_CHECK(f, "chunk_downdate_kernel");
-            std::swap(gin, gout);
+        const int nchunks = cdiv(nm, bcMax);
+        const bool pipe = f->pipeline && nchunks > 1 && !f->profiling;
+        if (!pipe) {
+            for (int j0 = 0; j0 < nm; j0 += bcMax) {
+                const int bc = std::min(bcMax, nm - j0);
+                int pk = prof_begin(f, PROF_PANEL);
+                chunk_factor_kernel<<<ldy / CH_COLS, CH_THREADS, sizeof(ChunkSmem), f->stream>>>(
+                    f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Y, f->d_status, guard, nullptr);
+                prof_end(f, pk);
+                LAUNCH_CHECK(f, "chunk_factor_kernel");
+                int sk = prof_begin(f, PROF_SYRK);
+                chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Y, guard);
+                prof_end(f, sk);
+                LAUNCH_CHECK(f, "chunk_downdate_kernel");
+                std::swap(gin, gout);
+            }
+        } else {
+            // Pipelined: factor(c+1) runs on f->stream while downdate(c) runs on f->stream2.  downdate(c) reads the
+            // covariance buffer of chunk c and writes the other one; factor(c+1) reads the same (stable) input buffer
+            // and folds the pending downdate in from Y_c.  Dependencies:
+            //   downdate(c)  after factor(c) [event] and downdate(c-1) [stream order]
+            //   factor(c+1)  after factor(c) [stream order] and downdate(c-1) [event]
+            while ((int)f->chunkEv.size() < 2 * nchunks) {
+                cudaEvent_t e;
+                CUDA_TRY(f, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                f->chunkEv.push_back(e);
+            }
+            double* Ybuf[2] = {f->d_Z, f->d_Y2};
+            int sin = f->cur;
+            for (int c = 0; c < nchunks; ++c) {
+                const int j0 = c * bcMax;
+                const int bc = std::min(bcMax, nm - j0);
+                cudaEvent_t evF = f->chunkEv[2 * c], evD = f->chunkEv[2 * c + 1];
+                if (c >= 2) CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * (c - 2) + 1], 0));  // downdate(c-2) done
+                // factor(c) reads the INPUT buffer of downdate(c-1) (stable while that downdate runs) and folds Y_{c-1} in
+                const int cfIn = c == 0 ? sin : 1 - sin;
+                chunk_factor_kernel<<<ldy / CH_COLS, CH_THREADS, sizeof(ChunkSmem), f->stream>>>(
+                    f->Sig[cfIn], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Ybuf[c & 1], f->d_status, guard,
+                    c > 0 ? Ybuf[(c - 1) & 1] : nullptr);
+                LAUNCH_CHECK(f, "chunk_factor_kernel");
+                CUDA_TRY(f, cudaEventRecord(evF, f->stream));
+                CUDA_TRY(f, cudaStreamWaitEvent(f->stream2, evF, 0));
+                chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream2>>>(f->Sig[sin], f->Sig[1 - sin], f->ld, Ybuf[c & 1],
+                                                                                           guard);
+                LAUNCH_CHECK(f, "chunk_downdate_kernel");
+                CUDA_TRY(f, cudaEventRecord(evD, f->stream2));
+                std::swap(gin, gout);
+                sin = 1 - sin;  // downdate(c+1) reads what downdate(c) wrote
+            }
+            CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * (nchunks - 1) + 1], 0));  // join the last downdate
+            f->cur = sin;  // the final covariance lives in the last downdate's output buffer
         }
         gammaFinal = gin;
     } else {
@@ -1114,6 +1157,7 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
         return EQVIO_ERR_CUDA;
     }
     e = cudaFuncSetAttribute(chunk_downdate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChunkSmem));
     if (e != cudaSuccess) {
         g_createError = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
         return EQVIO_ERR_CUDA;
@@ -1338,6 +1382,8 @@ void eqvio_destroy(eqvio_filter* f) {
     cudaFree(f->d_uv);
     cudaFree(f->d_Z);
     cudaFree(f->d_Lout);
+    cudaFree(f->d_Y2);
+    for (auto& e : f->chunkEv) cudaEventDestroy(e);
     cudaFree(f->d_Cblk);
     cudaFree(f->d_Gamma);
     cudaFree(f->d_Gamma2);
@@ -1811,6 +1857,9 @@ int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
         case EQVIO_TUNE_CORRECTION:
             if (value != 0 && value != 1) return EQVIO_ERR_INVALID_ARG;
             f->corrMode = value;
+            return EQVIO_OK;
+        case EQVIO_TUNE_PIPELINE:
+            f->pipeline = value != 0;
             return EQVIO_OK;
         case EQVIO_TUNE_GRAPH:
             f->useGraph = value != 0;

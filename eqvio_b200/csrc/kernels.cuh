@@ -900,6 +900,10 @@ struct ChunkSmem {
     double Dc[CH_NT][CH_T];                   // reciprocal pivots of block column J
     double C[CH_R / 2][6];
     double Inv[CH_R];
+    // pending downdate of the previous chunk (pipelined mode): u-vectors of the augmented rows,
+    // Us[k][p] = C_c Yprev[k, L_c] for the S rows, Ur[k][sl] = Yprev[k, sbase + sl] for the right-hand-side rows
+    double Us[CH_R][CH_R + 4];
+    double Ur[CH_R][CH_RHS_ROWS * CH_T + 4];
     int Idx[CH_R / 2];
     volatile int ready;                       // block columns of S_c whose panels are published
 };
@@ -943,9 +947,10 @@ __global__ void __launch_bounds__(CH_THREADS)
     chunk_factor_kernel(const double* __restrict__ Sig, int ld, int dimp, const int* __restrict__ lmOf,
                         const double* __restrict__ Cblk, const double* __restrict__ ytilde, int j0, int bc, double r2,
                         const double* __restrict__ GammaIn, double* __restrict__ GammaOut, double* __restrict__ Y,
-                        int* __restrict__ status, const int* __restrict__ guard) {
+                        int* __restrict__ status, const int* __restrict__ guard, const double* __restrict__ Yprev) {
     if (*guard) return;
-    __shared__ ChunkSmem sm;
+    extern __shared__ __align__(16) unsigned char chunk_smem_raw[];
+    ChunkSmem& sm = *reinterpret_cast<ChunkSmem*>(chunk_smem_raw);
     const int tid = threadIdx.x;
     const int rc = 2 * bc;
     CH_STAMP(0);
@@ -954,6 +959,28 @@ __global__ void __launch_bounds__(CH_THREADS)
     if (tid == 0) sm.ready = 0;
     __syncthreads();
     CH_STAMP(1);
+    // Pipelined mode: Sig is the covariance BEFORE the previous chunk's downdate (that downdate is running
+    // concurrently, out of place).  Its effect on this chunk's augmented matrix, M -= U^T U_S with u_rho = the
+    // column of Yprev belonging to augmented row rho, is applied here from Yprev itself.
+    if (Yprev) {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int k = warp; k < CH_R; k += CH_THREADS / 32) {
+            // S rows: landmark `lane` of the chunk, rows 2 lane, 2 lane + 1
+            double u0 = 0.0, u1 = 0.0;
+            if (lane < bc) {
+                const int g = sm.Idx[lane];
+                const double y0 = Yprev[yb_index(k, g)], y1 = Yprev[yb_index(k, g + 1)], y2 = Yprev[yb_index(k, g + 2)];
+                u0 = sm.C[lane][0] * y0 + sm.C[lane][1] * y1 + sm.C[lane][2] * y2;
+                u1 = sm.C[lane][3] * y0 + sm.C[lane][4] * y1 + sm.C[lane][5] * y2;
+            }
+            sm.Us[k][2 * lane] = u0;
+            sm.Us[k][2 * lane + 1] = u1;
+            // right-hand-side rows: this CTA's 32 state columns; the residual row and the padding get no correction
+            sm.Ur[k][lane] = Yprev[yb_index(k, blockIdx.x * CH_COLS + lane)];
+            if (lane < CH_RHS_ROWS * CH_T - CH_COLS) sm.Ur[k][CH_COLS + lane] = 0.0;
+        }
+        __syncthreads();
+    }
 
     const bool sGroup = tid < CH_S_THREADS;
     const int sbase = blockIdx.x * CH_COLS;
@@ -1014,6 +1041,20 @@ __global__ void __launch_bounds__(CH_THREADS)
                     else
                         a[c][c] = 1.0;  // identity padding of a short last chunk
                 }
+            }
+        }
+        if (Yprev && owner) {
+#pragma unroll 4
+            for (int k = 0; k < CH_R; ++k) {
+                const double2 ra = *reinterpret_cast<const double2*>(&sm.Us[k][CH_T * TI]);
+                const double2 rb = *reinterpret_cast<const double2*>(&sm.Us[k][CH_T * TI + 2]);
+                const double2 ca = *reinterpret_cast<const double2*>(&sm.Us[k][CH_T * TK]);
+                const double2 cb = *reinterpret_cast<const double2*>(&sm.Us[k][CH_T * TK + 2]);
+                const double rv[CH_T] = {ra.x, ra.y, rb.x, rb.y}, cv[CH_T] = {ca.x, ca.y, cb.x, cb.y};
+#pragma unroll
+                for (int r = 0; r < CH_T; ++r)
+#pragma unroll
+                    for (int c = 0; c < CH_T; ++c) a[r][c] -= rv[r] * cv[c];
             }
         }
         CH_STAMP(2);
@@ -1157,6 +1198,20 @@ __global__ void __launch_bounds__(CH_THREADS)
                 }
             }
         }
+        if (Yprev && isRhs) {
+#pragma unroll 4
+            for (int k = 0; k < CH_R; ++k) {
+                const double2 ra = *reinterpret_cast<const double2*>(&sm.Ur[k][CH_T * trow]);
+                const double2 rb = *reinterpret_cast<const double2*>(&sm.Ur[k][CH_T * trow + 2]);
+                const double2 ca = *reinterpret_cast<const double2*>(&sm.Us[k][CH_T * TK]);
+                const double2 cb = *reinterpret_cast<const double2*>(&sm.Us[k][CH_T * TK + 2]);
+                const double rv[CH_T] = {ra.x, ra.y, rb.x, rb.y}, cv[CH_T] = {ca.x, ca.y, cb.x, cb.y};
+#pragma unroll
+                for (int r = 0; r < CH_T; ++r)
+#pragma unroll
+                    for (int c = 0; c < CH_T; ++c) a[r][c] -= rv[r] * cv[c];
+            }
+        }
         CH_STAMP(108);
         for (int J = 0; J < nJ; ++J) {
             while (sm.ready <= J) __nanosleep(64);
@@ -1241,7 +1296,8 @@ __global__ void __launch_bounds__(CH_THREADS)
 // 34 KB, mbarrier-signalled) straight into their padded shared-memory layout; the Sigma tile is read and
 // written with 16-byte coalesced loads/stores (one 512-byte column per warp instruction), the mirror
 // tile goes through a shared-memory transpose.  Math: mma.sync.m8n8k4.f64 (DMMA), 4 warps x 32x32.
-// Sigma must be allocated with ld and row count padded to a multiple of 64 (whole tiles are moved).
+// Sigma must be allocated with ld and row count padded to a multiple of 64 (whole tiles are moved).  SigOut may be
+// SigIn (in place) or the other covariance buffer (pipelined mode: the next chunk's factor kernel still reads SigIn).
 // ------------------------------------------------------------------------------------------------
 constexpr int DD_T = 64, DD_LD = YB_LD, DD_THREADS = 128;
 constexpr int DD_SMEM = 2 * DD_T * DD_LD * 8 + 16;
@@ -1273,7 +1329,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 __global__ void __launch_bounds__(DD_THREADS, 3)
-    chunk_downdate_kernel(double* __restrict__ Sig, int ld, const double* __restrict__ Y, const int* __restrict__ guard) {
+    chunk_downdate_kernel(const double* SigIn, double* SigOut, int ld, const double* __restrict__ Y,
+                          const int* __restrict__ guard) {
     if (*guard) return;
     int ti, tj;
     tri_decode(blockIdx.x, ti, tj);  // lower-triangular tile index -> (ti, tj), ti >= tj
@@ -1297,13 +1354,14 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
     const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
     const int fr = wm + (lane >> 2), fc = wn + (lane & 3) * 2;
     double acc[4][4][2];
-    double* cbase = Sig + (size_t)(j0 + fc) * ld + i0 + fr;
+    const double* cin = SigIn + (size_t)(j0 + fc) * ld + i0 + fr;
+    double* cbase = SigOut + (size_t)(j0 + fc) * ld + i0 + fr;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            acc[a][b][0] = -cbase[(size_t)(b * 8) * ld + a * 8];
-            acc[a][b][1] = -cbase[(size_t)(b * 8 + 1) * ld + a * 8];
+            acc[a][b][0] = -cin[(size_t)(b * 8) * ld + a * 8];
+            acc[a][b][1] = -cin[(size_t)(b * 8 + 1) * ld + a * 8];
         }
     __syncthreads();  // barrier initialised for everyone
     mbar_wait(bar, 0);
@@ -1332,7 +1390,7 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
                 double2 t;
                 t.x = v0;
                 t.y = v1;
-                *reinterpret_cast<double2*>(Sig + (size_t)(i0 + fr + a * 8) * ld + j0 + fc + b * 8) = t;
+                *reinterpret_cast<double2*>(SigOut + (size_t)(i0 + fr + a * 8) * ld + j0 + fc + b * 8) = t;
             }
         }
 }

@@ -344,12 +344,14 @@ class VIOFilter:
         self._check(lib.eqvio_get_stage_ms(self._h, _pd(ms)))
         return dict(propagation=ms[0], preprocessing=ms[1], correction=ms[2])
 
-    def setTuning(self, correction=None, chunkLandmarks=None, speculate=None, graph=None):
+    def setTuning(self, correction=None, chunkLandmarks=None, speculate=None, graph=None, pipeline=None):
         """Evaluation-order knobs (eqvio_set_tuning): correction 0 = sequential chunks, 1 = batch sweep."""
         if speculate is not None:
             self._check(lib.eqvio_set_tuning(self._h, 2, int(speculate)))
         if graph is not None:
             self._check(lib.eqvio_set_tuning(self._h, 3, int(graph)))
+        if pipeline is not None:
+            self._check(lib.eqvio_set_tuning(self._h, 4, int(pipeline)))
         if correction is not None:
             self._check(lib.eqvio_set_tuning(self._h, 0, int(correction)))
         if chunkLandmarks is not None:

@@ -192,6 +192,12 @@ int eqvio_get_kernel_profile(eqvio_filter* f, int reset, double ms[EQVIO_PROF_CL
 /*   EQVIO_TUNE_GRAPH: 1 (default) = replay the launch sequence of a steady frame (no landmark enters or leaves)
  *                      as a cached CUDA graph; 0 = issue the launches one by one. */
 #define EQVIO_TUNE_GRAPH 3
+/*   EQVIO_TUNE_PIPELINE: 1 = chunk c+1 is factored while chunk c's downdate is still running (the downdate goes out of
+ *                         place into the other covariance buffer, the factor kernel folds the pending downdate in
+ *                         from Y_c); 0 (default) = strictly one kernel after the other, in place.  Measured slower
+ *                         than the default on B200 at N = 256 / 1024 (the folded-in update costs more than the
+ *                         overlap returns); kept as a tested evaluation order. */
+#define EQVIO_TUNE_PIPELINE 4
 int eqvio_set_tuning(eqvio_filter* f, int key, int value);
 /* Version / build info string (arch the kernels were compiled for). */
 const char* eqvio_build_info(void);

@@ -36,7 +36,8 @@ def test_sequence_matches_oracle(N, coord):
 
 
 @pytest.mark.parametrize("tuning", [dict(correction=1), dict(correction=0, chunkLandmarks=5), dict(correction=0, chunkLandmarks=16),
-                                    dict(correction=0, chunkLandmarks=1)])
+                                    dict(correction=0, chunkLandmarks=1), dict(correction=0, chunkLandmarks=7, pipeline=1),
+                                    dict(correction=0, chunkLandmarks=16, pipeline=1)])
 def test_correction_evaluation_orders_agree(tuning):
     """Batch Cholesky sweep vs sequential chunks of any size: same result to rounding, both match the oracle."""
     stream = make_stream(N=40, frames=6, coord=1)
