@@ -237,17 +237,27 @@ def run_b200(args, rank, local_rank, world):
     cam = eb.Camera(**streams[0].camera)
     flush_buf = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
+    pool = None
+    if len(filters) > 1:
+        # one host thread per sequence: every C-ABI call releases the GIL, the filters own independent streams, so
+        # the host-side work of the replicas overlaps across cores and their kernels overlap on the GPU
+        from concurrent.futures import ThreadPoolExecutor
+
+        pool = ThreadPoolExecutor(max_workers=min(len(filters), max(1, (os.cpu_count() or 2) - 1)))
+        torch.cuda.set_device(local_rank)
+
+    def step_one(i, k):
+        flt, fr = filters[i], streams[i].frames[k]
+        flt.processIMUArray(fr.imu)
+        flt.augmentLandmarkStates(fr.ids, eb.VIOState(eb.VIOSensorState(), fr.provided_p, fr.ids))
+        flt.processVisionArrays(fr.stamp, fr.ids, fr.y, cam)
+        return flt.stateEstimate()
+
     def step(k):
         """One vision update of every local sequence; returns the state estimates."""
-        frs = [sm.frames[k] for sm in streams]
-        for flt, fr in zip(filters, frs):
-            flt.processIMUArray(fr.imu)
-            flt.augmentLandmarkStates(fr.ids, eb.VIOState(eb.VIOSensorState(), fr.provided_p, fr.ids))
-        if len(filters) == 1:
-            filters[0].processVisionArrays(frs[0].stamp, frs[0].ids, frs[0].y, cam)
-        else:
-            eb.batchProcessVision(filters, [fr.stamp for fr in frs], [fr.ids for fr in frs], [fr.y for fr in frs], cam)
-        return [flt.stateEstimate() for flt in filters]
+        if pool is None:
+            return [step_one(0, k)]
+        return list(pool.map(lambda i: step_one(i, k), range(len(filters))))
 
     def h2d_bytes(fr):
         return fr.imu.nbytes + fr.y.nbytes + 2 * 4 * len(fr.ids) + 8 * 13  # IMU rows, pixels, index maps, frame header scalars
@@ -288,8 +298,9 @@ def run_b200(args, rank, local_rank, world):
             for key in stage_acc:
                 stage_acc[key] += sm_[key] / len(filters)
             per_filter.append(sm_["propagation"] + sm_["preprocessing"] + sm_["correction"])
-        # sequences on one GPU run concurrently on their own streams: the step's device time is the slowest of them
-        dev_ms += max(per_filter)
+        # several sequences per GPU run concurrently on their own streams: their device times overlap, so the step is
+        # charged its host-side bracket (all sequences done) instead of a sum of per-filter device times
+        dev_ms += max(per_filter) if len(filters) == 1 else 1000.0 * (time.perf_counter() - t0)
         for inst, est, sm in zip(mine, ests, streams):
             traj[inst][kk] = trajectory_row(sm.frames[k].stamp, est)
             h2d += h2d_bytes(sm.frames[k])

@@ -590,7 +590,7 @@ int enqueue_propagation(eqvio_filter* f) {
         if (N > 0) {
             landmark_rows_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_ctx, s.coordinateChoice, f->d_rows);
             LAUNCH_CHECK(f, "landmark_rows_kernel");
-            prop_strip_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv);
+            prop_strip_kernel<<<cdiv(N, PS_LM), PS_LM * PS_TPL, 0, f->stream>>>(Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv);
             LAUNCH_CHECK(f, "prop_strip_kernel");
             const int nt = cdiv(N, TP);
             int pk = prof_begin(f, PROF_PROP_LL);

@@ -382,68 +382,91 @@ __global__ void observer_landmark_kernel(const double* __restrict__ lmIn, double
 // is written to both triangles of Sout.  uv[i] = U(81) | V(81) row-major 3x27.
 // ------------------------------------------------------------------------------------------------
 constexpr int UV_STRIDE = 162;
+constexpr int PS_LM = 8, PS_TPL = 24;  // landmarks per CTA, threads per landmark (21 sensor rows + 3 pad rows)
 
-__global__ void prop_strip_kernel(const double* __restrict__ Sin, double* __restrict__ Sout, int ld, int N,
-                                  const RiccatiCtx* __restrict__ ctx, const double* __restrict__ rows,
-                                  double* __restrict__ uv) {
-    __shared__ double sF[21 * 21], sS[21 * 21], sBG[63];
-    for (int t = threadIdx.x; t < 441; t += blockDim.x) {
-        int r = t / 21, c = t % 21;
-        sF[t] = ctx->Fs[t];
-        sS[t] = Sin[(size_t)c * ld + r];
-    }
-    for (int t = threadIdx.x; t < 63; t += blockDim.x) sBG[t] = ctx->BsG[t];
-    __syncthreads();
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const double cg = ctx->cg;
-    const double* ro = rows + (size_t)i * ROWS_STRIDE;
-    double D[9], G[36], Bl[9];
-    for (int k = 0; k < 9; ++k) D[k] = ro[k];
-    for (int k = 0; k < 36; ++k) G[k] = ro[9 + k];
-    for (int k = 0; k < 9; ++k) Bl[k] = ro[45 + k];
-    double L[63];  // L[a*21 + c] = Sigma[SOFF+3i+a, c]
+__global__ void __launch_bounds__(PS_LM* PS_TPL)
+    prop_strip_kernel(const double* __restrict__ Sin, double* __restrict__ Sout, int ld, int N,
+                      const RiccatiCtx* __restrict__ ctx, const double* __restrict__ rows, double* __restrict__ uv) {
+    __shared__ double sF[441], sS[441], sBG[63];
+    __shared__ double sRow[PS_LM][ROWS_STRIDE];  // D(9) | G(36) | Bl(9)
+    __shared__ double sL[PS_LM][63];              // sL[a*21 + c] = Sigma[row a of the landmark, sensor column c]
+    __shared__ double sX[PS_LM][63];              // X_i[r*3 + b]
+    const int tid = threadIdx.x;
+    const int li = tid / PS_TPL, t = tid % PS_TPL;
+    const int i = blockIdx.x * PS_LM + li;
+    const bool live = i < N;
     const int r0 = SOFF + 3 * i;
-    for (int c = 0; c < 21; ++c)
-        for (int a = 0; a < 3; ++a) L[a * 21 + c] = Sin[(size_t)c * ld + r0 + a];
-    double* U = uv + (size_t)i * UV_STRIDE;
-    double* V = U + 81;
-    for (int a = 0; a < 3; ++a)
-        for (int c = 0; c < 12; ++c) {
-            int sc = c_sidx[c];
-            double e = D[3 * a] * L[sc] + D[3 * a + 1] * L[21 + sc] + D[3 * a + 2] * L[42 + sc];
-            double h = e;
-            for (int k = 0; k < 12; ++k) h += G[12 * a + k] * sS[c_sidx[k] * 21 + sc];
-            U[27 * a + c] = G[12 * a + c];
-            U[27 * a + 12 + c] = h;
-            V[27 * a + c] = e;
-            V[27 * a + 12 + c] = G[12 * a + c];
+    for (int k = tid; k < 441; k += PS_LM * PS_TPL) {
+        const int r = k / 21, c = k % 21;
+        sF[k] = ctx->Fs[k];
+        sS[k] = Sin[(size_t)c * ld + r];
+    }
+    for (int k = tid; k < 63; k += PS_LM * PS_TPL) sBG[k] = ctx->BsG[k];
+    if (live) {
+        for (int k = t; k < ROWS_STRIDE; k += PS_TPL) sRow[li][k] = rows[(size_t)i * ROWS_STRIDE + k];
+        if (t < 21) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) sL[li][a * 21 + t] = Sin[(size_t)t * ld + r0 + a];
         }
-    for (int a = 0; a < 3; ++a)
-        for (int c = 0; c < 3; ++c) {
-            U[27 * a + 24 + c] = cg * Bl[3 * a + c];
-            V[27 * a + 24 + c] = Bl[3 * a + c];
+    }
+    __syncthreads();
+    const double* D = sRow[li];
+    const double* G = sRow[li] + 9;
+    const double* Bl = sRow[li] + 45;
+    const double* L = sL[li];
+    if (live) {
+        double* U = uv + (size_t)i * UV_STRIDE;
+        double* V = U + 81;
+        if (t < 12) {  // column t of E_i, H_i
+            const int sc = c_sidx[t];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double e = D[3 * a] * L[sc] + D[3 * a + 1] * L[21 + sc] + D[3 * a + 2] * L[42 + sc];
+                double h = e;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) h += G[12 * a + k] * sS[c_sidx[k] * 21 + sc];
+                U[27 * a + t] = G[12 * a + t];
+                U[27 * a + 12 + t] = h;
+                V[27 * a + t] = e;
+                V[27 * a + 12 + t] = G[12 * a + t];
+            }
+        } else if (t < 15) {
+            const int c = t - 12;
+            const double cg = ctx->cg;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                U[27 * a + 24 + c] = cg * Bl[3 * a + c];
+                V[27 * a + 24 + c] = Bl[3 * a + c];
+            }
         }
-    // sensor-landmark block
-    double tmp[63];  // tmp[r*3 + b]
-    for (int r = 0; r < 21; ++r)
+        if (t < 21) {  // row t of X_i = Sigma_ss[:, sidx] G_i^T + Sigma_{s,i} D_i^T
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                double x = L[t] * D[3 * b] + L[21 + t] * D[3 * b + 1] + L[42 + t] * D[3 * b + 2];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) x += sS[t * 21 + c_sidx[k]] * G[12 * b + k];
+                sX[li][t * 3 + b] = x;
+            }
+        }
+    }
+    __syncthreads();
+    if (!live) return;
+    if (t < 21) {  // row t of Sigma'_{s,i} = F_s X_i + BsG Bl_i^T, written to both triangles
+#pragma unroll
         for (int b = 0; b < 3; ++b) {
-            double s = L[r] * D[3 * b] + L[21 + r] * D[3 * b + 1] + L[42 + r] * D[3 * b + 2];
-            for (int k = 0; k < 12; ++k) s += sS[r * 21 + c_sidx[k]] * G[12 * b + k];
-            tmp[r * 3 + b] = s;
+            double v = sBG[t * 3] * Bl[3 * b] + sBG[t * 3 + 1] * Bl[3 * b + 1] + sBG[t * 3 + 2] * Bl[3 * b + 2];
+#pragma unroll
+            for (int k = 0; k < 21; ++k) v += sF[t * 21 + k] * sX[li][k * 3 + b];
+            Sout[(size_t)(r0 + b) * ld + t] = v;
+            Sout[(size_t)t * ld + r0 + b] = v;
         }
-    for (int r = 0; r < 21; ++r)
+    } else {  // pad rows / columns 21..23 stay zero
+#pragma unroll
         for (int b = 0; b < 3; ++b) {
-            double s = sBG[r * 3] * Bl[3 * b] + sBG[r * 3 + 1] * Bl[3 * b + 1] + sBG[r * 3 + 2] * Bl[3 * b + 2];
-            for (int k = 0; k < 21; ++k) s += sF[r * 21 + k] * tmp[k * 3 + b];
-            Sout[(size_t)(r0 + b) * ld + r] = s;
-            Sout[(size_t)r * ld + r0 + b] = s;
+            Sout[(size_t)(r0 + b) * ld + t] = 0.0;
+            Sout[(size_t)t * ld + r0 + b] = 0.0;
         }
-    for (int p = SENSOR_DIM; p < SOFF; ++p)
-        for (int b = 0; b < 3; ++b) {
-            Sout[(size_t)(r0 + b) * ld + p] = 0.0;
-            Sout[(size_t)p * ld + r0 + b] = 0.0;
-        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
