@@ -1,0 +1,275 @@
+// integrateRiccatiStateAccurate (src/mathematical/VIO_eqf.cpp:74-91) -- the reference's DEFAULT propagation
+// (fastRiccati = false, useDiscreteStateMatrix = false), executed once per buffered IMU sample:
+//
+//     [A0tExp BtExp; 0 I] = exp( dt [A0t Bt; 0 0] ),
+//     Sigma <- A0tExp Sigma A0tExp^T + BtExp (Q / dt) BtExp^T + dt P.
+//
+// This variant is a dense path on purpose: the matrix exponential is taken with a Pade-13 scaling-and-squaring
+// scheme (Higham 2005, the algorithm behind Eigen's unsupported MatrixFunctions `.exp()`), whose products and LU
+// solve are plain library calls (cuBLAS DGEMM / cuSOLVER getrf+getrs, resolved with dlopen at first use so that the
+// library has no link-time dependency on them).  The hand-written kernels here only assemble dt [A B; 0 0] from
+// the same per-landmark blocks the fast path uses, combine matrices, and move Sigma between its padded device
+// layout and the dense one.  A structured version (one 36x36 exponential per landmark) is the natural next step.
+#pragma once
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include "kernels.cuh"
+
+namespace eqvio {
+namespace dense {
+
+// ---- minimal cuBLAS / cuSOLVER surface, resolved at run time ---------------------------------------------------
+typedef void* blasHandle;
+typedef void* solverHandle;
+struct Libs {
+    void *hBlas = nullptr, *hSolver = nullptr;
+    int (*blasCreate)(blasHandle*) = nullptr;
+    int (*blasDestroy)(blasHandle) = nullptr;
+    int (*blasSetStream)(blasHandle, cudaStream_t) = nullptr;
+    int (*dgemm)(blasHandle, int, int, int, int, int, const double*, const double*, int, const double*, int, const double*, double*,
+                 int) = nullptr;
+    int (*solverCreate)(solverHandle*) = nullptr;
+    int (*solverDestroy)(solverHandle) = nullptr;
+    int (*solverSetStream)(solverHandle, cudaStream_t) = nullptr;
+    int (*getrfBuf)(solverHandle, int, int, double*, int, int*) = nullptr;
+    int (*getrf)(solverHandle, int, int, double*, int, double*, int*, int*) = nullptr;
+    int (*getrs)(solverHandle, int, int, int, const double*, int, const int*, double*, int, int*) = nullptr;
+    bool ok = false;
+    const char* why = "";
+};
+inline void* open_any(const char* a, const char* b) {
+    void* h = dlopen(a, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen(b, RTLD_NOW | RTLD_GLOBAL);
+    return h;
+}
+inline Libs& libs() {
+    static Libs L;
+    static bool tried = false;
+    if (tried) return L;
+    tried = true;
+    L.hBlas = open_any("libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12");
+    L.hSolver = open_any("libcusolver.so.11", "/usr/local/cuda/lib64/libcusolver.so.11");
+    if (!L.hBlas || !L.hSolver) {
+        L.why = "libcublas.so.12 / libcusolver.so.11 not found";
+        return L;
+    }
+#define EQ_SYM(field, handle, name)                                  \
+    *(void**)(&L.field) = dlsym(handle, name);                       \
+    if (!L.field) {                                                  \
+        L.why = "missing symbol " name;                              \
+        return L;                                                    \
+    }
+    EQ_SYM(blasCreate, L.hBlas, "cublasCreate_v2")
+    EQ_SYM(blasDestroy, L.hBlas, "cublasDestroy_v2")
+    EQ_SYM(blasSetStream, L.hBlas, "cublasSetStream_v2")
+    EQ_SYM(dgemm, L.hBlas, "cublasDgemm_v2")
+    EQ_SYM(solverCreate, L.hSolver, "cusolverDnCreate")
+    EQ_SYM(solverDestroy, L.hSolver, "cusolverDnDestroy")
+    EQ_SYM(solverSetStream, L.hSolver, "cusolverDnSetStream")
+    EQ_SYM(getrfBuf, L.hSolver, "cusolverDnDgetrf_bufferSize")
+    EQ_SYM(getrf, L.hSolver, "cusolverDnDgetrf")
+    EQ_SYM(getrs, L.hSolver, "cusolverDnDgetrs")
+#undef EQ_SYM
+    L.ok = true;
+    return L;
+}
+constexpr int OP_N = 0, OP_T = 1;  // cublasOperation_t
+
+// ---- kernels -------------------------------------------------------------------------------------------------------
+// M = dt [A B; 0 0] (n x n column-major, n = dim + 12).  Sensor rows come from the Riccati context of the current
+// sample (F_s = I + dt A_s, and dt q_gyr B_s[:, 0:3] is NOT enough for B, so the raw dt B_s is passed in dtBs).
+__global__ void dense_fill_sensor_kernel(double* __restrict__ M, int n, int dim, const RiccatiCtx* __restrict__ ctx,
+                                         const double* __restrict__ dtBs /*21x12 row-major*/) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 441) {
+        const int r = t / 21, c = t % 21;
+        M[(size_t)c * n + r] = ctx->Fs[t] - (r == c ? 1.0 : 0.0);
+    }
+    if (t < 252) {
+        const int r = t / 12, c = t % 12;
+        M[(size_t)(dim + c) * n + r] = dtBs[t];
+    }
+}
+// landmark rows from rows[i] = D(9) | G(36) | Bl(9): D = I + dt A_q, G = dt [-B_l | A_vel | A_cam] on columns c_sidx
+__global__ void dense_fill_landmark_kernel(double* __restrict__ M, int n, int dim, int N, const double* __restrict__ rows, double dt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double* ro = rows + (size_t)i * ROWS_STRIDE;
+    const int r0 = SENSOR_DIM + 3 * i;
+    for (int r = 0; r < 3; ++r) {
+        for (int k = 0; k < 12; ++k) M[(size_t)c_sidx[k] * n + r0 + r] = ro[9 + 12 * r + k];
+        for (int c = 0; c < 3; ++c) M[(size_t)(r0 + c) * n + r0 + r] = ro[3 * r + c] - (r == c ? 1.0 : 0.0);
+        for (int c = 0; c < 3; ++c) M[(size_t)(dim + c) * n + r0 + r] = dt * ro[45 + 3 * r + c];
+    }
+}
+// out = a A + b B + c C + d I  (any of A, B, C may be null)
+__global__ void dense_lincomb_kernel(double* __restrict__ out, int n, double a, const double* __restrict__ A, double b,
+                                     const double* __restrict__ B, double c, const double* __restrict__ C, double d) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * n) return;
+    double v = 0.0;
+    if (A) v += a * A[idx];
+    if (B) v += b * B[idx];
+    if (C) v += c * C[idx];
+    if (d != 0.0 && idx / n == idx % n) v += d;
+    out[idx] = v;
+}
+// 1-norm (max column abs sum) -> out[0]; one block per column then a host-side max over n values would need a second
+// pass: columns are few thousand at most, so one thread per column and an atomic max on the bit pattern suffices.
+__global__ void dense_norm1_kernel(const double* __restrict__ M, int n, unsigned long long* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double s = 0.0;
+    for (int r = 0; r < n; ++r) s += fabs(M[(size_t)c * n + r]);
+    atomicMax(out, (unsigned long long)__double_as_longlong(s));  // non-negative doubles order like their bit patterns
+}
+// Sigma (padded internal layout) <-> dense dim x dim
+__global__ void dense_unpack_sigma_kernel(const double* __restrict__ D, int ldd, int dim, double* __restrict__ S, int ld) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (r >= dim || c >= dim) return;
+    const int ri = r < SENSOR_DIM ? r : r + (SOFF - SENSOR_DIM);
+    const int ci = c < SENSOR_DIM ? c : c + (SOFF - SENSOR_DIM);
+    S[(size_t)ci * ld + ri] = D[(size_t)c * ldd + r];
+}
+// out (dim x dim, ld = dim) += E_B diag(q / dt) E_B^T + dt P ; E_B = R[0:dim, dim:dim+12] with leading dimension n.
+// Symmetrised on the fly: out is also averaged with its transpose? No -- the reference does not symmetrise either.
+__global__ void dense_noise_kernel(double* __restrict__ out, int dim, const double* __restrict__ R, int n, double q0, double q1,
+                                   double q2, double q3, double invdt, double dt, const double* __restrict__ pdiag /*8*/) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (r >= dim || c >= dim) return;
+    const double q[4] = {q0, q1, q2, q3};
+    double s = 0.0;
+    for (int k = 0; k < 12; ++k) s += R[(size_t)(dim + k) * n + r] * (q[k / 3] * invdt) * R[(size_t)(dim + k) * n + c];
+    if (r == c) s += dt * (r < SENSOR_DIM ? pdiag[r / 3] : pdiag[7]);
+    out[(size_t)c * dim + r] += s;
+}
+
+// ---- workspace + expm ------------------------------------------------------------------------------------------------
+struct Workspace {
+    int n = 0;
+    double* buf[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double* lwork = nullptr;
+    int lworkSize = 0;
+    int* ipiv = nullptr;
+    int* info = nullptr;
+    unsigned long long* norm = nullptr;
+    double* dtBs = nullptr;
+    double* pdiag = nullptr;
+    blasHandle blas = nullptr;
+    solverHandle solver = nullptr;
+    void release() {
+        for (auto& b : buf) {
+            cudaFree(b);
+            b = nullptr;
+        }
+        cudaFree(lwork);
+        cudaFree(ipiv);
+        cudaFree(info);
+        cudaFree(norm);
+        cudaFree(dtBs);
+        cudaFree(pdiag);
+        lwork = nullptr;
+        ipiv = nullptr;
+        info = nullptr;
+        norm = nullptr;
+        dtBs = nullptr;
+        pdiag = nullptr;
+        if (blas) libs().blasDestroy(blas);
+        if (solver) libs().solverDestroy(solver);
+        blas = nullptr;
+        solver = nullptr;
+        n = 0;
+    }
+};
+
+inline const char* ensure(Workspace& w, int n, cudaStream_t stream) {
+    Libs& L = libs();
+    if (!L.ok) return L.why;
+    if (!w.blas) {
+        if (L.blasCreate(&w.blas) != 0) return "cublasCreate failed";
+        if (L.solverCreate(&w.solver) != 0) return "cusolverDnCreate failed";
+    }
+    L.blasSetStream(w.blas, stream);
+    L.solverSetStream(w.solver, stream);
+    if (n > w.n) {
+        cudaStreamSynchronize(stream);
+        for (auto& b : w.buf) {
+            cudaFree(b);
+            b = nullptr;
+        }
+        cudaFree(w.lwork);
+        cudaFree(w.ipiv);
+        w.lwork = nullptr;
+        w.ipiv = nullptr;
+        const int cap = n + n / 8 + 16;
+        for (auto& b : w.buf)
+            if (cudaMalloc(&b, (size_t)cap * cap * sizeof(double)) != cudaSuccess) return "dense Riccati workspace allocation failed";
+        if (cudaMalloc(&w.ipiv, cap * sizeof(int)) != cudaSuccess) return "allocation failed";
+        int ls = 0;
+        if (L.getrfBuf(w.solver, cap, cap, w.buf[0], cap, &ls) != 0) return "cusolverDnDgetrf_bufferSize failed";
+        w.lworkSize = ls;
+        if (cudaMalloc(&w.lwork, (size_t)ls * sizeof(double)) != cudaSuccess) return "allocation failed";
+        if (!w.info) {
+            cudaMalloc(&w.info, sizeof(int));
+            cudaMalloc(&w.norm, sizeof(unsigned long long));
+            cudaMalloc(&w.dtBs, 252 * sizeof(double));
+            cudaMalloc(&w.pdiag, 8 * sizeof(double));
+        }
+        w.n = cap;
+    }
+    return nullptr;
+}
+
+inline int gemm(Workspace& w, int ta, int tb, int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb,
+                double beta, double* C, int ldc) {
+    return libs().dgemm(w.blas, ta, tb, m, n, k, &alpha, A, lda, B, ldb, &beta, C, ldc);
+}
+
+// R = exp(M) for the n x n matrix in w.buf[0]; result in w.buf[8].  Pade-13 with scaling and squaring.
+inline const char* expm(Workspace& w, int n, cudaStream_t stream) {
+    static const double b[14] = {64764752532480000.0, 32382376266240000.0, 7771770303897600.0, 1187353796428800.0, 129060195264000.0,
+                                 10559470521600.0,    670442572800.0,      33522128640.0,      1323241920.0,       40840800.0,
+                                 960960.0,            16380.0,             182.0,              1.0};
+    double *M = w.buf[0], *A2 = w.buf[1], *A4 = w.buf[2], *A6 = w.buf[3], *U = w.buf[4], *V = w.buf[5], *T1 = w.buf[6], *T2 = w.buf[7],
+           *R = w.buf[8];
+    const int blocks = (int)(((size_t)n * n + 255) / 256);
+    // scaling: s = max(0, ceil(log2(|M|_1 / theta13)))
+    cudaMemsetAsync(w.norm, 0, sizeof(unsigned long long), stream);
+    dense_norm1_kernel<<<(n + 127) / 128, 128, 0, stream>>>(M, n, w.norm);
+    unsigned long long bits = 0;
+    cudaMemcpyAsync(&bits, w.norm, sizeof(bits), cudaMemcpyDeviceToHost, stream);
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return "norm kernel failed";
+    double norm1;
+    memcpy(&norm1, &bits, sizeof(double));
+    if (!(norm1 == norm1) || norm1 > 1e300) return "non-finite state matrix";
+    int s = 0;
+    const double theta13 = 5.371920351148152;
+    if (norm1 > theta13) s = (int)ceil(log2(norm1 / theta13));
+    if (s > 0) dense_lincomb_kernel<<<blocks, 256, 0, stream>>>(M, n, ldexp(1.0, -s), M, 0, nullptr, 0, nullptr, 0.0);
+    if (gemm(w, OP_N, OP_N, n, n, n, 1.0, M, n, M, n, 0.0, A2, n)) return "dgemm failed";
+    if (gemm(w, OP_N, OP_N, n, n, n, 1.0, A2, n, A2, n, 0.0, A4, n)) return "dgemm failed";
+    if (gemm(w, OP_N, OP_N, n, n, n, 1.0, A4, n, A2, n, 0.0, A6, n)) return "dgemm failed";
+    // U = M (A6 (b13 A6 + b11 A4 + b9 A2) + b7 A6 + b5 A4 + b3 A2 + b1 I)
+    dense_lincomb_kernel<<<blocks, 256, 0, stream>>>(T1, n, b[13], A6, b[11], A4, b[9], A2, 0.0);
+    dense_lincomb_kernel<<<blocks, 256, 0, stream>>>(T2, n, b[7], A6, b[5], A4, b[3], A2, b[1]);
+    if (gemm(w, OP_N, OP_N, n, n, n, 1.0, A6, n, T1, n, 1.0, T2, n)) return "dgemm failed";
+    if (gemm(w, OP_N, OP_N, n, n, n, 1.0, M, n, T2, n, 0.0, U, n)) return "dgemm failed";
+    // V = A6 (b12 A6 + b10 A4 + b8 A2) + b6 A6 + b4 A4 + b2 A2 + b0 I
+    dense_lincomb_kernel<<<blocks, 256, 0, stream>>>(T1, n, b[12], A6, b[10], A4, b[8], A2, 0.0);
+    dense_lincomb_kernel<<<blocks, 256, 0, stream>>>(V, n, b[6], A6, b[4], A4, b[2], A2, b[0]);
+    if (gemm(w, OP_N, OP_N, n, n, n, 1.0, A6, n, T1, n, 1.0, V, n)) return "dgemm failed";
+    // (V - U) R = (V + U)
+    dense_lincomb_kernel<<<blocks, 256, 0, stream>>>(T1, n, 1.0, V, -1.0, U, 0, nullptr, 0.0);
+    dense_lincomb_kernel<<<blocks, 256, 0, stream>>>(R, n, 1.0, V, 1.0, U, 0, nullptr, 0.0);
+    if (libs().getrf(w.solver, n, n, T1, n, w.lwork, w.ipiv, w.info)) return "getrf failed";
+    if (libs().getrs(w.solver, OP_N, n, n, T1, n, w.ipiv, R, n, w.info)) return "getrs failed";
+    for (int k = 0; k < s; ++k) {  // undo the scaling
+        if (gemm(w, OP_N, OP_N, n, n, n, 1.0, R, n, R, n, 0.0, T2, n)) return "dgemm failed";
+        cudaMemcpyAsync(R, T2, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice, stream);
+    }
+    return nullptr;
+}
+
+}  // namespace dense
+}  // namespace eqvio

@@ -18,6 +18,7 @@
 
 #include "../../include/eqvio_b200.h"
 #include "kernels.cuh"
+#include "dense_riccati.cuh"
 
 using namespace eqvio;
 
@@ -76,6 +77,8 @@ struct eqvio_filter {
     unsigned char* h_frame = nullptr;
     size_t frameBytes = 0, offImu = 0, offY = 0, offMeasIdx = 0, offLmOf = 0, offYIdx = 0;
     int* d_yIdx = nullptr;
+    FrameHeader* d_hdrSteps = nullptr;  // one header per IMU sample (per-sample Riccati variants)
+    dense::Workspace dense;
     FrameHeader* d_hdr = nullptr;
     double* d_imu = nullptr;
     int maxSteps = 0;
@@ -320,6 +323,8 @@ int alloc_frame(eqvio_filter* f, int steps, int ycap) {
     f->graphs.clear();
     cudaFree(f->d_frame);
     cudaFree(f->d_steps);
+    cudaFree(f->d_hdrSteps);
+    f->d_hdrSteps = nullptr;
     if (f->h_frame) cudaFreeHost(f->h_frame);
     f->d_frame = nullptr;
     f->h_frame = nullptr;
@@ -338,6 +343,7 @@ int alloc_frame(eqvio_filter* f, int steps, int ycap) {
     CUDA_TRY(f, cudaMallocHost(&f->h_frame, f->frameBytes));
     std::memset(f->h_frame, 0, f->frameBytes);
     CUDA_TRY(f, cudaMalloc(&f->d_steps, (size_t)steps * sizeof(ObsStep)));
+    CUDA_TRY(f, cudaMalloc(&f->d_hdrSteps, (size_t)steps * sizeof(FrameHeader)));
     f->d_hdr = reinterpret_cast<FrameHeader*>(f->d_frame);
     f->d_imu = reinterpret_cast<double*>(f->d_frame + f->offImu);
     f->d_y = reinterpret_cast<double*>(f->d_frame + f->offY);
@@ -508,8 +514,8 @@ int plan_integration(eqvio_filter* f, double newTime, int* advanced) {
     *advanced = 0;
     if (newTime <= f->time || f->time < 0 || f->buf.empty()) return EQVIO_OK;
     const eqvio_settings& s = f->st;
-    if (!s.fastRiccati) {
-        f->err = "fastRiccati=false (integrateRiccatiStateAccurate/Discrete) has no CUDA path in this build";
+    if (!s.fastRiccati && s.useDiscreteStateMatrix) {
+        f->err = "useDiscreteStateMatrix (integrateRiccatiStateDiscrete, numerically differentiated A) has no CUDA path in this build";
         return EQVIO_ERR_UNSUPPORTED;
     }
     const int n = (int)f->buf.size();
@@ -585,7 +591,7 @@ int enqueue_propagation(eqvio_filter* f) {
     {
         const double* Sin = f->Sig[f->cur];
         double* Sout = f->Sig[1 - f->cur];
-        riccati_prep_kernel<<<1, 448, 0, f->stream>>>(a, Sin, Sout, f->ld);
+        riccati_prep_kernel<<<1, 448, 0, f->stream>>>(a, Sin, Sout, f->ld, nullptr);
         LAUNCH_CHECK(f, "riccati_prep_kernel");
         if (N > 0) {
             landmark_rows_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_ctx, s.coordinateChoice, f->d_rows);
@@ -603,6 +609,101 @@ int enqueue_propagation(eqvio_filter* f) {
     CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->evJoin, 0));
     f->xcur = 1 - f->xcur;
     if (N > 0) f->lmcur = 1 - f->lmcur;
+    return EQVIO_OK;
+}
+
+// fastRiccati = false: per buffered IMU sample, integrateRiccatiStateAccurate (dense matrix exponential, see
+// dense_riccati.cuh) followed by that sample's integrateObserverState -- VIOFilter.cpp:160-178.  Synchronises once per
+// sample (the scaling of the exponential is decided from a norm); this is the slow, faithful variant.
+int enqueue_propagation_accurate(eqvio_filter* f) {
+    const eqvio_settings& s = f->st;
+    const int N = (int)f->ids.size();
+    const int dim = SENSOR_DIM + 3 * N, n = dim + 12;
+    const FrameHeader* hh = reinterpret_cast<const FrameHeader*>(f->h_frame);
+    const double* himu = reinterpret_cast<const double*>(f->h_frame + f->offImu);
+    const int nsteps = hh->fs.nsteps;
+    const char* why = dense::ensure(f->dense, n, f->stream);
+    if (why) {
+        f->err = std::string("fastRiccati=false needs cuBLAS / cuSOLVER: ") + why;
+        return EQVIO_ERR_UNSUPPORTED;
+    }
+    int rc;
+    std::vector<FrameHeader> hdrs(nsteps);
+    for (int i = 0; i < nsteps; ++i) {
+        hdrs[i] = *hh;
+        for (int k = 0; k < 12; ++k) hdrs[i].fs.meanImu[k] = himu[13 * i + 1 + k];
+        hdrs[i].fs.dtTotal = himu[13 * i];
+        hdrs[i].fs.nsteps = 1;
+    }
+    if ((rc = upload(f, f->d_hdrSteps, hdrs.data(), (size_t)nsteps)) != EQVIO_OK) return rc;
+    const double pd[8] = {s.biasOmegaProcessVariance,      s.biasAccelProcessVariance,     s.attitudeProcessVariance,
+                          s.positionProcessVariance,       s.velocityProcessVariance,      s.cameraAttitudeProcessVariance,
+                          s.cameraPositionProcessVariance, s.pointProcessVariance};
+    if ((rc = upload(f, f->dense.pdiag, pd, 8)) != EQVIO_OK) return rc;
+    dense::Workspace& w = f->dense;
+    for (int i = 0; i < nsteps; ++i) {
+        const double dt = himu[13 * i];
+        PrepArgs a;
+        a.xi0s = f->d_xi0s;
+        a.Xs = f->d_Xs[f->xcur];
+        a.XsOut = f->d_Xs[1 - f->xcur];
+        a.ctx = f->d_ctx;
+        a.steps = f->d_steps + i;
+        a.fr = f->d_hdrSteps + i;
+        a.imu = f->d_imu + (size_t)13 * i;
+        a.discreteLift = s.useDiscreteVelocityLift ? 1 : 0;
+        a.qdiag[0] = s.velGyrNoise * s.velGyrNoise;
+        a.qdiag[1] = s.velAccNoise * s.velAccNoise;
+        a.qdiag[2] = s.velGyrBiasWalk * s.velGyrBiasWalk;
+        a.qdiag[3] = s.velAccBiasWalk * s.velAccBiasWalk;
+        for (int k = 0; k < 8; ++k) a.pdiag[k] = pd[k];
+        if (dt > 0) {
+            const double* Sin = f->Sig[f->cur];
+            double* Sout = f->Sig[1 - f->cur];
+            double *M = w.buf[0], *P0 = w.buf[1], *T = w.buf[2], *P1 = w.buf[3], *R = w.buf[8];
+            riccati_prep_kernel<<<1, 448, 0, f->stream>>>(a, Sin, Sout, f->ld, w.dtBs);
+            LAUNCH_CHECK(f, "riccati_prep_kernel");
+            if (N > 0) {
+                landmark_rows_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_ctx, s.coordinateChoice, f->d_rows);
+                LAUNCH_CHECK(f, "landmark_rows_kernel");
+            }
+            CUDA_TRY(f, cudaMemsetAsync(M, 0, (size_t)n * n * sizeof(double), f->stream));
+            dense::dense_fill_sensor_kernel<<<2, 256, 0, f->stream>>>(M, n, dim, f->d_ctx, w.dtBs);
+            LAUNCH_CHECK(f, "dense_fill_sensor_kernel");
+            if (N > 0) {
+                dense::dense_fill_landmark_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(M, n, dim, N, f->d_rows, dt);
+                LAUNCH_CHECK(f, "dense_fill_landmark_kernel");
+            }
+            why = dense::expm(w, n, f->stream);
+            if (why) {
+                f->err = std::string("matrix exponential: ") + why;
+                return EQVIO_ERR_CUDA;
+            }
+            pack_sigma_kernel<<<dim3(cdiv(dim, 128), dim), 128, 0, f->stream>>>(Sin, f->ld, dim, P0, dim);
+            LAUNCH_CHECK(f, "pack_sigma_kernel");
+            if (dense::gemm(w, dense::OP_N, dense::OP_N, dim, dim, dim, 1.0, R, n, P0, dim, 0.0, T, dim) ||
+                dense::gemm(w, dense::OP_N, dense::OP_T, dim, dim, dim, 1.0, T, dim, R, n, 0.0, P1, dim)) {
+                f->err = "cublasDgemm failed";
+                return EQVIO_ERR_CUDA;
+            }
+            dense::dense_noise_kernel<<<dim3(cdiv(dim, 128), dim), 128, 0, f->stream>>>(P1, dim, R, n, a.qdiag[0], a.qdiag[1], a.qdiag[2],
+                                                                                       a.qdiag[3], 1.0 / dt, dt, w.pdiag);
+            LAUNCH_CHECK(f, "dense_noise_kernel");
+            CUDA_TRY(f, cudaMemsetAsync(Sout, 0, (size_t)f->ld * dimp_of(N) * sizeof(double), f->stream));
+            dense::dense_unpack_sigma_kernel<<<dim3(cdiv(dim, 128), dim), 128, 0, f->stream>>>(P1, dim, dim, Sout, f->ld);
+            LAUNCH_CHECK(f, "dense_unpack_sigma_kernel");
+            f->cur = 1 - f->cur;
+        }
+        observer_sensor_kernel<<<1, 32, 0, f->stream>>>(a);
+        LAUNCH_CHECK(f, "observer_sensor_kernel");
+        if (N > 0) {
+            observer_landmark_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(f->lm[f->lmcur], f->lm[1 - f->lmcur], f->dids[f->lmcur],
+                                                                        f->dids[1 - f->lmcur], f->cap, N, f->d_steps + i, f->d_hdrSteps + i);
+            LAUNCH_CHECK(f, "observer_landmark_kernel");
+            f->lmcur = 1 - f->lmcur;
+        }
+        f->xcur = 1 - f->xcur;
+    }
     return EQVIO_OK;
 }
 
@@ -704,7 +805,7 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
     const bool anyNew = matched < n;
     const size_t maxOutliers = (size_t)((1.0 - f->st.featureRetention) * n);
     // steady frame: nothing enters or leaves before the gate, so the launch sequence is fully known now
-    P.steady = f->speculate && f->corrMode == 0 && N > 0 && n > 0 && !anyNew && !anyLost;
+    P.steady = f->speculate && f->corrMode == 0 && N > 0 && n > 0 && !anyNew && !anyLost && f->st.fastRiccati;
     P.ignoreGate = maxOutliers == 0;
     if (P.steady) {
         P.speculated = true;
@@ -776,7 +877,7 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
     // general frame: upload, propagate, gate; decisions follow in phase B
     CUDA_TRY(f, cudaMemcpyAsync(f->d_frame, f->h_frame, f->frameBytes, cudaMemcpyHostToDevice, f->stream));
     stage_mark(f, 0);
-    if ((rc = enqueue_propagation(f)) != EQVIO_OK) return rc;
+    if ((rc = f->st.fastRiccati ? enqueue_propagation(f) : enqueue_propagation_accurate(f)) != EQVIO_OK) return rc;
     stage_mark(f, 1);
     if (N > 0) {
         if ((rc = enqueue_gate(f, N)) != EQVIO_OK) return rc;
@@ -1392,6 +1493,8 @@ void eqvio_destroy(eqvio_filter* f) {
     cudaFree(f->d_newP);
     cudaFree(f->d_out);
     cudaFree(f->d_frame);
+    cudaFree(f->d_hdrSteps);
+    f->dense.release();
     if (f->h_frame) cudaFreeHost(f->h_frame);
     if (f->h_out) cudaFreeHost(f->h_out);
     for (auto& g : f->graphs)

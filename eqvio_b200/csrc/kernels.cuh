@@ -213,7 +213,8 @@ __global__ void observer_sensor_kernel(PrepArgs a) {
 
 // One CTA: Riccati context (thread 0 builds the sparse A_s, B_s; 441 threads fill F_s, N_s) and, fused, the
 // sensor-sensor block  Sigma'_ss = F_s Sigma_ss F_s^T + N_s  plus the zero pad rows/cols of the sensor block.
-__global__ void __launch_bounds__(448) riccati_prep_kernel(PrepArgs a, const double* __restrict__ Sin, double* __restrict__ Sout, int ld) {
+__global__ void __launch_bounds__(448)
+    riccati_prep_kernel(PrepArgs a, const double* __restrict__ Sin, double* __restrict__ Sout, int ld, double* __restrict__ dtBsOut) {
     __shared__ double sAs[441], sBs[252], sF[441], sS[441], sT[441];
     const int t = threadIdx.x;
     if (t == 0) riccati_small(a, sAs, sBs);
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(448) riccati_prep_kernel(PrepArgs a, const dou
         riccati_entry(a, sAs, sBs, t, fs, ns);
         sF[t] = fs;
     }
+    if (dtBsOut && t < 252) dtBsOut[t] = a.fr->fs.dtTotal * sBs[t];  // dense (matrix-exponential) variant needs dt B_s itself
     __syncthreads();
     if (t < 441) {
         const int r = t / 21, c = t % 21;
@@ -928,7 +930,7 @@ struct ChunkSmem {
     double Us[CH_R][CH_R + 4];
     double Ur[CH_R][CH_RHS_ROWS * CH_T + 4];
     int Idx[CH_R / 2];
-    volatile int ready;                       // block columns of S_c whose panels are published
+    int ready;                                // block columns of S_c whose panels are published (release / acquire)
 };
 
 // reciprocal to <= 1 ulp: hardware approximation + two Newton steps (a correctly rounded division is
@@ -954,6 +956,15 @@ __device__ long long g_chunk_t[16];
 #else
 #define CH_STAMP(i) do { } while (0)
 #endif
+// progress flag between the two warp groups of chunk_factor_kernel: release store / acquire load at CTA scope
+__device__ __forceinline__ void flag_release(int* p, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int flag_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
 __device__ __forceinline__ void s_group_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(CH_S_THREADS) : "memory"); }
 
 // chunk_factor_kernel: every CTA eliminates the augmented matrix [S_c; W_c^T(its 32 state columns); r^T] in
@@ -1130,10 +1141,7 @@ __global__ void __launch_bounds__(CH_THREADS)
                     for (int j = 0; j < CH_T; ++j) sm.Lp[J][r][j][TI] = a[r][j];
             }
             s_group_barrier();
-            if (tid == 0) {
-                __threadfence_block();
-                sm.ready = J + 1;  // the right-hand-side warps may consume block column J
-            }
+            if (tid == 0) flag_release(&sm.ready, J + 1);  // the right-hand-side warps may consume block column J
             if (owner && TK > J) {
                 double li[CH_T][CH_T], pk[CH_T][CH_T];
 #pragma unroll
@@ -1237,8 +1245,7 @@ __global__ void __launch_bounds__(CH_THREADS)
         }
         CH_STAMP(108);
         for (int J = 0; J < nJ; ++J) {
-            while (sm.ready <= J) __nanosleep(64);
-            __threadfence_block();
+            while (flag_acquire(&sm.ready) <= J) __nanosleep(64);
             // the lane holding tile column J finishes its four columns ...
             double c[CH_T];
 #pragma unroll

@@ -194,7 +194,7 @@ def test_silent_returns_and_errors():
     with pytest.raises(eb.EqvioError) as ei:
         eb.VIOFilter(eb.Settings(coordinateChoice=2), capacity=4)
     assert ei.value.code == eb._capi.EQVIO_ERR_UNSUPPORTED
-    g = eb.VIOFilter(eb.Settings(fastRiccati=0), capacity=4)
+    g = eb.VIOFilter(eb.Settings(fastRiccati=0, useDiscreteStateMatrix=1), capacity=4)
     g.processIMUArray(fr.imu)
     with pytest.raises(eb.EqvioError) as ei:
         g.processVisionArrays(fr.stamp, fr.ids[:2], fr.y[:2], cam)
@@ -353,3 +353,11 @@ def test_nees_matches_oracle(coord):
         ng = g.computeNEES(eb.VIOState(eb.VIOSensorState.fromFlat(true.sensor.flat()), true.p, true.ids))
         assert np.isfinite(ng) and abs(ng - no) <= 1e-8 * max(1.0, abs(no)), (ng, no)
     g.close()
+
+
+@pytest.mark.parametrize("coord", [0, 1])
+def test_accurate_riccati_default_settings(coord):
+    """fastRiccati = false, the struct default: integrateRiccatiStateAccurate per IMU sample (VIO_eqf.cpp:74-91,
+    VIOFilter.cpp:160-178) -- dense matrix exponential on the device vs the oracle's scipy expm."""
+    stream = make_stream(N=12, frames=4, coord=coord, settings_overrides=dict(fastRiccati=False))
+    _check(run_gpu(stream), run_oracle(stream), tol=1e-8)
