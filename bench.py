@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--sequences-per-gpu", type=int, default=1, help="independent sequences (replicas) run concurrently per GPU")
     ap.add_argument("--no-graph", action="store_true", help="issue per-kernel launches instead of replaying CUDA graphs")
     ap.add_argument("--pipeline", action="store_true", help="experimental: overlap chunk c+1's factor kernel with chunk c's downdate")
+    ap.add_argument("--downdate", default="f64", choices=["f64", "tc"],
+                    help="f64: DMMA fp64 downdate (default); tc: tcgen05 split-bf16 operands, fp32 accumulate in TMEM (BASELINE configs[2])")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="updates in the cpu_baseline sample (0 = auto)")
@@ -233,6 +235,8 @@ def run_b200(args, rank, local_rank, world):
             flt.setTuning(graph=0)
         if args.pipeline:
             flt.setTuning(pipeline=1)
+        if args.downdate == "tc":
+            flt.setTuning(downdate=1)
         filters.append(flt)
     cam = eb.Camera(**streams[0].camera)
     flush_buf = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -380,7 +384,13 @@ def run_b200(args, rank, local_rank, world):
             per_update_ms = d["ms"] / max(nprof, 1)
             e = dict(ms_per_update=per_update_ms, launches_per_update=d["launches"] / max(nprof, 1),
                      avg_launch_us=1000.0 * d["ms"] / d["launches"])
-            if name == "downdate":
+            if name == "downdate" and args.downdate == "tc":
+                # six bf16 products per fp64-equivalent product; the tile kernel is bound by the fp64 Sigma traffic
+                # (read + write of the lower tiles and their mirrors), not by the tensor pipe
+                e.update(bound="hbm", achieved=2.0 * 8 * cnt["dim"] ** 2 * (cnt["m"] / 64.0) / (per_update_ms * 1e-3) / 1e9, peak=hbm_peak,
+                         unit="GB/s", tensor_tflops=6.0 * cnt["syrk_flops"] / (per_update_ms * 1e-3) / 1e12,
+                         tensor_peak_tflops=peaks.get("bf16_tflops", 1590.0))
+            elif name == "downdate":
                 e.update(bound="tensor", achieved=cnt["syrk_flops"] / (per_update_ms * 1e-3) / 1e12, peak=f64_peak, unit="TFLOP/s")
             elif name == "chunk_factor":
                 e.update(bound="latency", note="64 sequential pivots per chunk; fp64 CUDA-core work, one 4x4 register tile per thread")

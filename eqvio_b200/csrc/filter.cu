@@ -104,6 +104,8 @@ struct eqvio_filter {
     double *d_Gamma2 = nullptr, *d_ytilde = nullptr;
     int corrMode = 0;    // 0: sequential chunks (default), 1: batch Cholesky sweep over Z
     int speculate = 1;   // launch the correction before the gate results reach the host (redone on a gate hit)
+    int downdateTC = 0;  // 1: tcgen05 split-bf16 downdate (fp32 accumulate in TMEM) instead of the fp64 DMMA one
+    unsigned char* d_Ysplit = nullptr;
     int pipeline = 0;    // experimental: overlap chunk c+1's factor kernel with chunk c's (out-of-place) downdate
     double* d_Y2 = nullptr;
     std::vector<cudaEvent_t> chunkEv;
@@ -356,7 +358,7 @@ int alloc_frame(eqvio_filter* f, int steps, int ycap) {
 int alloc_device(eqvio_filter* f) {
     const int cap = f->cap;
     const int dimpMax = dimp_of(cap);
-    f->ld = (dimpMax + 63) & ~63;  // whole 64x64 tiles are moved by the downdate kernel
+    f->ld = (dimpMax + 127) & ~127;  // whole 64x64 (DMMA) / 128x128 (tcgen05) tiles are moved by the downdate kernels
     const size_t sigElems = (size_t)f->ld * f->ld;
     for (int k = 0; k < 2; ++k) {
         CUDA_TRY(f, cudaMalloc(&f->Sig[k], sigElems * sizeof(double)));
@@ -383,6 +385,7 @@ int alloc_device(eqvio_filter* f) {
     const size_t ldzMax = (mMax + dimpMax + 1 + 7) & ~size_t(7);
     f->zElems = std::max(std::max(ldzMax * mMax, sigElems), (size_t)(f->ld / YB_T) * YB_TILE);
     CUDA_TRY(f, cudaMalloc(&f->d_Z, f->zElems * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&f->d_Ysplit, (size_t)(f->ld / TC_T) * TC_BLOCK_BYTES));
     CUDA_TRY(f, cudaMalloc(&f->d_Y2, (size_t)(f->ld / YB_T) * YB_TILE * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Lout, ((size_t)dimpMax + mMax + NB) * NB * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Cblk, c1 * 6 * sizeof(double)));
@@ -1078,9 +1081,21 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
                 prof_end(f, pk);
                 LAUNCH_CHECK(f, "chunk_factor_kernel");
                 int sk = prof_begin(f, PROF_SYRK);
-                chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Y, guard);
+                if (f->downdateTC) {
+                    const int ncols = cdiv(ldy, TC_T) * TC_T;  // Y's pad columns up to ld are zero
+                    const int T128 = ncols / TC_T;
+                    if (ncols > ldy)  // the last 128-column block is only half covered by Y: the rest must read as zeros
+                        CUDA_TRY(f, cudaMemsetAsync(f->d_Ysplit + (size_t)(T128 - 1) * TC_BLOCK_BYTES, 0, TC_BLOCK_BYTES, f->stream));
+                    y_split_kernel<<<cdiv(ldy * 8, 256), 256, 0, f->stream>>>(Y, f->d_Ysplit, ldy);
+                    LAUNCH_CHECK(f, "y_split_kernel");
+                    chunk_downdate_tc_kernel<<<T128 * (T128 + 1) / 2, 128, TC_SMEM, f->stream>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld,
+                                                                                                 f->d_Ysplit, guard);
+                    LAUNCH_CHECK(f, "chunk_downdate_tc_kernel");
+                } else {
+                    chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Y, guard);
+                    LAUNCH_CHECK(f, "chunk_downdate_kernel");
+                }
                 prof_end(f, sk);
-                LAUNCH_CHECK(f, "chunk_downdate_kernel");
                 std::swap(gin, gout);
             }
         } else {
@@ -1258,6 +1273,7 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
         return EQVIO_ERR_CUDA;
     }
     e = cudaFuncSetAttribute(chunk_downdate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChunkSmem));
     if (e != cudaSuccess) {
         g_createError = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
@@ -1484,6 +1500,7 @@ void eqvio_destroy(eqvio_filter* f) {
     cudaFree(f->d_Z);
     cudaFree(f->d_Lout);
     cudaFree(f->d_Y2);
+    cudaFree(f->d_Ysplit);
     for (auto& e : f->chunkEv) cudaEventDestroy(e);
     cudaFree(f->d_Cblk);
     cudaFree(f->d_Gamma);
@@ -1960,6 +1977,13 @@ int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
         case EQVIO_TUNE_CORRECTION:
             if (value != 0 && value != 1) return EQVIO_ERR_INVALID_ARG;
             f->corrMode = value;
+            return EQVIO_OK;
+        case EQVIO_TUNE_DOWNDATE:
+            if (value != 0 && value != 1) return EQVIO_ERR_INVALID_ARG;
+            f->downdateTC = value;
+            for (auto& g : f->graphs)
+                if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+            f->graphs.clear();
             return EQVIO_OK;
         case EQVIO_TUNE_PIPELINE:
             f->pipeline = value != 0;

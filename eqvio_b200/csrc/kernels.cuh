@@ -13,6 +13,7 @@
 //             L (lower), Y^T = W^T L^-T and (L^-1 ytilde)^T in place, i.e. the partial
 //             Cholesky of [[S, W],[W^T, Sigma]] whose Schur complement is the updated Sigma.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -1423,6 +1424,143 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
                 *reinterpret_cast<double2*>(SigOut + (size_t)(i0 + fr + a * 8) * ld + j0 + fc + b * 8) = t;
             }
         }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core (tcgen05) variant of the chunk downdate -- BASELINE configs[2]: reduced-precision operands, fp32
+// accumulation.  tcgen05.mma has no fp64 kind, so Y_c is split into three bf16 terms (y = y0 + y1 + y2, 24 bits of
+// mantissa) and Y^T Y is accumulated in TMEM as the six products with i + j <= 2:
+//     Y0'Y0 + Y0'Y1 + Y1'Y0 + Y0'Y2 + Y2'Y0 + Y1'Y1        (fp32 accumulate, 24 UTCHMMA of 128x128x16 per tile)
+// then Sigma (still fp64 in HBM) <- Sigma - that.  One 128x128 tile of Sigma per CTA (tiles on / below the
+// diagonal); the mirror tile is produced by a second set of MMAs with the operands swapped (tensor time is free
+// here, transposing through shared memory is not), so every global access of the epilogue is coalesced.
+//   y_split_kernel   : fp64 Y (tile-blocked) -> bf16 splits in the canonical K-major no-swizzle core-matrix
+//                      layout of a UMMA shared-memory descriptor, one contiguous 48 KB block per 128 columns
+//   chunk_downdate_tc_kernel : TMA bulk copies of the blocks (cp.async.bulk + mbarrier), one elected thread issues
+//                      the MMAs, tcgen05.commit -> mbarrier, four warps read TMEM with tcgen05.ld (32x32b.x16).
+// Sigma's ld must be a multiple of 128.
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_T = 128, TC_K = 64;
+constexpr uint32_t TC_SBO = 128, TC_LBO = (TC_T / 8) * 128;          // bytes: next 8-row group / next 8-wide K chunk
+constexpr uint32_t TC_SPLIT_BYTES = TC_T * TC_K * 2;                 // 16 KB: one bf16 term of one 128-column block
+constexpr uint32_t TC_BLOCK_BYTES = 3 * TC_SPLIT_BYTES;              // 48 KB
+constexpr int TC_SMEM = 2 * TC_BLOCK_BYTES + 64;
+
+__global__ void y_split_kernel(const double* __restrict__ Y, unsigned char* __restrict__ Ys, int ncols) {
+    // one thread per (state column s, K chunk of 8)
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = t >> 3, kc = t & 7;
+    if (s >= ncols) return;
+    __nv_bfloat16 b0[8], b1[8], b2[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const double y = Y[yb_index(8 * kc + q, s)];
+        const __nv_bfloat16 h0 = __float2bfloat16_rn((float)y);
+        const double r1 = y - (double)__bfloat162float(h0);
+        const __nv_bfloat16 h1 = __float2bfloat16_rn((float)r1);
+        const double r2 = r1 - (double)__bfloat162float(h1);
+        b0[q] = h0;
+        b1[q] = h1;
+        b2[q] = __float2bfloat16_rn((float)r2);
+    }
+    const int blk = s / TC_T, r = s % TC_T;
+    unsigned char* base = Ys + (size_t)blk * TC_BLOCK_BYTES + kc * TC_LBO + (r / 8) * TC_SBO + (r % 8) * 16;
+    *reinterpret_cast<uint4*>(base) = *reinterpret_cast<const uint4*>(b0);
+    *reinterpret_cast<uint4*>(base + TC_SPLIT_BYTES) = *reinterpret_cast<const uint4*>(b1);
+    *reinterpret_cast<uint4*>(base + 2 * TC_SPLIT_BYTES) = *reinterpret_cast<const uint4*>(b2);
+}
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    // K-major, no swizzle: start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((TC_LBO >> 4) & 0x3FFF) << 16) | ((uint64_t)((TC_SBO >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(128)
+    chunk_downdate_tc_kernel(const double* SigIn, double* SigOut, int ld, const unsigned char* __restrict__ Ys,
+                             const int* __restrict__ guard) {
+    if (*guard) return;
+    int ti, tj;
+    tri_decode(blockIdx.x, ti, tj);
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    unsigned char* sA = tc_smem;
+    unsigned char* sB = tc_smem + TC_BLOCK_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + 2 * TC_BLOCK_BYTES);  // [0] operands landed, [1] MMAs done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_smem + 2 * TC_BLOCK_BYTES + 16);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool diag = ti == tj;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&bars[0], diag ? TC_BLOCK_BYTES : 2 * TC_BLOCK_BYTES);
+        bulk_g2s(sA, Ys + (size_t)ti * TC_BLOCK_BYTES, TC_BLOCK_BYTES, &bars[0]);
+        if (!diag) bulk_g2s(sB, Ys + (size_t)tj * TC_BLOCK_BYTES, TC_BLOCK_BYTES, &bars[0]);
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm = *tmem_slot;
+    if (tid == 0) {
+        mbar_wait(&bars[0], 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // c = F32, a = b = BF16, both K-major, N = 128, M = 128
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_T >> 3) << 17) | ((uint32_t)(TC_T >> 4) << 24);
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(diag ? sA : sB);
+        const int pa[6] = {0, 0, 1, 0, 2, 1}, pb[6] = {0, 1, 0, 2, 0, 1};  // split terms with i + j <= 2
+        for (int pass = 0; pass < (diag ? 1 : 2); ++pass) {
+            // pass 0: D1 = Y(ti)^T Y(tj) -> columns [0,128); pass 1: D2 = Y(tj)^T Y(ti) -> columns [128,256)
+            const uint32_t ra = pass == 0 ? a0 : b0, rb = pass == 0 ? b0 : a0;
+            uint32_t acc = 0;
+            for (int p = 0; p < 6; ++p)
+                for (int kk = 0; kk < TC_K / 16; ++kk) {
+                    umma_bf16(tm + 128 * pass, umma_desc(ra + pa[p] * TC_SPLIT_BYTES + (2 * kk) * TC_LBO),
+                              umma_desc(rb + pb[p] * TC_SPLIT_BYTES + (2 * kk) * TC_LBO), idesc, acc);
+                    acc = 1;
+                }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[1])) : "memory");
+    }
+    mbar_wait(&bars[1], 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int r = 32 * warp + lane;  // TMEM lane = row of the accumulator tile
+    const int i0 = ti * TC_T, j0 = tj * TC_T;
+    for (int pass = 0; pass < (diag ? 1 : 2); ++pass) {
+        // pass 0: element (r, c) of tile (ti, tj) = Sigma[i0 + r, j0 + c]; pass 1: of tile (tj, ti) = Sigma[j0 + r, i0 + c]
+        const int rbase = pass == 0 ? i0 : j0, cbase = pass == 0 ? j0 : i0;
+        for (int c0 = 0; c0 < TC_T; c0 += 16) {
+            uint32_t v[16];
+            const uint32_t taddr = tm + ((uint32_t)(32 * warp) << 16) + 128 * pass + c0;
+            double cin[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) cin[j] = SigIn[(size_t)(cbase + c0 + j) * ld + rbase + r];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) SigOut[(size_t)(cbase + c0 + j) * ld + rbase + r] = cin[j] - (double)__uint_as_float(v[j]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tm) : "memory");
 }
 
 // Gamma = Y^T (L^-1 ytilde):  Gamma[r] = sum_k Z[m + r, k] * Z[yrow, k].  One thread per r.

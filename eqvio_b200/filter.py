@@ -344,7 +344,7 @@ class VIOFilter:
         self._check(lib.eqvio_get_stage_ms(self._h, _pd(ms)))
         return dict(propagation=ms[0], preprocessing=ms[1], correction=ms[2])
 
-    def setTuning(self, correction=None, chunkLandmarks=None, speculate=None, graph=None, pipeline=None):
+    def setTuning(self, correction=None, chunkLandmarks=None, speculate=None, graph=None, pipeline=None, downdate=None):
         """Evaluation-order knobs (eqvio_set_tuning): correction 0 = sequential chunks, 1 = batch sweep."""
         if speculate is not None:
             self._check(lib.eqvio_set_tuning(self._h, 2, int(speculate)))
@@ -352,6 +352,8 @@ class VIOFilter:
             self._check(lib.eqvio_set_tuning(self._h, 3, int(graph)))
         if pipeline is not None:
             self._check(lib.eqvio_set_tuning(self._h, 4, int(pipeline)))
+        if downdate is not None:  # 0 = fp64 DMMA, 1 = tcgen05 split-bf16 / fp32 accumulate
+            self._check(lib.eqvio_set_tuning(self._h, 5, int(downdate)))
         if correction is not None:
             self._check(lib.eqvio_set_tuning(self._h, 0, int(correction)))
         if chunkLandmarks is not None:

@@ -199,6 +199,11 @@ int eqvio_get_kernel_profile(eqvio_filter* f, int reset, double ms[EQVIO_PROF_CL
  *                         than the default on B200 at N = 256 / 1024 (the folded-in update costs more than the
  *                         overlap returns); kept as a tested evaluation order. */
 #define EQVIO_TUNE_PIPELINE 4
+/*   EQVIO_TUNE_DOWNDATE: 0 (default) = Sigma -= Y^T Y in fp64 on the FP64 tensor pipe (DMMA);
+ *                         1 = BASELINE configs[2]: tcgen05 tensor cores, Y split into three bf16 terms (24-bit
+ *                         mantissa), fp32 accumulation in TMEM, Sigma itself stays fp64.  Parity with the fp64 path
+ *                         is ~1e-7 per update instead of ~1e-15. */
+#define EQVIO_TUNE_DOWNDATE 5
 int eqvio_set_tuning(eqvio_filter* f, int key, int value);
 /* Version / build info string (arch the kernels were compiled for). */
 const char* eqvio_build_info(void);

@@ -361,3 +361,38 @@ def test_accurate_riccati_default_settings(coord):
     VIOFilter.cpp:160-178) -- dense matrix exponential on the device vs the oracle's scipy expm."""
     stream = make_stream(N=12, frames=4, coord=coord, settings_overrides=dict(fastRiccati=False))
     _check(run_gpu(stream), run_oracle(stream), tol=1e-8)
+
+
+def test_tcgen05_probe():
+    """Stand-alone tcgen05 / TMEM / UMMA-descriptor probe (tests/csrc/tc_probe.cu): 128x128x64 bf16 GEMM, exact vs CPU."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "lib", "tc_probe")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-o", exe,
+                    os.path.join(root, "tests", "csrc", "tc_probe.cu")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("N", [40, 100])
+def test_tensor_core_downdate_close_to_fp64(N):
+    """BASELINE configs[2] arithmetic: tcgen05 downdate with split-bf16 operands (24-bit mantissa) and fp32 accumulation
+    in TMEM.  Not an fp64 path: the downdate Sigma - Y^T Y cancels (the first updates shrink the landmark covariance
+    by ~1e3), so the fp32-accumulated product leaves ~1e-7 * |Sigma_old| / |Sigma_new| relative error in Sigma --
+    observed ~5e-4 right after initialisation, smaller once the filter has converged.  Landmark ids stay identical and
+    the state estimate stays within 1e-4 of the oracle."""
+    stream = make_stream(N=N, frames=8, coord=0)
+    ref = run_oracle(stream)
+    got = run_gpu(stream, tuning=dict(downdate=1))
+    worst_sigma = worst_state = 0.0
+    for k, (g, r) in enumerate(zip(got, ref)):
+        e = compare_states(g, r)
+        assert e["ids_equal"], f"update {k}: landmark ids differ"
+        worst_sigma, worst_state = max(worst_sigma, e["sigma"]), max(worst_state, e["state"])
+    print(f"tcgen05 downdate N={N}: worst rel-Frobenius vs oracle: Sigma {worst_sigma:.3e}, state {worst_state:.3e}")
+    assert worst_sigma < 5e-3 and worst_state < 1e-4
+    S = got[-1]["Sigma"]
+    assert np.abs(S - S.T).max() <= 1e-6 * np.abs(S).max() and np.all(np.linalg.eigvalsh(0.5 * (S + S.T)) > 0)
