@@ -106,6 +106,8 @@ struct eqvio_filter {
     int speculate = 1;   // launch the correction before the gate results reach the host (redone on a gate hit)
     int downdateTC = 0;  // 1: tcgen05 split-bf16 downdate (fp32 accumulate in TMEM) instead of the fp64 DMMA one
     unsigned char* d_Ysplit = nullptr;
+    int lazyMirror = 1;  // downdate refreshes the upper triangle only where the next chunk reads it
+    std::vector<int> h_lmOfSorted;  // state indices of the correction rows (host copy of d_lmOf)
     int pipeline = 0;    // experimental: overlap chunk c+1's factor kernel with chunk c's (out-of-place) downdate
     double* d_Y2 = nullptr;
     std::vector<cudaEvent_t> chunkEv;
@@ -805,6 +807,7 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
         hMeasIdx[i] = P.measIdx[i];
     }
     P.oldIds = f->ids;
+    f->h_lmOfSorted.assign(hLmOf, hLmOf + matched);
     const bool anyNew = matched < n;
     const size_t maxOutliers = (size_t)((1.0 - f->st.featureRetention) * n);
     // steady frame: nothing enters or leaves before the gate, so the launch sequence is fully known now
@@ -819,7 +822,9 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
         P.h_status = reinterpret_cast<int*>(f->h_out + f->outOffStatus);
         P.nStatus = 1 + N;
         stage_mark(f, 0);
-        const bool graphOk = f->useGraph && !f->profiling;
+        // kernel arguments derived from the row -> landmark map are baked into a captured graph: replay only when that map
+        // is the identity (every state landmark measured)
+        const bool graphOk = f->useGraph && !f->profiling && matched == N;
         if (!graphOk) {
             if ((rc = enqueue_steady_update(f, N, n)) != EQVIO_OK) return rc;
             stage_mark(f, 3);
@@ -1032,6 +1037,7 @@ int launch_correction(eqvio_filter* f, const int* guard) {
             yIdx[j] = rows[j].second;
         }
     }
+    f->h_lmOfSorted = lmOf;
     if ((rc = upload(f, f->d_lmOf, lmOf.data(), nm)) != EQVIO_OK) return rc;
     if ((rc = upload(f, f->d_yIdx, yIdx.data(), nm)) != EQVIO_OK) return rc;
     if ((rc = upload(f, f->d_y, ky.data(), ky.size())) != EQVIO_OK) return rc;
@@ -1092,7 +1098,22 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
                                                                                                  f->d_Ysplit, guard);
                     LAUNCH_CHECK(f, "chunk_downdate_tc_kernel");
                 } else {
-                    chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Y, guard);
+                    // mirror tiles are only refreshed where the next chunk will gather (rows of its landmarks); the last
+                    // chunk writes them all
+                    int mlo = 0, mhi = T;
+                    if (j0 + bcMax < nm && f->lazyMirror) {
+                        const int* lo = f->h_lmOfSorted.data();
+                        const int nb = std::min(bcMax, nm - (j0 + bcMax));
+                        int rmin = lo[j0 + bcMax], rmax = lo[j0 + bcMax];
+                        for (int q = 1; q < nb; ++q) {
+                            rmin = std::min(rmin, lo[j0 + bcMax + q]);
+                            rmax = std::max(rmax, lo[j0 + bcMax + q]);
+                        }
+                        mlo = (SOFF + 3 * rmin) / DD_T;
+                        mhi = (SOFF + 3 * rmax + 2) / DD_T;
+                    }
+                    chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Y, guard,
+                                                                                              mlo, mhi);
                     LAUNCH_CHECK(f, "chunk_downdate_kernel");
                 }
                 prof_end(f, sk);
@@ -1125,7 +1146,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
                 CUDA_TRY(f, cudaEventRecord(evF, f->stream));
                 CUDA_TRY(f, cudaStreamWaitEvent(f->stream2, evF, 0));
                 chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream2>>>(f->Sig[sin], f->Sig[1 - sin], f->ld, Ybuf[c & 1],
-                                                                                           guard);
+                                                                                           guard, 0, T);
                 LAUNCH_CHECK(f, "chunk_downdate_kernel");
                 CUDA_TRY(f, cudaEventRecord(evD, f->stream2));
                 std::swap(gin, gout);

@@ -1361,7 +1361,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 __global__ void __launch_bounds__(DD_THREADS, 3)
     chunk_downdate_kernel(const double* SigIn, double* SigOut, int ld, const double* __restrict__ Y,
-                          const int* __restrict__ guard) {
+                          const int* __restrict__ guard, int mirrorLo, int mirrorHi) {
     if (*guard) return;
     int ti, tj;
     tri_decode(blockIdx.x, ti, tj);  // lower-triangular tile index -> (ti, tj), ti >= tj
@@ -1409,7 +1409,10 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
 #pragma unroll
             for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
     }
-    // acc = -(Sigma - Y^T Y): store negated.  Mirror tile: (c, c+1) are adjacent in memory -> 16-byte stores.
+    // acc = -(Sigma - Y^T Y): store negated.  Mirror tile: (c, c+1) are adjacent in memory -> 16-byte stores.  Between
+    // chunks only the lower triangle has to be current, except for the columns the NEXT chunk gathers (its landmarks'
+    // tile rows [mirrorLo, mirrorHi]); the last chunk (mirrorLo = 0, mirrorHi = all) restores full symmetric storage.
+    const bool mirror = !diag && ti >= mirrorLo && ti <= mirrorHi;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -1417,7 +1420,7 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
             const double v0 = -acc[a][b][0], v1 = -acc[a][b][1];
             cbase[(size_t)(b * 8) * ld + a * 8] = v0;
             cbase[(size_t)(b * 8 + 1) * ld + a * 8] = v1;
-            if (!diag) {
+            if (mirror) {
                 double2 t;
                 t.x = v0;
                 t.y = v1;
