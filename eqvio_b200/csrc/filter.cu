@@ -760,7 +760,7 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
             f->err = "measurement ids must be strictly ascending";
             return EQVIO_ERR_INVALID_ARG;
         }
-    if (cam->model != EQVIO_CAMERA_PINHOLE && cam->model != EQVIO_CAMERA_RADTAN) {
+    if (cam->model != EQVIO_CAMERA_PINHOLE && cam->model != EQVIO_CAMERA_RADTAN && cam->model != EQVIO_CAMERA_EQUIDISTANT) {
         f->err = "unsupported camera model";
         return EQVIO_ERR_UNSUPPORTED;
     }
@@ -1854,7 +1854,7 @@ int eqvio_get_feature_predictions(eqvio_filter* f, const eqvio_camera* cam, doub
     if (n_out) *n_out = 0;
     if (!f->st.useFeaturePredictions) return EQVIO_OK;  // VIOFilter.cpp:247-252: an empty measurement
     if (!cam) return EQVIO_ERR_INVALID_ARG;
-    if (cam->model != EQVIO_CAMERA_PINHOLE && cam->model != EQVIO_CAMERA_RADTAN) {
+    if (cam->model != EQVIO_CAMERA_PINHOLE && cam->model != EQVIO_CAMERA_RADTAN && cam->model != EQVIO_CAMERA_EQUIDISTANT) {
         f->err = "unsupported camera model";
         return EQVIO_ERR_UNSUPPORTED;
     }

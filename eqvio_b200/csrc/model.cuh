@@ -21,7 +21,7 @@ constexpr int SENSOR_DIM = 21;  // VIOSensorState::CompDim
 constexpr int SOFF = 24;        // internal row offset of landmark 0 in Sigma (sensor block padded 21 -> 24)
 
 enum { COORD_EUCLIDEAN = 0, COORD_INVDEPTH = 1 };
-enum { CAM_PINHOLE = 0, CAM_RADTAN = 1 };
+enum { CAM_PINHOLE = 0, CAM_RADTAN = 1, CAM_EQUIDISTANT = 2 };
 
 struct Camera {
     int model, width, height, ndist;
@@ -114,8 +114,23 @@ HD void distort_homogeneous(double x, double y, const double* d, int n, double& 
         oy += y * d[4] * r2 * r2 * r2;
     }
 }
+// EquidistantCamera::distortHomogeneousPoint (external/GIFT/GIFT/src/camera/EquidistantCamera.cpp:70-81)
+HD void distort_equidistant(double x, double y, const double* d, double& ox, double& oy) {
+    const double r = sqrt(x * x + y * y);
+    const double th = atan(r);
+    const double t2 = th * th;
+    const double temp = th * (1.0 + d[0] * t2 + d[1] * t2 * t2 + d[2] * t2 * t2 * t2 + d[3] * t2 * t2 * t2 * t2);
+    const double scale = (r > 1e-6) ? temp / r : 1.0;
+    ox = scale * x;
+    oy = scale * y;
+}
 HD void cam_project(const Camera& c, V3 p, double& u, double& v) {
-    if (c.model == CAM_RADTAN) {  // StandardCamera.cpp:41-48
+    if (c.model == CAM_EQUIDISTANT) {  // EquidistantCamera.cpp:38-46
+        double dx, dy;
+        distort_equidistant(p.x / p.z, p.y / p.z, c.dist, dx, dy);
+        u = c.fx * dx / 1.0 + c.cx;
+        v = c.fy * dy / 1.0 + c.cy;
+    } else if (c.model == CAM_RADTAN) {  // StandardCamera.cpp:41-48
         double dx, dy;
         distort_homogeneous(p.x / p.z, p.y / p.z, c.dist, c.ndist, dx, dy);
         u = c.fx * dx / 1.0 + c.cx;
@@ -125,19 +140,37 @@ HD void cam_project(const Camera& c, V3 p, double& u, double& v) {
         v = c.fy * p.y / p.z + c.cy;
     }
 }
-HD V3 cam_undistort(const Camera& c, double u, double v) {
-    V3 b = normalized(V3{(u - c.cx) / c.fx, (v - c.cy) / c.fy, 1.0});  // PinholeCamera.cpp:57-61
-    if (c.model == CAM_RADTAN) {                                        // StandardCamera.cpp:50-56
-        double dx, dy;
-        distort_homogeneous(b.x / b.z, b.y / b.z, c.inv_dist, c.ndist, dx, dy);
-        b = normalized(V3{dx, dy, 1.0});
-    }
-    return b;
-}
 // J: 2x3 row-major
 HD void cam_jacobian(const Camera& c, V3 p, double* J) {
     double iz = 1.0 / p.z;
-    if (c.model == CAM_RADTAN) {  // StandardCamera.cpp:77-111
+    if (c.model == CAM_EQUIDISTANT) {  // EquidistantCamera.cpp:83-119
+        const double Jh[6] = {1.0 / p.z, 0, -1.0 * p.x / (p.z * p.z), 0, 1.0 / p.z, -1.0 * p.y / (p.z * p.z)};
+        const double hx = p.x / p.z, hy = p.y / p.z;
+        double D00 = 1, D01 = 0, D10 = 0, D11 = 1;
+        const double r = sqrt(hx * hx + hy * hy);
+        if (r > 1e-6) {
+            const double* d = c.dist;
+            const double th = atan(r), t2 = th * th;
+            const double temp = 1.0 + d[0] * t2 + d[1] * t2 * t2 + d[2] * t2 * t2 * t2 + d[3] * t2 * t2 * t2 * t2;
+            D00 = D11 = temp * th / r;
+            D01 = D10 = 0;
+            const double Drx = hx / r, Dry = hy / r;
+            const double Dthx = Drx / (1.0 + r * r), Dthy = Dry / (1.0 + r * r);
+            double DTemp = temp / r;
+            double tp = th;  // theta^(2i-1)
+            for (int i = 1; i < 5; ++i) {
+                DTemp += th / r * d[i - 1] * (2 * i) * tp;
+                tp *= t2;
+            }
+            D00 += hx * DTemp * Dthx; D01 += hx * DTemp * Dthy; D10 += hy * DTemp * Dthx; D11 += hy * DTemp * Dthy;
+            const double k = -th / (r * r) * temp;
+            D00 += k * hx * Drx; D01 += k * hx * Dry; D10 += k * hy * Drx; D11 += k * hy * Dry;
+        }
+        for (int j = 0; j < 3; ++j) {
+            J[j] = c.fx * (D00 * Jh[j] + D01 * Jh[3 + j]);
+            J[3 + j] = c.fy * (D10 * Jh[j] + D11 * Jh[3 + j]);
+        }
+    } else if (c.model == CAM_RADTAN) {  // StandardCamera.cpp:77-111
         double Jh[6] = {1.0 / p.z, 0, -1.0 * p.x / (p.z * p.z), 0, 1.0 / p.z, -1.0 * p.y / (p.z * p.z)};
         double px = p.x / p.z, py = p.y / p.z;
         double r2 = px * px + py * py;
@@ -172,6 +205,32 @@ HD void cam_jacobian(const Camera& c, V3 p, double* J) {
         J[3] = 0; J[4] = c.fy / p.z; J[5] = -c.fy * p.y / (p.z * p.z);
     }
     (void)iz;
+}
+
+HD V3 cam_undistort(const Camera& c, double u, double v) {
+    V3 b = normalized(V3{(u - c.cx) / c.fx, (v - c.cy) / c.fy, 1.0});  // PinholeCamera.cpp:57-61
+    if (c.model == CAM_RADTAN) {                                        // StandardCamera.cpp:50-56
+        double dx, dy;
+        distort_homogeneous(b.x / b.z, b.y / b.z, c.inv_dist, c.ndist, dx, dy);
+        b = normalized(V3{dx, dy, 1.0});
+    } else if (c.model == CAM_EQUIDISTANT) {  // EquidistantCamera.cpp:48-68: damped Gauss-Newton on the sphere
+        for (int iter = 0; iter < 30; ++iter) {
+            double eu, ev;
+            cam_project(c, b, eu, ev);
+            const double r0 = u - eu, r1 = v - ev;
+            if (sqrt(r0 * r0 + r1 * r1) < 0.1) break;
+            double J[6];
+            cam_jacobian(c, b, J);
+            M3 H;
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) H(i, j) = J[i] * J[j] + J[3 + i] * J[3 + j] + (i == j ? 1000.0 : 0.0);
+            const V3 g = V3{J[0] * r0 + J[3] * r1, J[1] * r0 + J[4] * r1, J[2] * r0 + J[5] * r1};
+            const V3 step = inverse(H) * g;
+            b = normalized(b + step);
+            if (norm(step) < 0.005) break;
+        }
+    }
+    return b;
 }
 
 // ---------------------------------------------------------------- stereographic chart about a pole

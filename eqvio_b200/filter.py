@@ -20,7 +20,7 @@ from . import _capi
 from ._capi import EqvioError, lib
 
 COORD_EUCLIDEAN, COORD_INVDEPTH, COORD_NORMAL = 0, 1, 2
-CAMERA_PINHOLE, CAMERA_RADTAN = 0, 1
+CAMERA_PINHOLE, CAMERA_RADTAN, CAMERA_EQUIDISTANT = 0, 1, 2
 
 
 def _pd(a):
@@ -100,15 +100,15 @@ class Camera:
     """Flattened GIFT::GICamera (pinhole / radtan).  ``invDist`` of a radtan camera is recomputed by
     the library (StandardCamera::computeInverseDistortion) unless given."""
 
-    def __init__(self, width, height, fx, fy, cx, cy, dist=(), inv_dist=None):
+    def __init__(self, width, height, fx, fy, cx, cy, dist=(), inv_dist=None, model=None):
         pod = _capi.Camera()
-        pod.model = CAMERA_RADTAN if len(dist) else CAMERA_PINHOLE
+        pod.model = model if model is not None else (CAMERA_RADTAN if len(dist) else CAMERA_PINHOLE)
         pod.width, pod.height, pod.ndist = int(width), int(height), len(dist)
         pod.fx, pod.fy, pod.cx, pod.cy = float(fx), float(fy), float(cx), float(cy)
         for i in range(5):
             pod.dist[i] = float(dist[i]) if i < len(dist) else 0.0
             pod.inv_dist[i] = 0.0
-        if len(dist):
+        if len(dist) and pod.model == CAMERA_RADTAN:
             if inv_dist is None:
                 rc = lib.eqvio_camera_fit_inverse_distortion(C.byref(pod))
                 if rc != 0:
@@ -123,7 +123,7 @@ class Camera:
         """From the dict produced by the oracle cameras' ``pod()`` (tests) or any mapping with the same keys."""
         nd = d["ndist"]
         return Camera(d["width"], d["height"], d["fx"], d["fy"], d["cx"], d["cy"], d["dist"][:nd],
-                      d["inv_dist"][:nd] if nd else None)
+                      d["inv_dist"][:nd] if (nd and d["model"] == CAMERA_RADTAN) else None, model=d["model"])
 
 
 @dataclass

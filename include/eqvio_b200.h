@@ -52,6 +52,7 @@ extern "C" {
 
 #define EQVIO_CAMERA_PINHOLE 0
 #define EQVIO_CAMERA_RADTAN 1
+#define EQVIO_CAMERA_EQUIDISTANT 2 /* Kannala-Brandt fisheye, dist[0..3] (GIFT EquidistantCamera) */
 
 typedef struct eqvio_filter eqvio_filter;
 

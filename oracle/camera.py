@@ -15,6 +15,7 @@ from .liegroups import normalized
 
 MODEL_PINHOLE = 0
 MODEL_RADTAN = 1
+MODEL_EQUIDISTANT = 2
 
 
 class PinholeCamera:
@@ -168,6 +169,79 @@ class StandardCamera(PinholeCamera):
                 rhs.append(npt[1] - p[1])
         sol, *_ = np.linalg.lstsq(np.array(rows), np.array(rhs), rcond=None)
         return [float(s) for s in sol]
+
+
+class EquidistantCamera(PinholeCamera):
+    """Pinhole + Kannala-Brandt equidistant (fisheye) distortion, 4 coefficients
+    (external/GIFT/GIFT/src/camera/EquidistantCamera.cpp)."""
+
+    model = MODEL_EQUIDISTANT
+
+    def __init__(self, width, height, fx, fy, cx, cy, dist):
+        super().__init__(width, height, fx, fy, cx, cy)
+        self.dist = [float(d) for d in dist][:4]
+        self.invDist = []
+
+    # EquidistantCamera.cpp:70-81
+    def _distort(self, h):
+        h = np.asarray(h, dtype=np.float64)
+        r = np.sqrt(h[..., 0] * h[..., 0] + h[..., 1] * h[..., 1])
+        theta = np.arctan(r)
+        d = self.dist
+        temp = theta * (1.0 + d[0] * theta**2 + d[1] * theta**4 + d[2] * theta**6 + d[3] * theta**8)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            scale = np.where(r > 1e-6, temp / np.where(r > 1e-6, r, 1.0), 1.0)
+        return scale[..., None] * h
+
+    # EquidistantCamera.cpp:38-46
+    def projectPoint(self, p):
+        p = np.asarray(p, dtype=np.float64)
+        h = np.stack([p[..., 0] / p[..., 2], p[..., 1] / p[..., 2]], -1)
+        d = self._distort(h)
+        return np.stack([self.fx * d[..., 0] / 1.0 + self.cx, self.fy * d[..., 1] / 1.0 + self.cy], -1)
+
+    # EquidistantCamera.cpp:48-68: damped Gauss-Newton on the sphere, stops at 0.1 px residual / 0.005 step
+    def undistortPoint(self, y):
+        y = np.asarray(y, dtype=np.float64)
+        if y.ndim > 1:
+            return np.stack([self.undistortPoint(v) for v in y.reshape(-1, 2)], 0).reshape(y.shape[:-1] + (3,))
+        result = PinholeCamera.undistortPoint(self, y)
+        for _ in range(30):
+            res = y - self.projectPoint(result)
+            if np.sqrt(res @ res) < 0.1:
+                break
+            J = self.projectionJacobian(result)
+            H = J.T @ J + np.eye(3) * 1000.0
+            step = np.linalg.solve(H, J.T @ res)
+            result = normalized(result + step)
+            if np.sqrt(step @ step) < 0.005:
+                break
+        return result
+
+    # EquidistantCamera.cpp:83-119
+    def projectionJacobian(self, p):
+        p = np.asarray(p, dtype=np.float64)
+        if p.ndim > 1:
+            return np.stack([self.projectionJacobian(v) for v in p.reshape(-1, 3)], 0).reshape(p.shape[:-1] + (2, 3))
+        x, yy, z = p
+        Jh = np.array([[1.0 / z, 0.0, -1.0 * x / (z * z)], [0.0, 1.0 / z, -1.0 * yy / (z * z)]])
+        h = np.array([x / z, yy / z])
+        D = np.eye(2)
+        r = np.sqrt(h @ h)
+        if r > 1e-6:
+            d = self.dist
+            theta = np.arctan(r)
+            temp = 1.0 + d[0] * theta**2 + d[1] * theta**4 + d[2] * theta**6 + d[3] * theta**8
+            D = temp * theta / r * np.eye(2)
+            Dr = h / r
+            Dth = Dr / (1.0 + r * r)
+            DTemp = temp / r
+            for i in range(1, 5):
+                DTemp += theta / r * d[i - 1] * (2 * i) * theta ** (2 * i - 1)
+            D = D + np.outer(h, Dth) * DTemp
+            D = D + (-theta / (r * r) * temp) * np.outer(h, Dr)
+        K2 = np.array([[self.fx, 0.0], [0.0, self.fy]])
+        return K2 @ D @ Jh
 
 
 def createDefaultCamera():

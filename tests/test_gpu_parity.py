@@ -146,6 +146,23 @@ def test_radtan_camera():
     _check(run_gpu(stream), run_oracle(stream))
 
 
+def test_equidistant_camera():
+    """GIFT EquidistantCamera (fisheye): iterative undistort + its Jacobian inside C* on the device."""
+    from oracle.camera import EquidistantCamera
+    from oracle.simulator import SimulationDataServer, benchmarkSim
+
+    for coord in (0, 1):
+        stream = make_stream(N=24, frames=1, coord=coord)
+        cam = EquidistantCamera(752, 480, 458.654, 457.296, 367.215, 248.375,
+                                [-0.013721808247486035, 0.020727425669427896, -0.012786476702685545, 0.0025242267320687625])
+        stream["cam"] = cam
+        server = SimulationDataServer(benchmarkSim(24, 0), stream["settings"])
+        server.simulator.cameraPtr = cam
+        stream["init"] = server.initialCondition()
+        stream["frames"] = server.record(6)
+        _check(run_gpu(stream), run_oracle(stream))
+
+
 def test_config2_n256():
     """BASELINE configs[1]: N=256 landmarks, fp64 Sigma, correctness vs the CPU reference path."""
     stream = make_stream(N=256, frames=4, coord=0)

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import eqf
-from oracle.camera import StandardCamera, createDefaultCamera
+from oracle.camera import EquidistantCamera, StandardCamera, createDefaultCamera
 from parity_utils import make_stream
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -74,11 +74,12 @@ def test_riccati_context_and_observer_sensor_part(hooks, coord, discrete):
 
 
 @pytest.mark.parametrize("coord", [0, 1])
-@pytest.mark.parametrize("radtan", [False, True])
+@pytest.mark.parametrize("radtan", [0, 1, 2])
 def test_output_block_matches_oracle(hooks, coord, radtan):
     rng = np.random.default_rng(5)
-    cam = StandardCamera(752, 480, 458.654, 457.296, 367.215, 248.375, [-0.283, 0.074, 0.0002, 1.8e-05, 0.0]) if radtan \
-        else createDefaultCamera()
+    cam = [createDefaultCamera(),
+           StandardCamera(752, 480, 458.654, 457.296, 367.215, 248.375, [-0.283, 0.074, 0.0002, 1.8e-05, 0.0]),
+           EquidistantCamera(512, 512, 190.978, 190.973, 254.93, 256.9, [-0.0137, 0.0207, -0.0128, 0.0025])][radtan]
     pod = cam.pod()
     camv = np.array([pod["model"], pod["width"], pod["height"], pod["ndist"], pod["fx"], pod["fy"], pod["cx"], pod["cy"]]
                     + list(pod["dist"]) + list(pod["inv_dist"]), dtype=np.float64)

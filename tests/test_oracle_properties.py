@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import eqf, liegroups as lg
-from oracle.camera import PinholeCamera, StandardCamera, createDefaultCamera
+from oracle.camera import EquidistantCamera, PinholeCamera, StandardCamera, createDefaultCamera
 
 from oracle_utils import (NEAR_ZERO, TEST_REPS, assertMatrixEquality, logNorm, measurementDistance,
                           randomGroupElement, randomStateElement, randomVelocityElement, randomVisionMeasurement,
@@ -112,6 +112,40 @@ def test_camera_standard_reprojection():
         for y in range(60, 420, 60):
             px = np.array([x, y], dtype=np.float64)
             assert np.linalg.norm(cam.projectPoint(cam.undistortPoint(px)) - px) < 1.0
+
+
+# external/GIFT/GIFT/test/test_Camera.cpp (Equidistant cases): Jacobian vs finite differences and
+# undistort -> project round trip; the Gauss-Newton inverse stops at a 0.1 px residual by design
+EQUI_DIST = [-0.013721808247486035, 0.020727425669427896, -0.012786476702685545, 0.0025242267320687625]
+
+
+def test_camera_equidistant_projection_jacobian():
+    cam = EquidistantCamera(512, 512, 190.978, 190.973, 254.93, 256.9, EQUI_DIST)
+    for x in range(20, 512, 41):
+        for y in range(20, 512, 41):
+            if np.hypot((x - cam.cx) / cam.fx, (y - cam.cy) / cam.fy) > 1.3:
+                continue
+            sp = cam.undistortPoint(np.array([x, y], dtype=np.float64))
+            testDifferential(cam.projectPoint, sp, cam.projectionJacobian(sp))
+    # the r <= 1e-6 branch: optical axis
+    J = cam.projectionJacobian(np.array([0.0, 0.0, 2.0]))
+    assert np.allclose(J, np.array([[cam.fx / 2, 0, 0], [0, cam.fy / 2, 0]]))
+
+
+def test_camera_equidistant_reprojection():
+    cam = EquidistantCamera(512, 512, 190.978, 190.973, 254.93, 256.9, EQUI_DIST)
+    for x in range(20, 512, 41):
+        for y in range(20, 512, 41):
+            px = np.array([x, y], dtype=np.float64)
+            if np.hypot((x - cam.cx) / cam.fx, (y - cam.cy) / cam.fy) > 1.3:
+                continue  # beyond ~75 deg off-axis: outside what atan(r) of a z>0 bearing can reach reliably
+            b = cam.undistortPoint(px)
+            assert abs(np.linalg.norm(b) - 1.0) < 1e-12
+            assert np.linalg.norm(cam.projectPoint(b) - px) < 0.5
+    # batched evaluation agrees with the scalar path
+    P = np.random.default_rng(2).uniform(-1, 1, (7, 3)) + np.array([0, 0, 2.0])
+    assert np.allclose(cam.projectPoint(P), np.stack([cam.projectPoint(p) for p in P]))
+    assert np.allclose(cam.projectionJacobian(P), np.stack([cam.projectionJacobian(p) for p in P]))
 
 
 # --------------------------------------------------------------- test/test_VIOGroup.cpp:26-60
