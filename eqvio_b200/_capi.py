@@ -9,6 +9,7 @@ import ctypes as C
 import os
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libeqvio_b200.so")
+LIB_PATH = os.environ.get("EQVIO_B200_LIB", LIB_PATH)  # debug builds (-DEQVIO_TIMELINE ...); still no CPU fallback
 
 EQVIO_OK = 0
 EQVIO_ERR_INVALID_ARG = -1
@@ -94,6 +95,7 @@ SIGNATURES = {
     "eqvio_get_launch_count": (C.c_longlong, [_H]),
     "eqvio_enable_kernel_profile": (_I, [_H, _I]),
     "eqvio_get_kernel_profile": (_I, [_H, _I, _PD, C.POINTER(C.c_longlong)]),
+    "eqvio_get_host_profile": (_I, [_H, _I, _PD, C.POINTER(C.c_longlong)]),
     "eqvio_set_tuning": (_I, [_H, _I, _I]),
     "eqvio_build_info": (C.c_char_p, []),
 }

@@ -7,6 +7,7 @@
 // There is no CPU fallback: every entry point that touches filter state needs a CUDA device and
 // returns EQVIO_ERR_CUDA otherwise.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <deque>
@@ -68,6 +69,7 @@ struct eqvio_filter {
     double* d_xi0s = nullptr;
     double* d_Xs[2] = {nullptr, nullptr};  // X sensor part, ping-pong across the observer integration
     int xcur = 0;
+    cudaStream_t stream3 = nullptr;  // low priority: deferred downdate tiles of the look-ahead correction
     cudaStream_t stream2 = nullptr;  // observer chain of the propagation runs beside the Riccati chain
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     RiccatiCtx* d_ctx = nullptr;
@@ -85,7 +87,8 @@ struct eqvio_filter {
     int yCap = 0;
     // fixed pinned output block of the steady path: gate scalars | spec flag | status words
     unsigned char* h_out = nullptr;
-    size_t outOffSpec = 0, outOffStatus = 0, outOffEst = 0;
+    size_t outOffSpec = 0, outOffStatus = 0, outOffEst = 0, outBytes = 0;
+    unsigned char* d_outblk = nullptr;  // device mirror of h_out: d_gate / d_spec / d_status / d_out point into it
     bool estValid = false;  // h_out holds the state estimate of the current state (produced by the steady update)
     // CUDA graphs of the steady-state update, keyed by everything that shapes the launch sequence
     struct GraphEntry {
@@ -108,6 +111,13 @@ struct eqvio_filter {
     unsigned char* d_Ysplit = nullptr;
     int lazyMirror = 1;  // downdate refreshes the upper triangle only where the next chunk reads it
     std::vector<int> h_lmOfSorted;  // state indices of the correction rows (host copy of d_lmOf)
+    int pdl = 1;           // chunk kernels are launched with programmatic dependent launch allowed
+    int fuseObserver = 1;  // sensor + landmark parts of the observer integration as one software-pipelined kernel
+    int tlNext = 0;  // debug timeline slot counter (EQVIO_TIMELINE builds)
+    double hostUs[4] = {0, 0, 0, 0};  // process_vision host time: phase A (plan + enqueue), phase B, wait for the device, rest of phase C
+    long long hostCalls = 0;
+    double hostWaitUs = 0;
+    int lookahead = 2;   // 2 = automatic (on when the tile grid spans more than one wave, T >= 24), 1 = on, 0 = off: split each downdate into the tiles the next chunk gathers (urgent) and the rest (beside the next factor)
     int pipeline = 0;    // experimental: overlap chunk c+1's factor kernel with chunk c's (out-of-place) downdate
     double* d_Y2 = nullptr;
     std::vector<cudaEvent_t> chunkEv;
@@ -259,6 +269,24 @@ int check_launch(eqvio_filter* f, const char* what) {
         if (rc_ != EQVIO_OK) return rc_;               \
     } while (0)
 
+// Launch with programmatic dependent launch allowed: the grid may be scheduled while its predecessor on the stream is
+// still draining; the kernel itself blocks in griddepcontrol.wait (pdl_wait() in kernels.cuh) before it touches global
+// memory, so only launch latency / CTA set-up overlaps.  Under stream capture the edge becomes a programmatic graph edge.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(eqvio_filter* f, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = f->pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // profiling brackets -------------------------------------------------------------------------
 int prof_begin(eqvio_filter* f, int cls) {
     if (!f->profiling) return -1;
@@ -372,7 +400,15 @@ int alloc_device(eqvio_filter* f) {
     CUDA_TRY(f, cudaMalloc(&f->d_xi0s, 23 * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Xs[0], 23 * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Xs[1], 23 * sizeof(double)));
-    CUDA_TRY(f, cudaStreamCreateWithFlags(&f->stream2, cudaStreamNonBlocking));
+    {
+        // the deferred downdate tiles of the look-ahead correction run at the LOWEST priority and everything on the critical
+        // path (f->stream, f->stream2) at the highest: the CTAs of the next chunk's factor kernel must be dispatched ahead
+        // of the queued tile CTAs, not after them
+        int prLeast = 0, prGreatest = 0;
+        CUDA_TRY(f, cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest));
+        CUDA_TRY(f, cudaStreamCreateWithPriority(&f->stream2, cudaStreamNonBlocking, prGreatest));
+        CUDA_TRY(f, cudaStreamCreateWithPriority(&f->stream3, cudaStreamNonBlocking, prLeast));
+    }
     CUDA_TRY(f, cudaEventCreateWithFlags(&f->evFork, cudaEventDisableTiming));
     CUDA_TRY(f, cudaEventCreateWithFlags(&f->evJoin, cudaEventDisableTiming));
     CUDA_TRY(f, cudaMalloc(&f->d_ctx, sizeof(RiccatiCtx)));
@@ -394,19 +430,22 @@ int alloc_device(eqvio_filter* f) {
     CUDA_TRY(f, cudaMalloc(&f->d_Gamma, (size_t)(dimpMax + 8) * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Gamma2, (size_t)(dimpMax + 8) * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_ytilde, 2 * c1 * sizeof(double)));
-    CUDA_TRY(f, cudaMalloc(&f->d_gate, c1 * 3 * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_newP, c1 * 3 * sizeof(double)));
-    CUDA_TRY(f, cudaMalloc(&f->d_out, (23 + 3 * c1) * sizeof(double)));
+    // everything the host reads back after an update lives in ONE device block with the layout of the pinned h_out:
+    // gate scalars | gate flag (+ a constant 0) | status words | state estimate  -- a steady frame downloads it with one copy
     f->outOffSpec = ((3 * c1 * sizeof(double)) + 63) & ~size_t(63);
     f->outOffStatus = f->outOffSpec + 64;
     f->outOffEst = (f->outOffStatus + (1 + c1) * sizeof(int) + 63) & ~size_t(63);
-    CUDA_TRY(f, cudaMallocHost(&f->h_out, f->outOffEst + (23 + 3 * c1) * sizeof(double)));
+    f->outBytes = f->outOffEst + (23 + 3 * c1) * sizeof(double);
+    CUDA_TRY(f, cudaMallocHost(&f->h_out, f->outBytes));
+    CUDA_TRY(f, cudaMalloc(&f->d_outblk, f->outBytes));
+    CUDA_TRY(f, cudaMemsetAsync(f->d_outblk, 0, f->outBytes, f->stream));
+    f->d_gate = reinterpret_cast<double*>(f->d_outblk);
+    f->d_spec = reinterpret_cast<int*>(f->d_outblk + f->outOffSpec);
+    f->d_status = reinterpret_cast<int*>(f->d_outblk + f->outOffStatus);
+    f->d_out = reinterpret_cast<double*>(f->d_outblk + f->outOffEst);
     CUDA_TRY(f, cudaMalloc(&f->d_map, c1 * sizeof(int)));
     CUDA_TRY(f, cudaMalloc(&f->d_newIds, c1 * sizeof(int)));
-    CUDA_TRY(f, cudaMalloc(&f->d_status, (1 + c1) * sizeof(int)));
-    CUDA_TRY(f, cudaMemsetAsync(f->d_status, 0, (1 + c1) * sizeof(int), f->stream));
-    CUDA_TRY(f, cudaMalloc(&f->d_spec, 2 * sizeof(int)));
-    CUDA_TRY(f, cudaMemsetAsync(f->d_spec, 0, 2 * sizeof(int), f->stream));
     for (int i = 0; i < 2; ++i) CUDA_TRY(f, cudaEventCreate(&f->augEv[i]));
     for (int i = 0; i < 4; ++i) CUDA_TRY(f, cudaEventCreate(&f->stageEv[i]));
     return EQVIO_OK;
@@ -585,18 +624,25 @@ int enqueue_propagation(eqvio_filter* f) {
     a.pdiag[7] = s.pointProcessVariance;
     CUDA_TRY(f, cudaEventRecord(f->evFork, f->stream));
     CUDA_TRY(f, cudaStreamWaitEvent(f->stream2, f->evFork, 0));
-    observer_sensor_kernel<<<1, 32, 0, f->stream2>>>(a);
-    LAUNCH_CHECK(f, "observer_sensor_kernel");
-    if (N > 0) {
-        observer_landmark_kernel<<<cdiv(N, 64), 64, 0, f->stream2>>>(f->lm[f->lmcur], f->lm[1 - f->lmcur], f->dids[f->lmcur],
-                                                                     f->dids[1 - f->lmcur], f->cap, N, f->d_steps, f->d_hdr);
-        LAUNCH_CHECK(f, "observer_landmark_kernel");
+    const int nsteps = reinterpret_cast<const FrameHeader*>(f->h_frame)->fs.nsteps;
+    if (N > 0 && nsteps <= OBS_STAGE && f->fuseObserver) {
+        observer_fused_kernel<<<cdiv(N, OBSF_LM), OBSF_THREADS, 0, f->stream2>>>(a, f->lm[f->lmcur], f->lm[1 - f->lmcur], f->dids[f->lmcur],
+                                                                                 f->dids[1 - f->lmcur], f->cap, N);
+        LAUNCH_CHECK(f, "observer_fused_kernel");
+    } else {
+        observer_sensor_kernel<<<1, 32, 0, f->stream2>>>(a);
+        LAUNCH_CHECK(f, "observer_sensor_kernel");
+        if (N > 0) {
+            observer_landmark_kernel<<<cdiv(N, 64), 64, 0, f->stream2>>>(f->lm[f->lmcur], f->lm[1 - f->lmcur], f->dids[f->lmcur],
+                                                                         f->dids[1 - f->lmcur], f->cap, N, f->d_steps, f->d_hdr);
+            LAUNCH_CHECK(f, "observer_landmark_kernel");
+        }
     }
     CUDA_TRY(f, cudaEventRecord(f->evJoin, f->stream2));
     {
         const double* Sin = f->Sig[f->cur];
         double* Sout = f->Sig[1 - f->cur];
-        riccati_prep_kernel<<<1, 448, 0, f->stream>>>(a, Sin, Sout, f->ld, nullptr);
+        riccati_prep_kernel<<<1, 448, 0, f->stream>>>(a, Sin, Sout, f->ld, nullptr, f->d_spec);  // also re-arms the gate flag
         LAUNCH_CHECK(f, "riccati_prep_kernel");
         if (N > 0) {
             landmark_rows_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_ctx, s.coordinateChoice, f->d_rows);
@@ -666,7 +712,7 @@ int enqueue_propagation_accurate(eqvio_filter* f) {
             const double* Sin = f->Sig[f->cur];
             double* Sout = f->Sig[1 - f->cur];
             double *M = w.buf[0], *P0 = w.buf[1], *T = w.buf[2], *P1 = w.buf[3], *R = w.buf[8];
-            riccati_prep_kernel<<<1, 448, 0, f->stream>>>(a, Sin, Sout, f->ld, w.dtBs);
+            riccati_prep_kernel<<<1, 448, 0, f->stream>>>(a, Sin, Sout, f->ld, w.dtBs, nullptr);
             LAUNCH_CHECK(f, "riccati_prep_kernel");
             if (N > 0) {
                 landmark_rows_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_ctx, s.coordinateChoice, f->d_rows);
@@ -712,8 +758,8 @@ int enqueue_propagation_accurate(eqvio_filter* f) {
     return EQVIO_OK;
 }
 
-int enqueue_gate(eqvio_filter* f, int N) {
-    CUDA_TRY(f, cudaMemsetAsync(f->d_spec, 0, sizeof(int), f->stream));
+int enqueue_gate(eqvio_filter* f, int N, bool clearFlag) {
+    if (clearFlag) CUDA_TRY(f, cudaMemsetAsync(f->d_spec, 0, sizeof(int), f->stream));
     gate_kernel<<<cdiv(N, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->Sig[f->cur], f->ld, f->d_measIdx, f->d_y,
                                                       f->d_hdr, f->st.coordinateChoice, f->d_gate, f->st.outlierThresholdAbs,
                                                       f->st.outlierThresholdProb, f->d_spec);
@@ -722,6 +768,11 @@ int enqueue_gate(eqvio_filter* f, int N) {
 }
 
 int enqueue_correction(eqvio_filter* f, int nm, const int* guard);
+#ifdef EQVIO_TIMELINE
+#define TL_SLOT(f) ((f)->tlNext++)
+#else
+#define TL_SLOT(f) (-1)
+#endif
 
 // The whole device side of a steady frame (no landmark enters or leaves before the gate): frame upload,
 // propagation, gate, guarded correction, result downloads into the fixed pinned block.  Issued either directly
@@ -730,16 +781,13 @@ int enqueue_steady_update(eqvio_filter* f, int N, int nm) {
     int rc;
     CUDA_TRY(f, cudaMemcpyAsync(f->d_frame, f->h_frame, f->frameBytes, cudaMemcpyHostToDevice, f->stream));
     if ((rc = enqueue_propagation(f)) != EQVIO_OK) return rc;
-    if ((rc = enqueue_gate(f, N)) != EQVIO_OK) return rc;
-    CUDA_TRY(f, cudaMemcpyAsync(f->h_out, f->d_gate, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
-    CUDA_TRY(f, cudaMemcpyAsync(f->h_out + f->outOffSpec, f->d_spec, sizeof(int), cudaMemcpyDeviceToHost, f->stream));
+    if ((rc = enqueue_gate(f, N, false)) != EQVIO_OK) return rc;  // riccati_prep_kernel re-armed the flag
     if ((rc = enqueue_correction(f, nm, f->d_spec)) != EQVIO_OK) return rc;
-    CUDA_TRY(f, cudaMemcpyAsync(f->h_out + f->outOffStatus, f->d_status, (1 + (size_t)N) * sizeof(int), cudaMemcpyDeviceToHost,
-                                f->stream));
     // stateEstimate() is what every caller asks for next (main_opt.cpp:225, main_sim.cpp:146): produce it here
     state_estimate_kernel<<<cdiv(N, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_xi0s, f->d_Xs[f->xcur], f->d_out);
     LAUNCH_CHECK(f, "state_estimate_kernel");
-    CUDA_TRY(f, cudaMemcpyAsync(f->h_out + f->outOffEst, f->d_out, (23 + 3 * (size_t)N) * sizeof(double), cudaMemcpyDeviceToHost,
+    // one download: gate scalars, gate flag, status words, state estimate (the block has the layout of h_out)
+    CUDA_TRY(f, cudaMemcpyAsync(f->h_out, f->d_outblk, f->outOffEst + (23 + 3 * (size_t)N) * sizeof(double), cudaMemcpyDeviceToHost,
                                 f->stream));
     return EQVIO_OK;
 }
@@ -888,7 +936,7 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
     if ((rc = f->st.fastRiccati ? enqueue_propagation(f) : enqueue_propagation_accurate(f)) != EQVIO_OK) return rc;
     stage_mark(f, 1);
     if (N > 0) {
-        if ((rc = enqueue_gate(f, N)) != EQVIO_OK) return rc;
+        if ((rc = enqueue_gate(f, N, true)) != EQVIO_OK) return rc;
         if ((rc = download_async(f, &P.h_gate, f->d_gate, 3 * (size_t)N)) != EQVIO_OK) return rc;
         if ((rc = download_async(f, &P.h_spec, f->d_spec, 1)) != EQVIO_OK) return rc;
         P.gated = true;
@@ -1061,7 +1109,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
     const int Mz = m + dimp + 1;
     const int ldz = (Mz + 7) & ~7;
     double* Z = f->d_Z;
-    CUDA_TRY(f, cudaMemsetAsync(f->d_status, 0, (1 + (size_t)Nn) * sizeof(int), f->stream));
+    if (f->corrMode != 0) CUDA_TRY(f, cudaMemsetAsync(f->d_status, 0, (1 + (size_t)Nn) * sizeof(int), f->stream));
     const double r2 = s.measurementNoise * s.measurementNoise;
     const double* gammaFinal = f->d_Gamma;
     if (f->corrMode == 0) {
@@ -1069,21 +1117,75 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
         const int ldy = (dimp + 63) & ~63;
         const int T = ldy / DD_T;
         double* Y = f->d_Z;
-        meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
-                                                          s.useEquivariantOutput ? 1 : 0, f->d_Cblk, f->d_ytilde, 1, 0, guard, f->d_yIdx);
-        LAUNCH_CHECK(f, "meas_kernel");
         double* gin = f->d_Gamma;
         double* gout = f->d_Gamma2;
-        CUDA_TRY(f, cudaMemsetAsync(gin, 0, (size_t)dimp * sizeof(double), f->stream));
+        // also clears the status words and Gamma (no memset nodes between the kernels of the update)
+        meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
+                                                          s.useEquivariantOutput ? 1 : 0, f->d_Cblk, f->d_ytilde, 1, 0, guard, f->d_yIdx,
+                                                          f->d_status, 1 + Nn, gin, dimp);
+        LAUNCH_CHECK(f, "meas_kernel");
         const int bcMax = std::max(1, std::min(f->chunkLm, CH_R / 2));
         const int nchunks = cdiv(nm, bcMax);
         const bool pipe = f->pipeline && nchunks > 1 && !f->profiling;
-        if (!pipe) {
+        const bool look = !pipe && (f->lookahead == 1 || (f->lookahead == 2 && T >= 24)) && nchunks > 1 && !f->profiling && !f->downdateTC;
+        if (look) {
+            // Look-ahead: factor(c+1) only gathers the tile rows / columns of ITS landmarks (the band).  downdate(c) is split
+            // into the band tiles (urgent, f->stream) and all other lower tiles (deferred, f->stream3, beside factor(c+1)).
+            //   band(c)   after factor(c) [stream order] and rest(c-1) [event: both write the band of chunk c+1]
+            //   rest(c)   after factor(c) [event] and rest(c-1) [stream order]
+            //   factor(c+2) overwrites the Y buffer rest(c) reads: ordered through band(c+1)'s wait on rest(c)
+            while ((int)f->chunkEv.size() < 2 * nchunks) {
+                cudaEvent_t e;
+                CUDA_TRY(f, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                f->chunkEv.push_back(e);
+            }
+            double* Ybuf[2] = {f->d_Z, f->d_Y2};
+            const int* lo = f->h_lmOfSorted.data();
+            for (int c = 0; c < nchunks; ++c) {
+                const int j0 = c * bcMax;
+                const int bc = std::min(bcMax, nm - j0);
+                double* Yc = Ybuf[c & 1];
+                cudaEvent_t evF = f->chunkEv[2 * c], evR = f->chunkEv[2 * c + 1];
+                launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), sizeof(ChunkSmem), f->stream, f->Sig[f->cur], f->ld,
+                           dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Yc, f->d_status, guard, nullptr, TL_SLOT(f));
+                LAUNCH_CHECK(f, "chunk_factor_kernel");
+                std::swap(gin, gout);
+                if (c > 0) CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * (c - 1) + 1], 0));  // rest(c-1) done
+                if (c == nchunks - 1) {  // last chunk: everything, and full symmetric storage again
+                    chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Yc, guard,
+                                                                                              0, T, DD_ALL, T, TL_SLOT(f));
+                    LAUNCH_CHECK(f, "chunk_downdate_kernel");
+                    break;
+                }
+                const int nb = std::min(bcMax, nm - (j0 + bcMax));
+                int rmin = lo[j0 + bcMax], rmax = rmin;
+                for (int q = 1; q < nb; ++q) {
+                    rmin = std::min(rmin, lo[j0 + bcMax + q]);
+                    rmax = std::max(rmax, lo[j0 + bcMax + q]);
+                }
+                const int mlo = (SOFF + 3 * rmin) / DD_T, mhi = (SOFF + 3 * rmax + 2) / DD_T;
+                const int w = mhi - mlo + 1;
+                int nBand = w * (T - 1 - mhi);
+                for (int ti = mlo; ti <= mhi; ++ti) nBand += ti + 1;
+                const int nRest = (T - w) * (T - w + 1) / 2;
+                CUDA_TRY(f, cudaEventRecord(evF, f->stream));
+                chunk_downdate_kernel<<<nBand, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Yc, guard, mlo, mhi,
+                                                                                 DD_BAND, T, TL_SLOT(f));
+                LAUNCH_CHECK(f, "chunk_downdate_kernel");
+                CUDA_TRY(f, cudaStreamWaitEvent(f->stream3, evF, 0));
+                if (nRest > 0) {
+                    chunk_downdate_kernel<<<nRest, DD_THREADS, DD_SMEM, f->stream3>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Yc, guard, mlo,
+                                                                                      mhi, DD_REST, T, TL_SLOT(f));
+                    LAUNCH_CHECK(f, "chunk_downdate_kernel");
+                }
+                CUDA_TRY(f, cudaEventRecord(evR, f->stream3));
+            }
+        } else if (!pipe) {
             for (int j0 = 0; j0 < nm; j0 += bcMax) {
                 const int bc = std::min(bcMax, nm - j0);
                 int pk = prof_begin(f, PROF_PANEL);
-                chunk_factor_kernel<<<ldy / CH_COLS, CH_THREADS, sizeof(ChunkSmem), f->stream>>>(
-                    f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Y, f->d_status, guard, nullptr);
+                launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), sizeof(ChunkSmem), f->stream, f->Sig[f->cur], f->ld,
+                           dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Y, f->d_status, guard, nullptr, TL_SLOT(f));
                 prof_end(f, pk);
                 LAUNCH_CHECK(f, "chunk_factor_kernel");
                 int sk = prof_begin(f, PROF_SYRK);
@@ -1112,8 +1214,8 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
                         mlo = (SOFF + 3 * rmin) / DD_T;
                         mhi = (SOFF + 3 * rmax + 2) / DD_T;
                     }
-                    chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Y, guard,
-                                                                                              mlo, mhi);
+                    launch_pdl(f, chunk_downdate_kernel, dim3(T * (T + 1) / 2), dim3(DD_THREADS), DD_SMEM, f->stream, f->Sig[f->cur],
+                               f->Sig[f->cur], f->ld, Y, guard, mlo, mhi, (int)DD_ALL, T, TL_SLOT(f));
                     LAUNCH_CHECK(f, "chunk_downdate_kernel");
                 }
                 prof_end(f, sk);
@@ -1141,12 +1243,12 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
                 const int cfIn = c == 0 ? sin : 1 - sin;
                 chunk_factor_kernel<<<ldy / CH_COLS, CH_THREADS, sizeof(ChunkSmem), f->stream>>>(
                     f->Sig[cfIn], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Ybuf[c & 1], f->d_status, guard,
-                    c > 0 ? Ybuf[(c - 1) & 1] : nullptr);
+                    c > 0 ? Ybuf[(c - 1) & 1] : nullptr, TL_SLOT(f));
                 LAUNCH_CHECK(f, "chunk_factor_kernel");
                 CUDA_TRY(f, cudaEventRecord(evF, f->stream));
                 CUDA_TRY(f, cudaStreamWaitEvent(f->stream2, evF, 0));
                 chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream2>>>(f->Sig[sin], f->Sig[1 - sin], f->ld, Ybuf[c & 1],
-                                                                                           guard, 0, T);
+                                                                                           guard, 0, T, DD_ALL, T, TL_SLOT(f));
                 LAUNCH_CHECK(f, "chunk_downdate_kernel");
                 CUDA_TRY(f, cudaEventRecord(evD, f->stream2));
                 std::swap(gin, gout);
@@ -1158,7 +1260,8 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
         gammaFinal = gin;
     } else {
     meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
-                                                      s.useEquivariantOutput ? 1 : 0, f->d_Cblk, Z, ldz, m + dimp, guard, f->d_yIdx);
+                                                      s.useEquivariantOutput ? 1 : 0, f->d_Cblk, Z, ldz, m + dimp, guard, f->d_yIdx,
+                                                      nullptr, 0, nullptr, 0);
     LAUNCH_CHECK(f, "meas_kernel");
     zbuild_kernel<<<dim3(cdiv(dimp, 256), nm), 256, 0, f->stream>>>(f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, Z, ldz, m);
     LAUNCH_CHECK(f, "zbuild_kernel");
@@ -1203,7 +1306,11 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
 int vision_phase_c(eqvio_filter* f, int* did_update) {
     auto& P = f->pend;
     if (did_update) *did_update = 0;
-    CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+    {
+        const auto w0 = std::chrono::steady_clock::now();
+        CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+        f->hostWaitUs = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
+    }
     prof_collect(f);
     if (f->stageTiming && P.active) {
         for (int i = 0; i < 3; ++i) f->stageMs[i] = 0;
@@ -1307,7 +1414,9 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
     if (stream) {
         f->stream = static_cast<cudaStream_t>(stream);
     } else {
-        e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+        int prLeast = 0, prGreatest = 0;
+        e = cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&f->stream, cudaStreamNonBlocking, prGreatest);
         if (e != cudaSuccess) {
             g_createError = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
             delete f;
@@ -1512,6 +1621,7 @@ void eqvio_destroy(eqvio_filter* f) {
     cudaFree(f->d_Xs[0]);
     cudaFree(f->d_Xs[1]);
     if (f->stream2) cudaStreamDestroy(f->stream2);
+    if (f->stream3) cudaStreamDestroy(f->stream3);
     if (f->evFork) cudaEventDestroy(f->evFork);
     if (f->evJoin) cudaEventDestroy(f->evJoin);
     cudaFree(f->d_ctx);
@@ -1527,20 +1637,17 @@ void eqvio_destroy(eqvio_filter* f) {
     cudaFree(f->d_Gamma);
     cudaFree(f->d_Gamma2);
     cudaFree(f->d_ytilde);
-    cudaFree(f->d_gate);
     cudaFree(f->d_newP);
-    cudaFree(f->d_out);
     cudaFree(f->d_frame);
     cudaFree(f->d_hdrSteps);
     f->dense.release();
     if (f->h_frame) cudaFreeHost(f->h_frame);
     if (f->h_out) cudaFreeHost(f->h_out);
+    cudaFree(f->d_outblk);
     for (auto& g : f->graphs)
         if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     cudaFree(f->d_map);
     cudaFree(f->d_newIds);
-    cudaFree(f->d_status);
-    cudaFree(f->d_spec);
     for (int i = 0; i < 2; ++i)
         if (f->augEv[i]) cudaEventDestroy(f->augEv[i]);
     for (auto& A : f->arenaSets) {
@@ -1722,10 +1829,33 @@ int eqvio_process_vision(eqvio_filter* f, double stamp, int n, const int* ids, c
                          int* did_update) {
     ENTER(f);
     if (did_update) *did_update = 0;
+    using clk = std::chrono::steady_clock;
+    auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+    const auto t0 = clk::now();
     int rc = vision_phase_a(f, stamp, n, ids, y, cam);
+    const auto t1 = clk::now();
     if (rc == EQVIO_OK) rc = vision_phase_b(f);
+    const auto t2 = clk::now();
+    f->hostWaitUs = 0;
     int rc2 = vision_phase_c(f, did_update);
+    const auto t3 = clk::now();
+    f->hostUs[0] += us(t0, t1);
+    f->hostUs[1] += us(t1, t2);
+    f->hostUs[2] += f->hostWaitUs;
+    f->hostUs[3] += us(t2, t3) - f->hostWaitUs;
+    ++f->hostCalls;
     return rc != EQVIO_OK ? rc : rc2;
+}
+
+int eqvio_get_host_profile(eqvio_filter* f, int reset, double us[4], long long* calls) {
+    if (!f || !us) return EQVIO_ERR_INVALID_ARG;
+    for (int i = 0; i < 4; ++i) us[i] = f->hostUs[i];
+    if (calls) *calls = f->hostCalls;
+    if (reset) {
+        for (int i = 0; i < 4; ++i) f->hostUs[i] = 0;
+        f->hostCalls = 0;
+    }
+    return EQVIO_OK;
 }
 
 int eqvio_batch_process_vision(eqvio_filter* const* fs, int count, const double* stamps, const int* n, const int* const* ids,
@@ -1992,6 +2122,12 @@ int eqvio_get_kernel_profile(eqvio_filter* f, int reset, double ms[EQVIO_PROF_CL
     return EQVIO_OK;
 }
 
+static void clear_graphs(eqvio_filter* f) {
+    for (auto& g : f->graphs)
+        if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    f->graphs.clear();
+}
+
 int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
     if (!f) return EQVIO_ERR_INVALID_ARG;
     switch (key) {
@@ -2002,12 +2138,24 @@ int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
         case EQVIO_TUNE_DOWNDATE:
             if (value != 0 && value != 1) return EQVIO_ERR_INVALID_ARG;
             f->downdateTC = value;
-            for (auto& g : f->graphs)
-                if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
-            f->graphs.clear();
+            clear_graphs(f);
             return EQVIO_OK;
         case EQVIO_TUNE_PIPELINE:
             f->pipeline = value != 0;
+            clear_graphs(f);
+            return EQVIO_OK;
+        case EQVIO_TUNE_PDL:
+            f->pdl = value != 0;
+            clear_graphs(f);
+            return EQVIO_OK;
+        case EQVIO_TUNE_FUSE_OBSERVER:
+            f->fuseObserver = value != 0;
+            clear_graphs(f);
+            return EQVIO_OK;
+        case EQVIO_TUNE_LOOKAHEAD:
+            if (value < 0 || value > 2) return EQVIO_ERR_INVALID_ARG;
+            f->lookahead = value;
+            clear_graphs(f);
             return EQVIO_OK;
         case EQVIO_TUNE_GRAPH:
             f->useGraph = value != 0;
@@ -2023,6 +2171,27 @@ int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
             return EQVIO_ERR_INVALID_ARG;
     }
 }
+
+#ifdef EQVIO_TIMELINE
+// out[2 * slot] / out[2 * slot + 1] = first start / last end (globaltimer ns) of the chunk kernels launched since the last
+// reset, in launch order (factor, downdate parts ...); returns the number of slots used.  reset re-arms the stamps.
+int eqvio_debug_timeline(eqvio_filter* f, unsigned long long* out, int maxSlots, int reset) {
+    if (!f) return -1;
+    cudaStreamSynchronize(f->stream);
+    const int n = std::min(TL_MAX, maxSlots);  // graph replays keep the slots baked in at capture: the caller filters unstamped slots
+    if (out && n > 0) cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 2 * n);
+    if (reset) {
+        std::vector<unsigned long long> init(2 * TL_MAX);
+        for (int i = 0; i < TL_MAX; ++i) {
+            init[2 * i] = ~0ull;
+            init[2 * i + 1] = 0;
+        }
+        cudaMemcpyToSymbol(g_tl, init.data(), sizeof(unsigned long long) * 2 * TL_MAX);
+        f->tlNext = 0;
+    }
+    return n;
+}
+#endif
 
 #ifdef EQVIO_CHUNK_TIMING
 int eqvio_debug_chunk_timing(long long out[16]) {

@@ -155,7 +155,8 @@ HD void riccati_entry(const PrepArgs& a, const double* As, const double* Bs, int
 // (VIO_eqf.cpp:47-60, VIOGroup.cpp:190-271), X <- X * Lambda; records per segment what the landmark
 // part needs.  Serial by nature (each segment starts from the previous estimate).
 // ------------------------------------------------------------------------------------------------
-HD void observer_sensor_body(const PrepArgs& a) {
+template <class Publish>
+HD void observer_sensor_steps(const PrepArgs& a, Publish publish) {
     SensorState xi0 = unpack_sensor(a.xi0s);
     GroupSensor X = unpack_group(a.Xs);
     const int nsteps = a.fr->fs.nsteps;
@@ -195,7 +196,7 @@ HD void observer_sensor_body(const PrepArgs& a) {
             st.vC = V3{UB[3], UB[4], UB[5]};
             st.camChangeInv = se3_identity();
         }
-        a.steps[s] = st;
+        publish(s, st);
         // X <- X * Lambda (VIOGroup.cpp:71-92)
         GroupSensor Xn;
         for (int i = 0; i < 6; ++i) Xn.beta[i] = X.beta[i] + L.beta[i];
@@ -204,8 +205,14 @@ HD void observer_sensor_body(const PrepArgs& a) {
         Xn.w = X.w + qrot(X.A.q, L.w);
         X = Xn;
     }
-    pack_group(X, a.XsOut);
+    publish.finish(X);
 }
+struct PublishGlobal {  // two-kernel form: segments go to a.steps for observer_landmark_kernel
+    const PrepArgs& a;
+    HD void operator()(int s, const ObsStep& st) const { a.steps[s] = st; }
+    HD void finish(const GroupSensor& X) const { pack_group(X, a.XsOut); }
+};
+HD void observer_sensor_body(const PrepArgs& a) { observer_sensor_steps(a, PublishGlobal{a}); }
 
 __global__ void observer_sensor_kernel(PrepArgs a) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -215,9 +222,11 @@ __global__ void observer_sensor_kernel(PrepArgs a) {
 // One CTA: Riccati context (thread 0 builds the sparse A_s, B_s; 441 threads fill F_s, N_s) and, fused, the
 // sensor-sensor block  Sigma'_ss = F_s Sigma_ss F_s^T + N_s  plus the zero pad rows/cols of the sensor block.
 __global__ void __launch_bounds__(448)
-    riccati_prep_kernel(PrepArgs a, const double* __restrict__ Sin, double* __restrict__ Sout, int ld, double* __restrict__ dtBsOut) {
+    riccati_prep_kernel(PrepArgs a, const double* __restrict__ Sin, double* __restrict__ Sout, int ld, double* __restrict__ dtBsOut,
+                        int* __restrict__ clearFlag) {
     __shared__ double sAs[441], sBs[252], sF[441], sS[441], sT[441];
     const int t = threadIdx.x;
+    if (clearFlag && t == 447) *clearFlag = 0;  // first kernel of an update: re-arm the gate flag (no memset node)
     if (t == 0) riccati_small(a, sAs, sBs);
     if (t < 441) {
         const int r = t / 21, c = t % 21;
@@ -372,6 +381,83 @@ __global__ void observer_landmark_kernel(const double* __restrict__ lmIn, double
         lmOut[F_QA * cap + i] = a;
         idsOut[i] = idsIn[i];
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused observer integration (steady path, nsteps <= OBS_STAGE): the serial sensor chain and the per-landmark chain
+// run in ONE kernel as a software pipeline.  In every CTA lane 0 of warp 0 integrates the sensor part (redundantly per
+// CTA -- it is one thread of latency-bound work) and publishes each segment to shared memory through a release /
+// acquire counter; warps 1-2 (64 landmarks) consume segment s while the sensor thread is already on segment s + 1.
+// The update takes ~the sensor chain alone instead of sensor chain + landmark chain + a kernel boundary.
+// ------------------------------------------------------------------------------------------------
+constexpr int OBSF_LM = 64, OBSF_THREADS = 32 + OBSF_LM;
+__device__ __forceinline__ void flag_release_cta(int* p, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int flag_acquire_cta(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+struct PublishShared {
+    const PrepArgs& a;
+    ObsStep* s_steps;
+    int* ready;
+    bool writeGlobal;
+    __device__ void operator()(int s, const ObsStep& st) const {
+        s_steps[s] = st;
+        flag_release_cta(ready, s + 1);
+    }
+    __device__ void finish(const GroupSensor& X) const {
+        if (writeGlobal) pack_group(X, a.XsOut);
+    }
+};
+__global__ void __launch_bounds__(OBSF_THREADS)
+    observer_fused_kernel(PrepArgs a, const double* __restrict__ lmIn, double* __restrict__ lmOut, const int* __restrict__ idsIn,
+                          int* __restrict__ idsOut, int cap, int N) {
+    __shared__ ObsStep s_steps[OBS_STAGE];
+    __shared__ int s_ready;
+    if (threadIdx.x == 0) s_ready = 0;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) observer_sensor_steps(a, PublishShared{a, s_steps, &s_ready, blockIdx.x == 0});
+        return;
+    }
+    const int nsteps = a.fr->fs.nsteps;
+    const int i = blockIdx.x * OBSF_LM + (threadIdx.x - 32);
+    if (i >= N) return;
+    V3 q0 = V3{lmIn[F_Q0X * cap + i], lmIn[F_Q0Y * cap + i], lmIn[F_Q0Z * cap + i]};
+    Quat Q = Quat{lmIn[F_QW * cap + i], lmIn[F_QX * cap + i], lmIn[F_QY * cap + i], lmIn[F_QZ * cap + i]};
+    double a_ = lmIn[F_QA * cap + i];
+    const int id = idsIn[i];
+    for (int s = 0; s < nsteps; ++s) {
+        while (flag_acquire_cta(&s_ready) <= s) __nanosleep(20);
+        const ObsStep& st = s_steps[s];
+        V3 p0 = landmark_action(Q, a_, q0);
+        Quat LQ;
+        double La;
+        if (st.discrete) {  // same arithmetic as observer_landmark_kernel
+            V3 p1 = se3_apply(st.camChangeInv, p0);
+            LQ = quat_from_two_vectors(normalized(p1), normalized(p0));
+            La = norm(p0) / norm(p1);
+        } else {
+            double n2 = norm2(p0);
+            V3 wv = st.omegaC + cross(p0, st.vC) / n2;
+            LQ = so3_exp(st.dt * wv);
+            La = exp(st.dt * (dot(p0, st.vC) / n2));
+        }
+        Q = qmul(Q, LQ);
+        a_ = a_ * La;
+    }
+    lmOut[F_Q0X * cap + i] = q0.x;
+    lmOut[F_Q0Y * cap + i] = q0.y;
+    lmOut[F_Q0Z * cap + i] = q0.z;
+    lmOut[F_QW * cap + i] = Q.w;
+    lmOut[F_QX * cap + i] = Q.x;
+    lmOut[F_QY * cap + i] = Q.y;
+    lmOut[F_QZ * cap + i] = Q.z;
+    lmOut[F_QA * cap + i] = a_;
+    idsOut[i] = id;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -658,8 +744,12 @@ __global__ void fill_ll_diag_kernel(double* __restrict__ S, int ld, int n3, doub
 __global__ void meas_kernel(const double* __restrict__ lm, int cap, const int* __restrict__ lmOf, int n,
                             const double* __restrict__ y, const FrameHeader* __restrict__ fr, int coord, int useStar,
                             double* __restrict__ Cblk, double* __restrict__ Z, int ldz, int yrow,
-                            const int* __restrict__ guard, const int* __restrict__ yIdx) {
+                            const int* __restrict__ guard, const int* __restrict__ yIdx, int* __restrict__ zeroStatus, int nStatus,
+                            double* __restrict__ zeroGamma, int nGamma) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
+    // first kernel of the correction: clears the status words and the Gamma accumulator (also when the guard is set)
+    for (int t = j; t < nStatus; t += gridDim.x * blockDim.x) zeroStatus[t] = 0;
+    for (int t = j; t < nGamma; t += gridDim.x * blockDim.x) zeroGamma[t] = 0.0;
     if (j >= n || *guard) return;
     const int jm = yIdx ? yIdx[j] : j;  // row pair j of the correction takes the pixel of measurement jm
     const Camera cam = fr->cam;
@@ -957,6 +1047,31 @@ __device__ long long g_chunk_t[16];
 #else
 #define CH_STAMP(i) do { } while (0)
 #endif
+// Programmatic dependent launch: block until the preceding grid on the stream has completed and its writes are visible,
+// then let the NEXT grid be scheduled early (it blocks in its own pdl_wait).  No-ops for a plain launch.
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// Debug timeline (library built with -DEQVIO_TIMELINE): first-start / last-end globaltimer stamps per launch slot of the
+// chunk kernels, read back by eqvio_debug_timeline -- shows how the look-ahead launches overlap on the device.
+#ifdef EQVIO_TIMELINE
+constexpr int TL_MAX = 512;
+__device__ unsigned long long g_tl[2 * TL_MAX];
+__device__ __forceinline__ void tl_mark(int slot, int end) {
+    if (threadIdx.x == 0 && slot >= 0 && slot < TL_MAX) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (end)
+            atomicMax(&g_tl[2 * slot + 1], t);
+        else
+            atomicMin(&g_tl[2 * slot], t);
+    }
+}
+#define TL_MARK(slot, end) tl_mark(slot, end)
+#else
+#define TL_MARK(slot, end) do { } while (0)
+#endif
 // progress flag between the two warp groups of chunk_factor_kernel: release store / acquire load at CTA scope
 __device__ __forceinline__ void flag_release(int* p, int v) {
     asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
@@ -982,8 +1097,10 @@ __global__ void __launch_bounds__(CH_THREADS)
     chunk_factor_kernel(const double* __restrict__ Sig, int ld, int dimp, const int* __restrict__ lmOf,
                         const double* __restrict__ Cblk, const double* __restrict__ ytilde, int j0, int bc, double r2,
                         const double* __restrict__ GammaIn, double* __restrict__ GammaOut, double* __restrict__ Y,
-                        int* __restrict__ status, const int* __restrict__ guard, const double* __restrict__ Yprev) {
+                        int* __restrict__ status, const int* __restrict__ guard, const double* __restrict__ Yprev, int tl) {
+    pdl_wait();
     if (*guard) return;
+    TL_MARK(tl, 0);
     extern __shared__ __align__(16) unsigned char chunk_smem_raw[];
     ChunkSmem& sm = *reinterpret_cast<ChunkSmem*>(chunk_smem_raw);
     const int tid = threadIdx.x;
@@ -1318,6 +1435,7 @@ __global__ void __launch_bounds__(CH_THREADS)
         GammaOut[sbase + tid] = GammaIn[sbase + tid] + g;  // ping-pong: other CTAs may still be reading GammaIn
     }
     CH_STAMP(6);
+    TL_MARK(tl, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1332,6 +1450,7 @@ __global__ void __launch_bounds__(CH_THREADS)
 // ------------------------------------------------------------------------------------------------
 constexpr int DD_T = 64, DD_LD = YB_LD, DD_THREADS = 128;
 constexpr int DD_SMEM = 2 * DD_T * DD_LD * 8 + 16;
+enum { DD_ALL = 0, DD_BAND = 1, DD_REST = 2 };  // which tiles a launch of chunk_downdate_kernel covers
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -1361,10 +1480,35 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 __global__ void __launch_bounds__(DD_THREADS, 3)
     chunk_downdate_kernel(const double* SigIn, double* SigOut, int ld, const double* __restrict__ Y,
-                          const int* __restrict__ guard, int mirrorLo, int mirrorHi) {
+                          const int* __restrict__ guard, int mirrorLo, int mirrorHi, int mode, int T, int tl) {
+    pdl_wait();
     if (*guard) return;
+    TL_MARK(tl, 0);
     int ti, tj;
-    tri_decode(blockIdx.x, ti, tj);  // lower-triangular tile index -> (ti, tj), ti >= tj
+    if (mode == DD_ALL) {
+        tri_decode(blockIdx.x, ti, tj);  // lower-triangular tile index -> (ti, tj), ti >= tj
+    } else if (mode == DD_BAND) {
+        // look-ahead split, urgent part: the lower tiles that meet the band [mirrorLo, mirrorHi] of tile rows / columns
+        // the NEXT chunk gathers from -- first the band's tile rows (mirrored into the band's tile columns above the
+        // diagonal), then the band's tile columns below the band
+        int b = blockIdx.x;
+        ti = mirrorLo;
+        while (ti <= mirrorHi && b >= ti + 1) b -= ++ti;  // rows mirrorLo.. hold ti + 1 tiles each
+        if (ti <= mirrorHi) {
+            tj = b;
+        } else {
+            const int below = T - 1 - mirrorHi;
+            tj = mirrorLo + b / below;
+            ti = mirrorHi + 1 + b % below;
+        }
+    } else {
+        // look-ahead split, deferred part: the lower tiles with neither index in the band (runs beside the next factor)
+        int ci, cj;
+        tri_decode(blockIdx.x, ci, cj);
+        const int w = mirrorHi - mirrorLo + 1;
+        ti = ci < mirrorLo ? ci : ci + w;
+        tj = cj < mirrorLo ? cj : cj + w;
+    }
     extern __shared__ __align__(16) unsigned char dd_smem_raw[];
     double(*sA)[DD_LD] = reinterpret_cast<double(*)[DD_LD]>(dd_smem_raw);
     double(*sB)[DD_LD] = sA + DD_T;
@@ -1427,6 +1571,7 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
                 *reinterpret_cast<double2*>(SigOut + (size_t)(i0 + fr + a * 8) * ld + j0 + fc + b * 8) = t;
             }
         }
+    TL_MARK(tl, 1);
 }
 
 // ------------------------------------------------------------------------------------------------

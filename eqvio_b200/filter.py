@@ -344,7 +344,8 @@ class VIOFilter:
         self._check(lib.eqvio_get_stage_ms(self._h, _pd(ms)))
         return dict(propagation=ms[0], preprocessing=ms[1], correction=ms[2])
 
-    def setTuning(self, correction=None, chunkLandmarks=None, speculate=None, graph=None, pipeline=None, downdate=None):
+    def setTuning(self, correction=None, chunkLandmarks=None, speculate=None, graph=None, pipeline=None, downdate=None,
+                  lookahead=None, fuseObserver=None, pdl=None):
         """Evaluation-order knobs (eqvio_set_tuning): correction 0 = sequential chunks, 1 = batch sweep."""
         if speculate is not None:
             self._check(lib.eqvio_set_tuning(self._h, 2, int(speculate)))
@@ -354,10 +355,24 @@ class VIOFilter:
             self._check(lib.eqvio_set_tuning(self._h, 4, int(pipeline)))
         if downdate is not None:  # 0 = fp64 DMMA, 1 = tcgen05 split-bf16 / fp32 accumulate
             self._check(lib.eqvio_set_tuning(self._h, 5, int(downdate)))
+        if pdl is not None:
+            self._check(lib.eqvio_set_tuning(self._h, 8, int(pdl)))
+        if fuseObserver is not None:
+            self._check(lib.eqvio_set_tuning(self._h, 7, int(fuseObserver)))
+        if lookahead is not None:  # 1 = split downdates (band / rest) overlapped with the next chunk's factor kernel
+            self._check(lib.eqvio_set_tuning(self._h, 6, int(lookahead)))
         if correction is not None:
             self._check(lib.eqvio_set_tuning(self._h, 0, int(correction)))
         if chunkLandmarks is not None:
             self._check(lib.eqvio_set_tuning(self._h, 1, int(chunkLandmarks)))
+
+    def hostProfile(self, reset=True):
+        """Host-side microseconds per processVisionData call since the last reset (eqvio_get_host_profile)."""
+        us = np.zeros(4)
+        calls = C.c_longlong(0)
+        self._check(lib.eqvio_get_host_profile(self._h, int(reset), _pd(us), C.byref(calls)))
+        n = max(int(calls.value), 1)
+        return dict(enqueue_us=us[0] / n, decisions_us=us[1] / n, device_wait_us=us[2] / n, finish_us=us[3] / n, calls=int(calls.value))
 
     def launchCount(self):
         return int(lib.eqvio_get_launch_count(self._h))

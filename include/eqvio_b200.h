@@ -180,6 +180,10 @@ int eqvio_enable_kernel_profile(eqvio_filter* f, int on);
 /* Accumulated ms and launch counts per class since the last reset. */
 int eqvio_get_kernel_profile(eqvio_filter* f, int reset, double ms[EQVIO_PROF_CLASSES],
                              long long launches[EQVIO_PROF_CLASSES]);
+/* Host-side time of eqvio_process_vision since the last reset, microseconds summed over `calls` calls:
+ * us[0] phase A (id matching, frame staging, enqueue / graph launch), us[1] phase B (host decisions of a non-steady
+ * frame), us[2] waiting for the device, us[3] the rest of phase C (status check, bookkeeping). */
+int eqvio_get_host_profile(eqvio_filter* f, int reset, double us[4], long long* calls);
 /* Evaluation-order knobs of the correction (results agree to rounding; tests run both).
  *   EQVIO_TUNE_CORRECTION: 0 = sequential landmark chunks exploiting C's block sparsity (default),
  *                          1 = batch form: Cholesky sweep over [S; W^T; ytilde^T], then Sigma -= Y^T Y.
@@ -205,6 +209,18 @@ int eqvio_get_kernel_profile(eqvio_filter* f, int reset, double ms[EQVIO_PROF_CL
  *                         mantissa), fp32 accumulation in TMEM, Sigma itself stays fp64.  Parity with the fp64 path
  *                         is ~1e-7 per update instead of ~1e-15. */
 #define EQVIO_TUNE_DOWNDATE 5
+/*   EQVIO_TUNE_LOOKAHEAD: 2 (default) = automatic: 1 when the tile grid of Sigma spans more than one wave (>= 24 tile
+ *                         rows, N >= ~500), else 0.  1 = each chunk's downdate is split into the tiles the NEXT chunk gathers from
+ *                         (its landmarks' tile rows / columns; launched at once) and the remaining lower tiles, which run
+ *                         on a second stream beside the next chunk's factor kernel; 0 = one downdate launch per chunk,
+ *                         strictly in order.  Same arithmetic per tile either way (bit-identical results). */
+#define EQVIO_TUNE_LOOKAHEAD 6
+/*   EQVIO_TUNE_FUSE_OBSERVER: 1 (default) = integrateObserverState's serial sensor chain and per-landmark chain run as one
+ *                         software-pipelined kernel; 0 = two kernels.  Same arithmetic (bit-identical results). */
+#define EQVIO_TUNE_FUSE_OBSERVER 7
+/*   EQVIO_TUNE_PDL: 1 (default) = the chunk kernels are launched with programmatic dependent launch allowed (the next
+ *                         grid is scheduled while its predecessor drains and blocks in griddepcontrol.wait); 0 = plain. */
+#define EQVIO_TUNE_PDL 8
 int eqvio_set_tuning(eqvio_filter* f, int key, int value);
 /* Version / build info string (arch the kernels were compiled for). */
 const char* eqvio_build_info(void);

@@ -32,6 +32,7 @@ def step(fr):
 
 for fr in sm.frames[:20]:
     step(fr)
+flt.hostProfile(reset=True)
 t = {"imu": 0.0, "aug": 0.0, "vis": 0.0, "est": 0.0}
 for fr in sm.frames[20:70]:
     t0 = time.perf_counter(); flt.processIMUArray(fr.imu)
@@ -41,6 +42,7 @@ for fr in sm.frames[20:70]:
     t4 = time.perf_counter()
     t["imu"] += t1 - t0; t["aug"] += t2 - t1; t["vis"] += t3 - t2; t["est"] += t4 - t3
 print({k: round(1e6 * v / 50, 1) for k, v in t.items()}, "us per step; total", round(1e6 * sum(t.values()) / 50, 1))
+print("inside eqvio_process_vision:", {k: round(v, 1) for k, v in flt.hostProfile().items()})
 pr = cProfile.Profile()
 pr.enable()
 for fr in sm.frames[70:120]:

@@ -1,0 +1,42 @@
+"""Device timeline of the chunk kernels of ONE steady update (globaltimer stamps, first start / last end per launch).
+Needs a library built with -DEQVIO_TIMELINE:
+    nvcc <flags of __graft_entry__> -DEQVIO_TIMELINE -o eqvio_b200/lib/libeqvio_b200_tl.so eqvio_b200/csrc/filter.cu -ldl
+    EQVIO_B200_LIB=eqvio_b200/lib/libeqvio_b200_tl.so python scripts/timeline.py [N] [lookahead 0|1] [graph 0|1]"""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+import eqvio_b200 as eb
+from eqvio_b200 import _capi
+from simdata import SimConfig, record_stream
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+look = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+graph = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+sm = record_stream(SimConfig.benchmark(N, 0), 14)
+flt = eb.VIOFilter(eb.Settings(fastRiccati=1), eb.VIOState(eb.VIOSensorState.fromFlat(sm.init_sensor), sm.init_p, sm.init_ids), 0.0,
+                   capacity=N + 8)
+flt.setTuning(graph=graph, lookahead=look)
+cam = eb.Camera(**sm.camera)
+fn = _capi.lib.eqvio_debug_timeline
+fn.restype = C.c_int
+fn.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int, C.c_int]
+buf = (C.c_ulonglong * 1024)()
+for k, fr in enumerate(sm.frames):
+    flt.processIMUArray(fr.imu)
+    flt.augmentLandmarkStates(fr.ids, eb.VIOState(eb.VIOSensorState(), fr.provided_p, fr.ids))
+    if k == len(sm.frames) - 1:
+        fn(flt._h, buf, 512, 1)
+    flt.processVisionArrays(fr.stamp, fr.ids, fr.y, cam)
+n = fn(flt._h, buf, 512, 0)
+t = np.array(buf[:2 * n], dtype=np.float64).reshape(n, 2)
+t = t[t[:, 1] > 0]  # slots stamped since the reset (a replayed graph keeps the slot numbers of its capture)
+n = len(t)
+t0 = t[:, 0].min()
+print(f"N={N} lookahead={look} graph={graph}: {n} launches, span {(t[:, 1].max() - t0) / 1e3:.1f} us")
+for i in range(n):
+    print(f"{i:3d}  start {(t[i, 0] - t0) / 1e3:8.1f}  end {(t[i, 1] - t0) / 1e3:8.1f}  dur {(t[i, 1] - t[i, 0]) / 1e3:6.1f}")

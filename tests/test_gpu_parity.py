@@ -28,6 +28,33 @@ def _check(gpu, ref, tol=TOL):
     return worst
 
 
+@pytest.mark.parametrize("discrete", [1, 0])
+def test_fused_observer_matches_two_kernel_form(discrete):
+    """integrateObserverState as one software-pipelined kernel (sensor chain publishing segments to the landmark warps)
+    vs the sensor kernel followed by the landmark kernel: same arithmetic, checked against each other and the oracle."""
+    stream = make_stream(N=70, frames=8, coord=0, settings_overrides=dict(useDiscreteVelocityLift=bool(discrete)))
+    ref = run_gpu(stream, tuning=dict(fuseObserver=0))
+    got = run_gpu(stream, tuning=dict(fuseObserver=1))
+    for g, r in zip(got, ref):
+        e = compare_states(g, r)
+        assert e["ids_equal"] and e["sigma"] < 1e-13 and e["state"] < 1e-13
+    _check(got, run_oracle(stream))
+
+
+@pytest.mark.parametrize("N,chunk", [(40, 8), (100, 32), (150, 32)])
+@pytest.mark.parametrize("graph", [0, 1])
+def test_lookahead_downdate_is_bit_identical(N, chunk, graph):
+    """The look-ahead split (band tiles at once, the other tiles beside the next factor kernel on a second stream)
+    runs the same arithmetic per tile as one in-order downdate per chunk: identical bits, with and without graphs."""
+    stream = make_stream(N=N, frames=8, coord=0)
+    ref = run_gpu(stream, tuning=dict(lookahead=0, graph=0, chunkLandmarks=chunk))
+    got = run_gpu(stream, tuning=dict(lookahead=1, graph=graph, chunkLandmarks=chunk))
+    for g, r in zip(got, ref):
+        e = compare_states(g, r)
+        assert e["ids_equal"] and e["sigma"] == 0.0 and e["state"] == 0.0
+    _check(got, run_oracle(stream))
+
+
 @pytest.mark.parametrize("coord", [0, 1])
 @pytest.mark.parametrize("N", [8, 64])
 def test_sequence_matches_oracle(N, coord):
@@ -45,7 +72,7 @@ def test_correction_evaluation_orders_agree(tuning):
     _check(run_gpu(stream, tuning=tuning), ref)
 
 
-@pytest.mark.parametrize("tuning", [dict(graph=0), dict(graph=0, speculate=0), dict(graph=1)])
+@pytest.mark.parametrize("tuning", [dict(graph=0), dict(graph=0, speculate=0), dict(graph=1), dict(graph=1, pdl=0), dict(graph=0, pdl=0)])
 def test_steady_path_variants_agree(tuning):
     """CUDA-graph replay, plain speculative launches and the wait-for-the-gate path give identical results
     (same kernels, same order), over enough frames for graphs to be captured AND replayed."""
