@@ -111,8 +111,13 @@ struct eqvio_filter {
     unsigned char* d_Ysplit = nullptr;
     int lazyMirror = 1;  // downdate refreshes the upper triangle only where the next chunk reads it
     std::vector<int> h_lmOfSorted;  // state indices of the correction rows (host copy of d_lmOf)
+    int chain = 0;         // 0 = off (default); 2 = chained correction kernels in stream order; 1 = with concurrent downdates (experimental)
+    int* d_cnt = nullptr;  // per-chunk completion counters of the downdates (chained correction)
+    double* d_Snext[2] = {nullptr, nullptr};  // S block handed from one factor launch to the next
+    bool pdlHold = false;  // next launch_pdl is a plain launch (its predecessor produces what the kernel reads before its wait)
     int pdl = 1;           // chunk kernels are launched with programmatic dependent launch allowed
     int fuseObserver = 1;  // sensor + landmark parts of the observer integration as one software-pipelined kernel
+    const char* tlNames[512] = {nullptr};
     int tlNext = 0;  // debug timeline slot counter (EQVIO_TIMELINE builds)
     double hostUs[4] = {0, 0, 0, 0};  // process_vision host time: phase A (plan + enqueue), phase B, wait for the device, rest of phase C
     long long hostCalls = 0;
@@ -261,8 +266,16 @@ int check_launch(eqvio_filter* f, const char* what) {
         return EQVIO_ERR_CUDA;
     }
     ++f->launches;
+#ifdef EQVIO_TIMELINE
+    if (f->tlNext > 0 && f->tlNext <= 512) f->tlNames[f->tlNext - 1] = what;  // the slot TL_SLOT handed to this launch
+#endif
     return EQVIO_OK;
 }
+#ifdef EQVIO_TIMELINE
+#define TL_SLOT(f) ((f)->tlNext++)
+#else
+#define TL_SLOT(f) (-1)
+#endif
 #define LAUNCH_CHECK(f, what)                          \
     do {                                               \
         int rc_ = check_launch((f), (what));           \
@@ -281,7 +294,7 @@ cudaError_t launch_pdl(eqvio_filter* f, void (*kernel)(KArgs...), dim3 grid, dim
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = f->pdl ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = (f->pdl && !f->pdlHold) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
@@ -444,6 +457,9 @@ int alloc_device(eqvio_filter* f) {
     f->d_spec = reinterpret_cast<int*>(f->d_outblk + f->outOffSpec);
     f->d_status = reinterpret_cast<int*>(f->d_outblk + f->outOffStatus);
     f->d_out = reinterpret_cast<double*>(f->d_outblk + f->outOffEst);
+    CUDA_TRY(f, cudaMalloc(&f->d_cnt, 2 * (c1 + 1) * sizeof(int)));
+    CUDA_TRY(f, cudaMemsetAsync(f->d_cnt, 0, 2 * (c1 + 1) * sizeof(int), f->stream));
+    for (int k = 0; k < 2; ++k) CUDA_TRY(f, cudaMalloc(&f->d_Snext[k], CH_R * CH_R * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_map, c1 * sizeof(int)));
     CUDA_TRY(f, cudaMalloc(&f->d_newIds, c1 * sizeof(int)));
     for (int i = 0; i < 2; ++i) CUDA_TRY(f, cudaEventCreate(&f->augEv[i]));
@@ -627,14 +643,14 @@ int enqueue_propagation(eqvio_filter* f) {
     const int nsteps = reinterpret_cast<const FrameHeader*>(f->h_frame)->fs.nsteps;
     if (N > 0 && nsteps <= OBS_STAGE && f->fuseObserver) {
         observer_fused_kernel<<<cdiv(N, OBSF_LM), OBSF_THREADS, 0, f->stream2>>>(a, f->lm[f->lmcur], f->lm[1 - f->lmcur], f->dids[f->lmcur],
-                                                                                 f->dids[1 - f->lmcur], f->cap, N);
+                                                                                 f->dids[1 - f->lmcur], f->cap, N, TL_SLOT(f));
         LAUNCH_CHECK(f, "observer_fused_kernel");
     } else {
-        observer_sensor_kernel<<<1, 32, 0, f->stream2>>>(a);
+        observer_sensor_kernel<<<1, 32, 0, f->stream2>>>(a, TL_SLOT(f));
         LAUNCH_CHECK(f, "observer_sensor_kernel");
         if (N > 0) {
             observer_landmark_kernel<<<cdiv(N, 64), 64, 0, f->stream2>>>(f->lm[f->lmcur], f->lm[1 - f->lmcur], f->dids[f->lmcur],
-                                                                         f->dids[1 - f->lmcur], f->cap, N, f->d_steps, f->d_hdr);
+                                                                         f->dids[1 - f->lmcur], f->cap, N, f->d_steps, f->d_hdr, TL_SLOT(f));
             LAUNCH_CHECK(f, "observer_landmark_kernel");
         }
     }
@@ -642,16 +658,16 @@ int enqueue_propagation(eqvio_filter* f) {
     {
         const double* Sin = f->Sig[f->cur];
         double* Sout = f->Sig[1 - f->cur];
-        riccati_prep_kernel<<<1, 448, 0, f->stream>>>(a, Sin, Sout, f->ld, nullptr, f->d_spec);  // also re-arms the gate flag
+        riccati_prep_kernel<<<1, 448, 0, f->stream>>>(a, Sin, Sout, f->ld, nullptr, f->d_spec, TL_SLOT(f));  // also re-arms the gate flag
         LAUNCH_CHECK(f, "riccati_prep_kernel");
         if (N > 0) {
-            landmark_rows_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_ctx, s.coordinateChoice, f->d_rows);
+            landmark_rows_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_ctx, s.coordinateChoice, f->d_rows, TL_SLOT(f));
             LAUNCH_CHECK(f, "landmark_rows_kernel");
-            prop_strip_kernel<<<cdiv(N, PS_LM), PS_LM * PS_TPL, 0, f->stream>>>(Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv);
+            prop_strip_kernel<<<cdiv(N, PS_LM), PS_LM * PS_TPL, 0, f->stream>>>(Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv, TL_SLOT(f));
             LAUNCH_CHECK(f, "prop_strip_kernel");
             const int nt = cdiv(N, TP);
             int pk = prof_begin(f, PROF_PROP_LL);
-            prop_ll_kernel<<<dim3(nt, nt), dim3(TP, TP), 0, f->stream>>>(Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv);
+            prop_ll_kernel<<<dim3(nt, nt), dim3(TP, TP), 0, f->stream>>>(Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv, TL_SLOT(f));
             prof_end(f, pk);
             LAUNCH_CHECK(f, "prop_ll_kernel");
         }
@@ -712,10 +728,10 @@ int enqueue_propagation_accurate(eqvio_filter* f) {
             const double* Sin = f->Sig[f->cur];
             double* Sout = f->Sig[1 - f->cur];
             double *M = w.buf[0], *P0 = w.buf[1], *T = w.buf[2], *P1 = w.buf[3], *R = w.buf[8];
-            riccati_prep_kernel<<<1, 448, 0, f->stream>>>(a, Sin, Sout, f->ld, w.dtBs, nullptr);
+            riccati_prep_kernel<<<1, 448, 0, f->stream>>>(a, Sin, Sout, f->ld, w.dtBs, nullptr, TL_SLOT(f));
             LAUNCH_CHECK(f, "riccati_prep_kernel");
             if (N > 0) {
-                landmark_rows_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_ctx, s.coordinateChoice, f->d_rows);
+                landmark_rows_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_ctx, s.coordinateChoice, f->d_rows, TL_SLOT(f));
                 LAUNCH_CHECK(f, "landmark_rows_kernel");
             }
             CUDA_TRY(f, cudaMemsetAsync(M, 0, (size_t)n * n * sizeof(double), f->stream));
@@ -745,11 +761,11 @@ int enqueue_propagation_accurate(eqvio_filter* f) {
             LAUNCH_CHECK(f, "dense_unpack_sigma_kernel");
             f->cur = 1 - f->cur;
         }
-        observer_sensor_kernel<<<1, 32, 0, f->stream>>>(a);
+        observer_sensor_kernel<<<1, 32, 0, f->stream>>>(a, TL_SLOT(f));
         LAUNCH_CHECK(f, "observer_sensor_kernel");
         if (N > 0) {
             observer_landmark_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(f->lm[f->lmcur], f->lm[1 - f->lmcur], f->dids[f->lmcur],
-                                                                        f->dids[1 - f->lmcur], f->cap, N, f->d_steps + i, f->d_hdrSteps + i);
+                                                                        f->dids[1 - f->lmcur], f->cap, N, f->d_steps + i, f->d_hdrSteps + i, TL_SLOT(f));
             LAUNCH_CHECK(f, "observer_landmark_kernel");
             f->lmcur = 1 - f->lmcur;
         }
@@ -762,17 +778,12 @@ int enqueue_gate(eqvio_filter* f, int N, bool clearFlag) {
     if (clearFlag) CUDA_TRY(f, cudaMemsetAsync(f->d_spec, 0, sizeof(int), f->stream));
     gate_kernel<<<cdiv(N, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->Sig[f->cur], f->ld, f->d_measIdx, f->d_y,
                                                       f->d_hdr, f->st.coordinateChoice, f->d_gate, f->st.outlierThresholdAbs,
-                                                      f->st.outlierThresholdProb, f->d_spec);
+                                                      f->st.outlierThresholdProb, f->d_spec, TL_SLOT(f));
     LAUNCH_CHECK(f, "gate_kernel");
     return EQVIO_OK;
 }
 
 int enqueue_correction(eqvio_filter* f, int nm, const int* guard);
-#ifdef EQVIO_TIMELINE
-#define TL_SLOT(f) ((f)->tlNext++)
-#else
-#define TL_SLOT(f) (-1)
-#endif
 
 // The whole device side of a steady frame (no landmark enters or leaves before the gate): frame upload,
 // propagation, gate, guarded correction, result downloads into the fixed pinned block.  Issued either directly
@@ -784,7 +795,7 @@ int enqueue_steady_update(eqvio_filter* f, int N, int nm) {
     if ((rc = enqueue_gate(f, N, false)) != EQVIO_OK) return rc;  // riccati_prep_kernel re-armed the flag
     if ((rc = enqueue_correction(f, nm, f->d_spec)) != EQVIO_OK) return rc;
     // stateEstimate() is what every caller asks for next (main_opt.cpp:225, main_sim.cpp:146): produce it here
-    state_estimate_kernel<<<cdiv(N, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_xi0s, f->d_Xs[f->xcur], f->d_out);
+    state_estimate_kernel<<<cdiv(N, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_xi0s, f->d_Xs[f->xcur], f->d_out, TL_SLOT(f));
     LAUNCH_CHECK(f, "state_estimate_kernel");
     // one download: gate scalars, gate flag, status words, state estimate (the block has the layout of h_out)
     CUDA_TRY(f, cudaMemcpyAsync(f->h_out, f->d_outblk, f->outOffEst + (23 + 3 * (size_t)N) * sizeof(double), cudaMemcpyDeviceToHost,
@@ -1119,16 +1130,91 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
         double* Y = f->d_Z;
         double* gin = f->d_Gamma;
         double* gout = f->d_Gamma2;
+        const int nchunksAll = cdiv(nm, std::max(1, std::min(f->chunkLm, CH_R / 2)));
         // also clears the status words and Gamma (no memset nodes between the kernels of the update)
         meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
                                                           s.useEquivariantOutput ? 1 : 0, f->d_Cblk, f->d_ytilde, 1, 0, guard, f->d_yIdx,
-                                                          f->d_status, 1 + Nn, gin, dimp);
+                                                          f->d_status, 1 + Nn, gin, dimp, f->d_cnt, 2 * nchunksAll, TL_SLOT(f));
         LAUNCH_CHECK(f, "meas_kernel");
         const int bcMax = std::max(1, std::min(f->chunkLm, CH_R / 2));
         const int nchunks = cdiv(nm, bcMax);
         const bool pipe = f->pipeline && nchunks > 1 && !f->profiling;
         const bool look = !pipe && (f->lookahead == 1 || (f->lookahead == 2 && T >= 24)) && nchunks > 1 && !f->profiling && !f->downdateTC;
-        if (look) {
+        const bool chain = f->chain != 0 && !pipe && !f->downdateTC;
+        if (chain) {
+            // Chained correction (see chunk_factor2_kernel).  Three streams:
+            //   f->stream2: look(c)    after look(c-1) [stream order]; its RHS warps after downdate(c-1) [counter]
+            //   f->stream : factor(c)  after factor(c-1) [stream order] and look(c-1) [event: S_c]; RHS warps after downdate(c-1)
+            //   f->stream3: downdate(c) after factor(c) [event] and downdate(c-1) [stream order]
+            // Y buffers alternate: factor(c+2) writes Y_{c&1} after its RHS warps saw downdate(c+1) (hence downdate(c)) done;
+            // the S hand-over buffers alternate the same way (look(c+2) finishes after downdate(c+1), i.e. after factor(c+1)).
+            const bool serial = f->chain == 2 || f->profiling;  // serial: one stream, no counter waits
+            while ((int)f->chunkEv.size() < 2 * nchunks + 2) {
+                cudaEvent_t e;
+                CUDA_TRY(f, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                f->chunkEv.push_back(e);
+            }
+            double* Ybuf[2] = {f->d_Z, f->d_Y2};
+            const int* lo = f->h_lmOfSorted.data();
+            const int nTiles = T * (T + 1) / 2;
+            cudaStream_t sLook = serial ? f->stream : f->stream2, sDown = serial ? f->stream : f->stream3;
+            if (!serial && nchunks > 1) {  // fork: the look-ahead stream starts behind everything enqueued so far
+                CUDA_TRY(f, cudaEventRecord(f->chunkEv[2 * nchunks], f->stream));
+                CUDA_TRY(f, cudaStreamWaitEvent(f->stream2, f->chunkEv[2 * nchunks], 0));
+            }
+            for (int c = 0; c < nchunks; ++c) {
+                const int j0 = c * bcMax;
+                const int bc = std::min(bcMax, nm - j0);
+                const int nb = c + 1 < nchunks ? std::min(bcMax, nm - (j0 + bcMax)) : 0;
+                double* Yc = Ybuf[c & 1];
+                const int* waitCnt = (c > 0 && !serial) ? f->d_cnt + (c - 1) : nullptr;
+                const double* Sin = c > 0 ? f->d_Snext[c & 1] : nullptr;
+                if (nb > 0) {
+                    f->pdlHold = c == 0;
+                    launch_pdl(f, chunk_factor2_kernel<true>, dim3(1), dim3(LOOK_THREADS), LOOK_SMEM, sLook,
+                               (const double*)f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, nb, r2, (const double*)nullptr,
+                               (double*)nullptr, (double*)nullptr, f->d_status, guard, Sin, f->d_Snext[(c + 1) & 1], waitCnt, nTiles,
+                               serial ? (int*)nullptr : f->d_cnt + nchunks + c, TL_SLOT(f));
+                    f->pdlHold = false;
+                    LAUNCH_CHECK(f, "chunk_look_kernel");
+                    if (!serial) CUDA_TRY(f, cudaEventRecord(f->chunkEv[2 * c + 1], f->stream2));
+                }
+                if (c > 0 && !serial) CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * (c - 1) + 1], 0));  // S_c from look(c-1)
+                int pk = prof_begin(f, PROF_PANEL);
+                f->pdlHold = c == 0;  // chunk 0 follows meas_kernel, whose Cblk the kernel reads ahead of its dependency wait
+                launch_pdl(f, chunk_factor2_kernel<false>, dim3(ldy / CH_COLS), dim3(CH_THREADS), sizeof(Chunk2Smem), f->stream,
+                           (const double*)f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, nb, r2, (const double*)gin, gout, Yc,
+                           f->d_status, guard, Sin, (double*)nullptr, waitCnt, nTiles, (int*)nullptr, TL_SLOT(f));
+                f->pdlHold = false;
+                prof_end(f, pk);
+                LAUNCH_CHECK(f, "chunk_factor2_kernel");
+                std::swap(gin, gout);
+                int mlo = 0, mhi = T;
+                if (nb > 0 && f->lazyMirror) {
+                    int rmin = lo[j0 + bcMax], rmax = rmin;
+                    for (int q = 1; q < nb; ++q) {
+                        rmin = std::min(rmin, lo[j0 + bcMax + q]);
+                        rmax = std::max(rmax, lo[j0 + bcMax + q]);
+                    }
+                    mlo = (SOFF + 3 * rmin) / DD_T;
+                    mhi = (SOFF + 3 * rmax + 2) / DD_T;
+                }
+                int sk = prof_begin(f, PROF_SYRK);
+                if (!serial) {
+                    CUDA_TRY(f, cudaEventRecord(f->chunkEv[2 * c], f->stream));
+                    CUDA_TRY(f, cudaStreamWaitEvent(f->stream3, f->chunkEv[2 * c], 0));
+                }
+                launch_pdl(f, chunk_downdate_kernel, dim3(nTiles), dim3(DD_THREADS), DD_SMEM, sDown, (const double*)f->Sig[f->cur], f->Sig[f->cur],
+                           f->ld, (const double*)Yc, guard, mlo, mhi, (int)DD_ALL, T, TL_SLOT(f), serial ? (int*)nullptr : f->d_cnt + c,
+                           (!serial && nb > 0) ? (const int*)(f->d_cnt + nchunks + c) : (const int*)nullptr);
+                prof_end(f, sk);
+                LAUNCH_CHECK(f, "chunk_downdate_kernel");
+            }
+            if (!serial) {
+                CUDA_TRY(f, cudaEventRecord(f->chunkEv[2 * nchunks + 1], f->stream3));
+                CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * nchunks + 1], 0));
+            }
+        } else if (look) {
             // Look-ahead: factor(c+1) only gathers the tile rows / columns of ITS landmarks (the band).  downdate(c) is split
             // into the band tiles (urgent, f->stream) and all other lower tiles (deferred, f->stream3, beside factor(c+1)).
             //   band(c)   after factor(c) [stream order] and rest(c-1) [event: both write the band of chunk c+1]
@@ -1153,7 +1239,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
                 if (c > 0) CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * (c - 1) + 1], 0));  // rest(c-1) done
                 if (c == nchunks - 1) {  // last chunk: everything, and full symmetric storage again
                     chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Yc, guard,
-                                                                                              0, T, DD_ALL, T, TL_SLOT(f));
+                                                                                              0, T, DD_ALL, T, TL_SLOT(f), nullptr, nullptr);
                     LAUNCH_CHECK(f, "chunk_downdate_kernel");
                     break;
                 }
@@ -1170,12 +1256,12 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
                 const int nRest = (T - w) * (T - w + 1) / 2;
                 CUDA_TRY(f, cudaEventRecord(evF, f->stream));
                 chunk_downdate_kernel<<<nBand, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Yc, guard, mlo, mhi,
-                                                                                 DD_BAND, T, TL_SLOT(f));
+                                                                                 DD_BAND, T, TL_SLOT(f), nullptr, nullptr);
                 LAUNCH_CHECK(f, "chunk_downdate_kernel");
                 CUDA_TRY(f, cudaStreamWaitEvent(f->stream3, evF, 0));
                 if (nRest > 0) {
                     chunk_downdate_kernel<<<nRest, DD_THREADS, DD_SMEM, f->stream3>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Yc, guard, mlo,
-                                                                                      mhi, DD_REST, T, TL_SLOT(f));
+                                                                                      mhi, DD_REST, T, TL_SLOT(f), nullptr, nullptr);
                     LAUNCH_CHECK(f, "chunk_downdate_kernel");
                 }
                 CUDA_TRY(f, cudaEventRecord(evR, f->stream3));
@@ -1215,7 +1301,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
                         mhi = (SOFF + 3 * rmax + 2) / DD_T;
                     }
                     launch_pdl(f, chunk_downdate_kernel, dim3(T * (T + 1) / 2), dim3(DD_THREADS), DD_SMEM, f->stream, f->Sig[f->cur],
-                               f->Sig[f->cur], f->ld, Y, guard, mlo, mhi, (int)DD_ALL, T, TL_SLOT(f));
+                               f->Sig[f->cur], f->ld, Y, guard, mlo, mhi, (int)DD_ALL, T, TL_SLOT(f), (int*)nullptr, (const int*)nullptr);
                     LAUNCH_CHECK(f, "chunk_downdate_kernel");
                 }
                 prof_end(f, sk);
@@ -1248,7 +1334,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
                 CUDA_TRY(f, cudaEventRecord(evF, f->stream));
                 CUDA_TRY(f, cudaStreamWaitEvent(f->stream2, evF, 0));
                 chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream2>>>(f->Sig[sin], f->Sig[1 - sin], f->ld, Ybuf[c & 1],
-                                                                                           guard, 0, T, DD_ALL, T, TL_SLOT(f));
+                                                                                           guard, 0, T, DD_ALL, T, TL_SLOT(f), nullptr, nullptr);
                 LAUNCH_CHECK(f, "chunk_downdate_kernel");
                 CUDA_TRY(f, cudaEventRecord(evD, f->stream2));
                 std::swap(gin, gout);
@@ -1261,7 +1347,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
     } else {
     meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
                                                       s.useEquivariantOutput ? 1 : 0, f->d_Cblk, Z, ldz, m + dimp, guard, f->d_yIdx,
-                                                      nullptr, 0, nullptr, 0);
+                                                      nullptr, 0, nullptr, 0, nullptr, 0, TL_SLOT(f));
     LAUNCH_CHECK(f, "meas_kernel");
     zbuild_kernel<<<dim3(cdiv(dimp, 256), nm), 256, 0, f->stream>>>(f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, Z, ldz, m);
     LAUNCH_CHECK(f, "zbuild_kernel");
@@ -1297,7 +1383,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
     }
     lift_kernel<<<cdiv(std::max(Nn, 1), 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, Nn, f->d_xi0s, f->d_Xs[f->xcur], gammaFinal,
                                                                    s.useDiscreteInnovationLift ? 1 : 0, s.coordinateChoice,
-                                                                   f->d_status, f->d_status + 1, guard);
+                                                                   f->d_status, f->d_status + 1, guard, TL_SLOT(f));
     LAUNCH_CHECK(f, "lift_kernel");
     return EQVIO_OK;
 }
@@ -1403,6 +1489,8 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
     e = cudaFuncSetAttribute(chunk_downdate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChunkSmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Chunk2Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LOOK_SMEM);
     if (e != cudaSuccess) {
         g_createError = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
         return EQVIO_ERR_CUDA;
@@ -1644,6 +1732,9 @@ void eqvio_destroy(eqvio_filter* f) {
     if (f->h_frame) cudaFreeHost(f->h_frame);
     if (f->h_out) cudaFreeHost(f->h_out);
     cudaFree(f->d_outblk);
+    cudaFree(f->d_cnt);
+    cudaFree(f->d_Snext[0]);
+    cudaFree(f->d_Snext[1]);
     for (auto& g : f->graphs)
         if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     cudaFree(f->d_map);
@@ -1901,7 +1992,7 @@ int eqvio_get_state_estimate(eqvio_filter* f, double sensor[23], int* ids, doubl
         return EQVIO_OK;
     }
     stage_reset(f);
-    state_estimate_kernel<<<cdiv(std::max(N, 1), 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_xi0s, f->d_Xs[f->xcur], f->d_out);
+    state_estimate_kernel<<<cdiv(std::max(N, 1), 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_xi0s, f->d_Xs[f->xcur], f->d_out, TL_SLOT(f));
     LAUNCH_CHECK(f, "state_estimate_kernel");
     double* h = nullptr;
     int rc = download_async(f, &h, f->d_out, 23 + 3 * (size_t)N);
@@ -2144,6 +2235,11 @@ int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
             f->pipeline = value != 0;
             clear_graphs(f);
             return EQVIO_OK;
+        case EQVIO_TUNE_CHAIN:
+            if (value < 0 || value > 2) return EQVIO_ERR_INVALID_ARG;
+            f->chain = value;
+            clear_graphs(f);
+            return EQVIO_OK;
         case EQVIO_TUNE_PDL:
             f->pdl = value != 0;
             clear_graphs(f);
@@ -2190,6 +2286,12 @@ int eqvio_debug_timeline(eqvio_filter* f, unsigned long long* out, int maxSlots,
         f->tlNext = 0;
     }
     return n;
+}
+#endif
+
+#ifdef EQVIO_TIMELINE
+const char* eqvio_debug_timeline_name(eqvio_filter* f, int slot) {
+    return (f && slot >= 0 && slot < 512 && f->tlNames[slot]) ? f->tlNames[slot] : "?";
 }
 #endif
 

@@ -71,6 +71,26 @@ struct PrepArgs {
     double pdiag[8];  // process variances per 3-block + point     (VIOFilterSettings.h:176-190)
 };
 
+// Debug timeline (library built with -DEQVIO_TIMELINE): first-start / last-end globaltimer stamps per launch slot of the
+// chunk kernels, read back by eqvio_debug_timeline -- shows how the look-ahead launches overlap on the device.
+#ifdef EQVIO_TIMELINE
+constexpr int TL_MAX = 512;
+__device__ unsigned long long g_tl[2 * TL_MAX];
+__device__ __forceinline__ void tl_mark(int slot, int end) {
+    if (threadIdx.x == 0 && slot >= 0 && slot < TL_MAX) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (end)
+            atomicMax(&g_tl[2 * slot + 1], t);
+        else
+            atomicMin(&g_tl[2 * slot], t);
+    }
+}
+#define TL_MARK(slot, end) tl_mark(slot, end)
+#else
+#define TL_MARK(slot, end) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // Riccati context, part 1 (sensor-sized, serial): the sensor blocks of A and B (euclid.cpp:99-160,
 // 186-233; identical for invdepth) from X *before* the observer integration, and the quantities the
@@ -214,16 +234,19 @@ struct PublishGlobal {  // two-kernel form: segments go to a.steps for observer_
 };
 HD void observer_sensor_body(const PrepArgs& a) { observer_sensor_steps(a, PublishGlobal{a}); }
 
-__global__ void observer_sensor_kernel(PrepArgs a) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void observer_sensor_kernel(PrepArgs a, int tl) {
+    TL_MARK(tl, 0);
+    if (threadIdx.x != 0 || blockIdx.x != 0) { TL_MARK(tl, 1); return; }
     observer_sensor_body(a);
+    TL_MARK(tl, 1);
 }
 
 // One CTA: Riccati context (thread 0 builds the sparse A_s, B_s; 441 threads fill F_s, N_s) and, fused, the
 // sensor-sensor block  Sigma'_ss = F_s Sigma_ss F_s^T + N_s  plus the zero pad rows/cols of the sensor block.
 __global__ void __launch_bounds__(448)
     riccati_prep_kernel(PrepArgs a, const double* __restrict__ Sin, double* __restrict__ Sout, int ld, double* __restrict__ dtBsOut,
-                        int* __restrict__ clearFlag) {
+                        int* __restrict__ clearFlag, int tl) {
+    TL_MARK(tl, 0);
     __shared__ double sAs[441], sBs[252], sF[441], sS[441], sT[441];
     const int t = threadIdx.x;
     if (clearFlag && t == 447) *clearFlag = 0;  // first kernel of an update: re-arm the gate flag (no memset node)
@@ -259,6 +282,7 @@ __global__ void __launch_bounds__(448)
         Sout[(size_t)q * ld + p] = 0.0;
         Sout[(size_t)p * ld + q] = 0.0;
     }
+    TL_MARK(tl, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -269,9 +293,10 @@ __global__ void __launch_bounds__(448)
 constexpr int ROWS_STRIDE = 54;
 
 __global__ void landmark_rows_kernel(const double* __restrict__ lm, int cap, int N, const RiccatiCtx* __restrict__ ctx, int coord,
-                                     double* __restrict__ rows) {
+                                     double* __restrict__ rows, int tl) {
+    TL_MARK(tl, 0);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+    if (i >= N) { TL_MARK(tl, 1); return; }
     V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
     Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
     double a = lm[F_QA * cap + i];
@@ -319,6 +344,7 @@ __global__ void landmark_rows_kernel(const double* __restrict__ lm, int cap, int
         for (int c = 0; c < 6; ++c) o[9 + 12 * r + 6 + c] = dt * camB[6 * r + c];
     }
     for (int k = 0; k < 9; ++k) o[45 + k] = Bl.m[k];
+    TL_MARK(tl, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -330,7 +356,8 @@ constexpr int OBS_STAGE = 64;  // IMU segments staged in shared memory at a time
 
 __global__ void observer_landmark_kernel(const double* __restrict__ lmIn, double* __restrict__ lmOut, const int* __restrict__ idsIn,
                                          int* __restrict__ idsOut, int cap, int N, const ObsStep* __restrict__ steps,
-                                         const FrameHeader* __restrict__ fr) {
+                                         const FrameHeader* __restrict__ fr, int tl) {
+    TL_MARK(tl, 0);
     __shared__ ObsStep s_steps[OBS_STAGE];
     const int nsteps = fr->fs.nsteps;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -381,6 +408,7 @@ __global__ void observer_landmark_kernel(const double* __restrict__ lmIn, double
         lmOut[F_QA * cap + i] = a;
         idsOut[i] = idsIn[i];
     }
+    TL_MARK(tl, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -414,18 +442,19 @@ struct PublishShared {
 };
 __global__ void __launch_bounds__(OBSF_THREADS)
     observer_fused_kernel(PrepArgs a, const double* __restrict__ lmIn, double* __restrict__ lmOut, const int* __restrict__ idsIn,
-                          int* __restrict__ idsOut, int cap, int N) {
+                          int* __restrict__ idsOut, int cap, int N, int tl) {
+    TL_MARK(tl, 0);
     __shared__ ObsStep s_steps[OBS_STAGE];
     __shared__ int s_ready;
     if (threadIdx.x == 0) s_ready = 0;
     __syncthreads();
     if (threadIdx.x < 32) {
         if (threadIdx.x == 0) observer_sensor_steps(a, PublishShared{a, s_steps, &s_ready, blockIdx.x == 0});
-        return;
+        { TL_MARK(tl, 1); return; }
     }
     const int nsteps = a.fr->fs.nsteps;
     const int i = blockIdx.x * OBSF_LM + (threadIdx.x - 32);
-    if (i >= N) return;
+    if (i >= N) { TL_MARK(tl, 1); return; }
     V3 q0 = V3{lmIn[F_Q0X * cap + i], lmIn[F_Q0Y * cap + i], lmIn[F_Q0Z * cap + i]};
     Quat Q = Quat{lmIn[F_QW * cap + i], lmIn[F_QX * cap + i], lmIn[F_QY * cap + i], lmIn[F_QZ * cap + i]};
     double a_ = lmIn[F_QA * cap + i];
@@ -458,6 +487,7 @@ __global__ void __launch_bounds__(OBSF_THREADS)
     lmOut[F_QZ * cap + i] = Q.z;
     lmOut[F_QA * cap + i] = a_;
     idsOut[i] = id;
+    TL_MARK(tl, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -475,7 +505,8 @@ constexpr int PS_LM = 8, PS_TPL = 24;  // landmarks per CTA, threads per landmar
 
 __global__ void __launch_bounds__(PS_LM* PS_TPL)
     prop_strip_kernel(const double* __restrict__ Sin, double* __restrict__ Sout, int ld, int N,
-                      const RiccatiCtx* __restrict__ ctx, const double* __restrict__ rows, double* __restrict__ uv) {
+                      const RiccatiCtx* __restrict__ ctx, const double* __restrict__ rows, double* __restrict__ uv, int tl) {
+    TL_MARK(tl, 0);
     __shared__ double sF[441], sS[441], sBG[63];
     __shared__ double sRow[PS_LM][ROWS_STRIDE];  // D(9) | G(36) | Bl(9)
     __shared__ double sL[PS_LM][63];              // sL[a*21 + c] = Sigma[row a of the landmark, sensor column c]
@@ -539,7 +570,7 @@ __global__ void __launch_bounds__(PS_LM* PS_TPL)
         }
     }
     __syncthreads();
-    if (!live) return;
+    if (!live) { TL_MARK(tl, 1); return; }
     if (t < 21) {  // row t of Sigma'_{s,i} = F_s X_i + BsG Bl_i^T, written to both triangles
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
@@ -556,6 +587,7 @@ __global__ void __launch_bounds__(PS_LM* PS_TPL)
             Sout[(size_t)t * ld + r0 + b] = 0.0;
         }
     }
+    TL_MARK(tl, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -569,9 +601,10 @@ constexpr int TP = 16;
 __global__ void __launch_bounds__(TP* TP)
     prop_ll_kernel(const double* __restrict__ Sin, double* __restrict__ Sout, int ld, int N,
                    const RiccatiCtx* __restrict__ ctx, const double* __restrict__ rows,
-                   const double* __restrict__ uv) {
+                   const double* __restrict__ uv, int tl) {
+    TL_MARK(tl, 0);
     const int ti = blockIdx.y, tj = blockIdx.x;
-    if (tj > ti) return;
+    if (tj > ti) { TL_MARK(tl, 1); return; }
     __shared__ double sU[TP][82], sV[TP][82], sDi[TP][9], sDj[TP][9];
     const int tid = threadIdx.y * TP + threadIdx.x;
     const int i0 = ti * TP, j0 = tj * TP;
@@ -588,7 +621,7 @@ __global__ void __launch_bounds__(TP* TP)
     __syncthreads();
     const int li = threadIdx.x, lj = threadIdx.y;  // threadIdx.x walks rows (contiguous in memory)
     const int i = i0 + li, j = j0 + lj;
-    if (i >= N || j >= N) return;
+    if (i >= N || j >= N) { TL_MARK(tl, 1); return; }
     const int r0 = SOFF + 3 * i, c0 = SOFF + 3 * j;
     double S[9];  // S[a*3+b] = Sigma[r0+a, c0+b]
     for (int b = 0; b < 3; ++b)
@@ -617,6 +650,7 @@ __global__ void __launch_bounds__(TP* TP)
         for (int a = 0; a < 3; ++a)
             for (int b = 0; b < 3; ++b) Sout[(size_t)(r0 + a) * ld + c0 + b] = O[a * 3 + b];
     }
+    TL_MARK(tl, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -626,9 +660,10 @@ __global__ void __launch_bounds__(TP* TP)
 // ------------------------------------------------------------------------------------------------
 __global__ void gate_kernel(const double* __restrict__ lm, int cap, int N, const double* __restrict__ Sig, int ld,
                             const int* __restrict__ measIdx, const double* __restrict__ y, const FrameHeader* __restrict__ fr, int coord,
-                            double* __restrict__ out, double thrAbs, double thrProb, int* __restrict__ tripped) {
+                            double* __restrict__ out, double thrAbs, double thrProb, int* __restrict__ tripped, int tl) {
+    TL_MARK(tl, 0);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+    if (i >= N) { TL_MARK(tl, 1); return; }
     const Camera cam = fr->cam;
     V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
     Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
@@ -639,7 +674,7 @@ __global__ void gate_kernel(const double* __restrict__ lm, int cap, int N, const
     if (mi < 0) {
         out[i] = -1.0;
         out[N + i] = -1.0;
-        return;
+        { TL_MARK(tl, 1); return; }
     }
     double u, v;
     cam_project(cam, qh, u, v);
@@ -664,6 +699,7 @@ __global__ void gate_kernel(const double* __restrict__ lm, int cap, int N, const
     const double eProb = d0 * (i00 * d0 + i01 * d1) + d1 * (i10 * d0 + i11 * d1);
     out[N + i] = eProb;
     if (out[i] > thrAbs || eProb > thrProb) atomicOr(tripped, 1);  // same comparisons as the host decision
+    TL_MARK(tl, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -745,12 +781,14 @@ __global__ void meas_kernel(const double* __restrict__ lm, int cap, const int* _
                             const double* __restrict__ y, const FrameHeader* __restrict__ fr, int coord, int useStar,
                             double* __restrict__ Cblk, double* __restrict__ Z, int ldz, int yrow,
                             const int* __restrict__ guard, const int* __restrict__ yIdx, int* __restrict__ zeroStatus, int nStatus,
-                            double* __restrict__ zeroGamma, int nGamma) {
+                            double* __restrict__ zeroGamma, int nGamma, int* __restrict__ zeroCnt, int nCnt, int tl) {
+    TL_MARK(tl, 0);
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     // first kernel of the correction: clears the status words and the Gamma accumulator (also when the guard is set)
     for (int t = j; t < nStatus; t += gridDim.x * blockDim.x) zeroStatus[t] = 0;
     for (int t = j; t < nGamma; t += gridDim.x * blockDim.x) zeroGamma[t] = 0.0;
-    if (j >= n || *guard) return;
+    for (int t = j; t < nCnt; t += gridDim.x * blockDim.x) zeroCnt[t] = 0;
+    if (j >= n || *guard) { TL_MARK(tl, 1); return; }
     const int jm = yIdx ? yIdx[j] : j;  // row pair j of the correction takes the pixel of measurement jm
     const Camera cam = fr->cam;
     int i = lmOf[j];
@@ -766,6 +804,7 @@ __global__ void meas_kernel(const double* __restrict__ lm, int cap, const int* _
     double C[6];
     output_block(cam, coord, q0, Q, a, useStar != 0, yu, yv, C);
     for (int k = 0; k < 6; ++k) Cblk[6 * j + k] = C[k];
+    TL_MARK(tl, 1);
 }
 
 // Step 2: W^T = Sigma C^T into Z rows [m, m+dimp).  grid (ceil(dimp/256), n).
@@ -1053,25 +1092,6 @@ __device__ __forceinline__ void pdl_wait() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
-// Debug timeline (library built with -DEQVIO_TIMELINE): first-start / last-end globaltimer stamps per launch slot of the
-// chunk kernels, read back by eqvio_debug_timeline -- shows how the look-ahead launches overlap on the device.
-#ifdef EQVIO_TIMELINE
-constexpr int TL_MAX = 512;
-__device__ unsigned long long g_tl[2 * TL_MAX];
-__device__ __forceinline__ void tl_mark(int slot, int end) {
-    if (threadIdx.x == 0 && slot >= 0 && slot < TL_MAX) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        if (end)
-            atomicMax(&g_tl[2 * slot + 1], t);
-        else
-            atomicMin(&g_tl[2 * slot], t);
-    }
-}
-#define TL_MARK(slot, end) tl_mark(slot, end)
-#else
-#define TL_MARK(slot, end) do { } while (0)
-#endif
 // progress flag between the two warp groups of chunk_factor_kernel: release store / acquire load at CTA scope
 __device__ __forceinline__ void flag_release(int* p, int v) {
     asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
@@ -1439,6 +1459,537 @@ __global__ void __launch_bounds__(CH_THREADS)
 }
 
 // ------------------------------------------------------------------------------------------------
+// chunk_factor2_kernel / chunk_look_kernel: the CHAINED correction.  The sequential-chunk update is a block Cholesky of
+// S = C Sigma C^T + R whose trailing update is applied to Sigma.  The elimination of S_c does not have to wait for the
+// downdate of chunk c-1 if S_c (already downdated) is handed over in measurement space:
+//   * chunk_look_kernel (one CTA, its own stream) eliminates S_c with the projected block S_{c+1,c} = C_{c+1} Sigma C_c^T as
+//     right-hand sides, which yields U = L_c^-1 S_{c,c+1}, and writes S_{c+1} = S_{c+1}^pre - U^T U for the next launches;
+//   * chunk_factor2_kernel is chunk_factor_kernel with its S group starting from that block instead of gathering Sigma;
+//   * the downdates run on a third stream; only the right-hand-side warps of the next launches wait for them (acquire on
+//     a completion counter the downdate CTAs bump) before they gather from Sigma, then catch up with the S group through
+//     the progress flag.  The cycle per chunk is downdate -> gather -> catch-up -> Y, the 64-pivot chain runs beside it.
+// ------------------------------------------------------------------------------------------------
+constexpr int C2_YT_LD = CH_R + 4;  // 68: rows of U / Y^T stay 16-byte aligned
+
+struct Chunk2Smem {
+    union {
+        double Lp[CH_NT][CH_T][CH_T][CH_NT + 1];
+        double Yt[CH_R][C2_YT_LD];
+    };
+    double Dc[CH_NT][CH_T];
+    double C[CH_R / 2][6];
+    double Cn[CH_R / 2][6];          // output blocks of the NEXT chunk (look-ahead kernel)
+    double Inv[CH_R];
+    double Spre[CH_R][CH_R + 1];     // S of the next chunk before this chunk's downdate (look-ahead kernel)
+    int Idx[CH_R / 2];
+    int IdxN[CH_R / 2];
+    int ready;
+    int t1ready;                     // look-ahead kernel: the row-projected blocks are staged
+    int urows;                       // look-ahead kernel: half-warps that have published their rows of U (16 per block column)
+};
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+template <int NTHREADS>
+__device__ __forceinline__ void rhs_group_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(NTHREADS) : "memory"); }
+
+// LOOK = false: 32 state columns + the residual per CTA (9 tile rows, 160 RHS threads), writes Y_c and Gamma.
+// LOOK = true : ONE CTA, right-hand sides = the 64 measurement rows of the next chunk (16 tile rows, 256 RHS threads),
+//               writes SnextOut.
+// Look-ahead kernel only: Sigma blocks projected on the row side, staged so that every global read is coalesced
+// (lanes walk the next chunk's landmarks = consecutive rows of a column of Sigma):
+//   Trhs[2 jn + e][cc] = sum_aa Cn[jn][e][aa] Sigma[row(jn) + aa, col_c(cc)]   cc over this chunk's 96 state columns
+//   Tpre[2 jn + e][cc] = the same against the next chunk's own columns (lower triangle: jn >= cc / 3)
+constexpr int LK_LD = 3 * (CH_R / 2) + 1;  // 97
+struct LookExtraSmem {
+    double Trhs[CH_R][LK_LD];
+    double Tpre[CH_R][LK_LD];
+};
+constexpr int LOOK_RHS = 256, LOOK_MMA = 128;
+constexpr int LOOK_THREADS = CH_S_THREADS + LOOK_RHS + LOOK_MMA;  // S group | right-hand sides | rank-4 updates of S_next
+constexpr int LOOK_SMEM = (int)(sizeof(Chunk2Smem) + sizeof(LookExtraSmem));
+
+template <bool LOOK>
+__global__ void __launch_bounds__(LOOK ? LOOK_THREADS : CH_THREADS)
+    chunk_factor2_kernel(const double* Sig, int ld, int dimp, const int* __restrict__ lmOf, const double* __restrict__ Cblk,
+                         const double* __restrict__ ytilde, int j0, int bc, int nb, double r2, const double* __restrict__ GammaIn,
+                         double* __restrict__ GammaOut, double* __restrict__ Y, int* __restrict__ status, const int* __restrict__ guard,
+                         const double* __restrict__ SnextIn, double* __restrict__ SnextOut, const int* waitCnt, int waitTarget,
+                         int* gatherDone, int tl) {
+    constexpr int RHS_THREADS = LOOK ? LOOK_RHS : CH_RHS_THREADS;
+    constexpr int NTHREADS = LOOK ? LOOK_THREADS : CH_THREADS;
+    constexpr int ROWS = LOOK ? CH_NT : CH_RHS_ROWS;  // tile rows of right-hand sides
+    // Cblk / lmOf were written by meas_kernel and the frame upload, several launches back on this stream's history: they are
+    // read BEFORE the dependency wait so that the set-up overlaps the predecessor's tail
+    extern __shared__ __align__(16) unsigned char chunk_smem_raw[];
+    Chunk2Smem& sm = *reinterpret_cast<Chunk2Smem*>(chunk_smem_raw);
+    const int tid = threadIdx.x;
+    const int rc = 2 * bc;
+    if (LOOK) CH_STAMP(0);
+    for (int t = tid; t < bc * 6; t += NTHREADS) sm.C[t / 6][t % 6] = Cblk[6 * (size_t)j0 + t];
+    for (int t = tid; t < bc; t += NTHREADS) sm.Idx[t] = SOFF + 3 * lmOf[j0 + t];
+    if (LOOK) {
+        for (int t = tid; t < (CH_R / 2) * 6; t += NTHREADS) sm.Cn[t / 6][t % 6] = t < nb * 6 ? Cblk[6 * (size_t)(j0 + bc) + t] : 0.0;
+        for (int t = tid; t < CH_R / 2; t += NTHREADS) sm.IdxN[t] = t < nb ? SOFF + 3 * lmOf[j0 + bc + t] : 0;
+    }
+    if (tid == 0) {
+        sm.ready = 0;
+        sm.t1ready = 0;
+        sm.urows = 0;
+    }
+    pdl_wait();
+    if (*guard) return;
+    TL_MARK(tl, 0);
+    __syncthreads();
+    if (LOOK) CH_STAMP(1);
+
+    const bool sGroup = tid < CH_S_THREADS;
+    const int sbase = blockIdx.x * CH_COLS;
+    const int nJ = (rc + CH_T - 1) / CH_T;
+    double a[CH_T][CH_T];
+#pragma unroll
+    for (int r = 0; r < CH_T; ++r)
+#pragma unroll
+        for (int c = 0; c < CH_T; ++c) a[r][c] = 0.0;
+
+    if (sGroup) {
+        // ================================ S group ================================
+        const bool owner = tid < CH_TILES;
+        int TI = 0, TK = 0;
+        if (owner) tri_decode(tid, TI, TK);
+        if (owner && SnextIn) {
+            // S_c arrives from the previous look-ahead launch (row-major 64 x 64, lower tiles)
+#pragma unroll
+            for (int r = 0; r < CH_T; ++r) {
+                const double2 p01 = *reinterpret_cast<const double2*>(SnextIn + (size_t)(CH_T * TI + r) * CH_R + CH_T * TK);
+                const double2 p23 = *reinterpret_cast<const double2*>(SnextIn + (size_t)(CH_T * TI + r) * CH_R + CH_T * TK + 2);
+                a[r][0] = p01.x;
+                a[r][1] = p01.y;
+                a[r][2] = p23.x;
+                a[r][3] = p23.y;
+            }
+        } else if (owner) {
+            // first chunk: gather from Sigma (full symmetric storage at this point), as chunk_factor_kernel does
+            double P[2][2][9];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    const int j = 2 * TI + u, k = 2 * TK + v;
+                    if (j < bc && k < bc) {
+                        const double* sp = Sig + (size_t)sm.Idx[j] * ld + sm.Idx[k];
+#pragma unroll
+                        for (int aa = 0; aa < 3; ++aa)
+#pragma unroll
+                            for (int b = 0; b < 3; ++b) P[u][v][aa * 3 + b] = __ldcg(sp + (size_t)aa * ld + b);
+                    }
+                }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    const int j = 2 * TI + u, k = 2 * TK + v;
+                    if (j < bc && k < bc) {
+                        double T[6];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+#pragma unroll
+                            for (int b = 0; b < 3; ++b)
+                                T[e * 3 + b] = sm.C[j][3 * e] * P[u][v][b] + sm.C[j][3 * e + 1] * P[u][v][3 + b] + sm.C[j][3 * e + 2] * P[u][v][6 + b];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+#pragma unroll
+                            for (int f = 0; f < 2; ++f)
+                                a[2 * u + e][2 * v + f] = T[e * 3] * sm.C[k][3 * f] + T[e * 3 + 1] * sm.C[k][3 * f + 1] + T[e * 3 + 2] * sm.C[k][3 * f + 2];
+                    }
+                }
+            if (TI == TK) {
+#pragma unroll
+                for (int c = 0; c < CH_T; ++c) {
+                    if (CH_T * TI + c < rc)
+                        a[c][c] += r2;
+                    else
+                        a[c][c] = 1.0;  // identity padding of a short last chunk
+                }
+            }
+        }
+        if (LOOK) CH_STAMP(2);
+        for (int J = 0; J < nJ; ++J) {
+            if (owner && TI == J && TK == J) {
+                // fraction-free 4x4 diagonal tile, see chunk_factor_kernel
+                const double a00 = a[0][0], a10 = a[1][0], a20 = a[2][0], a30 = a[3][0];
+                const double m11 = a[1][1] * a00 - a10 * a10, m21 = a[2][1] * a00 - a20 * a10, m22 = a[2][2] * a00 - a20 * a20;
+                const double m31 = a[3][1] * a00 - a30 * a10, m32 = a[3][2] * a00 - a30 * a20, m33 = a[3][3] * a00 - a30 * a30;
+                const double n22 = m22 * m11 - m21 * m21, n32 = m32 * m11 - m31 * m21, n33 = m33 * m11 - m31 * m31;
+                const double p33 = n33 * n22 - n32 * n32;
+                const double r0 = fast_rcp(a00), r1 = fast_rcp(m11), r2_ = fast_rcp(n22), r3 = fast_rcp(p33);
+                const double s2 = r0 * r1, s3 = s2 * r2_, e1 = a00 * m11;
+                a[1][1] = m11 * r0;
+                a[2][1] = m21 * r0;
+                a[3][1] = m31 * r0;
+                a[2][2] = n22 * s2;
+                a[3][2] = n32 * s2;
+                a[3][3] = p33 * s3;
+                sm.Dc[J][0] = r0;
+                sm.Dc[J][1] = a00 * r1;
+                sm.Dc[J][2] = e1 * r2_;
+                sm.Dc[J][3] = (e1 * n22) * r3;
+#pragma unroll
+                for (int i = 0; i < CH_T; ++i)
+#pragma unroll
+                    for (int j = 0; j < CH_T; ++j) sm.Lp[J][i][j][J] = a[i][j];
+            }
+            s_group_barrier();
+            if (owner && TK == J && TI > J) {
+                double c[CH_T], d[CH_T][CH_T];
+#pragma unroll
+                for (int j = 0; j < CH_T; ++j) c[j] = sm.Dc[J][j];
+#pragma unroll
+                for (int i = 0; i < CH_T; ++i)
+#pragma unroll
+                    for (int j = 0; j < CH_T; ++j) d[i][j] = sm.Lp[J][i][j][J];
+#pragma unroll
+                for (int j = 0; j < CH_T; ++j)
+#pragma unroll
+                    for (int k = j + 1; k < CH_T; ++k)
+#pragma unroll
+                        for (int r = 0; r < CH_T; ++r) a[r][k] -= (a[r][j] * c[j]) * d[k][j];
+#pragma unroll
+                for (int r = 0; r < CH_T; ++r)
+#pragma unroll
+                    for (int j = 0; j < CH_T; ++j) sm.Lp[J][r][j][TI] = a[r][j];
+            }
+            s_group_barrier();
+            if (tid == 0) flag_release(&sm.ready, J + 1);
+            if (owner && TK > J) {
+                double li[CH_T][CH_T], pk[CH_T][CH_T];
+#pragma unroll
+                for (int j = 0; j < CH_T; ++j) {
+                    const double c = sm.Dc[J][j];
+#pragma unroll
+                    for (int r = 0; r < CH_T; ++r) li[r][j] = sm.Lp[J][r][j][TI] * c;
+                }
+#pragma unroll
+                for (int cc = 0; cc < CH_T; ++cc)
+#pragma unroll
+                    for (int j = 0; j < CH_T; ++j) pk[cc][j] = sm.Lp[J][cc][j][TK];
+#pragma unroll
+                for (int r = 0; r < CH_T; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < CH_T; ++cc) {
+                        double acc = a[r][cc];
+#pragma unroll
+                        for (int j = 0; j < CH_T; ++j) acc -= li[r][j] * pk[cc][j];
+                        a[r][cc] = acc;
+                    }
+            }
+        }
+        if (LOOK) CH_STAMP(3);
+        if (owner && TI == TK) {
+#pragma unroll
+            for (int c = 0; c < CH_T; ++c) {
+                const double piv = a[c][c];
+                const int k = CH_T * TK + c;
+                if (!(piv > 0.0)) {
+                    if (blockIdx.x == 0 && !LOOK) atomicOr(status, 1);
+                    sm.Inv[k] = 1.0;
+                } else {
+                    sm.Inv[k] = 1.0 / sqrt(piv);
+                }
+            }
+        }
+    } else if (tid < CH_S_THREADS + RHS_THREADS) {
+        // ================================ RHS group ================================
+        const int q = tid - CH_S_THREADS;
+        const int trow = q / CH_NT, TK = q % CH_NT;
+        const bool isRhs = trow < ROWS;
+        if (waitCnt) {
+            // Sigma must carry the previous chunk's downdate (it runs on another stream): wait for all its tiles
+            if (q == 0) {
+                int spins = 0;
+                while (ld_acquire_gpu(waitCnt) < waitTarget) {
+                    __nanosleep(64);
+                    if (++spins > (1 << 24)) {  // ~1 s: never hang the device; the host sees the status bit
+                        atomicOr(status, 4);
+                        break;
+                    }
+                }
+            }
+            rhs_group_barrier<RHS_THREADS>();
+        }
+        if (LOOK) CH_STAMP(107);
+        if (LOOK) {
+            LookExtraSmem& lx = *reinterpret_cast<LookExtraSmem*>(chunk_smem_raw + sizeof(Chunk2Smem));
+            // step 1: coalesced reads of Sigma, projected on the row side with the next chunk's output blocks
+            constexpr int LK_ITEMS = 2 * 3 * (CH_R / 2) * (CH_R / 2), LK_BATCH = 8;  // 6144 items, 24 per thread, 8 in flight
+            for (int it0 = q; it0 < LK_ITEMS; it0 += RHS_THREADS * LK_BATCH) {
+                double v[LK_BATCH][3];
+#pragma unroll
+                for (int bi = 0; bi < LK_BATCH; ++bi) {
+                    // branch-free: every item loads three (possibly dummy) addresses so that the 24 loads of a batch are in flight
+                    // together; invalid items are zeroed afterwards
+                    const int item = it0 + bi * RHS_THREADS;
+                    const int jn = item % (CH_R / 2);
+                    int cc = item / (CH_R / 2);
+                    const bool pre = cc >= 3 * (CH_R / 2);
+                    if (pre) cc -= 3 * (CH_R / 2);
+                    const int jc = (cc / 3) & (CH_R / 2 - 1), b = cc % 3;
+                    const bool ok = item < LK_ITEMS && jn < nb && (pre ? jc <= jn : jc < bc);
+                    const int row = ok ? sm.IdxN[jn] : 0;
+                    const int col = ok ? (pre ? sm.IdxN[jc] : sm.Idx[jc]) + b : 0;
+#pragma unroll
+                    for (int aa = 0; aa < 3; ++aa) {
+                        const int R = row + aa;  // entries are read as (max, min): the lower triangle is always current
+                        // plain (L1-cached) load: the three rows of a lane share sectors; no stale line can sit in L1, this CTA has
+                        // not touched Sigma before the counter wait above
+                        const double x = Sig[(size_t)(R < col ? R : col) * ld + (R < col ? col : R)];
+                        v[bi][aa] = ok ? x : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int bi = 0; bi < LK_BATCH; ++bi) {
+                    const int item = it0 + bi * RHS_THREADS;
+                    if (item < LK_ITEMS) {
+                        const int jn = item % (CH_R / 2);
+                        int cc = item / (CH_R / 2);
+                        const bool pre = cc >= 3 * (CH_R / 2);
+                        if (pre) cc -= 3 * (CH_R / 2);
+                        double(*Tm)[LK_LD] = pre ? lx.Tpre : lx.Trhs;
+                        Tm[2 * jn][cc] = sm.Cn[jn][0] * v[bi][0] + sm.Cn[jn][1] * v[bi][1] + sm.Cn[jn][2] * v[bi][2];
+                        Tm[2 * jn + 1][cc] = sm.Cn[jn][3] * v[bi][0] + sm.Cn[jn][4] * v[bi][1] + sm.Cn[jn][5] * v[bi][2];
+                    }
+                }
+            }
+            rhs_group_barrier<RHS_THREADS>();
+            if (q == 0) {
+                flag_release(&sm.t1ready, 1);  // Tpre is complete: the MMA group projects S_pre from it
+                if (gatherDone) {              // this chunk's downdate may overwrite Sigma from here on
+                    __threadfence();
+                    atomicExch(gatherDone, 1);
+                }
+            }
+            CH_STAMP(110);
+            // step 2b: right-hand sides = the projected block S_{c+1,c}: rows = measurement rows of the next chunk (landmarks
+            // 2 trow, 2 trow + 1), columns from landmarks 2TK, 2TK+1 of this chunk
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    const int jn = 2 * trow + u, j = 2 * TK + v;
+                    if (jn < nb && j < bc) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+#pragma unroll
+                            for (int f = 0; f < 2; ++f)
+                                a[2 * u + e][2 * v + f] = lx.Trhs[2 * jn + e][3 * j] * sm.C[j][3 * f] + lx.Trhs[2 * jn + e][3 * j + 1] * sm.C[j][3 * f + 1] +
+                                                          lx.Trhs[2 * jn + e][3 * j + 2] * sm.C[j][3 * f + 2];
+                    }
+                }
+            rhs_group_barrier<RHS_THREADS>();  // Trhs is dead from here on: its storage becomes U
+        } else if (isRhs && trow < CH_COLS / CH_T) {
+            // rows s = sbase + 4 trow + r (state columns of W_c), columns k = 4TK + c from landmarks 2TK, 2TK+1
+            const int s0 = sbase + CH_T * trow;
+            double w[2][3][CH_T];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const int j = 2 * TK + v;
+                if (j < bc && s0 < dimp) {
+                    const double* sp = Sig + (size_t)sm.Idx[j] * ld + s0;
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        const double2 p01 = __ldcg(reinterpret_cast<const double2*>(sp + (size_t)b * ld));
+                        const double2 p23 = __ldcg(reinterpret_cast<const double2*>(sp + (size_t)b * ld + 2));
+                        w[v][b][0] = p01.x;
+                        w[v][b][1] = p01.y;
+                        w[v][b][2] = p23.x;
+                        w[v][b][3] = p23.y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const int j = 2 * TK + v;
+                if (j < bc && s0 < dimp) {
+#pragma unroll
+                    for (int r = 0; r < CH_T; ++r)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                            a[r][2 * v + e] = (s0 + r < dimp) ? sm.C[j][3 * e] * w[v][0][r] + sm.C[j][3 * e + 1] * w[v][1][r] + sm.C[j][3 * e + 2] * w[v][2][r] : 0.0;
+                }
+            }
+        } else if (isRhs) {
+            // residual row (r = 0 of the last tile row): ytilde_c - C_c Gamma
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const int j = 2 * TK + v;
+                if (j < bc) {
+                    const int g = sm.Idx[j];
+                    const double g0 = GammaIn[g], g1 = GammaIn[g + 1], g2 = GammaIn[g + 2];
+                    a[0][2 * v] = ytilde[2 * (j0 + j)] - (sm.C[j][0] * g0 + sm.C[j][1] * g1 + sm.C[j][2] * g2);
+                    a[0][2 * v + 1] = ytilde[2 * (j0 + j) + 1] - (sm.C[j][3] * g0 + sm.C[j][4] * g1 + sm.C[j][5] * g2);
+                }
+            }
+        }
+        if (LOOK) CH_STAMP(108);
+        for (int J = 0; J < nJ; ++J) {
+            while (flag_acquire(&sm.ready) <= J) __nanosleep(32);
+            double c[CH_T];
+#pragma unroll
+            for (int j = 0; j < CH_T; ++j) c[j] = sm.Dc[J][j];
+            if (TK == J) {
+                double d[CH_T][CH_T];
+#pragma unroll
+                for (int i = 0; i < CH_T; ++i)
+#pragma unroll
+                    for (int j = 0; j < CH_T; ++j) d[i][j] = sm.Lp[J][i][j][J];
+#pragma unroll
+                for (int j = 0; j < CH_T; ++j)
+#pragma unroll
+                    for (int k = j + 1; k < CH_T; ++k)
+#pragma unroll
+                        for (int r = 0; r < CH_T; ++r) a[r][k] -= (a[r][j] * c[j]) * d[k][j];
+                if (LOOK) {
+                    // rows 4J .. 4J+3 of U = L_c^-1 S_{c,c+1} are final (up to the scale 1 / L_kk, which the MMA group applies as
+                    // 1 / v_kk on one operand): publish them for the rank-4 update of S_next that runs beside the elimination
+                    LookExtraSmem& lx = *reinterpret_cast<LookExtraSmem*>(chunk_smem_raw + sizeof(Chunk2Smem));
+#pragma unroll
+                    for (int cc = 0; cc < CH_T; ++cc)
+#pragma unroll
+                        for (int r = 0; r < CH_T; ++r) lx.Trhs[CH_T * J + cc][CH_T * trow + r] = a[r][cc];  // unscaled: v_sk = L_sk L_kk
+                    __threadfence_block();
+                    atomicAdd(&sm.urows, 1);
+                }
+            }
+            double li[CH_T][CH_T];
+#pragma unroll
+            for (int r = 0; r < CH_T; ++r)
+#pragma unroll
+                for (int j = 0; j < CH_T; ++j) li[r][j] = __shfl_sync(0xffffffffu, a[r][j], J, CH_NT) * c[j];
+            if (TK > J) {
+                double pk[CH_T][CH_T];
+#pragma unroll
+                for (int cc = 0; cc < CH_T; ++cc)
+#pragma unroll
+                    for (int j = 0; j < CH_T; ++j) pk[cc][j] = sm.Lp[J][cc][j][TK];
+#pragma unroll
+                for (int r = 0; r < CH_T; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < CH_T; ++cc) {
+                        double acc = a[r][cc];
+#pragma unroll
+                        for (int j = 0; j < CH_T; ++j) acc -= li[r][j] * pk[cc][j];
+                        a[r][cc] = acc;
+                    }
+            }
+        }
+    } else if (LOOK) {
+        // ================================ MMA group (look-ahead kernel) ================================
+        // S_next = S_pre - U^T U, accumulated four rows of U at a time as they become final (one DMMA k-step per block
+        // column), so that only the last rank-4 update and the store remain after the elimination.
+        LookExtraSmem& lx = *reinterpret_cast<LookExtraSmem*>(chunk_smem_raw + sizeof(Chunk2Smem));
+        const int m = tid - CH_S_THREADS - RHS_THREADS;
+        while (flag_acquire(&sm.t1ready) == 0) __nanosleep(64);
+        for (int tile = m; tile < CH_TILES; tile += LOOK_MMA) {
+            int TIn, TKn;
+            tri_decode(tile, TIn, TKn);
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) {
+                        const int j = 2 * TIn + u, k = 2 * TKn + v;
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+#pragma unroll
+                            for (int f = 0; f < 2; ++f) {
+                                double val = 0.0;
+                                if (j < nb && k < nb) {
+                                    if (j >= k)
+                                        val = lx.Tpre[2 * j + e][3 * k] * sm.Cn[k][3 * f] + lx.Tpre[2 * j + e][3 * k + 1] * sm.Cn[k][3 * f + 1] +
+                                              lx.Tpre[2 * j + e][3 * k + 2] * sm.Cn[k][3 * f + 2];
+                                    else
+                                        val = lx.Tpre[2 * k + f][3 * j] * sm.Cn[j][3 * e] + lx.Tpre[2 * k + f][3 * j + 1] * sm.Cn[j][3 * e + 1] +
+                                              lx.Tpre[2 * k + f][3 * j + 2] * sm.Cn[j][3 * e + 2];
+                                }
+                                const int rr = 2 * j + e, cq = 2 * k + f;
+                                if (rr == cq) val = rr < 2 * nb ? val + r2 : 1.0;
+                                sm.Spre[rr][cq] = val;
+                                sm.Spre[cq][rr] = val;  // the epilogue updates the full 64 x 64 block
+                            }
+                    }
+        }
+        asm volatile("bar.sync 3, %0;" ::"n"(LOOK_MMA) : "memory");
+        const int lane = m & 31, warp = m >> 5;
+        const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+        const int fr = wm + (lane >> 2), fc = wn + (lane & 3) * 2;
+        double acc[4][4][2];
+#pragma unroll
+        for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                acc[aa][b][0] = -sm.Spre[fr + aa * 8][fc + b * 8];
+                acc[aa][b][1] = -sm.Spre[fr + aa * 8][fc + b * 8 + 1];
+            }
+        for (int J = 0; J < nJ; ++J) {
+            while (flag_acquire(&sm.urows) < CH_NT * (J + 1)) __nanosleep(200);
+            // U^T U = sum_k u'_k u'_k^T / v_kk with the unscaled rows u'_k and v_kk the diagonal of the finished diagonal tile
+            const double vkk = sm.Lp[J][lane & 3][lane & 3][J];
+            const double ik = vkk > 0.0 ? 1.0 / vkk : 1.0;
+            double af[4], bf[4];
+#pragma unroll
+            for (int aa = 0; aa < 4; ++aa) af[aa] = lx.Trhs[CH_T * J + (lane & 3)][wm + aa * 8 + (lane >> 2)];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bf[b] = lx.Trhs[CH_T * J + (lane & 3)][wn + b * 8 + (lane >> 2)] * ik;
+#pragma unroll
+            for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) dmma884(acc[aa][b][0], acc[aa][b][1], af[aa], bf[b]);
+        }
+#pragma unroll
+        for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                double2 o;
+                o.x = -acc[aa][b][0];
+                o.y = -acc[aa][b][1];
+                *reinterpret_cast<double2*>(SnextOut + (size_t)(fr + aa * 8) * CH_R + fc + b * 8) = o;
+            }
+    }
+    if (LOOK) CH_STAMP(109);
+    __syncthreads();  // Inv published, every tile final, Lp dead
+    if (LOOK) CH_STAMP(4);
+    if (!sGroup && !LOOK) {
+        const int q = tid - CH_S_THREADS;
+        const int trow = q / CH_NT, TK = q % CH_NT;
+        if (trow < ROWS) {
+#pragma unroll
+            for (int c = 0; c < CH_T; ++c) {
+                const double sc = sm.Inv[CH_T * TK + c];
+#pragma unroll
+                for (int r = 0; r < CH_T; ++r) sm.Yt[CH_T * TK + c][CH_T * trow + r] = a[r][c] * sc;
+            }
+        }
+    }
+    __syncthreads();
+    if (LOOK) CH_STAMP(5);
+    if (!LOOK) {
+        for (int t = tid; t < CH_R * CH_COLS; t += NTHREADS) {
+            const int k = t / CH_COLS, sl = t % CH_COLS;
+            Y[yb_index(k, sbase + sl)] = sm.Yt[k][sl];
+        }
+        if (tid < CH_COLS && sbase + tid < dimp) {
+            double g = 0.0;
+#pragma unroll 8
+            for (int k = 0; k < CH_R; ++k) g += sm.Yt[k][tid] * sm.Yt[k][CH_COLS];
+            GammaOut[sbase + tid] = GammaIn[sbase + tid] + g;
+        }
+    }
+    if (LOOK) CH_STAMP(6);
+    TL_MARK(tl, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Sigma <- Sigma - Y^T Y for one chunk (K = 64 rows of Y), one 64x64 tile of Sigma per CTA, tiles on
 // or below the diagonal; the transposed tile is written too so that Sigma stays stored in full.
 // The two Y panels arrive through the TMA unit as ONE bulk copy each (cp.async.bulk, SASS UBLKCP,
@@ -1480,9 +2031,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 __global__ void __launch_bounds__(DD_THREADS, 3)
     chunk_downdate_kernel(const double* SigIn, double* SigOut, int ld, const double* __restrict__ Y,
-                          const int* __restrict__ guard, int mirrorLo, int mirrorHi, int mode, int T, int tl) {
+                          const int* __restrict__ guard, int mirrorLo, int mirrorHi, int mode, int T, int tl, int* doneCnt,
+                          const int* waitFlag) {
     pdl_wait();
     if (*guard) return;
+    if (waitFlag) {
+        // chained correction: the look-ahead kernel of this chunk still gathers blocks of the covariance BEFORE this downdate
+        if (threadIdx.x == 0) {
+            int spins = 0;
+            while (ld_acquire_gpu(waitFlag) == 0 && ++spins < (1 << 24)) __nanosleep(64);
+        }
+        __syncthreads();
+    }
     TL_MARK(tl, 0);
     int ti, tj;
     if (mode == DD_ALL) {
@@ -1571,6 +2131,11 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
                 *reinterpret_cast<double2*>(SigOut + (size_t)(i0 + fr + a * 8) * ld + j0 + fc + b * 8) = t;
             }
         }
+    if (doneCnt) {  // chained correction: the next factor launch's right-hand-side warps wait for every tile of this downdate
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(doneCnt, 1);
+    }
     TL_MARK(tl, 1);
 }
 
@@ -1739,8 +2304,9 @@ __global__ void gamma_kernel(const double* __restrict__ Z, int ldz, int m, int d
 // ------------------------------------------------------------------------------------------------
 __global__ void lift_kernel(double* __restrict__ lm, int cap, int N, const double* __restrict__ xi0s,
                             double* __restrict__ Xs, const double* __restrict__ Gamma, int discrete, int coord,
-                            int* __restrict__ status, int* __restrict__ invalidFlag, const int* __restrict__ guard) {
-    if (*guard) return;
+                            int* __restrict__ status, int* __restrict__ invalidFlag, const int* __restrict__ guard, int tl) {
+    TL_MARK(tl, 0);
+    if (*guard) { TL_MARK(tl, 1); return; }
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         SensorState xi0 = unpack_sensor(xi0s);
@@ -1772,7 +2338,7 @@ __global__ void lift_kernel(double* __restrict__ lm, int cap, int N, const doubl
         pack_group(Xn, Xs);
         if (bad) atomicOr(status, 2);
     }
-    if (i >= N) return;
+    if (i >= N) { TL_MARK(tl, 1); return; }
     V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
     Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
     double a = lm[F_QA * cap + i];
@@ -1802,6 +2368,7 @@ __global__ void lift_kernel(double* __restrict__ lm, int cap, int N, const doubl
     int inv = (a <= 1e-8 || a > 1e8) ? 1 : 0;
     invalidFlag[i] = inv;
     if (inv) atomicOr(status, 4);
+    TL_MARK(tl, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1809,19 +2376,21 @@ __global__ void lift_kernel(double* __restrict__ lm, int cap, int N, const doubl
 // ------------------------------------------------------------------------------------------------
 // stateEstimate (VIOGroup.cpp:34-55): out = sensor(23) | p(3N)
 __global__ void state_estimate_kernel(const double* __restrict__ lm, int cap, int N, const double* __restrict__ xi0s,
-                                      const double* __restrict__ Xs, double* __restrict__ out) {
+                                      const double* __restrict__ Xs, double* __restrict__ out, int tl) {
+    TL_MARK(tl, 0);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         SensorState r = sensor_group_action(unpack_group(Xs), unpack_sensor(xi0s));
         pack_sensor(r, out);
     }
-    if (i >= N) return;
+    if (i >= N) { TL_MARK(tl, 1); return; }
     V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
     Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
     V3 p = landmark_action(Q, lm[F_QA * cap + i], q0);
     out[23 + 3 * i] = p.x;
     out[23 + 3 * i + 1] = p.y;
     out[23 + 3 * i + 2] = p.z;
+    TL_MARK(tl, 1);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -221,6 +221,13 @@ int eqvio_get_host_profile(eqvio_filter* f, int reset, double us[4], long long* 
 /*   EQVIO_TUNE_PDL: 1 (default) = the chunk kernels are launched with programmatic dependent launch allowed (the next
  *                         grid is scheduled while its predecessor drains and blocks in griddepcontrol.wait); 0 = plain. */
 #define EQVIO_TUNE_PDL 8
+/*   EQVIO_TUNE_CHAIN: EXPERIMENTAL chained correction (0 = off, default).  A look-ahead kernel (one CTA) eliminates S_c with the
+ *                         projected block S_{c+1,c} as right-hand sides and hands S_{c+1} = S_pre - U^T U (rank-4 DMMA updates
+ *                         beside the elimination) to the next launches, whose elimination then does not wait for the Sigma
+ *                         downdate.  2 = those kernels in stream order (deterministic; parity-tested against mode 0 and the
+ *                         oracle); 1 = downdates concurrent on a second stream behind completion counters -- measured slower
+ *                         than mode 0 on B200 (the look-ahead CTA is the bottleneck) and NOT yet race-free: do not use. */
+#define EQVIO_TUNE_CHAIN 9
 int eqvio_set_tuning(eqvio_filter* f, int key, int value);
 /* Version / build info string (arch the kernels were compiled for). */
 const char* eqvio_build_info(void);

@@ -1,5 +1,5 @@
-"""Phase timestamps (clock64) of chunk_factor_kernel, CTA 0 -- needs a library built with -DEQVIO_CHUNK_TIMING
-at gpurun_out/libtiming.so.   python scripts/chunk_timing.py [N]"""
+"""Phase timestamps (clock64) of chunk_factor_kernel, CTA 0 -- needs a library built with -DEQVIO_CHUNK_TIMING at
+eqvio_b200/lib/libeqvio_b200_timing.so (the stamps come from the look-ahead kernel in the chained correction).   python scripts/chunk_timing.py [N]"""
 import ctypes as C
 import os
 import sys
@@ -8,9 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import shutil
 
-lib_dst = os.path.join(ROOT, "eqvio_b200", "lib", "libeqvio_b200.so")
-shutil.copy(os.path.join(ROOT, "eqvio_b200", "lib", "libtiming.so"), lib_dst)
-os.utime(lib_dst, None)
+os.environ.setdefault("EQVIO_B200_LIB", os.path.join(ROOT, "eqvio_b200", "lib", "libeqvio_b200_timing.so"))
 import numpy as np
 
 import eqvio_b200 as eb
@@ -32,8 +30,8 @@ fn.restype = C.c_int
 out = (C.c_longlong * 16)()
 assert fn(out) == 0
 t = np.array(list(out), dtype=np.int64)
-names = {0: "start", 1: "C/Idx loaded", 2: "S gather done", 3: "S loop done", 4: "final barrier", 5: "Yt staged", 6: "end", 8: "RHS gather done",
-         9: "RHS loop done"}
+names = {0: "start", 1: "C/Idx loaded", 2: "S gather done", 3: "S loop done", 4: "final barrier", 5: "Yt staged", 6: "end", 7: "RHS wait done",
+         10: "look: Spre gathered", 8: "RHS gather done", 9: "RHS loop done"}
 base = t[0]
 for i in sorted(names):
     print(f"{names[i]:>18s}: {t[i] - base:8d} cycles")

@@ -33,10 +33,17 @@ for k, fr in enumerate(sm.frames):
         fn(flt._h, buf, 512, 1)
     flt.processVisionArrays(fr.stamp, fr.ids, fr.y, cam)
 n = fn(flt._h, buf, 512, 0)
+nm = _capi.lib.eqvio_debug_timeline_name
+nm.restype = C.c_char_p
+nm.argtypes = [C.c_void_p, C.c_int]
 t = np.array(buf[:2 * n], dtype=np.float64).reshape(n, 2)
-t = t[t[:, 1] > 0]  # slots stamped since the reset (a replayed graph keeps the slot numbers of its capture)
+valid = np.nonzero(t[:, 1] > 0)[0]  # slots stamped since the reset (a replayed graph keeps the slot numbers of its capture)
+names = [nm(flt._h, int(i)).decode() for i in valid]
+t = t[valid]
+order = np.argsort(t[:, 0], kind="stable")
+t, names = t[order], [names[i] for i in order]
 n = len(t)
 t0 = t[:, 0].min()
 print(f"N={N} lookahead={look} graph={graph}: {n} launches, span {(t[:, 1].max() - t0) / 1e3:.1f} us")
 for i in range(n):
-    print(f"{i:3d}  start {(t[i, 0] - t0) / 1e3:8.1f}  end {(t[i, 1] - t0) / 1e3:8.1f}  dur {(t[i, 1] - t[i, 0]) / 1e3:6.1f}")
+    print(f"{i:3d}  start {(t[i, 0] - t0) / 1e3:8.1f}  end {(t[i, 1] - t0) / 1e3:8.1f}  dur {(t[i, 1] - t[i, 0]) / 1e3:6.1f}  {names[i]}")

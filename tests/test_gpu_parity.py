@@ -28,6 +28,20 @@ def _check(gpu, ref, tol=TOL):
     return worst
 
 
+@pytest.mark.parametrize("N,chunk,coord", [(40, 8, 0), (100, 32, 1), (150, 32, 0), (70, 5, 0), (33, 32, 0)])
+def test_chained_correction_kernels(N, chunk, coord):
+    """Experimental chained correction, stream-order mode (EQVIO_TUNE_CHAIN = 2): the look-ahead kernel hands S_{c+1} to the
+    next factor launch in measurement space (S_pre - U^T U) instead of gathering it from the downdated covariance.  Same
+    result as the default per-chunk factor -> downdate sequence to rounding, and parity with the oracle."""
+    stream = make_stream(N=N, frames=8, coord=coord)
+    chained = run_gpu(stream, tuning=dict(chain=2, graph=0, chunkLandmarks=chunk))
+    default = run_gpu(stream, tuning=dict(chain=0, graph=0, chunkLandmarks=chunk))
+    for g, r in zip(chained, default):
+        e = compare_states(g, r)
+        assert e["ids_equal"] and e["sigma"] < 5e-11 and e["state"] < 5e-11
+    _check(chained, run_oracle(stream))
+
+
 @pytest.mark.parametrize("discrete", [1, 0])
 def test_fused_observer_matches_two_kernel_form(discrete):
     """integrateObserverState as one software-pipelined kernel (sensor chain publishing segments to the landmark warps)
