@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--sequences-per-gpu", type=int, default=1, help="independent sequences (replicas) run concurrently per GPU")
     ap.add_argument("--no-graph", action="store_true", help="issue per-kernel launches instead of replaying CUDA graphs")
     ap.add_argument("--pipeline", action="store_true", help="experimental: overlap chunk c+1's factor kernel with chunk c's downdate")
+    ap.add_argument("--chain", type=int, default=None, help="EQVIO_TUNE_CHAIN (experimental chained correction): 0 / 1 / 2")
     ap.add_argument("--no-lookahead", action="store_true", help="one in-order downdate launch per chunk (no band / rest split)")
     ap.add_argument("--downdate", default="f64", choices=["f64", "tc"],
                     help="f64: DMMA fp64 downdate (default); tc: tcgen05 split-bf16 operands, fp32 accumulate in TMEM (BASELINE configs[2])")
@@ -236,6 +237,8 @@ def run_b200(args, rank, local_rank, world):
             flt.setTuning(graph=0)
         if args.pipeline:
             flt.setTuning(pipeline=1)
+        if args.chain is not None:
+            flt.setTuning(chain=args.chain)
         if args.no_lookahead:
             flt.setTuning(lookahead=0)
         if args.downdate == "tc":

@@ -88,6 +88,8 @@ struct eqvio_filter {
     // fixed pinned output block of the steady path: gate scalars | spec flag | status words
     unsigned char* h_out = nullptr;
     size_t outOffSpec = 0, outOffStatus = 0, outOffEst = 0, outBytes = 0;
+    unsigned char* d_mapblk = nullptr;  // d_newP | d_map | d_newIds
+    size_t mapBlkBytes = 0;
     unsigned char* d_outblk = nullptr;  // device mirror of h_out: d_gate / d_spec / d_status / d_out point into it
     bool estValid = false;  // h_out holds the state estimate of the current state (produced by the steady update)
     // CUDA graphs of the steady-state update, keyed by everything that shapes the launch sequence
@@ -114,6 +116,7 @@ struct eqvio_filter {
     int chain = 0;         // 0 = off (default); 2 = chained correction kernels in stream order; 1 = with concurrent downdates (experimental)
     int* d_cnt = nullptr;  // per-chunk completion counters of the downdates (chained correction)
     double* d_Snext[2] = {nullptr, nullptr};  // S block handed from one factor launch to the next
+    int prLeast = 0, prGreatest = 0;  // stream priority range of the device
     bool pdlHold = false;  // next launch_pdl is a plain launch (its predecessor produces what the kernel reads before its wait)
     int pdl = 1;           // chunk kernels are launched with programmatic dependent launch allowed
     int fuseObserver = 1;  // sensor + landmark parts of the observer integration as one software-pipelined kernel
@@ -292,11 +295,15 @@ cudaError_t launch_pdl(eqvio_filter* f, void (*kernel)(KArgs...), dim3 grid, dim
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = (f->pdl && !f->pdlHold) ? 1 : 0;
+    // explicit launch priority (that of the stream): a captured kernel node keeps it, so that the block scheduler still
+    // prefers the critical-path kernels over the deferred downdate tiles when the update is replayed as a graph
+    attr[1].id = cudaLaunchAttributePriority;
+    attr[1].val.priority = st == f->stream3 ? f->prLeast : f->prGreatest;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -419,6 +426,8 @@ int alloc_device(eqvio_filter* f) {
         // of the queued tile CTAs, not after them
         int prLeast = 0, prGreatest = 0;
         CUDA_TRY(f, cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest));
+        f->prLeast = prLeast;
+        f->prGreatest = prGreatest;
         CUDA_TRY(f, cudaStreamCreateWithPriority(&f->stream2, cudaStreamNonBlocking, prGreatest));
         CUDA_TRY(f, cudaStreamCreateWithPriority(&f->stream3, cudaStreamNonBlocking, prLeast));
     }
@@ -443,7 +452,6 @@ int alloc_device(eqvio_filter* f) {
     CUDA_TRY(f, cudaMalloc(&f->d_Gamma, (size_t)(dimpMax + 8) * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Gamma2, (size_t)(dimpMax + 8) * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_ytilde, 2 * c1 * sizeof(double)));
-    CUDA_TRY(f, cudaMalloc(&f->d_newP, c1 * 3 * sizeof(double)));
     // everything the host reads back after an update lives in ONE device block with the layout of the pinned h_out:
     // gate scalars | gate flag (+ a constant 0) | status words | state estimate  -- a steady frame downloads it with one copy
     f->outOffSpec = ((3 * c1 * sizeof(double)) + 63) & ~size_t(63);
@@ -460,8 +468,12 @@ int alloc_device(eqvio_filter* f) {
     CUDA_TRY(f, cudaMalloc(&f->d_cnt, 2 * (c1 + 1) * sizeof(int)));
     CUDA_TRY(f, cudaMemsetAsync(f->d_cnt, 0, 2 * (c1 + 1) * sizeof(int), f->stream));
     for (int k = 0; k < 2; ++k) CUDA_TRY(f, cudaMalloc(&f->d_Snext[k], CH_R * CH_R * sizeof(double)));
-    CUDA_TRY(f, cudaMalloc(&f->d_map, c1 * sizeof(int)));
-    CUDA_TRY(f, cudaMalloc(&f->d_newIds, c1 * sizeof(int)));
+    // landmark-set changes arrive as ONE block: new positions | old-index map | new ids  (a single upload per change)
+    f->mapBlkBytes = c1 * (3 * sizeof(double) + 2 * sizeof(int));
+    CUDA_TRY(f, cudaMalloc(&f->d_mapblk, f->mapBlkBytes));
+    f->d_newP = reinterpret_cast<double*>(f->d_mapblk);
+    f->d_map = reinterpret_cast<int*>(f->d_mapblk + c1 * 3 * sizeof(double));
+    f->d_newIds = f->d_map + c1;
     for (int i = 0; i < 2; ++i) CUDA_TRY(f, cudaEventCreate(&f->augEv[i]));
     for (int i = 0; i < 4; ++i) CUDA_TRY(f, cudaEventCreate(&f->stageEv[i]));
     return EQVIO_OK;
@@ -533,10 +545,22 @@ int apply_map(eqvio_filter* f, const std::vector<int>& map, const std::vector<in
     std::vector<int> nids(newN);
     for (int p = 0; p < newN; ++p) nids[p] = map[p] >= 0 ? f->ids[map[p]] : newIds[-1 - map[p]];
     if (newN > 0) {
-        if ((rc = upload(f, f->d_map, map.data(), newN)) != EQVIO_OK) return rc;
-        if (!newIds.empty()) {
-            if ((rc = upload(f, f->d_newIds, newIds.data(), newIds.size())) != EQVIO_OK) return rc;
-            if ((rc = upload(f, f->d_newP, newP.data(), newP.size())) != EQVIO_OK) return rc;
+        {
+            const size_t c1 = (size_t)std::max(f->cap, 1);
+            const size_t offMap = c1 * 3 * sizeof(double), offIds = offMap + c1 * sizeof(int);
+            // upload the prefix that is in use: positions (if any), the map, the new ids (if any)
+            const size_t bytes = newIds.empty() ? offMap + (size_t)newN * sizeof(int) : offIds + newIds.size() * sizeof(int);
+            unsigned char* h = static_cast<unsigned char*>(stage_alloc(f, bytes));
+            if (!h) {
+                f->err = "pinned staging allocation failed";
+                return EQVIO_ERR_CUDA;
+            }
+            if (!newP.empty()) std::memcpy(h, newP.data(), newP.size() * sizeof(double));
+            std::memcpy(h + offMap, map.data(), (size_t)newN * sizeof(int));
+            if (!newIds.empty()) std::memcpy(h + offIds, newIds.data(), newIds.size() * sizeof(int));
+            // without new landmarks only the map travels
+            const size_t from = newIds.empty() ? offMap : 0;
+            CUDA_TRY(f, cudaMemcpyAsync(f->d_mapblk + from, h + from, bytes - from, cudaMemcpyHostToDevice, f->stream));
         }
         compact_landmarks_kernel<<<cdiv(newN, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->lm[1 - f->lmcur], f->cap,
                                                                           f->dids[f->lmcur], f->dids[1 - f->lmcur], f->d_map,
@@ -661,13 +685,13 @@ int enqueue_propagation(eqvio_filter* f) {
         riccati_prep_kernel<<<1, 448, 0, f->stream>>>(a, Sin, Sout, f->ld, nullptr, f->d_spec, TL_SLOT(f));  // also re-arms the gate flag
         LAUNCH_CHECK(f, "riccati_prep_kernel");
         if (N > 0) {
-            landmark_rows_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_ctx, s.coordinateChoice, f->d_rows, TL_SLOT(f));
+            launch_pdl(f, landmark_rows_kernel, dim3(cdiv(N, 64)), dim3(64), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, N, f->d_ctx, s.coordinateChoice, f->d_rows, TL_SLOT(f));
             LAUNCH_CHECK(f, "landmark_rows_kernel");
-            prop_strip_kernel<<<cdiv(N, PS_LM), PS_LM * PS_TPL, 0, f->stream>>>(Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv, TL_SLOT(f));
+            launch_pdl(f, prop_strip_kernel, dim3(cdiv(N, PS_LM)), dim3(PS_LM * PS_TPL), (size_t)(0), f->stream, Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv, TL_SLOT(f));
             LAUNCH_CHECK(f, "prop_strip_kernel");
             const int nt = cdiv(N, TP);
             int pk = prof_begin(f, PROF_PROP_LL);
-            prop_ll_kernel<<<dim3(nt, nt), dim3(TP, TP), 0, f->stream>>>(Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv, TL_SLOT(f));
+            launch_pdl(f, prop_ll_kernel, dim3(dim3(nt, nt)), dim3(dim3(TP, TP)), (size_t)(0), f->stream, Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv, TL_SLOT(f));
             prof_end(f, pk);
             LAUNCH_CHECK(f, "prop_ll_kernel");
         }
@@ -731,7 +755,7 @@ int enqueue_propagation_accurate(eqvio_filter* f) {
             riccati_prep_kernel<<<1, 448, 0, f->stream>>>(a, Sin, Sout, f->ld, w.dtBs, nullptr, TL_SLOT(f));
             LAUNCH_CHECK(f, "riccati_prep_kernel");
             if (N > 0) {
-                landmark_rows_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_ctx, s.coordinateChoice, f->d_rows, TL_SLOT(f));
+                launch_pdl(f, landmark_rows_kernel, dim3(cdiv(N, 64)), dim3(64), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, N, f->d_ctx, s.coordinateChoice, f->d_rows, TL_SLOT(f));
                 LAUNCH_CHECK(f, "landmark_rows_kernel");
             }
             CUDA_TRY(f, cudaMemsetAsync(M, 0, (size_t)n * n * sizeof(double), f->stream));
@@ -776,7 +800,7 @@ int enqueue_propagation_accurate(eqvio_filter* f) {
 
 int enqueue_gate(eqvio_filter* f, int N, bool clearFlag) {
     if (clearFlag) CUDA_TRY(f, cudaMemsetAsync(f->d_spec, 0, sizeof(int), f->stream));
-    gate_kernel<<<cdiv(N, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->Sig[f->cur], f->ld, f->d_measIdx, f->d_y,
+    launch_pdl(f, gate_kernel, dim3(cdiv(N, 128)), dim3(128), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, N, f->Sig[f->cur], f->ld, f->d_measIdx, f->d_y,
                                                       f->d_hdr, f->st.coordinateChoice, f->d_gate, f->st.outlierThresholdAbs,
                                                       f->st.outlierThresholdProb, f->d_spec, TL_SLOT(f));
     LAUNCH_CHECK(f, "gate_kernel");
@@ -795,7 +819,7 @@ int enqueue_steady_update(eqvio_filter* f, int N, int nm) {
     if ((rc = enqueue_gate(f, N, false)) != EQVIO_OK) return rc;  // riccati_prep_kernel re-armed the flag
     if ((rc = enqueue_correction(f, nm, f->d_spec)) != EQVIO_OK) return rc;
     // stateEstimate() is what every caller asks for next (main_opt.cpp:225, main_sim.cpp:146): produce it here
-    state_estimate_kernel<<<cdiv(N, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_xi0s, f->d_Xs[f->xcur], f->d_out, TL_SLOT(f));
+    launch_pdl(f, state_estimate_kernel, dim3(cdiv(N, 128)), dim3(128), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, N, f->d_xi0s, f->d_Xs[f->xcur], f->d_out, TL_SLOT(f));
     LAUNCH_CHECK(f, "state_estimate_kernel");
     // one download: gate scalars, gate flag, status words, state estimate (the block has the layout of h_out)
     CUDA_TRY(f, cudaMemcpyAsync(f->h_out, f->d_outblk, f->outOffEst + (23 + 3 * (size_t)N) * sizeof(double), cudaMemcpyDeviceToHost,
@@ -1232,7 +1256,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
                 const int bc = std::min(bcMax, nm - j0);
                 double* Yc = Ybuf[c & 1];
                 cudaEvent_t evF = f->chunkEv[2 * c], evR = f->chunkEv[2 * c + 1];
-                launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), sizeof(ChunkSmem), f->stream, f->Sig[f->cur], f->ld,
+                launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), (size_t)CH_SMEM_BASE, f->stream, f->Sig[f->cur], f->ld,
                            dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Yc, f->d_status, guard, nullptr, TL_SLOT(f));
                 LAUNCH_CHECK(f, "chunk_factor_kernel");
                 std::swap(gin, gout);
@@ -1260,8 +1284,10 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
                 LAUNCH_CHECK(f, "chunk_downdate_kernel");
                 CUDA_TRY(f, cudaStreamWaitEvent(f->stream3, evF, 0));
                 if (nRest > 0) {
-                    chunk_downdate_kernel<<<nRest, DD_THREADS, DD_SMEM, f->stream3>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Yc, guard, mlo,
-                                                                                      mhi, DD_REST, T, TL_SLOT(f), nullptr, nullptr);
+                    f->pdlHold = true;
+                    launch_pdl(f, chunk_downdate_kernel, dim3(nRest), dim3(DD_THREADS), (size_t)DD_SMEM, f->stream3, (const double*)f->Sig[f->cur],
+                               f->Sig[f->cur], f->ld, (const double*)Yc, guard, mlo, mhi, (int)DD_REST, T, TL_SLOT(f), (int*)nullptr, (const int*)nullptr);
+                    f->pdlHold = false;
                     LAUNCH_CHECK(f, "chunk_downdate_kernel");
                 }
                 CUDA_TRY(f, cudaEventRecord(evR, f->stream3));
@@ -1270,7 +1296,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
             for (int j0 = 0; j0 < nm; j0 += bcMax) {
                 const int bc = std::min(bcMax, nm - j0);
                 int pk = prof_begin(f, PROF_PANEL);
-                launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), sizeof(ChunkSmem), f->stream, f->Sig[f->cur], f->ld,
+                launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), (size_t)CH_SMEM_BASE, f->stream, f->Sig[f->cur], f->ld,
                            dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Y, f->d_status, guard, nullptr, TL_SLOT(f));
                 prof_end(f, pk);
                 LAUNCH_CHECK(f, "chunk_factor_kernel");
@@ -1381,7 +1407,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
     gamma_kernel<<<cdiv(dimp, 128), 128, m * sizeof(double), f->stream>>>(Z, ldz, m, dimp, f->d_Gamma);
     LAUNCH_CHECK(f, "gamma_kernel");
     }
-    lift_kernel<<<cdiv(std::max(Nn, 1), 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, Nn, f->d_xi0s, f->d_Xs[f->xcur], gammaFinal,
+    launch_pdl(f, lift_kernel, dim3(cdiv(std::max(Nn, 1), 128)), dim3(128), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, Nn, f->d_xi0s, f->d_Xs[f->xcur], gammaFinal,
                                                                    s.useDiscreteInnovationLift ? 1 : 0, s.coordinateChoice,
                                                                    f->d_status, f->d_status + 1, guard, TL_SLOT(f));
     LAUNCH_CHECK(f, "lift_kernel");
@@ -1487,6 +1513,9 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
         return EQVIO_ERR_CUDA;
     }
     e = cudaFuncSetAttribute(chunk_downdate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM);
+    // factor CTAs of the next chunk must fit beside the deferred downdate CTAs: keep the shared-memory carve-out at its maximum
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChunkSmem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Chunk2Smem));
@@ -1725,7 +1754,6 @@ void eqvio_destroy(eqvio_filter* f) {
     cudaFree(f->d_Gamma);
     cudaFree(f->d_Gamma2);
     cudaFree(f->d_ytilde);
-    cudaFree(f->d_newP);
     cudaFree(f->d_frame);
     cudaFree(f->d_hdrSteps);
     f->dense.release();
@@ -1737,8 +1765,7 @@ void eqvio_destroy(eqvio_filter* f) {
     cudaFree(f->d_Snext[1]);
     for (auto& g : f->graphs)
         if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
-    cudaFree(f->d_map);
-    cudaFree(f->d_newIds);
+    cudaFree(f->d_mapblk);
     for (int i = 0; i < 2; ++i)
         if (f->augEv[i]) cudaEventDestroy(f->augEv[i]);
     for (auto& A : f->arenaSets) {
@@ -1849,17 +1876,23 @@ int eqvio_augment_landmark_states(eqvio_filter* f, int n_new, const int* new_ids
         auto it = std::lower_bound(idx.begin(), idx.end(), std::make_pair(id, -1));
         return (it != idx.end() && it->first == id) ? it->second : -1;
     };
-    std::vector<std::pair<int, int>> want, prov, have;
+    std::vector<std::pair<int, int>> want, prov;
     make_index(n_new, new_ids, want);
     make_index(n_provided, provided_ids, prov);
-    make_index(N, f->ids.data(), have);
-    std::vector<char> keep(N, 1);
-    for (int i = 0; i < N; ++i)
-        if (find_in(want, f->ids[i]) < 0) keep[i] = 0;
+    // one pass over the state: which state ids are wanted (keep) and which wanted ids are already in the state -- no index of
+    // the (unsorted) state id list is needed
+    std::vector<char> keep(N, 1), inState(n_new, 0);
+    for (int i = 0; i < N; ++i) {
+        const int j = find_in(want, f->ids[i]);
+        if (j < 0)
+            keep[i] = 0;
+        else
+            inState[j] = 1;
+    }
     std::vector<int> addIds;
     std::vector<double> addP;
     for (int j = 0; j < n_new; ++j) {
-        if (find_in(have, new_ids[j]) >= 0) continue;
+        if (inState[j]) continue;
         bool dup = false;
         for (int a : addIds) dup |= (a == new_ids[j]);
         if (dup) continue;
@@ -1992,7 +2025,7 @@ int eqvio_get_state_estimate(eqvio_filter* f, double sensor[23], int* ids, doubl
         return EQVIO_OK;
     }
     stage_reset(f);
-    state_estimate_kernel<<<cdiv(std::max(N, 1), 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, f->d_xi0s, f->d_Xs[f->xcur], f->d_out, TL_SLOT(f));
+    launch_pdl(f, state_estimate_kernel, dim3(cdiv(std::max(N, 1), 128)), dim3(128), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, N, f->d_xi0s, f->d_Xs[f->xcur], f->d_out, TL_SLOT(f));
     LAUNCH_CHECK(f, "state_estimate_kernel");
     double* h = nullptr;
     int rc = download_async(f, &h, f->d_out, 23 + 3 * (size_t)N);

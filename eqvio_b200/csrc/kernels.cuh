@@ -71,6 +71,12 @@ struct PrepArgs {
     double pdiag[8];  // process variances per 3-block + point     (VIOFilterSettings.h:176-190)
 };
 
+// Programmatic dependent launch: block until the preceding grid on the stream has completed and its writes are visible,
+// then let the NEXT grid be scheduled early (it blocks in its own pdl_wait).  No-ops for a plain launch.
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 // Debug timeline (library built with -DEQVIO_TIMELINE): first-start / last-end globaltimer stamps per launch slot of the
 // chunk kernels, read back by eqvio_debug_timeline -- shows how the look-ahead launches overlap on the device.
 #ifdef EQVIO_TIMELINE
@@ -246,6 +252,7 @@ __global__ void observer_sensor_kernel(PrepArgs a, int tl) {
 __global__ void __launch_bounds__(448)
     riccati_prep_kernel(PrepArgs a, const double* __restrict__ Sin, double* __restrict__ Sout, int ld, double* __restrict__ dtBsOut,
                         int* __restrict__ clearFlag, int tl) {
+    pdl_wait();
     TL_MARK(tl, 0);
     __shared__ double sAs[441], sBs[252], sF[441], sS[441], sT[441];
     const int t = threadIdx.x;
@@ -294,6 +301,7 @@ constexpr int ROWS_STRIDE = 54;
 
 __global__ void landmark_rows_kernel(const double* __restrict__ lm, int cap, int N, const RiccatiCtx* __restrict__ ctx, int coord,
                                      double* __restrict__ rows, int tl) {
+    pdl_wait();
     TL_MARK(tl, 0);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) { TL_MARK(tl, 1); return; }
@@ -506,6 +514,7 @@ constexpr int PS_LM = 8, PS_TPL = 24;  // landmarks per CTA, threads per landmar
 __global__ void __launch_bounds__(PS_LM* PS_TPL)
     prop_strip_kernel(const double* __restrict__ Sin, double* __restrict__ Sout, int ld, int N,
                       const RiccatiCtx* __restrict__ ctx, const double* __restrict__ rows, double* __restrict__ uv, int tl) {
+    pdl_wait();
     TL_MARK(tl, 0);
     __shared__ double sF[441], sS[441], sBG[63];
     __shared__ double sRow[PS_LM][ROWS_STRIDE];  // D(9) | G(36) | Bl(9)
@@ -602,6 +611,7 @@ __global__ void __launch_bounds__(TP* TP)
     prop_ll_kernel(const double* __restrict__ Sin, double* __restrict__ Sout, int ld, int N,
                    const RiccatiCtx* __restrict__ ctx, const double* __restrict__ rows,
                    const double* __restrict__ uv, int tl) {
+    pdl_wait();
     TL_MARK(tl, 0);
     const int ti = blockIdx.y, tj = blockIdx.x;
     if (tj > ti) { TL_MARK(tl, 1); return; }
@@ -661,6 +671,7 @@ __global__ void __launch_bounds__(TP* TP)
 __global__ void gate_kernel(const double* __restrict__ lm, int cap, int N, const double* __restrict__ Sig, int ld,
                             const int* __restrict__ measIdx, const double* __restrict__ y, const FrameHeader* __restrict__ fr, int coord,
                             double* __restrict__ out, double thrAbs, double thrProb, int* __restrict__ tripped, int tl) {
+    pdl_wait();
     TL_MARK(tl, 0);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) { TL_MARK(tl, 1); return; }
@@ -782,6 +793,7 @@ __global__ void meas_kernel(const double* __restrict__ lm, int cap, const int* _
                             double* __restrict__ Cblk, double* __restrict__ Z, int ldz, int yrow,
                             const int* __restrict__ guard, const int* __restrict__ yIdx, int* __restrict__ zeroStatus, int nStatus,
                             double* __restrict__ zeroGamma, int nGamma, int* __restrict__ zeroCnt, int nCnt, int tl) {
+    pdl_wait();
     TL_MARK(tl, 0);
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     // first kernel of the correction: clears the status words and the Gamma accumulator (also when the guard is set)
@@ -1055,13 +1067,17 @@ struct ChunkSmem {
     double Dc[CH_NT][CH_T];                   // reciprocal pivots of block column J
     double C[CH_R / 2][6];
     double Inv[CH_R];
-    // pending downdate of the previous chunk (pipelined mode): u-vectors of the augmented rows,
-    // Us[k][p] = C_c Yprev[k, L_c] for the S rows, Ur[k][sl] = Yprev[k, sbase + sl] for the right-hand-side rows
-    double Us[CH_R][CH_R + 4];
-    double Ur[CH_R][CH_RHS_ROWS * CH_T + 4];
     int Idx[CH_R / 2];
     int ready;                                // block columns of S_c whose panels are published (release / acquire)
+    int pad_;
+    // pending downdate of the previous chunk (pipelined mode ONLY -- the launch allocates the struct up to here otherwise, so
+    // that a factor CTA fits beside two downdate CTAs on one SM):
+    // Us[k][p] = C_c Yprev[k, L_c] for the S rows, Ur[k][sl] = Yprev[k, sbase + sl] for the right-hand-side rows
+    alignas(16) double Us[CH_R][CH_R + 4];
+    alignas(16) double Ur[CH_R][CH_RHS_ROWS * CH_T + 4];
 };
+constexpr int CH_SMEM_BASE = (int)offsetof(ChunkSmem, Us);
+
 
 // reciprocal to <= 1 ulp: hardware approximation + two Newton steps (a correctly rounded division is
 // ~3x longer and sits on the critical path of every elimination step)
@@ -1086,12 +1102,6 @@ __device__ long long g_chunk_t[16];
 #else
 #define CH_STAMP(i) do { } while (0)
 #endif
-// Programmatic dependent launch: block until the preceding grid on the stream has completed and its writes are visible,
-// then let the NEXT grid be scheduled early (it blocks in its own pdl_wait).  No-ops for a plain launch.
-__device__ __forceinline__ void pdl_wait() {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
 // progress flag between the two warp groups of chunk_factor_kernel: release store / acquire load at CTA scope
 __device__ __forceinline__ void flag_release(int* p, int v) {
     asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
@@ -1485,7 +1495,7 @@ struct Chunk2Smem {
     int IdxN[CH_R / 2];
     int ready;
     int t1ready;                     // look-ahead kernel: the row-projected blocks are staged
-    int urows;                       // look-ahead kernel: half-warps that have published their rows of U (16 per block column)
+    int urows[CH_NT];                // look-ahead kernel: half-warps that have published rows 4J..4J+3 of U, per block column J
 };
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;
@@ -1537,8 +1547,8 @@ __global__ void __launch_bounds__(LOOK ? LOOK_THREADS : CH_THREADS)
     if (tid == 0) {
         sm.ready = 0;
         sm.t1ready = 0;
-        sm.urows = 0;
     }
+    if (LOOK && tid < CH_NT) sm.urows[tid] = 0;
     pdl_wait();
     if (*guard) return;
     TL_MARK(tl, 0);
@@ -1859,7 +1869,7 @@ __global__ void __launch_bounds__(LOOK ? LOOK_THREADS : CH_THREADS)
 #pragma unroll
                         for (int r = 0; r < CH_T; ++r) lx.Trhs[CH_T * J + cc][CH_T * trow + r] = a[r][cc];  // unscaled: v_sk = L_sk L_kk
                     __threadfence_block();
-                    atomicAdd(&sm.urows, 1);
+                    atomicAdd(&sm.urows[J], 1);
                 }
             }
             double li[CH_T][CH_T];
@@ -1932,7 +1942,7 @@ __global__ void __launch_bounds__(LOOK ? LOOK_THREADS : CH_THREADS)
                 acc[aa][b][1] = -sm.Spre[fr + aa * 8][fc + b * 8 + 1];
             }
         for (int J = 0; J < nJ; ++J) {
-            while (flag_acquire(&sm.urows) < CH_NT * (J + 1)) __nanosleep(200);
+            while (flag_acquire(&sm.urows[J]) < CH_NT) __nanosleep(200);
             // U^T U = sum_k u'_k u'_k^T / v_kk with the unscaled rows u'_k and v_kk the diagonal of the finished diagonal tile
             const double vkk = sm.Lp[J][lane & 3][lane & 3][J];
             const double ik = vkk > 0.0 ? 1.0 / vkk : 1.0;
@@ -2305,6 +2315,7 @@ __global__ void gamma_kernel(const double* __restrict__ Z, int ldz, int m, int d
 __global__ void lift_kernel(double* __restrict__ lm, int cap, int N, const double* __restrict__ xi0s,
                             double* __restrict__ Xs, const double* __restrict__ Gamma, int discrete, int coord,
                             int* __restrict__ status, int* __restrict__ invalidFlag, const int* __restrict__ guard, int tl) {
+    pdl_wait();
     TL_MARK(tl, 0);
     if (*guard) { TL_MARK(tl, 1); return; }
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2377,6 +2388,7 @@ __global__ void lift_kernel(double* __restrict__ lm, int cap, int N, const doubl
 // stateEstimate (VIOGroup.cpp:34-55): out = sensor(23) | p(3N)
 __global__ void state_estimate_kernel(const double* __restrict__ lm, int cap, int N, const double* __restrict__ xi0s,
                                       const double* __restrict__ Xs, double* __restrict__ out, int tl) {
+    pdl_wait();
     TL_MARK(tl, 0);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {

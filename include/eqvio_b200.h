@@ -225,8 +225,9 @@ int eqvio_get_host_profile(eqvio_filter* f, int reset, double us[4], long long* 
  *                         projected block S_{c+1,c} as right-hand sides and hands S_{c+1} = S_pre - U^T U (rank-4 DMMA updates
  *                         beside the elimination) to the next launches, whose elimination then does not wait for the Sigma
  *                         downdate.  2 = those kernels in stream order (deterministic; parity-tested against mode 0 and the
- *                         oracle); 1 = downdates concurrent on a second stream behind completion counters -- measured slower
- *                         than mode 0 on B200 (the look-ahead CTA is the bottleneck) and NOT yet race-free: do not use. */
+ *                         oracle); 1 = downdates concurrent on a second stream behind completion counters (bit-identical to
+ *                         mode 2 in the tests).  Measured slower than mode 0 on B200 (3040 vs 3320 updates/s at N = 256: the
+ *                         single look-ahead CTA becomes the per-chunk bottleneck), hence off by default. */
 #define EQVIO_TUNE_CHAIN 9
 int eqvio_set_tuning(eqvio_filter* f, int key, int value);
 /* Version / build info string (arch the kernels were compiled for). */

@@ -42,6 +42,19 @@ def test_chained_correction_kernels(N, chunk, coord):
     _check(chained, run_oracle(stream))
 
 
+@pytest.mark.parametrize("N,chunk,coord", [(100, 32, 1), (150, 32, 0), (70, 5, 0)])
+def test_chained_correction_concurrent_downdates(N, chunk, coord):
+    """EQVIO_TUNE_CHAIN = 1: the same kernels with the downdates on a second stream behind completion counters must give
+    the bits of the stream-order mode (any race would show), with and without graph replay."""
+    stream = make_stream(N=N, frames=8, coord=coord)
+    serial = run_gpu(stream, tuning=dict(chain=2, graph=0, chunkLandmarks=chunk))
+    for graph in (0, 1):
+        got = run_gpu(stream, tuning=dict(chain=1, graph=graph, chunkLandmarks=chunk))
+        for g, r in zip(got, serial):
+            e = compare_states(g, r)
+            assert e["ids_equal"] and e["sigma"] == 0.0 and e["state"] == 0.0
+
+
 @pytest.mark.parametrize("discrete", [1, 0])
 def test_fused_observer_matches_two_kernel_form(discrete):
     """integrateObserverState as one software-pipelined kernel (sensor chain publishing segments to the landmark warps)
