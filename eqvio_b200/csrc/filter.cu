@@ -1256,8 +1256,10 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
                 const int bc = std::min(bcMax, nm - j0);
                 double* Yc = Ybuf[c & 1];
                 cudaEvent_t evF = f->chunkEv[2 * c], evR = f->chunkEv[2 * c + 1];
+                f->pdlHold = (j0 == 0);  // chunk 0 follows meas_kernel, whose output the kernel stages ahead of its dependency wait
                 launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), (size_t)CH_SMEM_BASE, f->stream, f->Sig[f->cur], f->ld,
                            dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Yc, f->d_status, guard, nullptr, TL_SLOT(f));
+                f->pdlHold = false;
                 LAUNCH_CHECK(f, "chunk_factor_kernel");
                 std::swap(gin, gout);
                 if (c > 0) CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * (c - 1) + 1], 0));  // rest(c-1) done
@@ -1296,9 +1298,11 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
             for (int j0 = 0; j0 < nm; j0 += bcMax) {
                 const int bc = std::min(bcMax, nm - j0);
                 int pk = prof_begin(f, PROF_PANEL);
+                f->pdlHold = (j0 == 0);  // chunk 0 follows meas_kernel, whose output the kernel stages ahead of its dependency wait
                 launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), (size_t)CH_SMEM_BASE, f->stream, f->Sig[f->cur], f->ld,
                            dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Y, f->d_status, guard, nullptr, TL_SLOT(f));
                 prof_end(f, pk);
+                f->pdlHold = false;
                 LAUNCH_CHECK(f, "chunk_factor_kernel");
                 int sk = prof_begin(f, PROF_SYRK);
                 if (f->downdateTC) {
@@ -1356,6 +1360,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
                 chunk_factor_kernel<<<ldy / CH_COLS, CH_THREADS, sizeof(ChunkSmem), f->stream>>>(
                     f->Sig[cfIn], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Ybuf[c & 1], f->d_status, guard,
                     c > 0 ? Ybuf[(c - 1) & 1] : nullptr, TL_SLOT(f));
+                f->pdlHold = false;
                 LAUNCH_CHECK(f, "chunk_factor_kernel");
                 CUDA_TRY(f, cudaEventRecord(evF, f->stream));
                 CUDA_TRY(f, cudaStreamWaitEvent(f->stream2, evF, 0));

@@ -1128,9 +1128,8 @@ __global__ void __launch_bounds__(CH_THREADS)
                         const double* __restrict__ Cblk, const double* __restrict__ ytilde, int j0, int bc, double r2,
                         const double* __restrict__ GammaIn, double* __restrict__ GammaOut, double* __restrict__ Y,
                         int* __restrict__ status, const int* __restrict__ guard, const double* __restrict__ Yprev, int tl) {
-    pdl_wait();
-    if (*guard) return;
-    TL_MARK(tl, 0);
+    // Cblk / lmOf come from meas_kernel and the frame upload (the host launches chunk 0 as a plain launch, later chunks follow
+    // other chunk kernels): they are staged BEFORE the dependency wait, so the set-up overlaps the predecessor's tail
     extern __shared__ __align__(16) unsigned char chunk_smem_raw[];
     ChunkSmem& sm = *reinterpret_cast<ChunkSmem*>(chunk_smem_raw);
     const int tid = threadIdx.x;
@@ -1139,6 +1138,9 @@ __global__ void __launch_bounds__(CH_THREADS)
     for (int t = tid; t < bc * 6; t += CH_THREADS) sm.C[t / 6][t % 6] = Cblk[6 * (size_t)j0 + t];
     for (int t = tid; t < bc; t += CH_THREADS) sm.Idx[t] = SOFF + 3 * lmOf[j0 + t];
     if (tid == 0) sm.ready = 0;
+    pdl_wait();
+    if (*guard) return;
+    TL_MARK(tl, 0);
     __syncthreads();
     CH_STAMP(1);
     // Pipelined mode: Sig is the covariance BEFORE the previous chunk's downdate (that downdate is running
