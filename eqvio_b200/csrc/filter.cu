@@ -119,6 +119,7 @@ struct eqvio_filter {
     int prLeast = 0, prGreatest = 0;  // stream priority range of the device
     bool pdlHold = false;  // next launch_pdl is a plain launch (its predecessor produces what the kernel reads before its wait)
     int pdl = 1;           // chunk kernels are launched with programmatic dependent launch allowed
+    int fuseSmall = 1;     // steady update: gate + measurement rows in one launch, lift + state estimate in one launch
     int fuseObserver = 1;  // sensor + landmark parts of the observer integration as one software-pipelined kernel
     const char* tlNames[512] = {nullptr};
     int tlNext = 0;  // debug timeline slot counter (EQVIO_TIMELINE builds)
@@ -807,7 +808,7 @@ int enqueue_gate(eqvio_filter* f, int N, bool clearFlag) {
     return EQVIO_OK;
 }
 
-int enqueue_correction(eqvio_filter* f, int nm, const int* guard);
+int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fusedSteady = false);
 
 // The whole device side of a steady frame (no landmark enters or leaves before the gate): frame upload,
 // propagation, gate, guarded correction, result downloads into the fixed pinned block.  Issued either directly
@@ -816,11 +817,16 @@ int enqueue_steady_update(eqvio_filter* f, int N, int nm) {
     int rc;
     CUDA_TRY(f, cudaMemcpyAsync(f->d_frame, f->h_frame, f->frameBytes, cudaMemcpyHostToDevice, f->stream));
     if ((rc = enqueue_propagation(f)) != EQVIO_OK) return rc;
-    if ((rc = enqueue_gate(f, N, false)) != EQVIO_OK) return rc;  // riccati_prep_kernel re-armed the flag
-    if ((rc = enqueue_correction(f, nm, f->d_spec)) != EQVIO_OK) return rc;
-    // stateEstimate() is what every caller asks for next (main_opt.cpp:225, main_sim.cpp:146): produce it here
-    launch_pdl(f, state_estimate_kernel, dim3(cdiv(N, 128)), dim3(128), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, N, f->d_xi0s, f->d_Xs[f->xcur], f->d_out, TL_SLOT(f));
-    LAUNCH_CHECK(f, "state_estimate_kernel");
+    const bool fused = f->fuseSmall && f->corrMode == 0;
+    if (!fused && (rc = enqueue_gate(f, N, false)) != EQVIO_OK) return rc;  // riccati_prep_kernel re-armed the flag
+    if ((rc = enqueue_correction(f, nm, f->d_spec, fused)) != EQVIO_OK) return rc;
+    // stateEstimate() is what every caller asks for next (main_opt.cpp:225, main_sim.cpp:146): produced here, by the lift itself
+    // in the fused form
+    if (!fused) {
+        launch_pdl(f, state_estimate_kernel, dim3(cdiv(N, 128)), dim3(128), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, N, f->d_xi0s,
+                   f->d_Xs[f->xcur], f->d_out, TL_SLOT(f));
+        LAUNCH_CHECK(f, "state_estimate_kernel");
+    }
     // one download: gate scalars, gate flag, status words, state estimate (the block has the layout of h_out)
     CUDA_TRY(f, cudaMemcpyAsync(f->h_out, f->d_outblk, f->outOffEst + (23 + 3 * (size_t)N) * sizeof(double), cudaMemcpyDeviceToHost,
                                 f->stream));
@@ -1134,7 +1140,8 @@ int launch_correction(eqvio_filter* f, const int* guard) {
 
 // performVisionUpdate (VIO_eqf.cpp:105-135) in the symmetric form, for the nm measured landmarks whose pixels are
 // in d_y and state indices in d_lmOf.  Every kernel returns at once when *guard != 0.
-int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
+// fusedSteady: the gate launch carries the measurement rows (gate_meas_kernel) and the lift also emits the state estimate.
+int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fusedSteady) {
     auto& P = f->pend;
     (void)P;
     const eqvio_settings& s = f->st;
@@ -1156,10 +1163,22 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
         double* gout = f->d_Gamma2;
         const int nchunksAll = cdiv(nm, std::max(1, std::min(f->chunkLm, CH_R / 2)));
         // also clears the status words and Gamma (no memset nodes between the kernels of the update)
+        if (fusedSteady) {
+            // one launch: gate CTAs (per state landmark) | measurement-row CTAs (per measured landmark); the rows are built
+            // whatever the gate says -- d_spec + 1 is a constant 0
+            const int gb = cdiv(Nn, 128), mb = cdiv(nm, 128);
+            launch_pdl(f, gate_meas_kernel, dim3(gb + mb), dim3(128), (size_t)0, f->stream, gb, (const double*)f->lm[f->lmcur], f->cap, Nn,
+                       (const double*)f->Sig[f->cur], f->ld, (const int*)f->d_measIdx, (const double*)f->d_y, (const FrameHeader*)f->d_hdr,
+                       (int)s.coordinateChoice, f->d_gate, s.outlierThresholdAbs, s.outlierThresholdProb, f->d_spec, (const int*)f->d_lmOf, nm,
+                       (const double*)f->d_y, s.useEquivariantOutput ? 1 : 0, f->d_Cblk, f->d_ytilde, 1, 0, (const int*)(f->d_spec + 1),
+                       (const int*)f->d_yIdx, f->d_status, 1 + Nn, gin, dimp, f->d_cnt, 2 * nchunksAll, TL_SLOT(f));
+            LAUNCH_CHECK(f, "gate_meas_kernel");
+        } else {
         meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
                                                           s.useEquivariantOutput ? 1 : 0, f->d_Cblk, f->d_ytilde, 1, 0, guard, f->d_yIdx,
                                                           f->d_status, 1 + Nn, gin, dimp, f->d_cnt, 2 * nchunksAll, TL_SLOT(f));
         LAUNCH_CHECK(f, "meas_kernel");
+        }
         const int bcMax = std::max(1, std::min(f->chunkLm, CH_R / 2));
         const int nchunks = cdiv(nm, bcMax);
         const bool pipe = f->pipeline && nchunks > 1 && !f->profiling;
@@ -1414,7 +1433,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard) {
     }
     launch_pdl(f, lift_kernel, dim3(cdiv(std::max(Nn, 1), 128)), dim3(128), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, Nn, f->d_xi0s, f->d_Xs[f->xcur], gammaFinal,
                                                                    s.useDiscreteInnovationLift ? 1 : 0, s.coordinateChoice,
-                                                                   f->d_status, f->d_status + 1, guard, TL_SLOT(f));
+                                                                   f->d_status, f->d_status + 1, guard, fusedSteady ? f->d_out : (double*)nullptr, TL_SLOT(f));
     LAUNCH_CHECK(f, "lift_kernel");
     return EQVIO_OK;
 }
@@ -1987,6 +2006,48 @@ int eqvio_get_host_profile(eqvio_filter* f, int reset, double us[4], long long* 
     return EQVIO_OK;
 }
 
+int eqvio_replay(eqvio_filter* f, int count, const eqvio_replay_frame* frames, const eqvio_camera* cam, size_t flush_bytes,
+                 double* frame_ms, double* est_sensor) {
+    if (!f || count < 0 || (count > 0 && !frames) || !cam) return EQVIO_ERR_INVALID_ARG;
+    using clk = std::chrono::steady_clock;
+    if (cudaSetDevice(f->device) != cudaSuccess) return EQVIO_ERR_CUDA;
+    void* scratch = nullptr;
+    if (flush_bytes > 0 && cudaMalloc(&scratch, flush_bytes) != cudaSuccess) {
+        f->err = "eqvio_replay: cannot allocate the L2 flush scratch";
+        return EQVIO_ERR_CUDA;
+    }
+    int rc = EQVIO_OK;
+    std::vector<int> ids;
+    std::vector<double> p;
+    for (int k = 0; k < count && rc == EQVIO_OK; ++k) {
+        const eqvio_replay_frame& fr = frames[k];
+        if (scratch) {  // outside the bracket: evict Sigma and everything else from L2
+            cudaMemsetAsync(scratch, k & 0xFF, flush_bytes, f->stream);
+            cudaStreamSynchronize(f->stream);
+        }
+        const auto t0 = clk::now();
+        for (int i = 0; i < fr.n_imu && rc == EQVIO_OK; ++i) {
+            const double* r = fr.imu_rows + 13 * (size_t)i;
+            rc = eqvio_process_imu(f, r[0], r + 1, r + 4, r + 7, r + 10);
+        }
+        if (rc == EQVIO_OK && fr.provided_p) rc = eqvio_augment_landmark_states(f, fr.n, fr.ids, fr.n, fr.ids, fr.provided_p);
+        int did = 0;
+        if (rc == EQVIO_OK) rc = eqvio_process_vision(f, fr.stamp, fr.n, fr.ids, fr.y, cam, &did);
+        if (rc == EQVIO_OK) {
+            const int N = eqvio_num_landmarks(f);
+            ids.resize(std::max(N, 1));
+            p.resize(3 * (size_t)std::max(N, 1));
+            double sensor[23];
+            int n_out = 0;
+            rc = eqvio_get_state_estimate(f, sensor, ids.data(), p.data(), &n_out);
+            if (rc == EQVIO_OK && est_sensor) std::memcpy(est_sensor + 23 * (size_t)k, sensor, sizeof(sensor));
+        }
+        if (frame_ms) frame_ms[k] = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+    }
+    if (scratch) cudaFree(scratch);
+    return rc;
+}
+
 int eqvio_batch_process_vision(eqvio_filter* const* fs, int count, const double* stamps, const int* n, const int* const* ids,
                                const double* const* y, const eqvio_camera* cam, int* did_update) {
     if (!fs || count < 0 || !stamps || !n || !ids || !y || !cam) return EQVIO_ERR_INVALID_ARG;
@@ -2276,6 +2337,10 @@ int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
         case EQVIO_TUNE_CHAIN:
             if (value < 0 || value > 2) return EQVIO_ERR_INVALID_ARG;
             f->chain = value;
+            clear_graphs(f);
+            return EQVIO_OK;
+        case EQVIO_TUNE_FUSE_SMALL:
+            f->fuseSmall = value != 0;
             clear_graphs(f);
             return EQVIO_OK;
         case EQVIO_TUNE_PDL:

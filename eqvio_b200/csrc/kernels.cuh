@@ -668,12 +668,11 @@ __global__ void __launch_bounds__(TP* TP)
 // (VIOFilter.cpp:304-336, VIO_eqf.cpp:196-211, VIOFilter.cpp:366-380).
 // measIdx[i] = index of landmark i's pixel in y, or -1.   out: errAbs[N] | errProb[N] | depth2[N]
 // ------------------------------------------------------------------------------------------------
-__global__ void gate_kernel(const double* __restrict__ lm, int cap, int N, const double* __restrict__ Sig, int ld,
-                            const int* __restrict__ measIdx, const double* __restrict__ y, const FrameHeader* __restrict__ fr, int coord,
-                            double* __restrict__ out, double thrAbs, double thrProb, int* __restrict__ tripped, int tl) {
-    pdl_wait();
-    TL_MARK(tl, 0);
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void gate_body(int bid, const double* __restrict__ lm, int cap, int N, const double* __restrict__ Sig, int ld,
+                                          const int* __restrict__ measIdx, const double* __restrict__ y, const FrameHeader* __restrict__ fr,
+                                          int coord, double* __restrict__ out, double thrAbs, double thrProb, int* __restrict__ tripped,
+                                          int tl) {
+    int i = bid * blockDim.x + threadIdx.x;
     if (i >= N) { TL_MARK(tl, 1); return; }
     const Camera cam = fr->cam;
     V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
@@ -711,6 +710,13 @@ __global__ void gate_kernel(const double* __restrict__ lm, int cap, int N, const
     out[N + i] = eProb;
     if (out[i] > thrAbs || eProb > thrProb) atomicOr(tripped, 1);  // same comparisons as the host decision
     TL_MARK(tl, 1);
+}
+__global__ void gate_kernel(const double* __restrict__ lm, int cap, int N, const double* __restrict__ Sig, int ld,
+                            const int* __restrict__ measIdx, const double* __restrict__ y, const FrameHeader* __restrict__ fr, int coord,
+                            double* __restrict__ out, double thrAbs, double thrProb, int* __restrict__ tripped, int tl) {
+    pdl_wait();
+    TL_MARK(tl, 0);
+    gate_body(blockIdx.x, lm, cap, N, Sig, ld, measIdx, y, fr, coord, out, thrAbs, thrProb, tripped, tl);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -788,18 +794,16 @@ __global__ void fill_ll_diag_kernel(double* __restrict__ S, int ld, int n3, doub
 // (VIOState.cpp:70-78, VisionMeasurement.cpp:60-79, EqFMatrices.cpp:43-82).
 // Writes Cblk[j] (2x3 row-major) and the ytilde row of Z.
 // ------------------------------------------------------------------------------------------------
-__global__ void meas_kernel(const double* __restrict__ lm, int cap, const int* __restrict__ lmOf, int n,
+__device__ __forceinline__ void meas_body(int bid, int nblk, const double* __restrict__ lm, int cap, const int* __restrict__ lmOf, int n,
                             const double* __restrict__ y, const FrameHeader* __restrict__ fr, int coord, int useStar,
                             double* __restrict__ Cblk, double* __restrict__ Z, int ldz, int yrow,
                             const int* __restrict__ guard, const int* __restrict__ yIdx, int* __restrict__ zeroStatus, int nStatus,
                             double* __restrict__ zeroGamma, int nGamma, int* __restrict__ zeroCnt, int nCnt, int tl) {
-    pdl_wait();
-    TL_MARK(tl, 0);
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = bid * blockDim.x + threadIdx.x;
     // first kernel of the correction: clears the status words and the Gamma accumulator (also when the guard is set)
-    for (int t = j; t < nStatus; t += gridDim.x * blockDim.x) zeroStatus[t] = 0;
-    for (int t = j; t < nGamma; t += gridDim.x * blockDim.x) zeroGamma[t] = 0.0;
-    for (int t = j; t < nCnt; t += gridDim.x * blockDim.x) zeroCnt[t] = 0;
+    for (int t = j; t < nStatus; t += nblk * blockDim.x) zeroStatus[t] = 0;
+    for (int t = j; t < nGamma; t += nblk * blockDim.x) zeroGamma[t] = 0.0;
+    for (int t = j; t < nCnt; t += nblk * blockDim.x) zeroCnt[t] = 0;
     if (j >= n || *guard) { TL_MARK(tl, 1); return; }
     const int jm = yIdx ? yIdx[j] : j;  // row pair j of the correction takes the pixel of measurement jm
     const Camera cam = fr->cam;
@@ -818,6 +822,34 @@ __global__ void meas_kernel(const double* __restrict__ lm, int cap, const int* _
     for (int k = 0; k < 6; ++k) Cblk[6 * j + k] = C[k];
     TL_MARK(tl, 1);
 }
+__global__ void meas_kernel(const double* __restrict__ lm, int cap, const int* __restrict__ lmOf, int n,
+                            const double* __restrict__ y, const FrameHeader* __restrict__ fr, int coord, int useStar,
+                            double* __restrict__ Cblk, double* __restrict__ Z, int ldz, int yrow,
+                            const int* __restrict__ guard, const int* __restrict__ yIdx, int* __restrict__ zeroStatus, int nStatus,
+                            double* __restrict__ zeroGamma, int nGamma, int* __restrict__ zeroCnt, int nCnt, int tl) {
+    pdl_wait();
+    TL_MARK(tl, 0);
+    meas_body(blockIdx.x, gridDim.x, lm, cap, lmOf, n, y, fr, coord, useStar, Cblk, Z, ldz, yrow, guard, yIdx, zeroStatus, nStatus, zeroGamma, nGamma, zeroCnt, nCnt, tl);
+}
+// Steady update: the gate (per state landmark) and the measurement rows C*, ytilde (per measured landmark) only read the
+// propagated state, so they run as ONE launch -- the first gateBlocks CTAs gate, the others build the rows.  The rows are
+// built whatever the gate says (their consumers are the guarded kernels).
+__global__ void gate_meas_kernel(int gateBlocks, const double* __restrict__ lm, int cap, int N, const double* __restrict__ Sig, int ld,
+                                 const int* __restrict__ measIdx, const double* __restrict__ yAll, const FrameHeader* __restrict__ fr,
+                                 int coord, double* __restrict__ gateOut, double thrAbs, double thrProb, int* __restrict__ tripped,
+                                 const int* __restrict__ lmOf, int n, const double* __restrict__ y, int useStar, double* __restrict__ Cblk,
+                                 double* __restrict__ Z, int ldz, int yrow, const int* __restrict__ zeroGuard,
+                                 const int* __restrict__ yIdx, int* __restrict__ zeroStatus, int nStatus, double* __restrict__ zeroGamma,
+                                 int nGamma, int* __restrict__ zeroCnt, int nCnt, int tl) {
+    pdl_wait();
+    TL_MARK(tl, 0);
+    if ((int)blockIdx.x < gateBlocks)
+        gate_body(blockIdx.x, lm, cap, N, Sig, ld, measIdx, yAll, fr, coord, gateOut, thrAbs, thrProb, tripped, tl);
+    else
+        meas_body(blockIdx.x - gateBlocks, gridDim.x - gateBlocks, lm, cap, lmOf, n, y, fr, coord, useStar, Cblk, Z, ldz, yrow, zeroGuard,
+                  yIdx, zeroStatus, nStatus, zeroGamma, nGamma, zeroCnt, nCnt, tl);
+}
+
 
 // Step 2: W^T = Sigma C^T into Z rows [m, m+dimp).  grid (ceil(dimp/256), n).
 __global__ void zbuild_kernel(const double* __restrict__ Sig, int ld, int dimp, const int* __restrict__ lmOf,
@@ -2316,7 +2348,8 @@ __global__ void gamma_kernel(const double* __restrict__ Z, int ldz, int m, int d
 // ------------------------------------------------------------------------------------------------
 __global__ void lift_kernel(double* __restrict__ lm, int cap, int N, const double* __restrict__ xi0s,
                             double* __restrict__ Xs, const double* __restrict__ Gamma, int discrete, int coord,
-                            int* __restrict__ status, int* __restrict__ invalidFlag, const int* __restrict__ guard, int tl) {
+                            int* __restrict__ status, int* __restrict__ invalidFlag, const int* __restrict__ guard,
+                            double* __restrict__ estOut /* may be null: sensor(23) | p(3N) of the corrected state */, int tl) {
     pdl_wait();
     TL_MARK(tl, 0);
     if (*guard) { TL_MARK(tl, 1); return; }
@@ -2350,6 +2383,7 @@ __global__ void lift_kernel(double* __restrict__ lm, int cap, int N, const doubl
         Xn.w = D.w + qrot(D.A.q, X.w);
         pack_group(Xn, Xs);
         if (bad) atomicOr(status, 2);
+        if (estOut) pack_sensor(sensor_group_action(Xn, xi0), estOut);  // stateEstimate of the corrected state (VIOGroup.cpp:34-55)
     }
     if (i >= N) { TL_MARK(tl, 1); return; }
     V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
@@ -2376,6 +2410,12 @@ __global__ void lift_kernel(double* __restrict__ lm, int cap, int N, const doubl
     lm[F_QY * cap + i] = Q.y;
     lm[F_QZ * cap + i] = Q.z;
     lm[F_QA * cap + i] = a;
+    if (estOut) {
+        const V3 p = landmark_action(Q, a, q0);
+        estOut[23 + 3 * i] = p.x;
+        estOut[23 + 3 * i + 1] = p.y;
+        estOut[23 + 3 * i + 2] = p.z;
+    }
     bool nan = !(isfinite(Q.w) && isfinite(Q.x) && isfinite(Q.y) && isfinite(Q.z) && isfinite(a));
     if (nan) atomicOr(status, 2);
     int inv = (a <= 1e-8 || a > 1e8) ? 1 : 0;

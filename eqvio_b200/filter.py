@@ -42,6 +42,11 @@ def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32).reshape(-1)
 
 
+class ReplayFrame(C.Structure):  # eqvio_replay_frame
+    _fields_ = [("stamp", C.c_double), ("n_imu", C.c_int), ("imu_rows", C.c_void_p), ("n", C.c_int), ("ids", C.c_void_p),
+                ("y", C.c_void_p), ("provided_p", C.c_void_p)]
+
+
 @dataclass
 class IMUVelocity:
     stamp: float = 0.0
@@ -345,7 +350,7 @@ class VIOFilter:
         return dict(propagation=ms[0], preprocessing=ms[1], correction=ms[2])
 
     def setTuning(self, correction=None, chunkLandmarks=None, speculate=None, graph=None, pipeline=None, downdate=None,
-                  lookahead=None, fuseObserver=None, pdl=None, chain=None):
+                  lookahead=None, fuseObserver=None, pdl=None, chain=None, fuseSmall=None):
         """Evaluation-order knobs (eqvio_set_tuning): correction 0 = sequential chunks, 1 = batch sweep."""
         if speculate is not None:
             self._check(lib.eqvio_set_tuning(self._h, 2, int(speculate)))
@@ -355,6 +360,8 @@ class VIOFilter:
             self._check(lib.eqvio_set_tuning(self._h, 4, int(pipeline)))
         if downdate is not None:  # 0 = fp64 DMMA, 1 = tcgen05 split-bf16 / fp32 accumulate
             self._check(lib.eqvio_set_tuning(self._h, 5, int(downdate)))
+        if fuseSmall is not None:
+            self._check(lib.eqvio_set_tuning(self._h, 10, int(fuseSmall)))
         if chain is not None:  # 1 = chained correction (look-ahead CTA + concurrent downdates), 2 = same in stream order, 0 = off
             self._check(lib.eqvio_set_tuning(self._h, 9, int(chain)))
         if pdl is not None:
@@ -367,6 +374,32 @@ class VIOFilter:
             self._check(lib.eqvio_set_tuning(self._h, 0, int(correction)))
         if chunkLandmarks is not None:
             self._check(lib.eqvio_set_tuning(self._h, 1, int(chunkLandmarks)))
+
+    def replay(self, frames, camera: Camera, flushBytes=0):
+        """C++ host loop over the C ABI (eqvio_replay): per frame processIMUData x k, augmentLandmarkStates,
+        processVisionData, stateEstimate on host buffers.  frames: objects with stamp, imu (k,13), ids, y (n,2),
+        provided_p (n,3) or None.  Returns (frame_ms, est_sensor (len, 23))."""
+        n = len(frames)
+        arr = (ReplayFrame * n)()
+        keep = []  # the C side reads these buffers during the call
+        for k, fr in enumerate(frames):
+            imu = np.ascontiguousarray(fr.imu, dtype=np.float64).reshape(-1, 13)
+            ids = _i32(fr.ids)
+            y = _f64(fr.y, 2 * len(ids))
+            pp = None if getattr(fr, "provided_p", None) is None else _f64(fr.provided_p, 3 * len(ids))
+            keep += [imu, ids, y, pp]
+            arr[k].stamp = float(fr.stamp)
+            arr[k].n_imu = imu.shape[0]
+            arr[k].imu_rows = imu.ctypes.data
+            arr[k].n = len(ids)
+            arr[k].ids = ids.ctypes.data
+            arr[k].y = y.ctypes.data
+            arr[k].provided_p = None if pp is None else pp.ctypes.data
+        ms = np.zeros(max(n, 1))
+        est = np.zeros((max(n, 1), 23))
+        self._check(lib.eqvio_replay(self._h, n, C.cast(arr, C.c_void_p), C.cast(C.pointer(camera.pod), C.c_void_p), int(flushBytes),
+                                     _pd(ms), _pd(est)))
+        return ms[:n], est[:n]
 
     def hostProfile(self, reset=True):
         """Host-side microseconds per processVisionData call since the last reset (eqvio_get_host_profile)."""

@@ -124,6 +124,23 @@ int eqvio_process_imu_rows(eqvio_filter* f, int count, const double* rows);
  * outliers, add new landmarks, EqF correction, drop invalid landmarks.  ids ascending. */
 int eqvio_process_vision(eqvio_filter* f, double stamp, int n, const int* ids, const double* y /* 2n pixels */,
                          const eqvio_camera* cam, int* did_update /* may be NULL */);
+/* Host-side replay of recorded frames through the entry points above, the way the reference's main loop drives VIOFilter
+ * (main_sim.cpp:136-148): per frame eqvio_process_imu (one call per row), eqvio_augment_landmark_states, eqvio_process_vision,
+ * eqvio_get_state_estimate -- all on HOST buffers.  This is the C++ host loop of the end-to-end measurement: frame_ms[k]
+ * (may be NULL) = host wall time of frame k, which ends synchronised with the state estimate on the host; est_sensor
+ * (count x 23, may be NULL) receives the sensor part of every estimate.  flush_bytes > 0 writes that many bytes of device
+ * scratch between frames, outside the timed bracket (L2 flush).  Stops at the first error and returns it. */
+typedef struct eqvio_replay_frame {
+    double stamp;
+    int n_imu;
+    const double* imu_rows; /* n_imu x 13: stamp, gyr3, acc3, gyrBiasVel3, accBiasVel3 */
+    int n;
+    const int* ids;            /* n measured ids, ascending */
+    const double* y;           /* 2n pixels */
+    const double* provided_p;  /* n x 3 landmark positions for augmentLandmarkStates (same ids), or NULL = skip the augment call */
+} eqvio_replay_frame;
+int eqvio_replay(eqvio_filter* f, int count, const eqvio_replay_frame* frames, const eqvio_camera* cam, size_t flush_bytes,
+                 double* frame_ms, double* est_sensor);
 /* Same update for `count` independent filters at once (Monte-Carlo replicas on one GPU):
  * kernels of different filters overlap on their streams.  Arrays are indexed per filter. */
 int eqvio_batch_process_vision(eqvio_filter* const* fs, int count, const double* stamps, const int* n,
@@ -229,6 +246,9 @@ int eqvio_get_host_profile(eqvio_filter* f, int reset, double us[4], long long* 
  *                         mode 2 in the tests).  Measured slower than mode 0 on B200 (3040 vs 3320 updates/s at N = 256: the
  *                         single look-ahead CTA becomes the per-chunk bottleneck), hence off by default. */
 #define EQVIO_TUNE_CHAIN 9
+/*   EQVIO_TUNE_FUSE_SMALL: 1 (default) = in a steady update the gate and the measurement rows (C*, ytilde) run as one launch
+ *                         and the innovation lift also emits the state estimate; 0 = four separate kernels.  Same arithmetic. */
+#define EQVIO_TUNE_FUSE_SMALL 10
 int eqvio_set_tuning(eqvio_filter* f, int key, int value);
 /* Version / build info string (arch the kernels were compiled for). */
 const char* eqvio_build_info(void);

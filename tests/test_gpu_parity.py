@@ -99,7 +99,7 @@ def test_correction_evaluation_orders_agree(tuning):
     _check(run_gpu(stream, tuning=tuning), ref)
 
 
-@pytest.mark.parametrize("tuning", [dict(graph=0), dict(graph=0, speculate=0), dict(graph=1), dict(graph=1, pdl=0), dict(graph=0, pdl=0)])
+@pytest.mark.parametrize("tuning", [dict(graph=0), dict(graph=0, speculate=0), dict(graph=1), dict(graph=1, pdl=0), dict(graph=0, pdl=0), dict(graph=1, fuseSmall=0), dict(graph=0, fuseSmall=0)])
 def test_steady_path_variants_agree(tuning):
     """CUDA-graph replay, plain speculative launches and the wait-for-the-gate path give identical results
     (same kernels, same order), over enough frames for graphs to be captured AND replayed."""
