@@ -219,6 +219,7 @@ def run_b200(args, rank, local_rank, world):
     if world > 1:
         import torch.distributed as dist
 
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     N, K, W, P, R = args.landmarks, args.steps, args.warmup, args.profile_steps, args.sequences_per_gpu
@@ -283,7 +284,7 @@ def run_b200(args, rank, local_rank, world):
         dist.barrier()
     sampler = ClockSampler(local_rank)
     if dist:  # bring the collective path up (communicator, buffers) before anything is timed
-        gather_trajectories({inst: np.zeros((1, 11)) for inst in mine}, total_instances, device=torch.device("cuda", local_rank))
+        gather_trajectories({inst: np.zeros((K, 11)) for inst in mine}, total_instances, device=torch.device("cuda", local_rank))
     launches0 = sum(f.launchCount() for f in filters)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     dev_ms = 0.0
@@ -323,6 +324,9 @@ def run_b200(args, rank, local_rank, world):
     e2e_ms = sum(a.elapsed_time(b) for a, b in ev)
     # the single collective of the path: all-gather of the trajectories at the end (timed into e2e)
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dist:
+        dist.barrier()  # the slowest rank's steps are already charged through the max over ranks: do not charge the skew twice
+        torch.cuda.synchronize()
     g0.record()
     all_traj = gather_trajectories(traj, total_instances, device=torch.device("cuda", local_rank) if dist else None)
     g1.record()
