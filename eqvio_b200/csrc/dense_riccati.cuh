@@ -103,6 +103,71 @@ __global__ void dense_fill_landmark_kernel(double* __restrict__ M, int n, int di
         for (int c = 0; c < 3; ++c) M[(size_t)(dim + c) * n + r0 + r] = dt * ro[45 + 3 * r + c];
     }
 }
+// ---- useDiscreteStateMatrix: stateMatrixADiscrete (EqFMatrices.cpp:24-41) -------------------------------------------
+// A0tD = numericalDifferential(a0Discrete, 0) with central differences of step h = cbrt(eps) (Geometry.cpp:25-36).  The
+// sensor coordinates of a0Discrete depend on the sensor coordinates only, landmark i's on the sensor coordinates and its
+// own three, so A0tD = [[F_s, 0], [G, blockdiag D_i]] needs 43 sensor evaluations (0, +-h e_j) and 49 per landmark
+// instead of 2 dim evaluations of the whole state; every entry outside those blocks is an exact zero in the reference
+// too (identical function values cancel).  Written into the top-left dim x dim block of R (n x n column-major).
+constexpr int DA_SENSOR_EVALS = 1 + 2 * SENSOR_DIM;  // 43
+__device__ __forceinline__ double num_diff_step() { return cbrt(2.220446049250313e-16); }
+__global__ void discrete_a_sensor_kernel(const double* __restrict__ xi0s, const double* __restrict__ Xs, const double* __restrict__ imuRow,
+                                         double* __restrict__ R, int n, SE3* __restrict__ ccOut) {
+    __shared__ double e1[DA_SENSOR_EVALS][SENSOR_DIM];
+    const int k = threadIdx.x;
+    const double h = num_diff_step();
+    if (k < DA_SENSOR_EVALS) {
+        const SensorState xi0 = unpack_sensor(xi0s);
+        const GroupSensor X = unpack_group(Xs);
+        double eps[SENSOR_DIM];
+        for (int j = 0; j < SENSOR_DIM; ++j) eps[j] = 0.0;
+        if (k > 0) eps[(k - 1) / 2] = ((k - 1) & 1) ? -h : h;
+        SE3 cc;
+        double out[SENSOR_DIM];
+        a0_discrete_sensor(X, xi0, imuRow + 1, imuRow[0], eps, out, cc);
+        for (int j = 0; j < SENSOR_DIM; ++j) e1[k][j] = out[j];
+        ccOut[k] = cc;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < SENSOR_DIM * SENSOR_DIM; t += blockDim.x) {
+        const int r = t / SENSOR_DIM, j = t % SENSOR_DIM;
+        R[(size_t)j * n + r] = (e1[1 + 2 * j][r] - e1[2 + 2 * j][r]) / (2 * h);
+    }
+}
+// one CTA per landmark: 43 evaluations under the sensor perturbations + 6 under its own
+__global__ void discrete_a_landmark_kernel(const double* __restrict__ lm, int cap, int N, int coord, const double* __restrict__ imuRow,
+                                           const SE3* __restrict__ cc, double* __restrict__ R, int n) {
+    __shared__ double o[DA_SENSOR_EVALS + 6][3];
+    const int i = blockIdx.x, e = threadIdx.x;
+    const double h = num_diff_step();
+    if (e < DA_SENSOR_EVALS + 6) {
+        const V3 p0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
+        const Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
+        const double a = lm[F_QA * cap + i];
+        V3 eps = V3{0, 0, 0};
+        int ks = e;  // sensor evaluation whose camera-frame change applies
+        if (e >= DA_SENSOR_EVALS) {
+            const int c = (e - DA_SENSOR_EVALS) / 2;
+            const double d = ((e - DA_SENSOR_EVALS) & 1) ? -h : h;
+            eps = V3{c == 0 ? d : 0.0, c == 1 ? d : 0.0, c == 2 ? d : 0.0};
+            ks = 0;
+        }
+        const V3 r = a0_discrete_landmark(coord, p0, Q, a, eps, cc[ks], cc[0]);
+        o[e][0] = r.x;
+        o[e][1] = r.y;
+        o[e][2] = r.z;
+    }
+    __syncthreads();
+    const int r0 = SENSOR_DIM + 3 * i;
+    for (int t = threadIdx.x; t < 3 * SENSOR_DIM; t += blockDim.x) {
+        const int r = t / SENSOR_DIM, j = t % SENSOR_DIM;
+        R[(size_t)j * n + r0 + r] = (o[1 + 2 * j][r] - o[2 + 2 * j][r]) / (2 * h);
+    }
+    if (threadIdx.x < 9) {
+        const int r = threadIdx.x / 3, c = threadIdx.x % 3;
+        R[(size_t)(r0 + c) * n + r0 + r] = (o[DA_SENSOR_EVALS + 2 * c][r] - o[DA_SENSOR_EVALS + 2 * c + 1][r]) / (2 * h);
+    }
+}
 // out = a A + b B + c C + d I  (any of A, B, C may be null)
 __global__ void dense_lincomb_kernel(double* __restrict__ out, int n, double a, const double* __restrict__ A, double b,
                                      const double* __restrict__ B, double c, const double* __restrict__ C, double d) {
@@ -156,6 +221,7 @@ struct Workspace {
     unsigned long long* norm = nullptr;
     double* dtBs = nullptr;
     double* pdiag = nullptr;
+    SE3* cc = nullptr;  // camera-frame changes of the 43 sensor evaluations of stateMatrixADiscrete
     blasHandle blas = nullptr;
     solverHandle solver = nullptr;
     void release() {
@@ -169,6 +235,8 @@ struct Workspace {
         cudaFree(norm);
         cudaFree(dtBs);
         cudaFree(pdiag);
+        cudaFree(cc);
+        cc = nullptr;
         lwork = nullptr;
         ipiv = nullptr;
         info = nullptr;
@@ -215,6 +283,7 @@ inline const char* ensure(Workspace& w, int n, cudaStream_t stream) {
             cudaMalloc(&w.norm, sizeof(unsigned long long));
             cudaMalloc(&w.dtBs, 252 * sizeof(double));
             cudaMalloc(&w.pdiag, 8 * sizeof(double));
+            cudaMalloc(&w.cc, DA_SENSOR_EVALS * sizeof(SE3));
         }
         w.n = cap;
     }

@@ -599,8 +599,10 @@ int plan_integration(eqvio_filter* f, double newTime, int* advanced) {
     *advanced = 0;
     if (newTime <= f->time || f->time < 0 || f->buf.empty()) return EQVIO_OK;
     const eqvio_settings& s = f->st;
-    if (!s.fastRiccati && s.useDiscreteStateMatrix) {
-        f->err = "useDiscreteStateMatrix (integrateRiccatiStateDiscrete, numerically differentiated A) has no CUDA path in this build";
+    if (!s.fastRiccati && s.useDiscreteStateMatrix && !s.useDiscreteVelocityLift) {
+        // the reference's stateMatrixADiscrete always differentiates liftVelocityDiscrete; the pairing with a continuous
+        // velocity lift in the observer is not a configuration its settings document, and it is not mapped here
+        f->err = "useDiscreteStateMatrix with useDiscreteVelocityLift = false has no CUDA path in this build";
         return EQVIO_ERR_UNSUPPORTED;
     }
     const int n = (int)f->buf.size();
@@ -759,17 +761,31 @@ int enqueue_propagation_accurate(eqvio_filter* f) {
                 launch_pdl(f, landmark_rows_kernel, dim3(cdiv(N, 64)), dim3(64), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, N, f->d_ctx, s.coordinateChoice, f->d_rows, TL_SLOT(f));
                 LAUNCH_CHECK(f, "landmark_rows_kernel");
             }
-            CUDA_TRY(f, cudaMemsetAsync(M, 0, (size_t)n * n * sizeof(double), f->stream));
-            dense::dense_fill_sensor_kernel<<<2, 256, 0, f->stream>>>(M, n, dim, f->d_ctx, w.dtBs);
+            // integrateRiccatiStateAccurate: M = dt [A B; 0 0], R = exp(M).  integrateRiccatiStateDiscrete (VIO_eqf.cpp:93-103,
+            // useDiscreteStateMatrix): R = [A0tD, dt B; 0 0] directly, with the numerically differentiated discrete state matrix
+            // -- the products and the noise term below are then the same expressions (dt B (Q / dt) (dt B)^T = dt B Q B^T).
+            double* Tgt = s.useDiscreteStateMatrix ? R : M;
+            CUDA_TRY(f, cudaMemsetAsync(Tgt, 0, (size_t)n * n * sizeof(double), f->stream));
+            dense::dense_fill_sensor_kernel<<<2, 256, 0, f->stream>>>(Tgt, n, dim, f->d_ctx, w.dtBs);
             LAUNCH_CHECK(f, "dense_fill_sensor_kernel");
             if (N > 0) {
-                dense::dense_fill_landmark_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(M, n, dim, N, f->d_rows, dt);
+                dense::dense_fill_landmark_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(Tgt, n, dim, N, f->d_rows, dt);
                 LAUNCH_CHECK(f, "dense_fill_landmark_kernel");
             }
-            why = dense::expm(w, n, f->stream);
-            if (why) {
-                f->err = std::string("matrix exponential: ") + why;
-                return EQVIO_ERR_CUDA;
+            if (s.useDiscreteStateMatrix) {
+                dense::discrete_a_sensor_kernel<<<1, 64, 0, f->stream>>>(f->d_xi0s, f->d_Xs[f->xcur], f->d_imu + (size_t)13 * i, R, n, w.cc);
+                LAUNCH_CHECK(f, "discrete_a_sensor_kernel");
+                if (N > 0) {
+                    dense::discrete_a_landmark_kernel<<<N, 64, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, s.coordinateChoice,
+                                                                               f->d_imu + (size_t)13 * i, w.cc, R, n);
+                    LAUNCH_CHECK(f, "discrete_a_landmark_kernel");
+                }
+            } else {
+                why = dense::expm(w, n, f->stream);
+                if (why) {
+                    f->err = std::string("matrix exponential: ") + why;
+                    return EQVIO_ERR_CUDA;
+                }
             }
             pack_sigma_kernel<<<dim3(cdiv(dim, 128), dim), 128, 0, f->stream>>>(Sin, f->ld, dim, P0, dim);
             LAUNCH_CHECK(f, "pack_sigma_kernel");

@@ -293,6 +293,70 @@ HD void sensor_chart_std(const SensorState& Xi, const SensorState& Xi0, double* 
     eps[14] = Xi.vel.z - Xi0.vel.z;
     se3_log(se3_mul(se3_inv(Xi0.cam), Xi.cam), eps + 15);
 }
+HD V3 invdepth_chart_inv(V3 eps, V3 q0);
+// sensorChart_std inverse (VIOState.cpp:114-121)
+HD SensorState sensor_chart_std_inv(const double* eps, const SensorState& Xi0) {
+    SensorState Xi;
+    for (int i = 0; i < 6; ++i) Xi.bias[i] = Xi0.bias[i] + eps[i];
+    Xi.pose = se3_mul(Xi0.pose, se3_exp(V3{eps[6], eps[7], eps[8]}, V3{eps[9], eps[10], eps[11]}));
+    Xi.vel = V3{Xi0.vel.x + eps[12], Xi0.vel.y + eps[13], Xi0.vel.z + eps[14]};
+    Xi.cam = se3_mul(Xi0.cam, se3_exp(V3{eps[15], eps[16], eps[17]}, V3{eps[18], eps[19], eps[20]}));
+    return Xi;
+}
+// VIOGroup product, sensor part (VIOGroup.cpp:71-92)
+HD GroupSensor group_mul(const GroupSensor& a, const GroupSensor& b) {
+    GroupSensor r;
+    for (int i = 0; i < 6; ++i) r.beta[i] = a.beta[i] + b.beta[i];
+    r.A = se3_mul(a.A, b.A);
+    r.B = se3_mul(a.B, b.B);
+    r.w = a.w + qrot(a.A.q, b.w);
+    return r;
+}
+// liftVelocityDiscrete, sensor part (VIOGroup.cpp:229-257): the lift of one IMU segment u = (gyr3, acc3, gyrBiasVel3,
+// accBiasVel3) of length dt at the state xh, and the camera-frame change the landmark part needs (:259)
+HD void lift_velocity_discrete_sensor(const SensorState& xh, const double* u, double dt, GroupSensor& L, SE3& camChangeInv) {
+    V3 gyr = V3{u[0] - xh.bias[0], u[1] - xh.bias[1], u[2] - xh.bias[2]};
+    V3 acc = V3{u[3] - xh.bias[3], u[4] - xh.bias[4], u[5] - xh.bias[5]};
+    V3 gdir = qrot(qinv(xh.pose.q), V3{0, 0, 1});
+    for (int i = 0; i < 6; ++i) L.beta[i] = dt * u[6 + i];
+    L.A.q = so3_exp(dt * gyr);
+    V3 x = dt * qrot(xh.pose.q, xh.vel) + (0.5 * dt * dt) * (qrot(xh.pose.q, acc) + V3{0, 0, -GRAVITY_CONSTANT});
+    L.A.x = qrot(qinv(xh.pose.q), x);
+    L.B = se3_mul(se3_mul(se3_inv(xh.cam), L.A), xh.cam);
+    V3 bvd = acc - GRAVITY_CONSTANT * gdir;
+    L.w = xh.vel - (xh.vel + dt * bvd);
+    camChangeInv = se3_mul(se3_mul(se3_inv(xh.cam), se3_inv(L.A)), xh.cam);
+}
+// a0Discrete of stateMatrixADiscrete (EqFMatrices.cpp:27-37), sensor part: the chart coordinates eps1 of
+// (X LambdaTilde X^-1) . chart^-1(eps) for the sensor coordinates eps (21); also returns the camera-frame change of
+// Lambda(xi) that the landmark part of the same evaluation needs.
+HD void a0_discrete_sensor(const GroupSensor& X, const SensorState& xi0, const double* u, double dt, const double* eps, double* eps1,
+                           SE3& camChangeInv) {
+    const SensorState xe = sensor_chart_std_inv(eps, xi0);
+    const SensorState xhat = sensor_group_action(X, xi0);
+    const SensorState xi = sensor_group_action(X, xe);
+    GroupSensor L1, L0;
+    SE3 cc0;
+    lift_velocity_discrete_sensor(xi, u, dt, L1, camChangeInv);
+    lift_velocity_discrete_sensor(xhat, u, dt, L0, cc0);
+    const GroupSensor G = group_mul(group_mul(X, group_mul(L1, group_inverse(L0))), group_inverse(X));
+    sensor_chart_std(sensor_group_action(G, xe), xi0, eps1);
+}
+// ... landmark part: eps (3) are the chart coordinates of landmark (p0; Q, a), cc1 / cc0 the camera-frame changes of
+// Lambda(xi) / Lambda(xi_hat).  Point chart: Euclidean or inverse depth.
+HD V3 a0_discrete_landmark(int coord, V3 p0, Quat Q, double a, V3 eps, const SE3& cc1, const SE3& cc0) {
+    const V3 pe = coord == COORD_INVDEPTH ? invdepth_chart_inv(eps, p0) : p0 + eps;
+    const V3 p = landmark_action(Q, a, pe), phat = landmark_action(Q, a, p0);
+    const V3 p1 = se3_apply(cc1, p), ph1 = se3_apply(cc0, phat);
+    const Quat R1 = quat_from_two_vectors(normalized(p1), normalized(p)), R0 = quat_from_two_vectors(normalized(ph1), normalized(phat));
+    const double a1 = norm(p) / norm(p1), a0 = norm(phat) / norm(ph1);
+    const Quat Rt = qmul(R1, qinv(R0));          // LambdaTilde = Lambda(xi) Lambda(xi_hat)^-1
+    const double at = a1 * (1.0 / a0);
+    const Quat Rg = qmul(qmul(Q, Rt), qinv(Q));  // X LambdaTilde X^-1
+    const double ag = (a * at) * (1.0 / a);
+    const V3 pe1 = landmark_action(Rg, ag, pe);
+    return coord == COORD_INVDEPTH ? invdepth_chart(pe1, p0) : pe1 - p0;
+}
 // integrateSystemFunction, sensor part (VIOState.cpp:27-68): advances s by one IMU segment u = (gyr, acc, gyrBiasVel,
 // accBiasVel) of length dt and returns the camera-frame change applied to every landmark.
 HD SE3 integrate_system_sensor(SensorState& s, const double* u, double dt) {

@@ -43,8 +43,8 @@ extern "C" {
 #define EQVIO_ERR_CUDA (-2)
 #define EQVIO_ERR_NUMERIC (-3)     /* NaN / non-SPD innovation covariance detected on device */
 #define EQVIO_ERR_CAPACITY (-4)    /* more landmarks than the handle was created for */
-#define EQVIO_ERR_UNSUPPORTED (-5) /* a Settings switch this build has no CUDA path for (useDiscreteStateMatrix,
-                                      Normal chart, other camera models) */
+#define EQVIO_ERR_UNSUPPORTED (-5) /* a Settings switch this build has no CUDA path for (Normal chart, useDiscreteStateMatrix
+                                      with a continuous velocity lift, other camera models) */
 
 #define EQVIO_COORD_EUCLIDEAN 0
 #define EQVIO_COORD_INVDEPTH 1

@@ -265,7 +265,7 @@ def test_silent_returns_and_errors():
     with pytest.raises(eb.EqvioError) as ei:
         eb.VIOFilter(eb.Settings(coordinateChoice=2), capacity=4)
     assert ei.value.code == eb._capi.EQVIO_ERR_UNSUPPORTED
-    g = eb.VIOFilter(eb.Settings(fastRiccati=0, useDiscreteStateMatrix=1), capacity=4)
+    g = eb.VIOFilter(eb.Settings(fastRiccati=0, useDiscreteStateMatrix=1, useDiscreteVelocityLift=0), capacity=4)
     g.processIMUArray(fr.imu)
     with pytest.raises(eb.EqvioError) as ei:
         g.processVisionArrays(fr.stamp, fr.ids[:2], fr.y[:2], cam)
@@ -432,6 +432,15 @@ def test_accurate_riccati_default_settings(coord):
     VIOFilter.cpp:160-178) -- dense matrix exponential on the device vs the oracle's scipy expm."""
     stream = make_stream(N=12, frames=4, coord=coord, settings_overrides=dict(fastRiccati=False))
     _check(run_gpu(stream), run_oracle(stream), tol=1e-8)
+
+
+@pytest.mark.parametrize("coord", [0, 1])
+def test_discrete_state_matrix(coord):
+    """fastRiccati = false with useDiscreteStateMatrix: integrateRiccatiStateDiscrete per IMU sample (VIO_eqf.cpp:93-103)
+    with the numerically differentiated stateMatrixADiscrete (EqFMatrices.cpp:24-41; central differences, h = cbrt(eps):
+    rounding in the function values is amplified by 1 / 2h ~ 8e4, hence the looser tolerance)."""
+    stream = make_stream(N=12, frames=4, coord=coord, settings_overrides=dict(fastRiccati=False, useDiscreteStateMatrix=True))
+    _check(run_gpu(stream), run_oracle(stream), tol=1e-7)
 
 
 def test_tcgen05_probe():
