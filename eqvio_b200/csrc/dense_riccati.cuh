@@ -168,6 +168,148 @@ __global__ void discrete_a_landmark_kernel(const double* __restrict__ lm, int ca
         R[(size_t)(r0 + c) * n + r0 + r] = (o[DA_SENSOR_EVALS + 2 * c][r] - o[DA_SENSOR_EVALS + 2 * c + 1][r]) / (2 * h);
     }
 }
+// ---- Normal coordinates: A_normal = M A_euclid M^-1, B_normal = M B_euclid (normal.cpp:37-45) ---------------------------
+// M = coordinateDifferential_normal_euclid(xi0) (VIOState.cpp:391-401) is the central-difference derivative of the chart
+// change; it is block diagonal (sensor 21 x 21, one 3 x 3 per landmark; every other entry is an exact zero in the reference).
+// Sensor block and its inverse (Gauss-Jordan with partial pivoting), row-major 21 x 21 each.
+__global__ void normal_m_sensor_kernel(const double* __restrict__ xi0s, double* __restrict__ Ms, double* __restrict__ MsInv) {
+    __shared__ double e[2 * SENSOR_DIM][SENSOR_DIM];
+    __shared__ double aug[SENSOR_DIM][2 * SENSOR_DIM];
+    __shared__ double mult[SENSOR_DIM];
+    __shared__ int piv;
+    const int k = threadIdx.x;
+    const double h = normal_diff_step();
+    if (k < 2 * SENSOR_DIM) {
+        const SensorState xi0 = unpack_sensor(xi0s);
+        double eps[SENSOR_DIM], out[SENSOR_DIM];
+        for (int j = 0; j < SENSOR_DIM; ++j) eps[j] = 0.0;
+        eps[k / 2] = (k & 1) ? -h : h;
+        sensor_chart_normal(sensor_chart_std_inv(eps, xi0), xi0, out);
+        for (int j = 0; j < SENSOR_DIM; ++j) e[k][j] = out[j];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < SENSOR_DIM * SENSOR_DIM; t += blockDim.x) {
+        const int r = t / SENSOR_DIM, j = t % SENSOR_DIM;
+        const double v = (e[2 * j][r] - e[2 * j + 1][r]) / (2 * h);
+        Ms[t] = v;
+        aug[r][j] = v;
+        aug[r][SENSOR_DIM + j] = r == j ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    for (int c = 0; c < SENSOR_DIM; ++c) {
+        if (threadIdx.x == 0) {
+            int p = c;
+            for (int r = c + 1; r < SENSOR_DIM; ++r)
+                if (fabs(aug[r][c]) > fabs(aug[p][c])) p = r;
+            piv = p;
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * SENSOR_DIM && piv != c) {
+            const double t = aug[c][threadIdx.x];
+            aug[c][threadIdx.x] = aug[piv][threadIdx.x];
+            aug[piv][threadIdx.x] = t;
+        }
+        __syncthreads();
+        const double d = aug[c][c];
+        __syncthreads();
+        if (threadIdx.x < 2 * SENSOR_DIM) aug[c][threadIdx.x] /= d;
+        if (threadIdx.x < SENSOR_DIM) mult[threadIdx.x] = aug[threadIdx.x][c];  // multipliers, read before column c is eliminated
+        __syncthreads();
+        if (threadIdx.x < 2 * SENSOR_DIM) {
+            const double pc = aug[c][threadIdx.x];
+            for (int r = 0; r < SENSOR_DIM; ++r)
+                if (r != c) aug[r][threadIdx.x] -= mult[r] * pc;
+        }
+        __syncthreads();
+    }
+    for (int t = threadIdx.x; t < SENSOR_DIM * SENSOR_DIM; t += blockDim.x) MsInv[t] = aug[t / SENSOR_DIM][SENSOR_DIM + t % SENSOR_DIM];
+}
+// In place on T = dt [A B; 0 0] (n x n column-major): blocks (s,s), (l_i,s), (l_i,l_i) of A and the rows of B.
+// Block 0 handles the sensor rows, block 1 + i landmark i.
+__global__ void normal_transform_kernel(double* __restrict__ T, int n, int dim, int N, const double* __restrict__ lm, int cap,
+                                        const double* __restrict__ Ms, const double* __restrict__ MsInv) {
+    __shared__ double sM[SENSOR_DIM * SENSOR_DIM], sMi[SENSOR_DIM * SENSOR_DIM], sX[SENSOR_DIM * (SENSOR_DIM + 12)], sY[SENSOR_DIM * SENSOR_DIM];
+    const int tid = threadIdx.x;
+    for (int t = tid; t < SENSOR_DIM * SENSOR_DIM; t += blockDim.x) {
+        sM[t] = Ms[t];
+        sMi[t] = MsInv[t];
+    }
+    if (blockIdx.x == 0) {
+        // X = [A_ss | B_s] (21 x 33), row-major in shared memory
+        for (int t = tid; t < SENSOR_DIM * (SENSOR_DIM + 12); t += blockDim.x) {
+            const int r = t / (SENSOR_DIM + 12), c = t % (SENSOR_DIM + 12);
+            sX[t] = T[(size_t)(c < SENSOR_DIM ? c : dim + c - SENSOR_DIM) * n + r];
+        }
+        __syncthreads();
+        // Y = A_ss Ms^-1
+        for (int t = tid; t < SENSOR_DIM * SENSOR_DIM; t += blockDim.x) {
+            const int r = t / SENSOR_DIM, c = t % SENSOR_DIM;
+            double acc = 0.0;
+            for (int k = 0; k < SENSOR_DIM; ++k) acc += sX[r * (SENSOR_DIM + 12) + k] * sMi[k * SENSOR_DIM + c];
+            sY[t] = acc;
+        }
+        __syncthreads();
+        for (int t = tid; t < SENSOR_DIM * (SENSOR_DIM + 12); t += blockDim.x) {
+            const int r = t / (SENSOR_DIM + 12), c = t % (SENSOR_DIM + 12);
+            double acc = 0.0;
+            if (c < SENSOR_DIM) {
+                for (int k = 0; k < SENSOR_DIM; ++k) acc += sM[r * SENSOR_DIM + k] * sY[k * SENSOR_DIM + c];
+                T[(size_t)c * n + r] = acc;
+            } else {
+                for (int k = 0; k < SENSOR_DIM; ++k) acc += sM[r * SENSOR_DIM + k] * sX[k * (SENSOR_DIM + 12) + c];
+                T[(size_t)(dim + c - SENSOR_DIM) * n + r] = acc;
+            }
+        }
+        return;
+    }
+    const int i = blockIdx.x - 1;
+    if (i >= N) return;
+    const int r0 = SENSOR_DIM + 3 * i;
+    __shared__ double sMl[9], sMli[9], sR[3 * (SENSOR_DIM + 3 + 12)], sZ[3 * SENSOR_DIM];
+    constexpr int W = SENSOR_DIM + 3 + 12;  // [A_is (21) | A_ii (3) | B_i (12)]
+    if (tid == 0) {
+        const V3 p0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
+        const M3 M = normal_M_landmark(p0), Mi = inverse(M);
+        for (int k = 0; k < 9; ++k) {
+            sMl[k] = M.m[k];
+            sMli[k] = Mi.m[k];
+        }
+    }
+    for (int t = tid; t < 3 * W; t += blockDim.x) {
+        const int r = t / W, c = t % W;
+        const int col = c < SENSOR_DIM ? c : (c < SENSOR_DIM + 3 ? r0 + c - SENSOR_DIM : dim + c - SENSOR_DIM - 3);
+        sR[t] = T[(size_t)col * n + r0 + r];
+    }
+    __syncthreads();
+    // Z = A_is Ms^-1 (3 x 21)
+    for (int t = tid; t < 3 * SENSOR_DIM; t += blockDim.x) {
+        const int r = t / SENSOR_DIM, c = t % SENSOR_DIM;
+        double acc = 0.0;
+        for (int k = 0; k < SENSOR_DIM; ++k) acc += sR[r * W + k] * sMi[k * SENSOR_DIM + c];
+        sZ[t] = acc;
+    }
+    __syncthreads();
+    for (int t = tid; t < 3 * W; t += blockDim.x) {
+        const int r = t / W, c = t % W;
+        double acc = 0.0;
+        if (c < SENSOR_DIM) {
+            for (int k = 0; k < 3; ++k) acc += sMl[3 * r + k] * sZ[k * SENSOR_DIM + c];
+            T[(size_t)c * n + r0 + r] = acc;
+        } else if (c < SENSOR_DIM + 3) {
+            // M_i A_ii M_i^-1
+            const int cc = c - SENSOR_DIM;
+            for (int k = 0; k < 3; ++k) {
+                double inner = 0.0;
+                for (int q = 0; q < 3; ++q) inner += sR[k * W + SENSOR_DIM + q] * sMli[3 * q + cc];
+                acc += sMl[3 * r + k] * inner;
+            }
+            T[(size_t)(r0 + cc) * n + r0 + r] = acc;
+        } else {
+            for (int k = 0; k < 3; ++k) acc += sMl[3 * r + k] * sR[k * W + c];
+            T[(size_t)(dim + c - SENSOR_DIM - 3) * n + r0 + r] = acc;
+        }
+    }
+}
 // out = a A + b B + c C + d I  (any of A, B, C may be null)
 __global__ void dense_lincomb_kernel(double* __restrict__ out, int n, double a, const double* __restrict__ A, double b,
                                      const double* __restrict__ B, double c, const double* __restrict__ C, double d) {

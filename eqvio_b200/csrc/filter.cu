@@ -114,6 +114,7 @@ struct eqvio_filter {
     int lazyMirror = 1;  // downdate refreshes the upper triangle only where the next chunk reads it
     std::vector<int> h_lmOfSorted;  // state indices of the correction rows (host copy of d_lmOf)
     int chain = 0;         // 0 = off (default); 2 = chained correction kernels in stream order; 1 = with concurrent downdates (experimental)
+    double* d_normalM = nullptr;  // Normal chart: sensor block of the coordinate differential and its inverse (2 x 441)
     int* d_cnt = nullptr;  // per-chunk completion counters of the downdates (chained correction)
     double* d_Snext[2] = {nullptr, nullptr};  // S block handed from one factor launch to the next
     int prLeast = 0, prGreatest = 0;  // stream priority range of the device
@@ -466,6 +467,7 @@ int alloc_device(eqvio_filter* f) {
     f->d_spec = reinterpret_cast<int*>(f->d_outblk + f->outOffSpec);
     f->d_status = reinterpret_cast<int*>(f->d_outblk + f->outOffStatus);
     f->d_out = reinterpret_cast<double*>(f->d_outblk + f->outOffEst);
+    CUDA_TRY(f, cudaMalloc(&f->d_normalM, 2 * 441 * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_cnt, 2 * (c1 + 1) * sizeof(int)));
     CUDA_TRY(f, cudaMemsetAsync(f->d_cnt, 0, 2 * (c1 + 1) * sizeof(int), f->stream));
     for (int k = 0; k < 2; ++k) CUDA_TRY(f, cudaMalloc(&f->d_Snext[k], CH_R * CH_R * sizeof(double)));
@@ -599,6 +601,10 @@ int plan_integration(eqvio_filter* f, double newTime, int* advanced) {
     *advanced = 0;
     if (newTime <= f->time || f->time < 0 || f->buf.empty()) return EQVIO_OK;
     const eqvio_settings& s = f->st;
+    if (!s.fastRiccati && s.useDiscreteStateMatrix && s.coordinateChoice == EQVIO_COORD_NORMAL) {
+        f->err = "useDiscreteStateMatrix in Normal coordinates has no CUDA path in this build";
+        return EQVIO_ERR_UNSUPPORTED;
+    }
     if (!s.fastRiccati && s.useDiscreteStateMatrix && !s.useDiscreteVelocityLift) {
         // the reference's stateMatrixADiscrete always differentiates liftVelocityDiscrete; the pairing with a continuous
         // velocity lift in the observer is not a configuration its settings document, and it is not mapped here
@@ -735,16 +741,25 @@ int enqueue_propagation_accurate(eqvio_filter* f) {
                           s.cameraPositionProcessVariance, s.pointProcessVariance};
     if ((rc = upload(f, f->dense.pdiag, pd, 8)) != EQVIO_OK) return rc;
     dense::Workspace& w = f->dense;
-    for (int i = 0; i < nsteps; ++i) {
-        const double dt = himu[13 * i];
+    const bool normal = s.coordinateChoice == EQVIO_COORD_NORMAL;
+    // Normal coordinates with fastRiccati: ONE step over the frame with the time-weighted mean IMU (VIOFilter.cpp:140-158),
+    // Sigma <- (I + dt A) Sigma (I + dt A)^T + dt (B Q B^T + P) with the dense A_normal = M A_euclid M^-1, B_normal = M B_euclid;
+    // the observer then integrates every buffered sample.  Otherwise one Riccati step per sample.
+    const bool single = s.fastRiccati != 0;
+    if (normal) {
+        dense::normal_m_sensor_kernel<<<1, 64, 0, f->stream>>>(f->d_xi0s, f->d_normalM, f->d_normalM + 441);
+        LAUNCH_CHECK(f, "normal_m_sensor_kernel");
+    }
+    for (int i = 0; i < (single ? 1 : nsteps); ++i) {
+        const double dt = single ? hh->fs.dtTotal : himu[13 * i];
         PrepArgs a;
         a.xi0s = f->d_xi0s;
         a.Xs = f->d_Xs[f->xcur];
         a.XsOut = f->d_Xs[1 - f->xcur];
         a.ctx = f->d_ctx;
-        a.steps = f->d_steps + i;
-        a.fr = f->d_hdrSteps + i;
-        a.imu = f->d_imu + (size_t)13 * i;
+        a.steps = single ? f->d_steps : f->d_steps + i;
+        a.fr = single ? f->d_hdr : f->d_hdrSteps + i;
+        a.imu = single ? f->d_imu : f->d_imu + (size_t)13 * i;
         a.discreteLift = s.useDiscreteVelocityLift ? 1 : 0;
         a.qdiag[0] = s.velGyrNoise * s.velGyrNoise;
         a.qdiag[1] = s.velAccNoise * s.velAccNoise;
@@ -764,7 +779,8 @@ int enqueue_propagation_accurate(eqvio_filter* f) {
             // integrateRiccatiStateAccurate: M = dt [A B; 0 0], R = exp(M).  integrateRiccatiStateDiscrete (VIO_eqf.cpp:93-103,
             // useDiscreteStateMatrix): R = [A0tD, dt B; 0 0] directly, with the numerically differentiated discrete state matrix
             // -- the products and the noise term below are then the same expressions (dt B (Q / dt) (dt B)^T = dt B Q B^T).
-            double* Tgt = s.useDiscreteStateMatrix ? R : M;
+            const bool discreteA = !single && s.useDiscreteStateMatrix;
+            double* Tgt = discreteA ? R : M;
             CUDA_TRY(f, cudaMemsetAsync(Tgt, 0, (size_t)n * n * sizeof(double), f->stream));
             dense::dense_fill_sensor_kernel<<<2, 256, 0, f->stream>>>(Tgt, n, dim, f->d_ctx, w.dtBs);
             LAUNCH_CHECK(f, "dense_fill_sensor_kernel");
@@ -772,7 +788,15 @@ int enqueue_propagation_accurate(eqvio_filter* f) {
                 dense::dense_fill_landmark_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(Tgt, n, dim, N, f->d_rows, dt);
                 LAUNCH_CHECK(f, "dense_fill_landmark_kernel");
             }
-            if (s.useDiscreteStateMatrix) {
+            if (normal) {
+                dense::normal_transform_kernel<<<1 + N, 128, 0, f->stream>>>(Tgt, n, dim, N, f->lm[f->lmcur], f->cap, f->d_normalM,
+                                                                             f->d_normalM + 441);
+                LAUNCH_CHECK(f, "normal_transform_kernel");
+            }
+            if (single) {
+                dense::dense_lincomb_kernel<<<cdiv((size_t)n * n, 256), 256, 0, f->stream>>>(R, n, 1.0, M, 0.0, nullptr, 0.0, nullptr, 1.0);
+                LAUNCH_CHECK(f, "dense_lincomb_kernel");
+            } else if (discreteA) {
                 dense::discrete_a_sensor_kernel<<<1, 64, 0, f->stream>>>(f->d_xi0s, f->d_Xs[f->xcur], f->d_imu + (size_t)13 * i, R, n, w.cc);
                 LAUNCH_CHECK(f, "discrete_a_sensor_kernel");
                 if (N > 0) {
@@ -806,7 +830,8 @@ int enqueue_propagation_accurate(eqvio_filter* f) {
         LAUNCH_CHECK(f, "observer_sensor_kernel");
         if (N > 0) {
             observer_landmark_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(f->lm[f->lmcur], f->lm[1 - f->lmcur], f->dids[f->lmcur],
-                                                                        f->dids[1 - f->lmcur], f->cap, N, f->d_steps + i, f->d_hdrSteps + i, TL_SLOT(f));
+                                                                        f->dids[1 - f->lmcur], f->cap, N, single ? f->d_steps : f->d_steps + i,
+                                                                        single ? f->d_hdr : f->d_hdrSteps + i, TL_SLOT(f));
             LAUNCH_CHECK(f, "observer_landmark_kernel");
             f->lmcur = 1 - f->lmcur;
         }
@@ -916,7 +941,8 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
     const bool anyNew = matched < n;
     const size_t maxOutliers = (size_t)((1.0 - f->st.featureRetention) * n);
     // steady frame: nothing enters or leaves before the gate, so the launch sequence is fully known now
-    P.steady = f->speculate && f->corrMode == 0 && N > 0 && n > 0 && !anyNew && !anyLost && f->st.fastRiccati;
+    const bool densePath = !f->st.fastRiccati || f->st.coordinateChoice == EQVIO_COORD_NORMAL;  // cuBLAS products, not graph-captured
+    P.steady = f->speculate && f->corrMode == 0 && N > 0 && n > 0 && !anyNew && !anyLost && !densePath;
     P.ignoreGate = maxOutliers == 0;
     if (P.steady) {
         P.speculated = true;
@@ -990,7 +1016,7 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
     // general frame: upload, propagate, gate; decisions follow in phase B
     CUDA_TRY(f, cudaMemcpyAsync(f->d_frame, f->h_frame, f->frameBytes, cudaMemcpyHostToDevice, f->stream));
     stage_mark(f, 0);
-    if ((rc = f->st.fastRiccati ? enqueue_propagation(f) : enqueue_propagation_accurate(f)) != EQVIO_OK) return rc;
+    if ((rc = densePath ? enqueue_propagation_accurate(f) : enqueue_propagation(f)) != EQVIO_OK) return rc;
     stage_mark(f, 1);
     if (N > 0) {
         if ((rc = enqueue_gate(f, N, true)) != EQVIO_OK) return rc;
@@ -1449,7 +1475,8 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fusedStea
     }
     launch_pdl(f, lift_kernel, dim3(cdiv(std::max(Nn, 1), 128)), dim3(128), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, Nn, f->d_xi0s, f->d_Xs[f->xcur], gammaFinal,
                                                                    s.useDiscreteInnovationLift ? 1 : 0, s.coordinateChoice,
-                                                                   f->d_status, f->d_status + 1, guard, fusedSteady ? f->d_out : (double*)nullptr, TL_SLOT(f));
+                                                                   f->d_status, f->d_status + 1, guard, fusedSteady ? f->d_out : (double*)nullptr,
+                                                                   s.coordinateChoice == EQVIO_COORD_NORMAL ? (const double*)(f->d_normalM + 441) : (const double*)nullptr, TL_SLOT(f));
     LAUNCH_CHECK(f, "lift_kernel");
     return EQVIO_OK;
 }
@@ -1533,8 +1560,9 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
         return EQVIO_ERR_INVALID_ARG;
     }
     *out = nullptr;
-    if (s->coordinateChoice != EQVIO_COORD_EUCLIDEAN && s->coordinateChoice != EQVIO_COORD_INVDEPTH) {
-        g_createError = "coordinateChoice: only Euclidean and InvDepth have a CUDA path";
+    if (s->coordinateChoice != EQVIO_COORD_EUCLIDEAN && s->coordinateChoice != EQVIO_COORD_INVDEPTH &&
+        s->coordinateChoice != EQVIO_COORD_NORMAL) {
+        g_createError = "coordinateChoice must be Euclidean, InvDepth or Normal";
         return EQVIO_ERR_UNSUPPORTED;
     }
     int count = 0;
@@ -1801,6 +1829,7 @@ void eqvio_destroy(eqvio_filter* f) {
     if (f->h_out) cudaFreeHost(f->h_out);
     cudaFree(f->d_outblk);
     cudaFree(f->d_cnt);
+    cudaFree(f->d_normalM);
     cudaFree(f->d_Snext[0]);
     cudaFree(f->d_Snext[1]);
     for (auto& g : f->graphs)

@@ -2349,7 +2349,9 @@ __global__ void gamma_kernel(const double* __restrict__ Z, int ldz, int m, int d
 __global__ void lift_kernel(double* __restrict__ lm, int cap, int N, const double* __restrict__ xi0s,
                             double* __restrict__ Xs, const double* __restrict__ Gamma, int discrete, int coord,
                             int* __restrict__ status, int* __restrict__ invalidFlag, const int* __restrict__ guard,
-                            double* __restrict__ estOut /* may be null: sensor(23) | p(3N) of the corrected state */, int tl) {
+                            double* __restrict__ estOut /* may be null: sensor(23) | p(3N) of the corrected state */,
+                            const double* __restrict__ MsInv /* Normal chart: inverse sensor block of the coordinate differential */,
+                            int tl) {
     pdl_wait();
     TL_MARK(tl, 0);
     if (*guard) { TL_MARK(tl, 1); return; }
@@ -2360,10 +2362,25 @@ __global__ void lift_kernel(double* __restrict__ lm, int cap, int N, const doubl
         GroupSensor D;
         bool bad = false;
         for (int k = 0; k < 21; ++k) bad |= !isfinite(Gamma[k]);
-        V3 gw = V3{Gamma[6], Gamma[7], Gamma[8]}, gx = V3{Gamma[9], Gamma[10], Gamma[11]};
-        V3 gv = V3{Gamma[12], Gamma[13], Gamma[14]};
-        V3 bw = V3{Gamma[15], Gamma[16], Gamma[17]}, bx = V3{Gamma[18], Gamma[19], Gamma[20]};
-        for (int k = 0; k < 6; ++k) D.beta[k] = Gamma[k];
+        double gs[21];
+        for (int k = 0; k < 21; ++k) gs[k] = Gamma[k];
+        if (coord == COORD_NORMAL) {
+            if (discrete) {  // normal.cpp:52-55: Euclidean coordinates of the point the normal chart assigns to Gamma
+                double gin[21];
+                for (int k = 0; k < 21; ++k) gin[k] = Gamma[k];
+                sensor_chart_std(sensor_chart_normal_inv(gin, xi0), xi0, gs);
+            } else {  // normal.cpp:47-50: M^-1 Gamma
+                for (int r = 0; r < 21; ++r) {
+                    double acc = 0.0;
+                    for (int c = 0; c < 21; ++c) acc += MsInv[r * 21 + c] * Gamma[c];
+                    gs[r] = acc;
+                }
+            }
+        }
+        V3 gw = V3{gs[6], gs[7], gs[8]}, gx = V3{gs[9], gs[10], gs[11]};
+        V3 gv = V3{gs[12], gs[13], gs[14]};
+        V3 bw = V3{gs[15], gs[16], gs[17]}, bx = V3{gs[18], gs[19], gs[20]};
+        for (int k = 0; k < 6; ++k) D.beta[k] = gs[k];
         if (discrete) {  // euclid.cpp:71-79
             D.A = se3_exp(gw, gx);
             D.w = xi0.vel - qrot(D.A.q, xi0.vel + gv);
@@ -2390,6 +2407,7 @@ __global__ void lift_kernel(double* __restrict__ lm, int cap, int N, const doubl
     Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
     double a = lm[F_QA * cap + i];
     V3 g = V3{Gamma[SOFF + 3 * i], Gamma[SOFF + 3 * i + 1], Gamma[SOFF + 3 * i + 2]};
+    if (coord == COORD_NORMAL) g = discrete ? point_chart_normal_inv(g, q0) - q0 : inverse(normal_M_landmark(q0)) * g;
     Quat DQ;
     double Da;
     if (discrete) {
@@ -2490,7 +2508,10 @@ __global__ void nees_eps_kernel(const double* __restrict__ lm, int cap, int N, c
         SensorState xi0 = unpack_sensor(xi0s);
         SensorState err = sensor_group_action(group_inverse(unpack_group(Xs)), unpack_sensor(trueSensor));
         double eps[21];
-        sensor_chart_std(err, xi0, eps);
+        if (coord == COORD_NORMAL)
+            sensor_chart_normal(err, xi0, eps);
+        else
+            sensor_chart_std(err, xi0, eps);
         for (int k = 0; k < 21; ++k) Z[(size_t)k * ldz + row] = eps[k];
     }
     if (i >= N) return;
@@ -2499,7 +2520,7 @@ __global__ void nees_eps_kernel(const double* __restrict__ lm, int cap, int N, c
     const double a = lm[F_QA * cap + i];
     V3 pt = V3{trueP[3 * i], trueP[3 * i + 1], trueP[3 * i + 2]};
     V3 pe = a * qrot(Q, pt);  // (Q^-1)^-1 p = Q p = a R_Q p  (VIOGroup.cpp:44-52 with X^-1, SOT3.h:95-97)
-    V3 e = (coord == COORD_INVDEPTH) ? invdepth_chart(pe, q0) : pe - q0;
+    V3 e = (coord == COORD_INVDEPTH) ? invdepth_chart(pe, q0) : (coord == COORD_NORMAL ? point_chart_normal(pe, q0) : pe - q0);
     Z[(size_t)(21 + 3 * i) * ldz + row] = e.x;
     Z[(size_t)(21 + 3 * i + 1) * ldz + row] = e.y;
     Z[(size_t)(21 + 3 * i + 2) * ldz + row] = e.z;

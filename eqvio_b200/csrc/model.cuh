@@ -20,7 +20,7 @@ namespace eqvio {
 constexpr int SENSOR_DIM = 21;  // VIOSensorState::CompDim
 constexpr int SOFF = 24;        // internal row offset of landmark 0 in Sigma (sensor block padded 21 -> 24)
 
-enum { COORD_EUCLIDEAN = 0, COORD_INVDEPTH = 1 };
+enum { COORD_EUCLIDEAN = 0, COORD_INVDEPTH = 1, COORD_NORMAL = 2 };
 enum { CAM_PINHOLE = 0, CAM_RADTAN = 1, CAM_EQUIDISTANT = 2 };
 
 struct Camera {
@@ -445,8 +445,107 @@ HD void drho3(const Camera& cam, V3 v, double* out /*2x3*/) {
         for (int j = 0; j < 3; ++j) out[3 * i + j] = J[3 * i] * S(0, j) + J[3 * i + 1] * S(1, j) + J[3 * i + 2] * S(2, j);
 }
 // useStar: y = measured pixel; otherwise y := project(qHat) (outputMatrixCi, EqFMatrices.cpp:84-89)
+// ------------------------------------------------------------------------------------------------
+// Normal coordinates (coordinateSuite/normal.cpp, VIOState.cpp:123-152,190-215,310-353)
+// ------------------------------------------------------------------------------------------------
+HD void sphere_chart_normal(V3 eta, V3 pole, double& e0, double& e1) {  // VIOState.cpp:310-327
+    const V3 y = qrot(quat_from_two_vectors(pole, V3{0, 0, 1}), eta);
+    const V3 ye3 = cross(y, V3{0, 0, 1});
+    const double sin_th = norm(ye3), cos_th = y.z;
+    const double th = atan2(sin_th, cos_th);
+    const double scale = fabs(th) < 1e-8 ? 1.0 : th / sin_th;
+    e0 = ye3.x * scale;
+    e1 = ye3.y * scale;
+}
+HD V3 sphere_chart_normal_inv(double e0, double e1, V3 pole) {  // VIOState.cpp:328-337
+    const V3 y = qrot(so3_exp(V3{-e0, -e1, -0.0}), V3{0, 0, 1});
+    return qrot(qinv(quat_from_two_vectors(pole, V3{0, 0, 1})), y);
+}
+HD void sphere_normal_inv_diff0(V3 pole, double* D /*3x2 row-major*/) {  // VIOState.cpp:346-353
+    const M3 Ri = qmat(qinv(quat_from_two_vectors(pole, V3{0, 0, 1})));
+    for (int r = 0; r < 3; ++r) {
+        D[2 * r] = Ri(r, 1);
+        D[2 * r + 1] = -Ri(r, 0);
+    }
+}
+HD V3 point_chart_normal(V3 p, V3 p0) {  // VIOState.cpp:190-203
+    const double rho = 1.0 / norm(p), rho0 = 1.0 / norm(p0);
+    double e0, e1;
+    sphere_chart_normal(rho * p, rho0 * p0, e0, e1);
+    return V3{e0, e1, log(rho / rho0)};
+}
+HD V3 point_chart_normal_inv(V3 eps, V3 p0) {  // VIOState.cpp:204-215
+    const double rho0 = 1.0 / norm(p0);
+    const V3 y = sphere_chart_normal_inv(eps.x, eps.y, rho0 * p0);
+    return y / (rho0 * exp(eps.z));
+}
+HD void se23_log(Quat q, V3 x0, V3 x1, double* out /*9*/) {  // SEn3.h:94-113
+    const V3 om = so3_log(q);
+    const M3 O = skew(om);
+    const double theta = sqrt(om.x * om.x + om.y * om.y + om.z * om.z);
+    double coef = 1.0 / 12.0;
+    if (fabs(theta) > 1e-8) coef = 1.0 / (theta * theta) * (1.0 - (theta * sin(theta)) / (2.0 * (1.0 - cos(theta))));
+    const M3 VInv = m3_identity() - 0.5 * O + coef * (O * O);
+    const V3 a = VInv * x0, b = VInv * x1;
+    out[0] = om.x; out[1] = om.y; out[2] = om.z;
+    out[3] = a.x; out[4] = a.y; out[5] = a.z;
+    out[6] = b.x; out[7] = b.y; out[8] = b.z;
+}
+HD void sensor_chart_normal(const SensorState& Xi, const SensorState& Xi0, double* eps) {  // VIOState.cpp:123-137
+    const SE3 A = se3_mul(se3_inv(Xi0.pose), Xi.pose);
+    const V3 v_xi0 = qrot(Xi0.pose.q, Xi0.vel), v_xi = qrot(Xi.pose.q, Xi.vel);
+    const V3 v_A = qrot(qinv(Xi0.pose.q), v_xi - v_xi0);
+    const SE3 B = se3_mul(se3_mul(se3_inv(Xi0.cam), A), Xi.cam);
+    for (int i = 0; i < 6; ++i) eps[i] = Xi.bias[i] - Xi0.bias[i];
+    se23_log(A.q, A.x, v_A, eps + 6);
+    se3_log(B, eps + 15);
+}
+HD SensorState sensor_chart_normal_inv(const double* eps, const SensorState& Xi0) {  // VIOState.cpp:138-152
+    Quat q;
+    V3 x0, x1;
+    se23_exp(V3{eps[6], eps[7], eps[8]}, V3{eps[9], eps[10], eps[11]}, V3{eps[12], eps[13], eps[14]}, q, x0, x1);
+    const SE3 B = se3_exp(V3{eps[15], eps[16], eps[17]}, V3{eps[18], eps[19], eps[20]});
+    const SE3 A = SE3{q, x0};
+    SensorState Xi;
+    for (int i = 0; i < 6; ++i) Xi.bias[i] = Xi0.bias[i] + eps[i];
+    Xi.pose = se3_mul(Xi0.pose, A);
+    const V3 v_xi0 = qrot(Xi0.pose.q, Xi0.vel);
+    Xi.vel = qrot(qinv(Xi.pose.q), v_xi0 + qrot(Xi0.pose.q, x1));
+    Xi.cam = se3_mul(se3_mul(se3_inv(A), Xi0.cam), B);
+    return Xi;
+}
+HD double normal_diff_step() { return cbrt(2.220446049250313e-16); }  // numericalDifferential's default h (Geometry.cpp:27-29)
+// landmark block of coordinateDifferential_normal_euclid (VIOState.cpp:391-401): central differences of
+// eps -> pointChart_normal(pointChart_euclid^-1(eps)); M row-major 3x3
+HD M3 normal_M_landmark(V3 p0) {
+    const double h = normal_diff_step();
+    M3 M;
+    for (int j = 0; j < 3; ++j) {
+        const V3 d = V3{j == 0 ? h : 0.0, j == 1 ? h : 0.0, j == 2 ? h : 0.0};
+        const V3 a = point_chart_normal(p0 + d, p0), b = point_chart_normal(p0 - d, p0);
+        M.m[0 * 3 + j] = (a.x - b.x) / (2 * h);
+        M.m[1 * 3 + j] = (a.y - b.y) / (2 * h);
+        M.m[2 * 3 + j] = (a.z - b.z) / (2 * h);
+    }
+    return M;
+}
+
 HD void output_block(const Camera& cam, int coord, V3 q0, Quat Qq, double Qa, bool useStar, double yu, double yv,
                      double* C /*2x3*/) {
+    if (coord == COORD_NORMAL) {  // normal.cpp:57-65: [J_pi(yHat) R_Q^T chartInvDiff0(q0), 0]; the measurement is not used
+        const V3 yHatN = qrot(qinv(Qq), normalized(q0));
+        double J[6], D[6];
+        cam_jacobian(cam, yHatN, J);
+        sphere_normal_inv_diff0(q0, D);  // the reference passes q0, not its bearing, as the pole (normalised inside)
+        const M3 Rt = qmat(qinv(Qq));
+        for (int i = 0; i < 2; ++i) {
+            double JR[3];
+            for (int k = 0; k < 3; ++k) JR[k] = J[3 * i] * Rt(0, k) + J[3 * i + 1] * Rt(1, k) + J[3 * i + 2] * Rt(2, k);
+            for (int j = 0; j < 2; ++j) C[3 * i + j] = JR[0] * D[j] + JR[1] * D[2 + j] + JR[2] * D[4 + j];
+            C[3 * i + 2] = 0.0;
+        }
+        return;
+    }
     V3 qHat = landmark_action(Qq, Qa, q0);
     V3 yHat = normalized(qHat);
     if (!useStar) cam_project(cam, qHat, yu, yv);

@@ -43,12 +43,12 @@ extern "C" {
 #define EQVIO_ERR_CUDA (-2)
 #define EQVIO_ERR_NUMERIC (-3)     /* NaN / non-SPD innovation covariance detected on device */
 #define EQVIO_ERR_CAPACITY (-4)    /* more landmarks than the handle was created for */
-#define EQVIO_ERR_UNSUPPORTED (-5) /* a Settings switch this build has no CUDA path for (Normal chart, useDiscreteStateMatrix
-                                      with a continuous velocity lift, other camera models) */
+#define EQVIO_ERR_UNSUPPORTED (-5) /* a Settings combination this build has no CUDA path for (useDiscreteStateMatrix with a
+                                      continuous velocity lift or in Normal coordinates, other camera models) */
 
 #define EQVIO_COORD_EUCLIDEAN 0
 #define EQVIO_COORD_INVDEPTH 1
-#define EQVIO_COORD_NORMAL 2 /* not implemented on device: EQVIO_ERR_UNSUPPORTED */
+#define EQVIO_COORD_NORMAL 2 /* normal.cpp: dense propagation (M A_euclid M^-1 with the numerically differentiated chart change M) */
 
 #define EQVIO_CAMERA_PINHOLE 0
 #define EQVIO_CAMERA_RADTAN 1

@@ -263,7 +263,7 @@ def test_silent_returns_and_errors():
     f.close()
     # switches without a CUDA path fail loudly
     with pytest.raises(eb.EqvioError) as ei:
-        eb.VIOFilter(eb.Settings(coordinateChoice=2), capacity=4)
+        eb.VIOFilter(eb.Settings(coordinateChoice=3), capacity=4)
     assert ei.value.code == eb._capi.EQVIO_ERR_UNSUPPORTED
     g = eb.VIOFilter(eb.Settings(fastRiccati=0, useDiscreteStateMatrix=1, useDiscreteVelocityLift=0), capacity=4)
     g.processIMUArray(fr.imu)
@@ -397,7 +397,7 @@ def test_feature_predictions_match_oracle():
     g2.close()
 
 
-@pytest.mark.parametrize("coord", [0, 1])
+@pytest.mark.parametrize("coord", [0, 1, 2])
 def test_nees_matches_oracle(coord):
     """computeNEES (VIO_eqf.cpp:153-170): device Cholesky solve vs the oracle's dense inverse, along a sequence."""
     import eqvio_b200 as eb
@@ -422,7 +422,7 @@ def test_nees_matches_oracle(coord):
         true.p = true.p * 1.01
         no = o.viewEqFState().computeNEES(true)
         ng = g.computeNEES(eb.VIOState(eb.VIOSensorState.fromFlat(true.sensor.flat()), true.p, true.ids))
-        assert np.isfinite(ng) and abs(ng - no) <= 1e-8 * max(1.0, abs(no)), (ng, no)
+        assert np.isfinite(ng) and abs(ng - no) <= (1e-6 if coord == 2 else 1e-8) * max(1.0, abs(no)), (ng, no)
     g.close()
 
 
@@ -440,6 +440,16 @@ def test_discrete_state_matrix(coord):
     with the numerically differentiated stateMatrixADiscrete (EqFMatrices.cpp:24-41; central differences, h = cbrt(eps):
     rounding in the function values is amplified by 1 / 2h ~ 8e4, hence the looser tolerance)."""
     stream = make_stream(N=12, frames=4, coord=coord, settings_overrides=dict(fastRiccati=False, useDiscreteStateMatrix=True))
+    _check(run_gpu(stream), run_oracle(stream), tol=1e-7)
+
+
+@pytest.mark.parametrize("overrides", [dict(), dict(useDiscreteInnovationLift=False), dict(useDiscreteVelocityLift=False),
+                                       dict(fastRiccati=False), dict(useEquivariantOutput=False)])
+def test_normal_coordinates(overrides):
+    """coordinateChoice = Normal (coordinateSuite/normal.cpp): A = M A_euclid M^-1, B = M B_euclid with the numerically
+    differentiated chart change M (VIOState.cpp:391-401), its own output block, innovation lifts through M^-1 / the chart
+    maps.  Dense propagation on the device vs the oracle; M carries ~1e-10 of differentiation noise in both."""
+    stream = make_stream(N=10, frames=5, coord=2, settings_overrides=overrides)
     _check(run_gpu(stream), run_oracle(stream), tol=1e-7)
 
 
