@@ -120,6 +120,9 @@ struct eqvio_filter {
     int prLeast = 0, prGreatest = 0;  // stream priority range of the device
     bool pdlHold = false;  // next launch_pdl is a plain launch (its predecessor produces what the kernel reads before its wait)
     int pdl = 1;           // chunk kernels are launched with programmatic dependent launch allowed
+    int specNew = 1;       // frames with new ids also speculate (new-landmark positions computed on the device)
+    int *d_keepI = nullptr, *d_newMeas = nullptr;
+    int newMeasCap = 0;
     int fuseSmall = 1;     // steady update: gate + measurement rows in one launch, lift + state estimate in one launch
     int fuseObserver = 1;  // sensor + landmark parts of the observer integration as one software-pipelined kernel
     const char* tlNames[512] = {nullptr};
@@ -175,6 +178,7 @@ struct eqvio_filter {
         Camera cam;
         bool corrected = false;
         bool speculated = false;       // correction launched before the gate results were read
+        int specNewCount = 0;          // new landmarks appended speculatively (positions from the device-side median depth)
         bool steady = false;           // phase A enqueued the whole update (possibly as a CUDA graph)
         bool ignoreGate = false;       // featureRetention leaves no room for removals: the gate flag is moot
         std::vector<int> oldIds;       // state ids when the gate ran (gate results are indexed like this)
@@ -468,6 +472,7 @@ int alloc_device(eqvio_filter* f) {
     f->d_status = reinterpret_cast<int*>(f->d_outblk + f->outOffStatus);
     f->d_out = reinterpret_cast<double*>(f->d_outblk + f->outOffEst);
     CUDA_TRY(f, cudaMalloc(&f->d_normalM, 2 * 441 * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&f->d_keepI, c1 * sizeof(int)));
     CUDA_TRY(f, cudaMalloc(&f->d_cnt, 2 * (c1 + 1) * sizeof(int)));
     CUDA_TRY(f, cudaMemsetAsync(f->d_cnt, 0, 2 * (c1 + 1) * sizeof(int), f->stream));
     for (int k = 0; k < 2; ++k) CUDA_TRY(f, cudaMalloc(&f->d_Snext[k], CH_R * CH_R * sizeof(double)));
@@ -535,7 +540,7 @@ int reset_state(eqvio_filter* f, const double sensor[23], int n, const int* ids,
 
 // Apply a landmark map (stable compaction + append) to lm / ids / Sigma.
 int apply_map(eqvio_filter* f, const std::vector<int>& map, const std::vector<int>& newIds, const std::vector<double>& newP,
-              double newVar, double newDepthVar) {
+              double newVar, double newDepthVar, bool newPOnDevice = false) {
     const int newN = (int)map.size();
     if (newN > f->cap) {
         f->err = "landmark count exceeds the capacity the handle was created with";
@@ -561,8 +566,8 @@ int apply_map(eqvio_filter* f, const std::vector<int>& map, const std::vector<in
             if (!newP.empty()) std::memcpy(h, newP.data(), newP.size() * sizeof(double));
             std::memcpy(h + offMap, map.data(), (size_t)newN * sizeof(int));
             if (!newIds.empty()) std::memcpy(h + offIds, newIds.data(), newIds.size() * sizeof(int));
-            // without new landmarks only the map travels
-            const size_t from = newIds.empty() ? offMap : 0;
+            // without new landmarks (or with positions a kernel already wrote to d_newP) only the map and the ids travel
+            const size_t from = (newIds.empty() || newPOnDevice) ? offMap : 0;
             CUDA_TRY(f, cudaMemcpyAsync(f->d_mapblk + from, h + from, bytes - from, cudaMemcpyHostToDevice, f->stream));
         }
         compact_landmarks_kernel<<<cdiv(newN, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->lm[1 - f->lmcur], f->cap,
@@ -586,13 +591,13 @@ int apply_map(eqvio_filter* f, const std::vector<int>& map, const std::vector<in
 
 // removeOldLandmarks (VIOFilter.cpp:280-302) followed by an append of `addIds` with positions `addP`.
 int remove_and_append(eqvio_filter* f, const std::vector<char>& keep, const std::vector<int>& addIds,
-                      const std::vector<double>& addP, double newVar, double newDepthVar) {
+                      const std::vector<double>& addP, double newVar, double newDepthVar, bool addPOnDevice = false) {
     std::vector<int> map;
     map.reserve(f->ids.size() + addIds.size());
     for (int i = 0; i < (int)f->ids.size(); ++i)
         if (keep[i]) map.push_back(i);
     for (int k = 0; k < (int)addIds.size(); ++k) map.push_back(-1 - k);
-    return apply_map(f, map, addIds, addP, newVar, newDepthVar);
+    return apply_map(f, map, addIds, addP, newVar, newDepthVar, addPOnDevice);
 }
 
 // integrateUpToTime (VIOFilter.cpp:134-192), host part: segment lengths, time-weighted mean IMU, buffer pruning.
@@ -1095,7 +1100,14 @@ int vision_phase_b(eqvio_filter* f) {
     // Speculation: with no new ids the only thing the host needs from the device is "did any landmark trip a
     // gate".  The correction is launched right away, guarded on the device by that flag; phase C redoes it
     // through the exact path in the (rare) case the flag came back set.
-    P.speculated = f->speculate && f->corrMode == 0 && P.gated && !anyNew && maxOutliers > 0;
+    // Frames that bring NEW ids speculate too: the positions of the new landmarks (bearing x median scene depth) are computed
+    // on the device from the gate kernel's depths under the same "no gate trips" assumption, so nothing waits for the host.
+    int nNewIds = 0, nKeptOld = 0;
+    for (int j = 0; j < n; ++j) nNewIds += !measInState[j];
+    for (int i = 0; i < N; ++i) nKeptOld += P.keep[i] ? 1 : 0;
+    const bool specNew = f->speculate && f->specNew && f->corrMode == 0 && P.gated && anyNew && maxOutliers > 0 && N > 0 &&
+                         nKeptOld + nNewIds <= f->cap;  // (over capacity: the exact path reports the error)
+    P.speculated = f->speculate && f->corrMode == 0 && P.gated && (!anyNew || specNew) && maxOutliers > 0;
     const bool noGateNeeded = !P.gated || (maxOutliers == 0 && !(anyNew && s.useMedianDepth));
     if (!P.speculated && !noGateNeeded) CUDA_TRY(f, cudaStreamSynchronize(f->stream));
     std::vector<char> outlier;
@@ -1106,6 +1118,31 @@ int vision_phase_b(eqvio_filter* f) {
     // addNewLandmarks (VIOFilter.cpp:258-278)
     std::vector<int> addIds;
     std::vector<double> addP;
+    if (anyNew && specNew) {
+        std::vector<int> keepI(N), newMeas;
+        for (int i = 0; i < N; ++i) keepI[i] = keep[i] ? 1 : 0;
+        for (int j = 0; j < n; ++j)
+            if (!measInState[j]) {
+                addIds.push_back(P.mids[j]);
+                newMeas.push_back(j);
+            }
+        P.specNewCount = (int)addIds.size();
+        if ((int)newMeas.size() > f->newMeasCap) {
+            CUDA_TRY(f, cudaStreamSynchronize(f->stream));
+            cudaFree(f->d_newMeas);
+            f->newMeasCap = 2 * (int)newMeas.size() + 64;
+            CUDA_TRY(f, cudaMalloc(&f->d_newMeas, f->newMeasCap * sizeof(int)));
+        }
+        if ((rc = upload(f, f->d_keepI, keepI.data(), (size_t)N)) != EQVIO_OK) return rc;
+        if ((rc = upload(f, f->d_newMeas, newMeas.data(), newMeas.size())) != EQVIO_OK) return rc;
+        launch_pdl(f, new_landmark_kernel, dim3(1), dim3(256), (size_t)0, f->stream, (const double*)f->d_gate, (const int*)f->d_keepI, N,
+                   s.useMedianDepth ? 1 : 0, s.initialSceneDepth, (const FrameHeader*)f->d_hdr, (const double*)f->d_y, (const int*)f->d_newMeas,
+                   (int)newMeas.size(), f->d_newP);
+        LAUNCH_CHECK(f, "new_landmark_kernel");
+        if ((rc = remove_and_append(f, keep, addIds, addP, s.initialPointVariance, -1.0, true)) != EQVIO_OK) return rc;
+        stage_mark(f, 2);
+        return launch_correction(f, f->d_spec);
+    }
     if (anyNew) {
         double depth = s.initialSceneDepth;
         if (s.useMedianDepth && P.h_gate) {  // getMedianSceneDepth, VIOFilter.cpp:366-380
@@ -1520,7 +1557,39 @@ int vision_phase_c(eqvio_filter* f, int* did_update) {
         std::vector<char> keepNow;
         for (size_t i = 0; i < P.oldIds.size(); ++i)
             if (P.keep[i]) keepNow.push_back(!outlier[i]);
-        int rc = remove_and_append(f, keepNow, {}, {}, 0.0, -1.0);
+        std::vector<int> addIds;
+        std::vector<double> addP;
+        if (P.specNewCount > 0) {
+            // the speculative append used the median depth of ALL kept landmarks: drop those landmarks and add them again
+            // with the depth of the landmarks that survive the gate (VIOFilter.cpp:206-219 order: outliers first, then new ids)
+            for (int k = 0; k < P.specNewCount; ++k) keepNow.push_back(0);
+            const eqvio_settings& s = f->st;
+            const int N0 = (int)P.oldIds.size();
+            double depth = s.initialSceneDepth;
+            if (s.useMedianDepth && P.h_gate) {
+                const double* depth2 = P.h_gate + 2 * N0;
+                std::vector<double> d2;
+                for (int i = 0; i < N0; ++i)
+                    if (P.keep[i] && !outlier[i]) d2.push_back(depth2[i]);
+                if (!d2.empty()) {
+                    auto mid = d2.begin() + d2.size() / 2;
+                    std::nth_element(d2.begin(), mid, d2.end());
+                    depth = std::sqrt(*mid);
+                }
+            }
+            std::vector<char> inState(P.n, 0);
+            for (int i = 0; i < N0; ++i)
+                if (P.measIdx[i] >= 0) inState[P.measIdx[i]] = 1;
+            for (int j = 0; j < P.n; ++j)
+                if (!inState[j]) {
+                    addIds.push_back(P.mids[j]);
+                    V3 b = cam_undistort(P.cam, P.my[2 * j], P.my[2 * j + 1]);
+                    addP.push_back(b.x * depth);
+                    addP.push_back(b.y * depth);
+                    addP.push_back(b.z * depth);
+                }
+        }
+        int rc = remove_and_append(f, keepNow, addIds, addP, f->st.initialPointVariance, -1.0);
         if (rc == EQVIO_OK) rc = launch_correction(f, f->d_spec + 1);
         if (rc != EQVIO_OK) return rc;
         CUDA_TRY(f, cudaStreamSynchronize(f->stream));
@@ -1830,6 +1899,8 @@ void eqvio_destroy(eqvio_filter* f) {
     cudaFree(f->d_outblk);
     cudaFree(f->d_cnt);
     cudaFree(f->d_normalM);
+    cudaFree(f->d_keepI);
+    cudaFree(f->d_newMeas);
     cudaFree(f->d_Snext[0]);
     cudaFree(f->d_Snext[1]);
     for (auto& g : f->graphs)
@@ -2383,6 +2454,9 @@ int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
             if (value < 0 || value > 2) return EQVIO_ERR_INVALID_ARG;
             f->chain = value;
             clear_graphs(f);
+            return EQVIO_OK;
+        case EQVIO_TUNE_SPECULATE_NEW:
+            f->specNew = value != 0;
             return EQVIO_OK;
         case EQVIO_TUNE_FUSE_SMALL:
             f->fuseSmall = value != 0;

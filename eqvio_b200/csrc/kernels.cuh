@@ -720,6 +720,58 @@ __global__ void gate_kernel(const double* __restrict__ lm, int cap, int N, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// addNewLandmarks on the device (VIOFilter.cpp:258-278 with getMedianSceneDepth :366-380): positions of the new ids =
+// undistorted bearing x scene depth, the depth being the square root of the MEDIAN squared depth of the kept landmarks
+// (std::nth_element at size / 2, i.e. the element of rank size / 2 in ascending order -- found here by rank counting,
+// exact whatever the ties).  gate = the gate kernel's output (depth^2 at [2N, 3N)); keep[i] != 0 for landmarks that stay.
+// One CTA.  Lets a frame that brings new ids run without a host round trip for the depth.
+// ------------------------------------------------------------------------------------------------
+__global__ void new_landmark_kernel(const double* __restrict__ gate, const int* __restrict__ keep, int N, int useMedian, double initialDepth,
+                                    const FrameHeader* __restrict__ fr, const double* __restrict__ y, const int* __restrict__ newMeas,
+                                    int nNew, double* __restrict__ newP) {
+    pdl_wait();
+    __shared__ double sDepth;
+    __shared__ int sCount;
+    if (threadIdx.x == 0) {
+        sDepth = initialDepth;
+        sCount = 0;
+    }
+    __syncthreads();
+    if (useMedian) {
+        int cnt = 0;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) cnt += keep[i] ? 1 : 0;
+        atomicAdd(&sCount, cnt);
+        __syncthreads();
+        const int M = sCount, mid = M / 2;
+        if (M > 0) {
+            const double* d2 = gate + 2 * (size_t)N;
+            for (int i = threadIdx.x; i < N; i += blockDim.x) {
+                if (!keep[i]) continue;
+                const double v = d2[i];
+                int less = 0, equal = 0;
+                for (int k = 0; k < N; ++k) {
+                    if (!keep[k]) continue;
+                    const double u = d2[k];
+                    less += u < v ? 1 : 0;
+                    equal += u == v ? 1 : 0;
+                }
+                if (less <= mid && mid < less + equal) sDepth = sqrt(v);  // every thread that qualifies writes the same value
+            }
+        }
+        __syncthreads();
+    }
+    const double depth = sDepth;
+    const Camera cam = fr->cam;
+    for (int t = threadIdx.x; t < nNew; t += blockDim.x) {
+        const int j = newMeas[t];
+        const V3 b = cam_undistort(cam, y[2 * j], y[2 * j + 1]);
+        newP[3 * t] = b.x * depth;
+        newP[3 * t + 1] = b.y * depth;
+        newP[3 * t + 2] = b.z * depth;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Stable compaction / append of landmarks (removeLandmarkByIndex + addNewLandmarks,
 // VIO_eqf.cpp:172-178,225-245).  map[p] = source landmark index of destination landmark p, or
 // -1-k for the k-th new landmark (identity Q, covariance newVar[0] I, newVar[1] on the depth

@@ -350,7 +350,7 @@ class VIOFilter:
         return dict(propagation=ms[0], preprocessing=ms[1], correction=ms[2])
 
     def setTuning(self, correction=None, chunkLandmarks=None, speculate=None, graph=None, pipeline=None, downdate=None,
-                  lookahead=None, fuseObserver=None, pdl=None, chain=None, fuseSmall=None):
+                  lookahead=None, fuseObserver=None, pdl=None, chain=None, fuseSmall=None, speculateNew=None):
         """Evaluation-order knobs (eqvio_set_tuning): correction 0 = sequential chunks, 1 = batch sweep."""
         if speculate is not None:
             self._check(lib.eqvio_set_tuning(self._h, 2, int(speculate)))
@@ -360,6 +360,8 @@ class VIOFilter:
             self._check(lib.eqvio_set_tuning(self._h, 4, int(pipeline)))
         if downdate is not None:  # 0 = fp64 DMMA, 1 = tcgen05 split-bf16 / fp32 accumulate
             self._check(lib.eqvio_set_tuning(self._h, 5, int(downdate)))
+        if speculateNew is not None:
+            self._check(lib.eqvio_set_tuning(self._h, 11, int(speculateNew)))
         if fuseSmall is not None:
             self._check(lib.eqvio_set_tuning(self._h, 10, int(fuseSmall)))
         if chain is not None:  # 1 = chained correction (look-ahead CTA + concurrent downdates), 2 = same in stream order, 0 = off

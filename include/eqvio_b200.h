@@ -249,6 +249,11 @@ int eqvio_get_host_profile(eqvio_filter* f, int reset, double us[4], long long* 
 /*   EQVIO_TUNE_FUSE_SMALL: 1 (default) = in a steady update the gate and the measurement rows (C*, ytilde) run as one launch
  *                         and the innovation lift also emits the state estimate; 0 = four separate kernels.  Same arithmetic. */
 #define EQVIO_TUNE_FUSE_SMALL 10
+/*   EQVIO_TUNE_SPECULATE_NEW: 1 (default) = frames that bring new ids speculate as well: the new landmarks' positions (bearing x
+ *                         median scene depth, VIOFilter.cpp:258-278,366-380) are computed on the device from the gate kernel's depths,
+ *                         so the update needs no host round trip; if a gate trips they are dropped and added again through the exact
+ *                         host path; 0 = wait for the gate scalars whenever a frame brings new ids. */
+#define EQVIO_TUNE_SPECULATE_NEW 11
 int eqvio_set_tuning(eqvio_filter* f, int key, int value);
 /* Version / build info string (arch the kernels were compiled for). */
 const char* eqvio_build_info(void);

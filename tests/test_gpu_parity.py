@@ -163,6 +163,37 @@ def test_new_landmarks_from_bearings_median_depth():
     g.close()
 
 
+@pytest.mark.parametrize("speculateNew", [1, 0])
+@pytest.mark.parametrize("noisy", [False, True])
+def test_real_data_flow_new_and_lost_ids_inside_the_vision_call(speculateNew, noisy):
+    """eqvio_opt's flow (no augmentLandmarkStates): lost ids are pruned and new ids added INSIDE processVisionData, on frames
+    whose gates may trip as well (noisy case: outliers + new ids on the same frame exercise the drop-and-re-add redo of the
+    speculative append).  Discrete decisions and values must match the oracle either way."""
+    import eqvio_b200 as eb
+    from oracle import eqf
+    from parity_utils import snapshot_oracle
+
+    ov = dict(outlierThresholdAbs=3.0, outlierThresholdProb=6.0, measurementNoise=0.5, featureRetention=0.2) if noisy else {}
+    so = dict(outputNoise=True, inputNoise=True) if noisy else {}
+    stream = make_stream(N=40, frames=12, coord=0, settings_overrides=ov, sim_overrides=so)
+    o = eqf.VIOFilter(stream["settings"], stream["init"], 0.0)
+    g, cam = gpu_filter(stream)
+    g.setTuning(speculateNew=speculateNew)
+    removed = 0
+    for fr in stream["frames"]:
+        for row in fr.imu:
+            o.processIMUData(eqf.IMUVelocity(row[0], row[1:4], row[4:7], row[7:10], row[10:13]))
+        g.processIMUArray(fr.imu)
+        o.processVisionData(eqf.VisionMeasurement.fromArrays(fr.stamp, fr.ids, fr.y, stream["cam"]))
+        g.processVisionArrays(fr.stamp, fr.ids, fr.y, cam)
+        e = compare_states(snapshot_gpu(g), snapshot_oracle(o))
+        assert e["ids_equal"] and e["sigma"] < TOL and e["state"] < TOL
+        removed += len(g.lastOutliers())
+    if noisy:
+        assert removed > 0, "the noisy case is meant to trip gates"
+    g.close()
+
+
 def test_keep_lost_landmarks():
     """removeLostLandmarks = false: unmeasured landmarks stay in the state with zero C columns."""
     import eqvio_b200 as eb
