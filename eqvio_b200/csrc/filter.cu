@@ -85,6 +85,8 @@ struct eqvio_filter {
     double* d_imu = nullptr;
     int maxSteps = 0;
     int yCap = 0;
+    size_t offKeepF = 0, offNewMeasF = 0, offMapF = 0, offNewIdsF = 0, offCounts = 0;
+    int *d_keepF = nullptr, *d_newMeasF = nullptr, *d_mapF = nullptr, *d_newIdsF = nullptr, *d_counts = nullptr;
     // fixed pinned output block of the steady path: gate scalars | spec flag | status words
     unsigned char* h_out = nullptr;
     size_t outOffSpec = 0, outOffStatus = 0, outOffEst = 0, outBytes = 0;
@@ -396,7 +398,14 @@ int alloc_frame(eqvio_filter* f, int steps, int ycap) {
     f->offMeasIdx = up(f->offY + (size_t)ycap * 2 * sizeof(double));
     f->offLmOf = up(f->offMeasIdx + cap1 * sizeof(int));
     f->offYIdx = up(f->offLmOf + cap1 * sizeof(int));
-    f->frameBytes = up(f->offYIdx + cap1 * sizeof(int));
+    // landmark-set change of a planned frame (lost ids pruned, new ids appended inside the update): keep flags of the old state,
+    // measurement indices of the new ids, old-index map and ids of the new state, counts
+    f->offKeepF = up(f->offYIdx + cap1 * sizeof(int));
+    f->offNewMeasF = up(f->offKeepF + cap1 * sizeof(int));
+    f->offMapF = up(f->offNewMeasF + (size_t)std::max(ycap, 1) * sizeof(int));
+    f->offNewIdsF = up(f->offMapF + cap1 * sizeof(int));
+    f->offCounts = up(f->offNewIdsF + cap1 * sizeof(int));
+    f->frameBytes = up(f->offCounts + 64);
     CUDA_TRY(f, cudaMalloc(&f->d_frame, f->frameBytes));
     CUDA_TRY(f, cudaMallocHost(&f->h_frame, f->frameBytes));
     std::memset(f->h_frame, 0, f->frameBytes);
@@ -408,6 +417,11 @@ int alloc_frame(eqvio_filter* f, int steps, int ycap) {
     f->d_measIdx = reinterpret_cast<int*>(f->d_frame + f->offMeasIdx);
     f->d_lmOf = reinterpret_cast<int*>(f->d_frame + f->offLmOf);
     f->d_yIdx = reinterpret_cast<int*>(f->d_frame + f->offYIdx);
+    f->d_keepF = reinterpret_cast<int*>(f->d_frame + f->offKeepF);
+    f->d_newMeasF = reinterpret_cast<int*>(f->d_frame + f->offNewMeasF);
+    f->d_mapF = reinterpret_cast<int*>(f->d_frame + f->offMapF);
+    f->d_newIdsF = reinterpret_cast<int*>(f->d_frame + f->offNewIdsF);
+    f->d_counts = reinterpret_cast<int*>(f->d_frame + f->offCounts);
     return EQVIO_OK;
 }
 
@@ -539,6 +553,24 @@ int reset_state(eqvio_filter* f, const double sensor[23], int n, const int* ids,
 }
 
 // Apply a landmark map (stable compaction + append) to lm / ids / Sigma.
+// Device part of a landmark-set change: stable compaction / append of the landmark arrays and of Sigma (both ping-pong).
+int launch_compaction(eqvio_filter* f, int newN, const int* d_map, const int* d_newIds, const double* d_newP, double newVar,
+                      double newDepthVar) {
+    if (newN > 0) {
+        compact_landmarks_kernel<<<cdiv(newN, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->lm[1 - f->lmcur], f->cap, f->dids[f->lmcur],
+                                                                          f->dids[1 - f->lmcur], d_map, newN, d_newP, d_newIds);
+        LAUNCH_CHECK(f, "compact_landmarks_kernel");
+        f->lmcur = 1 - f->lmcur;
+    }
+    const int nb = 8 + newN;
+    dim3 block(32, 8);
+    dim3 grid(cdiv(nb, 32), cdiv(nb, 8));
+    compact_sigma_kernel<<<grid, block, 0, f->stream>>>(f->Sig[f->cur], f->Sig[1 - f->cur], f->ld, d_map, newN, newVar, newDepthVar);
+    LAUNCH_CHECK(f, "compact_sigma_kernel");
+    f->cur = 1 - f->cur;
+    return EQVIO_OK;
+}
+
 int apply_map(eqvio_filter* f, const std::vector<int>& map, const std::vector<int>& newIds, const std::vector<double>& newP,
               double newVar, double newDepthVar, bool newPOnDevice = false) {
     const int newN = (int)map.size();
@@ -570,21 +602,8 @@ int apply_map(eqvio_filter* f, const std::vector<int>& map, const std::vector<in
             const size_t from = (newIds.empty() || newPOnDevice) ? offMap : 0;
             CUDA_TRY(f, cudaMemcpyAsync(f->d_mapblk + from, h + from, bytes - from, cudaMemcpyHostToDevice, f->stream));
         }
-        compact_landmarks_kernel<<<cdiv(newN, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->lm[1 - f->lmcur], f->cap,
-                                                                          f->dids[f->lmcur], f->dids[1 - f->lmcur], f->d_map,
-                                                                          newN, f->d_newP, f->d_newIds);
-        LAUNCH_CHECK(f, "compact_landmarks_kernel");
-        f->lmcur = 1 - f->lmcur;
     }
-    {
-        const int nb = 8 + newN;
-        dim3 block(32, 8);
-        dim3 grid(cdiv(nb, 32), cdiv(nb, 8));
-        compact_sigma_kernel<<<grid, block, 0, f->stream>>>(f->Sig[f->cur], f->Sig[1 - f->cur], f->ld, f->d_map, newN, newVar,
-                                                            newDepthVar);
-        LAUNCH_CHECK(f, "compact_sigma_kernel");
-        f->cur = 1 - f->cur;
-    }
+    if ((rc = launch_compaction(f, newN, f->d_map, f->d_newIds, f->d_newP, newVar, newDepthVar)) != EQVIO_OK) return rc;
     f->ids.swap(nids);
     return EQVIO_OK;
 }
@@ -854,27 +873,49 @@ int enqueue_gate(eqvio_filter* f, int N, bool clearFlag) {
     return EQVIO_OK;
 }
 
-int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fusedSteady = false);
+int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate = false, bool fuseEst = false);
+struct FramePlan;
 
 // The whole device side of a steady frame (no landmark enters or leaves before the gate): frame upload,
 // propagation, gate, guarded correction, result downloads into the fixed pinned block.  Issued either directly
 // or under stream capture (then replayed as one CUDA graph).
-int enqueue_steady_update(eqvio_filter* f, int N, int nm) {
+// plan: landmark-set change decided from the ids alone (lost ids pruned, new ids appended); null for a frame without one.
+struct FramePlan {
+    int Nnew = 0, nNew = 0;
+    std::vector<int> nids;  // ids of the new state
+};
+int enqueue_steady_update(eqvio_filter* f, int N, int nm, const FramePlan* plan) {
     int rc;
+    const eqvio_settings& s = f->st;
     CUDA_TRY(f, cudaMemcpyAsync(f->d_frame, f->h_frame, f->frameBytes, cudaMemcpyHostToDevice, f->stream));
     if ((rc = enqueue_propagation(f)) != EQVIO_OK) return rc;
-    const bool fused = f->fuseSmall && f->corrMode == 0;
-    if (!fused && (rc = enqueue_gate(f, N, false)) != EQVIO_OK) return rc;  // riccati_prep_kernel re-armed the flag
-    if ((rc = enqueue_correction(f, nm, f->d_spec, fused)) != EQVIO_OK) return rc;
+    const bool fuseEst = f->fuseSmall && f->corrMode == 0;
+    const bool fuseGate = fuseEst && !plan;  // with a landmark-set change the gate sees the OLD state, the rows the NEW one
+    if (!fuseGate && (rc = enqueue_gate(f, N, false)) != EQVIO_OK) return rc;  // riccati_prep_kernel re-armed the flag
+    int Nout = N;
+    if (plan) {
+        // everything below reads its per-frame data (keep flags, new measurement indices, map, new ids, count) from the frame
+        // block, so the same graph serves every frame with these sizes
+        if (plan->nNew > 0) {
+            launch_pdl(f, new_landmark_kernel, dim3(1), dim3(256), (size_t)0, f->stream, (const double*)f->d_gate, (const int*)f->d_keepF, N,
+                       s.useMedianDepth ? 1 : 0, s.initialSceneDepth, (const FrameHeader*)f->d_hdr, (const double*)f->d_y,
+                       (const int*)f->d_newMeasF, 0, (const int*)f->d_counts, f->d_newP);
+            LAUNCH_CHECK(f, "new_landmark_kernel");
+        }
+        if ((rc = launch_compaction(f, plan->Nnew, f->d_mapF, f->d_newIdsF, f->d_newP, s.initialPointVariance, -1.0)) != EQVIO_OK) return rc;
+        f->ids = plan->nids;
+        Nout = plan->Nnew;
+    }
+    if ((rc = enqueue_correction(f, nm, f->d_spec, fuseGate, fuseEst)) != EQVIO_OK) return rc;
     // stateEstimate() is what every caller asks for next (main_opt.cpp:225, main_sim.cpp:146): produced here, by the lift itself
     // in the fused form
-    if (!fused) {
-        launch_pdl(f, state_estimate_kernel, dim3(cdiv(N, 128)), dim3(128), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, N, f->d_xi0s,
+    if (!fuseEst) {
+        launch_pdl(f, state_estimate_kernel, dim3(cdiv(Nout, 128)), dim3(128), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, Nout, f->d_xi0s,
                    f->d_Xs[f->xcur], f->d_out, TL_SLOT(f));
         LAUNCH_CHECK(f, "state_estimate_kernel");
     }
     // one download: gate scalars, gate flag, status words, state estimate (the block has the layout of h_out)
-    CUDA_TRY(f, cudaMemcpyAsync(f->h_out, f->d_outblk, f->outOffEst + (23 + 3 * (size_t)N) * sizeof(double), cudaMemcpyDeviceToHost,
+    CUDA_TRY(f, cudaMemcpyAsync(f->h_out, f->d_outblk, f->outOffEst + (23 + 3 * (size_t)Nout) * sizeof(double), cudaMemcpyDeviceToHost,
                                 f->stream));
     return EQVIO_OK;
 }
@@ -945,29 +986,85 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
     f->h_lmOfSorted.assign(hLmOf, hLmOf + matched);
     const bool anyNew = matched < n;
     const size_t maxOutliers = (size_t)((1.0 - f->st.featureRetention) * n);
-    // steady frame: nothing enters or leaves before the gate, so the launch sequence is fully known now
+    // Planned frame: every decision that shapes the launch sequence is known now.  That is the case when nothing enters or
+    // leaves before the gate, and also when ids are lost (pruned, VIOFilter.cpp:203-205) or new (appended with bearing x median
+    // depth, :258-278) -- those sets follow from the ids alone, and the new landmarks' positions are computed on the device under
+    // the same "no gate trips" assumption the speculative correction makes (exact redo in phase C otherwise).
     const bool densePath = !f->st.fastRiccati || f->st.coordinateChoice == EQVIO_COORD_NORMAL;  // cuBLAS products, not graph-captured
-    P.steady = f->speculate && f->corrMode == 0 && N > 0 && n > 0 && !anyNew && !anyLost && !densePath;
+    int nLost = 0;
+    for (int i = 0; i < N; ++i) nLost += P.keep[i] ? 0 : 1;
+    const int nNewIds = n - matched;
+    const bool changeOk = (!anyNew && !anyLost) || (f->specNew && (N - nLost) + nNewIds <= f->cap && (N - nLost) + nNewIds > 0);
+    P.steady = f->speculate && f->corrMode == 0 && N > 0 && n > 0 && !densePath && changeOk;
     P.ignoreGate = maxOutliers == 0;
     if (P.steady) {
+        FramePlan plan;
+        const bool change = anyNew || anyLost;
+        int matchedNew = matched;
+        if (change) {
+            int* hKeep = reinterpret_cast<int*>(f->h_frame + f->offKeepF);
+            int* hNewMeas = reinterpret_cast<int*>(f->h_frame + f->offNewMeasF);
+            int* hMap = reinterpret_cast<int*>(f->h_frame + f->offMapF);
+            int* hNewIds = reinterpret_cast<int*>(f->h_frame + f->offNewIdsF);
+            int* hCounts = reinterpret_cast<int*>(f->h_frame + f->offCounts);
+            // new state = kept landmarks in their order, then the new ids in measurement (ascending id) order; its rows follow
+            int p = 0, rows = 0;
+            for (int i = 0; i < N; ++i) {
+                hKeep[i] = P.keep[i] ? 1 : 0;
+                if (!P.keep[i]) continue;
+                hMap[p] = i;
+                plan.nids.push_back(f->ids[i]);
+                if (P.measIdx[i] >= 0) {
+                    hLmOf[rows] = p;
+                    hYIdx[rows] = P.measIdx[i];
+                    ++rows;
+                }
+                ++p;
+            }
+            std::vector<char> inState(n, 0);
+            for (int i = 0; i < N; ++i)
+                if (P.measIdx[i] >= 0) inState[P.measIdx[i]] = 1;
+            int k = 0;
+            for (int j = 0; j < n; ++j)
+                if (!inState[j]) {
+                    hNewMeas[k] = j;
+                    hNewIds[k] = ids[j];
+                    hMap[p] = -1 - k;
+                    plan.nids.push_back(ids[j]);
+                    hLmOf[rows] = p;
+                    hYIdx[rows] = j;
+                    ++rows;
+                    ++p;
+                    ++k;
+                }
+            hCounts[0] = k;
+            plan.Nnew = p;
+            plan.nNew = k;
+            matchedNew = rows;
+            P.specNewCount = k;
+            f->h_lmOfSorted.assign(hLmOf, hLmOf + rows);
+        }
+        const int Nout = change ? plan.Nnew : N;
+        const int nm = change ? matchedNew : n;
         P.speculated = true;
         P.gated = true;
         P.measKept.assign(n, 1);
         P.h_gate = reinterpret_cast<double*>(f->h_out);
         P.h_spec = reinterpret_cast<int*>(f->h_out + f->outOffSpec);
         P.h_status = reinterpret_cast<int*>(f->h_out + f->outOffStatus);
-        P.nStatus = 1 + N;
+        P.nStatus = 1 + Nout;
         stage_mark(f, 0);
         // kernel arguments derived from the row -> landmark map are baked into a captured graph: replay only when that map
-        // is the identity (every state landmark measured)
-        const bool graphOk = f->useGraph && !f->profiling && matched == N;
+        // is the identity (every landmark of the updated state measured)
+        const bool graphOk = f->useGraph && !f->profiling && nm == Nout;
         if (!graphOk) {
-            if ((rc = enqueue_steady_update(f, N, n)) != EQVIO_OK) return rc;
+            if ((rc = enqueue_steady_update(f, N, nm, change ? &plan : nullptr)) != EQVIO_OK) return rc;
             stage_mark(f, 3);
         } else {
             const eqvio_settings& st = f->st;
             std::vector<int> key = {N, n, f->cur, f->lmcur, f->xcur, f->chunkLm, st.coordinateChoice, st.useDiscreteVelocityLift,
-                                    st.useDiscreteInnovationLift, st.useEquivariantOutput, f->maxSteps, f->yCap};
+                                    st.useDiscreteInnovationLift, st.useEquivariantOutput, f->maxSteps, f->yCap,
+                                    change ? 1 : 0, Nout, plan.nNew > 0 ? 1 : 0};
             auto it = f->graphs.find(key);
             if (it == f->graphs.end()) {
                 if (f->graphs.size() >= 32) {  // evict the least recently used
@@ -981,8 +1078,10 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
                 const long long launches0 = f->launches;
                 cudaGraph_t graph = nullptr;
                 CUDA_TRY(f, cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal));
-                rc = enqueue_steady_update(f, N, n);
+                std::vector<int> ids0 = f->ids;  // a captured landmark-set change assigns f->ids: the replay below does it for real
+                rc = enqueue_steady_update(f, N, nm, change ? &plan : nullptr);
                 cudaError_t ce = cudaStreamEndCapture(f->stream, &graph);
+                f->ids.swap(ids0);
                 eqvio_filter::GraphEntry ge;
                 ge.cur2 = f->cur;
                 ge.lmcur2 = f->lmcur;
@@ -1014,6 +1113,7 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
             f->xcur = it->second.xcur2;
             f->launches += it->second.launches;
             ++f->graphLaunches;
+            if (change) f->ids = plan.nids;
         }
         P.corrected = true;
         return EQVIO_OK;
@@ -1137,7 +1237,7 @@ int vision_phase_b(eqvio_filter* f) {
         if ((rc = upload(f, f->d_newMeas, newMeas.data(), newMeas.size())) != EQVIO_OK) return rc;
         launch_pdl(f, new_landmark_kernel, dim3(1), dim3(256), (size_t)0, f->stream, (const double*)f->d_gate, (const int*)f->d_keepI, N,
                    s.useMedianDepth ? 1 : 0, s.initialSceneDepth, (const FrameHeader*)f->d_hdr, (const double*)f->d_y, (const int*)f->d_newMeas,
-                   (int)newMeas.size(), f->d_newP);
+                   (int)newMeas.size(), (const int*)nullptr, f->d_newP);
         LAUNCH_CHECK(f, "new_landmark_kernel");
         if ((rc = remove_and_append(f, keep, addIds, addP, s.initialPointVariance, -1.0, true)) != EQVIO_OK) return rc;
         stage_mark(f, 2);
@@ -1219,8 +1319,8 @@ int launch_correction(eqvio_filter* f, const int* guard) {
 
 // performVisionUpdate (VIO_eqf.cpp:105-135) in the symmetric form, for the nm measured landmarks whose pixels are
 // in d_y and state indices in d_lmOf.  Every kernel returns at once when *guard != 0.
-// fusedSteady: the gate launch carries the measurement rows (gate_meas_kernel) and the lift also emits the state estimate.
-int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fusedSteady) {
+// fuseGate: the gate launch carries the measurement rows (gate_meas_kernel); fuseEst: the lift also emits the state estimate.
+int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate, bool fuseEst) {
     auto& P = f->pend;
     (void)P;
     const eqvio_settings& s = f->st;
@@ -1242,7 +1342,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fusedStea
         double* gout = f->d_Gamma2;
         const int nchunksAll = cdiv(nm, std::max(1, std::min(f->chunkLm, CH_R / 2)));
         // also clears the status words and Gamma (no memset nodes between the kernels of the update)
-        if (fusedSteady) {
+        if (fuseGate) {
             // one launch: gate CTAs (per state landmark) | measurement-row CTAs (per measured landmark); the rows are built
             // whatever the gate says -- d_spec + 1 is a constant 0
             const int gb = cdiv(Nn, 128), mb = cdiv(nm, 128);
@@ -1512,7 +1612,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fusedStea
     }
     launch_pdl(f, lift_kernel, dim3(cdiv(std::max(Nn, 1), 128)), dim3(128), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, Nn, f->d_xi0s, f->d_Xs[f->xcur], gammaFinal,
                                                                    s.useDiscreteInnovationLift ? 1 : 0, s.coordinateChoice,
-                                                                   f->d_status, f->d_status + 1, guard, fusedSteady ? f->d_out : (double*)nullptr,
+                                                                   f->d_status, f->d_status + 1, guard, fuseEst ? f->d_out : (double*)nullptr,
                                                                    s.coordinateChoice == EQVIO_COORD_NORMAL ? (const double*)(f->d_normalM + 441) : (const double*)nullptr, TL_SLOT(f));
     LAUNCH_CHECK(f, "lift_kernel");
     return EQVIO_OK;

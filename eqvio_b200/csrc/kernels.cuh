@@ -728,8 +728,10 @@ __global__ void gate_kernel(const double* __restrict__ lm, int cap, int N, const
 // ------------------------------------------------------------------------------------------------
 __global__ void new_landmark_kernel(const double* __restrict__ gate, const int* __restrict__ keep, int N, int useMedian, double initialDepth,
                                     const FrameHeader* __restrict__ fr, const double* __restrict__ y, const int* __restrict__ newMeas,
-                                    int nNew, double* __restrict__ newP) {
+                                    int nNew, const int* __restrict__ nNewPtr /* overrides nNew (count kept in the frame block, so that a
+                                    replayed graph does not bake it in) */, double* __restrict__ newP) {
     pdl_wait();
+    if (nNewPtr) nNew = *nNewPtr;
     __shared__ double sDepth;
     __shared__ int sCount;
     if (threadIdx.x == 0) {
