@@ -21,6 +21,8 @@ What is timed (CUDA events, after W warm-up steps, L2 flushed between steps outs
          K further frames of the same stream, L2 flushed between frames outside the bracket.
          e2e.python_driver is the same loop driven through the ctypes mirror (CUDA events around each
          synchronised step); with several sequences per GPU only that driver runs.
+         e2e.real_data_flow: K more frames through the C++ loop WITHOUT augmentLandmarkStates (how
+         eqvio_opt drives the filter on real data: ids are lost / added inside processVisionData).
 Multi-GPU (torchrun, one rank per GPU): independent sequences (seed = rank), no collective on the
 data path; one NCCL all-gather of the trajectories at the end (timed into e2e).  scaling = weak.
 
@@ -68,7 +70,7 @@ def settings_dict(coord):
 
 
 def workload_name(N, coord):
-    return (f"VIOSimulator wave, N={N} landmarks, fp64 Sigma (dim {21 + 3 * N}), {'Euclidean' if coord == 0 else 'InvDepth'} chart, "
+    return (f"VIOSimulator wave, N={N} landmarks, fp64 Sigma (dim {21 + 3 * N}), {('Euclidean', 'InvDepth', 'Normal')[coord]} chart, "
             "fastRiccati, 10 IMU samples per update")
 
 
@@ -224,7 +226,8 @@ def run_b200(args, rank, local_rank, world):
 
     N, K, W, P, R = args.landmarks, args.steps, args.warmup, args.profile_steps, args.sequences_per_gpu
     skw = settings_dict(args.coord)
-    total_frames = 1 + W + 2 * K + P  # warm-up | timed (Python driver) | timed again (C++ host loop) | per-kernel profile
+    K3 = K if 1 + W + 3 * K + P <= 399 else 0  # third pass (real-data flow) only when the 20 s lap has frames left
+    total_frames = 1 + W + 2 * K + K3 + P  # warm-up | timed (Python driver) | C++ host loop | C++ loop, real-data flow | per-kernel profile
     if total_frames > 399:
         raise SystemExit("bench.py: warmup + steps exceeds the 20 s simulated lap (399 updates)")
     # weak scaling: every rank owns R independent sequences (instance id = seed), contiguous blocks of ids
@@ -340,14 +343,26 @@ def run_b200(args, rank, local_rank, world):
     # frame (every frame ends synchronised with its estimate on the host), L2 flushed between frames outside the bracket.
     # Stage-event recording is off here (it is instrumentation for `value`).
     cpp_ms = 0.0
+    real_ms = 0.0
     if len(filters) == 1:
         filters[0].enableStageTiming(False)
         fms, est_s = filters[0].replay(streams[0].frames[1 + W + K:1 + W + 2 * K], cam, flushBytes=0 if args.no_l2_flush else 256 << 20)
-        filters[0].enableStageTiming(True)
         assert np.isfinite(est_s).all()
         cpp_ms = float(fms.sum())
         if dist:
             cpp_ms += g0.elapsed_time(g1)  # the one collective of the path counts into e2e
+        if K3:
+            # the same loop WITHOUT augmentLandmarkStates, as eqvio_opt drives the filter on real data: lost ids are pruned and
+            # new ids added inside processVisionData (planned frames)
+            class _NoAug:
+                def __init__(self, fr):
+                    self.stamp, self.imu, self.ids, self.y, self.provided_p = fr.stamp, fr.imu, fr.ids, fr.y, None
+
+            fms3, est3 = filters[0].replay([_NoAug(fr) for fr in streams[0].frames[1 + W + 2 * K:1 + W + 2 * K + K3]], cam,
+                                           flushBytes=0 if args.no_l2_flush else 256 << 20)
+            assert np.isfinite(est3).all()
+            real_ms = float(fms3.sum())
+        filters[0].enableStageTiming(True)
     if dist:
         dist.barrier()
 
@@ -358,7 +373,7 @@ def run_b200(args, rank, local_rank, world):
     flt.kernelProfile(reset=True)
     prof_stage = dict(propagation=0.0, preprocessing=0.0, correction=0.0)
     nprof = 0
-    for k in range(1 + W + 2 * K, 1 + W + 2 * K + P):
+    for k in range(1 + W + 2 * K + K3, 1 + W + 2 * K + K3 + P):
         if flush_buf is not None:
             flush_buf.fill_(1)
             torch.cuda.synchronize()
@@ -371,10 +386,10 @@ def run_b200(args, rank, local_rank, world):
     n_meas = len(streams[0].frames[1 + W].ids)
     n_state = flt.numLandmarks()
 
-    t = torch.tensor([dev_ms, e2e_ms, cpp_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_ms, cpp_ms, real_ms], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max, cpp_ms_max = float(t[0]), float(t[1]), float(t[2])
+    dev_ms_max, e2e_ms_max, cpp_ms_max, real_ms_max = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     if rank == 0:
         peaks = {}
@@ -464,6 +479,9 @@ def run_b200(args, rank, local_rank, world):
                              ms_per_step=(cpp_ms_max if cpp_ms_max > 0 else e2e_ms_max) / K,
                              driver="C++ host loop over the C ABI (eqvio_replay), host wall clock per synchronised frame" if cpp_ms_max > 0
                              else "Python ctypes driver, CUDA events around each synchronised step",
+                             real_data_flow=(dict(value=world * R * K3 / (real_ms_max * 1e-3), ms_per_step=real_ms_max / K3,
+                                                  note="same C++ loop without augmentLandmarkStates: ids lost / added inside "
+                                                  "processVisionData (eqvio_opt's flow)") if real_ms_max > 0 else None),
                              python_driver=dict(value=e2e_py, ms_per_step=e2e_ms_max / K, host_ms_per_step=1000.0 * wall_in / K,
                                                 timing="CUDA events around each synchronised step")),
                     gpu_launches=int(launches), launches_per_step=launches / K,

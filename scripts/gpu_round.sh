@@ -8,6 +8,9 @@ python -c "import __graft_entry__ as g; g.smoke()" > $O/final_smoke.txt 2>&1
 for n in 256 64 1024; do
   timeout 600 python bench.py --landmarks $n > $O/final_bench_n$n.json 2> $O/final_bench_n$n.err
 done
+for c in 1 2; do timeout 600 python bench.py --landmarks 256 --coord $c --no-cpu-baseline > $O/final_bench_n256_coord$c.json 2> $O/final_bench_n256_coord$c.err; done
+python scripts/nonsteady_profile.py 256 60 > $O/final_nonsteady.txt 2>&1; python scripts/nonsteady_profile.py 64 60 >> $O/final_nonsteady.txt 2>&1
+python scripts/host_profile.py 256 2>&1 | head -3 > $O/final_host_profile.txt
 timeout 600 python bench.py --impl reference --steps 10 --warmup 2 > $O/final_bench_reference_n256.json 2> $O/final_bench_reference.err
 timeout 300 python bench.py --landmarks 256 --sequences-per-gpu 8 --no-cpu-baseline > $O/final_bench_n256_r8.json 2>/dev/null
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/final_launches_n256.csv \
