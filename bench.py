@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--no-lookahead", action="store_true", help="one in-order downdate launch per chunk (no band / rest split)")
     ap.add_argument("--downdate", default="f64", choices=["f64", "tc"],
                     help="f64: DMMA fp64 downdate (default); tc: tcgen05 split-bf16 operands, fp32 accumulate in TMEM (BASELINE configs[2])")
+    ap.add_argument("--device-sim", action="store_true", help="generate the input streams with the device VIOSimulator (eqvio_b200.simulator)")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="updates in the cpu_baseline sample (0 = auto)")
@@ -233,7 +234,14 @@ def run_b200(args, rank, local_rank, world):
     # weak scaling: every rank owns R independent sequences (instance id = seed), contiguous blocks of ids
     total_instances = R * world
     mine = shard_instances(total_instances, world, rank)
-    streams = [record_stream(SimConfig.benchmark(N, inst), total_frames) for inst in mine]
+    if args.device_sim:  # IMU / vision streams of all local instances from one device launch
+        from eqvio_b200.simulator import DeviceSimulator
+
+        dsim = DeviceSimulator([SimConfig.benchmark(N, inst) for inst in mine], device=local_rank)
+        streams = dsim.record_streams(total_frames)
+        dsim.close()
+    else:
+        streams = [record_stream(SimConfig.benchmark(N, inst), total_frames) for inst in mine]
     st = eb.Settings(**skw)
     filters = []
     for sm in streams:
