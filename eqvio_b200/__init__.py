@@ -8,7 +8,7 @@ and raises ImportError when it has not been built -- there is no CPU fallback.
 from ._capi import EqvioError, LIB_PATH  # noqa: F401
 from .filter import (  # noqa: F401
     COORD_EUCLIDEAN, COORD_INVDEPTH, COORD_NORMAL, Camera, EqFState, IMUVelocity, Settings, VIOFilter, VIOSensorState,
-    VIOState, VisionMeasurement, batchProcessVision)
+    VIOState, VisionMeasurement, batchProcessVision, replayBatch)
 from .writer import VIOWriter, trajectory_errors  # noqa: F401
 
 

@@ -95,6 +95,7 @@ SIGNATURES = {
     "eqvio_get_launch_count": (C.c_longlong, [_H]),
     "eqvio_enable_kernel_profile": (_I, [_H, _I]),
     "eqvio_get_kernel_profile": (_I, [_H, _I, _PD, C.POINTER(C.c_longlong)]),
+    "eqvio_replay_batch": (_I, [C.c_void_p, _I, _I, C.c_void_p, C.c_void_p, _PD, _PD, _PD]),
     "eqvio_replay": (_I, [_H, _I, C.c_void_p, C.c_void_p, C.c_size_t, _PD, _PD]),
     "eqvio_get_host_profile": (_I, [_H, _I, _PD, C.POINTER(C.c_longlong)]),
     "eqvio_set_tuning": (_I, [_H, _I, _I]),

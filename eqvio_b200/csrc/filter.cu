@@ -14,6 +14,7 @@
 #include <map>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -2262,6 +2263,24 @@ int eqvio_replay(eqvio_filter* f, int count, const eqvio_replay_frame* frames, c
     }
     if (scratch) cudaFree(scratch);
     return rc;
+}
+
+int eqvio_replay_batch(eqvio_filter* const* fs, int count, int n_frames, const eqvio_replay_frame* const* frames, const eqvio_camera* cam,
+                       double* frame_ms, double* est_sensor, double* wall_ms) {
+    if (!fs || count < 0 || n_frames < 0 || (count > 0 && !frames) || !cam) return EQVIO_ERR_INVALID_ARG;
+    std::vector<int> rc(count, EQVIO_OK);
+    std::vector<std::thread> th;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int k = 0; k < count; ++k)
+        th.emplace_back([&, k] {
+            rc[k] = eqvio_replay(fs[k], n_frames, frames[k], cam, 0, frame_ms ? frame_ms + (size_t)k * n_frames : nullptr,
+                                 est_sensor ? est_sensor + (size_t)k * n_frames * 23 : nullptr);
+        });
+    for (auto& t : th) t.join();
+    if (wall_ms) *wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (int k = 0; k < count; ++k)
+        if (rc[k] != EQVIO_OK) return rc[k];
+    return EQVIO_OK;
 }
 
 int eqvio_batch_process_vision(eqvio_filter* const* fs, int count, const double* stamps, const int* n, const int* const* ids,

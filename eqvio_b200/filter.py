@@ -403,6 +403,25 @@ class VIOFilter:
                                      _pd(ms), _pd(est)))
         return ms[:n], est[:n]
 
+    @staticmethod
+    def _replay_frames(frames, keep):
+        n = len(frames)
+        arr = (ReplayFrame * n)()
+        for k, fr in enumerate(frames):
+            imu = np.ascontiguousarray(fr.imu, dtype=np.float64).reshape(-1, 13)
+            ids = _i32(fr.ids)
+            y = _f64(fr.y, 2 * len(ids))
+            pp = None if getattr(fr, "provided_p", None) is None else _f64(fr.provided_p, 3 * len(ids))
+            keep += [imu, ids, y, pp]
+            arr[k].stamp = float(fr.stamp)
+            arr[k].n_imu = imu.shape[0]
+            arr[k].imu_rows = imu.ctypes.data
+            arr[k].n = len(ids)
+            arr[k].ids = ids.ctypes.data
+            arr[k].y = y.ctypes.data
+            arr[k].provided_p = None if pp is None else pp.ctypes.data
+        return arr
+
     def hostProfile(self, reset=True):
         """Host-side microseconds per processVisionData call since the last reset (eqvio_get_host_profile)."""
         us = np.zeros(4)
@@ -422,6 +441,26 @@ class VIOFilter:
         ln = np.zeros(_capi.PROF_CLASSES, dtype=np.int64)
         self._check(lib.eqvio_get_kernel_profile(self._h, int(reset), _pd(ms), ln.ctypes.data_as(C.POINTER(C.c_longlong))))
         return {name: dict(ms=float(ms[i]), launches=int(ln[i])) for i, name in enumerate(_capi.PROF_NAMES)}
+
+
+def replayBatch(filters, frames_per_filter, camera: Camera):
+    """eqvio_replay_batch: one C++ host thread per filter, each replaying its own frames through the C ABI.
+    Returns (frame_ms (R, K), est_sensor (R, K, 23), wall_ms)."""
+    R = len(filters)
+    K = len(frames_per_filter[0])
+    keep = []
+    arrs = [VIOFilter._replay_frames(fr, keep) for fr in frames_per_filter]
+    ptrs = (C.c_void_p * R)(*[C.cast(a, C.c_void_p) for a in arrs])
+    hs = (C.c_void_p * R)(*[C.cast(f._h, C.c_void_p) for f in filters])
+    ms = np.zeros((R, max(K, 1)))
+    est = np.zeros((R, max(K, 1), 23))
+    wall = C.c_double(0.0)
+    rc = lib.eqvio_replay_batch(C.cast(hs, C.c_void_p), R, K, C.cast(ptrs, C.c_void_p), C.cast(C.pointer(camera.pod), C.c_void_p), _pd(ms),
+                                _pd(est), C.byref(wall))
+    if rc != 0:
+        for f in filters:
+            f._check(rc)
+    return ms[:, :K], est[:, :K], wall.value
 
 
 def batchProcessVision(filters, stamps, ids_list, y_list, camera: Camera):

@@ -141,6 +141,12 @@ typedef struct eqvio_replay_frame {
 } eqvio_replay_frame;
 int eqvio_replay(eqvio_filter* f, int count, const eqvio_replay_frame* frames, const eqvio_camera* cam, size_t flush_bytes,
                  double* frame_ms, double* est_sensor);
+/* eqvio_replay for `count` independent filters at once, one host thread per filter (Monte-Carlo replicas: their kernels overlap
+ * on the GPU through the filters' own streams, their host-side planning on the cores).  frames[k] points to n_frames frames of
+ * filter k; frame_ms / est_sensor as in eqvio_replay with filter k's block at offset k * n_frames (may be NULL);
+ * wall_ms (may be NULL) = wall time of the whole batch.  Returns the first error. */
+int eqvio_replay_batch(eqvio_filter* const* fs, int count, int n_frames, const eqvio_replay_frame* const* frames, const eqvio_camera* cam,
+                       double* frame_ms, double* est_sensor, double* wall_ms);
 /* Same update for `count` independent filters at once (Monte-Carlo replicas on one GPU):
  * kernels of different filters overlap on their streams.  Arrays are indexed per filter. */
 int eqvio_batch_process_vision(eqvio_filter* const* fs, int count, const double* stamps, const int* n,

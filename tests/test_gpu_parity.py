@@ -511,6 +511,40 @@ def test_writer_consistency_files(tmp_path):
     g.close()
 
 
+def test_replay_batch_matches_single_replay():
+    """eqvio_replay_batch (one C++ host thread per filter, kernels of the replicas overlapping on the GPU) gives every filter
+    exactly the estimates of its own eqvio_replay -- and those match the Python-driven calls."""
+    import eqvio_b200 as eb
+    from simdata import SimConfig, record_stream
+
+    R, K = 4, 10
+    streams = [record_stream(SimConfig.benchmark(40, seed), K) for seed in range(R)]
+    cam = eb.Camera(**streams[0].camera)
+
+    def make(sm):
+        return eb.VIOFilter(eb.Settings(fastRiccati=1), eb.VIOState(eb.VIOSensorState.fromFlat(sm.init_sensor), sm.init_p, sm.init_ids), 0.0,
+                            capacity=48)
+
+    batch = [make(sm) for sm in streams]
+    _, est_b, wall = eb.replayBatch(batch, [sm.frames for sm in streams], cam)
+    assert wall > 0
+    for k, sm in enumerate(streams):
+        single = make(sm)
+        _, est_s = single.replay(sm.frames, cam)
+        assert np.array_equal(est_b[k], est_s)
+        py = make(sm)
+        for fr in sm.frames:
+            py.processIMUArray(fr.imu)
+            py.augmentLandmarkStates(fr.ids, eb.VIOState(eb.VIOSensorState(), fr.provided_p, fr.ids))
+            py.processVisionArrays(fr.stamp, fr.ids, fr.y, cam)
+        assert np.array_equal(py.stateEstimate().sensor.flat(), est_s[-1])
+        assert np.array_equal(batch[k].stateEstimate().p, py.stateEstimate().p)
+        for f_ in (single, py):
+            f_.close()
+    for f_ in batch:
+        f_.close()
+
+
 def test_tcgen05_probe():
     """Stand-alone tcgen05 / TMEM / UMMA-descriptor probe (tests/csrc/tc_probe.cu): 128x128x64 bf16 GEMM, exact vs CPU."""
     import os
