@@ -189,7 +189,8 @@ def run_reference(args, rank, world):
 
     N = args.landmarks
     skw = settings_dict(args.coord)
-    stream = record_stream(SimConfig.benchmark(N, 0), 1 + args.warmup + args.steps)
+    frames = 1 + args.warmup + args.steps
+    stream = record_stream(SimConfig.benchmark(N, 0, duration=20.0 if frames <= 399 else float((frames + 1) // 20 + 2)), frames)
     ups, stages, done = time_cpu(stream, skw, args.warmup, args.steps)
     cores = blas_threads()
     sample = f"{done} consecutive updates of the same stream after {args.warmup} warm-up updates"
@@ -229,19 +230,19 @@ def run_b200(args, rank, local_rank, world):
     skw = settings_dict(args.coord)
     K3 = K if 1 + W + 3 * K + P <= 399 else 0  # third pass (real-data flow) only when the 20 s lap has frames left
     total_frames = 1 + W + 2 * K + K3 + P  # warm-up | timed (Python driver) | C++ host loop | C++ loop, real-data flow | per-kernel profile
-    if total_frames > 399:
-        raise SystemExit("bench.py: warmup + steps exceeds the 20 s simulated lap (399 updates)")
+    # the reference's simulated lap is 20 s (399 updates after the t = 0 image); longer runs keep circling the same trajectory
+    duration = 20.0 if total_frames <= 399 else float((total_frames + 1) // 20 + 2)
     # weak scaling: every rank owns R independent sequences (instance id = seed), contiguous blocks of ids
     total_instances = R * world
     mine = shard_instances(total_instances, world, rank)
     if args.device_sim:  # IMU / vision streams of all local instances from one device launch
         from eqvio_b200.simulator import DeviceSimulator
 
-        dsim = DeviceSimulator([SimConfig.benchmark(N, inst) for inst in mine], device=local_rank)
+        dsim = DeviceSimulator([SimConfig.benchmark(N, inst, duration=duration) for inst in mine], device=local_rank)
         streams = dsim.record_streams(total_frames)
         dsim.close()
     else:
-        streams = [record_stream(SimConfig.benchmark(N, inst), total_frames) for inst in mine]
+        streams = [record_stream(SimConfig.benchmark(N, inst, duration=duration), total_frames) for inst in mine]
     st = eb.Settings(**skw)
     filters = []
     for sm in streams:
