@@ -148,13 +148,16 @@ def oracle_stream(stream, settings_kw):
     return st, cam, init
 
 
-def time_cpu(stream, settings_kw, warmup, steps):
-    """The reference's dense evaluation order on the host cores: returns (updates/s, per-stage seconds)."""
+def time_cpu(stream, settings_kw, warmup, steps, structured=False):
+    """The reference's dense evaluation order on the host cores: returns (updates/s, per-stage seconds).
+    structured=True times the minimal-flop CPU formulation instead (sparse A and C, one Cholesky of S, Sigma -= Y^T Y),
+    so that the GPU speed-up is not credited with purely algorithmic gains."""
     from oracle import eqf
 
     st, cam, init = oracle_stream(stream, settings_kw)
     flt = eqf.VIOFilter(st, init, 0.0)
-    flt.filterState.mirrorLazyEvaluation = True
+    flt.filterState.mirrorLazyEvaluation = not structured
+    flt.filterState.structuredEvaluation = structured
     t_total = 0.0
     done = 0
     for k, fr in enumerate(stream.frames[: 1 + warmup + steps]):
@@ -171,6 +174,27 @@ def time_cpu(stream, settings_kw, warmup, steps):
             t_total += time.perf_counter() - t0
             done += 1
     return done / t_total, dict(flt.timing), done
+
+
+def cpu_variants(stream, settings_kw, warmup, dense_ups):
+    """Side figures of cpu_baseline: the dense reference order on ONE thread (the reference build never enables OpenMP,
+    so its Eigen GEMMs are single-core) and the structured + Cholesky formulation on all threads.  Bounded samples."""
+    out = {}
+    n1 = int(max(2, min(10, 4.0 * dense_ups / 8.0)))  # ~4 s assuming 1 thread is <= 8x slower
+    try:
+        from threadpoolctl import threadpool_limits
+
+        with threadpool_limits(limits=1):
+            ups1, _, d1 = time_cpu(stream, settings_kw, 1, n1)
+        out["single_thread"] = dict(value=ups1, cores=1, sample=f"{d1} updates, dense reference order")
+    except Exception as e:  # threadpoolctl missing: say so instead of guessing
+        out["single_thread"] = dict(value=None, note=repr(e))
+    ns = int(max(3, min(40, 4.0 * dense_ups * 5.0)))
+    ups_s, st_s, ds = time_cpu(stream, settings_kw, warmup, ns, structured=True)
+    out["structured_cholesky"] = dict(value=ups_s, cores=blas_threads(), sample=f"{ds} updates; sparse A / C, one Cholesky of S, "
+                                      "Sigma -= Y^T Y (F_alg of SURVEY 8d; scipy.sparse + LAPACK), same results to 1e-11",
+                                      stage_ms={k: 1000.0 * v / ds for k, v in st_s.items()})
+    return out
 
 
 def blas_threads():
@@ -194,6 +218,7 @@ def run_reference(args, rank, world):
     ups, stages, done = time_cpu(stream, skw, args.warmup, args.steps)
     cores = blas_threads()
     sample = f"{done} consecutive updates of the same stream after {args.warmup} warm-up updates"
+    variants = cpu_variants(stream, skw, min(args.warmup, 2), ups)
     line = dict(impl="reference", metric="vision-updates/sec", value=ups, unit="updates/s", n_gpus=args.gpus, steps=done,
                 warmup=args.warmup, ms_per_step=1000.0 / ups, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f64", data="synthetic",
@@ -201,7 +226,7 @@ def run_reference(args, rank, world):
                             "(numpy fp64 + OpenBLAS, reference evaluation order incl. doubly evaluated gain); the reference "
                             "itself cannot be built here (Eigen3/OpenCV/yaml-cpp absent)"),
                 cpu_baseline=dict(value=ups, unit="updates/s", cores=cores, kind="port", sample=sample,
-                                  stage_ms={k: 1000.0 * v / done for k, v in stages.items()}),
+                                  stage_ms={k: 1000.0 * v / done for k, v in stages.items()}, **variants),
                 e2e=dict(value=ups, unit="updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
@@ -523,6 +548,7 @@ def run_b200(args, rank, local_rank, world):
                                         "updates; oracle port of the dense Eigen path in the reference's evaluation order "
                                         "(numpy + OpenBLAS; includes ~20 ms/update of Python overhead)",
                                         stage_ms={k_: 1000.0 * v / done for k_, v in stages.items()})
+            line["cpu_baseline"].update(cpu_variants(streams[0], skw, min(W, 2), ups))
         print(json.dumps(line), flush=True)
     for f in filters:
         f.close()

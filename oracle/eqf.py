@@ -1072,6 +1072,9 @@ class VIO_eqf:
         # Eigen expressions (VIO_eqf.cpp:116-131); results are identical, only
         # the cost changes.  Used by the CPU-baseline timing.
         self.mirrorLazyEvaluation = False
+        # when True, propagation keeps A sparse and the correction uses sparse C + one Cholesky of S (minimal-flop
+        # symmetric form, F_alg of SURVEY 8d).  Same result to rounding; the "algorithmic" CPU baseline of bench.py.
+        self.structuredEvaluation = False
 
     def stateEstimate(self):  # :137
         return stateGroupAction(self.X, self.xi0)
@@ -1086,6 +1089,24 @@ class VIO_eqf:
     def integrateRiccatiStateFast(self, imuVelocity, dt, inputGainMatrix, stateGainMatrix):  # :62-72
         A0t = self.coordinateSuite.stateMatrixA(self.X, self.xi0, imuVelocity)
         Bt = self.coordinateSuite.inputMatrixB(self.X, self.xi0)
+        if self.structuredEvaluation:
+            # CPU algorithmic baseline (bench.py): the same step using the block structure of A: 21 dense
+            # sensor columns + one 3x3 diagonal block per landmark -- O(dim^2) instead of two dense GEMMs
+            N = self.xi0.N
+            dim = self.xi0.Dim()
+            As = A0t[:, :SENSOR_DIM]
+            ar = np.arange(N)
+            D = A0t[SENSOR_DIM:, SENSOR_DIM:].reshape(N, 3, N, 3)[ar, :, ar, :]  # (N, 3, 3) diagonal blocks
+            S0 = self.Sigma
+            FS = S0 + dt * (As @ S0[:SENSOR_DIM, :])
+            if N:
+                FS[SENSOR_DIM:, :] += np.matmul(dt * D, S0[SENSOR_DIM:, :].reshape(N, 3, dim)).reshape(3 * N, dim)
+            out = FS.T + dt * (As @ FS[:, :SENSOR_DIM].T)  # transposed result: (FS F^T)^T = F FS^T
+            if N:
+                out[SENSOR_DIM:, :] += np.matmul(dt * D, FS.T[SENSOR_DIM:, :].reshape(N, 3, dim)).reshape(3 * N, dim)
+                out = out.T
+            self.Sigma = out + dt * (Bt @ inputGainMatrix @ Bt.T + stateGainMatrix)
+            return
         A0tExp = np.eye(self.xi0.Dim()) + dt * A0t
         self.Sigma = A0tExp @ self.Sigma @ A0tExp.T + dt * (Bt @ inputGainMatrix @ Bt.T + stateGainMatrix)
 
@@ -1116,6 +1137,35 @@ class VIO_eqf:
         yTilde = (measurement - estimated).asVector()
         Ct = self.coordinateSuite.outputMatrixC(self.xi0, self.X, measurement, useEquivariantOutput)
         Sigma = self.Sigma
+        if self.structuredEvaluation:
+            # CPU algorithmic baseline (bench.py): sparse C, Cholesky of S, Sigma -= Y^T Y -- the minimal-flop symmetric form
+            # (F_alg of SURVEY 8d) instead of the reference's dense, doubly evaluated gain.  Same result to rounding.
+            import scipy.linalg as sl
+
+            N = self.xi0.N
+            dim = self.xi0.Dim()
+            m = Ct.shape[0]
+            n = m // 2
+            # one 2x3 block per row pair, at the column triple of its landmark (EqFMatrices.cpp:74-76)
+            C4 = Ct[:, SENSOR_DIM:].reshape(n, 2, N, 3)
+            lm = np.abs(C4).sum(axis=(1, 3)).argmax(axis=1)
+            Cb = C4[np.arange(n), :, lm, :]  # (n, 2, 3)
+            W = np.matmul(Cb, Sigma[SENSOR_DIM:, :].reshape(N, 3, dim)[lm]).reshape(m, dim)
+            Wl = W[:, SENSOR_DIM:].reshape(m, N, 3)[:, lm, :].transpose(1, 2, 0)  # (n, 3, m)
+            S = np.matmul(Cb, Wl).reshape(m, m).T + outputGainMatrix
+            L = np.linalg.cholesky(S)
+            Y = sl.solve_triangular(L, W, lower=True, check_finite=False)
+            z = sl.solve_triangular(L, yTilde, lower=True, check_finite=False)
+            Gamma = Y.T @ z
+            if discreteCorrection:
+                Delta = self.coordinateSuite.liftInnovationDiscrete(Gamma, self.xi0)
+            else:
+                Delta = VIOExp(self.coordinateSuite.liftInnovation(Gamma, self.xi0))
+            self.X = Delta * self.X
+            T = np.tril(sl.blas.dsyrk(1.0, Y, trans=1, lower=1))  # half the flops of Y^T Y
+            self.Sigma = Sigma - (T + np.tril(T, -1).T)
+            self.lastGamma = Gamma
+            return
 
         def SInv():
             return np.linalg.inv(Ct @ Sigma @ Ct.T + outputGainMatrix)

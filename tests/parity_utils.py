@@ -29,9 +29,10 @@ def snapshot_oracle(flt):
                 X_sensor=fs.X.sensorFlat(), Qq=fs.X.Qq.copy(), Qa=fs.X.Qa.copy(), time=flt.getTime())
 
 
-def run_oracle(stream, dense_lazy=False, on_update=None):
+def run_oracle(stream, dense_lazy=False, on_update=None, structured=False):
     flt = eqf.VIOFilter(stream["settings"], stream["init"], 0.0)
     flt.filterState.mirrorLazyEvaluation = dense_lazy
+    flt.filterState.structuredEvaluation = structured
     out = []
 
     def cb(k, f):

@@ -33,6 +33,17 @@ def test_dense_lazy_order_matches(name):
         assert e["ids_equal"] and e["sigma"] < TOL_ORACLE and e["state"] < TOL_ORACLE
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_structured_cholesky_order_matches(name):
+    """Second, independent evaluation order of the same update: sparse A in the propagation,
+    sparse C + one Cholesky of S + Sigma -= Y^T Y in the correction.  It is the "algorithmic" CPU baseline of bench.py."""
+    stream, outs = load(name)
+    got = run_oracle(stream, structured=True)
+    for g, r in zip(got, outs):
+        e = compare_states(g, r)
+        assert e["ids_equal"] and e["sigma"] < 1e-11 and e["state"] < 1e-11
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CASES)
 def test_cuda_matches_golden(name):
