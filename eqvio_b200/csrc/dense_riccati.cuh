@@ -111,8 +111,8 @@ __global__ void dense_fill_landmark_kernel(double* __restrict__ M, int n, int di
 // too (identical function values cancel).  Written into the top-left dim x dim block of R (n x n column-major).
 constexpr int DA_SENSOR_EVALS = 1 + 2 * SENSOR_DIM;  // 43
 __device__ __forceinline__ double num_diff_step() { return cbrt(2.220446049250313e-16); }
-__global__ void discrete_a_sensor_kernel(const double* __restrict__ xi0s, const double* __restrict__ Xs, const double* __restrict__ imuRow,
-                                         double* __restrict__ R, int n, SE3* __restrict__ ccOut) {
+__global__ void discrete_a_sensor_kernel(int coord, const double* __restrict__ xi0s, const double* __restrict__ Xs,
+                                         const double* __restrict__ imuRow, double* __restrict__ R, int n, SE3* __restrict__ ccOut) {
     __shared__ double e1[DA_SENSOR_EVALS][SENSOR_DIM];
     const int k = threadIdx.x;
     const double h = num_diff_step();
@@ -124,7 +124,7 @@ __global__ void discrete_a_sensor_kernel(const double* __restrict__ xi0s, const 
         if (k > 0) eps[(k - 1) / 2] = ((k - 1) & 1) ? -h : h;
         SE3 cc;
         double out[SENSOR_DIM];
-        a0_discrete_sensor(X, xi0, imuRow + 1, imuRow[0], eps, out, cc);
+        a0_discrete_sensor(coord, X, xi0, imuRow + 1, imuRow[0], eps, out, cc);
         for (int j = 0; j < SENSOR_DIM; ++j) e1[k][j] = out[j];
         ccOut[k] = cc;
     }

@@ -626,16 +626,8 @@ int plan_integration(eqvio_filter* f, double newTime, int* advanced) {
     *advanced = 0;
     if (newTime <= f->time || f->time < 0 || f->buf.empty()) return EQVIO_OK;
     const eqvio_settings& s = f->st;
-    if (!s.fastRiccati && s.useDiscreteStateMatrix && s.coordinateChoice == EQVIO_COORD_NORMAL) {
-        f->err = "useDiscreteStateMatrix in Normal coordinates has no CUDA path in this build";
-        return EQVIO_ERR_UNSUPPORTED;
-    }
-    if (!s.fastRiccati && s.useDiscreteStateMatrix && !s.useDiscreteVelocityLift) {
-        // the reference's stateMatrixADiscrete always differentiates liftVelocityDiscrete; the pairing with a continuous
-        // velocity lift in the observer is not a configuration its settings document, and it is not mapped here
-        f->err = "useDiscreteStateMatrix with useDiscreteVelocityLift = false has no CUDA path in this build";
-        return EQVIO_ERR_UNSUPPORTED;
-    }
+    // useDiscreteStateMatrix: stateMatrixADiscrete always differentiates liftVelocityDiscrete (EqFMatrices.cpp:24-41) whatever lift
+    // the observer itself uses (VIOFilter.cpp:177), and it does so in the chart of the selected coordinate suite.
     const int n = (int)f->buf.size();
     if (n > f->maxSteps) {
         CUDA_TRY(f, cudaStreamSynchronize(f->stream));
@@ -822,7 +814,7 @@ int enqueue_propagation_accurate(eqvio_filter* f) {
                 dense::dense_lincomb_kernel<<<cdiv((size_t)n * n, 256), 256, 0, f->stream>>>(R, n, 1.0, M, 0.0, nullptr, 0.0, nullptr, 1.0);
                 LAUNCH_CHECK(f, "dense_lincomb_kernel");
             } else if (discreteA) {
-                dense::discrete_a_sensor_kernel<<<1, 64, 0, f->stream>>>(f->d_xi0s, f->d_Xs[f->xcur], f->d_imu + (size_t)13 * i, R, n, w.cc);
+                dense::discrete_a_sensor_kernel<<<1, 64, 0, f->stream>>>(s.coordinateChoice, f->d_xi0s, f->d_Xs[f->xcur], f->d_imu + (size_t)13 * i, R, n, w.cc);
                 LAUNCH_CHECK(f, "discrete_a_sensor_kernel");
                 if (N > 0) {
                     dense::discrete_a_landmark_kernel<<<N, 64, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, s.coordinateChoice,
@@ -2639,6 +2631,9 @@ const char* eqvio_debug_timeline_name(eqvio_filter* f, int slot) {
 #ifdef EQVIO_CHUNK_TIMING
 int eqvio_debug_chunk_timing(long long out[16]) {
     return cudaMemcpyFromSymbol(out, g_chunk_t, sizeof(long long) * 16) == cudaSuccess ? 0 : -2;
+}
+int eqvio_debug_chunk_fine(long long out[128]) {
+    return cudaMemcpyFromSymbol(out, g_chunk_fine, sizeof(long long) * 128) == cudaSuccess ? 0 : -2;
 }
 #endif
 

@@ -1184,9 +1184,12 @@ __device__ __forceinline__ void tri_decode(int t, int& row, int& col) {
 }
 #ifdef EQVIO_CHUNK_TIMING
 __device__ long long g_chunk_t[16];
+__device__ long long g_chunk_fine[128];  // thread 0 of CTA 0: clock64 after every step of the S-group block-column loop
+#define CH_FINE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (i) < 128) g_chunk_fine[(i)] = clock64(); } while (0)
 #define CH_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == (i < 100 ? 0 : CH_S_THREADS)) g_chunk_t[(i) % 100] = clock64(); } while (0)
 #else
 #define CH_STAMP(i) do { } while (0)
+#define CH_FINE(i) do { } while (0)
 #endif
 // progress flag between the two warp groups of chunk_factor_kernel: release store / acquire load at CTA scope
 __device__ __forceinline__ void flag_release(int* p, int v) {
@@ -1329,6 +1332,7 @@ __global__ void __launch_bounds__(CH_THREADS)
         }
         CH_STAMP(2);
         for (int J = 0; J < nJ; ++J) {
+            CH_FINE(4 * J);
             if (owner && TI == J && TK == J) {
                 // 4x4 diagonal tile: fraction-free elimination (products only, 6 dependent operations) and then the
                 // four pivot reciprocals side by side -- the serial pivot -> reciprocal -> multiplier chain of the
@@ -1356,7 +1360,9 @@ __global__ void __launch_bounds__(CH_THREADS)
 #pragma unroll
                     for (int j = 0; j < CH_T; ++j) sm.Lp[J][i][j][J] = a[i][j];
             }
+            CH_FINE(4 * J + 1);
             s_group_barrier();
+            CH_FINE(4 * J + 2);
             if (owner && TK == J && TI > J) {
                 double c[CH_T], d[CH_T][CH_T];
 #pragma unroll
@@ -1377,6 +1383,7 @@ __global__ void __launch_bounds__(CH_THREADS)
                     for (int j = 0; j < CH_T; ++j) sm.Lp[J][r][j][TI] = a[r][j];
             }
             s_group_barrier();
+            CH_FINE(4 * J + 3);
             if (tid == 0) flag_release(&sm.ready, J + 1);  // the right-hand-side warps may consume block column J
             if (owner && TK > J) {
                 double li[CH_T][CH_T], pk[CH_T][CH_T];

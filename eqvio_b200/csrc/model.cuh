@@ -294,6 +294,10 @@ HD void sensor_chart_std(const SensorState& Xi, const SensorState& Xi0, double* 
     se3_log(se3_mul(se3_inv(Xi0.cam), Xi.cam), eps + 15);
 }
 HD V3 invdepth_chart_inv(V3 eps, V3 q0);
+HD V3 point_chart_normal(V3 p, V3 p0);
+HD V3 point_chart_normal_inv(V3 eps, V3 p0);
+HD void sensor_chart_normal(const SensorState& Xi, const SensorState& Xi0, double* eps);
+HD SensorState sensor_chart_normal_inv(const double* eps, const SensorState& Xi0);
 // sensorChart_std inverse (VIOState.cpp:114-121)
 HD SensorState sensor_chart_std_inv(const double* eps, const SensorState& Xi0) {
     SensorState Xi;
@@ -330,9 +334,9 @@ HD void lift_velocity_discrete_sensor(const SensorState& xh, const double* u, do
 // a0Discrete of stateMatrixADiscrete (EqFMatrices.cpp:27-37), sensor part: the chart coordinates eps1 of
 // (X LambdaTilde X^-1) . chart^-1(eps) for the sensor coordinates eps (21); also returns the camera-frame change of
 // Lambda(xi) that the landmark part of the same evaluation needs.
-HD void a0_discrete_sensor(const GroupSensor& X, const SensorState& xi0, const double* u, double dt, const double* eps, double* eps1,
-                           SE3& camChangeInv) {
-    const SensorState xe = sensor_chart_std_inv(eps, xi0);
+HD void a0_discrete_sensor(int coord, const GroupSensor& X, const SensorState& xi0, const double* u, double dt, const double* eps,
+                           double* eps1, SE3& camChangeInv) {
+    const SensorState xe = coord == COORD_NORMAL ? sensor_chart_normal_inv(eps, xi0) : sensor_chart_std_inv(eps, xi0);
     const SensorState xhat = sensor_group_action(X, xi0);
     const SensorState xi = sensor_group_action(X, xe);
     GroupSensor L1, L0;
@@ -340,12 +344,15 @@ HD void a0_discrete_sensor(const GroupSensor& X, const SensorState& xi0, const d
     lift_velocity_discrete_sensor(xi, u, dt, L1, camChangeInv);
     lift_velocity_discrete_sensor(xhat, u, dt, L0, cc0);
     const GroupSensor G = group_mul(group_mul(X, group_mul(L1, group_inverse(L0))), group_inverse(X));
-    sensor_chart_std(sensor_group_action(G, xe), xi0, eps1);
+    if (coord == COORD_NORMAL)
+        sensor_chart_normal(sensor_group_action(G, xe), xi0, eps1);
+    else
+        sensor_chart_std(sensor_group_action(G, xe), xi0, eps1);
 }
 // ... landmark part: eps (3) are the chart coordinates of landmark (p0; Q, a), cc1 / cc0 the camera-frame changes of
-// Lambda(xi) / Lambda(xi_hat).  Point chart: Euclidean or inverse depth.
+// Lambda(xi) / Lambda(xi_hat).  Point chart: Euclidean, inverse depth or normal.
 HD V3 a0_discrete_landmark(int coord, V3 p0, Quat Q, double a, V3 eps, const SE3& cc1, const SE3& cc0) {
-    const V3 pe = coord == COORD_INVDEPTH ? invdepth_chart_inv(eps, p0) : p0 + eps;
+    const V3 pe = coord == COORD_INVDEPTH ? invdepth_chart_inv(eps, p0) : (coord == COORD_NORMAL ? point_chart_normal_inv(eps, p0) : p0 + eps);
     const V3 p = landmark_action(Q, a, pe), phat = landmark_action(Q, a, p0);
     const V3 p1 = se3_apply(cc1, p), ph1 = se3_apply(cc0, phat);
     const Quat R1 = quat_from_two_vectors(normalized(p1), normalized(p)), R0 = quat_from_two_vectors(normalized(ph1), normalized(phat));
@@ -355,7 +362,7 @@ HD V3 a0_discrete_landmark(int coord, V3 p0, Quat Q, double a, V3 eps, const SE3
     const Quat Rg = qmul(qmul(Q, Rt), qinv(Q));  // X LambdaTilde X^-1
     const double ag = (a * at) * (1.0 / a);
     const V3 pe1 = landmark_action(Rg, ag, pe);
-    return coord == COORD_INVDEPTH ? invdepth_chart(pe1, p0) : pe1 - p0;
+    return coord == COORD_INVDEPTH ? invdepth_chart(pe1, p0) : (coord == COORD_NORMAL ? point_chart_normal(pe1, p0) : pe1 - p0);
 }
 // integrateSystemFunction, sensor part (VIOState.cpp:27-68): advances s by one IMU segment u = (gyr, acc, gyrBiasVel,
 // accBiasVel) of length dt and returns the camera-frame change applied to every landmark.

@@ -43,8 +43,8 @@ extern "C" {
 #define EQVIO_ERR_CUDA (-2)
 #define EQVIO_ERR_NUMERIC (-3)     /* NaN / non-SPD innovation covariance detected on device */
 #define EQVIO_ERR_CAPACITY (-4)    /* more landmarks than the handle was created for */
-#define EQVIO_ERR_UNSUPPORTED (-5) /* a Settings combination this build has no CUDA path for (useDiscreteStateMatrix with a
-                                      continuous velocity lift or in Normal coordinates, other camera models) */
+#define EQVIO_ERR_UNSUPPORTED (-5) /* something this build has no CUDA path for (an unknown coordinateChoice, a camera model other
+                                      than pinhole / radtan / equidistant, cuBLAS / cuSOLVER missing for the dense variants) */
 
 #define EQVIO_COORD_EUCLIDEAN 0
 #define EQVIO_COORD_INVDEPTH 1

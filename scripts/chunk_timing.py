@@ -35,3 +35,15 @@ names = {0: "start", 1: "C/Idx loaded", 2: "S gather done", 3: "S loop done", 4:
 base = t[0]
 for i in sorted(names):
     print(f"{names[i]:>18s}: {t[i] - base:8d} cycles")
+
+fine = getattr(_capi.lib, "eqvio_debug_chunk_fine", None)
+if fine is not None:
+    fine.restype = C.c_int
+    buf = (C.c_longlong * 128)()
+    if fine(buf) == 0:
+        f = np.array(list(buf), dtype=np.int64)
+        print("block column: diag-phase | barrier 1 | panel-phase + barrier 2 | trailing (thread 0's view; thread 0 owns tile (0,0))")
+        for J in range(16):
+            a, b, c, d = f[4 * J:4 * J + 4]
+            nxt = f[4 * J + 4] if J < 15 else d
+            print(f"  J={J:2d}  {b - a:6d} {c - b:6d} {d - c:6d} {nxt - d:6d}   total {nxt - a:6d}")

@@ -296,12 +296,6 @@ def test_silent_returns_and_errors():
     with pytest.raises(eb.EqvioError) as ei:
         eb.VIOFilter(eb.Settings(coordinateChoice=3), capacity=4)
     assert ei.value.code == eb._capi.EQVIO_ERR_UNSUPPORTED
-    g = eb.VIOFilter(eb.Settings(fastRiccati=0, useDiscreteStateMatrix=1, useDiscreteVelocityLift=0), capacity=4)
-    g.processIMUArray(fr.imu)
-    with pytest.raises(eb.EqvioError) as ei:
-        g.processVisionArrays(fr.stamp, fr.ids[:2], fr.y[:2], cam)
-    assert ei.value.code == eb._capi.EQVIO_ERR_UNSUPPORTED
-    g.close()
 
 
 def test_from_imu_initialisation_matches_oracle():
@@ -465,12 +459,15 @@ def test_accurate_riccati_default_settings(coord):
     _check(run_gpu(stream), run_oracle(stream), tol=1e-8)
 
 
-@pytest.mark.parametrize("coord", [0, 1])
-def test_discrete_state_matrix(coord):
+@pytest.mark.parametrize("coord,lift", [(0, True), (1, True), (0, False), (2, True), (2, False)])
+def test_discrete_state_matrix(coord, lift):
     """fastRiccati = false with useDiscreteStateMatrix: integrateRiccatiStateDiscrete per IMU sample (VIO_eqf.cpp:93-103)
     with the numerically differentiated stateMatrixADiscrete (EqFMatrices.cpp:24-41; central differences, h = cbrt(eps):
-    rounding in the function values is amplified by 1 / 2h ~ 8e4, hence the looser tolerance)."""
-    stream = make_stream(N=12, frames=4, coord=coord, settings_overrides=dict(fastRiccati=False, useDiscreteStateMatrix=True))
+    rounding in the function values is amplified by 1 / 2h ~ 8e4, hence the looser tolerance).  The discrete state matrix
+    always differentiates liftVelocityDiscrete, also when the observer integrates with the continuous lift (lift=False), and
+    it is taken in the chart of the coordinate suite (coord 2 = Normal: B still goes through M)."""
+    stream = make_stream(N=12, frames=4, coord=coord, settings_overrides=dict(fastRiccati=False, useDiscreteStateMatrix=True,
+                                                                             useDiscreteVelocityLift=lift))
     _check(run_gpu(stream), run_oracle(stream), tol=1e-7)
 
 
