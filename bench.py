@@ -51,9 +51,13 @@ def parse():
     ap.add_argument("--landmarks", type=int, default=256)
     ap.add_argument("--coord", type=int, default=0)
     ap.add_argument("--sequences-per-gpu", type=int, default=1, help="independent sequences (replicas) run concurrently per GPU")
+    ap.add_argument("--batched-sequences", type=int, default=16,
+                    help="extra leg of the single-GPU, single-sequence run: this many independent sequences replayed concurrently on "
+                         "the GPU (BASELINE configs[4]: 16 Monte-Carlo instances per GPU), reported as \"batched\"; 0 = skip")
     ap.add_argument("--no-graph", action="store_true", help="issue per-kernel launches instead of replaying CUDA graphs")
     ap.add_argument("--pipeline", action="store_true", help="experimental: overlap chunk c+1's factor kernel with chunk c's downdate")
     ap.add_argument("--chain", type=int, default=None, help="EQVIO_TUNE_CHAIN (experimental chained correction): 0 / 1 / 2")
+    ap.add_argument("--stage", action="store_true", help="chunk factor kernel stages Sigma[L_c, L_c] through TMA bulk copies (slower)")
     ap.add_argument("--no-lookahead", action="store_true", help="one in-order downdate launch per chunk (no band / rest split)")
     ap.add_argument("--downdate", default="f64", choices=["f64", "tc"],
                     help="f64: DMMA fp64 downdate (default); tc: tcgen05 split-bf16 operands, fp32 accumulate in TMEM (BASELINE configs[2])")
@@ -282,6 +286,8 @@ def run_b200(args, rank, local_rank, world):
             flt.setTuning(chain=args.chain)
         if args.no_lookahead:
             flt.setTuning(lookahead=0)
+        if args.stage:
+            flt.setTuning(stageS=1)
         if args.downdate == "tc":
             flt.setTuning(downdate=1)
         filters.append(flt)
@@ -431,6 +437,31 @@ def run_b200(args, rank, local_rank, world):
     n_meas = len(streams[0].frames[1 + W].ids)
     n_state = flt.numLandmarks()
 
+    # Batched leg (single GPU, single-sequence run only): B independent sequences -- the Monte-Carlo instances of BASELINE
+    # configs[4], 16 per GPU -- replayed concurrently through the same C ABI with HOST buffers, one C++ host thread per sequence
+    # (eqvio_replay_batch), wall clock over the whole batch.  A reported side figure: `value` / `e2e` stay the single sequence.
+    batched = None
+    B = args.batched_sequences
+    if world == 1 and R == 1 and B > 1:
+        Kb, Wb = min(K, 40 if N <= 256 else 15), 3
+        bstreams = [record_stream(SimConfig.benchmark(N, 1000 + b, duration=20.0), 1 + Wb + Kb) for b in range(B)]
+        bfilters = []
+        for sm_ in bstreams:
+            bf = eb.VIOFilter(st, eb.VIOState(eb.VIOSensorState.fromFlat(sm_.init_sensor), sm_.init_p, sm_.init_ids), 0.0, capacity=N + 8,
+                              device=local_rank)
+            if args.no_graph:
+                bf.setTuning(graph=0)
+            bfilters.append(bf)
+        eb.replayBatch(bfilters, [sm_.frames[:1 + Wb] for sm_ in bstreams], cam)  # t = 0 image + warm-up (graph capture)
+        l0 = sum(f_.launchCount() for f_ in bfilters)
+        _, est_bb, wall_bb = eb.replayBatch(bfilters, [sm_.frames[1 + Wb:] for sm_ in bstreams], cam)
+        assert np.isfinite(est_bb).all()
+        batched = dict(sequences=B, steps_per_sequence=Kb, value=B * Kb / (wall_bb * 1e-3), unit="updates/s", ms_per_batch_step=wall_bb / Kb,
+                       gpu_launches=int(sum(f_.launchCount() for f_ in bfilters) - l0),
+                       timing="host wall clock over the batch, host buffers in and state estimates out (same contract as e2e)")
+        for bf in bfilters:
+            bf.close()
+
     t = torch.tensor([dev_ms, e2e_ms, cpp_ms, real_ms], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -539,6 +570,8 @@ def run_b200(args, rank, local_rank, world):
                                                 timing="CUDA events around each synchronised step")),
                     gpu_launches=int(launches), launches_per_step=launches / K,
                     stage_ms={k_: v / K for k_, v in stage_acc.items()}, clocks=sampler.result(), roofline=roofline)
+        if batched:
+            line["batched"] = batched
         if not args.no_cpu_baseline:
             est_s = 17.0 * cnt["dim"] ** 3 / 50e9 + 0.02  # ~17 dim^3 flops of the dense path at a conservative 50 GFLOP/s
             sample_n = args.cpu_sample or int(max(3, min(K, 20.0 / est_s)))

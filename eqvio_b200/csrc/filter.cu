@@ -124,6 +124,7 @@ struct eqvio_filter {
     bool pdlHold = false;  // next launch_pdl is a plain launch (its predecessor produces what the kernel reads before its wait)
     int pdl = 1;           // chunk kernels are launched with programmatic dependent launch allowed
     int specNew = 1;       // frames with new ids also speculate (new-landmark positions computed on the device)
+    int stageS = 0;        // chunk factor kernel: Sigma[L_c, L_c] through TMA bulk copies when the chunk is contiguous in the state (measured slower)
     int *d_keepI = nullptr, *d_newMeas = nullptr;
     int newMeasCap = 0;
     int fuseSmall = 1;     // steady update: gate + measurement rows in one launch, lift + state estimate in one launch
@@ -1448,8 +1449,9 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                 double* Yc = Ybuf[c & 1];
                 cudaEvent_t evF = f->chunkEv[2 * c], evR = f->chunkEv[2 * c + 1];
                 f->pdlHold = (j0 == 0);  // chunk 0 follows meas_kernel, whose output the kernel stages ahead of its dependency wait
-                launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), (size_t)CH_SMEM_BASE, f->stream, f->Sig[f->cur], f->ld,
-                           dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Yc, f->d_status, guard, nullptr, TL_SLOT(f));
+                launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), (size_t)(f->stageS ? CH_SMEM_STAGED : CH_SMEM_BASE), f->stream,
+                           f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Yc, f->d_status, guard, nullptr,
+                           TL_SLOT(f), f->stageS ? 1 : 0);
                 f->pdlHold = false;
                 LAUNCH_CHECK(f, "chunk_factor_kernel");
                 std::swap(gin, gout);
@@ -1490,8 +1492,9 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                 const int bc = std::min(bcMax, nm - j0);
                 int pk = prof_begin(f, PROF_PANEL);
                 f->pdlHold = (j0 == 0);  // chunk 0 follows meas_kernel, whose output the kernel stages ahead of its dependency wait
-                launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), (size_t)CH_SMEM_BASE, f->stream, f->Sig[f->cur], f->ld,
-                           dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Y, f->d_status, guard, nullptr, TL_SLOT(f));
+                launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), (size_t)(f->stageS ? CH_SMEM_STAGED : CH_SMEM_BASE), f->stream,
+                           f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Y, f->d_status, guard, nullptr,
+                           TL_SLOT(f), f->stageS ? 1 : 0);
                 prof_end(f, pk);
                 f->pdlHold = false;
                 LAUNCH_CHECK(f, "chunk_factor_kernel");
@@ -1550,7 +1553,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                 const int cfIn = c == 0 ? sin : 1 - sin;
                 chunk_factor_kernel<<<ldy / CH_COLS, CH_THREADS, sizeof(ChunkSmem), f->stream>>>(
                     f->Sig[cfIn], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Ybuf[c & 1], f->d_status, guard,
-                    c > 0 ? Ybuf[(c - 1) & 1] : nullptr, TL_SLOT(f));
+                    c > 0 ? Ybuf[(c - 1) & 1] : nullptr, TL_SLOT(f), 0);
                 f->pdlHold = false;
                 LAUNCH_CHECK(f, "chunk_factor_kernel");
                 CUDA_TRY(f, cudaEventRecord(evF, f->stream));
@@ -1747,7 +1750,7 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChunkSmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ChunkSmem) > (size_t)CH_SMEM_STAGED ? sizeof(ChunkSmem) : (size_t)CH_SMEM_STAGED));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Chunk2Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LOOK_SMEM);
     if (e != cudaSuccess) {
@@ -2568,6 +2571,10 @@ int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
             return EQVIO_OK;
         case EQVIO_TUNE_SPECULATE_NEW:
             f->specNew = value != 0;
+            return EQVIO_OK;
+        case EQVIO_TUNE_STAGE_S:
+            f->stageS = value != 0;
+            clear_graphs(f);
             return EQVIO_OK;
         case EQVIO_TUNE_FUSE_SMALL:
             f->fuseSmall = value != 0;

@@ -1145,6 +1145,33 @@ constexpr int YB_T = 64, YB_LD = 68;
 constexpr size_t YB_TILE = (size_t)YB_T * YB_LD;
 __host__ __device__ __forceinline__ size_t yb_index(int k, int s) { return (size_t)(s >> 6) * YB_TILE + (size_t)k * YB_LD + (s & 63); }
 
+// mbarrier / TMA bulk-copy helpers (cp.async.bulk, SASS UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 struct ChunkSmem {
     union {
         double Lp[CH_NT][CH_T][CH_T][CH_NT + 1];  // Lp[J][r][j][TI] = v(row 4TI+r, col 4J+j): every finished panel is kept
@@ -1163,6 +1190,19 @@ struct ChunkSmem {
     alignas(16) double Ur[CH_R][CH_RHS_ROWS * CH_T + 4];
 };
 constexpr int CH_SMEM_BASE = (int)offsetof(ChunkSmem, Us);
+// Staged S gather (stage = 1, Yprev == nullptr): when the chunk's landmarks are consecutive in the state, Sigma[L_c, L_c] is
+// 96 runs of <= 96 contiguous doubles.  One warp hands them to the TMA unit (cp.async.bulk, one mbarrier) and the tile owners
+// project from shared memory, instead of every owner gathering 36 scattered doubles through the LSU (the scattered form costs
+// ~5.7 k cycles per launch, L1 wavefront-bound).  Only rows <= the column's own landmark pair are needed (lower tiles read
+// through their mirror).  The area starts at CH_SMEM_BASE, in place of the pipelined mode's Us / Ur.
+constexpr int CH_STG_N = 3 * (CH_R / 2);   // 96 state rows / columns of a chunk
+constexpr int CH_STG_LD = CH_STG_N + 2;    // + 1 for a 16-byte aligned start, rounded to an even count
+struct ChunkStage {
+    alignas(16) double S[CH_STG_N][CH_STG_LD];  // S[c][off + r] = Sigma[row0 + r, row0 + c]
+    alignas(8) uint64_t bar;
+};
+constexpr int CH_SMEM_STAGED = CH_SMEM_BASE + (int)sizeof(ChunkStage);
+static_assert(CH_SMEM_BASE % 16 == 0, "staging area must stay 16-byte aligned");
 
 
 // reciprocal to <= 1 ulp: hardware approximation + two Newton steps (a correctly rounded division is
@@ -1181,6 +1221,17 @@ __device__ __forceinline__ void tri_decode(int t, int& row, int& col) {
     while (r * (r + 1) / 2 > t) --r;
     row = r;
     col = t - r * (r + 1) / 2;
+}
+// column-major enumeration of the same triangle with nt block rows: (0,0),(1,0),...,(nt-1,0),(1,1),(2,1),...  A warp then holds
+// whole block columns: the tiles of a finished block column retire together, and a panel sits in one or two warps
+__device__ __forceinline__ void tri_decode_cm(int t, int nt, int& row, int& col) {
+    int c = 0, off = 0;
+    while (t >= off + (nt - c)) {
+        off += nt - c;
+        ++c;
+    }
+    col = c;
+    row = c + (t - off);
 }
 #ifdef EQVIO_CHUNK_TIMING
 __device__ long long g_chunk_t[16];
@@ -1216,7 +1267,7 @@ __global__ void __launch_bounds__(CH_THREADS)
     chunk_factor_kernel(const double* __restrict__ Sig, int ld, int dimp, const int* __restrict__ lmOf,
                         const double* __restrict__ Cblk, const double* __restrict__ ytilde, int j0, int bc, double r2,
                         const double* __restrict__ GammaIn, double* __restrict__ GammaOut, double* __restrict__ Y,
-                        int* __restrict__ status, const int* __restrict__ guard, const double* __restrict__ Yprev, int tl) {
+                        int* __restrict__ status, const int* __restrict__ guard, const double* __restrict__ Yprev, int tl, int stage) {
     // Cblk / lmOf come from meas_kernel and the frame upload (the host launches chunk 0 as a plain launch, later chunks follow
     // other chunk kernels): they are staged BEFORE the dependency wait, so the set-up overlaps the predecessor's tail
     extern __shared__ __align__(16) unsigned char chunk_smem_raw[];
@@ -1227,11 +1278,32 @@ __global__ void __launch_bounds__(CH_THREADS)
     for (int t = tid; t < bc * 6; t += CH_THREADS) sm.C[t / 6][t % 6] = Cblk[6 * (size_t)j0 + t];
     for (int t = tid; t < bc; t += CH_THREADS) sm.Idx[t] = SOFF + 3 * lmOf[j0 + t];
     if (tid == 0) sm.ready = 0;
+    ChunkStage& stg = *reinterpret_cast<ChunkStage*>(chunk_smem_raw + CH_SMEM_BASE);
+    if (stage && tid == 0) {
+        mbar_init(&stg.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     pdl_wait();
     if (*guard) return;
     TL_MARK(tl, 0);
-    __syncthreads();
+    // staged gather: the chunk's landmarks must be consecutive in the state (uniform decision riding on the barrier that
+    // publishes C / Idx), and the padded runs must stay inside their columns
+    const int lm0 = lmOf[j0];
+    const int consecutive = __syncthreads_and(tid >= bc || lmOf[j0 + tid] == lm0 + tid);
     CH_STAMP(1);
+    const int stgRows = 6 * ((3 * bc - 1) / 6 + 1);  // rows the last column group asks for
+    const bool staged = stage != 0 && consecutive && (SOFF + 3 * lm0 + stgRows + 1 <= ld);
+    const int stgOff = staged ? ((SOFF + 3 * lm0) & 1) : 0;
+    if (staged && tid >= CH_S_THREADS - 32 && tid < CH_S_THREADS) {
+        // warp 4 (8 tile owners + 24 idle lanes) issues the copies: column c needs rows 0 .. 6 (c / 6 + 1) - 1 of the block,
+        // i.e. 6 (c / 6 + 1) + 2 stgOff doubles from the even row below the block start (16-byte aligned: ld % 64 == 0)
+        const int lane = tid & 31;
+        const int ncol = 3 * bc, G = ncol / 6, rem = ncol - 6 * G;
+        if (lane == 0) mbar_expect_tx(&stg.bar, 8u * (uint32_t)(6 * (3 * G * (G + 1) + 2 * stgOff * G) + rem * (6 * (G + 1) + 2 * stgOff)));
+        const double* src = Sig + (size_t)(SOFF + 3 * lm0) * ld + (SOFF + 3 * lm0 - stgOff);
+        for (int c = lane; c < ncol; c += 32)
+            bulk_g2s(&stg.S[c][0], src + (size_t)c * ld, 8u * (uint32_t)(6 * (c / 6 + 1) + 2 * stgOff), &stg.bar);
+    }
     // Pipelined mode: Sig is the covariance BEFORE the previous chunk's downdate (that downdate is running
     // concurrently, out of place).  Its effect on this chunk's augmented matrix, M -= U^T U_S with u_rho = the
     // column of Yprev belonging to augmented row rho, is applied here from Yprev itself.
@@ -1268,7 +1340,7 @@ __global__ void __launch_bounds__(CH_THREADS)
         // ================================ S group ================================
         const bool owner = tid < CH_TILES;
         int TI = 0, TK = 0;
-        if (owner) tri_decode(tid, TI, TK);
+        if (owner) tri_decode_cm(tid, CH_NT, TI, TK);
         if (owner) {
             // S tile = 2x2 landmark pairs: rows from landmarks 2TI, 2TI+1; columns from 2TK, 2TK+1.  All loads first.
             double P[2][2][9];
@@ -1277,16 +1349,31 @@ __global__ void __launch_bounds__(CH_THREADS)
 #pragma unroll
                 for (int v = 0; v < 2; ++v) {
                     const int j = 2 * TI + u, k = 2 * TK + v;
-                    if (j < bc && k < bc) {
-                        // Sigma[rows of j, cols of k] read through its mirror Sigma[rows of k, cols of j]: lanes walk k, and
-                        // chunks follow the state order, so a warp touches a few contiguous lines instead of 32
-                        const double* sp = Sig + (size_t)sm.Idx[j] * ld + sm.Idx[k];
+                    if (j < bc && k < bc && !staged) {
+                        // Sigma[rows of j, cols of k]: lanes walk j (column-major tile order) and chunks follow the state order,
+                        // so a warp touches a few contiguous runs of the chunk's columns instead of 32 lines
+                        const double* sp = Sig + (size_t)sm.Idx[k] * ld + sm.Idx[j];
 #pragma unroll
-                        for (int aa = 0; aa < 3; ++aa)
+                        for (int b = 0; b < 3; ++b)
 #pragma unroll
-                            for (int b = 0; b < 3; ++b) P[u][v][aa * 3 + b] = sp[(size_t)aa * ld + b];
+                            for (int aa = 0; aa < 3; ++aa) P[u][v][aa * 3 + b] = sp[(size_t)b * ld + aa];
                     }
                 }
+            if (staged) {
+                mbar_wait(&stg.bar, 0);
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) {
+                        const int j = 2 * TI + u, k = 2 * TK + v;
+                        if (j < bc && k < bc) {
+#pragma unroll
+                            for (int aa = 0; aa < 3; ++aa)
+#pragma unroll
+                                for (int b = 0; b < 3; ++b) P[u][v][aa * 3 + b] = stg.S[3 * j + aa][stgOff + 3 * k + b];
+                        }
+                    }
+            }
 #pragma unroll
             for (int u = 0; u < 2; ++u)
 #pragma unroll
@@ -1553,11 +1640,24 @@ __global__ void __launch_bounds__(CH_THREADS)
         const int k = t / CH_COLS, sl = t % CH_COLS;
         Y[yb_index(k, sbase + sl)] = sm.Yt[k][sl];
     }
-    if (tid < CH_COLS && sbase + tid < dimp) {
+    // Gamma += Y_c^T z_c: eight partial sums per state column (one warp each, fixed order), combined by shuffles in the
+    // last warp group -- a single thread per column would walk 64 dependent FMAs at the very end of the launch
+    {
+        const int col = tid & 31, part = tid >> 5;  // warps 0-7 of the 10
         double g = 0.0;
-#pragma unroll 8
-        for (int k = 0; k < CH_R; ++k) g += sm.Yt[k][tid] * sm.Yt[k][CH_COLS];
-        GammaOut[sbase + tid] = GammaIn[sbase + tid] + g;  // ping-pong: other CTAs may still be reading GammaIn
+        if (part < 8) {
+#pragma unroll
+            for (int k = 0; k < CH_R / 8; ++k) g += sm.Yt[8 * part + k][col] * sm.Yt[8 * part + k][CH_COLS];
+        }
+        double* gpart = &sm.Lp[0][0][0][0] + CH_R * (CH_RHS_ROWS * CH_T + 1);  // behind Yt inside the union
+        if (part < 8) gpart[part * 32 + col] = g;
+        __syncthreads();
+        if (tid < CH_COLS && sbase + tid < dimp) {
+            double t = GammaIn[sbase + tid];
+            double acc = ((gpart[tid] + gpart[32 + tid]) + (gpart[64 + tid] + gpart[96 + tid])) +
+                         ((gpart[128 + tid] + gpart[160 + tid]) + (gpart[192 + tid] + gpart[224 + tid]));
+            GammaOut[sbase + tid] = t + acc;  // ping-pong: other CTAs may still be reading GammaIn
+        }
     }
     CH_STAMP(6);
     TL_MARK(tl, 1);
@@ -2107,32 +2207,6 @@ __global__ void __launch_bounds__(LOOK ? LOOK_THREADS : CH_THREADS)
 constexpr int DD_T = 64, DD_LD = YB_LD, DD_THREADS = 128;
 constexpr int DD_SMEM = 2 * DD_T * DD_LD * 8 + 16;
 enum { DD_ALL = 0, DD_BAND = 1, DD_REST = 2 };  // which tiles a launch of chunk_downdate_kernel covers
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 
 __global__ void __launch_bounds__(DD_THREADS, 3)
     chunk_downdate_kernel(const double* SigIn, double* SigOut, int ld, const double* __restrict__ Y,

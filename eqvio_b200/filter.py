@@ -350,7 +350,7 @@ class VIOFilter:
         return dict(propagation=ms[0], preprocessing=ms[1], correction=ms[2])
 
     def setTuning(self, correction=None, chunkLandmarks=None, speculate=None, graph=None, pipeline=None, downdate=None,
-                  lookahead=None, fuseObserver=None, pdl=None, chain=None, fuseSmall=None, speculateNew=None):
+                  lookahead=None, fuseObserver=None, pdl=None, chain=None, fuseSmall=None, speculateNew=None, stageS=None):
         """Evaluation-order knobs (eqvio_set_tuning): correction 0 = sequential chunks, 1 = batch sweep."""
         if speculate is not None:
             self._check(lib.eqvio_set_tuning(self._h, 2, int(speculate)))
@@ -362,6 +362,8 @@ class VIOFilter:
             self._check(lib.eqvio_set_tuning(self._h, 5, int(downdate)))
         if speculateNew is not None:
             self._check(lib.eqvio_set_tuning(self._h, 11, int(speculateNew)))
+        if stageS is not None:  # 1 = Sigma[L_c, L_c] staged through TMA bulk copies in the chunk factor kernel
+            self._check(lib.eqvio_set_tuning(self._h, 12, int(stageS)))
         if fuseSmall is not None:
             self._check(lib.eqvio_set_tuning(self._h, 10, int(fuseSmall)))
         if chain is not None:  # 1 = chained correction (look-ahead CTA + concurrent downdates), 2 = same in stream order, 0 = off
