@@ -1153,7 +1153,7 @@ class VIO_eqf:
             W = np.matmul(Cb, Sigma[SENSOR_DIM:, :].reshape(N, 3, dim)[lm]).reshape(m, dim)
             Wl = W[:, SENSOR_DIM:].reshape(m, N, 3)[:, lm, :].transpose(1, 2, 0)  # (n, 3, m)
             S = np.matmul(Cb, Wl).reshape(m, m).T + outputGainMatrix
-            L = np.linalg.cholesky(S)
+            L = sl.cholesky(S, lower=True, check_finite=False)
             Y = sl.solve_triangular(L, W, lower=True, check_finite=False)
             z = sl.solve_triangular(L, yTilde, lower=True, check_finite=False)
             Gamma = Y.T @ z
@@ -1162,8 +1162,11 @@ class VIO_eqf:
             else:
                 Delta = VIOExp(self.coordinateSuite.liftInnovation(Gamma, self.xi0))
             self.X = Delta * self.X
-            T = np.tril(sl.blas.dsyrk(1.0, Y, trans=1, lower=1))  # half the flops of Y^T Y
-            self.Sigma = Sigma - (T + np.tril(T, -1).T)
+            T = sl.blas.dsyrk(1.0, Y, trans=1, lower=1)  # lower triangle of Y^T Y (half the flops), zeros above the diagonal
+            out = Sigma - T
+            out -= T.T
+            out[np.diag_indices_from(out)] += np.diagonal(T)
+            self.Sigma = out
             self.lastGamma = Gamma
             return
 
