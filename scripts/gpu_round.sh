@@ -12,7 +12,7 @@ for c in 1 2; do timeout 600 python bench.py --landmarks 256 --coord $c --no-cpu
 python scripts/nonsteady_profile.py 256 60 > $O/final_nonsteady.txt 2>&1; python scripts/nonsteady_profile.py 64 60 >> $O/final_nonsteady.txt 2>&1
 python scripts/host_profile.py 256 2>&1 | head -3 > $O/final_host_profile.txt
 timeout 600 python bench.py --impl reference --steps 10 --warmup 2 > $O/final_bench_reference_n256.json 2> $O/final_bench_reference.err
-timeout 300 python bench.py --landmarks 256 --sequences-per-gpu 8 --no-cpu-baseline > $O/final_bench_n256_r8.json 2>/dev/null
+timeout 300 python bench.py --landmarks 256 --sequences-per-gpu 16 --no-cpu-baseline > $O/final_bench_n256_r16.json 2>/dev/null
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/final_launches_n256.csv \
   python bench.py --steps 3 --warmup 3 --profile-steps 0 --no-cpu-baseline --no-graph > $O/final_ncu_launch.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"chunk_factor_kernel|chunk_downdate_kernel|prop_ll_kernel|observer_fused_kernel" -s 40 -c 12 \
