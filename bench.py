@@ -42,6 +42,35 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
+class StdoutGuard:
+    """stdout carries the ONE JSON line only: while the benchmark runs, file descriptor 1 points at stderr (NCCL prints its
+    version banner to stdout from C, torchrun children inherit chatty libraries); emit() restores it for the line."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
+
+def all_host_threads():
+    """Context manager: BLAS / OpenMP pools at the host's core count.  torchrun exports OMP_NUM_THREADS=1 to its children, which
+    would silently turn the all-threads CPU baseline / reference arm into a one-thread run."""
+    try:
+        from threadpoolctl import threadpool_limits
+
+        return threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        import contextlib
+
+        return contextlib.nullcontext()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -219,7 +248,7 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, guard):
     if rank != 0:
         return
     from simdata import SimConfig, record_stream
@@ -228,8 +257,9 @@ def run_reference(args, rank, world):
     skw = settings_dict(args.coord)
     frames = 1 + args.warmup + args.steps
     stream = record_stream(SimConfig.benchmark(N, 0, duration=20.0 if frames <= 399 else float((frames + 1) // 20 + 2)), frames)
-    ups, stages, done = time_cpu(stream, skw, args.warmup, args.steps)
-    cores = blas_threads()
+    with all_host_threads():
+        ups, stages, done = time_cpu(stream, skw, args.warmup, args.steps)
+        cores = blas_threads()
     sample = f"{done} consecutive updates of the same stream after {args.warmup} warm-up updates"
     variants = cpu_variants(stream, skw, min(args.warmup, 2), ups)
     line = dict(impl="reference", metric="vision-updates/sec", value=ups, unit="updates/s", n_gpus=args.gpus, steps=done,
@@ -241,10 +271,10 @@ def run_reference(args, rank, world):
                 cpu_baseline=dict(value=ups, unit="updates/s", cores=cores, kind="port", sample=sample,
                                   stage_ms={k: 1000.0 * v / done for k, v in stages.items()}, **variants),
                 e2e=dict(value=ups, unit="updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    guard.emit(line)
 
 
-def run_b200(args, rank, local_rank, world):
+def run_b200(args, rank, local_rank, world, guard):
     import torch
 
     import __graft_entry__ as entry
@@ -581,17 +611,19 @@ def run_b200(args, rank, local_rank, world):
                     stage_ms={k_: v / K for k_, v in stage_acc.items()}, clocks=sampler.result(), roofline=roofline)
         if batched:
             line["batched"] = batched
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is a single-GPU-run figure (rank 0 at N = 1 only)
             est_s = 17.0 * cnt["dim"] ** 3 / 50e9 + 0.02  # ~17 dim^3 flops of the dense path at a conservative 50 GFLOP/s
             sample_n = args.cpu_sample or int(max(3, min(K, 20.0 / est_s)))
-            ups, stages, done = time_cpu(streams[0], skw, min(W, 2), sample_n)
-            line["cpu_baseline"] = dict(value=ups, unit="updates/s", cores=blas_threads(), kind="port",
+            with all_host_threads():
+                ups, stages, done = time_cpu(streams[0], skw, min(W, 2), sample_n)
+                ncores = blas_threads()
+            line["cpu_baseline"] = dict(value=ups, unit="updates/s", cores=ncores, kind="port",
                                         sample=f"{done} consecutive updates of sequence 0 (same inputs) after {min(W, 2)} warm-up "
                                         "updates; oracle port of the dense Eigen path in the reference's evaluation order "
                                         "(numpy + OpenBLAS; includes ~20 ms/update of Python overhead)",
                                         stage_ms={k_: 1000.0 * v / done for k_, v in stages.items()})
             line["cpu_baseline"].update(cpu_variants(streams[0], skw, min(W, 2), ups))
-        print(json.dumps(line), flush=True)
+        guard.emit(line)
     for f in filters:
         f.close()
     if dist:
@@ -604,10 +636,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    guard = StdoutGuard()
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, guard)
     else:
-        run_b200(args, rank, local_rank, world)
+        run_b200(args, rank, local_rank, world, guard)
 
 
 if __name__ == "__main__":
