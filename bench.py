@@ -59,15 +59,19 @@ class StdoutGuard:
 
 
 def all_host_threads():
-    """Context manager: BLAS / OpenMP pools at the host's core count.  torchrun exports OMP_NUM_THREADS=1 to its children, which
-    would silently turn the all-threads CPU baseline / reference arm into a one-thread run."""
+    """Context manager for the all-threads CPU arms.  torchrun exports OMP_NUM_THREADS=1 to its children, which would silently turn
+    the reference arm into a one-thread run: when the environment restricts the BLAS pools, lift them to the physical core count;
+    otherwise leave the pools at their own default."""
+    import contextlib
+
+    if not any(os.environ.get(v) for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")):
+        return contextlib.nullcontext()
     try:
+        import psutil
         from threadpoolctl import threadpool_limits
 
-        return threadpool_limits(limits=os.cpu_count() or 1)
+        return threadpool_limits(limits=psutil.cpu_count(logical=False) or os.cpu_count() or 1)
     except Exception:
-        import contextlib
-
         return contextlib.nullcontext()
 
 
