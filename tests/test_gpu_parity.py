@@ -111,6 +111,21 @@ def test_steady_path_variants_agree(tuning):
         assert e["ids_equal"] and e["sigma"] == 0.0 and e["state"] == 0.0
 
 
+@pytest.mark.parametrize("graph", [0, 1])
+def test_staged_s_gather(graph):
+    """EQVIO_TUNE_STAGE_S: the chunk factor kernel fetches Sigma[L_c, L_c] through TMA bulk copies instead of per-thread gathers.
+    It reads the block through its mirror (the other triangle of the symmetric storage, equal to the last bit only outside the
+    diagonal tiles), so the results agree to rounding, not bit for bit.  N = 40: one full chunk of 32 landmarks and a ragged one of
+    8; landmark-set changes make some chunks non-contiguous in the state, which falls back to the gather."""
+    stream = make_stream(N=40, frames=12, coord=0)
+    ref = run_gpu(stream, tuning=dict(graph=0, speculate=0))
+    got = run_gpu(stream, tuning=dict(graph=graph, stageS=1))
+    for g, r in zip(got, ref):
+        e = compare_states(g, r)
+        assert e["ids_equal"] and e["sigma"] < 1e-12 and e["state"] < 1e-12
+    _check(got, run_oracle(stream))
+
+
 @pytest.mark.parametrize("coord", [0, 1])
 def test_continuous_lifts(coord):
     """useDiscreteVelocityLift = useDiscreteInnovationLift = false (the EuRoC config's innovation lift)."""
