@@ -90,7 +90,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="issue per-kernel launches instead of replaying CUDA graphs")
     ap.add_argument("--pipeline", action="store_true", help="experimental: overlap chunk c+1's factor kernel with chunk c's downdate")
     ap.add_argument("--chain", type=int, default=None, help="EQVIO_TUNE_CHAIN (experimental chained correction): 0 / 1 / 2")
-    ap.add_argument("--stage", action="store_true", help="chunk factor kernel stages Sigma[L_c, L_c] through TMA bulk copies (slower)")
+    ap.add_argument("--no-stage", action="store_true", help="chunk factor kernel gathers Sigma[L_c, L_c] itself instead of the TMA tensor copy")
     ap.add_argument("--no-lookahead", action="store_true", help="one in-order downdate launch per chunk (no band / rest split)")
     ap.add_argument("--downdate", default="f64", choices=["f64", "tc"],
                     help="f64: DMMA fp64 downdate (default); tc: tcgen05 split-bf16 operands, fp32 accumulate in TMEM (BASELINE configs[2])")
@@ -329,8 +329,8 @@ def run_b200(args, rank, local_rank, world, guard):
             flt.setTuning(chain=args.chain)
         if args.no_lookahead:
             flt.setTuning(lookahead=0)
-        if args.stage:
-            flt.setTuning(stageS=1)
+        if args.no_stage:
+            flt.setTuning(stageS=0)
         if args.downdate == "tc":
             flt.setTuning(downdate=1)
         filters.append(flt)

@@ -63,6 +63,8 @@ struct eqvio_filter {
     // device state
     int ld = 0;
     double* Sig[2] = {nullptr, nullptr};
+    CUtensorMap sigMap[2] = {};  // 2-D tensor maps of the two covariance buffers (96 x 96 box): TMA staging of the S blocks
+    bool haveSigMap = false;
     int cur = 0;
     double* lm[2] = {nullptr, nullptr};
     int* dids[2] = {nullptr, nullptr};
@@ -124,7 +126,7 @@ struct eqvio_filter {
     bool pdlHold = false;  // next launch_pdl is a plain launch (its predecessor produces what the kernel reads before its wait)
     int pdl = 1;           // chunk kernels are launched with programmatic dependent launch allowed
     int specNew = 1;       // frames with new ids also speculate (new-landmark positions computed on the device)
-    int stageS = 0;        // chunk factor kernel: Sigma[L_c, L_c] through TMA bulk copies when the chunk is contiguous in the state (measured slower)
+    int stageS = 1;        // chunk factor kernel: Sigma[L_c, L_c] as one TMA tensor copy when the chunk is contiguous in the state
     int *d_keepI = nullptr, *d_newMeas = nullptr;
     int newMeasCap = 0;
     int fuseSmall = 1;     // steady update: gate + measurement rows in one launch, lift + state estimate in one launch
@@ -427,6 +429,28 @@ int alloc_frame(eqvio_filter* f, int steps, int ycap) {
     return EQVIO_OK;
 }
 
+// CUtensorMap of a column-major ld x ld fp64 covariance buffer with a 96 x 96 box (the S block of one chunk).  The encoder lives in
+// the driver library; it is fetched through the runtime so that nothing links against libcuda directly.
+bool make_sigma_maps(eqvio_filter* f) {
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn || q != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)f->ld, (cuuint64_t)f->ld};
+    const cuuint64_t strides[1] = {(cuuint64_t)f->ld * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)CH_STG_N, (cuuint32_t)CH_STG_N}, estr[2] = {1, 1};
+    for (int k = 0; k < 2; ++k)
+        if (reinterpret_cast<EncodeTiled>(fn)(&f->sigMap[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, f->Sig[k], dims, strides, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    return true;
+}
+
 int alloc_device(eqvio_filter* f) {
     const int cap = f->cap;
     const int dimpMax = dimp_of(cap);
@@ -439,6 +463,7 @@ int alloc_device(eqvio_filter* f) {
         CUDA_TRY(f, cudaMemsetAsync(f->lm[k], 0, (size_t)LM_FIELDS * std::max(cap, 1) * sizeof(double), f->stream));
         CUDA_TRY(f, cudaMalloc(&f->dids[k], std::max(cap, 1) * sizeof(int)));
     }
+    f->haveSigMap = make_sigma_maps(f);
     CUDA_TRY(f, cudaMalloc(&f->d_xi0s, 23 * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Xs[0], 23 * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Xs[1], 23 * sizeof(double)));
@@ -1449,9 +1474,9 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                 double* Yc = Ybuf[c & 1];
                 cudaEvent_t evF = f->chunkEv[2 * c], evR = f->chunkEv[2 * c + 1];
                 f->pdlHold = (j0 == 0);  // chunk 0 follows meas_kernel, whose output the kernel stages ahead of its dependency wait
-                launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), (size_t)(f->stageS ? CH_SMEM_STAGED : CH_SMEM_BASE), f->stream,
+                launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), (size_t)(f->stageS && f->haveSigMap ? CH_SMEM_STAGED : CH_SMEM_BASE), f->stream,
                            f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Yc, f->d_status, guard, nullptr,
-                           TL_SLOT(f), f->stageS ? 1 : 0);
+                           TL_SLOT(f), f->stageS && f->haveSigMap ? 1 : 0, f->sigMap[f->cur]);
                 f->pdlHold = false;
                 LAUNCH_CHECK(f, "chunk_factor_kernel");
                 std::swap(gin, gout);
@@ -1492,9 +1517,9 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                 const int bc = std::min(bcMax, nm - j0);
                 int pk = prof_begin(f, PROF_PANEL);
                 f->pdlHold = (j0 == 0);  // chunk 0 follows meas_kernel, whose output the kernel stages ahead of its dependency wait
-                launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), (size_t)(f->stageS ? CH_SMEM_STAGED : CH_SMEM_BASE), f->stream,
+                launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), (size_t)(f->stageS && f->haveSigMap ? CH_SMEM_STAGED : CH_SMEM_BASE), f->stream,
                            f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Y, f->d_status, guard, nullptr,
-                           TL_SLOT(f), f->stageS ? 1 : 0);
+                           TL_SLOT(f), f->stageS && f->haveSigMap ? 1 : 0, f->sigMap[f->cur]);
                 prof_end(f, pk);
                 f->pdlHold = false;
                 LAUNCH_CHECK(f, "chunk_factor_kernel");
@@ -1553,7 +1578,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                 const int cfIn = c == 0 ? sin : 1 - sin;
                 chunk_factor_kernel<<<ldy / CH_COLS, CH_THREADS, sizeof(ChunkSmem), f->stream>>>(
                     f->Sig[cfIn], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Ybuf[c & 1], f->d_status, guard,
-                    c > 0 ? Ybuf[(c - 1) & 1] : nullptr, TL_SLOT(f), 0);
+                    c > 0 ? Ybuf[(c - 1) & 1] : nullptr, TL_SLOT(f), 0, f->sigMap[cfIn]);
                 f->pdlHold = false;
                 LAUNCH_CHECK(f, "chunk_factor_kernel");
                 CUDA_TRY(f, cudaEventRecord(evF, f->stream));

@@ -14,6 +14,7 @@
 //             Cholesky of [[S, W],[W^T, Sigma]] whose Schur complement is the updated Sigma.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -1190,19 +1191,23 @@ struct ChunkSmem {
     alignas(16) double Ur[CH_R][CH_RHS_ROWS * CH_T + 4];
 };
 constexpr int CH_SMEM_BASE = (int)offsetof(ChunkSmem, Us);
-// Staged S gather (stage = 1, Yprev == nullptr): when the chunk's landmarks are consecutive in the state, Sigma[L_c, L_c] is
-// 96 runs of <= 96 contiguous doubles.  One warp hands them to the TMA unit (cp.async.bulk, one mbarrier) and the tile owners
-// project from shared memory, instead of every owner gathering 36 scattered doubles through the LSU (the scattered form costs
-// ~5.7 k cycles per launch, L1 wavefront-bound).  Only rows <= the column's own landmark pair are needed (lower tiles read
-// through their mirror).  The area starts at CH_SMEM_BASE, in place of the pipelined mode's Us / Ur.
+// Staged S gather (stage = 1, Yprev == nullptr): when the chunk's landmarks are consecutive in the state, Sigma[L_c, L_c] is one
+// 96 x 96 box of the covariance.  One thread hands it to the TMA unit as a single 2-D tensor copy (cp.async.bulk.tensor.2d over a
+// CUtensorMap of Sigma, one mbarrier) and the tile owners project from shared memory, instead of every owner gathering 36
+// scattered doubles through the LSU (~5.7 k cycles per launch, bound by the number of small requests).  Rows / columns past the
+// matrix come back as zeros.  TMA wants the box to start on a 16-byte boundary: chunks that start at an odd landmark use the gather.  The area starts at CH_STAGE_OFF, in place of the pipelined mode's Us / Ur.
 constexpr int CH_STG_N = 3 * (CH_R / 2);   // 96 state rows / columns of a chunk
-constexpr int CH_STG_LD = CH_STG_N + 2;    // + 1 for a 16-byte aligned start, rounded to an even count
 struct ChunkStage {
-    alignas(16) double S[CH_STG_N][CH_STG_LD];  // S[c][off + r] = Sigma[row0 + r, row0 + c]
+    alignas(128) double S[CH_STG_N][CH_STG_N];  // S[c][r] = Sigma[row0 + r, row0 + c]
     alignas(8) uint64_t bar;
 };
-constexpr int CH_SMEM_STAGED = CH_SMEM_BASE + (int)sizeof(ChunkStage);
-static_assert(CH_SMEM_BASE % 16 == 0, "staging area must stay 16-byte aligned");
+constexpr int CH_STAGE_OFF = (CH_SMEM_BASE + 127) & ~127;
+constexpr int CH_SMEM_STAGED = CH_STAGE_OFF + (int)sizeof(ChunkStage);
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 
 // reciprocal to <= 1 ulp: hardware approximation + two Newton steps (a correctly rounded division is
@@ -1267,10 +1272,11 @@ __global__ void __launch_bounds__(CH_THREADS)
     chunk_factor_kernel(const double* __restrict__ Sig, int ld, int dimp, const int* __restrict__ lmOf,
                         const double* __restrict__ Cblk, const double* __restrict__ ytilde, int j0, int bc, double r2,
                         const double* __restrict__ GammaIn, double* __restrict__ GammaOut, double* __restrict__ Y,
-                        int* __restrict__ status, const int* __restrict__ guard, const double* __restrict__ Yprev, int tl, int stage) {
+                        int* __restrict__ status, const int* __restrict__ guard, const double* __restrict__ Yprev, int tl, int stage,
+                        const __grid_constant__ CUtensorMap sigMap) {
     // Cblk / lmOf come from meas_kernel and the frame upload (the host launches chunk 0 as a plain launch, later chunks follow
     // other chunk kernels): they are staged BEFORE the dependency wait, so the set-up overlaps the predecessor's tail
-    extern __shared__ __align__(16) unsigned char chunk_smem_raw[];
+    extern __shared__ __align__(128) unsigned char chunk_smem_raw[];
     ChunkSmem& sm = *reinterpret_cast<ChunkSmem*>(chunk_smem_raw);
     const int tid = threadIdx.x;
     const int rc = 2 * bc;
@@ -1278,7 +1284,7 @@ __global__ void __launch_bounds__(CH_THREADS)
     for (int t = tid; t < bc * 6; t += CH_THREADS) sm.C[t / 6][t % 6] = Cblk[6 * (size_t)j0 + t];
     for (int t = tid; t < bc; t += CH_THREADS) sm.Idx[t] = SOFF + 3 * lmOf[j0 + t];
     if (tid == 0) sm.ready = 0;
-    ChunkStage& stg = *reinterpret_cast<ChunkStage*>(chunk_smem_raw + CH_SMEM_BASE);
+    ChunkStage& stg = *reinterpret_cast<ChunkStage*>(chunk_smem_raw + CH_STAGE_OFF);
     if (stage && tid == 0) {
         mbar_init(&stg.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1287,22 +1293,14 @@ __global__ void __launch_bounds__(CH_THREADS)
     if (*guard) return;
     TL_MARK(tl, 0);
     // staged gather: the chunk's landmarks must be consecutive in the state (uniform decision riding on the barrier that
-    // publishes C / Idx), and the padded runs must stay inside their columns
+    // publishes C / Idx)
     const int lm0 = lmOf[j0];
     const int consecutive = __syncthreads_and(tid >= bc || lmOf[j0 + tid] == lm0 + tid);
     CH_STAMP(1);
-    const int stgRows = 6 * ((3 * bc - 1) / 6 + 1);  // rows the last column group asks for
-    const bool staged = stage != 0 && consecutive && (SOFF + 3 * lm0 + stgRows + 1 <= ld);
-    const int stgOff = staged ? ((SOFF + 3 * lm0) & 1) : 0;
-    if (staged && tid >= CH_S_THREADS - 32 && tid < CH_S_THREADS) {
-        // warp 4 (8 tile owners + 24 idle lanes) issues the copies: column c needs rows 0 .. 6 (c / 6 + 1) - 1 of the block,
-        // i.e. 6 (c / 6 + 1) + 2 stgOff doubles from the even row below the block start (16-byte aligned: ld % 64 == 0)
-        const int lane = tid & 31;
-        const int ncol = 3 * bc, G = ncol / 6, rem = ncol - 6 * G;
-        if (lane == 0) mbar_expect_tx(&stg.bar, 8u * (uint32_t)(6 * (3 * G * (G + 1) + 2 * stgOff * G) + rem * (6 * (G + 1) + 2 * stgOff)));
-        const double* src = Sig + (size_t)(SOFF + 3 * lm0) * ld + (SOFF + 3 * lm0 - stgOff);
-        for (int c = lane; c < ncol; c += 32)
-            bulk_g2s(&stg.S[c][0], src + (size_t)c * ld, 8u * (uint32_t)(6 * (c / 6 + 1) + 2 * stgOff), &stg.bar);
+    const bool staged = stage != 0 && consecutive && (lm0 & 1) == 0;  // the box must start 16-byte aligned: even first row (SOFF is even)
+    if (staged && tid == CH_S_THREADS - 32) {  // first lane of warp 4 (8 tile owners + 24 idle lanes)
+        mbar_expect_tx(&stg.bar, (uint32_t)sizeof(stg.S));
+        tma_load_2d(&stg.S[0][0], &sigMap, SOFF + 3 * lm0, SOFF + 3 * lm0, &stg.bar);
     }
     // Pipelined mode: Sig is the covariance BEFORE the previous chunk's downdate (that downdate is running
     // concurrently, out of place).  Its effect on this chunk's augmented matrix, M -= U^T U_S with u_rho = the
@@ -1370,7 +1368,7 @@ __global__ void __launch_bounds__(CH_THREADS)
 #pragma unroll
                             for (int aa = 0; aa < 3; ++aa)
 #pragma unroll
-                                for (int b = 0; b < 3; ++b) P[u][v][aa * 3 + b] = stg.S[3 * j + aa][stgOff + 3 * k + b];
+                                for (int b = 0; b < 3; ++b) P[u][v][aa * 3 + b] = stg.S[3 * k + b][3 * j + aa];  // same entries as the gather
                         }
                     }
             }
@@ -1728,7 +1726,7 @@ __global__ void __launch_bounds__(LOOK ? LOOK_THREADS : CH_THREADS)
     constexpr int ROWS = LOOK ? CH_NT : CH_RHS_ROWS;  // tile rows of right-hand sides
     // Cblk / lmOf were written by meas_kernel and the frame upload, several launches back on this stream's history: they are
     // read BEFORE the dependency wait so that the set-up overlaps the predecessor's tail
-    extern __shared__ __align__(16) unsigned char chunk_smem_raw[];
+    extern __shared__ __align__(128) unsigned char chunk_smem_raw[];
     Chunk2Smem& sm = *reinterpret_cast<Chunk2Smem*>(chunk_smem_raw);
     const int tid = threadIdx.x;
     const int rc = 2 * bc;

@@ -260,9 +260,9 @@ int eqvio_get_host_profile(eqvio_filter* f, int reset, double us[4], long long* 
  *                         so the update needs no host round trip; if a gate trips they are dropped and added again through the exact
  *                         host path; 0 = wait for the gate scalars whenever a frame brings new ids. */
 #define EQVIO_TUNE_SPECULATE_NEW 11
-/*   EQVIO_TUNE_STAGE_S: 1 = the chunk factor kernel fetches Sigma[L_c, L_c] through the TMA unit into shared memory when the
- *     chunk's landmarks are consecutive in the state; 0 (default) = every tile owner gathers its entries itself (faster: 96 small
- *     bulk copies take ~8.8 k cycles against ~5.7 k for the direct gather). */
+/*   EQVIO_TUNE_STAGE_S: 1 (default) = the chunk factor kernel fetches Sigma[L_c, L_c] as ONE 2-D TMA tensor copy (96 x 96 box of a
+ *     CUtensorMap over the covariance) into shared memory when the chunk's landmarks are consecutive in the state; 0 = every tile
+ *     owner gathers its 36 entries itself (also the fall-back for non-consecutive chunks).  Same entries, bit-identical results. */
 #define EQVIO_TUNE_STAGE_S 12
 int eqvio_set_tuning(eqvio_filter* f, int key, int value);
 /* Version / build info string (arch the kernels were compiled for). */

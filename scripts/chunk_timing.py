@@ -19,7 +19,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 sm = record_stream(SimConfig.benchmark(N, 0), 12)
 flt = eb.VIOFilter(eb.Settings(fastRiccati=1), eb.VIOState(eb.VIOSensorState.fromFlat(sm.init_sensor), sm.init_p, sm.init_ids), 0.0,
                    capacity=N + 8)
-flt.setTuning(graph=0, stageS=int(os.environ.get('EQVIO_STAGE', '0')))
+flt.setTuning(graph=0, stageS=int(os.environ.get('EQVIO_STAGE', '1')))
 cam = eb.Camera(**sm.camera)
 for fr in sm.frames:
     flt.processIMUArray(fr.imu)
