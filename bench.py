@@ -612,7 +612,12 @@ def run_b200(args, rank, local_rank, world, guard):
                              python_driver=dict(value=e2e_py, ms_per_step=e2e_ms_max / K, host_ms_per_step=1000.0 * wall_in / K,
                                                 timing="CUDA events around each synchronised step")),
                     gpu_launches=int(launches), launches_per_step=launches / K,
-                    stage_ms={k_: v / K for k_, v in stage_acc.items()}, clocks=sampler.result(), roofline=roofline)
+                    stage_ms={k_: v / K for k_, v in stage_acc.items()},
+                    stage_ms_note=("per-stage event brackets of plain launches" if args.no_graph else
+                                   "the timed steps replay one CUDA graph per update: a single bracket, booked under correction; the "
+                                   "propagation / preprocessing / correction split of the same update with plain launches is "
+                                   "roofline.profile_stage_ms"),
+                    clocks=sampler.result(), roofline=roofline)
         if batched:
             line["batched"] = batched
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is a single-GPU-run figure (rank 0 at N = 1 only)

@@ -163,6 +163,8 @@ struct eqvio_filter {
     bool stageTiming = false;
     cudaEvent_t stageEv[4] = {nullptr, nullptr, nullptr, nullptr};
     double stageMs[3] = {0, 0, 0};
+    bool capturing = false;    // inside cudaStreamBeginCapture / EndCapture of a steady update
+    bool steadySplit = false;  // the last steady update was enqueued with plain launches: its stage events 1 and 2 are recorded
     double augMs = 0;  // device time of augment_landmark_states calls since the last process_vision
     bool profiling = false;
     std::vector<EventPair> evPool;
@@ -908,6 +910,8 @@ int enqueue_steady_update(eqvio_filter* f, int N, int nm, const FramePlan* plan)
     const eqvio_settings& s = f->st;
     CUDA_TRY(f, cudaMemcpyAsync(f->d_frame, f->h_frame, f->frameBytes, cudaMemcpyHostToDevice, f->stream));
     if ((rc = enqueue_propagation(f)) != EQVIO_OK) return rc;
+    f->steadySplit = !f->capturing;  // stage brackets inside the update exist only with plain launches (a replayed graph is one bracket)
+    if (f->steadySplit) stage_mark(f, 1);
     const bool fuseEst = f->fuseSmall && f->corrMode == 0;
     const bool fuseGate = fuseEst && !plan;  // with a landmark-set change the gate sees the OLD state, the rows the NEW one
     if (!fuseGate && (rc = enqueue_gate(f, N, false)) != EQVIO_OK) return rc;  // riccati_prep_kernel re-armed the flag
@@ -925,6 +929,7 @@ int enqueue_steady_update(eqvio_filter* f, int N, int nm, const FramePlan* plan)
         f->ids = plan->nids;
         Nout = plan->Nnew;
     }
+    if (f->steadySplit) stage_mark(f, 2);
     if ((rc = enqueue_correction(f, nm, f->d_spec, fuseGate, fuseEst)) != EQVIO_OK) return rc;
     // stateEstimate() is what every caller asks for next (main_opt.cpp:225, main_sim.cpp:146): produced here, by the lift itself
     // in the fused form
@@ -1098,7 +1103,9 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
                 cudaGraph_t graph = nullptr;
                 CUDA_TRY(f, cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal));
                 std::vector<int> ids0 = f->ids;  // a captured landmark-set change assigns f->ids: the replay below does it for real
+                f->capturing = true;
                 rc = enqueue_steady_update(f, N, nm, change ? &plan : nullptr);
+                f->capturing = false;
                 cudaError_t ce = cudaStreamEndCapture(f->stream, &graph);
                 f->ids.swap(ids0);
                 eqvio_filter::GraphEntry ge;
@@ -1651,7 +1658,7 @@ int vision_phase_c(eqvio_filter* f, int* did_update) {
     prof_collect(f);
     if (f->stageTiming && P.active) {
         for (int i = 0; i < 3; ++i) f->stageMs[i] = 0;
-        if (P.steady) {  // one bracket around the whole enqueued update
+        if (P.steady && !f->steadySplit) {  // a replayed graph: one bracket around the whole update
             float ms = 0;
             if (cudaEventElapsedTime(&ms, f->stageEv[0], f->stageEv[3]) == cudaSuccess) f->stageMs[2] = ms;
         } else {
