@@ -349,35 +349,18 @@ class VIOFilter:
         self._check(lib.eqvio_get_stage_ms(self._h, _pd(ms)))
         return dict(propagation=ms[0], preprocessing=ms[1], correction=ms[2])
 
-    def setTuning(self, correction=None, chunkLandmarks=None, speculate=None, graph=None, pipeline=None, downdate=None,
-                  lookahead=None, fuseObserver=None, pdl=None, chain=None, fuseSmall=None, speculateNew=None, stageS=None):
-        """Evaluation-order knobs (eqvio_set_tuning): correction 0 = sequential chunks, 1 = batch sweep."""
-        if speculate is not None:
-            self._check(lib.eqvio_set_tuning(self._h, 2, int(speculate)))
-        if graph is not None:
-            self._check(lib.eqvio_set_tuning(self._h, 3, int(graph)))
-        if pipeline is not None:
-            self._check(lib.eqvio_set_tuning(self._h, 4, int(pipeline)))
-        if downdate is not None:  # 0 = fp64 DMMA, 1 = tcgen05 split-bf16 / fp32 accumulate
-            self._check(lib.eqvio_set_tuning(self._h, 5, int(downdate)))
-        if speculateNew is not None:
-            self._check(lib.eqvio_set_tuning(self._h, 11, int(speculateNew)))
-        if stageS is not None:  # 1 = Sigma[L_c, L_c] staged through TMA bulk copies in the chunk factor kernel
-            self._check(lib.eqvio_set_tuning(self._h, 12, int(stageS)))
-        if fuseSmall is not None:
-            self._check(lib.eqvio_set_tuning(self._h, 10, int(fuseSmall)))
-        if chain is not None:  # 1 = chained correction (look-ahead CTA + concurrent downdates), 2 = same in stream order, 0 = off
-            self._check(lib.eqvio_set_tuning(self._h, 9, int(chain)))
-        if pdl is not None:
-            self._check(lib.eqvio_set_tuning(self._h, 8, int(pdl)))
-        if fuseObserver is not None:
-            self._check(lib.eqvio_set_tuning(self._h, 7, int(fuseObserver)))
-        if lookahead is not None:  # 1 = split downdates (band / rest) overlapped with the next chunk's factor kernel
-            self._check(lib.eqvio_set_tuning(self._h, 6, int(lookahead)))
-        if correction is not None:
-            self._check(lib.eqvio_set_tuning(self._h, 0, int(correction)))
-        if chunkLandmarks is not None:
-            self._check(lib.eqvio_set_tuning(self._h, 1, int(chunkLandmarks)))
+    def setTuning(self, **knobs):
+        """Evaluation-order knobs (eqvio_set_tuning, include/eqvio_b200.h EQVIO_TUNE_*): correction (0 = sequential chunks, 1 = batch
+        sweep), chunkLandmarks, speculate, graph, pipeline, downdate (0 = fp64 DMMA, 1 = tcgen05 split-bf16), lookahead (split
+        downdates beside the next factor kernel), fuseObserver, pdl, chain (1 = chained correction with concurrent downdates,
+        2 = the same in stream order), fuseSmall, speculateNew, stageS (S blocks through one TMA tensor copy).  Results agree across
+        every knob (tests/test_gpu_parity.py)."""
+        for name, value in knobs.items():
+            if value is None:
+                continue
+            if name not in _capi.TUNE:
+                raise TypeError(f"setTuning: unknown knob {name!r} (known: {', '.join(_capi.TUNE)})")
+            self._check(lib.eqvio_set_tuning(self._h, _capi.TUNE[name], int(value)))
 
     def replay(self, frames, camera: Camera, flushBytes=0):
         """C++ host loop over the C ABI (eqvio_replay): per frame processIMUData x k, augmentLandmarkStates,

@@ -44,6 +44,18 @@ def test_header_symbols_exported(capi):
     assert sorted(capi.SIGNATURES) == names
 
 
+def test_tuning_keys_match_header(capi):
+    """The keyword -> key table of VIOFilter.setTuning is the EQVIO_TUNE_* list of the header."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "eqvio_b200.h")).read()
+    header = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+EQVIO_TUNE_(\w+)\s+(\d+)", text)}
+    assert header, "no EQVIO_TUNE_* definitions found"
+    mine = {capi.TUNE_HEADER_NAMES[k]: v for k, v in capi.TUNE.items()}
+    assert mine == header
+
+
 def test_build_info(capi):
     assert b"sm_100a" in capi.lib.eqvio_build_info()
 
