@@ -930,7 +930,9 @@ int enqueue_steady_update(eqvio_filter* f, int N, int nm, const FramePlan* plan)
         Nout = plan->Nnew;
     }
     if (f->steadySplit) stage_mark(f, 2);
-    if ((rc = enqueue_correction(f, nm, f->d_spec, fuseGate, fuseEst)) != EQVIO_OK) return rc;
+    // maxOutliers == 0 (featureRetention = 1, or (1 - featureRetention) n < 1): removeOutliers removes nothing whatever the gate
+    // says (VIOFilter.cpp:304-364), so the correction must not be guarded by the gate flag -- d_spec + 1 is a constant 0
+    if ((rc = enqueue_correction(f, nm, f->pend.ignoreGate ? f->d_spec + 1 : f->d_spec, fuseGate, fuseEst)) != EQVIO_OK) return rc;
     // stateEstimate() is what every caller asks for next (main_opt.cpp:225, main_sim.cpp:146): produced here, by the lift itself
     // in the fused form
     if (!fuseEst) {
@@ -1088,7 +1090,9 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
             const eqvio_settings& st = f->st;
             std::vector<int> key = {N, n, f->cur, f->lmcur, f->xcur, f->chunkLm, st.coordinateChoice, st.useDiscreteVelocityLift,
                                     st.useDiscreteInnovationLift, st.useEquivariantOutput, f->maxSteps, f->yCap,
-                                    change ? 1 : 0, Nout, plan.nNew > 0 ? 1 : 0};
+                                    change ? 1 : 0, Nout, plan.nNew > 0 ? 1 : 0, P.ignoreGate ? 1 : 0,
+                                    // the observer kernel form is chosen on the host from the number of buffered IMU segments
+                                    reinterpret_cast<const FrameHeader*>(f->h_frame)->fs.nsteps <= OBS_STAGE ? 1 : 0};
             auto it = f->graphs.find(key);
             if (it == f->graphs.end()) {
                 if (f->graphs.size() >= 32) {  // evict the least recently used

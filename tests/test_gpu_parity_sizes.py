@@ -1,0 +1,203 @@
+"""Parity at BASELINE's sizes and with the reference's shipped switch sets: the CUDA path (through the C ABI) against the
+CPU oracle on the same seeded VIOSimulator streams.
+
+* N = 1024 (configs[2]) and N = 256 (configs[1]) against the oracle, state / Sigma / ids, several consecutive updates;
+* N = 256 with the InvDepth chart, and N = 256 in eqvio_opt's flow (ids lost / added inside processVisionData) with gating;
+* the switch set of configs/EQVIO_config_EuRoC_stationary.yaml:17-61 (InvDepth, radtan camera, continuous innovation lift,
+  fixed new-landmark depth, the YAML's thresholds / variances) at N = 40 (the YAML's maxFeatures) and N = 200 (configs[3]);
+* removeInvalidLandmarks (VIO_eqf.cpp:213-223) with a landmark whose Q.a leaves (1e-8, 1e8];
+* featureRetention leaving no room for removals (maxOutliers == 0) while gates trip (VIOFilter.cpp:304-364);
+* a vision drop-out (> 64 buffered IMU samples) through cached CUDA graphs.
+
+Tolerance: 1e-9 relative Frobenius where nothing else is said (BASELINE.json asks 1e-6).
+"""
+import numpy as np
+import pytest
+
+from parity_utils import compare_states, gpu_filter, make_stream, run_gpu, run_oracle, snapshot_gpu, snapshot_oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+def _check(gpu, ref, tol=TOL):
+    assert len(gpu) == len(ref)
+    worst = 0.0
+    for k, (g, r) in enumerate(zip(gpu, ref)):
+        e = compare_states(g, r)
+        assert e["ids_equal"], f"update {k}: landmark ids differ"
+        assert e["sigma"] < tol, f"update {k}: Sigma rel-Frobenius {e['sigma']:.3e}"
+        assert e["state"] < tol, f"update {k}: state rel-Frobenius {e['state']:.3e}"
+        worst = max(worst, e["sigma"], e["state"])
+    return worst
+
+
+def _lockstep(stream, augment, tuning=None, tol=TOL, frames=None):
+    """Oracle and CUDA filter side by side, compared after every update.  augment=False is eqvio_opt's flow."""
+    import eqvio_b200 as eb
+    from oracle import eqf
+
+    o = eqf.VIOFilter(stream["settings"], stream["init"], 0.0)
+    o.filterState.structuredEvaluation = True  # same update, block-structured evaluation (seconds instead of minutes at N >= 256)
+    g, cam = gpu_filter(stream)
+    if tuning:
+        g.setTuning(**tuning)
+    worst, removed, sizes = 0.0, 0, []
+    for k, fr in enumerate(frames if frames is not None else stream["frames"]):
+        for row in fr.imu:
+            o.processIMUData(eqf.IMUVelocity(row[0], row[1:4], row[4:7], row[7:10], row[10:13]))
+        g.processIMUArray(fr.imu)
+        if augment:
+            o.augmentLandmarkStates(list(fr.ids), eqf.VIOState(None, fr.provided_p, fr.ids))
+            g.augmentLandmarkStates(fr.ids, eb.VIOState(eb.VIOSensorState(), fr.provided_p, fr.ids))
+        o.processVisionData(eqf.VisionMeasurement.fromArrays(fr.stamp, fr.ids, fr.y, stream["cam"]))
+        g.processVisionArrays(fr.stamp, fr.ids, fr.y, cam)
+        e = compare_states(snapshot_gpu(g), snapshot_oracle(o))
+        assert e["ids_equal"], f"update {k}: landmark ids differ"
+        assert e["sigma"] < tol and e["state"] < tol, f"update {k}: Sigma {e['sigma']:.3e}, state {e['state']:.3e}"
+        worst = max(worst, e["sigma"], e["state"])
+        removed += len(g.lastOutliers())
+        sizes.append(g.numLandmarks())
+    g.close()
+    return worst, removed, sizes
+
+
+def test_n1024_matches_oracle():
+    """BASELINE configs[2] size, fp64 (DMMA) mode: three consecutive updates against the oracle -- state, Sigma, ids."""
+    stream = make_stream(N=1024, frames=3, coord=0)
+    worst, _, sizes = _lockstep(stream, augment=True)
+    assert sizes[-1] == 1024
+    print(f"N=1024 fp64: worst rel-Frobenius vs oracle {worst:.3e}")
+
+
+def test_n1024_tensor_core_mode_vs_oracle():
+    """configs[2] arithmetic (tcgen05 downdate, split-bf16 operands, fp32 accumulation) at its own size against the oracle.
+    Not an fp64 path: the bound is what the mode delivers, ids must be identical."""
+    stream = make_stream(N=1024, frames=3, coord=0)
+    ref = run_oracle(stream, structured=True)
+    got = run_gpu(stream, tuning=dict(downdate=1))
+    ws = wx = 0.0
+    for g, r in zip(got, ref):
+        e = compare_states(g, r)
+        assert e["ids_equal"]
+        ws, wx = max(ws, e["sigma"]), max(wx, e["state"])
+    print(f"N=1024 tcgen05 downdate: Sigma {ws:.3e}, state {wx:.3e} (rel-Frobenius vs oracle)")
+    assert ws < 5e-3 and wx < 1e-4
+
+
+@pytest.mark.parametrize("coord", [0, 1])
+def test_n256_charts_match_oracle(coord):
+    """BASELINE configs[1] size with the Euclidean and the InvDepth chart, six updates."""
+    stream = make_stream(N=256, frames=6, coord=coord)
+    worst, _, sizes = _lockstep(stream, augment=True)
+    assert sizes[-1] == 256
+    print(f"N=256 coord={coord}: worst {worst:.3e}")
+
+
+@pytest.mark.parametrize("graph", [1, 0])
+def test_n256_real_data_flow_with_gating(graph):
+    """N = 256 in eqvio_opt's flow: no augmentLandmarkStates, ids lost / added inside processVisionData (planned frames inside
+    the cached graph), noisy pixels and IMU with gates that trip -- discrete decisions and values against the oracle."""
+    ov = dict(outlierThresholdAbs=3.0, outlierThresholdProb=6.0, measurementNoise=0.5, featureRetention=0.2)
+    stream = make_stream(N=256, frames=10, coord=0, settings_overrides=ov, sim_overrides=dict(outputNoise=True, inputNoise=True))
+    worst, removed, sizes = _lockstep(stream, augment=False, tuning=dict(graph=graph))
+    assert removed > 0, "the case is meant to trip gates"
+    print(f"N=256 real-data flow, graph={graph}: worst {worst:.3e}, {removed} outliers removed, sizes {sizes}")
+
+
+def euroc_settings():
+    """configs/EQVIO_config_EuRoC_stationary.yaml:17-61 (the switch set and gains the reference ships for EuRoC)."""
+    return dict(coordinateChoice=1, fastRiccati=True, useDiscreteInnovationLift=False, useDiscreteVelocityLift=True,
+                useEquivariantOutput=True, useFeaturePredictions=False, useMedianDepth=False, initialSceneDepth=5.00028218320243,
+                initialAttitudeVariance=0.13565029126052572, initialBiasAccelVariance=1.5813333765300104,
+                initialBiasOmegaVariance=97162.79515771076, initialCameraAttitudeVariance=0.0010228558965517584,
+                initialCameraPositionVariance=0.023501400846134893, initialPointVariance=129.90415638150924,
+                initialPositionVariance=0.1, initialVelocityVariance=8.974852995731e-08, measurementNoise=1.9297839969591413,
+                outlierThresholdAbs=4.852186665580312, outlierThresholdProb=0.03229809583062128,
+                featureRetention=0.18594708334486176, attitudeProcessVariance=6.025875320811407e-05, biasAccelProcessVariance=0.0,
+                biasOmegaProcessVariance=0.0, cameraAttitudeProcessVariance=5.075382174045239e-06,
+                cameraPositionProcessVariance=1.2188313140115635e-05, pointProcessVariance=0.00029845436136043135,
+                positionProcessVariance=9.981466095928483e-06, velocityProcessVariance=0.025317333863551263,
+                velAccNoise=0.012438843268295521, velAccBiasWalk=0.004462289865453429, velGyrNoise=0.000243153572917808,
+                velGyrBiasWalk=0.00013372703521098622)
+
+
+@pytest.mark.parametrize("N,frames", [(40, 20), (200, 8)])
+def test_euroc_switch_set(N, frames):
+    """The configuration the reference ships for BASELINE configs[3] (EuRoC): InvDepth chart, radtan camera with the EuRoC cam0
+    intrinsics, continuous innovation lift, new landmarks at the fixed scene depth, the YAML's gating thresholds and
+    feature retention, on a noisy simulated stream in eqvio_opt's flow.  (The dataset itself and the GIFT front-end are absent.)"""
+    from oracle.camera import StandardCamera
+    from oracle.simulator import SimulationDataServer, benchmarkSim
+
+    ov = euroc_settings()
+    coord = ov.pop("coordinateChoice")
+    stream = make_stream(N=N, frames=1, coord=coord, settings_overrides=ov)
+    cam = StandardCamera(752, 480, 458.654, 457.296, 367.215, 248.375, [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0])
+    server = SimulationDataServer(benchmarkSim(N, 0, outputNoise=True, inputNoise=True), stream["settings"])
+    server.simulator.cameraPtr = cam
+    stream["cam"] = cam
+    stream["init"] = server.initialCondition()
+    stream["frames"] = server.record(frames)
+    # the YAML's initial variances span 1e-7 .. 1e5 (biasGyr 97162, velocity 9e-8): rounding differences between two fp64
+    # evaluation orders are amplified accordingly (observed <= 4e-8 in the state, 4e-11 in Sigma); BASELINE's bound is 1e-6
+    worst, removed, sizes = _lockstep(stream, augment=False, tol=1e-6)
+    print(f"EuRoC switch set N={N}: worst {worst:.3e}, outliers removed {removed}, sizes {sizes}")
+    assert worst < 2e-7
+    assert removed > 0, "the YAML's probabilistic threshold (0.032) trips on noisy pixels"
+
+
+def test_remove_invalid_landmarks():
+    """VIO_eqf.cpp:213-223: a landmark whose scale Q.a leaves (1e-8, 1e8] is dropped after the update.  Two landmarks start a
+    thousand times too close to the camera with a large point variance and the continuous InvDepth innovation lift: the
+    first parallax drives their inverse-depth innovation far enough that exp(w) underflows the lower bound."""
+    from oracle import eqf
+
+    stream = make_stream(N=16, frames=10, coord=1, settings_overrides=dict(useDiscreteInnovationLift=False, initialPointVariance=100.0))
+    stream["init"].p[3] *= 1e-3
+    stream["init"].p[7] *= 1e-3
+    dropped = []
+    orig = eqf.VIO_eqf.removeInvalidLandmarks
+
+    def counting(self):
+        n0 = len(self.X.ids)
+        orig(self)
+        dropped.append(n0 - len(self.X.ids))
+
+    eqf.VIO_eqf.removeInvalidLandmarks = counting
+    try:
+        _lockstep(stream, augment=True, tol=1e-7)
+    finally:
+        eqf.VIO_eqf.removeInvalidLandmarks = orig
+    assert sum(dropped) > 0, "the case is meant to trip removeInvalidLandmarks in the oracle"
+
+
+@pytest.mark.parametrize("graph", [1, 0])
+@pytest.mark.parametrize("retention,N", [(1.0, 24), (0.3, 1)])
+def test_gate_trips_without_room_for_removals(retention, N, graph):
+    """maxOutliers = (1 - featureRetention) n == 0: removeOutliers proposes but removes nothing (VIOFilter.cpp:304-364) and the
+    full correction runs although gates trip -- also on the speculative / graph path, whose device-side gate flag must not
+    suppress the correction."""
+    ov = dict(outlierThresholdAbs=0.5, outlierThresholdProb=0.5, measurementNoise=0.5, featureRetention=retention)
+    stream = make_stream(N=N, frames=8, coord=0, settings_overrides=ov, sim_overrides=dict(outputNoise=True, inputNoise=True))
+    worst, removed, sizes = _lockstep(stream, augment=True, tuning=dict(graph=graph))
+    assert removed == 0 and sizes[-1] == N
+
+
+def test_vision_dropout_replays_graphs_with_many_imu_segments():
+    """A vision drop-out buffers > 64 IMU samples (the fused observer kernel stages at most 64): short and long frames alternate
+    so that graphs captured for one kind are never replayed on the other; against the oracle after every update."""
+    stream = make_stream(N=24, frames=40, coord=0)
+    fr = stream["frames"]
+
+    class Merged:
+        def __init__(self, group):
+            last = group[-1]
+            self.stamp, self.ids, self.y, self.provided_p = last.stamp, last.ids, last.y, last.provided_p
+            self.imu = np.concatenate([g.imu for g in group], axis=0)
+
+    seq = list(fr[:4]) + [Merged(fr[4:12])] + list(fr[12:15]) + [Merged(fr[15:23])] + list(fr[23:26]) + [Merged(fr[26:40])]
+    assert max(len(f.imu) for f in seq) > 128
+    worst, _, _ = _lockstep(stream, augment=True, frames=seq)
+    print(f"drop-out sequence: worst {worst:.3e}")
