@@ -123,9 +123,11 @@ struct eqvio_filter {
     int* d_cnt = nullptr;  // per-chunk completion counters of the downdates (chained correction)
     double* d_Snext[2] = {nullptr, nullptr};  // S block handed from one factor launch to the next
     int prLeast = 0, prGreatest = 0;  // stream priority range of the device
+    int smCount = 148;                // SMs of the device (grid sizing)
     bool pdlHold = false;  // next launch_pdl is a plain launch (its predecessor produces what the kernel reads before its wait)
     int pdl = 1;           // chunk kernels are launched with programmatic dependent launch allowed
     int specNew = 1;       // frames with new ids also speculate (new-landmark positions computed on the device)
+    int dfFactor = 1;      // dataflow chunk factor kernel (chunk_factor_df_kernel) instead of the barrier-synchronised one
     int stageS = 1;        // chunk factor kernel: Sigma[L_c, L_c] as one TMA tensor copy when the chunk is contiguous in the state
     int *d_keepI = nullptr, *d_newMeas = nullptr;
     int newMeasCap = 0;
@@ -1347,6 +1349,30 @@ int launch_correction(eqvio_filter* f, const int* guard) {
     return EQVIO_OK;
 }
 
+// One chunk factor launch (S_c, its elimination, Y_c, Gamma): the dataflow kernel by default, the round-1 kernel behind
+// EQVIO_TUNE_FACTOR = 0.  COLS = 16 state columns per CTA while that stays within one wave of CTAs, else 32.
+int launch_chunk_factor(eqvio_filter* f, int ldy, int dimp, int j0, int bc, double r2, const double* gin, double* gout, double* Yc,
+                        const int* guard) {
+    const int stage = f->stageS && f->haveSigMap ? 1 : 0;
+    if (f->dfFactor) {
+        if (ldy / 16 <= f->smCount)
+            launch_pdl(f, chunk_factor_df_kernel<16>, dim3(ldy / 16), dim3(CF_THREADS), (size_t)cf_smem_bytes<16>(), f->stream,
+                       (const double*)f->Sig[f->cur], f->ld, dimp, (const int*)f->d_lmOf, (const double*)f->d_Cblk, (const double*)f->d_ytilde, j0, bc, r2,
+                       gin, gout, Yc, f->d_status, guard, TL_SLOT(f), stage, f->sigMap[f->cur]);
+        else
+            launch_pdl(f, chunk_factor_df_kernel<32>, dim3(ldy / 32), dim3(CF_THREADS), (size_t)cf_smem_bytes<32>(), f->stream,
+                       (const double*)f->Sig[f->cur], f->ld, dimp, (const int*)f->d_lmOf, (const double*)f->d_Cblk, (const double*)f->d_ytilde, j0, bc, r2,
+                       gin, gout, Yc, f->d_status, guard, TL_SLOT(f), stage, f->sigMap[f->cur]);
+        LAUNCH_CHECK(f, "chunk_factor_df_kernel");
+    } else {
+        launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), (size_t)(stage ? CH_SMEM_STAGED : CH_SMEM_BASE), f->stream,
+                   (const double*)f->Sig[f->cur], f->ld, dimp, (const int*)f->d_lmOf, (const double*)f->d_Cblk, (const double*)f->d_ytilde, j0, bc, r2, gin, gout, Yc,
+                   f->d_status, guard, (const double*)nullptr, TL_SLOT(f), stage, f->sigMap[f->cur]);
+        LAUNCH_CHECK(f, "chunk_factor_kernel");
+    }
+    return EQVIO_OK;
+}
+
 // performVisionUpdate (VIO_eqf.cpp:105-135) in the symmetric form, for the nm measured landmarks whose pixels are
 // in d_y and state indices in d_lmOf.  Every kernel returns at once when *guard != 0.
 // fuseGate: the gate launch carries the measurement rows (gate_meas_kernel); fuseEst: the lift also emits the state estimate.
@@ -1485,11 +1511,9 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                 double* Yc = Ybuf[c & 1];
                 cudaEvent_t evF = f->chunkEv[2 * c], evR = f->chunkEv[2 * c + 1];
                 f->pdlHold = (j0 == 0);  // chunk 0 follows meas_kernel, whose output the kernel stages ahead of its dependency wait
-                launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), (size_t)(f->stageS && f->haveSigMap ? CH_SMEM_STAGED : CH_SMEM_BASE), f->stream,
-                           f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Yc, f->d_status, guard, nullptr,
-                           TL_SLOT(f), f->stageS && f->haveSigMap ? 1 : 0, f->sigMap[f->cur]);
+                const int rc = launch_chunk_factor(f, ldy, dimp, j0, bc, r2, gin, gout, Yc, guard);
                 f->pdlHold = false;
-                LAUNCH_CHECK(f, "chunk_factor_kernel");
+                if (rc != EQVIO_OK) return rc;
                 std::swap(gin, gout);
                 if (c > 0) CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * (c - 1) + 1], 0));  // rest(c-1) done
                 if (c == nchunks - 1) {  // last chunk: everything, and full symmetric storage again
@@ -1528,12 +1552,10 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                 const int bc = std::min(bcMax, nm - j0);
                 int pk = prof_begin(f, PROF_PANEL);
                 f->pdlHold = (j0 == 0);  // chunk 0 follows meas_kernel, whose output the kernel stages ahead of its dependency wait
-                launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), (size_t)(f->stageS && f->haveSigMap ? CH_SMEM_STAGED : CH_SMEM_BASE), f->stream,
-                           f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Y, f->d_status, guard, nullptr,
-                           TL_SLOT(f), f->stageS && f->haveSigMap ? 1 : 0, f->sigMap[f->cur]);
+                const int rc = launch_chunk_factor(f, ldy, dimp, j0, bc, r2, gin, gout, Y, guard);
                 prof_end(f, pk);
                 f->pdlHold = false;
-                LAUNCH_CHECK(f, "chunk_factor_kernel");
+                if (rc != EQVIO_OK) return rc;
                 int sk = prof_begin(f, PROF_SYRK);
                 if (f->downdateTC) {
                     const int ncols = cdiv(ldy, TC_T) * TC_T;  // Y's pad columns up to ld are zero
@@ -1741,6 +1763,10 @@ int vision_phase_c(eqvio_filter* f, int* did_update) {
         f->err = "NaN detected in the correction";
         return EQVIO_ERR_NUMERIC;
     }
+    if (st & 8) {
+        f->err = "chunk factor kernel: a bounded device-side wait ran out";
+        return EQVIO_ERR_CUDA;
+    }
     if (did_update) *did_update = 1;
     f->estValid = wasSteady && !redone && !(st & 4);
     if (st & 4) {  // removeInvalidLandmarks, VIO_eqf.cpp:213-223
@@ -1787,6 +1813,8 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ChunkSmem) > (size_t)CH_SMEM_STAGED ? sizeof(ChunkSmem) : (size_t)CH_SMEM_STAGED));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_df_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf_smem_bytes<16>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_df_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf_smem_bytes<32>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Chunk2Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LOOK_SMEM);
     if (e != cudaSuccess) {
@@ -1797,6 +1825,7 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
     f->st = *s;
     f->device = device;
     f->cap = capacity;
+    if (cudaDeviceGetAttribute(&f->smCount, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || f->smCount <= 0) f->smCount = 148;
     if (stream) {
         f->stream = static_cast<cudaStream_t>(stream);
     } else {
@@ -2610,6 +2639,10 @@ int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
             return EQVIO_OK;
         case EQVIO_TUNE_STAGE_S:
             f->stageS = value != 0;
+            clear_graphs(f);
+            return EQVIO_OK;
+        case EQVIO_TUNE_FACTOR:
+            f->dfFactor = value != 0;
             clear_graphs(f);
             return EQVIO_OK;
         case EQVIO_TUNE_FUSE_SMALL:

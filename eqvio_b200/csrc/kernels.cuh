@@ -1661,6 +1661,8 @@ __global__ void __launch_bounds__(CH_THREADS)
     TL_MARK(tl, 1);
 }
 
+#include "chunk_factor_df.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // chunk_factor2_kernel / chunk_look_kernel: the CHAINED correction.  The sequential-chunk update is a block Cholesky of
 // S = C Sigma C^T + R whose trailing update is applied to Sigma.  The elimination of S_c does not have to wait for the

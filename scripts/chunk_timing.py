@@ -19,7 +19,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 sm = record_stream(SimConfig.benchmark(N, 0), 12)
 flt = eb.VIOFilter(eb.Settings(fastRiccati=1), eb.VIOState(eb.VIOSensorState.fromFlat(sm.init_sensor), sm.init_p, sm.init_ids), 0.0,
                    capacity=N + 8)
-flt.setTuning(graph=0, stageS=int(os.environ.get('EQVIO_STAGE', '1')))
+flt.setTuning(graph=0, stageS=int(os.environ.get('EQVIO_STAGE', '1')), factor=int(os.environ.get('EQVIO_FACTOR', '1')))
 cam = eb.Camera(**sm.camera)
 for fr in sm.frames:
     flt.processIMUArray(fr.imu)
@@ -30,8 +30,12 @@ fn.restype = C.c_int
 out = (C.c_longlong * 16)()
 assert fn(out) == 0
 t = np.array(list(out), dtype=np.int64)
-names = {0: "start", 1: "C/Idx loaded", 2: "S gather done", 3: "S loop done", 4: "final barrier", 5: "Yt staged", 6: "end", 7: "RHS wait done",
-         10: "look: Spre gathered", 8: "RHS gather done", 9: "RHS loop done"}
+factor = int(os.environ.get('EQVIO_FACTOR', '1'))
+flt_names_old = {0: "start", 1: "C/Idx loaded", 2: "S gather done", 3: "S loop done", 4: "final barrier", 5: "Yt staged", 6: "end",
+                 8: "RHS gather done", 9: "RHS loop done"}
+flt_names_df = {0: "start", 1: "C/Idx loaded", 2: "chain warp starts waiting", 3: "chain done", 4: "final barrier", 5: "Yt staged", 6: "end",
+                8: "S warp 3: tile projected", 9: "S warp 3: past the elimination"}
+names = flt_names_df if factor else flt_names_old
 base = t[0]
 for i in sorted(names):
     print(f"{names[i]:>18s}: {t[i] - base:8d} cycles")
@@ -42,7 +46,8 @@ if fine is not None:
     buf = (C.c_longlong * 128)()
     if fine(buf) == 0:
         f = np.array(list(buf), dtype=np.int64)
-        print("block column: diag-phase | barrier 1 | panel-phase + barrier 2 | trailing (thread 0's view; thread 0 owns tile (0,0))")
+        print("block column: diag-phase | barrier 1 | panel-phase + barrier 2 | trailing (thread 0's view; thread 0 owns tile (0,0))" if not factor else
+              "chain step: wait for the handed tiles | load + panel op + rank-4 update | eliminate + publish | 1/L_kk (chain warp)")
         for J in range(16):
             a, b, c, d = f[4 * J:4 * J + 4]
             nxt = f[4 * J + 4] if J < 15 else d

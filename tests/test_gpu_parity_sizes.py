@@ -148,15 +148,19 @@ def test_euroc_switch_set(N, frames):
     assert removed > 0, "the YAML's probabilistic threshold (0.032) trips on noisy pixels"
 
 
-def test_remove_invalid_landmarks():
+@pytest.mark.parametrize("discrete,tol", [(False, 1e-9), (True, 1e-3)])
+def test_remove_invalid_landmarks(discrete, tol):
     """VIO_eqf.cpp:213-223: a landmark whose scale Q.a leaves (1e-8, 1e8] is dropped after the update.  Two landmarks start a
-    thousand times too close to the camera with a large point variance and the continuous InvDepth innovation lift: the
-    first parallax drives their inverse-depth innovation far enough that exp(w) underflows the lower bound."""
+    billion times too far along their bearing (InvDepth chart: inverse depth ~1e-9 with unit variance, so the update stays
+    well conditioned); the first parallax brings their estimates back to metres, i.e. Q.a = |q0| / |p| beyond 1e8 -- with the
+    continuous lift exp() even overflows to inf, which the reference's comparison also catches.  The discrete-lift case crosses
+    the bound one update later, after an update whose two oracle evaluation orders already differ by 7e-6 (checked on the
+    CPU), hence its loose value tolerance; the discrete decisions (ids) must match exactly in both."""
     from oracle import eqf
 
-    stream = make_stream(N=16, frames=10, coord=1, settings_overrides=dict(useDiscreteInnovationLift=False, initialPointVariance=100.0))
-    stream["init"].p[3] *= 1e-3
-    stream["init"].p[7] *= 1e-3
+    stream = make_stream(N=16, frames=8, coord=1, settings_overrides=dict(useDiscreteInnovationLift=discrete))
+    stream["init"].p[3] *= 1e9
+    stream["init"].p[7] *= 1e9
     dropped = []
     orig = eqf.VIO_eqf.removeInvalidLandmarks
 
@@ -167,10 +171,11 @@ def test_remove_invalid_landmarks():
 
     eqf.VIO_eqf.removeInvalidLandmarks = counting
     try:
-        _lockstep(stream, augment=True, tol=1e-7)
+        with np.errstate(over="ignore"):
+            _lockstep(stream, augment=True, tol=tol)
     finally:
         eqf.VIO_eqf.removeInvalidLandmarks = orig
-    assert sum(dropped) > 0, "the case is meant to trip removeInvalidLandmarks in the oracle"
+    assert sum(dropped) == 2, "the case is meant to trip removeInvalidLandmarks for both landmarks in the oracle"
 
 
 @pytest.mark.parametrize("graph", [1, 0])
@@ -201,3 +206,19 @@ def test_vision_dropout_replays_graphs_with_many_imu_segments():
     assert max(len(f.imu) for f in seq) > 128
     worst, _, _ = _lockstep(stream, augment=True, frames=seq)
     print(f"drop-out sequence: worst {worst:.3e}")
+
+
+@pytest.mark.parametrize("N,chunk,coord,frames", [(40, 32, 0, 12), (100, 32, 1, 8), (150, 32, 0, 8), (70, 5, 0, 8), (33, 32, 0, 8),
+                                                  (256, 32, 0, 4), (21, 7, 1, 8)])
+@pytest.mark.parametrize("graph", [1, 0])
+def test_dataflow_factor_kernel_is_bit_identical(N, chunk, coord, frames, graph):
+    """chunk_factor_df_kernel (chain warp + per-tile flags, the default) runs the arithmetic of the round-1 barrier-synchronised
+    chunk_factor_kernel in the same order: identical bits along a sequence -- full and ragged chunks, 16 and 32 state columns
+    per CTA, staged and gathered S blocks -- and parity with the oracle."""
+    stream = make_stream(N=N, frames=frames, coord=coord)
+    old = run_gpu(stream, tuning=dict(factor=0, graph=0, chunkLandmarks=chunk))
+    new = run_gpu(stream, tuning=dict(factor=1, graph=graph, chunkLandmarks=chunk))
+    for k, (g, r) in enumerate(zip(new, old)):
+        e = compare_states(g, r)
+        assert e["ids_equal"] and e["sigma"] == 0.0 and e["state"] == 0.0, f"update {k}: {e}"
+    _check(new, run_oracle(stream, structured=N > 100))
