@@ -265,8 +265,8 @@ int eqvio_get_host_profile(eqvio_filter* f, int reset, double us[4], long long* 
  *     owner gathers its 36 entries itself (also the fall-back for non-consecutive chunks).  Same entries, bit-identical results. */
 #define EQVIO_TUNE_STAGE_S 12
 /*   EQVIO_TUNE_FACTOR: 1 (default) = dataflow chunk factor kernel (chunk_factor_df_kernel: the 64 pivots of a chunk walked by one
- *     chain warp, per-tile release / acquire flags instead of CTA-wide barriers); 0 = the barrier-synchronised kernel of round 1.
- *     Same arithmetic in the same order: bit-identical results. */
+ *     chain warp, tiles handed over through write-once shared memory words instead of CTA-wide barriers); 0 = the
+ *     barrier-synchronised kernel of round 1.  Same arithmetic in the same order: bit-identical results. */
 #define EQVIO_TUNE_FACTOR 13
 int eqvio_set_tuning(eqvio_filter* f, int key, int value);
 /* Version / build info string (arch the kernels were compiled for). */

@@ -47,7 +47,7 @@ if fine is not None:
     if fine(buf) == 0:
         f = np.array(list(buf), dtype=np.int64)
         print("block column: diag-phase | barrier 1 | panel-phase + barrier 2 | trailing (thread 0's view; thread 0 owns tile (0,0))" if not factor else
-              "chain step: wait for the handed tiles | load + panel op + rank-4 update | eliminate + publish | 1/L_kk (chain warp)")
+              "chain step: wait for the handed tiles | load + panel op + rank-4 update | eliminate + publish | loop back (chain warp)")
         for J in range(16):
             a, b, c, d = f[4 * J:4 * J + 4]
             nxt = f[4 * J + 4] if J < 15 else d
