@@ -127,7 +127,7 @@ struct eqvio_filter {
     bool pdlHold = false;  // next launch_pdl is a plain launch (its predecessor produces what the kernel reads before its wait)
     int pdl = 1;           // chunk kernels are launched with programmatic dependent launch allowed
     int specNew = 1;       // frames with new ids also speculate (new-landmark positions computed on the device)
-    int dfFactor = 1;      // dataflow chunk factor kernel (chunk_factor_df_kernel) instead of the barrier-synchronised one
+    int dfFactor = 2;      // chunk factor kernel: 2 = DMMA fragments (chunk_factor_mma_kernel), 1 = dataflow 4x4 tiles, 0 = round-1 kernel
     int stageS = 1;        // chunk factor kernel: Sigma[L_c, L_c] as one TMA tensor copy when the chunk is contiguous in the state
     int *d_keepI = nullptr, *d_newMeas = nullptr;
     int newMeasCap = 0;
@@ -1354,7 +1354,17 @@ int launch_correction(eqvio_filter* f, const int* guard) {
 int launch_chunk_factor(eqvio_filter* f, int ldy, int dimp, int j0, int bc, double r2, const double* gin, double* gout, double* Yc,
                         const int* guard) {
     const int stage = f->stageS && f->haveSigMap ? 1 : 0;
-    if (f->dfFactor) {
+    if (f->dfFactor == 2) {
+        if (ldy / 16 <= f->smCount)
+            launch_pdl(f, chunk_factor_mma_kernel<16>, dim3(ldy / 16), dim3(MM_THREADS), (size_t)mm_smem_bytes<16>(), f->stream,
+                       (const double*)f->Sig[f->cur], f->ld, dimp, (const int*)f->d_lmOf, (const double*)f->d_Cblk, (const double*)f->d_ytilde, j0, bc, r2,
+                       gin, gout, Yc, f->d_status, guard, TL_SLOT(f), stage, f->sigMap[f->cur]);
+        else
+            launch_pdl(f, chunk_factor_mma_kernel<32>, dim3(ldy / 32), dim3(MM_THREADS), (size_t)mm_smem_bytes<32>(), f->stream,
+                       (const double*)f->Sig[f->cur], f->ld, dimp, (const int*)f->d_lmOf, (const double*)f->d_Cblk, (const double*)f->d_ytilde, j0, bc, r2,
+                       gin, gout, Yc, f->d_status, guard, TL_SLOT(f), stage, f->sigMap[f->cur]);
+        LAUNCH_CHECK(f, "chunk_factor_mma_kernel");
+    } else if (f->dfFactor) {
         if (ldy / 16 <= f->smCount)
             launch_pdl(f, chunk_factor_df_kernel<16>, dim3(ldy / 16), dim3(CF_THREADS), (size_t)cf_smem_bytes<16>(), f->stream,
                        (const double*)f->Sig[f->cur], f->ld, dimp, (const int*)f->d_lmOf, (const double*)f->d_Cblk, (const double*)f->d_ytilde, j0, bc, r2,
@@ -1813,6 +1823,8 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ChunkSmem) > (size_t)CH_SMEM_STAGED ? sizeof(ChunkSmem) : (size_t)CH_SMEM_STAGED));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mm_smem_bytes<16>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mm_smem_bytes<32>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_df_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf_smem_bytes<16>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_df_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf_smem_bytes<32>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Chunk2Smem));
@@ -2642,7 +2654,8 @@ int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
             clear_graphs(f);
             return EQVIO_OK;
         case EQVIO_TUNE_FACTOR:
-            f->dfFactor = value != 0;
+            if (value < 0 || value > 2) return EQVIO_ERR_INVALID_ARG;
+            f->dfFactor = value;
             clear_graphs(f);
             return EQVIO_OK;
         case EQVIO_TUNE_FUSE_SMALL:

@@ -1662,6 +1662,7 @@ __global__ void __launch_bounds__(CH_THREADS)
 }
 
 #include "chunk_factor_df.cuh"
+#include "chunk_factor_mma.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // chunk_factor2_kernel / chunk_look_kernel: the CHAINED correction.  The sequential-chunk update is a block Cholesky of

@@ -264,9 +264,10 @@ int eqvio_get_host_profile(eqvio_filter* f, int reset, double us[4], long long* 
  *     CUtensorMap over the covariance) into shared memory when the chunk's landmarks are consecutive in the state; 0 = every tile
  *     owner gathers its 36 entries itself (also the fall-back for non-consecutive chunks).  Same entries, bit-identical results. */
 #define EQVIO_TUNE_STAGE_S 12
-/*   EQVIO_TUNE_FACTOR: 1 (default) = dataflow chunk factor kernel (chunk_factor_df_kernel: the 64 pivots of a chunk walked by one
- *     chain warp, tiles handed over through write-once shared memory words instead of CTA-wide barriers); 0 = the
- *     barrier-synchronised kernel of round 1.  Same arithmetic in the same order: bit-identical results. */
+/*   EQVIO_TUNE_FACTOR: chunk factor kernel.  2 (default) = chunk_factor_mma_kernel: the augmented matrix of a chunk in
+ *     mma.sync.m8n8k4.f64 accumulator fragments, one DMMA per 8x8 tile and block column for the trailing update; 1 =
+ *     chunk_factor_df_kernel: 4x4 register tiles, warp-specialised dataflow through single-use mbarriers; 0 = the
+ *     barrier-synchronised 4x4-tile kernel of round 1 (1 and 0 agree bit for bit, 2 to rounding). */
 #define EQVIO_TUNE_FACTOR 13
 int eqvio_set_tuning(eqvio_filter* f, int key, int value);
 /* Version / build info string (arch the kernels were compiled for). */

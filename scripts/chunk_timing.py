@@ -36,6 +36,8 @@ flt_names_old = {0: "start", 1: "C/Idx loaded", 2: "S gather done", 3: "S loop d
 flt_names_df = {0: "start", 1: "C/Idx loaded", 2: "chain warp starts waiting", 3: "chain done", 4: "final barrier", 5: "Yt staged", 6: "end",
                 8: "S warp 3: tile projected", 9: "S warp 3: past the elimination"}
 names = flt_names_df if factor else flt_names_old
+if factor == 2:
+    names = {0: 'start', 1: 'C/Idx loaded', 2: 'tiles initialised', 3: 'elimination done', 4: '1/L_kk', 5: 'Yt staged', 6: 'end'}
 base = t[0]
 for i in sorted(names):
     print(f"{names[i]:>18s}: {t[i] - base:8d} cycles")
@@ -47,7 +49,8 @@ if fine is not None:
     if fine(buf) == 0:
         f = np.array(list(buf), dtype=np.int64)
         print("block column: diag-phase | barrier 1 | panel-phase + barrier 2 | trailing (thread 0's view; thread 0 owns tile (0,0))" if not factor else
-              "chain step: wait for the handed tiles | load + panel op + rank-4 update | eliminate + publish | loop back (chain warp)")
+              ("chain step: wait for the handed tiles | load + panel op + rank-4 update | eliminate + publish | loop back (chain warp)" if factor == 1 else
+               "block column (thread 0): diagonal phase | barrier | panel phase + barrier | trailing DMMAs"))
         for J in range(16):
             a, b, c, d = f[4 * J:4 * J + 4]
             nxt = f[4 * J + 4] if J < 15 else d
