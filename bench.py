@@ -88,8 +88,6 @@ def parse():
                     help="extra leg of the single-GPU, single-sequence run: this many independent sequences replayed concurrently on "
                          "the GPU (BASELINE configs[4]: 16 Monte-Carlo instances per GPU), reported as \"batched\"; 0 = skip")
     ap.add_argument("--no-graph", action="store_true", help="issue per-kernel launches instead of replaying CUDA graphs")
-    ap.add_argument("--pipeline", action="store_true", help="experimental: overlap chunk c+1's factor kernel with chunk c's downdate")
-    ap.add_argument("--chain", type=int, default=None, help="EQVIO_TUNE_CHAIN (experimental chained correction): 0 / 1 / 2")
     ap.add_argument("--no-stage", action="store_true", help="chunk factor kernel gathers Sigma[L_c, L_c] itself instead of the TMA tensor copy")
     ap.add_argument("--no-lookahead", action="store_true", help="one in-order downdate launch per chunk (no band / rest split)")
     ap.add_argument("--downdate", default="f64", choices=["f64", "tc"],
@@ -323,10 +321,6 @@ def run_b200(args, rank, local_rank, world, guard):
         flt.enableStageTiming(True)
         if args.no_graph:
             flt.setTuning(graph=0)
-        if args.pipeline:
-            flt.setTuning(pipeline=1)
-        if args.chain is not None:
-            flt.setTuning(chain=args.chain)
         if args.no_lookahead:
             flt.setTuning(lookahead=0)
         if args.no_stage:

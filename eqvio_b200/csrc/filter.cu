@@ -118,16 +118,12 @@ struct eqvio_filter {
     unsigned char* d_Ysplit = nullptr;
     int lazyMirror = 1;  // downdate refreshes the upper triangle only where the next chunk reads it
     std::vector<int> h_lmOfSorted;  // state indices of the correction rows (host copy of d_lmOf)
-    int chain = 0;         // 0 = off (default); 2 = chained correction kernels in stream order; 1 = with concurrent downdates (experimental)
     double* d_normalM = nullptr;  // Normal chart: sensor block of the coordinate differential and its inverse (2 x 441)
-    int* d_cnt = nullptr;  // per-chunk completion counters of the downdates (chained correction)
-    double* d_Snext[2] = {nullptr, nullptr};  // S block handed from one factor launch to the next
     int prLeast = 0, prGreatest = 0;  // stream priority range of the device
     int smCount = 148;                // SMs of the device (grid sizing)
     bool pdlHold = false;  // next launch_pdl is a plain launch (its predecessor produces what the kernel reads before its wait)
     int pdl = 1;           // chunk kernels are launched with programmatic dependent launch allowed
     int specNew = 1;       // frames with new ids also speculate (new-landmark positions computed on the device)
-    int dfFactor = 2;      // chunk factor kernel: 2 = DMMA fragments (chunk_factor_mma_kernel), 1 = dataflow 4x4 tiles, 0 = round-1 kernel
     int stageS = 1;        // chunk factor kernel: Sigma[L_c, L_c] as one TMA tensor copy when the chunk is contiguous in the state
     int *d_keepI = nullptr, *d_newMeas = nullptr;
     int newMeasCap = 0;
@@ -139,7 +135,6 @@ struct eqvio_filter {
     long long hostCalls = 0;
     double hostWaitUs = 0;
     int lookahead = 2;   // 2 = automatic (on when the tile grid spans more than one wave, T >= 24), 1 = on, 0 = off: split each downdate into the tiles the next chunk gathers (urgent) and the rest (beside the next factor)
-    int pipeline = 0;    // experimental: overlap chunk c+1's factor kernel with chunk c's (out-of-place) downdate
     double* d_Y2 = nullptr;
     std::vector<cudaEvent_t> chunkEv;
     int* d_spec = nullptr;  // [0] set by the gate kernel when any measured landmark exceeds a threshold, [1] constant 0
@@ -518,9 +513,6 @@ int alloc_device(eqvio_filter* f) {
     f->d_out = reinterpret_cast<double*>(f->d_outblk + f->outOffEst);
     CUDA_TRY(f, cudaMalloc(&f->d_normalM, 2 * 441 * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_keepI, c1 * sizeof(int)));
-    CUDA_TRY(f, cudaMalloc(&f->d_cnt, 2 * (c1 + 1) * sizeof(int)));
-    CUDA_TRY(f, cudaMemsetAsync(f->d_cnt, 0, 2 * (c1 + 1) * sizeof(int), f->stream));
-    for (int k = 0; k < 2; ++k) CUDA_TRY(f, cudaMalloc(&f->d_Snext[k], CH_R * CH_R * sizeof(double)));
     // landmark-set changes arrive as ONE block: new positions | old-index map | new ids  (a single upload per change)
     f->mapBlkBytes = c1 * (3 * sizeof(double) + 2 * sizeof(int));
     CUDA_TRY(f, cudaMalloc(&f->d_mapblk, f->mapBlkBytes));
@@ -1349,37 +1341,14 @@ int launch_correction(eqvio_filter* f, const int* guard) {
     return EQVIO_OK;
 }
 
-// One chunk factor launch (S_c, its elimination, Y_c, Gamma): the dataflow kernel by default, the round-1 kernel behind
-// EQVIO_TUNE_FACTOR = 0.  COLS = 16 state columns per CTA while that stays within one wave of CTAs, else 32.
+// One chunk factor launch (S_c, its elimination, Y_c, Gamma).
 int launch_chunk_factor(eqvio_filter* f, int ldy, int dimp, int j0, int bc, double r2, const double* gin, double* gout, double* Yc,
                         const int* guard) {
     const int stage = f->stageS && f->haveSigMap ? 1 : 0;
-    if (f->dfFactor == 2) {
-        if (ldy / 16 <= f->smCount)
-            launch_pdl(f, chunk_factor_mma_kernel<16>, dim3(ldy / 16), dim3(MM_THREADS), (size_t)mm_smem_bytes<16>(), f->stream,
-                       (const double*)f->Sig[f->cur], f->ld, dimp, (const int*)f->d_lmOf, (const double*)f->d_Cblk, (const double*)f->d_ytilde, j0, bc, r2,
-                       gin, gout, Yc, f->d_status, guard, TL_SLOT(f), stage, f->sigMap[f->cur]);
-        else
-            launch_pdl(f, chunk_factor_mma_kernel<32>, dim3(ldy / 32), dim3(MM_THREADS), (size_t)mm_smem_bytes<32>(), f->stream,
-                       (const double*)f->Sig[f->cur], f->ld, dimp, (const int*)f->d_lmOf, (const double*)f->d_Cblk, (const double*)f->d_ytilde, j0, bc, r2,
-                       gin, gout, Yc, f->d_status, guard, TL_SLOT(f), stage, f->sigMap[f->cur]);
-        LAUNCH_CHECK(f, "chunk_factor_mma_kernel");
-    } else if (f->dfFactor) {
-        if (ldy / 16 <= f->smCount)
-            launch_pdl(f, chunk_factor_df_kernel<16>, dim3(ldy / 16), dim3(CF_THREADS), (size_t)cf_smem_bytes<16>(), f->stream,
-                       (const double*)f->Sig[f->cur], f->ld, dimp, (const int*)f->d_lmOf, (const double*)f->d_Cblk, (const double*)f->d_ytilde, j0, bc, r2,
-                       gin, gout, Yc, f->d_status, guard, TL_SLOT(f), stage, f->sigMap[f->cur]);
-        else
-            launch_pdl(f, chunk_factor_df_kernel<32>, dim3(ldy / 32), dim3(CF_THREADS), (size_t)cf_smem_bytes<32>(), f->stream,
-                       (const double*)f->Sig[f->cur], f->ld, dimp, (const int*)f->d_lmOf, (const double*)f->d_Cblk, (const double*)f->d_ytilde, j0, bc, r2,
-                       gin, gout, Yc, f->d_status, guard, TL_SLOT(f), stage, f->sigMap[f->cur]);
-        LAUNCH_CHECK(f, "chunk_factor_df_kernel");
-    } else {
-        launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), (size_t)(stage ? CH_SMEM_STAGED : CH_SMEM_BASE), f->stream,
-                   (const double*)f->Sig[f->cur], f->ld, dimp, (const int*)f->d_lmOf, (const double*)f->d_Cblk, (const double*)f->d_ytilde, j0, bc, r2, gin, gout, Yc,
-                   f->d_status, guard, (const double*)nullptr, TL_SLOT(f), stage, f->sigMap[f->cur]);
-        LAUNCH_CHECK(f, "chunk_factor_kernel");
-    }
+    launch_pdl(f, chunk_factor_kernel, dim3(ldy / CH_COLS), dim3(CH_THREADS), (size_t)(stage ? CH_SMEM_STAGED : CH_SMEM_BASE), f->stream,
+               (const double*)f->Sig[f->cur], f->ld, dimp, (const int*)f->d_lmOf, (const double*)f->d_Cblk, (const double*)f->d_ytilde, j0, bc, r2, gin, gout, Yc,
+               f->d_status, guard, TL_SLOT(f), stage, f->sigMap[f->cur]);
+    LAUNCH_CHECK(f, "chunk_factor_kernel");
     return EQVIO_OK;
 }
 
@@ -1406,7 +1375,6 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
         double* Y = f->d_Z;
         double* gin = f->d_Gamma;
         double* gout = f->d_Gamma2;
-        const int nchunksAll = cdiv(nm, std::max(1, std::min(f->chunkLm, CH_R / 2)));
         // also clears the status words and Gamma (no memset nodes between the kernels of the update)
         if (fuseGate) {
             // one launch: gate CTAs (per state landmark) | measurement-row CTAs (per measured landmark); the rows are built
@@ -1416,93 +1384,18 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                        (const double*)f->Sig[f->cur], f->ld, (const int*)f->d_measIdx, (const double*)f->d_y, (const FrameHeader*)f->d_hdr,
                        (int)s.coordinateChoice, f->d_gate, s.outlierThresholdAbs, s.outlierThresholdProb, f->d_spec, (const int*)f->d_lmOf, nm,
                        (const double*)f->d_y, s.useEquivariantOutput ? 1 : 0, f->d_Cblk, f->d_ytilde, 1, 0, (const int*)(f->d_spec + 1),
-                       (const int*)f->d_yIdx, f->d_status, 1 + Nn, gin, dimp, f->d_cnt, 2 * nchunksAll, TL_SLOT(f));
+                       (const int*)f->d_yIdx, f->d_status, 1 + Nn, gin, dimp, (int*)nullptr, 0, TL_SLOT(f));
             LAUNCH_CHECK(f, "gate_meas_kernel");
         } else {
         meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
                                                           s.useEquivariantOutput ? 1 : 0, f->d_Cblk, f->d_ytilde, 1, 0, guard, f->d_yIdx,
-                                                          f->d_status, 1 + Nn, gin, dimp, f->d_cnt, 2 * nchunksAll, TL_SLOT(f));
+                                                          f->d_status, 1 + Nn, gin, dimp, (int*)nullptr, 0, TL_SLOT(f));
         LAUNCH_CHECK(f, "meas_kernel");
         }
         const int bcMax = std::max(1, std::min(f->chunkLm, CH_R / 2));
         const int nchunks = cdiv(nm, bcMax);
-        const bool pipe = f->pipeline && nchunks > 1 && !f->profiling;
-        const bool look = !pipe && (f->lookahead == 1 || (f->lookahead == 2 && T >= 24)) && nchunks > 1 && !f->profiling && !f->downdateTC;
-        const bool chain = f->chain != 0 && !pipe && !f->downdateTC;
-        if (chain) {
-            // Chained correction (see chunk_factor2_kernel).  Three streams:
-            //   f->stream2: look(c)    after look(c-1) [stream order]; its RHS warps after downdate(c-1) [counter]
-            //   f->stream : factor(c)  after factor(c-1) [stream order] and look(c-1) [event: S_c]; RHS warps after downdate(c-1)
-            //   f->stream3: downdate(c) after factor(c) [event] and downdate(c-1) [stream order]
-            // Y buffers alternate: factor(c+2) writes Y_{c&1} after its RHS warps saw downdate(c+1) (hence downdate(c)) done;
-            // the S hand-over buffers alternate the same way (look(c+2) finishes after downdate(c+1), i.e. after factor(c+1)).
-            const bool serial = f->chain == 2 || f->profiling;  // serial: one stream, no counter waits
-            while ((int)f->chunkEv.size() < 2 * nchunks + 2) {
-                cudaEvent_t e;
-                CUDA_TRY(f, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-                f->chunkEv.push_back(e);
-            }
-            double* Ybuf[2] = {f->d_Z, f->d_Y2};
-            const int* lo = f->h_lmOfSorted.data();
-            const int nTiles = T * (T + 1) / 2;
-            cudaStream_t sLook = serial ? f->stream : f->stream2, sDown = serial ? f->stream : f->stream3;
-            if (!serial && nchunks > 1) {  // fork: the look-ahead stream starts behind everything enqueued so far
-                CUDA_TRY(f, cudaEventRecord(f->chunkEv[2 * nchunks], f->stream));
-                CUDA_TRY(f, cudaStreamWaitEvent(f->stream2, f->chunkEv[2 * nchunks], 0));
-            }
-            for (int c = 0; c < nchunks; ++c) {
-                const int j0 = c * bcMax;
-                const int bc = std::min(bcMax, nm - j0);
-                const int nb = c + 1 < nchunks ? std::min(bcMax, nm - (j0 + bcMax)) : 0;
-                double* Yc = Ybuf[c & 1];
-                const int* waitCnt = (c > 0 && !serial) ? f->d_cnt + (c - 1) : nullptr;
-                const double* Sin = c > 0 ? f->d_Snext[c & 1] : nullptr;
-                if (nb > 0) {
-                    f->pdlHold = c == 0;
-                    launch_pdl(f, chunk_factor2_kernel<true>, dim3(1), dim3(LOOK_THREADS), LOOK_SMEM, sLook,
-                               (const double*)f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, nb, r2, (const double*)nullptr,
-                               (double*)nullptr, (double*)nullptr, f->d_status, guard, Sin, f->d_Snext[(c + 1) & 1], waitCnt, nTiles,
-                               serial ? (int*)nullptr : f->d_cnt + nchunks + c, TL_SLOT(f));
-                    f->pdlHold = false;
-                    LAUNCH_CHECK(f, "chunk_look_kernel");
-                    if (!serial) CUDA_TRY(f, cudaEventRecord(f->chunkEv[2 * c + 1], f->stream2));
-                }
-                if (c > 0 && !serial) CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * (c - 1) + 1], 0));  // S_c from look(c-1)
-                int pk = prof_begin(f, PROF_PANEL);
-                f->pdlHold = c == 0;  // chunk 0 follows meas_kernel, whose Cblk the kernel reads ahead of its dependency wait
-                launch_pdl(f, chunk_factor2_kernel<false>, dim3(ldy / CH_COLS), dim3(CH_THREADS), sizeof(Chunk2Smem), f->stream,
-                           (const double*)f->Sig[f->cur], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, nb, r2, (const double*)gin, gout, Yc,
-                           f->d_status, guard, Sin, (double*)nullptr, waitCnt, nTiles, (int*)nullptr, TL_SLOT(f));
-                f->pdlHold = false;
-                prof_end(f, pk);
-                LAUNCH_CHECK(f, "chunk_factor2_kernel");
-                std::swap(gin, gout);
-                int mlo = 0, mhi = T;
-                if (nb > 0 && f->lazyMirror) {
-                    int rmin = lo[j0 + bcMax], rmax = rmin;
-                    for (int q = 1; q < nb; ++q) {
-                        rmin = std::min(rmin, lo[j0 + bcMax + q]);
-                        rmax = std::max(rmax, lo[j0 + bcMax + q]);
-                    }
-                    mlo = (SOFF + 3 * rmin) / DD_T;
-                    mhi = (SOFF + 3 * rmax + 2) / DD_T;
-                }
-                int sk = prof_begin(f, PROF_SYRK);
-                if (!serial) {
-                    CUDA_TRY(f, cudaEventRecord(f->chunkEv[2 * c], f->stream));
-                    CUDA_TRY(f, cudaStreamWaitEvent(f->stream3, f->chunkEv[2 * c], 0));
-                }
-                launch_pdl(f, chunk_downdate_kernel, dim3(nTiles), dim3(DD_THREADS), DD_SMEM, sDown, (const double*)f->Sig[f->cur], f->Sig[f->cur],
-                           f->ld, (const double*)Yc, guard, mlo, mhi, (int)DD_ALL, T, TL_SLOT(f), serial ? (int*)nullptr : f->d_cnt + c,
-                           (!serial && nb > 0) ? (const int*)(f->d_cnt + nchunks + c) : (const int*)nullptr);
-                prof_end(f, sk);
-                LAUNCH_CHECK(f, "chunk_downdate_kernel");
-            }
-            if (!serial) {
-                CUDA_TRY(f, cudaEventRecord(f->chunkEv[2 * nchunks + 1], f->stream3));
-                CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * nchunks + 1], 0));
-            }
-        } else if (look) {
+        const bool look = (f->lookahead == 1 || (f->lookahead == 2 && T >= 24)) && nchunks > 1 && !f->profiling && !f->downdateTC;
+        if (look) {
             // Look-ahead: factor(c+1) only gathers the tile rows / columns of ITS landmarks (the band).  downdate(c) is split
             // into the band tiles (urgent, f->stream) and all other lower tiles (deferred, f->stream3, beside factor(c+1)).
             //   band(c)   after factor(c) [stream order] and rest(c-1) [event: both write the band of chunk c+1]
@@ -1528,7 +1421,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                 if (c > 0) CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * (c - 1) + 1], 0));  // rest(c-1) done
                 if (c == nchunks - 1) {  // last chunk: everything, and full symmetric storage again
                     chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Yc, guard,
-                                                                                              0, T, DD_ALL, T, TL_SLOT(f), nullptr, nullptr);
+                                                                                              0, T, DD_ALL, T, TL_SLOT(f));
                     LAUNCH_CHECK(f, "chunk_downdate_kernel");
                     break;
                 }
@@ -1545,19 +1438,19 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                 const int nRest = (T - w) * (T - w + 1) / 2;
                 CUDA_TRY(f, cudaEventRecord(evF, f->stream));
                 chunk_downdate_kernel<<<nBand, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Yc, guard, mlo, mhi,
-                                                                                 DD_BAND, T, TL_SLOT(f), nullptr, nullptr);
+                                                                                 DD_BAND, T, TL_SLOT(f));
                 LAUNCH_CHECK(f, "chunk_downdate_kernel");
                 CUDA_TRY(f, cudaStreamWaitEvent(f->stream3, evF, 0));
                 if (nRest > 0) {
                     f->pdlHold = true;
                     launch_pdl(f, chunk_downdate_kernel, dim3(nRest), dim3(DD_THREADS), (size_t)DD_SMEM, f->stream3, (const double*)f->Sig[f->cur],
-                               f->Sig[f->cur], f->ld, (const double*)Yc, guard, mlo, mhi, (int)DD_REST, T, TL_SLOT(f), (int*)nullptr, (const int*)nullptr);
+                               f->Sig[f->cur], f->ld, (const double*)Yc, guard, mlo, mhi, (int)DD_REST, T, TL_SLOT(f));
                     f->pdlHold = false;
                     LAUNCH_CHECK(f, "chunk_downdate_kernel");
                 }
                 CUDA_TRY(f, cudaEventRecord(evR, f->stream3));
             }
-        } else if (!pipe) {
+        } else {
             for (int j0 = 0; j0 < nm; j0 += bcMax) {
                 const int bc = std::min(bcMax, nm - j0);
                 int pk = prof_begin(f, PROF_PANEL);
@@ -1593,48 +1486,12 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                         mhi = (SOFF + 3 * rmax + 2) / DD_T;
                     }
                     launch_pdl(f, chunk_downdate_kernel, dim3(T * (T + 1) / 2), dim3(DD_THREADS), DD_SMEM, f->stream, f->Sig[f->cur],
-                               f->Sig[f->cur], f->ld, Y, guard, mlo, mhi, (int)DD_ALL, T, TL_SLOT(f), (int*)nullptr, (const int*)nullptr);
+                               f->Sig[f->cur], f->ld, Y, guard, mlo, mhi, (int)DD_ALL, T, TL_SLOT(f));
                     LAUNCH_CHECK(f, "chunk_downdate_kernel");
                 }
                 prof_end(f, sk);
                 std::swap(gin, gout);
             }
-        } else {
-            // Pipelined: factor(c+1) runs on f->stream while downdate(c) runs on f->stream2.  downdate(c) reads the
-            // covariance buffer of chunk c and writes the other one; factor(c+1) reads the same (stable) input buffer
-            // and folds the pending downdate in from Y_c.  Dependencies:
-            //   downdate(c)  after factor(c) [event] and downdate(c-1) [stream order]
-            //   factor(c+1)  after factor(c) [stream order] and downdate(c-1) [event]
-            while ((int)f->chunkEv.size() < 2 * nchunks) {
-                cudaEvent_t e;
-                CUDA_TRY(f, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-                f->chunkEv.push_back(e);
-            }
-            double* Ybuf[2] = {f->d_Z, f->d_Y2};
-            int sin = f->cur;
-            for (int c = 0; c < nchunks; ++c) {
-                const int j0 = c * bcMax;
-                const int bc = std::min(bcMax, nm - j0);
-                cudaEvent_t evF = f->chunkEv[2 * c], evD = f->chunkEv[2 * c + 1];
-                if (c >= 2) CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * (c - 2) + 1], 0));  // downdate(c-2) done
-                // factor(c) reads the INPUT buffer of downdate(c-1) (stable while that downdate runs) and folds Y_{c-1} in
-                const int cfIn = c == 0 ? sin : 1 - sin;
-                chunk_factor_kernel<<<ldy / CH_COLS, CH_THREADS, sizeof(ChunkSmem), f->stream>>>(
-                    f->Sig[cfIn], f->ld, dimp, f->d_lmOf, f->d_Cblk, f->d_ytilde, j0, bc, r2, gin, gout, Ybuf[c & 1], f->d_status, guard,
-                    c > 0 ? Ybuf[(c - 1) & 1] : nullptr, TL_SLOT(f), 0, f->sigMap[cfIn]);
-                f->pdlHold = false;
-                LAUNCH_CHECK(f, "chunk_factor_kernel");
-                CUDA_TRY(f, cudaEventRecord(evF, f->stream));
-                CUDA_TRY(f, cudaStreamWaitEvent(f->stream2, evF, 0));
-                chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream2>>>(f->Sig[sin], f->Sig[1 - sin], f->ld, Ybuf[c & 1],
-                                                                                           guard, 0, T, DD_ALL, T, TL_SLOT(f), nullptr, nullptr);
-                LAUNCH_CHECK(f, "chunk_downdate_kernel");
-                CUDA_TRY(f, cudaEventRecord(evD, f->stream2));
-                std::swap(gin, gout);
-                sin = 1 - sin;  // downdate(c+1) reads what downdate(c) wrote
-            }
-            CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * (nchunks - 1) + 1], 0));  // join the last downdate
-            f->cur = sin;  // the final covariance lives in the last downdate's output buffer
         }
         gammaFinal = gin;
     } else {
@@ -1823,12 +1680,6 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ChunkSmem) > (size_t)CH_SMEM_STAGED ? sizeof(ChunkSmem) : (size_t)CH_SMEM_STAGED));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mm_smem_bytes<16>());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mm_smem_bytes<32>());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_df_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf_smem_bytes<16>());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_df_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, cf_smem_bytes<32>());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Chunk2Smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LOOK_SMEM);
     if (e != cudaSuccess) {
         g_createError = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
         return EQVIO_ERR_CUDA;
@@ -2070,12 +1921,9 @@ void eqvio_destroy(eqvio_filter* f) {
     if (f->h_frame) cudaFreeHost(f->h_frame);
     if (f->h_out) cudaFreeHost(f->h_out);
     cudaFree(f->d_outblk);
-    cudaFree(f->d_cnt);
     cudaFree(f->d_normalM);
     cudaFree(f->d_keepI);
     cudaFree(f->d_newMeas);
-    cudaFree(f->d_Snext[0]);
-    cudaFree(f->d_Snext[1]);
     for (auto& g : f->graphs)
         if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     cudaFree(f->d_mapblk);
@@ -2637,25 +2485,11 @@ int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
             f->downdateTC = value;
             clear_graphs(f);
             return EQVIO_OK;
-        case EQVIO_TUNE_PIPELINE:
-            f->pipeline = value != 0;
-            clear_graphs(f);
-            return EQVIO_OK;
-        case EQVIO_TUNE_CHAIN:
-            if (value < 0 || value > 2) return EQVIO_ERR_INVALID_ARG;
-            f->chain = value;
-            clear_graphs(f);
-            return EQVIO_OK;
         case EQVIO_TUNE_SPECULATE_NEW:
             f->specNew = value != 0;
             return EQVIO_OK;
         case EQVIO_TUNE_STAGE_S:
             f->stageS = value != 0;
-            clear_graphs(f);
-            return EQVIO_OK;
-        case EQVIO_TUNE_FACTOR:
-            if (value < 0 || value > 2) return EQVIO_ERR_INVALID_ARG;
-            f->dfFactor = value;
             clear_graphs(f);
             return EQVIO_OK;
         case EQVIO_TUNE_FUSE_SMALL:

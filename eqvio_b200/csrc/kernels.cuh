@@ -1184,18 +1184,13 @@ struct ChunkSmem {
     int Idx[CH_R / 2];
     int ready;                                // block columns of S_c whose panels are published (release / acquire)
     int pad_;
-    // pending downdate of the previous chunk (pipelined mode ONLY -- the launch allocates the struct up to here otherwise, so
-    // that a factor CTA fits beside two downdate CTAs on one SM):
-    // Us[k][p] = C_c Yprev[k, L_c] for the S rows, Ur[k][sl] = Yprev[k, sbase + sl] for the right-hand-side rows
-    alignas(16) double Us[CH_R][CH_R + 4];
-    alignas(16) double Ur[CH_R][CH_RHS_ROWS * CH_T + 4];
 };
-constexpr int CH_SMEM_BASE = (int)offsetof(ChunkSmem, Us);
-// Staged S gather (stage = 1, Yprev == nullptr): when the chunk's landmarks are consecutive in the state, Sigma[L_c, L_c] is one
+constexpr int CH_SMEM_BASE = (int)sizeof(ChunkSmem);
+// Staged S gather (stage = 1): when the chunk's landmarks are consecutive in the state, Sigma[L_c, L_c] is one
 // 96 x 96 box of the covariance.  One thread hands it to the TMA unit as a single 2-D tensor copy (cp.async.bulk.tensor.2d over a
 // CUtensorMap of Sigma, one mbarrier) and the tile owners project from shared memory, instead of every owner gathering 36
 // scattered doubles through the LSU (~5.7 k cycles per launch, bound by the number of small requests).  Rows / columns past the
-// matrix come back as zeros.  TMA wants the box to start on a 16-byte boundary: chunks that start at an odd landmark use the gather.  The area starts at CH_STAGE_OFF, in place of the pipelined mode's Us / Ur.
+// matrix come back as zeros.  TMA wants the box to start on a 16-byte boundary: chunks that start at an odd landmark use the gather.  The area starts at CH_STAGE_OFF, behind ChunkSmem.
 constexpr int CH_STG_N = 3 * (CH_R / 2);   // 96 state rows / columns of a chunk
 struct ChunkStage {
     alignas(128) double S[CH_STG_N][CH_STG_N];  // S[c][r] = Sigma[row0 + r, row0 + c]
@@ -1272,7 +1267,7 @@ __global__ void __launch_bounds__(CH_THREADS)
     chunk_factor_kernel(const double* __restrict__ Sig, int ld, int dimp, const int* __restrict__ lmOf,
                         const double* __restrict__ Cblk, const double* __restrict__ ytilde, int j0, int bc, double r2,
                         const double* __restrict__ GammaIn, double* __restrict__ GammaOut, double* __restrict__ Y,
-                        int* __restrict__ status, const int* __restrict__ guard, const double* __restrict__ Yprev, int tl, int stage,
+                        int* __restrict__ status, const int* __restrict__ guard, int tl, int stage,
                         const __grid_constant__ CUtensorMap sigMap) {
     // Cblk / lmOf come from meas_kernel and the frame upload (the host launches chunk 0 as a plain launch, later chunks follow
     // other chunk kernels): they are staged BEFORE the dependency wait, so the set-up overlaps the predecessor's tail
@@ -1302,29 +1297,6 @@ __global__ void __launch_bounds__(CH_THREADS)
         mbar_expect_tx(&stg.bar, (uint32_t)sizeof(stg.S));
         tma_load_2d(&stg.S[0][0], &sigMap, SOFF + 3 * lm0, SOFF + 3 * lm0, &stg.bar);
     }
-    // Pipelined mode: Sig is the covariance BEFORE the previous chunk's downdate (that downdate is running
-    // concurrently, out of place).  Its effect on this chunk's augmented matrix, M -= U^T U_S with u_rho = the
-    // column of Yprev belonging to augmented row rho, is applied here from Yprev itself.
-    if (Yprev) {
-        const int lane = tid & 31, warp = tid >> 5;
-        for (int k = warp; k < CH_R; k += CH_THREADS / 32) {
-            // S rows: landmark `lane` of the chunk, rows 2 lane, 2 lane + 1
-            double u0 = 0.0, u1 = 0.0;
-            if (lane < bc) {
-                const int g = sm.Idx[lane];
-                const double y0 = Yprev[yb_index(k, g)], y1 = Yprev[yb_index(k, g + 1)], y2 = Yprev[yb_index(k, g + 2)];
-                u0 = sm.C[lane][0] * y0 + sm.C[lane][1] * y1 + sm.C[lane][2] * y2;
-                u1 = sm.C[lane][3] * y0 + sm.C[lane][4] * y1 + sm.C[lane][5] * y2;
-            }
-            sm.Us[k][2 * lane] = u0;
-            sm.Us[k][2 * lane + 1] = u1;
-            // right-hand-side rows: this CTA's 32 state columns; the residual row and the padding get no correction
-            sm.Ur[k][lane] = Yprev[yb_index(k, blockIdx.x * CH_COLS + lane)];
-            if (lane < CH_RHS_ROWS * CH_T - CH_COLS) sm.Ur[k][CH_COLS + lane] = 0.0;
-        }
-        __syncthreads();
-    }
-
     const bool sGroup = tid < CH_S_THREADS;
     const int sbase = blockIdx.x * CH_COLS;
     const int nJ = (rc + CH_T - 1) / CH_T;
@@ -1399,20 +1371,6 @@ __global__ void __launch_bounds__(CH_THREADS)
                     else
                         a[c][c] = 1.0;  // identity padding of a short last chunk
                 }
-            }
-        }
-        if (Yprev && owner) {
-#pragma unroll 4
-            for (int k = 0; k < CH_R; ++k) {
-                const double2 ra = *reinterpret_cast<const double2*>(&sm.Us[k][CH_T * TI]);
-                const double2 rb = *reinterpret_cast<const double2*>(&sm.Us[k][CH_T * TI + 2]);
-                const double2 ca = *reinterpret_cast<const double2*>(&sm.Us[k][CH_T * TK]);
-                const double2 cb = *reinterpret_cast<const double2*>(&sm.Us[k][CH_T * TK + 2]);
-                const double rv[CH_T] = {ra.x, ra.y, rb.x, rb.y}, cv[CH_T] = {ca.x, ca.y, cb.x, cb.y};
-#pragma unroll
-                for (int r = 0; r < CH_T; ++r)
-#pragma unroll
-                    for (int c = 0; c < CH_T; ++c) a[r][c] -= rv[r] * cv[c];
             }
         }
         CH_STAMP(2);
@@ -1557,20 +1515,6 @@ __global__ void __launch_bounds__(CH_THREADS)
                 }
             }
         }
-        if (Yprev && isRhs) {
-#pragma unroll 4
-            for (int k = 0; k < CH_R; ++k) {
-                const double2 ra = *reinterpret_cast<const double2*>(&sm.Ur[k][CH_T * trow]);
-                const double2 rb = *reinterpret_cast<const double2*>(&sm.Ur[k][CH_T * trow + 2]);
-                const double2 ca = *reinterpret_cast<const double2*>(&sm.Us[k][CH_T * TK]);
-                const double2 cb = *reinterpret_cast<const double2*>(&sm.Us[k][CH_T * TK + 2]);
-                const double rv[CH_T] = {ra.x, ra.y, rb.x, rb.y}, cv[CH_T] = {ca.x, ca.y, cb.x, cb.y};
-#pragma unroll
-                for (int r = 0; r < CH_T; ++r)
-#pragma unroll
-                    for (int c = 0; c < CH_T; ++c) a[r][c] -= rv[r] * cv[c];
-            }
-        }
         CH_STAMP(108);
         for (int J = 0; J < nJ; ++J) {
             while (flag_acquire(&sm.ready) <= J) __nanosleep(64);
@@ -1661,540 +1605,6 @@ __global__ void __launch_bounds__(CH_THREADS)
     TL_MARK(tl, 1);
 }
 
-#include "chunk_factor_df.cuh"
-#include "chunk_factor_mma.cuh"
-
-// ------------------------------------------------------------------------------------------------
-// chunk_factor2_kernel / chunk_look_kernel: the CHAINED correction.  The sequential-chunk update is a block Cholesky of
-// S = C Sigma C^T + R whose trailing update is applied to Sigma.  The elimination of S_c does not have to wait for the
-// downdate of chunk c-1 if S_c (already downdated) is handed over in measurement space:
-//   * chunk_look_kernel (one CTA, its own stream) eliminates S_c with the projected block S_{c+1,c} = C_{c+1} Sigma C_c^T as
-//     right-hand sides, which yields U = L_c^-1 S_{c,c+1}, and writes S_{c+1} = S_{c+1}^pre - U^T U for the next launches;
-//   * chunk_factor2_kernel is chunk_factor_kernel with its S group starting from that block instead of gathering Sigma;
-//   * the downdates run on a third stream; only the right-hand-side warps of the next launches wait for them (acquire on
-//     a completion counter the downdate CTAs bump) before they gather from Sigma, then catch up with the S group through
-//     the progress flag.  The cycle per chunk is downdate -> gather -> catch-up -> Y, the 64-pivot chain runs beside it.
-// ------------------------------------------------------------------------------------------------
-constexpr int C2_YT_LD = CH_R + 4;  // 68: rows of U / Y^T stay 16-byte aligned
-
-struct Chunk2Smem {
-    union {
-        double Lp[CH_NT][CH_T][CH_T][CH_NT + 1];
-        double Yt[CH_R][C2_YT_LD];
-    };
-    double Dc[CH_NT][CH_T];
-    double C[CH_R / 2][6];
-    double Cn[CH_R / 2][6];          // output blocks of the NEXT chunk (look-ahead kernel)
-    double Inv[CH_R];
-    double Spre[CH_R][CH_R + 1];     // S of the next chunk before this chunk's downdate (look-ahead kernel)
-    int Idx[CH_R / 2];
-    int IdxN[CH_R / 2];
-    int ready;
-    int t1ready;                     // look-ahead kernel: the row-projected blocks are staged
-    int urows[CH_NT];                // look-ahead kernel: half-warps that have published rows 4J..4J+3 of U, per block column J
-};
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-template <int NTHREADS>
-__device__ __forceinline__ void rhs_group_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(NTHREADS) : "memory"); }
-
-// LOOK = false: 32 state columns + the residual per CTA (9 tile rows, 160 RHS threads), writes Y_c and Gamma.
-// LOOK = true : ONE CTA, right-hand sides = the 64 measurement rows of the next chunk (16 tile rows, 256 RHS threads),
-//               writes SnextOut.
-// Look-ahead kernel only: Sigma blocks projected on the row side, staged so that every global read is coalesced
-// (lanes walk the next chunk's landmarks = consecutive rows of a column of Sigma):
-//   Trhs[2 jn + e][cc] = sum_aa Cn[jn][e][aa] Sigma[row(jn) + aa, col_c(cc)]   cc over this chunk's 96 state columns
-//   Tpre[2 jn + e][cc] = the same against the next chunk's own columns (lower triangle: jn >= cc / 3)
-constexpr int LK_LD = 3 * (CH_R / 2) + 1;  // 97
-struct LookExtraSmem {
-    double Trhs[CH_R][LK_LD];
-    double Tpre[CH_R][LK_LD];
-};
-constexpr int LOOK_RHS = 256, LOOK_MMA = 128;
-constexpr int LOOK_THREADS = CH_S_THREADS + LOOK_RHS + LOOK_MMA;  // S group | right-hand sides | rank-4 updates of S_next
-constexpr int LOOK_SMEM = (int)(sizeof(Chunk2Smem) + sizeof(LookExtraSmem));
-
-template <bool LOOK>
-__global__ void __launch_bounds__(LOOK ? LOOK_THREADS : CH_THREADS)
-    chunk_factor2_kernel(const double* Sig, int ld, int dimp, const int* __restrict__ lmOf, const double* __restrict__ Cblk,
-                         const double* __restrict__ ytilde, int j0, int bc, int nb, double r2, const double* __restrict__ GammaIn,
-                         double* __restrict__ GammaOut, double* __restrict__ Y, int* __restrict__ status, const int* __restrict__ guard,
-                         const double* __restrict__ SnextIn, double* __restrict__ SnextOut, const int* waitCnt, int waitTarget,
-                         int* gatherDone, int tl) {
-    constexpr int RHS_THREADS = LOOK ? LOOK_RHS : CH_RHS_THREADS;
-    constexpr int NTHREADS = LOOK ? LOOK_THREADS : CH_THREADS;
-    constexpr int ROWS = LOOK ? CH_NT : CH_RHS_ROWS;  // tile rows of right-hand sides
-    // Cblk / lmOf were written by meas_kernel and the frame upload, several launches back on this stream's history: they are
-    // read BEFORE the dependency wait so that the set-up overlaps the predecessor's tail
-    extern __shared__ __align__(128) unsigned char chunk_smem_raw[];
-    Chunk2Smem& sm = *reinterpret_cast<Chunk2Smem*>(chunk_smem_raw);
-    const int tid = threadIdx.x;
-    const int rc = 2 * bc;
-    if (LOOK) CH_STAMP(0);
-    for (int t = tid; t < bc * 6; t += NTHREADS) sm.C[t / 6][t % 6] = Cblk[6 * (size_t)j0 + t];
-    for (int t = tid; t < bc; t += NTHREADS) sm.Idx[t] = SOFF + 3 * lmOf[j0 + t];
-    if (LOOK) {
-        for (int t = tid; t < (CH_R / 2) * 6; t += NTHREADS) sm.Cn[t / 6][t % 6] = t < nb * 6 ? Cblk[6 * (size_t)(j0 + bc) + t] : 0.0;
-        for (int t = tid; t < CH_R / 2; t += NTHREADS) sm.IdxN[t] = t < nb ? SOFF + 3 * lmOf[j0 + bc + t] : 0;
-    }
-    if (tid == 0) {
-        sm.ready = 0;
-        sm.t1ready = 0;
-    }
-    if (LOOK && tid < CH_NT) sm.urows[tid] = 0;
-    pdl_wait();
-    if (*guard) return;
-    TL_MARK(tl, 0);
-    __syncthreads();
-    if (LOOK) CH_STAMP(1);
-
-    const bool sGroup = tid < CH_S_THREADS;
-    const int sbase = blockIdx.x * CH_COLS;
-    const int nJ = (rc + CH_T - 1) / CH_T;
-    double a[CH_T][CH_T];
-#pragma unroll
-    for (int r = 0; r < CH_T; ++r)
-#pragma unroll
-        for (int c = 0; c < CH_T; ++c) a[r][c] = 0.0;
-
-    if (sGroup) {
-        // ================================ S group ================================
-        const bool owner = tid < CH_TILES;
-        int TI = 0, TK = 0;
-        if (owner) tri_decode(tid, TI, TK);
-        if (owner && SnextIn) {
-            // S_c arrives from the previous look-ahead launch (row-major 64 x 64, lower tiles)
-#pragma unroll
-            for (int r = 0; r < CH_T; ++r) {
-                const double2 p01 = *reinterpret_cast<const double2*>(SnextIn + (size_t)(CH_T * TI + r) * CH_R + CH_T * TK);
-                const double2 p23 = *reinterpret_cast<const double2*>(SnextIn + (size_t)(CH_T * TI + r) * CH_R + CH_T * TK + 2);
-                a[r][0] = p01.x;
-                a[r][1] = p01.y;
-                a[r][2] = p23.x;
-                a[r][3] = p23.y;
-            }
-        } else if (owner) {
-            // first chunk: gather from Sigma (full symmetric storage at this point), as chunk_factor_kernel does
-            double P[2][2][9];
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                for (int v = 0; v < 2; ++v) {
-                    const int j = 2 * TI + u, k = 2 * TK + v;
-                    if (j < bc && k < bc) {
-                        const double* sp = Sig + (size_t)sm.Idx[j] * ld + sm.Idx[k];
-#pragma unroll
-                        for (int aa = 0; aa < 3; ++aa)
-#pragma unroll
-                            for (int b = 0; b < 3; ++b) P[u][v][aa * 3 + b] = __ldcg(sp + (size_t)aa * ld + b);
-                    }
-                }
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                for (int v = 0; v < 2; ++v) {
-                    const int j = 2 * TI + u, k = 2 * TK + v;
-                    if (j < bc && k < bc) {
-                        double T[6];
-#pragma unroll
-                        for (int e = 0; e < 2; ++e)
-#pragma unroll
-                            for (int b = 0; b < 3; ++b)
-                                T[e * 3 + b] = sm.C[j][3 * e] * P[u][v][b] + sm.C[j][3 * e + 1] * P[u][v][3 + b] + sm.C[j][3 * e + 2] * P[u][v][6 + b];
-#pragma unroll
-                        for (int e = 0; e < 2; ++e)
-#pragma unroll
-                            for (int f = 0; f < 2; ++f)
-                                a[2 * u + e][2 * v + f] = T[e * 3] * sm.C[k][3 * f] + T[e * 3 + 1] * sm.C[k][3 * f + 1] + T[e * 3 + 2] * sm.C[k][3 * f + 2];
-                    }
-                }
-            if (TI == TK) {
-#pragma unroll
-                for (int c = 0; c < CH_T; ++c) {
-                    if (CH_T * TI + c < rc)
-                        a[c][c] += r2;
-                    else
-                        a[c][c] = 1.0;  // identity padding of a short last chunk
-                }
-            }
-        }
-        if (LOOK) CH_STAMP(2);
-        for (int J = 0; J < nJ; ++J) {
-            if (owner && TI == J && TK == J) {
-                // fraction-free 4x4 diagonal tile, see chunk_factor_kernel
-                const double a00 = a[0][0], a10 = a[1][0], a20 = a[2][0], a30 = a[3][0];
-                const double m11 = a[1][1] * a00 - a10 * a10, m21 = a[2][1] * a00 - a20 * a10, m22 = a[2][2] * a00 - a20 * a20;
-                const double m31 = a[3][1] * a00 - a30 * a10, m32 = a[3][2] * a00 - a30 * a20, m33 = a[3][3] * a00 - a30 * a30;
-                const double n22 = m22 * m11 - m21 * m21, n32 = m32 * m11 - m31 * m21, n33 = m33 * m11 - m31 * m31;
-                const double p33 = n33 * n22 - n32 * n32;
-                const double r0 = fast_rcp(a00), r1 = fast_rcp(m11), r2_ = fast_rcp(n22), r3 = fast_rcp(p33);
-                const double s2 = r0 * r1, s3 = s2 * r2_, e1 = a00 * m11;
-                a[1][1] = m11 * r0;
-                a[2][1] = m21 * r0;
-                a[3][1] = m31 * r0;
-                a[2][2] = n22 * s2;
-                a[3][2] = n32 * s2;
-                a[3][3] = p33 * s3;
-                sm.Dc[J][0] = r0;
-                sm.Dc[J][1] = a00 * r1;
-                sm.Dc[J][2] = e1 * r2_;
-                sm.Dc[J][3] = (e1 * n22) * r3;
-#pragma unroll
-                for (int i = 0; i < CH_T; ++i)
-#pragma unroll
-                    for (int j = 0; j < CH_T; ++j) sm.Lp[J][i][j][J] = a[i][j];
-            }
-            s_group_barrier();
-            if (owner && TK == J && TI > J) {
-                double c[CH_T], d[CH_T][CH_T];
-#pragma unroll
-                for (int j = 0; j < CH_T; ++j) c[j] = sm.Dc[J][j];
-#pragma unroll
-                for (int i = 0; i < CH_T; ++i)
-#pragma unroll
-                    for (int j = 0; j < CH_T; ++j) d[i][j] = sm.Lp[J][i][j][J];
-#pragma unroll
-                for (int j = 0; j < CH_T; ++j)
-#pragma unroll
-                    for (int k = j + 1; k < CH_T; ++k)
-#pragma unroll
-                        for (int r = 0; r < CH_T; ++r) a[r][k] -= (a[r][j] * c[j]) * d[k][j];
-#pragma unroll
-                for (int r = 0; r < CH_T; ++r)
-#pragma unroll
-                    for (int j = 0; j < CH_T; ++j) sm.Lp[J][r][j][TI] = a[r][j];
-            }
-            s_group_barrier();
-            if (tid == 0) flag_release(&sm.ready, J + 1);
-            if (owner && TK > J) {
-                double li[CH_T][CH_T], pk[CH_T][CH_T];
-#pragma unroll
-                for (int j = 0; j < CH_T; ++j) {
-                    const double c = sm.Dc[J][j];
-#pragma unroll
-                    for (int r = 0; r < CH_T; ++r) li[r][j] = sm.Lp[J][r][j][TI] * c;
-                }
-#pragma unroll
-                for (int cc = 0; cc < CH_T; ++cc)
-#pragma unroll
-                    for (int j = 0; j < CH_T; ++j) pk[cc][j] = sm.Lp[J][cc][j][TK];
-#pragma unroll
-                for (int r = 0; r < CH_T; ++r)
-#pragma unroll
-                    for (int cc = 0; cc < CH_T; ++cc) {
-                        double acc = a[r][cc];
-#pragma unroll
-                        for (int j = 0; j < CH_T; ++j) acc -= li[r][j] * pk[cc][j];
-                        a[r][cc] = acc;
-                    }
-            }
-        }
-        if (LOOK) CH_STAMP(3);
-        if (owner && TI == TK) {
-#pragma unroll
-            for (int c = 0; c < CH_T; ++c) {
-                const double piv = a[c][c];
-                const int k = CH_T * TK + c;
-                if (!(piv > 0.0)) {
-                    if (blockIdx.x == 0 && !LOOK) atomicOr(status, 1);
-                    sm.Inv[k] = 1.0;
-                } else {
-                    sm.Inv[k] = 1.0 / sqrt(piv);
-                }
-            }
-        }
-    } else if (tid < CH_S_THREADS + RHS_THREADS) {
-        // ================================ RHS group ================================
-        const int q = tid - CH_S_THREADS;
-        const int trow = q / CH_NT, TK = q % CH_NT;
-        const bool isRhs = trow < ROWS;
-        if (waitCnt) {
-            // Sigma must carry the previous chunk's downdate (it runs on another stream): wait for all its tiles
-            if (q == 0) {
-                int spins = 0;
-                while (ld_acquire_gpu(waitCnt) < waitTarget) {
-                    __nanosleep(64);
-                    if (++spins > (1 << 24)) {  // ~1 s: never hang the device; the host sees the status bit
-                        atomicOr(status, 4);
-                        break;
-                    }
-                }
-            }
-            rhs_group_barrier<RHS_THREADS>();
-        }
-        if (LOOK) CH_STAMP(107);
-        if (LOOK) {
-            LookExtraSmem& lx = *reinterpret_cast<LookExtraSmem*>(chunk_smem_raw + sizeof(Chunk2Smem));
-            // step 1: coalesced reads of Sigma, projected on the row side with the next chunk's output blocks
-            constexpr int LK_ITEMS = 2 * 3 * (CH_R / 2) * (CH_R / 2), LK_BATCH = 8;  // 6144 items, 24 per thread, 8 in flight
-            for (int it0 = q; it0 < LK_ITEMS; it0 += RHS_THREADS * LK_BATCH) {
-                double v[LK_BATCH][3];
-#pragma unroll
-                for (int bi = 0; bi < LK_BATCH; ++bi) {
-                    // branch-free: every item loads three (possibly dummy) addresses so that the 24 loads of a batch are in flight
-                    // together; invalid items are zeroed afterwards
-                    const int item = it0 + bi * RHS_THREADS;
-                    const int jn = item % (CH_R / 2);
-                    int cc = item / (CH_R / 2);
-                    const bool pre = cc >= 3 * (CH_R / 2);
-                    if (pre) cc -= 3 * (CH_R / 2);
-                    const int jc = (cc / 3) & (CH_R / 2 - 1), b = cc % 3;
-                    const bool ok = item < LK_ITEMS && jn < nb && (pre ? jc <= jn : jc < bc);
-                    const int row = ok ? sm.IdxN[jn] : 0;
-                    const int col = ok ? (pre ? sm.IdxN[jc] : sm.Idx[jc]) + b : 0;
-#pragma unroll
-                    for (int aa = 0; aa < 3; ++aa) {
-                        const int R = row + aa;  // entries are read as (max, min): the lower triangle is always current
-                        // plain (L1-cached) load: the three rows of a lane share sectors; no stale line can sit in L1, this CTA has
-                        // not touched Sigma before the counter wait above
-                        const double x = Sig[(size_t)(R < col ? R : col) * ld + (R < col ? col : R)];
-                        v[bi][aa] = ok ? x : 0.0;
-                    }
-                }
-#pragma unroll
-                for (int bi = 0; bi < LK_BATCH; ++bi) {
-                    const int item = it0 + bi * RHS_THREADS;
-                    if (item < LK_ITEMS) {
-                        const int jn = item % (CH_R / 2);
-                        int cc = item / (CH_R / 2);
-                        const bool pre = cc >= 3 * (CH_R / 2);
-                        if (pre) cc -= 3 * (CH_R / 2);
-                        double(*Tm)[LK_LD] = pre ? lx.Tpre : lx.Trhs;
-                        Tm[2 * jn][cc] = sm.Cn[jn][0] * v[bi][0] + sm.Cn[jn][1] * v[bi][1] + sm.Cn[jn][2] * v[bi][2];
-                        Tm[2 * jn + 1][cc] = sm.Cn[jn][3] * v[bi][0] + sm.Cn[jn][4] * v[bi][1] + sm.Cn[jn][5] * v[bi][2];
-                    }
-                }
-            }
-            rhs_group_barrier<RHS_THREADS>();
-            if (q == 0) {
-                flag_release(&sm.t1ready, 1);  // Tpre is complete: the MMA group projects S_pre from it
-                if (gatherDone) {              // this chunk's downdate may overwrite Sigma from here on
-                    __threadfence();
-                    atomicExch(gatherDone, 1);
-                }
-            }
-            CH_STAMP(110);
-            // step 2b: right-hand sides = the projected block S_{c+1,c}: rows = measurement rows of the next chunk (landmarks
-            // 2 trow, 2 trow + 1), columns from landmarks 2TK, 2TK+1 of this chunk
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                for (int v = 0; v < 2; ++v) {
-                    const int jn = 2 * trow + u, j = 2 * TK + v;
-                    if (jn < nb && j < bc) {
-#pragma unroll
-                        for (int e = 0; e < 2; ++e)
-#pragma unroll
-                            for (int f = 0; f < 2; ++f)
-                                a[2 * u + e][2 * v + f] = lx.Trhs[2 * jn + e][3 * j] * sm.C[j][3 * f] + lx.Trhs[2 * jn + e][3 * j + 1] * sm.C[j][3 * f + 1] +
-                                                          lx.Trhs[2 * jn + e][3 * j + 2] * sm.C[j][3 * f + 2];
-                    }
-                }
-            rhs_group_barrier<RHS_THREADS>();  // Trhs is dead from here on: its storage becomes U
-        } else if (isRhs && trow < CH_COLS / CH_T) {
-            // rows s = sbase + 4 trow + r (state columns of W_c), columns k = 4TK + c from landmarks 2TK, 2TK+1
-            const int s0 = sbase + CH_T * trow;
-            double w[2][3][CH_T];
-#pragma unroll
-            for (int v = 0; v < 2; ++v) {
-                const int j = 2 * TK + v;
-                if (j < bc && s0 < dimp) {
-                    const double* sp = Sig + (size_t)sm.Idx[j] * ld + s0;
-#pragma unroll
-                    for (int b = 0; b < 3; ++b) {
-                        const double2 p01 = __ldcg(reinterpret_cast<const double2*>(sp + (size_t)b * ld));
-                        const double2 p23 = __ldcg(reinterpret_cast<const double2*>(sp + (size_t)b * ld + 2));
-                        w[v][b][0] = p01.x;
-                        w[v][b][1] = p01.y;
-                        w[v][b][2] = p23.x;
-                        w[v][b][3] = p23.y;
-                    }
-                }
-            }
-#pragma unroll
-            for (int v = 0; v < 2; ++v) {
-                const int j = 2 * TK + v;
-                if (j < bc && s0 < dimp) {
-#pragma unroll
-                    for (int r = 0; r < CH_T; ++r)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e)
-                            a[r][2 * v + e] = (s0 + r < dimp) ? sm.C[j][3 * e] * w[v][0][r] + sm.C[j][3 * e + 1] * w[v][1][r] + sm.C[j][3 * e + 2] * w[v][2][r] : 0.0;
-                }
-            }
-        } else if (isRhs) {
-            // residual row (r = 0 of the last tile row): ytilde_c - C_c Gamma
-#pragma unroll
-            for (int v = 0; v < 2; ++v) {
-                const int j = 2 * TK + v;
-                if (j < bc) {
-                    const int g = sm.Idx[j];
-                    const double g0 = GammaIn[g], g1 = GammaIn[g + 1], g2 = GammaIn[g + 2];
-                    a[0][2 * v] = ytilde[2 * (j0 + j)] - (sm.C[j][0] * g0 + sm.C[j][1] * g1 + sm.C[j][2] * g2);
-                    a[0][2 * v + 1] = ytilde[2 * (j0 + j) + 1] - (sm.C[j][3] * g0 + sm.C[j][4] * g1 + sm.C[j][5] * g2);
-                }
-            }
-        }
-        if (LOOK) CH_STAMP(108);
-        for (int J = 0; J < nJ; ++J) {
-            while (flag_acquire(&sm.ready) <= J) __nanosleep(32);
-            double c[CH_T];
-#pragma unroll
-            for (int j = 0; j < CH_T; ++j) c[j] = sm.Dc[J][j];
-            if (TK == J) {
-                double d[CH_T][CH_T];
-#pragma unroll
-                for (int i = 0; i < CH_T; ++i)
-#pragma unroll
-                    for (int j = 0; j < CH_T; ++j) d[i][j] = sm.Lp[J][i][j][J];
-#pragma unroll
-                for (int j = 0; j < CH_T; ++j)
-#pragma unroll
-                    for (int k = j + 1; k < CH_T; ++k)
-#pragma unroll
-                        for (int r = 0; r < CH_T; ++r) a[r][k] -= (a[r][j] * c[j]) * d[k][j];
-                if (LOOK) {
-                    // rows 4J .. 4J+3 of U = L_c^-1 S_{c,c+1} are final (up to the scale 1 / L_kk, which the MMA group applies as
-                    // 1 / v_kk on one operand): publish them for the rank-4 update of S_next that runs beside the elimination
-                    LookExtraSmem& lx = *reinterpret_cast<LookExtraSmem*>(chunk_smem_raw + sizeof(Chunk2Smem));
-#pragma unroll
-                    for (int cc = 0; cc < CH_T; ++cc)
-#pragma unroll
-                        for (int r = 0; r < CH_T; ++r) lx.Trhs[CH_T * J + cc][CH_T * trow + r] = a[r][cc];  // unscaled: v_sk = L_sk L_kk
-                    __threadfence_block();
-                    atomicAdd(&sm.urows[J], 1);
-                }
-            }
-            double li[CH_T][CH_T];
-#pragma unroll
-            for (int r = 0; r < CH_T; ++r)
-#pragma unroll
-                for (int j = 0; j < CH_T; ++j) li[r][j] = __shfl_sync(0xffffffffu, a[r][j], J, CH_NT) * c[j];
-            if (TK > J) {
-                double pk[CH_T][CH_T];
-#pragma unroll
-                for (int cc = 0; cc < CH_T; ++cc)
-#pragma unroll
-                    for (int j = 0; j < CH_T; ++j) pk[cc][j] = sm.Lp[J][cc][j][TK];
-#pragma unroll
-                for (int r = 0; r < CH_T; ++r)
-#pragma unroll
-                    for (int cc = 0; cc < CH_T; ++cc) {
-                        double acc = a[r][cc];
-#pragma unroll
-                        for (int j = 0; j < CH_T; ++j) acc -= li[r][j] * pk[cc][j];
-                        a[r][cc] = acc;
-                    }
-            }
-        }
-    } else if (LOOK) {
-        // ================================ MMA group (look-ahead kernel) ================================
-        // S_next = S_pre - U^T U, accumulated four rows of U at a time as they become final (one DMMA k-step per block
-        // column), so that only the last rank-4 update and the store remain after the elimination.
-        LookExtraSmem& lx = *reinterpret_cast<LookExtraSmem*>(chunk_smem_raw + sizeof(Chunk2Smem));
-        const int m = tid - CH_S_THREADS - RHS_THREADS;
-        while (flag_acquire(&sm.t1ready) == 0) __nanosleep(64);
-        for (int tile = m; tile < CH_TILES; tile += LOOK_MMA) {
-            int TIn, TKn;
-            tri_decode(tile, TIn, TKn);
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-#pragma unroll
-                    for (int v = 0; v < 2; ++v) {
-                        const int j = 2 * TIn + u, k = 2 * TKn + v;
-#pragma unroll
-                        for (int e = 0; e < 2; ++e)
-#pragma unroll
-                            for (int f = 0; f < 2; ++f) {
-                                double val = 0.0;
-                                if (j < nb && k < nb) {
-                                    if (j >= k)
-                                        val = lx.Tpre[2 * j + e][3 * k] * sm.Cn[k][3 * f] + lx.Tpre[2 * j + e][3 * k + 1] * sm.Cn[k][3 * f + 1] +
-                                              lx.Tpre[2 * j + e][3 * k + 2] * sm.Cn[k][3 * f + 2];
-                                    else
-                                        val = lx.Tpre[2 * k + f][3 * j] * sm.Cn[j][3 * e] + lx.Tpre[2 * k + f][3 * j + 1] * sm.Cn[j][3 * e + 1] +
-                                              lx.Tpre[2 * k + f][3 * j + 2] * sm.Cn[j][3 * e + 2];
-                                }
-                                const int rr = 2 * j + e, cq = 2 * k + f;
-                                if (rr == cq) val = rr < 2 * nb ? val + r2 : 1.0;
-                                sm.Spre[rr][cq] = val;
-                                sm.Spre[cq][rr] = val;  // the epilogue updates the full 64 x 64 block
-                            }
-                    }
-        }
-        asm volatile("bar.sync 3, %0;" ::"n"(LOOK_MMA) : "memory");
-        const int lane = m & 31, warp = m >> 5;
-        const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
-        const int fr = wm + (lane >> 2), fc = wn + (lane & 3) * 2;
-        double acc[4][4][2];
-#pragma unroll
-        for (int aa = 0; aa < 4; ++aa)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                acc[aa][b][0] = -sm.Spre[fr + aa * 8][fc + b * 8];
-                acc[aa][b][1] = -sm.Spre[fr + aa * 8][fc + b * 8 + 1];
-            }
-        for (int J = 0; J < nJ; ++J) {
-            while (flag_acquire(&sm.urows[J]) < CH_NT) __nanosleep(200);
-            // U^T U = sum_k u'_k u'_k^T / v_kk with the unscaled rows u'_k and v_kk the diagonal of the finished diagonal tile
-            const double vkk = sm.Lp[J][lane & 3][lane & 3][J];
-            const double ik = vkk > 0.0 ? 1.0 / vkk : 1.0;
-            double af[4], bf[4];
-#pragma unroll
-            for (int aa = 0; aa < 4; ++aa) af[aa] = lx.Trhs[CH_T * J + (lane & 3)][wm + aa * 8 + (lane >> 2)];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) bf[b] = lx.Trhs[CH_T * J + (lane & 3)][wn + b * 8 + (lane >> 2)] * ik;
-#pragma unroll
-            for (int aa = 0; aa < 4; ++aa)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) dmma884(acc[aa][b][0], acc[aa][b][1], af[aa], bf[b]);
-        }
-#pragma unroll
-        for (int aa = 0; aa < 4; ++aa)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                double2 o;
-                o.x = -acc[aa][b][0];
-                o.y = -acc[aa][b][1];
-                *reinterpret_cast<double2*>(SnextOut + (size_t)(fr + aa * 8) * CH_R + fc + b * 8) = o;
-            }
-    }
-    if (LOOK) CH_STAMP(109);
-    __syncthreads();  // Inv published, every tile final, Lp dead
-    if (LOOK) CH_STAMP(4);
-    if (!sGroup && !LOOK) {
-        const int q = tid - CH_S_THREADS;
-        const int trow = q / CH_NT, TK = q % CH_NT;
-        if (trow < ROWS) {
-#pragma unroll
-            for (int c = 0; c < CH_T; ++c) {
-                const double sc = sm.Inv[CH_T * TK + c];
-#pragma unroll
-                for (int r = 0; r < CH_T; ++r) sm.Yt[CH_T * TK + c][CH_T * trow + r] = a[r][c] * sc;
-            }
-        }
-    }
-    __syncthreads();
-    if (LOOK) CH_STAMP(5);
-    if (!LOOK) {
-        for (int t = tid; t < CH_R * CH_COLS; t += NTHREADS) {
-            const int k = t / CH_COLS, sl = t % CH_COLS;
-            Y[yb_index(k, sbase + sl)] = sm.Yt[k][sl];
-        }
-        if (tid < CH_COLS && sbase + tid < dimp) {
-            double g = 0.0;
-#pragma unroll 8
-            for (int k = 0; k < CH_R; ++k) g += sm.Yt[k][tid] * sm.Yt[k][CH_COLS];
-            GammaOut[sbase + tid] = GammaIn[sbase + tid] + g;
-        }
-    }
-    if (LOOK) CH_STAMP(6);
-    TL_MARK(tl, 1);
-}
-
 // ------------------------------------------------------------------------------------------------
 // Sigma <- Sigma - Y^T Y for one chunk (K = 64 rows of Y), one 64x64 tile of Sigma per CTA, tiles on
 // or below the diagonal; the transposed tile is written too so that Sigma stays stored in full.
@@ -2202,8 +1612,8 @@ __global__ void __launch_bounds__(LOOK ? LOOK_THREADS : CH_THREADS)
 // 34 KB, mbarrier-signalled) straight into their padded shared-memory layout; the Sigma tile is read and
 // written with 16-byte coalesced loads/stores (one 512-byte column per warp instruction), the mirror
 // tile goes through a shared-memory transpose.  Math: mma.sync.m8n8k4.f64 (DMMA), 4 warps x 32x32.
-// Sigma must be allocated with ld and row count padded to a multiple of 64 (whole tiles are moved).  SigOut may be
-// SigIn (in place) or the other covariance buffer (pipelined mode: the next chunk's factor kernel still reads SigIn).
+// Sigma must be allocated with ld and row count padded to a multiple of 64 (whole tiles are moved); the update is in place
+// (SigOut == SigIn).
 // ------------------------------------------------------------------------------------------------
 constexpr int DD_T = 64, DD_LD = YB_LD, DD_THREADS = 128;
 constexpr int DD_SMEM = 2 * DD_T * DD_LD * 8 + 16;
@@ -2211,18 +1621,9 @@ enum { DD_ALL = 0, DD_BAND = 1, DD_REST = 2 };  // which tiles a launch of chunk
 
 __global__ void __launch_bounds__(DD_THREADS, 3)
     chunk_downdate_kernel(const double* SigIn, double* SigOut, int ld, const double* __restrict__ Y,
-                          const int* __restrict__ guard, int mirrorLo, int mirrorHi, int mode, int T, int tl, int* doneCnt,
-                          const int* waitFlag) {
+                          const int* __restrict__ guard, int mirrorLo, int mirrorHi, int mode, int T, int tl) {
     pdl_wait();
     if (*guard) return;
-    if (waitFlag) {
-        // chained correction: the look-ahead kernel of this chunk still gathers blocks of the covariance BEFORE this downdate
-        if (threadIdx.x == 0) {
-            int spins = 0;
-            while (ld_acquire_gpu(waitFlag) == 0 && ++spins < (1 << 24)) __nanosleep(64);
-        }
-        __syncthreads();
-    }
     TL_MARK(tl, 0);
     int ti, tj;
     if (mode == DD_ALL) {
@@ -2311,11 +1712,6 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
                 *reinterpret_cast<double2*>(SigOut + (size_t)(i0 + fr + a * 8) * ld + j0 + fc + b * 8) = t;
             }
         }
-    if (doneCnt) {  // chained correction: the next factor launch's right-hand-side warps wait for every tile of this downdate
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) atomicAdd(doneCnt, 1);
-    }
     TL_MARK(tl, 1);
 }
 

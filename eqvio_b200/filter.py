@@ -351,10 +351,9 @@ class VIOFilter:
 
     def setTuning(self, **knobs):
         """Evaluation-order knobs (eqvio_set_tuning, include/eqvio_b200.h EQVIO_TUNE_*): correction (0 = sequential chunks, 1 = batch
-        sweep), chunkLandmarks, speculate, graph, pipeline, downdate (0 = fp64 DMMA, 1 = tcgen05 split-bf16), lookahead (split
-        downdates beside the next factor kernel), fuseObserver, pdl, chain (1 = chained correction with concurrent downdates,
-        2 = the same in stream order), fuseSmall, speculateNew, stageS (S blocks through one TMA tensor copy).  Results agree across
-        every knob (tests/test_gpu_parity.py)."""
+        sweep), chunkLandmarks, speculate, graph, downdate (0 = fp64 DMMA, 1 = tcgen05 split-bf16), lookahead (split
+        downdates beside the next factor kernel), fuseObserver, pdl, fuseSmall, speculateNew, stageS (S blocks through one TMA
+        tensor copy).  Results agree across every knob (tests/test_gpu_parity.py)."""
         for name, value in knobs.items():
             if value is None:
                 continue

@@ -221,12 +221,6 @@ int eqvio_get_host_profile(eqvio_filter* f, int reset, double us[4], long long* 
 /*   EQVIO_TUNE_GRAPH: 1 (default) = replay the launch sequence of a steady frame (no landmark enters or leaves)
  *                      as a cached CUDA graph; 0 = issue the launches one by one. */
 #define EQVIO_TUNE_GRAPH 3
-/*   EQVIO_TUNE_PIPELINE: 1 = chunk c+1 is factored while chunk c's downdate is still running (the downdate goes out of
- *                         place into the other covariance buffer, the factor kernel folds the pending downdate in
- *                         from Y_c); 0 (default) = strictly one kernel after the other, in place.  Measured slower
- *                         than the default on B200 at N = 256 / 1024 (the folded-in update costs more than the
- *                         overlap returns); kept as a tested evaluation order. */
-#define EQVIO_TUNE_PIPELINE 4
 /*   EQVIO_TUNE_DOWNDATE: 0 (default) = Sigma -= Y^T Y in fp64 on the FP64 tensor pipe (DMMA);
  *                         1 = BASELINE configs[2]: tcgen05 tensor cores, Y split into three bf16 terms (24-bit
  *                         mantissa), fp32 accumulation in TMEM, Sigma itself stays fp64.  Parity with the fp64 path
@@ -244,14 +238,6 @@ int eqvio_get_host_profile(eqvio_filter* f, int reset, double us[4], long long* 
 /*   EQVIO_TUNE_PDL: 1 (default) = the chunk kernels are launched with programmatic dependent launch allowed (the next
  *                         grid is scheduled while its predecessor drains and blocks in griddepcontrol.wait); 0 = plain. */
 #define EQVIO_TUNE_PDL 8
-/*   EQVIO_TUNE_CHAIN: EXPERIMENTAL chained correction (0 = off, default).  A look-ahead kernel (one CTA) eliminates S_c with the
- *                         projected block S_{c+1,c} as right-hand sides and hands S_{c+1} = S_pre - U^T U (rank-4 DMMA updates
- *                         beside the elimination) to the next launches, whose elimination then does not wait for the Sigma
- *                         downdate.  2 = those kernels in stream order (deterministic; parity-tested against mode 0 and the
- *                         oracle); 1 = downdates concurrent on a second stream behind completion counters (bit-identical to
- *                         mode 2 in the tests).  Measured slower than mode 0 on B200 (3040 vs 3320 updates/s at N = 256: the
- *                         single look-ahead CTA becomes the per-chunk bottleneck), hence off by default. */
-#define EQVIO_TUNE_CHAIN 9
 /*   EQVIO_TUNE_FUSE_SMALL: 1 (default) = in a steady update the gate and the measurement rows (C*, ytilde) run as one launch
  *                         and the innovation lift also emits the state estimate; 0 = four separate kernels.  Same arithmetic. */
 #define EQVIO_TUNE_FUSE_SMALL 10
@@ -264,11 +250,6 @@ int eqvio_get_host_profile(eqvio_filter* f, int reset, double us[4], long long* 
  *     CUtensorMap over the covariance) into shared memory when the chunk's landmarks are consecutive in the state; 0 = every tile
  *     owner gathers its 36 entries itself (also the fall-back for non-consecutive chunks).  Same entries, bit-identical results. */
 #define EQVIO_TUNE_STAGE_S 12
-/*   EQVIO_TUNE_FACTOR: chunk factor kernel.  2 (default) = chunk_factor_mma_kernel: the augmented matrix of a chunk in
- *     mma.sync.m8n8k4.f64 accumulator fragments, one DMMA per 8x8 tile and block column for the trailing update; 1 =
- *     chunk_factor_df_kernel: 4x4 register tiles, warp-specialised dataflow through single-use mbarriers; 0 = the
- *     barrier-synchronised 4x4-tile kernel of round 1 (1 and 0 agree bit for bit, 2 to rounding). */
-#define EQVIO_TUNE_FACTOR 13
 int eqvio_set_tuning(eqvio_filter* f, int key, int value);
 /* Version / build info string (arch the kernels were compiled for). */
 const char* eqvio_build_info(void);

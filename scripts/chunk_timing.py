@@ -19,7 +19,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 sm = record_stream(SimConfig.benchmark(N, 0), 12)
 flt = eb.VIOFilter(eb.Settings(fastRiccati=1), eb.VIOState(eb.VIOSensorState.fromFlat(sm.init_sensor), sm.init_p, sm.init_ids), 0.0,
                    capacity=N + 8)
-flt.setTuning(graph=0, stageS=int(os.environ.get('EQVIO_STAGE', '1')), factor=int(os.environ.get('EQVIO_FACTOR', '1')))
+flt.setTuning(graph=0, stageS=int(os.environ.get('EQVIO_STAGE', '1')))
 cam = eb.Camera(**sm.camera)
 for fr in sm.frames:
     flt.processIMUArray(fr.imu)
@@ -30,7 +30,7 @@ fn.restype = C.c_int
 out = (C.c_longlong * 16)()
 assert fn(out) == 0
 t = np.array(list(out), dtype=np.int64)
-factor = int(os.environ.get('EQVIO_FACTOR', '1'))
+factor = 0
 flt_names_old = {0: "start", 1: "C/Idx loaded", 2: "S gather done", 3: "S loop done", 4: "final barrier", 5: "Yt staged", 6: "end",
                  8: "RHS gather done", 9: "RHS loop done"}
 flt_names_df = {0: "start", 1: "C/Idx loaded", 2: "chain warp starts waiting", 3: "chain done", 4: "final barrier", 5: "Yt staged", 6: "end",

@@ -28,33 +28,6 @@ def _check(gpu, ref, tol=TOL):
     return worst
 
 
-@pytest.mark.parametrize("N,chunk,coord", [(40, 8, 0), (100, 32, 1), (150, 32, 0), (70, 5, 0), (33, 32, 0)])
-def test_chained_correction_kernels(N, chunk, coord):
-    """Experimental chained correction, stream-order mode (EQVIO_TUNE_CHAIN = 2): the look-ahead kernel hands S_{c+1} to the
-    next factor launch in measurement space (S_pre - U^T U) instead of gathering it from the downdated covariance.  Same
-    result as the default per-chunk factor -> downdate sequence to rounding, and parity with the oracle."""
-    stream = make_stream(N=N, frames=8, coord=coord)
-    chained = run_gpu(stream, tuning=dict(chain=2, graph=0, chunkLandmarks=chunk))
-    default = run_gpu(stream, tuning=dict(chain=0, graph=0, chunkLandmarks=chunk))
-    for g, r in zip(chained, default):
-        e = compare_states(g, r)
-        assert e["ids_equal"] and e["sigma"] < 5e-11 and e["state"] < 5e-11
-    _check(chained, run_oracle(stream))
-
-
-@pytest.mark.parametrize("N,chunk,coord", [(100, 32, 1), (150, 32, 0), (70, 5, 0)])
-def test_chained_correction_concurrent_downdates(N, chunk, coord):
-    """EQVIO_TUNE_CHAIN = 1: the same kernels with the downdates on a second stream behind completion counters must give
-    the bits of the stream-order mode (any race would show), with and without graph replay."""
-    stream = make_stream(N=N, frames=8, coord=coord)
-    serial = run_gpu(stream, tuning=dict(chain=2, graph=0, chunkLandmarks=chunk))
-    for graph in (0, 1):
-        got = run_gpu(stream, tuning=dict(chain=1, graph=graph, chunkLandmarks=chunk))
-        for g, r in zip(got, serial):
-            e = compare_states(g, r)
-            assert e["ids_equal"] and e["sigma"] == 0.0 and e["state"] == 0.0
-
-
 @pytest.mark.parametrize("discrete", [1, 0])
 def test_fused_observer_matches_two_kernel_form(discrete):
     """integrateObserverState as one software-pipelined kernel (sensor chain publishing segments to the landmark warps)
@@ -90,8 +63,7 @@ def test_sequence_matches_oracle(N, coord):
 
 
 @pytest.mark.parametrize("tuning", [dict(correction=1), dict(correction=0, chunkLandmarks=5), dict(correction=0, chunkLandmarks=16),
-                                    dict(correction=0, chunkLandmarks=1), dict(correction=0, chunkLandmarks=7, pipeline=1),
-                                    dict(correction=0, chunkLandmarks=16, pipeline=1)])
+                                    dict(correction=0, chunkLandmarks=1), dict(correction=0, chunkLandmarks=7)])
 def test_correction_evaluation_orders_agree(tuning):
     """Batch Cholesky sweep vs sequential chunks of any size: same result to rounding, both match the oracle."""
     stream = make_stream(N=40, frames=6, coord=1)

@@ -206,26 +206,3 @@ def test_vision_dropout_replays_graphs_with_many_imu_segments():
     assert max(len(f.imu) for f in seq) > 128
     worst, _, _ = _lockstep(stream, augment=True, frames=seq)
     print(f"drop-out sequence: worst {worst:.3e}")
-
-
-@pytest.mark.parametrize("N,chunk,coord,frames", [(40, 32, 0, 12), (100, 32, 1, 8), (150, 32, 0, 8), (70, 5, 0, 8), (33, 32, 0, 8),
-                                                  (256, 32, 0, 4), (21, 7, 1, 8)])
-@pytest.mark.parametrize("graph", [1, 0])
-def test_dataflow_factor_kernel_is_bit_identical(N, chunk, coord, frames, graph):
-    """chunk_factor_df_kernel (chain warp + per-tile flags, the default) runs the arithmetic of the round-1 barrier-synchronised
-    chunk_factor_kernel in the same order: identical bits along a sequence -- full and ragged chunks, 16 and 32 state columns
-    per CTA, staged and gathered S blocks -- and parity with the oracle."""
-    stream = make_stream(N=N, frames=frames, coord=coord)
-    old = run_gpu(stream, tuning=dict(factor=0, graph=0, chunkLandmarks=chunk))
-    new = run_gpu(stream, tuning=dict(factor=1, graph=graph, chunkLandmarks=chunk))
-    for k, (g, r) in enumerate(zip(new, old)):
-        e = compare_states(g, r)
-        assert e["ids_equal"] and e["sigma"] == 0.0 and e["state"] == 0.0, f"update {k}: {e}"
-    ref = run_oracle(stream, structured=N > 100)
-    _check(new, ref)
-    # the DMMA-fragment kernel (default) sums the rank-4 updates inside the tensor pipe: same result to rounding
-    mma = run_gpu(stream, tuning=dict(factor=2, graph=graph, chunkLandmarks=chunk))
-    for k, (g, r) in enumerate(zip(mma, old)):
-        e = compare_states(g, r)
-        assert e["ids_equal"] and e["sigma"] < 1e-11 and e["state"] < 1e-11, f"mma, update {k}: {e}"
-    _check(mma, ref)
