@@ -19,27 +19,32 @@ What is timed (CUDA events, after W warm-up steps, L2 flushed between steps outs
          processVisionData (H2D of pixels / ids / IMU inside), and a D2H read of the state estimate;
          host wall clock per frame (every frame ends synchronised with its estimate on the host), on
          K further frames of the same stream, L2 flushed between frames outside the bracket.
-         e2e.python_driver is the same loop driven through the ctypes mirror (CUDA events around each
-         synchronised step); with several sequences per GPU only that driver runs.
-         e2e.real_data_flow: K more frames through the C++ loop WITHOUT augmentLandmarkStates (how
-         eqvio_opt drives the filter on real data: ids are lost / added inside processVisionData).
+         e2e.python_driver is the same loop driven through the ctypes mirror; e2e.real_data_flow the
+         C++ loop WITHOUT augmentLandmarkStates (eqvio_opt's flow on real data).
+  sweep  (single-GPU default run only) the same measurement, shortened, at N = 64 and N = 1024 -- north_star's sizes --
+         with per-kernel roofline fractions, the parity error against the oracle after the warm-up updates and a CPU figure.
 Multi-GPU (torchrun, one rank per GPU): independent sequences (seed = rank), no collective on the
-data path; one NCCL all-gather of the trajectories at the end (timed into e2e).  scaling = weak.
+data path; the single collective of the path is the all-gather of the trajectories that closes a simulated lap
+(399 updates, main_sim.cpp:128-184): it is timed (e2e.collective_ms) and charged to e2e in proportion to the K
+updates timed, K / 399 of it.  `batched` = BASELINE configs[4]: 16 noisy Monte-Carlo instances per GPU
+(128 on 8 GPUs) replayed concurrently, poses gathered at the end.  scaling = weak.
 
---impl reference times the CPU restatement of the reference's dense Eigen path (oracle/, numpy fp64,
-same evaluation order incl. the doubly evaluated gain) on the host cores with the same stream.
+--impl reference times the reference's CPU path: oracle/cpu_update.c, a C restatement of its dense linear algebra in
+its own evaluation order (incl. the doubly evaluated gain) on the numpy-bundled OpenBLAS, all host threads; operands
+come from the numpy oracle outside the timed region and every C result is checked against the oracle's.
 """
 import argparse
 import json
 import os
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
+
+LAP_UPDATES = 399  # vision updates of the reference's simulated 20 s lap (20 Hz, the t = 0 image only augments)
 
 
 class StdoutGuard:
@@ -58,21 +63,13 @@ class StdoutGuard:
         os.dup2(2, 1)
 
 
-def all_host_threads():
-    """Context manager for the all-threads CPU arms.  torchrun exports OMP_NUM_THREADS=1 to its children, which would silently turn
-    the reference arm into a one-thread run: when the environment restricts the BLAS pools, lift them to the physical core count;
-    otherwise leave the pools at their own default."""
-    import contextlib
-
-    if not any(os.environ.get(v) for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")):
-        return contextlib.nullcontext()
+def host_threads():
     try:
         import psutil
-        from threadpoolctl import threadpool_limits
 
-        return threadpool_limits(limits=psutil.cpu_count(logical=False) or os.cpu_count() or 1)
+        return psutil.cpu_count(logical=False) or os.cpu_count() or 1
     except Exception:
-        return contextlib.nullcontext()
+        return os.cpu_count() or 1
 
 
 def parse():
@@ -85,8 +82,9 @@ def parse():
     ap.add_argument("--coord", type=int, default=0)
     ap.add_argument("--sequences-per-gpu", type=int, default=1, help="independent sequences (replicas) run concurrently per GPU")
     ap.add_argument("--batched-sequences", type=int, default=16,
-                    help="extra leg of the single-GPU, single-sequence run: this many independent sequences replayed concurrently on "
-                         "the GPU (BASELINE configs[4]: 16 Monte-Carlo instances per GPU), reported as \"batched\"; 0 = skip")
+                    help="extra leg: this many independent NOISY sequences per GPU replayed concurrently (BASELINE configs[4]: 16 "
+                         "Monte-Carlo instances per GPU), reported as \"batched\"; 0 = skip")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the N = 64 / N = 1024 side measurements of the default single-GPU run")
     ap.add_argument("--no-graph", action="store_true", help="issue per-kernel launches instead of replaying CUDA graphs")
     ap.add_argument("--no-stage", action="store_true", help="chunk factor kernel gathers Sigma[L_c, L_c] itself instead of the TMA tensor copy")
     ap.add_argument("--no-lookahead", action="store_true", help="one in-order downdate launch per chunk (no band / rest split)")
@@ -111,14 +109,20 @@ def workload_name(N, coord):
 
 
 # ---- algorithmic work per update (DESIGN.md "Roofline bookkeeping") -------------------------
-def alg_counts(N, n):
+def alg_counts(N, n, chunk_rows=64):
+    """Flops the sequential-chunk algorithm EXECUTES per update: the downdates m dim^2 (lower triangle: 2 m dim^2 / 2), the
+    structured propagation 72 dim^2, and per chunk of r rows its elimination r^3 / 3 and the substitution of dim right-hand
+    sides r^2 dim.  The m^3 / 3 + m^2 dim of factoring the full S and solving for the full W do not occur."""
     dim, m = 21 + 3 * N, 2 * n
+    chunks = [min(chunk_rows, m - r0) for r0 in range(0, m, chunk_rows)]
+    factor_flops = sum(r ** 3 / 3.0 + float(r) * r * dim for r in chunks)
     return dict(
-        dim=dim, m=m,
-        syrk_flops=float(dim) * dim * m,  # Sigma -= Y^T Y on the lower triangle (2 m dim^2 / 2)
-        trail_flops=float(m) * m * m / 3 + float(m) * m * dim,  # Cholesky of S + trsm of W
+        dim=dim, m=m, chunks=len(chunks),
+        syrk_flops=float(dim) * dim * m,
+        factor_flops=factor_flops,
+        trail_flops=float(m) * m * m / 3 + float(m) * m * dim,  # batch sweep only (Cholesky of S + trsm of W)
         prop_bytes=2.0 * 8 * dim * dim,  # read + write Sigma once
-        upd_flops=float(m) ** 3 / 3 + float(m) * m * dim + 2.0 * m * dim * dim / 2 + 72.0 * dim * dim,
+        upd_flops=float(dim) * dim * m + 72.0 * dim * dim + factor_flops,
         upd_bytes=8.0 * (4 * dim * dim + 4 * m * dim))
 
 
@@ -166,8 +170,9 @@ class ClockSampler:
                     samples=len(self.samples))
 
 
-def oracle_stream(stream, settings_kw):
-    """simdata stream -> the oracle's containers (cpu_baseline / reference arm only)."""
+# ---- CPU arm --------------------------------------------------------------------------------------------------
+def oracle_filter(stream, settings_kw):
+    """simdata stream -> an oracle VIOFilter + camera (cpu_baseline / reference arm / sweep parity only)."""
     from oracle import eqf
     from oracle.camera import PinholeCamera
     from oracle.liegroups import SE3
@@ -180,74 +185,44 @@ def oracle_stream(stream, settings_kw):
     cam = PinholeCamera(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"])
     init = eqf.VIOState(eqf.VIOSensorState.fromFlat(stream.init_sensor), stream.init_p, stream.init_ids)
     st.cameraOffset = SE3(stream.init_sensor[16:20], stream.init_sensor[20:23])
-    return st, cam, init
-
-
-def time_cpu(stream, settings_kw, warmup, steps, structured=False):
-    """The reference's dense evaluation order on the host cores: returns (updates/s, per-stage seconds).
-    structured=True times the minimal-flop CPU formulation instead (sparse A and C, one Cholesky of S, Sigma -= Y^T Y),
-    so that the GPU speed-up is not credited with purely algorithmic gains."""
-    from oracle import eqf
-
-    st, cam, init = oracle_stream(stream, settings_kw)
     flt = eqf.VIOFilter(st, init, 0.0)
-    flt.filterState.mirrorLazyEvaluation = not structured
-    flt.filterState.structuredEvaluation = structured
-    t_total = 0.0
-    done = 0
-    for k, fr in enumerate(stream.frames[: 1 + warmup + steps]):
-        if k == 1 + warmup:
-            flt.timing = {"propagation": 0.0, "preprocessing": 0.0, "correction": 0.0}
-        t0 = time.perf_counter()
-        for row in fr.imu:
-            flt.processIMUData(eqf.IMUVelocity(row[0], row[1:4], row[4:7], row[7:10], row[10:13]))
-        meas = eqf.VisionMeasurement.fromArrays(fr.stamp, fr.ids, fr.y, cam)
-        flt.augmentLandmarkStates(meas.getIds(), eqf.VIOState(None, fr.provided_p, fr.ids))
-        flt.processVisionData(meas)
-        flt.stateEstimate()
-        if k >= 1 + warmup:
-            t_total += time.perf_counter() - t0
-            done += 1
-    return done / t_total, dict(flt.timing), done
+    flt.filterState.structuredEvaluation = True  # operands are recorded, not timed: the cheap evaluation of the same update
+    return flt, cam
 
 
-def cpu_variants(stream, settings_kw, warmup, dense_ups):
-    """Side figures of cpu_baseline: the dense reference order on ONE thread (the reference build never enables OpenMP,
-    so its Eigen GEMMs are single-core) and the structured + Cholesky formulation on all threads.  Bounded samples."""
-    out = {}
-    n1 = int(max(2, min(10, 4.0 * dense_ups / 8.0)))  # ~4 s assuming 1 thread is <= 8x slower
-    try:
-        from threadpoolctl import threadpool_limits
+def cpu_arm(stream, settings_kw, warmup, sample_updates, variants=True):
+    """CPU baseline on a bounded sample: `sample_updates` consecutive updates of the stream after `warmup` updates.  The numpy
+    oracle produces the operands (untimed); oracle/cpu_update.c runs and times the dense stages in the reference's evaluation
+    order on all host threads (the headline figure), on one thread (the reference build never enables OpenMP: its Eigen
+    products are single-core) and in the block-structured + Cholesky form."""
+    from oracle import cpu_baseline as cb
 
-        with threadpool_limits(limits=1):
-            ups1, _, d1 = time_cpu(stream, settings_kw, 1, n1)
-        out["single_thread"] = dict(value=ups1, cores=1, sample=f"{d1} updates, dense reference order")
-    except Exception as e:  # threadpoolctl missing: say so instead of guessing
-        out["single_thread"] = dict(value=None, note=repr(e))
-    ns = int(max(3, min(30, 4.0 * dense_ups)))
-    try:
-        from threadpoolctl import threadpool_limits
-
-        # one thread as well: the pair (single_thread, structured_cholesky) isolates the algorithmic gain; with all threads the
-        # skinny products of this form run slower than on one (OpenBLAS threading overhead, two BLAS pools under numpy + scipy)
-        with threadpool_limits(limits=1):
-            ups_s, st_s, ds = time_cpu(stream, settings_kw, 1, ns, structured=True)
-        out["structured_cholesky"] = dict(value=ups_s, cores=1, sample=f"{ds} updates; block-structured A / C, one Cholesky of S, "
-                                          "Sigma -= Y^T Y (F_alg of SURVEY 8d; numpy + LAPACK), same results to 1e-11; at N = 256 "
-                                          "Python / numpy overheads are a large part of it",
-                                          stage_ms={k: 1000.0 * v / ds for k, v in st_s.items()})
-    except Exception as e:
-        out["structured_cholesky"] = dict(value=None, note=repr(e))
+    flt, cam = oracle_filter(stream, settings_kw)
+    cb.record_updates(flt, stream.frames[:1 + warmup], cam)
+    ups = cb.record_updates(flt, stream.frames[1 + warmup:1 + warmup + sample_updates], cam)
+    nthreads = host_threads()
+    dense = cb.run_updates(ups, structured=False, threads=nthreads)
+    out = dict(value=dense["updates_per_s"], unit="updates/s", cores=dense["threads"], kind="port",
+               sample=f"{dense['updates']} consecutive updates of sequence 0 (same inputs) after {warmup} warm-up updates; C restatement "
+               "(oracle/cpu_update.c, OpenBLAS) of the reference's dense evaluation order incl. the doubly evaluated gain; "
+               "operands from the numpy oracle outside the timed region; O(N) Lie-group / Jacobian glue not included",
+               stage_ms=dense["stage_ms"], worst_rel_error_vs_oracle=dense["worst_rel_error_vs_oracle"])
+    if variants:
+        one = cb.run_updates(ups[:max(1, min(len(ups), 3))], structured=False, threads=1)
+        out["single_thread"] = dict(value=one["updates_per_s"], cores=1, stage_ms=one["stage_ms"],
+                                    sample=f"{one['updates']} updates, dense reference order (the reference's own build is single-threaded)")
+        s1 = cb.run_updates(ups, structured=True, threads=1)
+        sa = cb.run_updates(ups, structured=True, threads=nthreads)
+        out["structured_cholesky"] = dict(value=s1["updates_per_s"], cores=1, stage_ms=s1["stage_ms"], all_threads_value=sa["updates_per_s"],
+                                          all_threads_cores=sa["threads"], worst_rel_error_vs_oracle=s1["worst_rel_error_vs_oracle"],
+                                          sample="block-structured A / C, one Cholesky of S, Sigma -= Y^T Y (the flops the GPU path executes)")
     return out
 
 
-def blas_threads():
-    try:
-        from threadpoolctl import threadpool_info
-
-        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
-    except Exception:
-        return os.cpu_count() or 1
+def cpu_sample_size(N, K):
+    dim = 21 + 3 * N
+    est_s = 17.0 * dim ** 3 / 200e9 + 0.01  # ~17 dim^3 flops of the dense path at a conservative 200 GFLOP/s on all threads
+    return int(max(2, min(K, 10.0 / est_s)))
 
 
 def run_reference(args, rank, world, guard):
@@ -257,23 +232,226 @@ def run_reference(args, rank, world, guard):
 
     N = args.landmarks
     skw = settings_dict(args.coord)
-    frames = 1 + args.warmup + args.steps
+    steps = min(args.steps, max(2, cpu_sample_size(N, args.steps) * 2))  # each step is one update of a bounded sample
+    frames = 1 + args.warmup + steps
     stream = record_stream(SimConfig.benchmark(N, 0, duration=20.0 if frames <= 399 else float((frames + 1) // 20 + 2)), frames)
-    with all_host_threads():
-        ups, stages, done = time_cpu(stream, skw, args.warmup, args.steps)
-        cores = blas_threads()
-    sample = f"{done} consecutive updates of the same stream after {args.warmup} warm-up updates"
-    variants = cpu_variants(stream, skw, min(args.warmup, 2), ups)
-    line = dict(impl="reference", metric="vision-updates/sec", value=ups, unit="updates/s", n_gpus=args.gpus, steps=done,
+    cb = cpu_arm(stream, skw, args.warmup, steps)
+    ups = cb["value"]
+    line = dict(impl="reference", metric="vision-updates/sec", value=ups, unit="updates/s", n_gpus=args.gpus, steps=steps,
                 warmup=args.warmup, ms_per_step=1000.0 / ups, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f64", data="synthetic",
-                config=dict(workload=workload_name(N, args.coord), landmarks=N, impl_detail="oracle port of the dense Eigen path "
-                            "(numpy fp64 + OpenBLAS, reference evaluation order incl. doubly evaluated gain); the reference "
-                            "itself cannot be built here (Eigen3/OpenCV/yaml-cpp absent)"),
-                cpu_baseline=dict(value=ups, unit="updates/s", cores=cores, kind="port", sample=sample,
-                                  stage_ms={k: 1000.0 * v / done for k, v in stages.items()}, **variants),
+                config=dict(workload=workload_name(N, args.coord), landmarks=N, impl_detail="C restatement of the reference's dense Eigen "
+                            "path (oracle/cpu_update.c on the numpy-bundled OpenBLAS, reference evaluation order incl. the doubly "
+                            "evaluated gain, all host threads); the reference itself cannot be built here (Eigen3/OpenCV/yaml-cpp absent)"),
+                cpu_baseline=cb,
                 e2e=dict(value=ups, unit="updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     guard.emit(line)
+
+
+# ---- GPU arm --------------------------------------------------------------------------------------------------
+def fp64_peak(torch):
+    """cuBLAS DGEMM 4096^3 as the fp64 denominator (MEASURED_PEAKS.json has HBM and bf16 only; tcgen05 has no fp64 kind, the
+    path runs on the FP64 DMMA pipe like cuBLAS does)."""
+    a = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
+    b = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        a @ b
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 2.0 * 4096 ** 3 / (best * 1e-3) / 1e12, best
+
+
+def kernel_rooflines(prof, nprof, cnt, N, hbm_peak, f64_peak, traffic, tc=False, bf16_peak=1590.0):
+    """Per kernel class: time per update, launches, and achieved / peak of the bound that applies -- flops for the factor and
+    downdate kernels (fp64 pipe, denominator = measured DGEMM), bytes for the propagation (HBM)."""
+    kern = {}
+    for name, d in prof.items():
+        if d["launches"] == 0:
+            continue
+        ms = d["ms"] / max(nprof, 1)
+        e = dict(ms_per_update=ms, launches_per_update=d["launches"] / max(nprof, 1), avg_launch_us=1000.0 * d["ms"] / d["launches"])
+        if name == "downdate" and tc:
+            e.update(bound="hbm", achieved=2.0 * 8 * cnt["dim"] ** 2 * (cnt["m"] / 64.0) / (ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s",
+                     tensor_tflops=6.0 * cnt["syrk_flops"] / (ms * 1e-3) / 1e12, tensor_peak_tflops=bf16_peak)
+        elif name == "downdate":
+            e.update(bound="tensor", achieved=cnt["syrk_flops"] / (ms * 1e-3) / 1e12, peak=f64_peak, unit="TFLOP/s")
+        elif name == "chunk_factor":
+            e.update(bound="tensor", achieved=cnt["factor_flops"] / (ms * 1e-3) / 1e12, peak=f64_peak, unit="TFLOP/s",
+                     note="latency-bound: a chain of 64 dependent pivots per launch; the fraction is of the fp64 (DGEMM) peak")
+        elif name == "chol_trail":
+            e.update(bound="tensor", achieved=cnt["trail_flops"] / (ms * 1e-3) / 1e12, peak=f64_peak, unit="TFLOP/s")
+        elif name == "prop_ll":
+            e.update(bound="hbm", achieved=cnt["prop_bytes"] / (ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s")
+        if "achieved" in e:
+            e["frac"] = e["achieved"] / e["peak"]
+        e["traffic"] = traffic.get(name, {}).get(str(N))
+        kern[name] = e
+    return kern
+
+
+class Sequence:
+    """One simulated sequence and its filter."""
+
+    def __init__(self, eb, stream, N, device, args):
+        self.stream = stream
+        xi0 = eb.VIOState(eb.VIOSensorState.fromFlat(stream.init_sensor), stream.init_p, stream.init_ids)
+        self.flt = eb.VIOFilter(eb.Settings(**settings_dict(args.coord)), xi0, 0.0, capacity=N + 8, device=device)
+        if args.no_graph:
+            self.flt.setTuning(graph=0)
+        if args.no_lookahead:
+            self.flt.setTuning(lookahead=0)
+        if args.no_stage:
+            self.flt.setTuning(stageS=0)
+        if args.downdate == "tc":
+            self.flt.setTuning(downdate=1)
+
+    def step(self, eb, cam, k):
+        fr = self.stream.frames[k]
+        self.flt.processIMUArray(fr.imu)
+        self.flt.augmentLandmarkStates(fr.ids, eb.VIOState(eb.VIOSensorState(), fr.provided_p, fr.ids))
+        self.flt.processVisionArrays(fr.stamp, fr.ids, fr.y, cam)
+        return self.flt.stateEstimate()
+
+
+def h2d_bytes(fr):
+    return fr.imu.nbytes + fr.y.nbytes + 2 * 4 * len(fr.ids) + 8 * 13  # IMU rows, pixels, index maps, frame header scalars
+
+
+def measure_single(eb, torch, args, N, K, W, P, device, flush_buf, sampler=None, stream=None, parity=False):
+    """One sequence on one GPU: `value` (CUDA events per update), `e2e` (C++ host loop, host buffers), the real-data flow and the
+    per-kernel profile.  Returns a dict of raw figures (ms sums, counts) for the caller to combine across ranks."""
+    from eqvio_b200.replicas import trajectory_row
+    from simdata import SimConfig, record_stream
+
+    K3 = K if 1 + W + 3 * K + P <= LAP_UPDATES else 0
+    total = 1 + W + 2 * K + K3 + P
+    if stream is None:
+        stream = record_stream(SimConfig.benchmark(N, 0, duration=20.0 if total <= LAP_UPDATES else float((total + 1) // 20 + 2)), total)
+    seq = Sequence(eb, stream, N, device, args)
+    flt = seq.flt
+    flt.enableStageTiming(True)
+    cam = eb.Camera(**stream.camera)
+    out = dict(stream=stream, seq=seq)
+    for k in range(0, 1 + W):
+        seq.step(eb, cam, k)
+    torch.cuda.synchronize()
+    if parity:
+        # the CUDA path against the oracle after the t = 0 image + W warm-up updates (same inputs, both from the same prior)
+        from oracle import eqf
+
+        ofl, ocam = oracle_filter(stream, settings_dict(args.coord))
+        for fr in stream.frames[:1 + W]:
+            for row in fr.imu:
+                ofl.processIMUData(eqf.IMUVelocity(row[0], row[1:4], row[4:7], row[7:10], row[10:13]))
+            meas = eqf.VisionMeasurement.fromArrays(fr.stamp, fr.ids, fr.y, ocam)
+            ofl.augmentLandmarkStates(meas.getIds(), eqf.VIOState(None, fr.provided_p, fr.ids))
+            ofl.processVisionData(meas)
+        fs, est, oest = flt.viewEqFState(), flt.stateEstimate(), ofl.stateEstimate()
+        S_ref = ofl.viewEqFState().Sigma
+        x_g = np.concatenate([est.sensor.flat(), est.p.reshape(-1)])
+        x_o = np.concatenate([oest.sensor.flat(), oest.p.reshape(-1)])
+        same_ids = bool(np.array_equal(np.asarray(est.ids), np.asarray(oest.ids)))
+        out["parity"] = dict(updates=W, ids_equal=same_ids,
+                             sigma_rel_fro=float(np.linalg.norm(fs.Sigma - S_ref) / np.linalg.norm(S_ref)) if same_ids else None,
+                             state_rel_fro=float(np.linalg.norm(x_g - x_o) / np.linalg.norm(x_o)) if same_ids else None)
+    launches0 = flt.launchCount()
+    dev_ms = wall_in = 0.0
+    stage_acc = dict(propagation=0.0, preprocessing=0.0, correction=0.0)
+    traj = np.zeros((K, 11))
+    h2d = d2h = 0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for kk in range(K):
+        k = 1 + W + kk
+        if flush_buf is not None:
+            flush_buf.fill_(kk & 0xFF)
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ev[kk][0].record()
+        est = seq.step(eb, cam, k)
+        ev[kk][1].record()
+        wall_in += time.perf_counter() - t0
+        if sampler is not None and kk % max(1, K // 8) == 0:
+            if flush_buf is not None:
+                flush_buf.fill_(kk & 0xFF)  # keep the GPU busy while NVML is queried
+            sampler.sample()
+        sm_ = flt.stageMs()
+        for key in stage_acc:
+            stage_acc[key] += sm_[key]
+        dev_ms += sm_["propagation"] + sm_["preprocessing"] + sm_["correction"]
+        fr = stream.frames[k]
+        traj[kk] = trajectory_row(fr.stamp, est)
+        h2d += h2d_bytes(fr)
+        d2h += 8 * (23 + 3 * len(est.ids)) + 8 * 3 * N + 4 * (2 + N)  # state estimate + gate scalars + flag/status words
+    torch.cuda.synchronize()
+    py_ms = sum(a.elapsed_time(b) for a, b in ev)
+    out.update(dev_ms=dev_ms, py_ms=py_ms, wall_in=wall_in, stage_acc=stage_acc, traj=traj, h2d=h2d // K, d2h=d2h // K,
+               launches=flt.launchCount() - launches0)
+    # e2e through the C++ host loop (stage-event recording is instrumentation for `value`: off here)
+    flt.enableStageTiming(False)
+    fms, est_s = flt.replay(stream.frames[1 + W + K:1 + W + 2 * K], cam, flushBytes=0 if args.no_l2_flush else 256 << 20)
+    assert np.isfinite(est_s).all()
+    out["cpp_ms"] = float(fms.sum())
+    out["real_ms"] = 0.0
+    if K3:
+        class _NoAug:
+            def __init__(self, fr):
+                self.stamp, self.imu, self.ids, self.y, self.provided_p = fr.stamp, fr.imu, fr.ids, fr.y, None
+
+        fms3, est3 = flt.replay([_NoAug(fr) for fr in stream.frames[1 + W + 2 * K:1 + W + 2 * K + K3]], cam,
+                                flushBytes=0 if args.no_l2_flush else 256 << 20)
+        assert np.isfinite(est3).all()
+        out["real_ms"] = float(fms3.sum())
+    out["K3"] = K3
+    flt.enableStageTiming(True)
+    # per-kernel profile on extra steps (event pairs around every launch of a class; the graph path is off while profiling)
+    flt.enableKernelProfile(True)
+    flt.kernelProfile(reset=True)
+    prof_stage = dict(propagation=0.0, preprocessing=0.0, correction=0.0)
+    nprof = 0
+    for k in range(1 + W + 2 * K + K3, 1 + W + 2 * K + K3 + P):
+        if flush_buf is not None:
+            flush_buf.fill_(1)
+            torch.cuda.synchronize()
+        seq.step(eb, cam, k)
+        for key, v in flt.stageMs().items():
+            prof_stage[key] += v
+        nprof += 1
+    out.update(prof=flt.kernelProfile(reset=True), nprof=nprof, prof_stage=prof_stage, n_meas=len(stream.frames[1 + W].ids),
+               n_state=flt.numLandmarks())
+    flt.enableKernelProfile(False)
+    return out
+
+
+def batched_leg(eb, args, N, B, Kb, Wb, device, first_instance):
+    """B independent NOISY Monte-Carlo sequences (BASELINE configs[4]: 16 per GPU) replayed concurrently through the C ABI with HOST
+    buffers, one C++ host thread per sequence (eqvio_replay_batch), wall clock over the whole batch.  Returns
+    (wall ms, updates, launches, final sensor states (B, 23))."""
+    from simdata import SimConfig, record_stream
+
+    streams = [record_stream(SimConfig.benchmark(N, first_instance + b, duration=20.0, inputNoise=True, outputNoise=True), 1 + Wb + Kb)
+               for b in range(B)]
+    cam = eb.Camera(**streams[0].camera)
+    filters = []
+    for sm_ in streams:
+        bf = eb.VIOFilter(eb.Settings(**settings_dict(args.coord)), eb.VIOState(eb.VIOSensorState.fromFlat(sm_.init_sensor), sm_.init_p, sm_.init_ids),
+                          0.0, capacity=N + 8, device=device)
+        if args.no_graph:
+            bf.setTuning(graph=0)
+        filters.append(bf)
+    eb.replayBatch(filters, [sm_.frames[:1 + Wb] for sm_ in streams], cam)  # t = 0 image + warm-up (graph capture)
+    l0 = sum(f_.launchCount() for f_ in filters)
+    _, est, wall = eb.replayBatch(filters, [sm_.frames[1 + Wb:] for sm_ in streams], cam)
+    assert np.isfinite(est).all()
+    launches = int(sum(f_.launchCount() for f_ in filters) - l0)
+    for bf in filters:
+        bf.close()
+    return wall, B * Kb, launches, np.ascontiguousarray(est[:, -1, :])
 
 
 def run_b200(args, rank, local_rank, world, guard):
@@ -297,212 +475,118 @@ def run_b200(args, rank, local_rank, world, guard):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     N, K, W, P, R = args.landmarks, args.steps, args.warmup, args.profile_steps, args.sequences_per_gpu
-    skw = settings_dict(args.coord)
-    K3 = K if 1 + W + 3 * K + P <= 399 else 0  # third pass (real-data flow) only when the 20 s lap has frames left
-    total_frames = 1 + W + 2 * K + K3 + P  # warm-up | timed (Python driver) | C++ host loop | C++ loop, real-data flow | per-kernel profile
-    # the reference's simulated lap is 20 s (399 updates after the t = 0 image); longer runs keep circling the same trajectory
-    duration = 20.0 if total_frames <= 399 else float((total_frames + 1) // 20 + 2)
-    # weak scaling: every rank owns R independent sequences (instance id = seed), contiguous blocks of ids
+    dev = torch.device("cuda", local_rank)
+    flush_buf = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    sampler = ClockSampler(local_rank)
     total_instances = R * world
     mine = shard_instances(total_instances, world, rank)
-    if args.device_sim:  # IMU / vision streams of all local instances from one device launch
-        from eqvio_b200.simulator import DeviceSimulator
+    if dist:  # bring the collective path up (communicator, buffers) before anything is timed
+        gather_trajectories({inst: np.zeros((K, 11)) for inst in mine}, total_instances, device=dev)
 
-        dsim = DeviceSimulator([SimConfig.benchmark(N, inst, duration=duration) for inst in mine], device=local_rank)
-        streams = dsim.record_streams(total_frames)
-        dsim.close()
+    collective_ms = 0.0
+    if R == 1:
+        K3 = K if 1 + W + 3 * K + P <= LAP_UPDATES else 0
+        total = 1 + W + 2 * K + K3 + P
+        duration = 20.0 if total <= LAP_UPDATES else float((total + 1) // 20 + 2)
+        if args.device_sim:  # IMU / vision streams from one device launch
+            from eqvio_b200.simulator import DeviceSimulator
+
+            dsim = DeviceSimulator([SimConfig.benchmark(N, mine[0], duration=duration)], device=local_rank)
+            stream = dsim.record_streams(total)[0]
+            dsim.close()
+        else:
+            stream = record_stream(SimConfig.benchmark(N, mine[0], duration=duration), total)
+        if dist:
+            dist.barrier()
+        m = measure_single(eb, torch, args, N, K, W, P, local_rank, flush_buf, sampler=sampler, stream=stream)
+        dev_ms, py_ms, cpp_ms, real_ms = m["dev_ms"], m["py_ms"], m["cpp_ms"], m["real_ms"]
+        traj = {mine[0]: m["traj"]}
     else:
-        streams = [record_stream(SimConfig.benchmark(N, inst, duration=duration), total_frames) for inst in mine]
-    st = eb.Settings(**skw)
-    filters = []
-    for sm in streams:
-        xi0 = eb.VIOState(eb.VIOSensorState.fromFlat(sm.init_sensor), sm.init_p, sm.init_ids)
-        flt = eb.VIOFilter(st, xi0, 0.0, capacity=N + 8, device=local_rank)
-        flt.enableStageTiming(True)
-        if args.no_graph:
-            flt.setTuning(graph=0)
-        if args.no_lookahead:
-            flt.setTuning(lookahead=0)
-        if args.no_stage:
-            flt.setTuning(stageS=0)
-        if args.downdate == "tc":
-            flt.setTuning(downdate=1)
-        filters.append(flt)
-    cam = eb.Camera(**streams[0].camera)
-    flush_buf = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-
-    pool = None
-    if len(filters) > 1:
-        # one host thread per sequence: every C-ABI call releases the GIL, the filters own independent streams, so
-        # the host-side work of the replicas overlaps across cores and their kernels overlap on the GPU
+        # several sequences per GPU (--sequences-per-gpu): Python-threaded loop for `value` (host bracket of each step: the
+        # sequences' device times overlap), C++ batch for e2e
         from concurrent.futures import ThreadPoolExecutor
 
-        pool = ThreadPoolExecutor(max_workers=min(len(filters), max(1, (os.cpu_count() or 2) - 1)))
-        torch.cuda.set_device(local_rank)
-
-    def step_one(i, k):
-        flt, fr = filters[i], streams[i].frames[k]
-        flt.processIMUArray(fr.imu)
-        flt.augmentLandmarkStates(fr.ids, eb.VIOState(eb.VIOSensorState(), fr.provided_p, fr.ids))
-        flt.processVisionArrays(fr.stamp, fr.ids, fr.y, cam)
-        return flt.stateEstimate()
-
-    def step(k):
-        """One vision update of every local sequence; returns the state estimates."""
-        if pool is None:
-            return [step_one(0, k)]
-        return list(pool.map(lambda i: step_one(i, k), range(len(filters))))
-
-    def h2d_bytes(fr):
-        return fr.imu.nbytes + fr.y.nbytes + 2 * 4 * len(fr.ids) + 8 * 13  # IMU rows, pixels, index maps, frame header scalars
-
-    step(0)  # t = 0 image: augments only
-    for k in range(1, 1 + W):
-        step(k)
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if dist:  # bring the collective path up (communicator, buffers) before anything is timed
-        gather_trajectories({inst: np.zeros((K, 11)) for inst in mine}, total_instances, device=torch.device("cuda", local_rank))
-    launches0 = sum(f.launchCount() for f in filters)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    dev_ms = 0.0
-    stage_acc = dict(propagation=0.0, preprocessing=0.0, correction=0.0)
-    traj = {inst: np.zeros((K, 11)) for inst in mine}
-    h2d = d2h = 0
-    wall_in = 0.0
-    for kk in range(K):
-        k = 1 + W + kk
-        if flush_buf is not None:
-            flush_buf.fill_(kk & 0xFF)
-            torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ev[kk][0].record()
-        ests = step(k)
-        ev[kk][1].record()
-        wall_in += time.perf_counter() - t0
-        if kk % max(1, K // 8) == 0:
+        total = 1 + W + 2 * K
+        streams = [record_stream(SimConfig.benchmark(N, inst, duration=20.0 if total <= LAP_UPDATES else float((total + 1) // 20 + 2)), total)
+                   for inst in mine]
+        seqs = [Sequence(eb, sm_, N, local_rank, args) for sm_ in streams]
+        cam = eb.Camera(**streams[0].camera)
+        pool = ThreadPoolExecutor(max_workers=min(len(seqs), max(1, (os.cpu_count() or 2) - 1)))
+        for k in range(0, 1 + W):
+            list(pool.map(lambda s: s.step(eb, cam, k), seqs))
+        torch.cuda.synchronize()
+        launches0 = sum(s.flt.launchCount() for s in seqs)
+        dev_ms = 0.0
+        traj = {inst: np.zeros((K, 11)) for inst in mine}
+        h2d = d2h = 0
+        for kk in range(K):
+            k = 1 + W + kk
             if flush_buf is not None:
-                flush_buf.fill_(kk & 0xFF)  # keep the GPU busy while NVML is queried
-            sampler.sample()
-        per_filter = []
-        for flt in filters:
-            sm_ = flt.stageMs()
-            for key in stage_acc:
-                stage_acc[key] += sm_[key] / len(filters)
-            per_filter.append(sm_["propagation"] + sm_["preprocessing"] + sm_["correction"])
-        # several sequences per GPU run concurrently on their own streams: their device times overlap, so the step is
-        # charged its host-side bracket (all sequences done) instead of a sum of per-filter device times
-        dev_ms += max(per_filter) if len(filters) == 1 else 1000.0 * (time.perf_counter() - t0)
-        for inst, est, sm in zip(mine, ests, streams):
-            traj[inst][kk] = trajectory_row(sm.frames[k].stamp, est)
-            h2d += h2d_bytes(sm.frames[k])
-            d2h += 8 * (23 + 3 * len(est.ids)) + 8 * 3 * N + 4 * (2 + N)  # state estimate + gate scalars + flag/status words
-    torch.cuda.synchronize()
-    launches = sum(f.launchCount() for f in filters) - launches0
-    e2e_ms = sum(a.elapsed_time(b) for a, b in ev)
-    # the single collective of the path: all-gather of the trajectories at the end (timed into e2e)
+                flush_buf.fill_(kk & 0xFF)
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ests = list(pool.map(lambda s: s.step(eb, cam, k), seqs))
+            dev_ms += 1000.0 * (time.perf_counter() - t0)
+            if kk % max(1, K // 8) == 0:
+                sampler.sample()
+            for inst, est, sm_ in zip(mine, ests, streams):
+                traj[inst][kk] = trajectory_row(sm_.frames[k].stamp, est)
+                h2d += h2d_bytes(sm_.frames[k])
+                d2h += 8 * (23 + 3 * len(est.ids)) + 8 * 3 * N + 4 * (2 + N)
+        py_ms = dev_ms
+        _, est_b, wall_b = eb.replayBatch([s.flt for s in seqs], [sm_.frames[1 + W + K:1 + W + 2 * K] for sm_ in streams], cam)
+        assert np.isfinite(est_b).all()
+        cpp_ms, real_ms = float(wall_b), 0.0
+        m = dict(launches=sum(s.flt.launchCount() for s in seqs) - launches0, h2d=h2d // K, d2h=d2h // K, K3=0,
+                 stage_acc=dict(propagation=0.0, preprocessing=0.0, correction=dev_ms), wall_in=dev_ms / 1e3, prof={}, nprof=0,
+                 prof_stage={}, n_meas=len(streams[0].frames[1 + W].ids), n_state=seqs[0].flt.numLandmarks(), seq=seqs[0], stream=streams[0])
+
+    # the single collective of the path: all-gather of the trajectories (closes a simulated lap)
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if dist:
         dist.barrier()  # the slowest rank's steps are already charged through the max over ranks: do not charge the skew twice
         torch.cuda.synchronize()
     g0.record()
-    all_traj = gather_trajectories(traj, total_instances, device=torch.device("cuda", local_rank) if dist else None)
+    all_traj = gather_trajectories(traj, total_instances, device=dev if dist else None)
     g1.record()
     torch.cuda.synchronize()
     if dist:
-        e2e_ms += g0.elapsed_time(g1)
+        collective_ms = g0.elapsed_time(g1)
     assert all_traj.shape == (total_instances, K, 11) and np.isfinite(all_traj).all()
 
-    # e2e through a C++ host loop over the C ABI (eqvio_replay: the reference's host is C++): the next K frames, per frame
-    # processIMUData x 10, augmentLandmarkStates, processVisionData, stateEstimate on host buffers, host wall clock per
-    # frame (every frame ends synchronised with its estimate on the host), L2 flushed between frames outside the bracket.
-    # Stage-event recording is off here (it is instrumentation for `value`).
-    cpp_ms = 0.0
-    real_ms = 0.0
-    if len(filters) == 1:
-        filters[0].enableStageTiming(False)
-        fms, est_s = filters[0].replay(streams[0].frames[1 + W + K:1 + W + 2 * K], cam, flushBytes=0 if args.no_l2_flush else 256 << 20)
-        assert np.isfinite(est_s).all()
-        cpp_ms = float(fms.sum())
-        if dist:
-            cpp_ms += g0.elapsed_time(g1)  # the one collective of the path counts into e2e
-        if K3:
-            # the same loop WITHOUT augmentLandmarkStates, as eqvio_opt drives the filter on real data: lost ids are pruned and
-            # new ids added inside processVisionData (planned frames, DESIGN.md 4)
-            class _NoAug:
-                def __init__(self, fr):
-                    self.stamp, self.imu, self.ids, self.y, self.provided_p = fr.stamp, fr.imu, fr.ids, fr.y, None
-
-            fms3, est3 = filters[0].replay([_NoAug(fr) for fr in streams[0].frames[1 + W + 2 * K:1 + W + 2 * K + K3]], cam,
-                                           flushBytes=0 if args.no_l2_flush else 256 << 20)
-            assert np.isfinite(est3).all()
-            real_ms = float(fms3.sum())
-        filters[0].enableStageTiming(True)
-    elif len(filters) > 1:
-        # several sequences per GPU: one C++ host thread per sequence (eqvio_replay_batch), wall clock over the whole batch of
-        # R x K frames; no L2 flush between frames here (the sequences run concurrently; R covariance pairs exceed L2 anyway
-        # from R ~ 12 at N = 256)
-        for flt_ in filters:
-            flt_.enableStageTiming(False)
-        _, est_b, wall_b = eb.replayBatch(filters, [sm_.frames[1 + W + K:1 + W + 2 * K] for sm_ in streams], cam)
-        for flt_ in filters:
-            flt_.enableStageTiming(True)
-        assert np.isfinite(est_b).all()
-        cpp_ms = float(wall_b)
-    if dist:
-        dist.barrier()
-
-    # per-kernel profile on extra steps of the first sequence (event pairs around every launch of a class; the
-    # graph path is off while profiling)
-    flt = filters[0]
-    flt.enableKernelProfile(True)
-    flt.kernelProfile(reset=True)
-    prof_stage = dict(propagation=0.0, preprocessing=0.0, correction=0.0)
-    nprof = 0
-    for k in range(1 + W + 2 * K + K3, 1 + W + 2 * K + K3 + P):
-        if flush_buf is not None:
-            flush_buf.fill_(1)
-            torch.cuda.synchronize()
-        step(k)
-        for key, v in flt.stageMs().items():
-            prof_stage[key] += v
-        nprof += 1
-    prof = flt.kernelProfile(reset=True)
-    flt.enableKernelProfile(False)
-    n_meas = len(streams[0].frames[1 + W].ids)
-    n_state = flt.numLandmarks()
-
-    # Batched leg (single GPU, single-sequence run only): B independent sequences -- the Monte-Carlo instances of BASELINE
-    # configs[4], 16 per GPU -- replayed concurrently through the same C ABI with HOST buffers, one C++ host thread per sequence
-    # (eqvio_replay_batch), wall clock over the whole batch.  A reported side figure: `value` / `e2e` stay the single sequence.
+    # batched leg: BASELINE configs[4], B noisy Monte-Carlo instances per GPU, poses gathered at the end
     batched = None
     B = args.batched_sequences
-    if world == 1 and R == 1 and B > 1:
+    if R == 1 and B > 1:
         Kb, Wb = min(K, 40 if N <= 256 else 15), 3
-        bstreams = [record_stream(SimConfig.benchmark(N, 1000 + b, duration=20.0), 1 + Wb + Kb) for b in range(B)]
-        bfilters = []
-        for sm_ in bstreams:
-            bf = eb.VIOFilter(st, eb.VIOState(eb.VIOSensorState.fromFlat(sm_.init_sensor), sm_.init_p, sm_.init_ids), 0.0, capacity=N + 8,
-                              device=local_rank)
-            if args.no_graph:
-                bf.setTuning(graph=0)
-            bfilters.append(bf)
-        eb.replayBatch(bfilters, [sm_.frames[:1 + Wb] for sm_ in bstreams], cam)  # t = 0 image + warm-up (graph capture)
-        l0 = sum(f_.launchCount() for f_ in bfilters)
-        _, est_bb, wall_bb = eb.replayBatch(bfilters, [sm_.frames[1 + Wb:] for sm_ in bstreams], cam)
-        assert np.isfinite(est_bb).all()
-        batched = dict(sequences=B, steps_per_sequence=Kb, value=B * Kb / (wall_bb * 1e-3), unit="updates/s", ms_per_batch_step=wall_bb / Kb,
-                       gpu_launches=int(sum(f_.launchCount() for f_ in bfilters) - l0),
-                       timing="host wall clock over the batch, host buffers in and state estimates out (same contract as e2e)")
-        for bf in bfilters:
-            bf.close()
+        if dist:
+            dist.barrier()
+        wall_b, upd_b, launch_b, poses = batched_leg(eb, args, N, B, Kb, Wb, local_rank, first_instance=1000 + rank * B)
+        tb = torch.tensor([wall_b], dtype=torch.float64, device="cuda")
+        gather_ms = 0.0
+        if dist:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+            pt = torch.from_numpy(poses).to(dev)
+            parts = [torch.empty_like(pt) for _ in range(world)]
+            gb0, gb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            gb0.record()
+            dist.all_gather(parts, pt)  # "NCCL gather of poses" of configs[4]
+            gb1.record()
+            torch.cuda.synchronize()
+            gather_ms = gb0.elapsed_time(gb1)
+            assert bool(torch.isfinite(torch.stack(parts)).all())
+        wall_max = float(tb[0])
+        batched = dict(sequences_per_gpu=B, sequences=B * world, steps_per_sequence=Kb, noisy=True,
+                       value=world * upd_b / ((wall_max + gather_ms) * 1e-3), unit="updates/s", ms_per_batch_step=wall_max / Kb,
+                       pose_gather_ms=gather_ms, gpu_launches=launch_b,
+                       timing="max over ranks of the host wall clock over the batch (host buffers in, state estimates out: the e2e "
+                       "contract) + the all-gather of the final poses")
 
-    t = torch.tensor([dev_ms, e2e_ms, cpp_ms, real_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, py_ms, cpp_ms, real_ms, collective_ms], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max, cpp_ms_max, real_ms_max = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    dev_ms_max, py_ms_max, cpp_ms_max, real_ms_max, coll_ms_max = (float(x) for x in t)
 
     if rank == 0:
         peaks = {}
@@ -512,101 +596,68 @@ def run_b200(args, rank, local_rank, world, guard):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        # fp64 has no entry in MEASURED_PEAKS.json (tcgen05 has no fp64 kind; the path runs on the FP64
-        # DMMA pipe): calibrate a cuBLAS DGEMM here and use it as the tensor-bound denominator.
-        a = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
-        b = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
-        for _ in range(2):
-            a @ b
-        best = 1e9
-        for _ in range(5):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            a @ b
-            e1.record()
-            torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
-        f64_peak = 2.0 * 4096**3 / (best * 1e-3) / 1e12
-
-        cnt = alg_counts(n_state, n_meas)
+        f64_tflops, f64_ms = fp64_peak(torch)
+        sampler.sample()
         traffic = {}
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         except Exception:
             pass
-        kern = {}
-        for name, d in prof.items():
-            if d["launches"] == 0:
-                continue
-            per_update_ms = d["ms"] / max(nprof, 1)
-            e = dict(ms_per_update=per_update_ms, launches_per_update=d["launches"] / max(nprof, 1),
-                     avg_launch_us=1000.0 * d["ms"] / d["launches"])
-            if name == "downdate" and args.downdate == "tc":
-                # six bf16 products per fp64-equivalent product; the tile kernel is bound by the fp64 Sigma traffic
-                # (read + write of the lower tiles and their mirrors), not by the tensor pipe
-                e.update(bound="hbm", achieved=2.0 * 8 * cnt["dim"] ** 2 * (cnt["m"] / 64.0) / (per_update_ms * 1e-3) / 1e9, peak=hbm_peak,
-                         unit="GB/s", tensor_tflops=6.0 * cnt["syrk_flops"] / (per_update_ms * 1e-3) / 1e12,
-                         tensor_peak_tflops=peaks.get("bf16_tflops", 1590.0))
-            elif name == "downdate":
-                e.update(bound="tensor", achieved=cnt["syrk_flops"] / (per_update_ms * 1e-3) / 1e12, peak=f64_peak, unit="TFLOP/s")
-            elif name == "chunk_factor":
-                e.update(bound="latency", note="64 sequential pivots per chunk; fp64 CUDA-core work, one 4x4 register tile per thread")
-            elif name == "chol_trail":
-                e.update(bound="tensor", achieved=cnt["trail_flops"] / (per_update_ms * 1e-3) / 1e12, peak=f64_peak, unit="TFLOP/s")
-            elif name == "prop_ll":
-                e.update(bound="hbm", achieved=cnt["prop_bytes"] / (per_update_ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s")
-            if "achieved" in e:
-                e["frac"] = e["achieved"] / e["peak"]
-            kern[name] = e
-        dom = max(kern, key=lambda k_: kern[k_]["ms_per_update"]) if kern else None
-        dom_r = max((k_ for k_ in kern if "achieved" in kern[k_]), key=lambda k_: kern[k_]["ms_per_update"], default=None)
+        K3 = m["K3"]
+        cnt = alg_counts(m["n_state"], m["n_meas"])
+        kern = kernel_rooflines(m["prof"], m["nprof"], cnt, N, hbm_peak, f64_tflops, traffic, tc=args.downdate == "tc",
+                                bf16_peak=peaks.get("bf16_tflops", 1590.0))
         roofline = None
-        if dom_r:
-            d = kern[dom_r]
-            tr = traffic.get(dom_r, {}).get(str(N))
-            roofline = dict(kernel=dom_r, bound=d["bound"], achieved=d["achieved"], peak=d["peak"], unit=d["unit"], frac=d["frac"],
-                            traffic=tr, avg_launch_us=d["avg_launch_us"],
-                            peak_source=(hbm_src if d["bound"] == "hbm" else
-                                         f"cuBLAS DGEMM 4096^3 measured in this run ({f64_peak:.1f} TFLOP/s); MEASURED_PEAKS.json "
-                                         "has no fp64 figure"),
-                            dominant_by_time=dom, kernels=kern, profile_stage_ms={k_: v / max(nprof, 1) for k_, v in prof_stage.items()},
-                            update=dict(flops=cnt["upd_flops"], bytes=cnt["upd_bytes"],
-                                        flops_frac=cnt["upd_flops"] * K * R / (dev_ms / 1e3) / 1e12 / f64_peak,
+        if kern:
+            dom = max(kern, key=lambda k_: kern[k_]["ms_per_update"])
+            d = kern[dom]
+            roofline = dict(kernel=dom, bound=d.get("bound"), achieved=d.get("achieved"), peak=d.get("peak"), unit=d.get("unit"),
+                            frac=d.get("frac"), traffic=d.get("traffic"), avg_launch_us=d["avg_launch_us"],
+                            traffic_source="profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu "
+                            "--set full captures named there (scripts/ncu_traffic.py)",
+                            peak_source=(hbm_src if d.get("bound") == "hbm" else
+                                         f"cuBLAS DGEMM 4096^3 measured in this run ({f64_tflops:.1f} TFLOP/s, {f64_ms:.2f} ms); "
+                                         "MEASURED_PEAKS.json has no fp64 figure"),
+                            fp64_peak=dict(tflops=f64_tflops, how="torch.matmul fp64 4096^3, best of 5, CUDA events", ms=f64_ms),
+                            hbm_peak=dict(gbs=hbm_peak, source=hbm_src),
+                            dominant_by_time=dom, kernels=kern,
+                            profile_stage_ms={k_: v / max(m["nprof"], 1) for k_, v in m["prof_stage"].items()},
+                            update=dict(flops=cnt["upd_flops"], bytes=cnt["upd_bytes"], chunks=cnt["chunks"],
+                                        flops_note="flops the sequential-chunk algorithm executes: m dim^2 + 72 dim^2 + sum over chunks "
+                                        "(r^3 / 3 + r^2 dim)",
+                                        flops_frac=cnt["upd_flops"] * K * R / (dev_ms / 1e3) / 1e12 / f64_tflops,
                                         hbm_frac=cnt["upd_bytes"] * K * R / (dev_ms / 1e3) / 1e9 / hbm_peak))
         value = world * R * K / (dev_ms_max * 1e-3)
-        e2e_py = world * R * K / (e2e_ms_max * 1e-3)
-        e2e = world * R * K / (cpp_ms_max * 1e-3) if cpp_ms_max > 0 else e2e_py
-        value_note = None
-        if R > 1 and cpp_ms_max > 0:
-            # concurrent sequences: per-filter device brackets overlap, and the Python-threaded loop is GIL-bound; the C++ batch is
-            # the only run that shows what the GPU sustains, so it also stands for `value` (its 13 KB uploads per update included)
-            value = max(value, e2e)
-            value_note = "R > 1: wall clock of the C++ batch (one host thread per sequence), uploads included"
+        # the all-gather closes a lap of LAP_UPDATES updates: K of them were timed, so K / LAP_UPDATES of it is charged
+        coll_share = coll_ms_max * min(1.0, K / float(LAP_UPDATES))
+        e2e_ms = cpp_ms_max + coll_share
         line = dict(metric="vision-updates/sec", value=value, unit="updates/s", n_gpus=world, steps=K, warmup=W,
                     ms_per_step=dev_ms_max / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                     data="synthetic",
-                    config=dict(workload=workload_name(N, args.coord), landmarks=N, measured_per_update=n_meas, state_dim=cnt["dim"],
+                    config=dict(workload=workload_name(N, args.coord), landmarks=N, measured_per_update=m["n_meas"], state_dim=cnt["dim"],
                                 sequences_per_gpu=R, l2="not flushed" if args.no_l2_flush else
                                 "flushed between steps (256 MiB write) outside the per-step event brackets",
-                                value_timing="CUDA events on each filter's stream around the device work of processVisionData "
-                                "(frame upload -> status download; + augmentLandmarkStates kernels); per step the slowest of the "
-                                "GPU's concurrent sequences counts",
+                                value_timing="CUDA events on the filter's stream around the device work of processVisionData "
+                                "(frame upload -> status download; + augmentLandmarkStates kernels)" if R == 1 else
+                                "host bracket of each step of the GPU's concurrent sequences (their device times overlap)",
                                 launch_mode="per-kernel launches" if args.no_graph else "steady frames replayed as a cached CUDA graph",
                                 parallelism=f"replicas: {R} sequence(s) per GPU x {world} GPU(s), no data-path collective, "
-                                "one all-gather of trajectories at the end"),
-                    value_note=value_note,
-                    e2e=dict(value=e2e, unit="updates/s", h2d_bytes_per_step=h2d // K, d2h_bytes_per_step=d2h // K,
-                             ms_per_step=(cpp_ms_max if cpp_ms_max > 0 else e2e_ms_max) / K,
+                                "one all-gather of trajectories per lap"),
+                    e2e=dict(value=world * R * K / (e2e_ms * 1e-3), unit="updates/s", h2d_bytes_per_step=m["h2d"], d2h_bytes_per_step=m["d2h"],
+                             ms_per_step=e2e_ms / K, collective_ms=coll_ms_max, collective_charged_ms=coll_share,
+                             collective_note=(f"one all-gather of the trajectories per simulated lap ({LAP_UPDATES} updates); "
+                                              f"{K} updates timed -> {K}/{LAP_UPDATES} of it is charged to e2e") if world > 1
+                             else "single GPU: no collective",
                              driver=("C++ host loop over the C ABI (eqvio_replay), host wall clock per synchronised frame" if R == 1 else
-                                     "one C++ host thread per sequence over the C ABI (eqvio_replay_batch), wall clock of the batch") if cpp_ms_max > 0
-                             else "Python ctypes driver, CUDA events around each synchronised step",
+                                     "one C++ host thread per sequence over the C ABI (eqvio_replay_batch), wall clock of the batch"),
                              real_data_flow=(dict(value=world * R * K3 / (real_ms_max * 1e-3), ms_per_step=real_ms_max / K3,
                                                   note="same C++ loop without augmentLandmarkStates: ids lost / added inside "
                                                   "processVisionData (eqvio_opt's flow)") if real_ms_max > 0 else None),
-                             python_driver=dict(value=e2e_py, ms_per_step=e2e_ms_max / K, host_ms_per_step=1000.0 * wall_in / K,
+                             python_driver=dict(value=world * R * K / (py_ms_max * 1e-3), ms_per_step=py_ms_max / K,
+                                                host_ms_per_step=1000.0 * m["wall_in"] / K,
                                                 timing="CUDA events around each synchronised step")),
-                    gpu_launches=int(launches), launches_per_step=launches / K,
-                    stage_ms={k_: v / K for k_, v in stage_acc.items()},
+                    gpu_launches=int(m["launches"]), launches_per_step=m["launches"] / K,
+                    stage_ms={k_: v / K for k_, v in m["stage_acc"].items()},
                     stage_ms_note=("per-stage event brackets of plain launches" if args.no_graph else
                                    "the timed steps replay one CUDA graph per update: a single bracket, booked under correction; the "
                                    "propagation / preprocessing / correction split of the same update with plain launches is "
@@ -614,21 +665,29 @@ def run_b200(args, rank, local_rank, world, guard):
                     clocks=sampler.result(), roofline=roofline)
         if batched:
             line["batched"] = batched
-        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is a single-GPU-run figure (rank 0 at N = 1 only)
-            est_s = 17.0 * cnt["dim"] ** 3 / 50e9 + 0.02  # ~17 dim^3 flops of the dense path at a conservative 50 GFLOP/s
-            sample_n = args.cpu_sample or int(max(3, min(K, 20.0 / est_s)))
-            with all_host_threads():
-                ups, stages, done = time_cpu(streams[0], skw, min(W, 2), sample_n)
-                ncores = blas_threads()
-            line["cpu_baseline"] = dict(value=ups, unit="updates/s", cores=ncores, kind="port",
-                                        sample=f"{done} consecutive updates of sequence 0 (same inputs) after {min(W, 2)} warm-up "
-                                        "updates; oracle port of the dense Eigen path in the reference's evaluation order "
-                                        "(numpy + OpenBLAS; includes ~20 ms/update of Python overhead)",
-                                        stage_ms={k_: 1000.0 * v / done for k_, v in stages.items()})
-            line["cpu_baseline"].update(cpu_variants(streams[0], skw, min(W, 2), ups))
+        if world == 1 and R == 1 and not args.no_sweep and N == 256:
+            sweep = {}
+            for Ns, Ks, Ps in ((64, min(K, 30), 6), (1024, min(K, 10), 3)):
+                ms_ = measure_single(eb, torch, args, Ns, Ks, 3, Ps, local_rank, flush_buf, parity=True)
+                cs = alg_counts(ms_["n_state"], ms_["n_meas"])
+                ks = kernel_rooflines(ms_["prof"], ms_["nprof"], cs, Ns, hbm_peak, f64_tflops, traffic)
+                keep = ("ms_per_update", "avg_launch_us", "bound", "achieved", "peak", "unit", "frac", "traffic")
+                entry_ = dict(value=Ks / (ms_["dev_ms"] * 1e-3), e2e=Ks / (ms_["cpp_ms"] * 1e-3), unit="updates/s", steps=Ks, warmup=3,
+                              ms_per_step=ms_["dev_ms"] / Ks, state_dim=cs["dim"],
+                              real_data_flow=(ms_["K3"] / (ms_["real_ms"] * 1e-3) if ms_["real_ms"] > 0 else None),
+                              update_flops_frac=cs["upd_flops"] * Ks / (ms_["dev_ms"] / 1e3) / 1e12 / f64_tflops,
+                              kernels={k_: {kk_: v for kk_, v in e.items() if kk_ in keep} for k_, e in ks.items()},
+                              parity_vs_oracle=ms_["parity"])
+                if not args.no_cpu_baseline:
+                    c_ = cpu_arm(ms_["stream"], settings_dict(args.coord), 2, 3 if Ns >= 1024 else 10, variants=Ns < 1024)
+                    entry_["cpu_baseline"] = {k_: c_[k_] for k_ in c_ if k_ != "sample"}
+                ms_["seq"].flt.close()
+                sweep[str(Ns)] = entry_
+            line["sweep"] = sweep
+        if not args.no_cpu_baseline and world == 1 and R == 1:  # the CPU baseline is a single-GPU-run figure (rank 0 at N = 1 only)
+            line["cpu_baseline"] = cpu_arm(m["stream"], settings_dict(args.coord), min(W, 2), args.cpu_sample or cpu_sample_size(N, K))
         guard.emit(line)
-    for f in filters:
-        f.close()
+    m["seq"].flt.close()
     if dist:
         dist.barrier()
         dist.destroy_process_group()
