@@ -1966,7 +1966,9 @@ __global__ void lift_kernel(double* __restrict__ lm, int cap, int N, const doubl
         estOut[23 + 3 * i + 1] = p.y;
         estOut[23 + 3 * i + 2] = p.z;
     }
-    bool nan = !(isfinite(Q.w) && isfinite(Q.x) && isfinite(Q.y) && isfinite(Q.z) && isfinite(a));
+    // NaN only: an overflowed scale (a = inf, continuous lift of a huge innovation) is an INVALID landmark for the reference
+    // (VIO_eqf.cpp:213-223: a > 1e8), dropped below -- its hasNaN() asserts do not fire on infinities either
+    bool nan = isnan(Q.w) || isnan(Q.x) || isnan(Q.y) || isnan(Q.z) || isnan(a);
     if (nan) atomicOr(status, 2);
     int inv = (a <= 1e-8 || a > 1e8) ? 1 : 0;
     invalidFlag[i] = inv;
