@@ -432,10 +432,14 @@ def batched_leg(eb, args, N, B, Kb, Wb, device, first_instance):
     """B independent NOISY Monte-Carlo sequences (BASELINE configs[4]: 16 per GPU) replayed concurrently through the C ABI with HOST
     buffers, one C++ host thread per sequence (eqvio_replay_batch), wall clock over the whole batch.  Returns
     (wall ms, updates, launches, final sensor states (B, 23))."""
-    from simdata import SimConfig, record_stream
+    from eqvio_b200.simulator import DeviceSimulator
+    from simdata import SimConfig
 
-    streams = [record_stream(SimConfig.benchmark(N, first_instance + b, duration=20.0, inputNoise=True, outputNoise=True), 1 + Wb + Kb)
-               for b in range(B)]
+    # the noisy instances come from the device VIOSimulator: all B streams (IMU, visibility, pixel / IMU noise) in one launch each
+    dsim = DeviceSimulator([SimConfig.benchmark(N, first_instance + b, duration=20.0, inputNoise=True, outputNoise=True) for b in range(B)],
+                           device=device)
+    streams = dsim.record_streams(1 + Wb + Kb)
+    dsim.close()
     cam = eb.Camera(**streams[0].camera)
     filters = []
     for sm_ in streams:

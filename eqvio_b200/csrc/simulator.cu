@@ -31,6 +31,43 @@ struct SimParams {
     SE3 camOffset;
 };
 
+// Measurement / input noise of the reference's simulator (VIOSimulator.cpp:163-167: IMU, zero-mean Gaussian with covariance
+// constructInputGainMatrix() * samplingFrequency; :258-262: pixels, constructOutputGainMatrix(n) = measurementNoise^2 I).
+// The reference draws from a std::normal_distribution stream that no other platform reproduces; here every draw is a pure
+// function of (instance seed, stream, event index, component) through the counter-based Philox4x32-10 generator and a
+// Box-Muller transform, so that any number of Monte-Carlo instances is generated in one launch, in any order, reproducibly
+// (simdata/philox.py is the host statement of the same function).
+struct NoiseParams {
+    int input, output;          // switches (SimulationDataServer.cpp:229-230)
+    double imuSigma[12];        // per component: sqrt(variance * samplingFrequency)
+    double pixelSigma;
+    double imuFreq, imageFreq;  // event index = round(stamp * frequency)
+};
+enum { STREAM_IMU = 1, STREAM_VISION = 2 };
+
+__host__ __device__ inline void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned (&out)[4]) {
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+        c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
+}
+// two independent N(0, 1) draws for (seed, stream, event, component)
+__host__ __device__ inline void normal_pair(unsigned long long seed, int stream, long long event, int comp, double& z0, double& z1) {
+    unsigned x[4];
+    philox4x32_10((unsigned)event, (unsigned)((unsigned long long)event >> 32), (unsigned)comp, (unsigned)stream, (unsigned)seed,
+                  (unsigned)(seed >> 32), x);
+    const unsigned long long a = (((unsigned long long)x[0] << 32) | x[1]) >> 11, b = (((unsigned long long)x[2] << 32) | x[3]) >> 11;
+    const double u1 = ((double)a + 1.0) * (1.0 / 9007199254740992.0);  // (0, 1]
+    const double u2 = (double)b * (1.0 / 9007199254740992.0);          // [0, 1)
+    const double r = sqrt(-2.0 * log(u1)), th = 6.283185307179586476925286766559 * u2;
+    z0 = r * cos(th);
+    z1 = r * sin(th);
+}
+
 __host__ __device__ inline double traj_time(int i) { return ((double)i / TRAJ_FREQUENCY + TRAJ_T0) - TRAJ_T0; }
 __host__ __device__ inline void traj_pose(int i, Quat& q, V3& x) {
     const double t0 = (double)i / TRAJ_FREQUENCY + TRAJ_T0;
@@ -128,11 +165,23 @@ __host__ __device__ inline void inertial_states(int it, double ct, V3& pos, V3& 
 }
 
 // IMU sample at time t (VIOSimulator.cpp:163-214): row = stamp, gyr3, acc3, gyrBiasVel3 (0), accBiasVel3 (0)
-__global__ void sim_imu_kernel(const double* __restrict__ stamps, int n, int M, double* __restrict__ rows) {
+// blockIdx.y = instance (one row block per instance when noise is on; a single block otherwise)
+__global__ void sim_imu_kernel(const double* __restrict__ stamps, int n, int M, double* __restrict__ rows, NoiseParams np,
+                               const unsigned long long* __restrict__ seeds) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const double t = stamps[k];
-    double* o = rows + 13 * (size_t)k;
+    double* o = rows + 13 * ((size_t)blockIdx.y * n + k);
+    auto add_noise = [&]() {  // VIOSimulator.cpp:163-167
+        if (!np.input || !seeds) return;
+        const long long ev = llround(t * np.imuFreq);
+        for (int c = 0; c < 6; ++c) {
+            double z0, z1;
+            normal_pair(seeds[blockIdx.y], STREAM_IMU, ev, c, z0, z1);
+            o[1 + 2 * c] += np.imuSigma[2 * c] * z0;
+            o[2 + 2 * c] += np.imuSigma[2 * c + 1] * z1;
+        }
+    };
     for (int j = 0; j < 13; ++j) o[j] = 0.0;
     o[0] = t;
     int it = time_index(t, M);
@@ -142,6 +191,7 @@ __global__ void sim_imu_kernel(const double* __restrict__ stamps, int n, int M, 
         traj_pose(M - 1, q, x);
         const V3 a = qrot(qinv(q), V3{0, 0, GRAVITY_CONSTANT});
         o[4] = a.x; o[5] = a.y; o[6] = a.z;
+        add_noise();
         return;
     }
     it = clamp_index(it, M);
@@ -157,6 +207,7 @@ __global__ void sim_imu_kernel(const double* __restrict__ stamps, int n, int M, 
     const V3 acc = qrot(qinv(att), a - V3{0, 0, -GRAVITY_CONSTANT});
     o[1] = gyr.x; o[2] = gyr.y; o[3] = gyr.z;
     o[4] = acc.x; o[5] = acc.y; o[6] = acc.z;
+    add_noise();
 }
 
 __device__ __forceinline__ bool in_domain(const SimParams& sp, V3 pc, double& u, double& v) {
@@ -169,7 +220,8 @@ __device__ __forceinline__ bool in_domain(const SimParams& sp, V3 pc, double& u,
 // measured points and the true sensor state (getFullState, :269-310) at the same stamp.
 __global__ void __launch_bounds__(SIM_THREADS)
     sim_vision_kernel(SimParams sp, const double* __restrict__ stamps, const double* __restrict__ points, const int* __restrict__ pointIds,
-                      int* __restrict__ nOut, int* __restrict__ idsOut, double* __restrict__ yOut, double* __restrict__ pOut,
+                      int* __restrict__ nOut, int* __restrict__ idsOut, double* __restrict__ yOut, double* __restrict__ pOut, NoiseParams np,
+                      const unsigned long long* __restrict__ seeds,
                       double* __restrict__ sensorOut) {
     __shared__ SE3 sCi, sCi2;
     __shared__ int sEmpty;
@@ -293,6 +345,12 @@ __global__ void __launch_bounds__(SIM_THREADS)
         const V3 pt = se3_apply(ci2, pw);
         const size_t o = slot * sp.maxFeatures + i;
         idsOut[o] = sKey[i];
+        if (np.output && seeds) {  // VIOSimulator.cpp:258-262: after the visibility test, one pair of draws per measured point (ascending id)
+            double z0, z1;
+            normal_pair(seeds[blockIdx.y], STREAM_VISION, llround(stamps[blockIdx.x] * np.imageFreq), i, z0, z1);
+            u += np.pixelSigma * z0;
+            v += np.pixelSigma * z1;
+        }
         yOut[2 * o] = u;
         yOut[2 * o + 1] = v;
         pOut[3 * o] = pt.x;
@@ -307,6 +365,8 @@ struct eqvio_sim {
     SimParams sp;
     double* d_points = nullptr;
     int* d_ids = nullptr;
+    unsigned long long* d_seeds = nullptr;
+    NoiseParams np = {};
     cudaStream_t stream = nullptr;
 };
 
@@ -359,26 +419,52 @@ void eqvio_sim_destroy(eqvio_sim* s) {
     cudaSetDevice(s->device);
     cudaFree(s->d_points);
     cudaFree(s->d_ids);
+    cudaFree(s->d_seeds);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
 
-int eqvio_sim_imu(eqvio_sim* s, int n, const double* stamps, double* rows) {
+int eqvio_sim_set_noise(eqvio_sim* s, int input_noise, int output_noise, const double imu_sigma[12], double pixel_sigma, double imu_freq,
+                        double image_freq, const unsigned long long* seeds) {
+    if (!s || ((input_noise || output_noise) && (!seeds || !imu_sigma))) return -1;
+    cudaSetDevice(s->device);
+    s->np.input = input_noise ? 1 : 0;
+    s->np.output = output_noise ? 1 : 0;
+    for (int i = 0; i < 12; ++i) s->np.imuSigma[i] = imu_sigma ? imu_sigma[i] : 0.0;
+    s->np.pixelSigma = pixel_sigma;
+    s->np.imuFreq = imu_freq;
+    s->np.imageFreq = image_freq;
+    if (seeds) {
+        if (!s->d_seeds && cudaMalloc(&s->d_seeds, s->nInst * sizeof(unsigned long long)) != cudaSuccess) return -2;
+        if (cudaMemcpyAsync(s->d_seeds, seeds, s->nInst * sizeof(unsigned long long), cudaMemcpyHostToDevice, s->stream) != cudaSuccess ||
+            cudaStreamSynchronize(s->stream) != cudaSuccess)
+            return -2;
+    }
+    return 0;
+}
+
+static int sim_imu_impl(eqvio_sim* s, int n, const double* stamps, double* rows, int per_instance) {
     if (!s || n < 0 || (n > 0 && (!stamps || !rows))) return -1;
     if (n == 0) return 0;
     cudaSetDevice(s->device);
+    const int blocksY = per_instance ? s->nInst : 1;
+    const size_t total = (size_t)blocksY * n * 13;
     double *d_t = nullptr, *d_r = nullptr;
-    bool ok = cudaMalloc(&d_t, n * sizeof(double)) == cudaSuccess && cudaMalloc(&d_r, (size_t)n * 13 * sizeof(double)) == cudaSuccess;
+    bool ok = cudaMalloc(&d_t, n * sizeof(double)) == cudaSuccess && cudaMalloc(&d_r, total * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMemcpyAsync(d_t, stamps, n * sizeof(double), cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
-    if (ok) sim_imu_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(d_t, n, s->sp.numPoses, d_r);
+    if (ok)
+        sim_imu_kernel<<<dim3((n + 127) / 128, blocksY), 128, 0, s->stream>>>(d_t, n, s->sp.numPoses, d_r, s->np,
+                                                                             per_instance ? s->d_seeds : (const unsigned long long*)nullptr);
     ok = ok && cudaGetLastError() == cudaSuccess;
-    ok = ok && cudaMemcpyAsync(rows, d_r, (size_t)n * 13 * sizeof(double), cudaMemcpyDeviceToHost, s->stream) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(rows, d_r, total * sizeof(double), cudaMemcpyDeviceToHost, s->stream) == cudaSuccess;
     ok = ok && cudaStreamSynchronize(s->stream) == cudaSuccess;
     if (!ok) g_simError = std::string("eqvio_sim_imu: ") + cudaGetErrorString(cudaGetLastError());
     cudaFree(d_t);
     cudaFree(d_r);
     return ok ? 0 : -2;
 }
+int eqvio_sim_imu(eqvio_sim* s, int n, const double* stamps, double* rows) { return sim_imu_impl(s, n, stamps, rows, 0); }
+int eqvio_sim_imu_instances(eqvio_sim* s, int n, const double* stamps, double* rows) { return sim_imu_impl(s, n, stamps, rows, 1); }
 
 int eqvio_sim_vision(eqvio_sim* s, int n, const double* stamps, int* n_out, int* ids, double* y, double* provided_p, double* true_sensor,
                      float* device_ms) {
@@ -400,7 +486,8 @@ int eqvio_sim_vision(eqvio_sim* s, int n, const double* stamps, int* n_out, int*
     ok = ok && cudaMemsetAsync(d_s, 0, (size_t)n * 23 * sizeof(double), s->stream) == cudaSuccess;
     if (ok) {
         cudaEventRecord(e0, s->stream);
-        sim_vision_kernel<<<dim3(n, s->nInst), SIM_THREADS, 0, s->stream>>>(s->sp, d_t, s->d_points, s->d_ids, d_n, d_i, d_y, d_p, d_s);
+        sim_vision_kernel<<<dim3(n, s->nInst), SIM_THREADS, 0, s->stream>>>(s->sp, d_t, s->d_points, s->d_ids, d_n, d_i, d_y, d_p, s->np,
+                                                                            (const unsigned long long*)s->d_seeds, d_s);
         cudaEventRecord(e1, s->stream);
     }
     ok = ok && cudaGetLastError() == cudaSuccess;

@@ -1,7 +1,9 @@
 """Device VIOSimulator (include/eqvio_b200_sim.h): IMU and vision streams of the reference's simulator for many Monte-Carlo
 instances at once.  The world points of each instance come from the host generator (``simdata``, seeded
 numpy draws -- SURVEY 8c: the reference's libc ``rand()`` stream is not reproducible across platforms); trajectory, IMU,
-visibility, selection, sorting and the true states run on the GPU.  Noise-free configurations only."""
+visibility, selection, sorting and the true states run on the GPU, and so does the reference's input / output noise
+(VIOSimulator.cpp:163-167, 258-262): counter-based Philox draws keyed by the instance's noise seed (simdata/philox.py states the
+same function on the host), i.e. the noisy Monte-Carlo instances of BASELINE configs[4] come out of the same launches."""
 from __future__ import annotations
 
 import ctypes as C
@@ -21,6 +23,10 @@ lib.eqvio_sim_imu.restype = C.c_int
 lib.eqvio_sim_imu.argtypes = [_H, C.c_int, _PD, _PD]
 lib.eqvio_sim_vision.restype = C.c_int
 lib.eqvio_sim_vision.argtypes = [_H, C.c_int, _PD, _PI, _PI, _PD, _PD, _PD, C.POINTER(C.c_float)]
+lib.eqvio_sim_imu_instances.restype = C.c_int
+lib.eqvio_sim_imu_instances.argtypes = [_H, C.c_int, _PD, _PD]
+lib.eqvio_sim_set_noise.restype = C.c_int
+lib.eqvio_sim_set_noise.argtypes = [_H, C.c_int, C.c_int, _PD, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_ulonglong)]
 lib.eqvio_sim_last_error.restype = C.c_char_p
 
 
@@ -40,8 +46,8 @@ class DeviceSimulator:
 
         c0 = configs[0]
         for c in configs:
-            if c.inputNoise or c.outputNoise:
-                raise ValueError("the device simulator generates noise-free streams")
+            if (c.inputNoise, c.outputNoise) != (c0.inputNoise, c0.outputNoise):
+                raise ValueError("instances must share the noise switches")
             if (c.numPoints, c.maxFeatures, c.duration, c.numWalls, c.wallDistance) != (c0.numPoints, c0.maxFeatures, c0.duration, c0.numWalls,
                                                                                           c0.wallDistance):
                 raise ValueError("instances must share the scene geometry (only the seed differs)")
@@ -56,6 +62,15 @@ class DeviceSimulator:
         if not self._h:
             raise RuntimeError((lib.eqvio_sim_last_error() or b"").decode())
         self.last_vision_ms = 0.0
+        self.noise_seeds = np.array([(c.randomSeed if c.noiseSeed is None else c.noiseSeed) for c in configs], dtype=np.uint64)
+        if c0.inputNoise or c0.outputNoise:
+            # standard deviations of VIOSimulator.cpp:163-167 (constructInputGainMatrix() x sampling frequency) and :258-262
+            self.imu_sigma = np.sqrt(np.repeat(np.array([c0.velGyrNoise, c0.velAccNoise, c0.velGyrBiasWalk, c0.velAccBiasWalk]) ** 2, 3)
+                                     * max(c0.imuFreq, 0.0))
+            rc = lib.eqvio_sim_set_noise(self._h, int(c0.inputNoise), int(c0.outputNoise), _pd(self.imu_sigma), float(c0.measurementNoise),
+                                         float(c0.imuFreq), float(c0.imageFreq), self.noise_seeds.ctypes.data_as(C.POINTER(C.c_ulonglong)))
+            if rc != 0:
+                raise RuntimeError("eqvio_sim_set_noise failed")
 
     def close(self):
         if getattr(self, "_h", None):
@@ -73,6 +88,14 @@ class DeviceSimulator:
         t = np.ascontiguousarray(stamps, dtype=np.float64).reshape(-1)
         rows = np.zeros((t.shape[0], 13))
         if lib.eqvio_sim_imu(self._h, t.shape[0], _pd(t), _pd(rows)) != 0:
+            raise RuntimeError((lib.eqvio_sim_last_error() or b"").decode())
+        return rows
+
+    def imu_instances(self, stamps):
+        """(k,) stamps -> (instances, k, 13): the IMU rows of every instance (they differ when input noise is on)."""
+        t = np.ascontiguousarray(stamps, dtype=np.float64).reshape(-1)
+        rows = np.zeros((len(self.configs), t.shape[0], 13))
+        if lib.eqvio_sim_imu_instances(self._h, t.shape[0], _pd(t), _pd(rows)) != 0:
             raise RuntimeError((lib.eqvio_sim_last_error() or b"").decode())
         return rows
 
@@ -110,13 +133,17 @@ class DeviceSimulator:
                 imu_t.append(t_imu)
                 imu_of.append(len(img_t))  # belongs to the next image
                 n_imu += 1
-        rows = self.imu(np.array(imu_t)) if imu_t else np.zeros((0, 13))
+        if imu_t and c.inputNoise:
+            rows_all = self.imu_instances(np.array(imu_t))
+        else:
+            rows_all = np.broadcast_to(self.imu(np.array(imu_t)) if imu_t else np.zeros((0, 13)), (len(self.configs), len(imu_t), 13))
         imu_of = np.array(imu_of, dtype=np.int64)
         n, ids, y, p, sensor = self.vision(np.array(img_t))
         cam = dict(width=c.width, height=c.height, fx=c.fx, fy=c.fy, cx=c.cx, cy=c.cy)
         streams = []
         for i, cfg in enumerate(self.configs):
             frames = []
+            rows = rows_all[i]
             for k, t in enumerate(img_t):
                 m = int(n[i, k])
                 frames.append(Frame(t, ids[i, k, :m].astype(np.int64), y[i, k, :m].copy(), p[i, k, :m].copy(), rows[imu_of == k].copy(),

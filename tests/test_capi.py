@@ -30,7 +30,8 @@ def test_simulator_header_symbols_exported(capi):
     src = open(os.path.join(ROOT, "include", "eqvio_b200_sim.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = sorted(set(re.findall(r"\b(eqvio_sim_[a-z_0-9]+)\s*\(", src)))
-    assert names == ["eqvio_sim_create", "eqvio_sim_destroy", "eqvio_sim_imu", "eqvio_sim_last_error", "eqvio_sim_vision"]
+    assert names == ["eqvio_sim_create", "eqvio_sim_destroy", "eqvio_sim_imu", "eqvio_sim_imu_instances", "eqvio_sim_last_error",
+                     "eqvio_sim_set_noise", "eqvio_sim_vision"]
     for n in names:
         assert hasattr(capi.lib, n), f"{n} declared in include/eqvio_b200_sim.h but not exported"
 
