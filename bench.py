@@ -341,26 +341,12 @@ def measure_single(eb, torch, args, N, K, W, P, device, flush_buf, sampler=None,
     for k in range(0, 1 + W):
         seq.step(eb, cam, k)
     torch.cuda.synchronize()
-    if parity:
-        # the CUDA path against the oracle after the t = 0 image + W warm-up updates (same inputs, both from the same prior)
-        from oracle import eqf
-
-        ofl, ocam = oracle_filter(stream, settings_dict(args.coord))
-        for fr in stream.frames[:1 + W]:
-            for row in fr.imu:
-                ofl.processIMUData(eqf.IMUVelocity(row[0], row[1:4], row[4:7], row[7:10], row[10:13]))
-            meas = eqf.VisionMeasurement.fromArrays(fr.stamp, fr.ids, fr.y, ocam)
-            ofl.augmentLandmarkStates(meas.getIds(), eqf.VIOState(None, fr.provided_p, fr.ids))
-            ofl.processVisionData(meas)
-        fs, est, oest = flt.viewEqFState(), flt.stateEstimate(), ofl.stateEstimate()
-        S_ref = ofl.viewEqFState().Sigma
-        x_g = np.concatenate([est.sensor.flat(), est.p.reshape(-1)])
-        x_o = np.concatenate([oest.sensor.flat(), oest.p.reshape(-1)])
-        same_ids = bool(np.array_equal(np.asarray(est.ids), np.asarray(oest.ids)))
-        out["parity"] = dict(updates=W, ids_equal=same_ids,
-                             sigma_rel_fro=float(np.linalg.norm(fs.Sigma - S_ref) / np.linalg.norm(S_ref)) if same_ids else None,
-                             state_rel_fro=float(np.linalg.norm(x_g - x_o) / np.linalg.norm(x_o)) if same_ids else None)
+    snap = None
+    if parity:  # state after the t = 0 image + W warm-up updates; compared with the oracle AFTER the timed steps (no idle gap before them)
+        fs0, est0 = flt.viewEqFState(), flt.stateEstimate()
+        snap = (fs0.Sigma.copy(), np.concatenate([est0.sensor.flat(), est0.p.reshape(-1)]), np.asarray(est0.ids).copy())
     launches0 = flt.launchCount()
+    graphs0 = flt.graphStats()
     dev_ms = wall_in = 0.0
     stage_acc = dict(propagation=0.0, preprocessing=0.0, correction=0.0)
     traj = np.zeros((K, 11))
@@ -390,8 +376,10 @@ def measure_single(eb, torch, args, N, K, W, P, device, flush_buf, sampler=None,
         d2h += 8 * (23 + 3 * len(est.ids)) + 8 * 3 * N + 4 * (2 + N)  # state estimate + gate scalars + flag/status words
     torch.cuda.synchronize()
     py_ms = sum(a.elapsed_time(b) for a, b in ev)
+    graphs1 = flt.graphStats()
     out.update(dev_ms=dev_ms, py_ms=py_ms, wall_in=wall_in, stage_acc=stage_acc, traj=traj, h2d=h2d // K, d2h=d2h // K,
-               launches=flt.launchCount() - launches0)
+               launches=flt.launchCount() - launches0,
+               graphs=dict(captured_in_timed_steps=graphs1[0] - graphs0[0], replayed_in_timed_steps=graphs1[1] - graphs0[1]))
     # e2e through the C++ host loop (stage-event recording is instrumentation for `value`: off here)
     flt.enableStageTiming(False)
     fms, est_s = flt.replay(stream.frames[1 + W + K:1 + W + 2 * K], cam, flushBytes=0 if args.no_l2_flush else 256 << 20)
@@ -408,6 +396,23 @@ def measure_single(eb, torch, args, N, K, W, P, device, flush_buf, sampler=None,
         assert np.isfinite(est3).all()
         out["real_ms"] = float(fms3.sum())
     out["K3"] = K3
+    if snap is not None:
+        # the CUDA path against the oracle after the t = 0 image + W warm-up updates (same inputs, both from the same prior)
+        from oracle import eqf
+
+        ofl, ocam = oracle_filter(stream, settings_dict(args.coord))
+        for fr in stream.frames[:1 + W]:
+            for row in fr.imu:
+                ofl.processIMUData(eqf.IMUVelocity(row[0], row[1:4], row[4:7], row[7:10], row[10:13]))
+            meas = eqf.VisionMeasurement.fromArrays(fr.stamp, fr.ids, fr.y, ocam)
+            ofl.augmentLandmarkStates(meas.getIds(), eqf.VIOState(None, fr.provided_p, fr.ids))
+            ofl.processVisionData(meas)
+        oest, S_ref = ofl.stateEstimate(), ofl.viewEqFState().Sigma
+        x_o = np.concatenate([oest.sensor.flat(), oest.p.reshape(-1)])
+        same_ids = bool(np.array_equal(snap[2], np.asarray(oest.ids)))
+        out["parity"] = dict(updates=W, ids_equal=same_ids,
+                             sigma_rel_fro=float(np.linalg.norm(snap[0] - S_ref) / np.linalg.norm(S_ref)) if same_ids else None,
+                             state_rel_fro=float(np.linalg.norm(snap[1] - x_o) / np.linalg.norm(x_o)) if same_ids else None)
     flt.enableStageTiming(True)
     # per-kernel profile on extra steps (event pairs around every launch of a class; the graph path is off while profiling)
     flt.enableKernelProfile(True)
@@ -660,7 +665,7 @@ def run_b200(args, rank, local_rank, world, guard):
                              python_driver=dict(value=world * R * K / (py_ms_max * 1e-3), ms_per_step=py_ms_max / K,
                                                 host_ms_per_step=1000.0 * m["wall_in"] / K,
                                                 timing="CUDA events around each synchronised step")),
-                    gpu_launches=int(m["launches"]), launches_per_step=m["launches"] / K,
+                    gpu_launches=int(m["launches"]), launches_per_step=m["launches"] / K, graphs=m.get("graphs"),
                     stage_ms={k_: v / K for k_, v in m["stage_acc"].items()},
                     stage_ms_note=("per-stage event brackets of plain launches" if args.no_graph else
                                    "the timed steps replay one CUDA graph per update: a single bracket, booked under correction; the "
@@ -678,7 +683,8 @@ def run_b200(args, rank, local_rank, world, guard):
                 ks = kernel_rooflines(ms_["prof"], ms_["nprof"], cs, Ns, hbm_peak, f64_tflops, traffic)
                 keep = ("ms_per_update", "avg_launch_us", "bound", "achieved", "peak", "unit", "frac", "traffic")
                 entry_ = dict(value=Ks / (ms_["dev_ms"] * 1e-3), e2e=Ks / (ms_["cpp_ms"] * 1e-3), unit="updates/s", steps=Ks, warmup=Ws,
-                              ms_per_step=ms_["dev_ms"] / Ks, state_dim=cs["dim"],
+                              ms_per_step=ms_["dev_ms"] / Ks, state_dim=cs["dim"], graphs=ms_["graphs"],
+                              stage_ms={k_: v / Ks for k_, v in ms_["stage_acc"].items()},
                               real_data_flow=(ms_["K3"] / (ms_["real_ms"] * 1e-3) if ms_["real_ms"] > 0 else None),
                               update_flops_frac=cs["upd_flops"] * Ks / (ms_["dev_ms"] / 1e3) / 1e12 / f64_tflops,
                               kernels={k_: {kk_: v for kk_, v in e.items() if kk_ in keep} for k_, e in ks.items()},

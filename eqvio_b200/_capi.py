@@ -99,6 +99,7 @@ SIGNATURES = {
     "eqvio_get_stage_ms": (_I, [_H, _PD]),
     "eqvio_enable_stage_timing": (_I, [_H, _I]),
     "eqvio_get_launch_count": (C.c_longlong, [_H]),
+    "eqvio_get_graph_stats": (_I, [_H, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "eqvio_enable_kernel_profile": (_I, [_H, _I]),
     "eqvio_get_kernel_profile": (_I, [_H, _I, _PD, C.POINTER(C.c_longlong)]),
     "eqvio_replay_batch": (_I, [C.c_void_p, _I, _I, C.c_void_p, C.c_void_p, _PD, _PD, _PD]),

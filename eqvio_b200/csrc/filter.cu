@@ -2448,6 +2448,12 @@ int eqvio_enable_stage_timing(eqvio_filter* f, int on) {
     return EQVIO_OK;
 }
 long long eqvio_get_launch_count(const eqvio_filter* f) { return f ? f->launches : 0; }
+int eqvio_get_graph_stats(const eqvio_filter* f, long long* captures, long long* replays) {
+    if (!f) return EQVIO_ERR_INVALID_ARG;
+    if (captures) *captures = f->graphCaptures;
+    if (replays) *replays = f->graphLaunches;
+    return EQVIO_OK;
+}
 
 int eqvio_enable_kernel_profile(eqvio_filter* f, int on) {
     if (!f) return EQVIO_ERR_INVALID_ARG;

@@ -417,6 +417,12 @@ class VIOFilter:
     def launchCount(self):
         return int(lib.eqvio_get_launch_count(self._h))
 
+    def graphStats(self):
+        """(captures, replays) of the cached CUDA graphs of steady frames (eqvio_get_graph_stats)."""
+        c, r = C.c_longlong(0), C.c_longlong(0)
+        self._check(lib.eqvio_get_graph_stats(self._h, C.byref(c), C.byref(r)))
+        return int(c.value), int(r.value)
+
     def enableKernelProfile(self, on=True):
         self._check(lib.eqvio_enable_kernel_profile(self._h, int(on)))
 

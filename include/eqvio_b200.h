@@ -191,6 +191,8 @@ int eqvio_get_stage_ms(eqvio_filter* f, double ms[3]);
 int eqvio_enable_stage_timing(eqvio_filter* f, int on);
 /* Number of kernel launches issued by this handle since creation. */
 long long eqvio_get_launch_count(const eqvio_filter* f);
+/* CUDA graphs captured (instantiated) and replayed so far: a steady frame shape is captured once and replayed afterwards. */
+int eqvio_get_graph_stats(const eqvio_filter* f, long long* captures, long long* replays);
 /* Per-kernel-class device time, measured with CUDA events recorded on the handle's stream around
  * every launch of the class (adds two event records per launch; off by default, not meant to be on
  * while whole-update throughput is timed).  Classes: */
