@@ -80,6 +80,9 @@ struct eqvio_filter {
     // per-frame input block (FrameHeader | imu | y | measIdx | lmOf) at fixed device / pinned addresses
     unsigned char* d_frame = nullptr;
     unsigned char* h_frame = nullptr;
+    unsigned char* hd_frame = nullptr;  // device-side address of the pinned frame block (zero-copy upload kernel)
+    unsigned char* hd_out = nullptr;    // ... of the pinned result block
+    int zeroCopy = 1;                   // frame / result blocks move through block_copy_kernel instead of memcpy nodes
     size_t frameBytes = 0, offImu = 0, offY = 0, offMeasIdx = 0, offLmOf = 0, offYIdx = 0;
     int* d_yIdx = nullptr;
     FrameHeader* d_hdrSteps = nullptr;  // one header per IMU sample (per-sample Riccati variants)
@@ -412,6 +415,10 @@ int alloc_frame(eqvio_filter* f, int steps, int ycap) {
     CUDA_TRY(f, cudaMalloc(&f->d_frame, f->frameBytes));
     CUDA_TRY(f, cudaMallocHost(&f->h_frame, f->frameBytes));
     std::memset(f->h_frame, 0, f->frameBytes);
+    if (cudaHostGetDevicePointer((void**)&f->hd_frame, f->h_frame, 0) != cudaSuccess) {
+        cudaGetLastError();
+        f->hd_frame = nullptr;
+    }
     CUDA_TRY(f, cudaMalloc(&f->d_steps, (size_t)steps * sizeof(ObsStep)));
     CUDA_TRY(f, cudaMalloc(&f->d_hdrSteps, (size_t)steps * sizeof(FrameHeader)));
     f->d_hdr = reinterpret_cast<FrameHeader*>(f->d_frame);
@@ -503,8 +510,12 @@ int alloc_device(eqvio_filter* f) {
     f->outOffSpec = ((3 * c1 * sizeof(double)) + 63) & ~size_t(63);
     f->outOffStatus = f->outOffSpec + 64;
     f->outOffEst = (f->outOffStatus + (1 + c1) * sizeof(int) + 63) & ~size_t(63);
-    f->outBytes = f->outOffEst + (23 + 3 * c1) * sizeof(double);
+    f->outBytes = (f->outOffEst + (23 + 3 * c1) * sizeof(double) + 63) & ~size_t(63);  // whole 16-byte words are copied
     CUDA_TRY(f, cudaMallocHost(&f->h_out, f->outBytes));
+    if (cudaHostGetDevicePointer((void**)&f->hd_out, f->h_out, 0) != cudaSuccess) {
+        cudaGetLastError();
+        f->hd_out = nullptr;
+    }
     CUDA_TRY(f, cudaMalloc(&f->d_outblk, f->outBytes));
     CUDA_TRY(f, cudaMemsetAsync(f->d_outblk, 0, f->outBytes, f->stream));
     f->d_gate = reinterpret_cast<double*>(f->d_outblk);
@@ -902,7 +913,14 @@ struct FramePlan {
 int enqueue_steady_update(eqvio_filter* f, int N, int nm, const FramePlan* plan) {
     int rc;
     const eqvio_settings& s = f->st;
-    CUDA_TRY(f, cudaMemcpyAsync(f->d_frame, f->h_frame, f->frameBytes, cudaMemcpyHostToDevice, f->stream));
+    const bool zc = f->zeroCopy && f->hd_frame && f->hd_out;
+    if (zc) {
+        block_copy_kernel<<<2, 256, 0, f->stream>>>(reinterpret_cast<const double2*>(f->hd_frame), reinterpret_cast<double2*>(f->d_frame),
+                                                    (int)(f->frameBytes / 16), TL_SLOT(f));
+        LAUNCH_CHECK(f, "block_copy_kernel<frame>");
+    } else {
+        CUDA_TRY(f, cudaMemcpyAsync(f->d_frame, f->h_frame, f->frameBytes, cudaMemcpyHostToDevice, f->stream));
+    }
     if ((rc = enqueue_propagation(f)) != EQVIO_OK) return rc;
     f->steadySplit = !f->capturing;  // stage brackets inside the update exist only with plain launches (a replayed graph is one bracket)
     if (f->steadySplit) stage_mark(f, 1);
@@ -935,8 +953,14 @@ int enqueue_steady_update(eqvio_filter* f, int N, int nm, const FramePlan* plan)
         LAUNCH_CHECK(f, "state_estimate_kernel");
     }
     // one download: gate scalars, gate flag, status words, state estimate (the block has the layout of h_out)
-    CUDA_TRY(f, cudaMemcpyAsync(f->h_out, f->d_outblk, f->outOffEst + (23 + 3 * (size_t)Nout) * sizeof(double), cudaMemcpyDeviceToHost,
-                                f->stream));
+    const size_t outBytes = f->outOffEst + (23 + 3 * (size_t)Nout) * sizeof(double);
+    if (zc) {
+        launch_pdl(f, block_copy_kernel, dim3(2), dim3(256), (size_t)0, f->stream, reinterpret_cast<const double2*>(f->d_outblk),
+                   reinterpret_cast<double2*>(f->hd_out), (int)((outBytes + 15) / 16), TL_SLOT(f));
+        LAUNCH_CHECK(f, "block_copy_kernel<result>");
+    } else {
+        CUDA_TRY(f, cudaMemcpyAsync(f->h_out, f->d_outblk, outBytes, cudaMemcpyDeviceToHost, f->stream));
+    }
     return EQVIO_OK;
 }
 
@@ -2496,6 +2520,10 @@ int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
             return EQVIO_OK;
         case EQVIO_TUNE_STAGE_S:
             f->stageS = value != 0;
+            clear_graphs(f);
+            return EQVIO_OK;
+        case EQVIO_TUNE_ZERO_COPY:
+            f->zeroCopy = value != 0;
             clear_graphs(f);
             return EQVIO_OK;
         case EQVIO_TUNE_FUSE_SMALL:

@@ -99,6 +99,18 @@ __device__ __forceinline__ void tl_mark(int slot, int end) {
 #endif
 
 // ------------------------------------------------------------------------------------------------
+// Frame block in, result block out, as KERNELS over host-mapped pinned memory (zero copy): inside a replayed graph a memcpy node
+// runs on a copy engine, and the hand-over between the copy engine and the SMs at both ends of the update costs more than
+// moving ~13 KB through one CTA's loads / stores does.  n16 = number of 16-byte words.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) block_copy_kernel(const double2* __restrict__ src, double2* __restrict__ dst, int n16, int tl) {
+    pdl_wait();
+    TL_MARK(tl, 0);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = src[i];
+    TL_MARK(tl, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Riccati context, part 1 (sensor-sized, serial): the sensor blocks of A and B (euclid.cpp:99-160,
 // 186-233; identical for invdepth) from X *before* the observer integration, and the quantities the
 // landmark rows need.  As is 21x21, Bs 21x12, row-major.

@@ -252,6 +252,9 @@ int eqvio_get_host_profile(eqvio_filter* f, int reset, double us[4], long long* 
  *     CUtensorMap over the covariance) into shared memory when the chunk's landmarks are consecutive in the state; 0 = every tile
  *     owner gathers its 36 entries itself (also the fall-back for non-consecutive chunks).  Same entries, bit-identical results. */
 #define EQVIO_TUNE_STAGE_S 12
+/*   EQVIO_TUNE_ZERO_COPY: 1 (default) = the per-frame input block and the result block of a steady update move through a copy
+ *     KERNEL over host-mapped pinned memory; 0 = cudaMemcpyAsync (memcpy nodes on a copy engine inside the replayed graph). */
+#define EQVIO_TUNE_ZERO_COPY 13
 int eqvio_set_tuning(eqvio_filter* f, int key, int value);
 /* Version / build info string (arch the kernels were compiled for). */
 const char* eqvio_build_info(void);

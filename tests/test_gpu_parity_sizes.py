@@ -206,3 +206,15 @@ def test_vision_dropout_replays_graphs_with_many_imu_segments():
     assert max(len(f.imu) for f in seq) > 128
     worst, _, _ = _lockstep(stream, augment=True, frames=seq)
     print(f"drop-out sequence: worst {worst:.3e}")
+
+
+@pytest.mark.parametrize("N", [24, 256])
+def test_zero_copy_blocks_agree_with_memcpy_nodes(N):
+    """EQVIO_TUNE_ZERO_COPY: the frame block in / result block out through a copy kernel over host-mapped pinned memory gives
+    the bits of the cudaMemcpyAsync path (graph replay on both sides), incl. the downloaded gate scalars and state estimate."""
+    stream = make_stream(N=N, frames=10, coord=0)
+    a = run_gpu(stream, tuning=dict(zeroCopy=0))
+    b = run_gpu(stream, tuning=dict(zeroCopy=1))
+    for k, (g, r) in enumerate(zip(b, a)):
+        e = compare_states(g, r)
+        assert e["ids_equal"] and e["sigma"] == 0.0 and e["state"] == 0.0, f"update {k}: {e}"
