@@ -83,6 +83,7 @@ struct eqvio_filter {
     unsigned char* hd_frame = nullptr;  // device-side address of the pinned frame block (zero-copy upload kernel)
     unsigned char* hd_out = nullptr;    // ... of the pinned result block
     int zeroCopy = 1;                   // frame / result blocks move through block_copy_kernel instead of memcpy nodes
+    int splitDowndate = 1;              // two CTAs per Sigma tile when the whole downdate is a single wave
     size_t frameBytes = 0, offImu = 0, offY = 0, offMeasIdx = 0, offLmOf = 0, offYIdx = 0;
     int* d_yIdx = nullptr;
     FrameHeader* d_hdrSteps = nullptr;  // one header per IMU sample (per-sample Riccati variants)
@@ -1444,7 +1445,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                 std::swap(gin, gout);
                 if (c > 0) CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * (c - 1) + 1], 0));  // rest(c-1) done
                 if (c == nchunks - 1) {  // last chunk: everything, and full symmetric storage again
-                    chunk_downdate_kernel<<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Yc, guard,
+                    chunk_downdate_kernel<false><<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Yc, guard,
                                                                                               0, T, DD_ALL, T, TL_SLOT(f));
                     LAUNCH_CHECK(f, "chunk_downdate_kernel");
                     break;
@@ -1461,13 +1462,13 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                 for (int ti = mlo; ti <= mhi; ++ti) nBand += ti + 1;
                 const int nRest = (T - w) * (T - w + 1) / 2;
                 CUDA_TRY(f, cudaEventRecord(evF, f->stream));
-                chunk_downdate_kernel<<<nBand, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Yc, guard, mlo, mhi,
+                chunk_downdate_kernel<false><<<nBand, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Yc, guard, mlo, mhi,
                                                                                  DD_BAND, T, TL_SLOT(f));
                 LAUNCH_CHECK(f, "chunk_downdate_kernel");
                 CUDA_TRY(f, cudaStreamWaitEvent(f->stream3, evF, 0));
                 if (nRest > 0) {
                     f->pdlHold = true;
-                    launch_pdl(f, chunk_downdate_kernel, dim3(nRest), dim3(DD_THREADS), (size_t)DD_SMEM, f->stream3, (const double*)f->Sig[f->cur],
+                    launch_pdl(f, chunk_downdate_kernel<false>, dim3(nRest), dim3(DD_THREADS), (size_t)DD_SMEM, f->stream3, (const double*)f->Sig[f->cur],
                                f->Sig[f->cur], f->ld, (const double*)Yc, guard, mlo, mhi, (int)DD_REST, T, TL_SLOT(f));
                     f->pdlHold = false;
                     LAUNCH_CHECK(f, "chunk_downdate_kernel");
@@ -1509,8 +1510,13 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                         mlo = (SOFF + 3 * rmin) / DD_T;
                         mhi = (SOFF + 3 * rmax + 2) / DD_T;
                     }
-                    launch_pdl(f, chunk_downdate_kernel, dim3(T * (T + 1) / 2), dim3(DD_THREADS), DD_SMEM, f->stream, f->Sig[f->cur],
-                               f->Sig[f->cur], f->ld, Y, guard, mlo, mhi, (int)DD_ALL, T, TL_SLOT(f));
+                    // one wave with SMs to spare: two CTAs per tile (the launch lasts as long as its slowest CTA)
+                    if (f->splitDowndate && T * (T + 1) / 2 <= f->smCount)
+                        launch_pdl(f, chunk_downdate_kernel<true>, dim3(T * (T + 1)), dim3(DD_THREADS), DD_SMEM, f->stream, f->Sig[f->cur],
+                                   f->Sig[f->cur], f->ld, Y, guard, mlo, mhi, (int)DD_ALL, T, TL_SLOT(f));
+                    else
+                        launch_pdl(f, chunk_downdate_kernel<false>, dim3(T * (T + 1) / 2), dim3(DD_THREADS), DD_SMEM, f->stream, f->Sig[f->cur],
+                                   f->Sig[f->cur], f->ld, Y, guard, mlo, mhi, (int)DD_ALL, T, TL_SLOT(f));
                     LAUNCH_CHECK(f, "chunk_downdate_kernel");
                 }
                 prof_end(f, sk);
@@ -1698,9 +1704,11 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
         g_createError = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
         return EQVIO_ERR_CUDA;
     }
-    e = cudaFuncSetAttribute(chunk_downdate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM);
+    e = cudaFuncSetAttribute(chunk_downdate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     // factor CTAs of the next chunk must fit beside the deferred downdate CTAs: keep the shared-memory carve-out at its maximum
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ChunkSmem) > (size_t)CH_SMEM_STAGED ? sizeof(ChunkSmem) : (size_t)CH_SMEM_STAGED));

@@ -1631,6 +1631,10 @@ constexpr int DD_T = 64, DD_LD = YB_LD, DD_THREADS = 128;
 constexpr int DD_SMEM = 2 * DD_T * DD_LD * 8 + 16;
 enum { DD_ALL = 0, DD_BAND = 1, DD_REST = 2 };  // which tiles a launch of chunk_downdate_kernel covers
 
+// SPLIT: two CTAs per tile (32 of its 64 rows each).  When all lower tiles fit in one wave with SMs to spare (N <= 256: 91
+// tiles on 148 SMs) a launch is as long as ONE tile takes -- Y panels in, 64 x 64 x 64 FMAs on one SM's fp64 pipe (2.1 us),
+// tile out; halving the rows per CTA halves the pipe time of that critical CTA.
+template <bool SPLIT>
 __global__ void __launch_bounds__(DD_THREADS, 3)
     chunk_downdate_kernel(const double* SigIn, double* SigOut, int ld, const double* __restrict__ Y,
                           const int* __restrict__ guard, int mirrorLo, int mirrorHi, int mode, int T, int tl) {
@@ -1638,13 +1642,16 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
     if (*guard) return;
     TL_MARK(tl, 0);
     int ti, tj;
+    const int bid = SPLIT ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int half = SPLIT ? (int)(blockIdx.x & 1) : 0;
+    constexpr int NA = SPLIT ? 2 : 4;  // 8-row fragments per warp
     if (mode == DD_ALL) {
-        tri_decode(blockIdx.x, ti, tj);  // lower-triangular tile index -> (ti, tj), ti >= tj
+        tri_decode(bid, ti, tj);  // lower-triangular tile index -> (ti, tj), ti >= tj
     } else if (mode == DD_BAND) {
         // look-ahead split, urgent part: the lower tiles that meet the band [mirrorLo, mirrorHi] of tile rows / columns
         // the NEXT chunk gathers from -- first the band's tile rows (mirrored into the band's tile columns above the
         // diagonal), then the band's tile columns below the band
-        int b = blockIdx.x;
+        int b = bid;
         ti = mirrorLo;
         while (ti <= mirrorHi && b >= ti + 1) b -= ++ti;  // rows mirrorLo.. hold ti + 1 tiles each
         if (ti <= mirrorHi) {
@@ -1657,7 +1664,7 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
     } else {
         // look-ahead split, deferred part: the lower tiles with neither index in the band (runs beside the next factor)
         int ci, cj;
-        tri_decode(blockIdx.x, ci, cj);
+        tri_decode(bid, ci, cj);
         const int w = mirrorHi - mirrorLo + 1;
         ti = ci < mirrorLo ? ci : ci + w;
         tj = cj < mirrorLo ? cj : cj + w;
@@ -1679,13 +1686,13 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
     }
     // The Sigma tile goes straight into the accumulator fragment layout: element (r, c) of the tile is
     // Sigma[i0 + r, j0 + c]; for one (a, b, e) a warp touches 4 columns x 8 consecutive rows = whole sectors.
-    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int wm = half * 32 + (warp >> 1) * (8 * NA), wn = (warp & 1) * 32;
     const int fr = wm + (lane >> 2), fc = wn + (lane & 3) * 2;
-    double acc[4][4][2];
+    double acc[NA][4][2];
     const double* cin = SigIn + (size_t)(j0 + fc) * ld + i0 + fr;
     double* cbase = SigOut + (size_t)(j0 + fc) * ld + i0 + fr;
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < NA; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             acc[a][b][0] = -cin[(size_t)(b * 8) * ld + a * 8];
@@ -1696,13 +1703,13 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
     double(*sBB)[DD_LD] = diag ? sA : sB;
 #pragma unroll 4
     for (int k4 = 0; k4 < DD_T; k4 += 4) {
-        double af[4], bf[4];
+        double af[NA], bf[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) af[a] = sA[k4 + (lane & 3)][wm + a * 8 + (lane >> 2)];
+        for (int a = 0; a < NA; ++a) af[a] = sA[k4 + (lane & 3)][wm + a * 8 + (lane >> 2)];
 #pragma unroll
         for (int b = 0; b < 4; ++b) bf[b] = sBB[k4 + (lane & 3)][wn + b * 8 + (lane >> 2)];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < NA; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
     }
@@ -1711,7 +1718,7 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
     // tile rows [mirrorLo, mirrorHi]); the last chunk (mirrorLo = 0, mirrorHi = all) restores full symmetric storage.
     const bool mirror = !diag && ti >= mirrorLo && ti <= mirrorHi;
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < NA; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const double v0 = -acc[a][b][0], v1 = -acc[a][b][1];
