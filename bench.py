@@ -485,6 +485,18 @@ def run_b200(args, rank, local_rank, world, guard):
 
     N, K, W, P, R = args.landmarks, args.steps, args.warmup, args.profile_steps, args.sequences_per_gpu
     dev = torch.device("cuda", local_rank)
+    host_cores = None
+    if world > 1:
+        # one disjoint block of host cores per rank: the e2e figure is a max over ranks of HOST wall clock, and ranks whose driver
+        # threads share or migrate between cores pay for it (round 1: e2e efficiency 0.80 at 8 GPUs with every rank on cores 0-31)
+        try:
+            allowed = sorted(os.sched_getaffinity(0))
+            per = max(1, len(allowed) // world)
+            mine_cores = allowed[local_rank * per:(local_rank + 1) * per] or allowed
+            os.sched_setaffinity(0, mine_cores)
+            host_cores = [mine_cores[0], mine_cores[-1]]
+        except Exception:
+            host_cores = None
     flush_buf = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     sampler = ClockSampler(local_rank)
     total_instances = R * world
@@ -651,7 +663,8 @@ def run_b200(args, rank, local_rank, world, guard):
                                 "host bracket of each step of the GPU's concurrent sequences (their device times overlap)",
                                 launch_mode="per-kernel launches" if args.no_graph else "steady frames replayed as a cached CUDA graph",
                                 parallelism=f"replicas: {R} sequence(s) per GPU x {world} GPU(s), no data-path collective, "
-                                "one all-gather of trajectories per lap"),
+                                "one all-gather of trajectories per lap",
+                                host_cores_rank0=host_cores),
                     e2e=dict(value=world * R * K / (e2e_ms * 1e-3), unit="updates/s", h2d_bytes_per_step=m["h2d"], d2h_bytes_per_step=m["d2h"],
                              ms_per_step=e2e_ms / K, collective_ms=coll_ms_max, collective_charged_ms=coll_share,
                              collective_note=(f"one all-gather of the trajectories per simulated lap ({LAP_UPDATES} updates); "
