@@ -1,0 +1,725 @@
+// Correction, block form with look-ahead (EQVIO_TUNE_CORRECTION = 2): performVisionUpdate (VIO_eqf.cpp:105-135) as ONE
+// blocked right-looking Cholesky sweep over the augmented matrix
+//        Z = [ S ; W^T ],   S = C Sigma C^T + sigma^2 I  (m x m),   W^T = Sigma C^T  (dimp x m, ytilde^T riding in pad row 21)
+// with 64-wide block columns.  After block column k:  P = Z[below, blk k] L_kk^-T  (the W rows of P are Y_k^T, row 21 is z_k^T),
+// the trailing blocks take  Z_ij -= P_i P_j^T,  and  Sigma -= Y_k^T Y_k,  Gamma += Y_k^T z_k  follow from the same product.
+//
+// What is on the critical path is only the chain of 64 x 64 diagonal factorizations:
+//   bc_diag_kernel   (1 CTA, stream A)   step k:  D = T_kk - P_{k,k-1} P_{k,k-1}^T  with  P_{k,k-1} = T_{k,k-1} L_{k-1,k-1}^-T  (DMMA, the
+//                    look-ahead: T_* are current through step k-2), factor D in 4x4 register tiles; hands over L_kk (transposed) and the
+//                    inverses of its four diagonal 16 x 16 blocks.
+//   bc_panel_kernel  (stream B)          P = Z[rows below, blk k] L_kk^-T  for every row tile (DMMA block substitution) -> Zp (tile-blocked panels)
+//   bc_trail_kernel  (stream B)          S / W trailing tiles  Z_ij -= P_i P_j^T,  Sigma tiles -= Y_a Y_b^T,  Gamma   (DMMA)
+// Dependencies:  diag(k) -> panel(k) -> trail(k) -> diag(k+2);  diag(k) -> diag(k+1) is a programmatic (PDL) edge.
+// The sequential-chunk form (kernels.cuh) needs the downdated Sigma before the next chunk can even be gathered; here the trailing
+// work runs beside the next factorization and only ~2 us of DMMA products per block sit between two factorizations.
+#pragma once
+#include "kernels.cuh"
+
+namespace eqvio {
+
+constexpr int BC_T = 64;                 // block width of the sweep
+constexpr int BC_YROW = 21;              // pad row of the state that carries ytilde / z
+constexpr int BC_MAX_ROWS = 768;         // largest m served by this form (beyond that the trailing work dominates: sequential chunks)
+
+// ------------------------------------------------------------------------------------------------
+// Z build.  Tile list: lower tiles of S (i >= j), then the W tiles (w, j).  256 threads per 64 x 64 tile.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    bc_build_kernel(const double* __restrict__ Sig, int ld, int dimp, const int* __restrict__ lmOf, const double* __restrict__ Cblk,
+                    const double* __restrict__ ytilde, int nm, double r2, double* __restrict__ Z, int ldz, int nT, int TW,
+                    const int* __restrict__ guard, int tl) {
+    pdl_wait();
+    if (*guard) return;
+    TL_MARK(tl, 0);
+    __shared__ double sC[32][6];
+    __shared__ int sIdx[32];
+    __shared__ double sCr[32][6];
+    __shared__ int sIdxR[32];
+    const int tid = threadIdx.x;
+    const int nS = nT * (nT + 1) / 2;
+    const int m = 2 * nm;
+    int bid = blockIdx.x;
+    if (bid < nS) {
+        int ti, tj;
+        tri_decode(bid, ti, tj);
+        // landmark pairs of the tile rows (32 of them) and tile columns
+        if (tid < 32) {
+            const int j = 32 * tj + tid;
+            sIdx[tid] = j < nm ? SOFF + 3 * lmOf[j] : -1;
+            for (int q = 0; q < 6; ++q) sC[tid][q] = j < nm ? Cblk[6 * (size_t)j + q] : 0.0;
+        } else if (tid < 64) {
+            const int t = tid - 32;
+            const int j = 32 * ti + t;
+            sIdxR[t] = j < nm ? SOFF + 3 * lmOf[j] : -1;
+            for (int q = 0; q < 6; ++q) sCr[t][q] = j < nm ? Cblk[6 * (size_t)j + q] : 0.0;
+        }
+        __syncthreads();
+        // thread: row landmark u = tid & 31, column landmarks v = (tid >> 5) + 8 q
+        const int u = tid & 31;
+        const int ir = sIdxR[u];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int v = (tid >> 5) + 8 * q;
+            const int ic = sIdx[v];
+            double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            if (ir >= 0 && ic >= 0) {
+                double P[3][3];
+#pragma unroll
+                for (int b = 0; b < 3; ++b)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) P[a][b] = Sig[(size_t)(ic + b) * ld + ir + a];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double T[3];
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) T[b] = sCr[u][3 * e] * P[0][b] + sCr[u][3 * e + 1] * P[1][b] + sCr[u][3 * e + 2] * P[2][b];
+#pragma unroll
+                    for (int f = 0; f < 2; ++f) o[e][f] = T[0] * sC[v][3 * f] + T[1] * sC[v][3 * f + 1] + T[2] * sC[v][3 * f + 2];
+                }
+            }
+            const int R0 = 64 * ti + 2 * u, C0 = 64 * tj + 2 * v;
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int f = 0; f < 2; ++f) {
+                    const int R = R0 + e, Cc = C0 + f;
+                    double val = o[e][f];
+                    if (R == Cc) val = (R < m) ? val + r2 : 1.0;  // identity padding of a short last block
+                    Z[(size_t)Cc * ldz + R] = val;
+                }
+        }
+    } else {
+        bid -= nS;
+        const int tw = bid / nT, tj = bid % nT;
+        if (tid < 32) {
+            const int j = 32 * tj + tid;
+            sIdx[tid] = j < nm ? SOFF + 3 * lmOf[j] : -1;
+            for (int q = 0; q < 6; ++q) sC[tid][q] = j < nm ? Cblk[6 * (size_t)j + q] : 0.0;
+        }
+        __syncthreads();
+        const int sl = tid & 63;
+        const int s = 64 * tw + sl;
+        double* zrow = Z + (size_t)nT * BC_T + s;  // W rows start behind the nT S tiles
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int v = (tid >> 6) + 4 * q;
+            const int ic = sIdx[v];
+            double o0 = 0.0, o1 = 0.0;
+            if (ic >= 0) {
+                if (s == BC_YROW) {
+                    o0 = ytilde[2 * (32 * tj + v)];
+                    o1 = ytilde[2 * (32 * tj + v) + 1];
+                } else if (s < dimp) {
+                    const double s0 = Sig[(size_t)ic * ld + s], s1 = Sig[(size_t)(ic + 1) * ld + s], s2 = Sig[(size_t)(ic + 2) * ld + s];
+                    o0 = sC[v][0] * s0 + sC[v][1] * s1 + sC[v][2] * s2;
+                    o1 = sC[v][3] * s0 + sC[v][4] * s1 + sC[v][5] * s2;
+                }
+            }
+            const int C0 = 64 * tj + 2 * v;
+            zrow[(size_t)C0 * ldz] = o0;
+            zrow[(size_t)(C0 + 1) * ldz] = o1;
+        }
+    }
+    TL_MARK(tl, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Diagonal step of the sweep (the critical path).
+//
+// The factorization follows chunk_factor_kernel (right-looking over 4x4 tiles of the lower triangle, unscaled columns, fraction-free
+// elimination of the diagonal tile with its four reciprocals side by side), with two changes measured on this kernel (per-warp clock
+// stamps, scripts/bc_timing.py): a lone warp issues one fp64 instruction every ~4 clocks, so what a block column costs is the LENGTH of
+// each warp's instruction stream, not the pipe's throughput --
+//   * every tile is split between two threads (rows 2h, 2h+1): 40 instead of 80 fp64 instructions per rank-4 update and warp, twice the
+//     warps to interleave; published tiles are 16 contiguous doubles (+2 pad) so panels move as 16-byte shared-memory accesses;
+//   * the next diagonal tile is eliminated right after its own update (look-ahead), not behind a barrier of its own.
+// M_k = L_kk^-1 comes from 256 threads that carry the identity through the same elimination, one block column behind (mbarrier per
+// block column), and do not take part in the S group's barriers.
+// ------------------------------------------------------------------------------------------------
+constexpr int BC_S_WARPS = 9;                      // 136 tiles x 2 half-tile owners = 272 threads
+constexpr int BC_S_THREADS = BC_S_WARPS * 32;      // 288
+constexpr int BC_X_THREADS = 64;                   // 4 diagonal 16 x 16 blocks x (4 x 4 tiles): their inverses ride along
+constexpr int BC_DIAG_THREADS = 512;               // 16 warps for the DMMA prologue; warps 0-8 = S group, 9-10 = X group
+constexpr int BC_PLD = 18;                         // doubles per published tile: [r][j] and 2 of padding (conflict-free 16-byte reads)
+// What a diagonal step hands to its consumers (the next diagonal step, the panel kernel), per block k, two 64 x YB_LD arrays:
+//   LT[c][r] = L_kk[r][c]   (strictly lower 4x4 tiles; only the 16 x 16 blocks BELOW the diagonal blocks are read)
+//   XT[j][c] = X_b[c][j]    for j, c in the same 16-block b: X_b = (b-th diagonal 16 x 16 block of L_kk)^-1
+// P = T L_kk^-T is then a 4-stage block substitution on the FP64 tensor pipe:  P_b = (T_b - sum_{j<b} P_j L_bj^T) X_b^T.
+// (An explicit 64 x 64 inverse riding along the whole factorization was measured first: its 256 threads made the loop fp64-pipe
+// bound, ~1200 clocks per block column instead of ~650.)
+constexpr size_t BC_LX = 2 * YB_TILE;
+
+struct BcDiagSmem {
+    double A[BC_T][YB_LD];            // T_{k,k-1} as A[j][r]; stage by stage replaced by P_{k,k-1} as A[c][r]
+    double B[BC_T][YB_LD];            // LT of block k-1; after the substitution the updated diagonal block as B[c][r]
+    double X[BC_T][YB_LD];            // XT of block k-1
+    double Q[16][YB_LD];              // one stage's 64 x 16 block between its two products
+    double Lp[CH_NT][CH_NT][BC_PLD];  // Lp[J][TI][4 r + j]: tile (TI, J) once block column J is finished (unscaled columns); TI = J: the diagonal tile
+    double Dc[CH_NT][CH_T];           // reciprocal pivots of block column J
+    double Inv[BC_T];
+    uint64_t colBar[CH_NT];           // one mbarrier per block column: "its panels are published" (S group -> X group)
+};
+constexpr int BC_DIAG_SMEM = (int)sizeof(BcDiagSmem);
+
+#ifdef EQVIO_CHUNK_TIMING
+__device__ long long g_bc_t[16];
+__device__ int g_bc_warp[BC_S_WARPS * 64];
+// per-warp stamps go to shared memory (no global stores inside the loop) and are dumped after it
+#define BC_FINE(i) do { if ((threadIdx.x & 31) == 0 && threadIdx.x < BC_S_THREADS) bc_stamps[threadIdx.x >> 5][(i)] = (int)clock(); } while (0)
+#define BC_STAMP(i) do { if (threadIdx.x == 0 && kblk == 1) g_bc_t[(i)] = clock64(); } while (0)
+#else
+#define BC_FINE(i) do { } while (0)
+#define BC_STAMP(i) do { } while (0)
+#endif
+__device__ __forceinline__ void bc_s_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(BC_S_THREADS) : "memory"); }
+__device__ __forceinline__ int bc_diag_tile(int J) { return CH_NT * J - J * (J - 1) / 2; }  // column-major index of tile (J, J)
+
+// Z: augmented matrix (ldz), kblk: block column.  LxAll: per block the LT | XT pair described above.
+__global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
+    bc_diag_kernel(const double* __restrict__ Z, int ldz, int kblk, double* __restrict__ LxAll, int* __restrict__ status,
+                   const int* __restrict__ guard, int tl) {
+    extern __shared__ __align__(128) unsigned char bc_smem_raw[];
+    BcDiagSmem& sm = *reinterpret_cast<BcDiagSmem*>(bc_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int k0 = kblk * BC_T;
+    BC_STAMP(0);
+    if (tid == 0) {
+        for (int J = 0; J < CH_NT; ++J) mbar_init(&sm.colBar[J], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // Everything this kernel reads comes from earlier kernels: wait first.  (Reading T_* ahead of the wait would need the edge from
+    // trail(k-2) to be a full dependency; with the programmatic-serialization attribute set, a captured node's kernel
+    // predecessors all become programmatic edges, and trail kernels release their dependents at their start.)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (*guard) return;
+    TL_MARK(tl, 0);
+    BC_STAMP(1);
+    const bool sGroup = tid < BC_S_THREADS;
+    const int t = tid >> 1, h = tid & 1;  // S group: tile t (column-major over the lower triangle), rows 2h, 2h+1 of it
+    const bool owner = sGroup && t < CH_TILES;
+    int TI = 0, TK = 0;
+    if (owner) tri_decode_cm(t, CH_NT, TI, TK);
+    double a[2][CH_T];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < CH_T; ++c) a[r][c] = 0.0;
+
+    if (kblk > 0) {
+        // ---- look-ahead products on the FP64 tensor pipe (16 warps):  P = T_{k,k-1} L^-T (block substitution),  D = T_kk - P P^T  ----
+        const double* Tp = Z + (size_t)(k0 - BC_T) * ldz + k0;  // T_{k,k-1}
+        const double* Td = Z + (size_t)k0 * ldz + k0;           // T_{k,k}
+        const double2* Lxp = reinterpret_cast<const double2*>(LxAll + (size_t)(kblk - 1) * BC_LX);
+        double2* Bp = reinterpret_cast<double2*>(&sm.B[0][0]);  // B and X are adjacent: LT | XT in one run
+        for (int q = tid; q < BC_T * (BC_T / 2); q += BC_DIAG_THREADS) {
+            const int j = q >> 5, r = (q & 31) * 2;
+            const double2 v = *reinterpret_cast<const double2*>(Tp + (size_t)j * ldz + r);
+            sm.A[j][r] = v.x;
+            sm.A[j][r + 1] = v.y;
+        }
+        for (int q = tid; q < (int)(BC_LX / 2); q += BC_DIAG_THREADS) Bp[q] = Lxp[q];
+        // second product: the 36 lower 8x8 fragments of D go round-robin over the 16 warps (9 per SM sub-partition)
+        double acc2[3][2];
+        if (warp < 16) {
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int f = warp + 16 * u;
+                if (f < 36) {
+                    int fi, fj;
+                    tri_decode(f, fi, fj);
+                    acc2[u][0] = -Td[(size_t)(8 * fj + 2 * t4) * ldz + 8 * fi + g];
+                    acc2[u][1] = -Td[(size_t)(8 * fj + 2 * t4 + 1) * ldz + 8 * fi + g];
+                }
+            }
+        }
+        __syncthreads();
+        BC_STAMP(2);
+        // four stages, one 8 x 8 fragment of the stage's 64 x 16 block per warp (row fragment fi, column fragment fn)
+        {
+            const int fi = warp & 7, fn = warp >> 3;
+#pragma unroll 1
+            for (int b = 0; b < 4; ++b) {
+                const int c0 = 16 * b + 8 * fn;
+                double q0 = -sm.A[c0 + 2 * t4][8 * fi + g], q1 = -sm.A[c0 + 2 * t4 + 1][8 * fi + g];
+                for (int k4 = 0; k4 < 16 * b; k4 += 4) dmma884(q0, q1, sm.A[k4 + t4][8 * fi + g], sm.B[k4 + t4][c0 + g]);
+                sm.Q[8 * fn + 2 * t4][8 * fi + g] = -q0;
+                sm.Q[8 * fn + 2 * t4 + 1][8 * fi + g] = -q1;
+                __syncthreads();
+                double p0 = 0.0, p1 = 0.0;
+                for (int k4 = 0; k4 < 8 * (fn + 1); k4 += 4) dmma884(p0, p1, sm.Q[k4 + t4][8 * fi + g], sm.X[16 * b + k4 + t4][c0 + g]);
+                sm.A[c0 + 2 * t4][8 * fi + g] = p0;  // P_b takes the place of T's block column b
+                sm.A[c0 + 2 * t4 + 1][8 * fi + g] = p1;
+                __syncthreads();
+            }
+        }
+        BC_STAMP(3);
+        if (warp < 16) {
+            int fi[3], fj[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                fi[u] = fj[u] = 0;
+                if (warp + 16 * u < 36) tri_decode(warp + 16 * u, fi[u], fj[u]);
+            }
+            const int nf = warp < 4 ? 3 : 2;
+#pragma unroll 4
+            for (int c4 = 0; c4 < BC_T; c4 += 4) {
+#pragma unroll
+                for (int u = 0; u < 3; ++u)
+                    if (u < nf) dmma884(acc2[u][0], acc2[u][1], sm.A[c4 + t4][8 * fi[u] + g], sm.A[c4 + t4][8 * fj[u] + g]);
+            }
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+                if (u < nf) {
+                    sm.B[8 * fj[u] + 2 * t4][8 * fi[u] + g] = -acc2[u][0];
+                    sm.B[8 * fj[u] + 2 * t4 + 1][8 * fi[u] + g] = -acc2[u][1];
+                }
+        }
+        __syncthreads();
+        BC_STAMP(4);
+        if (owner) {
+#pragma unroll
+            for (int c = 0; c < CH_T; ++c)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) a[r][c] = sm.B[CH_T * TK + c][CH_T * TI + 2 * h + r];
+        }
+    } else {
+        BC_STAMP(2);
+        BC_STAMP(3);
+        if (owner) {
+            const double* Td = Z + (size_t)k0 * ldz + k0;
+#pragma unroll
+            for (int c = 0; c < CH_T; ++c) {
+                const double2 v = *reinterpret_cast<const double2*>(Td + (size_t)(CH_T * TK + c) * ldz + CH_T * TI + 2 * h);
+                a[0][c] = v.x;
+                a[1][c] = v.y;
+            }
+        }
+        __syncthreads();  // mbarriers initialised
+        BC_STAMP(4);
+    }
+
+#ifdef EQVIO_CHUNK_TIMING
+    __shared__ int bc_stamps[BC_S_WARPS][64];
+#endif
+    if (sGroup) {
+        // ================================ S group: the factorization ================================
+        double pv[CH_T] = {1.0, 1.0, 1.0, 1.0};  // pivots of the diagonal tile eliminated by this thread
+        // Diagonal tile (J, J): called by the whole warp that holds it; the h = 0 thread fetches rows 2, 3 from its neighbour and
+        // eliminates (fraction-free: products only, then the four reciprocals side by side), publishes the tile and 1 / pivots.
+        auto eliminate = [&](int J) {
+            const double a20 = __shfl_down_sync(0xffffffffu, a[0][0], 1), g21 = __shfl_down_sync(0xffffffffu, a[0][1], 1),
+                         g22 = __shfl_down_sync(0xffffffffu, a[0][2], 1);
+            const double a30 = __shfl_down_sync(0xffffffffu, a[1][0], 1), g31 = __shfl_down_sync(0xffffffffu, a[1][1], 1),
+                         g32 = __shfl_down_sync(0xffffffffu, a[1][2], 1), g33 = __shfl_down_sync(0xffffffffu, a[1][3], 1);
+            if (tid == 2 * bc_diag_tile(J)) {
+                const double a00 = a[0][0], a10 = a[1][0];
+                const double m11 = a[1][1] * a00 - a10 * a10, m21 = g21 * a00 - a20 * a10, m22 = g22 * a00 - a20 * a20;
+                const double m31 = g31 * a00 - a30 * a10, m32 = g32 * a00 - a30 * a20, m33 = g33 * a00 - a30 * a30;
+                const double n22 = m22 * m11 - m21 * m21, n32 = m32 * m11 - m31 * m21, n33 = m33 * m11 - m31 * m31;
+                const double p33 = n33 * n22 - n32 * n32;
+                const double r0 = fast_rcp(a00), r1 = fast_rcp(m11), r2_ = fast_rcp(n22), r3 = fast_rcp(p33);
+                const double s2 = r0 * r1, s3 = s2 * r2_, e1 = a00 * m11;
+                pv[0] = a00;
+                pv[1] = m11 * r0;
+                pv[2] = n22 * s2;
+                pv[3] = p33 * s3;
+                double2* dc = reinterpret_cast<double2*>(&sm.Dc[J][0]);
+                dc[0] = make_double2(r0, a00 * r1);
+                dc[1] = make_double2(e1 * r2_, (e1 * n22) * r3);
+                // unscaled columns below the diagonal (what the panel owners need): d[k][j], j < k
+                double2* dt = reinterpret_cast<double2*>(&sm.Lp[J][J][0]);
+                dt[2] = make_double2(a10, 0.0);
+                dt[4] = make_double2(a20, m21 * r0);
+                dt[6] = make_double2(a30, m31 * r0);
+                dt[7] = make_double2(n32 * s2, 0.0);
+            }
+        };
+        const int myWarpFirstTile = (warp * 32) >> 1, myWarpLastTile = myWarpFirstTile + 15;
+        if (warp == 0) eliminate(0);
+        for (int J = 0; J < CH_NT; ++J) {
+            BC_FINE(4 * J);
+            BC_FINE(4 * J + 1);
+            bc_s_barrier();  // diagonal tile J published
+            BC_FINE(4 * J + 2);
+            if (owner && TK == J && TI > J) {
+                const double2 c01 = *reinterpret_cast<const double2*>(&sm.Dc[J][0]);
+                const double c2 = sm.Dc[J][2];
+                const double2* dt = reinterpret_cast<const double2*>(&sm.Lp[J][J][0]);
+                const double d10 = dt[2].x;
+                const double2 d2 = dt[4], d3 = dt[6];
+                const double d32 = dt[7].x;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const double t0 = a[r][0] * c01.x;
+                    a[r][1] -= t0 * d10;
+                    a[r][2] -= t0 * d2.x;
+                    a[r][3] -= t0 * d3.x;
+                    const double t1 = a[r][1] * c01.y;
+                    a[r][2] -= t1 * d2.y;
+                    a[r][3] -= t1 * d3.y;
+                    const double t2 = a[r][2] * c2;
+                    a[r][3] -= t2 * d32;
+                }
+                double2* out = reinterpret_cast<double2*>(&sm.Lp[J][TI][8 * h]);
+                out[0] = make_double2(a[0][0], a[0][1]);
+                out[1] = make_double2(a[0][2], a[0][3]);
+                out[2] = make_double2(a[1][0], a[1][1]);
+                out[3] = make_double2(a[1][2], a[1][3]);
+            }
+            bc_s_barrier();  // panels of block column J published
+            BC_FINE(4 * J + 3);
+            // the S group's barrier above ordered every panel store before this arrive (release, cumulative); a release STORE to a
+            // flag word would cost a MEMBAR.ALL.CTA in warp 0 on every block column, the mbarrier arrive does not
+            if (tid == 0) mbar_arrive(&sm.colBar[J]);
+            if (owner && TK > J) {
+                const double2* cp = reinterpret_cast<const double2*>(&sm.Dc[J][0]);
+                const double2 c01 = cp[0], c23 = cp[1];
+                const double2* lp = reinterpret_cast<const double2*>(&sm.Lp[J][TI][8 * h]);
+                const double2* pp = reinterpret_cast<const double2*>(&sm.Lp[J][TK][0]);
+                double li[2][CH_T];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const double2 x = lp[2 * r], y = lp[2 * r + 1];
+                    li[r][0] = x.x * c01.x;
+                    li[r][1] = x.y * c01.y;
+                    li[r][2] = y.x * c23.x;
+                    li[r][3] = y.y * c23.y;
+                }
+#pragma unroll
+                for (int cc = 0; cc < CH_T; ++cc) {
+                    const double2 x = pp[2 * cc], y = pp[2 * cc + 1];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        double acc = a[r][cc];
+                        acc -= li[r][0] * x.x;
+                        acc -= li[r][1] * x.y;
+                        acc -= li[r][2] * y.x;
+                        acc -= li[r][3] * y.y;
+                        a[r][cc] = acc;
+                    }
+                }
+            }
+            // look-ahead: the next diagonal tile is eliminated as soon as its own update is in, while the other warps are still in
+            // theirs -- the next iteration goes straight to its first barrier
+            if (J + 1 < CH_NT) {
+                const int dn = bc_diag_tile(J + 1);
+                if (dn >= myWarpFirstTile && dn <= myWarpLastTile) eliminate(J + 1);
+            }
+        }
+        if (owner && TI == TK && h == 0) {
+#pragma unroll
+            for (int c = 0; c < CH_T; ++c) {
+                const double piv = pv[c];
+                const int k = CH_T * TK + c;
+                if (!(piv > 0.0)) {
+                    atomicOr(status, 1);
+                    sm.Inv[k] = 1.0;
+                } else {
+                    sm.Inv[k] = 1.0 / sqrt(piv);
+                }
+            }
+        }
+        BC_STAMP(5);
+        __syncthreads();  // Inv published
+        // LT: the off-diagonal tiles are still in their owners' registers (unscaled columns: L_ij = v_ij / L_jj)
+        if (owner && TI > TK) {
+            double* Lt = LxAll + (size_t)kblk * BC_LX;
+#pragma unroll
+            for (int j = 0; j < CH_T; ++j) {
+                const double sc = sm.Inv[CH_T * TK + j];
+                *reinterpret_cast<double2*>(Lt + (size_t)(CH_T * TK + j) * YB_LD + CH_T * TI + 2 * h) = make_double2(a[0][j] * sc, a[1][j] * sc);
+            }
+        }
+    } else if (tid < BC_S_THREADS + BC_X_THREADS) {
+        // ======== X group: the identity rides along inside each diagonal 16 x 16 block (4 steps per block): X_b = L_bb^-1 ========
+        const int q = tid - BC_S_THREADS;
+        const int blk = q >> 4, i = (q >> 2) & 3, tk = q & 3;
+        TI = 4 * blk + i;   // tile row: rows 4 TI .. 4 TI + 3 of the identity
+        TK = 4 * blk + tk;  // tile column
+        const unsigned grp = 0xffffu << (16 * (blk & 1));  // the 16 lanes of this block: the two blocks of a warp run at their own pace
+        double b[CH_T][CH_T];
+#pragma unroll
+        for (int r = 0; r < CH_T; ++r)
+#pragma unroll
+            for (int c = 0; c < CH_T; ++c) b[r][c] = (i == tk && r == c) ? 1.0 : 0.0;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            const int J = 4 * blk + j;
+            if (!mbar_wait_bounded(&sm.colBar[J], 0)) atomicOr(status, 8);
+            const double2* cp = reinterpret_cast<const double2*>(&sm.Dc[J][0]);
+            const double2 c01 = cp[0], c23 = cp[1];
+            const double c[CH_T] = {c01.x, c01.y, c23.x, c23.y};
+            if (tk == j) {
+                const double2* dt = reinterpret_cast<const double2*>(&sm.Lp[J][J][0]);
+                const double d10 = dt[2].x;
+                const double2 d2 = dt[4], d3 = dt[6];
+                const double d32 = dt[7].x;
+#pragma unroll
+                for (int r = 0; r < CH_T; ++r) {
+                    const double t0 = b[r][0] * c[0];
+                    b[r][1] -= t0 * d10;
+                    b[r][2] -= t0 * d2.x;
+                    b[r][3] -= t0 * d3.x;
+                    const double t1 = b[r][1] * c[1];
+                    b[r][2] -= t1 * d2.y;
+                    b[r][3] -= t1 * d3.y;
+                    const double t2 = b[r][2] * c[2];
+                    b[r][3] -= t2 * d32;
+                }
+            }
+            double li[CH_T][CH_T];
+#pragma unroll
+            for (int r = 0; r < CH_T; ++r)
+#pragma unroll
+                for (int jj = 0; jj < CH_T; ++jj) li[r][jj] = __shfl_sync(grp, b[r][jj], j, 4) * c[jj];
+            if (tk > j) {
+                const double2* pp = reinterpret_cast<const double2*>(&sm.Lp[J][TK][0]);
+#pragma unroll
+                for (int cc = 0; cc < CH_T; ++cc) {
+                    const double2 x = pp[2 * cc], y = pp[2 * cc + 1];
+#pragma unroll
+                    for (int r = 0; r < CH_T; ++r) {
+                        double acc = b[r][cc];
+                        acc -= li[r][0] * x.x;
+                        acc -= li[r][1] * x.y;
+                        acc -= li[r][2] * y.x;
+                        acc -= li[r][3] * y.y;
+                        b[r][cc] = acc;
+                    }
+                }
+            }
+        }
+        __syncthreads();  // Inv published
+        double* Xt = LxAll + (size_t)kblk * BC_LX + YB_TILE;
+#pragma unroll
+        for (int r = 0; r < CH_T; ++r) {
+            double2 lo, hi;
+            lo.x = b[r][0] * sm.Inv[CH_T * TK];
+            lo.y = b[r][1] * sm.Inv[CH_T * TK + 1];
+            hi.x = b[r][2] * sm.Inv[CH_T * TK + 2];
+            hi.y = b[r][3] * sm.Inv[CH_T * TK + 3];
+            double* p = Xt + (size_t)(CH_T * TI + r) * YB_LD + CH_T * TK;
+            *reinterpret_cast<double2*>(p) = lo;
+            *reinterpret_cast<double2*>(p + 2) = hi;
+        }
+    } else {
+        __syncthreads();  // the idle warps of the loop only take part in the barrier
+    }
+#ifdef EQVIO_CHUNK_TIMING
+    if (kblk == 1 && tid < BC_S_WARPS * 32) {
+        g_bc_warp[2 * tid] = bc_stamps[(2 * tid) / 64][(2 * tid) % 64];
+        g_bc_warp[2 * tid + 1] = bc_stamps[(2 * tid + 1) / 64][(2 * tid + 1) % 64];
+    }
+#endif
+    BC_STAMP(6);
+    TL_MARK(tl, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Panel step: P = Z[rows of tile t, blk k] L_kk^-T for every row tile t below the diagonal block (S tiles k+1 .. nT-1, then the
+// W tiles), two CTAs per tile (32 rows each), by the 4-stage block substitution described at BcDiagSmem (LT / XT of block k).
+// Output in the tile-blocked panel layout of the downdate kernel: Zp[t][c][r].
+// ------------------------------------------------------------------------------------------------
+constexpr int BC_PA_LD = 36;  // 32 rows of a half tile (+4: conflict-free fragment reads)
+struct BcPanelSmem {
+    double L[BC_T][YB_LD];      // LT
+    double X[BC_T][YB_LD];      // XT
+    double A[BC_T][BC_PA_LD];   // T as A[j][r]; stage by stage replaced by P as A[c][r]
+    double Q[16][BC_PA_LD];
+    uint64_t bar;
+};
+constexpr int BC_PANEL_SMEM = (int)sizeof(BcPanelSmem);
+
+__global__ void __launch_bounds__(128)
+    bc_panel_kernel(const double* __restrict__ Z, int ldz, int kblk, const double* __restrict__ LxAll, double* __restrict__ Zp,
+                    const int* __restrict__ guard, int tl) {
+    pdl_wait();
+    if (*guard) return;
+    TL_MARK(tl, 0);
+    extern __shared__ __align__(128) unsigned char bcp_smem_raw[];
+    BcPanelSmem& sm = *reinterpret_cast<BcPanelSmem*>(bcp_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int t = kblk + 1 + (int)(blockIdx.x >> 1), half = blockIdx.x & 1;
+    if (tid == 0) {
+        mbar_init(&sm.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&sm.bar, (uint32_t)(BC_LX * 8));
+        bulk_g2s(&sm.L[0][0], LxAll + (size_t)kblk * BC_LX, (uint32_t)(BC_LX * 8), &sm.bar);  // L and X are adjacent: LT | XT in one copy
+    }
+    const double* Tp = Z + (size_t)(kblk * BC_T) * ldz + (size_t)t * BC_T + 32 * half;
+    for (int q = tid; q < BC_T * 16; q += 128) {
+        const int j = q >> 4, r = (q & 15) * 2;
+        const double2 v = *reinterpret_cast<const double2*>(Tp + (size_t)j * ldz + r);
+        sm.A[j][r] = v.x;
+        sm.A[j][r + 1] = v.y;
+    }
+    __syncthreads();
+    mbar_wait(&sm.bar, 0);
+    // 32 rows x 16 columns per stage: row fragment = warp, both column fragments
+    const int fi = warp;
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+        double q[2][2];
+#pragma unroll
+        for (int fn = 0; fn < 2; ++fn) {
+            q[fn][0] = -sm.A[16 * b + 8 * fn + 2 * t4][8 * fi + g];
+            q[fn][1] = -sm.A[16 * b + 8 * fn + 2 * t4 + 1][8 * fi + g];
+        }
+        for (int k4 = 0; k4 < 16 * b; k4 += 4) {
+            const double af = sm.A[k4 + t4][8 * fi + g];
+#pragma unroll
+            for (int fn = 0; fn < 2; ++fn) dmma884(q[fn][0], q[fn][1], af, sm.L[k4 + t4][16 * b + 8 * fn + g]);
+        }
+#pragma unroll
+        for (int fn = 0; fn < 2; ++fn) {
+            sm.Q[8 * fn + 2 * t4][8 * fi + g] = -q[fn][0];
+            sm.Q[8 * fn + 2 * t4 + 1][8 * fi + g] = -q[fn][1];
+        }
+        __syncwarp();  // a warp only reads back its own 8 rows of Q
+        double p[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int k4 = 0; k4 < 16; k4 += 4) {
+            const double af = sm.Q[k4 + t4][8 * fi + g];
+            if (k4 < 8) dmma884(p[0][0], p[0][1], af, sm.X[16 * b + k4 + t4][16 * b + g]);
+            dmma884(p[1][0], p[1][1], af, sm.X[16 * b + k4 + t4][16 * b + 8 + g]);
+        }
+#pragma unroll
+        for (int fn = 0; fn < 2; ++fn) {
+            sm.A[16 * b + 8 * fn + 2 * t4][8 * fi + g] = p[fn][0];
+            sm.A[16 * b + 8 * fn + 2 * t4 + 1][8 * fi + g] = p[fn][1];
+        }
+        __syncwarp();  // ... and its own 8 rows of A
+    }
+    __syncthreads();
+    double* out = Zp + (size_t)t * YB_TILE + 32 * half;
+    for (int q = tid; q < BC_T * 16; q += 128) {
+        const int c = q >> 4, r = (q & 15) * 2;
+        *reinterpret_cast<double2*>(out + (size_t)c * YB_LD + r) = make_double2(sm.A[c][r], sm.A[c][r + 1]);
+    }
+    TL_MARK(tl, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Trailing step: one 64 x 64 tile per CTA pair (32 rows each), C -= P_a P_b^T with the panels from Zp.
+//   S tiles  (i >= j > k, except (k+1, k+1): the next diagonal step applies that one itself)  in Z
+//   W tiles  (w, j > k)                                                                         in Z
+//   Sigma tiles (a >= b), mirrored on the last step; column BC_YROW of the product is -dGamma, row / column BC_YROW of Sigma stay zero
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DD_THREADS, 3)
+    bc_trail_kernel(double* Z, int ldz, double* Sig, int ld, const double* __restrict__ Zp, double* Gamma, const int* __restrict__ guard,
+                    int kblk, int nT, int TW, int dimp, int mirrorAll, int tl) {
+    pdl_wait();
+    if (*guard) return;
+    TL_MARK(tl, 0);
+    const int bid = (int)(blockIdx.x >> 1), half = (int)(blockIdx.x & 1);
+    const int q = nT - kblk - 1;
+    const int nS = q > 0 ? q * (q + 1) / 2 - 1 : 0;
+    int ta, tb;       // panel tiles in Zp
+    double* C;
+    int ldc;
+    bool isSig = false;
+    if (bid < nS) {
+        int li, lj;
+        tri_decode(bid + 1, li, lj);
+        ta = kblk + 1 + li;
+        tb = kblk + 1 + lj;
+        C = Z + (size_t)tb * BC_T * ldz + (size_t)ta * BC_T;
+        ldc = ldz;
+    } else if (bid < nS + TW * q) {
+        const int x = bid - nS;
+        const int w = x / q, lj = x % q;
+        ta = nT + w;
+        tb = kblk + 1 + lj;
+        C = Z + (size_t)tb * BC_T * ldz + (size_t)ta * BC_T;
+        ldc = ldz;
+    } else {
+        int sa, sb;
+        tri_decode(bid - nS - TW * q, sa, sb);
+        ta = nT + sa;
+        tb = nT + sb;
+        C = Sig + (size_t)sb * BC_T * ld + (size_t)sa * BC_T;
+        ldc = ld;
+        isSig = true;
+    }
+    extern __shared__ __align__(16) unsigned char bct_smem_raw[];
+    double(*sA)[DD_LD] = reinterpret_cast<double(*)[DD_LD]>(bct_smem_raw);
+    double(*sB)[DD_LD] = sA + DD_T;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(bct_smem_raw + 2 * DD_T * DD_LD * 8);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool diag = ta == tb;
+    constexpr uint32_t PANEL_BYTES = DD_T * DD_LD * 8;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar, diag ? PANEL_BYTES : 2 * PANEL_BYTES);
+        bulk_g2s(&sA[0][0], Zp + (size_t)ta * YB_TILE, PANEL_BYTES, bar);
+        if (!diag) bulk_g2s(&sB[0][0], Zp + (size_t)tb * YB_TILE, PANEL_BYTES, bar);
+    }
+    const int wm = half * 32 + (warp >> 1) * 16, wn = (warp & 1) * 32;
+    const int fr = wm + (lane >> 2), fc = wn + (lane & 3) * 2;
+    double acc[2][4][2];
+    double* cbase = C + (size_t)fc * ldc + fr;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            acc[a][b][0] = -cbase[(size_t)(b * 8) * ldc + a * 8];
+            acc[a][b][1] = -cbase[(size_t)(b * 8 + 1) * ldc + a * 8];
+        }
+    __syncthreads();
+    mbar_wait(bar, 0);
+    double(*sBB)[DD_LD] = diag ? sA : sB;
+#pragma unroll 4
+    for (int k4 = 0; k4 < DD_T; k4 += 4) {
+        double af[2], bf[4];
+#pragma unroll
+        for (int a = 0; a < 2; ++a) af[a] = sA[k4 + (lane & 3)][wm + a * 8 + (lane >> 2)];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bf[b] = sBB[k4 + (lane & 3)][wn + b * 8 + (lane >> 2)];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+    if (!isSig) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                cbase[(size_t)(b * 8) * ldc + a * 8] = -acc[a][b][0];
+                cbase[(size_t)(b * 8 + 1) * ldc + a * 8] = -acc[a][b][1];
+            }
+    } else {
+        const int i0 = (ta - nT) * BC_T, j0 = (tb - nT) * BC_T;
+        const bool mirror = !diag && mirrorAll;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int R = i0 + fr + a * 8, Cc = j0 + fc + b * 8;
+                const double v0 = -acc[a][b][0], v1 = -acc[a][b][1];
+                if (R == BC_YROW) continue;  // the ytilde row of W: not a state row
+                if (Cc == BC_YROW - 1) {     // columns 20 | 21: the second one is -dGamma
+                    cbase[(size_t)(b * 8) * ldc + a * 8] = v0;
+                    if (R < dimp) Gamma[R] -= v1;
+                    if (mirror) Sig[(size_t)R * ld + Cc] = v0;
+                    continue;
+                }
+                cbase[(size_t)(b * 8) * ldc + a * 8] = v0;
+                cbase[(size_t)(b * 8 + 1) * ldc + a * 8] = v1;
+                if (mirror) {
+                    double2 tt;
+                    tt.x = v0;
+                    tt.y = v1;
+                    *reinterpret_cast<double2*>(Sig + (size_t)R * ld + Cc) = tt;
+                }
+            }
+    }
+    TL_MARK(tl, 1);
+}
+
+}  // namespace eqvio

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <map>
@@ -21,6 +22,7 @@
 #include "../../include/eqvio_b200.h"
 #include "kernels.cuh"
 #include "dense_riccati.cuh"
+#include "blockchol.cuh"
 
 using namespace eqvio;
 
@@ -116,7 +118,9 @@ struct eqvio_filter {
     double *d_rows = nullptr, *d_uv = nullptr, *d_Z = nullptr, *d_Lout = nullptr;
     size_t zElems = 0;
     double *d_Gamma2 = nullptr, *d_ytilde = nullptr;
-    int corrMode = 0;    // 0: sequential chunks (default), 1: batch Cholesky sweep over Z
+    int corrMode = 0;    // 0: sequential chunks, 1: batch Cholesky sweep over Z, 2: block sweep with look-ahead (blockchol.cuh; m <= BC_MAX_ROWS)
+    double *d_bcZ = nullptr, *d_bcZp = nullptr, *d_bcMt = nullptr;  // mode 2: augmented matrix, panel tiles of the current block column, LT | XT per block (blockchol.cuh)
+    std::vector<cudaEvent_t> bcEv;
     int speculate = 1;   // launch the correction before the gate results reach the host (redone on a gate hit)
     int downdateTC = 0;  // 1: tcgen05 split-bf16 downdate (fp32 accumulate in TMEM) instead of the fp64 DMMA one
     unsigned char* d_Ysplit = nullptr;
@@ -502,6 +506,17 @@ int alloc_device(eqvio_filter* f) {
     CUDA_TRY(f, cudaMalloc(&f->d_Ysplit, (size_t)(f->ld / TC_T) * TC_BLOCK_BYTES));
     CUDA_TRY(f, cudaMalloc(&f->d_Y2, (size_t)(f->ld / YB_T) * YB_TILE * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Lout, ((size_t)dimpMax + mMax + NB) * NB * sizeof(double)));
+    {
+        // block sweep (mode 2): Z = [S; W^T] for at most BC_MAX_ROWS measurement rows, tile-blocked panels, one inverse per block
+        const size_t mp = (std::min<size_t>(mMax, BC_MAX_ROWS) + BC_T - 1) / BC_T * BC_T;
+        const size_t ldy = ((size_t)dimpMax + BC_T - 1) / BC_T * BC_T;
+        const size_t zb = (mp + ldy) * mp, zp = (mp / BC_T + ldy / BC_T) * YB_TILE, mt = (mp / BC_T) * BC_LX;
+        CUDA_TRY(f, cudaMalloc(&f->d_bcZ, zb * sizeof(double)));
+        CUDA_TRY(f, cudaMalloc(&f->d_bcZp, zp * sizeof(double)));
+        CUDA_TRY(f, cudaMalloc(&f->d_bcMt, mt * sizeof(double)));
+        CUDA_TRY(f, cudaMemsetAsync(f->d_bcZp, 0, zp * sizeof(double), f->stream));  // the pad columns of the tiles travel with the bulk copies
+        CUDA_TRY(f, cudaMemsetAsync(f->d_bcMt, 0, mt * sizeof(double), f->stream));
+    }
     CUDA_TRY(f, cudaMalloc(&f->d_Cblk, c1 * 6 * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Gamma, (size_t)(dimpMax + 8) * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Gamma2, (size_t)(dimpMax + 8) * sizeof(double)));
@@ -925,7 +940,7 @@ int enqueue_steady_update(eqvio_filter* f, int N, int nm, const FramePlan* plan)
     if ((rc = enqueue_propagation(f)) != EQVIO_OK) return rc;
     f->steadySplit = !f->capturing;  // stage brackets inside the update exist only with plain launches (a replayed graph is one bracket)
     if (f->steadySplit) stage_mark(f, 1);
-    const bool fuseEst = f->fuseSmall && f->corrMode == 0;
+    const bool fuseEst = f->fuseSmall && f->corrMode != 1;
     const bool fuseGate = fuseEst && !plan;  // with a landmark-set change the gate sees the OLD state, the rows the NEW one
     if (!fuseGate && (rc = enqueue_gate(f, N, false)) != EQVIO_OK) return rc;  // riccati_prep_kernel re-armed the flag
     int Nout = N;
@@ -1040,7 +1055,7 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
     for (int i = 0; i < N; ++i) nLost += P.keep[i] ? 0 : 1;
     const int nNewIds = n - matched;
     const bool changeOk = (!anyNew && !anyLost) || (f->specNew && (N - nLost) + nNewIds <= f->cap && (N - nLost) + nNewIds > 0);
-    P.steady = f->speculate && f->corrMode == 0 && N > 0 && n > 0 && !densePath && changeOk;
+    P.steady = f->speculate && f->corrMode != 1 && N > 0 && n > 0 && !densePath && changeOk;
     P.ignoreGate = maxOutliers == 0;
     if (P.steady) {
         FramePlan plan;
@@ -1107,7 +1122,7 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
             stage_mark(f, 3);
         } else {
             const eqvio_settings& st = f->st;
-            std::vector<int> key = {N, n, f->cur, f->lmcur, f->xcur, f->chunkLm, st.coordinateChoice, st.useDiscreteVelocityLift,
+            std::vector<int> key = {N, n, f->cur, f->lmcur, f->xcur, f->chunkLm, f->corrMode, st.coordinateChoice, st.useDiscreteVelocityLift,
                                     st.useDiscreteInnovationLift, st.useEquivariantOutput, f->maxSteps, f->yCap,
                                     change ? 1 : 0, Nout, plan.nNew > 0 ? 1 : 0, P.ignoreGate ? 1 : 0,
                                     // the observer kernel form is chosen on the host from the number of buffered IMU segments
@@ -1254,9 +1269,9 @@ int vision_phase_b(eqvio_filter* f) {
     int nNewIds = 0, nKeptOld = 0;
     for (int j = 0; j < n; ++j) nNewIds += !measInState[j];
     for (int i = 0; i < N; ++i) nKeptOld += P.keep[i] ? 1 : 0;
-    const bool specNew = f->speculate && f->specNew && f->corrMode == 0 && P.gated && anyNew && maxOutliers > 0 && N > 0 &&
+    const bool specNew = f->speculate && f->specNew && f->corrMode != 1 && P.gated && anyNew && maxOutliers > 0 && N > 0 &&
                          nKeptOld + nNewIds <= f->cap;  // (over capacity: the exact path reports the error)
-    P.speculated = f->speculate && f->corrMode == 0 && P.gated && (!anyNew || specNew) && maxOutliers > 0;
+    P.speculated = f->speculate && f->corrMode != 1 && P.gated && (!anyNew || specNew) && maxOutliers > 0;
     const bool noGateNeeded = !P.gated || (maxOutliers == 0 && !(anyNew && s.useMedianDepth));
     if (!P.speculated && !noGateNeeded) CUDA_TRY(f, cudaStreamSynchronize(f->stream));
     std::vector<char> outlier;
@@ -1348,7 +1363,7 @@ int launch_correction(eqvio_filter* f, const int* guard) {
     {
         std::vector<std::pair<int, int>> rows(nm);  // (state index, position in the kept measurement)
         for (int j = 0; j < nm; ++j) rows[j] = {spos.at(kmids[j]), j};
-        if (f->corrMode == 0) std::sort(rows.begin(), rows.end());  // batch mode keeps the reference's ascending-id rows
+        if (f->corrMode != 1) std::sort(rows.begin(), rows.end());  // batch mode keeps the reference's ascending-id rows
         for (int j = 0; j < nm; ++j) {
             lmOf[j] = rows[j].first;
             yIdx[j] = rows[j].second;
@@ -1377,6 +1392,57 @@ int launch_chunk_factor(eqvio_filter* f, int ldy, int dimp, int j0, int bc, doub
     return EQVIO_OK;
 }
 
+// Block sweep with look-ahead (blockchol.cuh): stream A = f->stream carries the build and the chain of diagonal steps (programmatic
+// edges between them), stream B = f->stream3 the panel / trailing kernels; diag(k) -> panel(k) -> trail(k) -> diag(k+2).
+// While the per-kernel profile runs everything is issued on f->stream (event brackets around each class).
+int enqueue_block_sweep(eqvio_filter* f, int nm, int dimp, double r2, const int* guard) {
+    const int m = 2 * nm;
+    const int nT = cdiv(m, BC_T);
+    const int ldy = (dimp + BC_T - 1) / BC_T * BC_T, TW = ldy / BC_T;
+    const int ldz = nT * BC_T + ldy;
+    const bool serial = f->profiling;
+    cudaStream_t sA = f->stream, sB = serial ? f->stream : f->stream3;
+    while ((int)f->bcEv.size() < 2 * nT + 1) {
+        cudaEvent_t e;
+        CUDA_TRY(f, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        f->bcEv.push_back(e);
+    }
+    launch_pdl(f, bc_build_kernel, dim3(nT * (nT + 1) / 2 + TW * nT), dim3(256), (size_t)0, sA, (const double*)f->Sig[f->cur], f->ld, dimp,
+               (const int*)f->d_lmOf, (const double*)f->d_Cblk, (const double*)f->d_ytilde, nm, r2, f->d_bcZ, ldz, nT, TW, guard, TL_SLOT(f));
+    LAUNCH_CHECK(f, "bc_build_kernel");
+    if (!serial) {
+        CUDA_TRY(f, cudaEventRecord(f->bcEv[2 * nT], sA));
+        CUDA_TRY(f, cudaStreamWaitEvent(sB, f->bcEv[2 * nT], 0));
+    }
+    for (int k = 0; k < nT; ++k) {
+        if (!serial && k >= 2) CUDA_TRY(f, cudaStreamWaitEvent(sA, f->bcEv[2 * (k - 2) + 1], 0));  // trail(k-2)
+        int pk = prof_begin(f, PROF_PANEL);
+        launch_pdl(f, bc_diag_kernel, dim3(1), dim3(BC_DIAG_THREADS), (size_t)BC_DIAG_SMEM, sA, (const double*)f->d_bcZ, ldz, k, f->d_bcMt, f->d_status,
+                   guard, TL_SLOT(f));
+        prof_end(f, pk);
+        LAUNCH_CHECK(f, "bc_diag_kernel");
+        if (!serial) {
+            CUDA_TRY(f, cudaEventRecord(f->bcEv[2 * k], sA));
+            CUDA_TRY(f, cudaStreamWaitEvent(sB, f->bcEv[2 * k], 0));
+        }
+        const int below = nT + TW - k - 1;  // row tiles under the diagonal block (S, then W)
+        int tk = prof_begin(f, PROF_TRAIL);
+        bc_panel_kernel<<<2 * below, 128, BC_PANEL_SMEM, sB>>>(f->d_bcZ, ldz, k, f->d_bcMt, f->d_bcZp, guard, TL_SLOT(f));
+        prof_end(f, tk);
+        LAUNCH_CHECK(f, "bc_panel_kernel");
+        const int q = nT - k - 1;
+        const int tiles = (q > 0 ? q * (q + 1) / 2 - 1 : 0) + TW * q + TW * (TW + 1) / 2;
+        int sk = prof_begin(f, PROF_SYRK);
+        bc_trail_kernel<<<2 * tiles, DD_THREADS, DD_SMEM, sB>>>(f->d_bcZ, ldz, f->Sig[f->cur], f->ld, f->d_bcZp, f->d_Gamma, guard, k, nT, TW, dimp,
+                                                               k == nT - 1 ? 1 : 0, TL_SLOT(f));
+        prof_end(f, sk);
+        LAUNCH_CHECK(f, "bc_trail_kernel");
+        if (!serial) CUDA_TRY(f, cudaEventRecord(f->bcEv[2 * k + 1], sB));
+    }
+    if (!serial) CUDA_TRY(f, cudaStreamWaitEvent(sA, f->bcEv[2 * (nT - 1) + 1], 0));
+    return EQVIO_OK;
+}
+
 // performVisionUpdate (VIO_eqf.cpp:105-135) in the symmetric form, for the nm measured landmarks whose pixels are
 // in d_y and state indices in d_lmOf.  Every kernel returns at once when *guard != 0.
 // fuseGate: the gate launch carries the measurement rows (gate_meas_kernel); fuseEst: the lift also emits the state estimate.
@@ -1390,10 +1456,13 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
     const int Mz = m + dimp + 1;
     const int ldz = (Mz + 7) & ~7;
     double* Z = f->d_Z;
-    if (f->corrMode != 0) CUDA_TRY(f, cudaMemsetAsync(f->d_status, 0, (1 + (size_t)Nn) * sizeof(int), f->stream));
+    // the block sweep serves up to BC_MAX_ROWS measurement rows; larger updates (where the trailing work on W would dominate)
+    // take the sequential chunks
+    const bool blockSweep = f->corrMode == 2 && m <= BC_MAX_ROWS && !f->downdateTC;
+    if (f->corrMode == 1) CUDA_TRY(f, cudaMemsetAsync(f->d_status, 0, (1 + (size_t)Nn) * sizeof(int), f->stream));
     const double r2 = s.measurementNoise * s.measurementNoise;
     const double* gammaFinal = f->d_Gamma;
-    if (f->corrMode == 0) {
+    if (f->corrMode != 1) {
         // sequential chunks: see chunk_factor_kernel
         const int ldy = (dimp + 63) & ~63;
         const int T = ldy / DD_T;
@@ -1417,6 +1486,10 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                                                           f->d_status, 1 + Nn, gin, dimp, (int*)nullptr, 0, TL_SLOT(f));
         LAUNCH_CHECK(f, "meas_kernel");
         }
+        if (blockSweep) {
+            const int rcb = enqueue_block_sweep(f, nm, dimp, r2, guard);
+            if (rcb != EQVIO_OK) return rcb;
+        } else {
         const int bcMax = std::max(1, std::min(f->chunkLm, CH_R / 2));
         const int nchunks = cdiv(nm, bcMax);
         const bool look = (f->lookahead == 1 || (f->lookahead == 2 && T >= 24)) && nchunks > 1 && !f->profiling && !f->downdateTC;
@@ -1524,6 +1597,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
             }
         }
         gammaFinal = gin;
+        }
     } else {
     meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
                                                       s.useEquivariantOutput ? 1 : 0, f->d_Cblk, Z, ldz, m + dimp, guard, f->d_yIdx,
@@ -1711,6 +1785,9 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(bc_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_DIAG_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(bc_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_PANEL_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(bc_trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ChunkSmem) > (size_t)CH_SMEM_STAGED ? sizeof(ChunkSmem) : (size_t)CH_SMEM_STAGED));
     if (e != cudaSuccess) {
         g_createError = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
@@ -1720,6 +1797,10 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
     f->st = *s;
     f->device = device;
     f->cap = capacity;
+    if (const char* cm = std::getenv("EQVIO_B200_CORRECTION")) {  // A/B runs of whole test / bench commands
+        const int v = std::atoi(cm);
+        if (v >= 0 && v <= 2) f->corrMode = v;
+    }
     if (cudaDeviceGetAttribute(&f->smCount, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || f->smCount <= 0) f->smCount = 148;
     if (stream) {
         f->stream = static_cast<cudaStream_t>(stream);
@@ -1940,6 +2021,10 @@ void eqvio_destroy(eqvio_filter* f) {
     cudaFree(f->d_uv);
     cudaFree(f->d_Z);
     cudaFree(f->d_Lout);
+    cudaFree(f->d_bcZ);
+    cudaFree(f->d_bcZp);
+    cudaFree(f->d_bcMt);
+    for (auto& e : f->bcEv) cudaEventDestroy(e);
     cudaFree(f->d_Y2);
     cudaFree(f->d_Ysplit);
     for (auto& e : f->chunkEv) cudaEventDestroy(e);
@@ -2515,8 +2600,9 @@ int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
     if (!f) return EQVIO_ERR_INVALID_ARG;
     switch (key) {
         case EQVIO_TUNE_CORRECTION:
-            if (value != 0 && value != 1) return EQVIO_ERR_INVALID_ARG;
+            if (value < 0 || value > 2) return EQVIO_ERR_INVALID_ARG;
             f->corrMode = value;
+            clear_graphs(f);
             return EQVIO_OK;
         case EQVIO_TUNE_DOWNDATE:
             if (value != 0 && value != 1) return EQVIO_ERR_INVALID_ARG;
@@ -2599,6 +2685,10 @@ int eqvio_debug_chunk_timing(long long out[16]) {
 }
 int eqvio_debug_chunk_fine(long long out[128]) {
     return cudaMemcpyFromSymbol(out, g_chunk_fine, sizeof(long long) * 128) == cudaSuccess ? 0 : -2;
+}
+int eqvio_debug_bc_timing(long long out[16], int warps[BC_S_WARPS * 64]) {
+    if (cudaMemcpyFromSymbol(out, g_bc_t, sizeof(long long) * 16) != cudaSuccess) return -2;
+    return cudaMemcpyFromSymbol(warps, g_bc_warp, sizeof(int) * BC_S_WARPS * 64) == cudaSuccess ? 0 : -2;
 }
 #endif
 

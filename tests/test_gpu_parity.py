@@ -62,10 +62,12 @@ def test_sequence_matches_oracle(N, coord):
     _check(run_gpu(stream), run_oracle(stream))
 
 
-@pytest.mark.parametrize("tuning", [dict(correction=1), dict(correction=0, chunkLandmarks=5), dict(correction=0, chunkLandmarks=16),
+@pytest.mark.parametrize("tuning", [dict(correction=1), dict(correction=2), dict(correction=2, graph=0), dict(correction=2, graph=0, speculate=0),
+                                    dict(correction=0, chunkLandmarks=5), dict(correction=0, chunkLandmarks=16),
                                     dict(correction=0, chunkLandmarks=1), dict(correction=0, chunkLandmarks=7)])
 def test_correction_evaluation_orders_agree(tuning):
-    """Batch Cholesky sweep vs sequential chunks of any size: same result to rounding, both match the oracle."""
+    """Batch Cholesky sweep, block sweep with look-ahead (blockchol.cuh) and sequential chunks of any size: same result to
+    rounding, all match the oracle.  N = 40: one full 64-row block and a ragged one of 16 rows."""
     stream = make_stream(N=40, frames=6, coord=1)
     ref = run_oracle(stream)
     _check(run_gpu(stream, tuning=tuning), ref)
