@@ -28,8 +28,9 @@ constexpr int BC_MAX_ROWS = 768;         // largest m served by this form (beyon
 __global__ void __launch_bounds__(256)
     bc_build_kernel(const double* __restrict__ Sig, int ld, int dimp, const int* __restrict__ lmOf, const double* __restrict__ Cblk,
                     const double* __restrict__ ytilde, int nm, double r2, double* __restrict__ Z, int ldz, int nT, int TW,
-                    const int* __restrict__ guard, int tl) {
+                    int* __restrict__ trailCnt, const int* __restrict__ guard, int tl) {
     pdl_wait();
+    if (blockIdx.x == 0 && threadIdx.x < nT) trailCnt[threadIdx.x] = 0;  // completion counters of the trailing steps (see bc_diag_kernel)
     if (*guard) return;
     TL_MARK(tl, 0);
     __shared__ double sC[32][6];
@@ -143,22 +144,28 @@ constexpr int BC_X_THREADS = 64;                   // 4 diagonal 16 x 16 blocks 
 constexpr int BC_DIAG_THREADS = 512;               // 16 warps for the DMMA prologue; warps 0-8 = S group, 9-10 = X group
 constexpr int BC_PLD = 18;                         // doubles per published tile: [r][j] and 2 of padding (conflict-free 16-byte reads)
 // What a diagonal step hands to its consumers (the next diagonal step, the panel kernel), per block k, two 64 x YB_LD arrays:
-//   LT[c][r] = L_kk[r][c]   (strictly lower 4x4 tiles; only the 16 x 16 blocks BELOW the diagonal blocks are read)
-//   XT[j][c] = X_b[c][j]    for j, c in the same 16-block b: X_b = (b-th diagonal 16 x 16 block of L_kk)^-1
+//   LT = L_kk transposed, the six 16 x 16 blocks below the diagonal blocks;
+//   XT = X_b transposed, X_b = (b-th diagonal 16 x 16 block of L_kk)^-1, b = 0..3.
 // P = T L_kk^-T is then a 4-stage block substitution on the FP64 tensor pipe:  P_b = (T_b - sum_{j<b} P_j L_bj^T) X_b^T.
 // (An explicit 64 x 64 inverse riding along the whole factorization was measured first: its 256 threads made the loop fp64-pipe
 // bound, ~1200 clocks per block column instead of ~650.)
-constexpr size_t BC_LX = 2 * YB_TILE;
+// Stored compactly: ten 16 x 16 blocks of 16 x BC_XLD doubles -- LT block (b, j), j < b, at index b (b - 1) / 2 + j as [k][n] =
+// L[16 b + n][16 j + k]; XT block b at index 6 + b as [k][n] = X_b[n][k]  (25.6 KB: one TMA bulk copy for every consumer).
+constexpr int BC_XLD = 20;                          // row stride of a block: 20 mod 16 = 4 -> conflict-free fragment reads
+constexpr int BC_XBLK = 16 * BC_XLD;
+constexpr size_t BC_LX = 10 * BC_XBLK;
+__host__ __device__ __forceinline__ int bc_lt_block(int b, int j) { return b * (b - 1) / 2 + j; }
 
 struct BcDiagSmem {
     double A[BC_T][YB_LD];            // T_{k,k-1} as A[j][r]; stage by stage replaced by P_{k,k-1} as A[c][r]
-    double B[BC_T][YB_LD];            // LT of block k-1; after the substitution the updated diagonal block as B[c][r]
-    double X[BC_T][YB_LD];            // XT of block k-1
+    double B[BC_T][YB_LD];            // the updated diagonal block as B[c][r]
+    double LX[10][16][BC_XLD];        // LT | XT of block k-1
     double Q[16][YB_LD];              // one stage's 64 x 16 block between its two products
     double Lp[CH_NT][CH_NT][BC_PLD];  // Lp[J][TI][4 r + j]: tile (TI, J) once block column J is finished (unscaled columns); TI = J: the diagonal tile
     double Dc[CH_NT][CH_T];           // reciprocal pivots of block column J
     double Inv[BC_T];
     uint64_t colBar[CH_NT];           // one mbarrier per block column: "its panels are published" (S group -> X group)
+    uint64_t lxBar;                   // arrival of the LT | XT bulk copy
 };
 constexpr int BC_DIAG_SMEM = (int)sizeof(BcDiagSmem);
 
@@ -178,7 +185,7 @@ __device__ __forceinline__ int bc_diag_tile(int J) { return CH_NT * J - J * (J -
 // Z: augmented matrix (ldz), kblk: block column.  LxAll: per block the LT | XT pair described above.
 __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
     bc_diag_kernel(const double* __restrict__ Z, int ldz, int kblk, double* __restrict__ LxAll, int* __restrict__ status,
-                   const int* __restrict__ guard, int tl) {
+                   const int* trailCnt, int waitCnt, const int* __restrict__ guard, int tl) {
     extern __shared__ __align__(128) unsigned char bc_smem_raw[];
     BcDiagSmem& sm = *reinterpret_cast<BcDiagSmem*>(bc_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -187,11 +194,46 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
     BC_STAMP(0);
     if (tid == 0) {
         for (int J = 0; J < CH_NT; ++J) mbar_init(&sm.colBar[J], 1);
+        mbar_init(&sm.lxBar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // Everything this kernel reads comes from earlier kernels: wait first.  (Reading T_* ahead of the wait would need the edge from
-    // trail(k-2) to be a full dependency; with the programmatic-serialization attribute set, a captured node's kernel
-    // predecessors all become programmatic edges, and trail kernels release their dependents at their start.)
+    // Two dependencies, taken one at a time:
+    //  (1) T_{k,k-1}, T_kk are current once trail(k-2) has finished.  That kernel runs on the other stream; an event edge into this
+    //      chain costs ~3 us per step inside a replayed graph, so the trailing CTAs count themselves off in trailCnt[k-2] instead
+    //      (release) and thread 0 polls it (acquire; bounded).  trail(k-2) never waits for this kernel, and everything it waits for
+    //      completed before this grid could start (its stream predecessor, diag(k-1), was past its own dependency wait).
+    //  (2) LT | XT of block k-1 come from diag(k-1): griddepcontrol.wait.  The T tiles are fetched ahead of it.
+    if (waitCnt > 0) {
+        if (tid == 0) {
+            int spins = 0, seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(trailCnt + (kblk - 2)) : "memory");
+            } while (seen < waitCnt && ++spins < (1 << 24));
+            if (seen < waitCnt) atomicOr(status, 8);
+        }
+        __syncthreads();
+    }
+    double2 tpre[4];
+    double acc2[3][2];
+    if (kblk > 0) {
+        const double* Tp = Z + (size_t)(k0 - BC_T) * ldz + k0;  // T_{k,k-1}: 2048 16-byte words, four per thread
+        const double* Td = Z + (size_t)k0 * ldz + k0;           // T_{k,k}: the 36 lower 8x8 fragments go round-robin over the 16 warps
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = tid + BC_DIAG_THREADS * u;
+            tpre[u] = *reinterpret_cast<const double2*>(Tp + (size_t)(q >> 5) * ldz + (q & 31) * 2);
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int f = warp + 16 * u;
+            if (f < 36) {
+                int fi, fj;
+                tri_decode(f, fi, fj);
+                acc2[u][0] = -Td[(size_t)(8 * fj + 2 * t4) * ldz + 8 * fi + g];
+                acc2[u][1] = -Td[(size_t)(8 * fj + 2 * t4 + 1) * ldz + 8 * fi + g];
+            }
+        }
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (*guard) return;
@@ -210,51 +252,57 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
 
     if (kblk > 0) {
         // ---- look-ahead products on the FP64 tensor pipe (16 warps):  P = T_{k,k-1} L^-T (block substitution),  D = T_kk - P P^T  ----
-        const double* Tp = Z + (size_t)(k0 - BC_T) * ldz + k0;  // T_{k,k-1}
-        const double* Td = Z + (size_t)k0 * ldz + k0;           // T_{k,k}
-        const double2* Lxp = reinterpret_cast<const double2*>(LxAll + (size_t)(kblk - 1) * BC_LX);
-        double2* Bp = reinterpret_cast<double2*>(&sm.B[0][0]);  // B and X are adjacent: LT | XT in one run
-        for (int q = tid; q < BC_T * (BC_T / 2); q += BC_DIAG_THREADS) {
-            const int j = q >> 5, r = (q & 31) * 2;
-            const double2 v = *reinterpret_cast<const double2*>(Tp + (size_t)j * ldz + r);
-            sm.A[j][r] = v.x;
-            sm.A[j][r + 1] = v.y;
+        if (tid == 0) {
+            mbar_expect_tx(&sm.lxBar, (uint32_t)(BC_LX * 8));
+            bulk_g2s(&sm.LX[0][0][0], LxAll + (size_t)(kblk - 1) * BC_LX, (uint32_t)(BC_LX * 8), &sm.lxBar);
         }
-        for (int q = tid; q < (int)(BC_LX / 2); q += BC_DIAG_THREADS) Bp[q] = Lxp[q];
-        // second product: the 36 lower 8x8 fragments of D go round-robin over the 16 warps (9 per SM sub-partition)
-        double acc2[3][2];
-        if (warp < 16) {
 #pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                const int f = warp + 16 * u;
-                if (f < 36) {
-                    int fi, fj;
-                    tri_decode(f, fi, fj);
-                    acc2[u][0] = -Td[(size_t)(8 * fj + 2 * t4) * ldz + 8 * fi + g];
-                    acc2[u][1] = -Td[(size_t)(8 * fj + 2 * t4 + 1) * ldz + 8 * fi + g];
+        for (int u = 0; u < 4; ++u) {
+            const int q = tid + BC_DIAG_THREADS * u;
+            *reinterpret_cast<double2*>(&sm.A[q >> 5][(q & 31) * 2]) = tpre[u];
+        }
+        __syncthreads();
+        mbar_wait(&sm.lxBar, 0);
+        BC_STAMP(2);
+        // four stages; warp fi < 8 owns rows 8 fi .. 8 fi + 7 of P through all of them (both 8-column fragments of a stage), so the
+        // stages only need warp-level synchronisation
+        if (warp < 8) {
+            const int fi = warp;
+#pragma unroll 1
+            for (int b = 0; b < 4; ++b) {
+                double q[2][2];
+#pragma unroll
+                for (int fn = 0; fn < 2; ++fn) {
+                    q[fn][0] = -sm.A[16 * b + 8 * fn + 2 * t4][8 * fi + g];
+                    q[fn][1] = -sm.A[16 * b + 8 * fn + 2 * t4 + 1][8 * fi + g];
                 }
+                for (int k4 = 0; k4 < 16 * b; k4 += 4) {
+                    const double af = sm.A[k4 + t4][8 * fi + g];
+#pragma unroll
+                    for (int fn = 0; fn < 2; ++fn) dmma884(q[fn][0], q[fn][1], af, sm.LX[bc_lt_block(b, k4 >> 4)][(k4 & 15) + t4][8 * fn + g]);
+                }
+#pragma unroll
+                for (int fn = 0; fn < 2; ++fn) {
+                    sm.Q[8 * fn + 2 * t4][8 * fi + g] = -q[fn][0];
+                    sm.Q[8 * fn + 2 * t4 + 1][8 * fi + g] = -q[fn][1];
+                }
+                __syncwarp();
+                double p[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+                for (int k4 = 0; k4 < 16; k4 += 4) {
+                    const double af = sm.Q[k4 + t4][8 * fi + g];
+                    if (k4 < 8) dmma884(p[0][0], p[0][1], af, sm.LX[6 + b][k4 + t4][g]);
+                    dmma884(p[1][0], p[1][1], af, sm.LX[6 + b][k4 + t4][8 + g]);
+                }
+#pragma unroll
+                for (int fn = 0; fn < 2; ++fn) {  // P_b takes the place of T's block column b
+                    sm.A[16 * b + 8 * fn + 2 * t4][8 * fi + g] = p[fn][0];
+                    sm.A[16 * b + 8 * fn + 2 * t4 + 1][8 * fi + g] = p[fn][1];
+                }
+                __syncwarp();
             }
         }
         __syncthreads();
-        BC_STAMP(2);
-        // four stages, one 8 x 8 fragment of the stage's 64 x 16 block per warp (row fragment fi, column fragment fn)
-        {
-            const int fi = warp & 7, fn = warp >> 3;
-#pragma unroll 1
-            for (int b = 0; b < 4; ++b) {
-                const int c0 = 16 * b + 8 * fn;
-                double q0 = -sm.A[c0 + 2 * t4][8 * fi + g], q1 = -sm.A[c0 + 2 * t4 + 1][8 * fi + g];
-                for (int k4 = 0; k4 < 16 * b; k4 += 4) dmma884(q0, q1, sm.A[k4 + t4][8 * fi + g], sm.B[k4 + t4][c0 + g]);
-                sm.Q[8 * fn + 2 * t4][8 * fi + g] = -q0;
-                sm.Q[8 * fn + 2 * t4 + 1][8 * fi + g] = -q1;
-                __syncthreads();
-                double p0 = 0.0, p1 = 0.0;
-                for (int k4 = 0; k4 < 8 * (fn + 1); k4 += 4) dmma884(p0, p1, sm.Q[k4 + t4][8 * fi + g], sm.X[16 * b + k4 + t4][c0 + g]);
-                sm.A[c0 + 2 * t4][8 * fi + g] = p0;  // P_b takes the place of T's block column b
-                sm.A[c0 + 2 * t4 + 1][8 * fi + g] = p1;
-                __syncthreads();
-            }
-        }
         BC_STAMP(3);
         if (warp < 16) {
             int fi[3], fj[3];
@@ -388,19 +436,23 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
                     li[r][2] = y.x * c23.x;
                     li[r][3] = y.y * c23.y;
                 }
+                // j outermost: eight independent accumulators per level, the four levels pipeline (cc outermost leaves two
+                // dependent chains of four per load pair and ~2x the latency)
+                double pk[CH_T][CH_T];
 #pragma unroll
                 for (int cc = 0; cc < CH_T; ++cc) {
                     const double2 x = pp[2 * cc], y = pp[2 * cc + 1];
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        double acc = a[r][cc];
-                        acc -= li[r][0] * x.x;
-                        acc -= li[r][1] * x.y;
-                        acc -= li[r][2] * y.x;
-                        acc -= li[r][3] * y.y;
-                        a[r][cc] = acc;
-                    }
+                    pk[cc][0] = x.x;
+                    pk[cc][1] = x.y;
+                    pk[cc][2] = y.x;
+                    pk[cc][3] = y.y;
                 }
+#pragma unroll
+                for (int j = 0; j < CH_T; ++j)
+#pragma unroll
+                    for (int cc = 0; cc < CH_T; ++cc)
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) a[r][cc] = fma(-li[r][j], pk[cc][j], a[r][cc]);
             }
             // look-ahead: the next diagonal tile is eliminated as soon as its own update is in, while the other warps are still in
             // theirs -- the next iteration goes straight to its first barrier
@@ -425,12 +477,12 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
         BC_STAMP(5);
         __syncthreads();  // Inv published
         // LT: the off-diagonal tiles are still in their owners' registers (unscaled columns: L_ij = v_ij / L_jj)
-        if (owner && TI > TK) {
-            double* Lt = LxAll + (size_t)kblk * BC_LX;
+        if (owner && (TI >> 2) > (TK >> 2)) {
+            double* Lt = LxAll + (size_t)kblk * BC_LX + (size_t)bc_lt_block(TI >> 2, TK >> 2) * BC_XBLK;
 #pragma unroll
             for (int j = 0; j < CH_T; ++j) {
                 const double sc = sm.Inv[CH_T * TK + j];
-                *reinterpret_cast<double2*>(Lt + (size_t)(CH_T * TK + j) * YB_LD + CH_T * TI + 2 * h) = make_double2(a[0][j] * sc, a[1][j] * sc);
+                *reinterpret_cast<double2*>(Lt + (CH_T * (TK & 3) + j) * BC_XLD + CH_T * (TI & 3) + 2 * h) = make_double2(a[0][j] * sc, a[1][j] * sc);
             }
         }
     } else if (tid < BC_S_THREADS + BC_X_THREADS) {
@@ -493,7 +545,7 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
             }
         }
         __syncthreads();  // Inv published
-        double* Xt = LxAll + (size_t)kblk * BC_LX + YB_TILE;
+        double* Xt = LxAll + (size_t)kblk * BC_LX + (size_t)(6 + blk) * BC_XBLK;
 #pragma unroll
         for (int r = 0; r < CH_T; ++r) {
             double2 lo, hi;
@@ -501,7 +553,7 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
             lo.y = b[r][1] * sm.Inv[CH_T * TK + 1];
             hi.x = b[r][2] * sm.Inv[CH_T * TK + 2];
             hi.y = b[r][3] * sm.Inv[CH_T * TK + 3];
-            double* p = Xt + (size_t)(CH_T * TI + r) * YB_LD + CH_T * TK;
+            double* p = Xt + (CH_T * i + r) * BC_XLD + CH_T * tk;
             *reinterpret_cast<double2*>(p) = lo;
             *reinterpret_cast<double2*>(p + 2) = hi;
         }
@@ -525,8 +577,7 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
 // ------------------------------------------------------------------------------------------------
 constexpr int BC_PA_LD = 36;  // 32 rows of a half tile (+4: conflict-free fragment reads)
 struct BcPanelSmem {
-    double L[BC_T][YB_LD];      // LT
-    double X[BC_T][YB_LD];      // XT
+    double LX[10][16][BC_XLD];  // LT | XT of block k
     double A[BC_T][BC_PA_LD];   // T as A[j][r]; stage by stage replaced by P as A[c][r]
     double Q[16][BC_PA_LD];
     uint64_t bar;
@@ -548,7 +599,7 @@ __global__ void __launch_bounds__(128)
         mbar_init(&sm.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(&sm.bar, (uint32_t)(BC_LX * 8));
-        bulk_g2s(&sm.L[0][0], LxAll + (size_t)kblk * BC_LX, (uint32_t)(BC_LX * 8), &sm.bar);  // L and X are adjacent: LT | XT in one copy
+        bulk_g2s(&sm.LX[0][0][0], LxAll + (size_t)kblk * BC_LX, (uint32_t)(BC_LX * 8), &sm.bar);
     }
     const double* Tp = Z + (size_t)(kblk * BC_T) * ldz + (size_t)t * BC_T + 32 * half;
     for (int q = tid; q < BC_T * 16; q += 128) {
@@ -572,7 +623,7 @@ __global__ void __launch_bounds__(128)
         for (int k4 = 0; k4 < 16 * b; k4 += 4) {
             const double af = sm.A[k4 + t4][8 * fi + g];
 #pragma unroll
-            for (int fn = 0; fn < 2; ++fn) dmma884(q[fn][0], q[fn][1], af, sm.L[k4 + t4][16 * b + 8 * fn + g]);
+            for (int fn = 0; fn < 2; ++fn) dmma884(q[fn][0], q[fn][1], af, sm.LX[bc_lt_block(b, k4 >> 4)][(k4 & 15) + t4][8 * fn + g]);
         }
 #pragma unroll
         for (int fn = 0; fn < 2; ++fn) {
@@ -584,8 +635,8 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
         for (int k4 = 0; k4 < 16; k4 += 4) {
             const double af = sm.Q[k4 + t4][8 * fi + g];
-            if (k4 < 8) dmma884(p[0][0], p[0][1], af, sm.X[16 * b + k4 + t4][16 * b + g]);
-            dmma884(p[1][0], p[1][1], af, sm.X[16 * b + k4 + t4][16 * b + 8 + g]);
+            if (k4 < 8) dmma884(p[0][0], p[0][1], af, sm.LX[6 + b][k4 + t4][g]);
+            dmma884(p[1][0], p[1][1], af, sm.LX[6 + b][k4 + t4][8 + g]);
         }
 #pragma unroll
         for (int fn = 0; fn < 2; ++fn) {
@@ -609,39 +660,91 @@ __global__ void __launch_bounds__(128)
 //   W tiles  (w, j > k)                                                                         in Z
 //   Sigma tiles (a >= b), mirrored on the last step; column BC_YROW of the product is -dGamma, row / column BC_YROW of Sigma stay zero
 // ------------------------------------------------------------------------------------------------
+enum { BC_PART_ALL = 0, BC_PART_NEXT = 1, BC_PART_REST = 2 };  // which tiles a launch covers (the split lets the next panel start early)
+constexpr int BC_TRAIL_URGENT = 4;
+__host__ __device__ __forceinline__ int bc_trail_tiles(int part, int q, int TW) {
+    const int all = (q > 0 ? q * (q + 1) / 2 - 1 : 0) + TW * q + TW * (TW + 1) / 2;
+    const int next = q >= 1 ? (q - 1) + (q >= 2 ? 1 : 0) + TW : 0;
+    return part == BC_PART_ALL ? all : part == BC_PART_NEXT ? next : all - next;
+}
 __global__ void __launch_bounds__(DD_THREADS, 3)
     bc_trail_kernel(double* Z, int ldz, double* Sig, int ld, const double* __restrict__ Zp, double* Gamma, const int* __restrict__ guard,
-                    int kblk, int nT, int TW, int dimp, int mirrorAll, int tl) {
+                    int kblk, int nT, int TW, int dimp, int mirrorAll, int part, int* __restrict__ trailCnt, int tl) {
     pdl_wait();
-    if (*guard) return;
-    TL_MARK(tl, 0);
     const int bid = (int)(blockIdx.x >> 1), half = (int)(blockIdx.x & 1);
-    const int q = nT - kblk - 1;
-    const int nS = q > 0 ? q * (q + 1) / 2 - 1 : 0;
-    int ta, tb;       // panel tiles in Zp
+    const int q = nT - kblk - 1;  // block columns to the right of this one
+    // the two tiles diag(k+2) reads, T(k+2, k+1) and T(k+2, k+2): their four CTAs count themselves off (BC_TRAIL_URGENT of them)
+    const bool urgent = part != BC_PART_REST && q >= 2 && (part == BC_PART_ALL ? bid < 2 : (bid == 0 || bid == q - 1));
+    if (*guard) {
+        if (urgent && threadIdx.x == 0) atomicAdd(trailCnt + kblk, 1);  // diag(k+2) counts them whatever they did
+        return;
+    }
+    TL_MARK(tl, 0);
+    int ta, tb;  // panel tiles in Zp
     double* C;
     int ldc;
     bool isSig = false;
-    if (bid < nS) {
-        int li, lj;
-        tri_decode(bid + 1, li, lj);
+    // local tile (li, lj) of the trailing S block, li >= lj, (0, 0) excluded; W tile (w, lj); Sigma tile (sa, sb)
+    int kind, li = 0, lj = 0;  // 0: S, 1: W, 2: Sigma
+    if (part == BC_PART_ALL) {
+        const int nS = q > 0 ? q * (q + 1) / 2 - 1 : 0;
+        if (bid < nS) {
+            kind = 0;
+            tri_decode(bid + 1, li, lj);
+        } else if (bid < nS + TW * q) {
+            kind = 1;
+            li = (bid - nS) / q;
+            lj = (bid - nS) % q;
+        } else {
+            kind = 2;
+            tri_decode(bid - nS - TW * q, li, lj);
+        }
+    } else if (part == BC_PART_NEXT) {
+        // what the next block column needs: its own tiles (lj = 0) and the diagonal tile after it
+        const int nSA = (q - 1) + (q >= 2 ? 1 : 0);  // (q - 1) tiles (li, 0), li >= 1, plus (1, 1) when it exists
+        if (bid < q - 1) {
+            kind = 0;
+            li = bid + 1;
+            lj = 0;
+        } else if (q >= 2 && bid == q - 1) {
+            kind = 0;
+            li = lj = 1;
+        } else {
+            kind = 1;
+            li = bid - nSA;
+            lj = 0;
+        }
+    } else {
+        const int nSB = q >= 2 ? (q - 1) * q / 2 - 1 : 0;
+        const int nWB = q >= 2 ? TW * (q - 1) : 0;
+        if (bid < nSB) {
+            kind = 0;
+            tri_decode(bid + 1, li, lj);
+            ++li;
+            ++lj;
+        } else if (bid < nSB + nWB) {
+            kind = 1;
+            li = (bid - nSB) / (q - 1);
+            lj = 1 + (bid - nSB) % (q - 1);
+        } else {
+            kind = 2;
+            tri_decode(bid - nSB - nWB, li, lj);
+        }
+    }
+    if (kind == 0) {
         ta = kblk + 1 + li;
         tb = kblk + 1 + lj;
         C = Z + (size_t)tb * BC_T * ldz + (size_t)ta * BC_T;
         ldc = ldz;
-    } else if (bid < nS + TW * q) {
-        const int x = bid - nS;
-        const int w = x / q, lj = x % q;
-        ta = nT + w;
+    } else if (kind == 1) {
+        ta = nT + li;
         tb = kblk + 1 + lj;
         C = Z + (size_t)tb * BC_T * ldz + (size_t)ta * BC_T;
         ldc = ldz;
     } else {
-        int sa, sb;
-        tri_decode(bid - nS - TW * q, sa, sb);
-        ta = nT + sa;
-        tb = nT + sb;
-        C = Sig + (size_t)sb * BC_T * ld + (size_t)sa * BC_T;
+        ta = nT + li;
+        tb = nT + lj;
+        C = Sig + (size_t)lj * BC_T * ld + (size_t)li * BC_T;
         ldc = ld;
         isSig = true;
     }
@@ -718,6 +821,13 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
                     *reinterpret_cast<double2*>(Sig + (size_t)R * ld + Cc) = tt;
                 }
             }
+    }
+    if (urgent) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(trailCnt + kblk, 1);
+        }
     }
     TL_MARK(tl, 1);
 }

@@ -74,6 +74,7 @@ struct eqvio_filter {
     double* d_xi0s = nullptr;
     double* d_Xs[2] = {nullptr, nullptr};  // X sensor part, ping-pong across the observer integration
     int xcur = 0;
+    cudaStream_t stream4 = nullptr;  // block sweep: panel / next-column trailing tiles
     cudaStream_t stream3 = nullptr;  // low priority: deferred downdate tiles of the look-ahead correction
     cudaStream_t stream2 = nullptr;  // observer chain of the propagation runs beside the Riccati chain
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
@@ -118,7 +119,8 @@ struct eqvio_filter {
     double *d_rows = nullptr, *d_uv = nullptr, *d_Z = nullptr, *d_Lout = nullptr;
     size_t zElems = 0;
     double *d_Gamma2 = nullptr, *d_ytilde = nullptr;
-    int corrMode = 0;    // 0: sequential chunks, 1: batch Cholesky sweep over Z, 2: block sweep with look-ahead (blockchol.cuh; m <= BC_MAX_ROWS)
+    int corrMode = 2;    // 0: sequential chunks, 1: batch Cholesky sweep over Z, 2 (default): block sweep with look-ahead (blockchol.cuh) up to BC_MAX_ROWS measurement rows, sequential chunks beyond
+    int* d_bcCnt = nullptr;  // mode 2: per trailing step, the number of its CTAs that have finished
     double *d_bcZ = nullptr, *d_bcZp = nullptr, *d_bcMt = nullptr;  // mode 2: augmented matrix, panel tiles of the current block column, LT | XT per block (blockchol.cuh)
     std::vector<cudaEvent_t> bcEv;
     int speculate = 1;   // launch the correction before the gate results reach the host (redone on a gate hit)
@@ -488,6 +490,7 @@ int alloc_device(eqvio_filter* f) {
         f->prGreatest = prGreatest;
         CUDA_TRY(f, cudaStreamCreateWithPriority(&f->stream2, cudaStreamNonBlocking, prGreatest));
         CUDA_TRY(f, cudaStreamCreateWithPriority(&f->stream3, cudaStreamNonBlocking, prLeast));
+        CUDA_TRY(f, cudaStreamCreateWithPriority(&f->stream4, cudaStreamNonBlocking, prGreatest));
     }
     CUDA_TRY(f, cudaEventCreateWithFlags(&f->evFork, cudaEventDisableTiming));
     CUDA_TRY(f, cudaEventCreateWithFlags(&f->evJoin, cudaEventDisableTiming));
@@ -510,12 +513,14 @@ int alloc_device(eqvio_filter* f) {
         // block sweep (mode 2): Z = [S; W^T] for at most BC_MAX_ROWS measurement rows, tile-blocked panels, one inverse per block
         const size_t mp = (std::min<size_t>(mMax, BC_MAX_ROWS) + BC_T - 1) / BC_T * BC_T;
         const size_t ldy = ((size_t)dimpMax + BC_T - 1) / BC_T * BC_T;
-        const size_t zb = (mp + ldy) * mp, zp = (mp / BC_T + ldy / BC_T) * YB_TILE, mt = (mp / BC_T) * BC_LX;
+        const size_t zb = (mp + ldy) * mp, zp = 2 * (mp / BC_T + ldy / BC_T) * YB_TILE, mt = (mp / BC_T) * BC_LX;
         CUDA_TRY(f, cudaMalloc(&f->d_bcZ, zb * sizeof(double)));
         CUDA_TRY(f, cudaMalloc(&f->d_bcZp, zp * sizeof(double)));
         CUDA_TRY(f, cudaMalloc(&f->d_bcMt, mt * sizeof(double)));
         CUDA_TRY(f, cudaMemsetAsync(f->d_bcZp, 0, zp * sizeof(double), f->stream));  // the pad columns of the tiles travel with the bulk copies
         CUDA_TRY(f, cudaMemsetAsync(f->d_bcMt, 0, mt * sizeof(double), f->stream));
+        CUDA_TRY(f, cudaMalloc(&f->d_bcCnt, (mp / BC_T + 1) * sizeof(int)));
+        CUDA_TRY(f, cudaMemsetAsync(f->d_bcCnt, 0, (mp / BC_T + 1) * sizeof(int), f->stream));
     }
     CUDA_TRY(f, cudaMalloc(&f->d_Cblk, c1 * 6 * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Gamma, (size_t)(dimpMax + 8) * sizeof(double)));
@@ -1401,45 +1406,68 @@ int enqueue_block_sweep(eqvio_filter* f, int nm, int dimp, double r2, const int*
     const int ldy = (dimp + BC_T - 1) / BC_T * BC_T, TW = ldy / BC_T;
     const int ldz = nT * BC_T + ldy;
     const bool serial = f->profiling;
-    cudaStream_t sA = f->stream, sB = serial ? f->stream : f->stream3;
-    while ((int)f->bcEv.size() < 2 * nT + 1) {
+    // A: build + diagonal chain; B: panel(k), then the trailing tiles the next block column needs; C: the other trailing tiles
+    cudaStream_t sA = f->stream, sB = serial ? f->stream : f->stream4, sC = serial ? f->stream : f->stream3;
+    while ((int)f->bcEv.size() < 3 * nT + 1) {
         cudaEvent_t e;
         CUDA_TRY(f, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         f->bcEv.push_back(e);
     }
+    auto evDiag = [&](int k) { return f->bcEv[3 * k]; };
+    auto evPanel = [&](int k) { return f->bcEv[3 * k + 1]; };
+    auto evRest = [&](int k) { return f->bcEv[3 * k + 2]; };
+    const size_t zpElems = (size_t)(nT + TW) * YB_TILE;  // panels ping-pong: rest(k) still reads Zp(k) while panel(k+1) writes
     launch_pdl(f, bc_build_kernel, dim3(nT * (nT + 1) / 2 + TW * nT), dim3(256), (size_t)0, sA, (const double*)f->Sig[f->cur], f->ld, dimp,
-               (const int*)f->d_lmOf, (const double*)f->d_Cblk, (const double*)f->d_ytilde, nm, r2, f->d_bcZ, ldz, nT, TW, guard, TL_SLOT(f));
+               (const int*)f->d_lmOf, (const double*)f->d_Cblk, (const double*)f->d_ytilde, nm, r2, f->d_bcZ, ldz, nT, TW, f->d_bcCnt, guard, TL_SLOT(f));
     LAUNCH_CHECK(f, "bc_build_kernel");
-    if (!serial) {
-        CUDA_TRY(f, cudaEventRecord(f->bcEv[2 * nT], sA));
-        CUDA_TRY(f, cudaStreamWaitEvent(sB, f->bcEv[2 * nT], 0));
-    }
     for (int k = 0; k < nT; ++k) {
-        if (!serial && k >= 2) CUDA_TRY(f, cudaStreamWaitEvent(sA, f->bcEv[2 * (k - 2) + 1], 0));  // trail(k-2)
+        // diag(k) needs two tiles of the trailing step k-2: counted off on the device (bc_diag_kernel), not an event edge into the chain
+        const int waitCnt = (!serial && k >= 2) ? BC_TRAIL_URGENT : 0;
         int pk = prof_begin(f, PROF_PANEL);
         launch_pdl(f, bc_diag_kernel, dim3(1), dim3(BC_DIAG_THREADS), (size_t)BC_DIAG_SMEM, sA, (const double*)f->d_bcZ, ldz, k, f->d_bcMt, f->d_status,
-                   guard, TL_SLOT(f));
+                   (const int*)f->d_bcCnt, waitCnt, guard, TL_SLOT(f));
         prof_end(f, pk);
         LAUNCH_CHECK(f, "bc_diag_kernel");
         if (!serial) {
-            CUDA_TRY(f, cudaEventRecord(f->bcEv[2 * k], sA));
-            CUDA_TRY(f, cudaStreamWaitEvent(sB, f->bcEv[2 * k], 0));
+            CUDA_TRY(f, cudaEventRecord(evDiag(k), sA));
+            CUDA_TRY(f, cudaStreamWaitEvent(sB, evDiag(k), 0));
         }
+        double* Zp = f->d_bcZp + (size_t)(k & 1) * zpElems;
         const int below = nT + TW - k - 1;  // row tiles under the diagonal block (S, then W)
+        const int q = nT - k - 1;
         int tk = prof_begin(f, PROF_TRAIL);
-        bc_panel_kernel<<<2 * below, 128, BC_PANEL_SMEM, sB>>>(f->d_bcZ, ldz, k, f->d_bcMt, f->d_bcZp, guard, TL_SLOT(f));
+        bc_panel_kernel<<<2 * below, 128, BC_PANEL_SMEM, sB>>>(f->d_bcZ, ldz, k, f->d_bcMt, Zp, guard, TL_SLOT(f));
         prof_end(f, tk);
         LAUNCH_CHECK(f, "bc_panel_kernel");
-        const int q = nT - k - 1;
-        const int tiles = (q > 0 ? q * (q + 1) / 2 - 1 : 0) + TW * q + TW * (TW + 1) / 2;
         int sk = prof_begin(f, PROF_SYRK);
-        bc_trail_kernel<<<2 * tiles, DD_THREADS, DD_SMEM, sB>>>(f->d_bcZ, ldz, f->Sig[f->cur], f->ld, f->d_bcZp, f->d_Gamma, guard, k, nT, TW, dimp,
-                                                               k == nT - 1 ? 1 : 0, TL_SLOT(f));
+        if (serial) {
+            bc_trail_kernel<<<2 * bc_trail_tiles(BC_PART_ALL, q, TW), DD_THREADS, DD_SMEM, sB>>>(f->d_bcZ, ldz, f->Sig[f->cur], f->ld, Zp, f->d_Gamma, guard, k,
+                                                                                               nT, TW, dimp, k == nT - 1 ? 1 : 0, (int)BC_PART_ALL,
+                                                                                               f->d_bcCnt, TL_SLOT(f));
+            LAUNCH_CHECK(f, "bc_trail_kernel");
+        } else {
+            CUDA_TRY(f, cudaEventRecord(evPanel(k), sB));
+            CUDA_TRY(f, cudaStreamWaitEvent(sC, evPanel(k), 0));
+            if (k >= 1) CUDA_TRY(f, cudaStreamWaitEvent(sB, evRest(k - 1), 0));  // next(k) rewrites tiles rest(k-1) wrote; panel(k+1) reuses Zp(k-1)
+            const int nNext = bc_trail_tiles(BC_PART_NEXT, q, TW);
+            if (nNext > 0) {
+                bc_trail_kernel<<<2 * nNext, DD_THREADS, DD_SMEM, sB>>>(f->d_bcZ, ldz, f->Sig[f->cur], f->ld, Zp, f->d_Gamma, guard, k, nT, TW, dimp, 0,
+                                                                      (int)BC_PART_NEXT, f->d_bcCnt, TL_SLOT(f));
+                LAUNCH_CHECK(f, "bc_trail_kernel<next>");
+            }
+            bc_trail_kernel<<<2 * bc_trail_tiles(BC_PART_REST, q, TW), DD_THREADS, DD_SMEM, sC>>>(f->d_bcZ, ldz, f->Sig[f->cur], f->ld, Zp, f->d_Gamma, guard, k,
+                                                                                                nT, TW, dimp, k == nT - 1 ? 1 : 0, (int)BC_PART_REST,
+                                                                                                f->d_bcCnt, TL_SLOT(f));
+            LAUNCH_CHECK(f, "bc_trail_kernel<rest>");
+            CUDA_TRY(f, cudaEventRecord(evRest(k), sC));
+        }
         prof_end(f, sk);
-        LAUNCH_CHECK(f, "bc_trail_kernel");
-        if (!serial) CUDA_TRY(f, cudaEventRecord(f->bcEv[2 * k + 1], sB));
     }
-    if (!serial) CUDA_TRY(f, cudaStreamWaitEvent(sA, f->bcEv[2 * (nT - 1) + 1], 0));
+    if (!serial) {
+        CUDA_TRY(f, cudaEventRecord(f->bcEv[3 * nT], sB));
+        CUDA_TRY(f, cudaStreamWaitEvent(sA, f->bcEv[3 * nT], 0));
+        CUDA_TRY(f, cudaStreamWaitEvent(sA, evRest(nT - 1), 0));
+    }
     return EQVIO_OK;
 }
 
@@ -2013,6 +2041,7 @@ void eqvio_destroy(eqvio_filter* f) {
     cudaFree(f->d_Xs[1]);
     if (f->stream2) cudaStreamDestroy(f->stream2);
     if (f->stream3) cudaStreamDestroy(f->stream3);
+    if (f->stream4) cudaStreamDestroy(f->stream4);
     if (f->evFork) cudaEventDestroy(f->evFork);
     if (f->evJoin) cudaEventDestroy(f->evJoin);
     cudaFree(f->d_ctx);
@@ -2024,6 +2053,7 @@ void eqvio_destroy(eqvio_filter* f) {
     cudaFree(f->d_bcZ);
     cudaFree(f->d_bcZp);
     cudaFree(f->d_bcMt);
+    cudaFree(f->d_bcCnt);
     for (auto& e : f->bcEv) cudaEventDestroy(e);
     cudaFree(f->d_Y2);
     cudaFree(f->d_Ysplit);

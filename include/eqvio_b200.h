@@ -210,8 +210,11 @@ int eqvio_get_kernel_profile(eqvio_filter* f, int reset, double ms[EQVIO_PROF_CL
  * frame), us[2] waiting for the device, us[3] the rest of phase C (status check, bookkeeping). */
 int eqvio_get_host_profile(eqvio_filter* f, int reset, double us[4], long long* calls);
 /* Evaluation-order knobs of the correction (results agree to rounding; tests run both).
- *   EQVIO_TUNE_CORRECTION: 0 = sequential landmark chunks exploiting C's block sparsity (default),
- *                          1 = batch form: Cholesky sweep over [S; W^T; ytilde^T], then Sigma -= Y^T Y.
+ *   EQVIO_TUNE_CORRECTION: 0 = sequential landmark chunks exploiting C's block sparsity,
+ *                          1 = batch form: Cholesky sweep over [S; W^T; ytilde^T], then Sigma -= Y^T Y,
+ *                          2 (default) = block Cholesky sweep with look-ahead (64-row blocks; the chain of diagonal factorizations on
+ *                              one stream, panels / trailing tiles / Sigma downdate beside it) for up to 768 measurement rows,
+ *                              sequential chunks beyond.
  *   EQVIO_TUNE_CHUNK_LANDMARKS: landmarks per chunk in mode 0 (1..32, default 32).
  *   EQVIO_TUNE_SPECULATE: 1 (default) = when a frame brings no new ids, launch the correction before the
  *                          gate scalars reach the host, guarded on the device by a "gate tripped" flag, and
