@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(256)
                     const double* __restrict__ ytilde, int nm, double r2, double* __restrict__ Z, int ldz, int nT, int TW,
                     int* __restrict__ trailCnt, const int* __restrict__ guard, int tl) {
     pdl_wait();
-    if (blockIdx.x == 0 && threadIdx.x < nT) trailCnt[threadIdx.x] = 0;  // completion counters of the trailing steps (see bc_diag_kernel)
+    // completion counters of the trailing steps and block-row flags of the diagonal steps (see bc_diag_kernel): trailCnt[0 .. 16) | flags
+    if (blockIdx.x == 0 && threadIdx.x < 16 + 8 * nT) trailCnt[threadIdx.x] = 0;
     if (*guard) return;
     TL_MARK(tl, 0);
     __shared__ double sC[32][6];
@@ -140,8 +141,9 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------------
 constexpr int BC_S_WARPS = 9;                      // 136 tiles x 2 half-tile owners = 272 threads
 constexpr int BC_S_THREADS = BC_S_WARPS * 32;      // 288
-constexpr int BC_X_THREADS = 64;                   // 4 diagonal 16 x 16 blocks x (4 x 4 tiles): their inverses ride along
-constexpr int BC_DIAG_THREADS = 512;               // 16 warps for the DMMA prologue; warps 0-8 = S group, 9-10 = X group
+constexpr int BC_X_THREADS = 128;                  // 4 diagonal 16 x 16 blocks x (4 x 4 tiles): their inverses ride along, one warp (16 lanes used) per
+                                                   // block -- two blocks in one warp wait on different block columns, and the spinning half starves the other
+constexpr int BC_DIAG_THREADS = 512;               // 16 warps for the DMMA prologue; warps 0-8 = S group, 9-12 = X group, 13 = publisher
 constexpr int BC_PLD = 18;                         // doubles per published tile: [r][j] and 2 of padding (conflict-free 16-byte reads)
 // What a diagonal step hands to its consumers (the next diagonal step, the panel kernel), per block k, two 64 x YB_LD arrays:
 //   LT = L_kk transposed, the six 16 x 16 blocks below the diagonal blocks;
@@ -159,13 +161,11 @@ __host__ __device__ __forceinline__ int bc_lt_block(int b, int j) { return b * (
 struct BcDiagSmem {
     double A[BC_T][YB_LD];            // T_{k,k-1} as A[j][r]; stage by stage replaced by P_{k,k-1} as A[c][r]
     double B[BC_T][YB_LD];            // the updated diagonal block as B[c][r]
-    double LX[10][16][BC_XLD];        // LT | XT of block k-1
     double Q[16][YB_LD];              // one stage's 64 x 16 block between its two products
     double Lp[CH_NT][CH_NT][BC_PLD];  // Lp[J][TI][4 r + j]: tile (TI, J) once block column J is finished (unscaled columns); TI = J: the diagonal tile
     double Dc[CH_NT][CH_T];           // reciprocal pivots of block column J
     double Inv[BC_T];
     uint64_t colBar[CH_NT];           // one mbarrier per block column: "its panels are published" (S group -> X group)
-    uint64_t lxBar;                   // arrival of the LT | XT bulk copy
 };
 constexpr int BC_DIAG_SMEM = (int)sizeof(BcDiagSmem);
 
@@ -175,7 +175,10 @@ __device__ int g_bc_warp[BC_S_WARPS * 64];
 // per-warp stamps go to shared memory (no global stores inside the loop) and are dumped after it
 #define BC_FINE(i) do { if ((threadIdx.x & 31) == 0 && threadIdx.x < BC_S_THREADS) bc_stamps[threadIdx.x >> 5][(i)] = (int)clock(); } while (0)
 #define BC_STAMP(i) do { if (threadIdx.x == 0 && kblk == 1) g_bc_t[(i)] = clock64(); } while (0)
+__device__ unsigned long long g_bc_gt[32];  // globaltimer stamps across the first two diagonal steps (hand-over latency)
+#define BC_GT(slot) do { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_bc_gt[(slot)] = t_; } while (0)
 #else
+#define BC_GT(slot) do { } while (0)
 #define BC_FINE(i) do { } while (0)
 #define BC_STAMP(i) do { } while (0)
 #endif
@@ -185,7 +188,7 @@ __device__ __forceinline__ int bc_diag_tile(int J) { return CH_NT * J - J * (J -
 // Z: augmented matrix (ldz), kblk: block column.  LxAll: per block the LT | XT pair described above.
 __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
     bc_diag_kernel(const double* __restrict__ Z, int ldz, int kblk, double* __restrict__ LxAll, int* __restrict__ status,
-                   const int* trailCnt, int waitCnt, const int* __restrict__ guard, int tl) {
+                   const int* trailCnt, int waitCnt, int* lxFlag, const int* __restrict__ guard, int tl) {
     extern __shared__ __align__(128) unsigned char bc_smem_raw[];
     BcDiagSmem& sm = *reinterpret_cast<BcDiagSmem*>(bc_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -194,7 +197,6 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
     BC_STAMP(0);
     if (tid == 0) {
         for (int J = 0; J < CH_NT; ++J) mbar_init(&sm.colBar[J], 1);
-        mbar_init(&sm.lxBar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // Two dependencies, taken one at a time:
@@ -202,7 +204,10 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
     //      chain costs ~3 us per step inside a replayed graph, so the trailing CTAs count themselves off in trailCnt[k-2] instead
     //      (release) and thread 0 polls it (acquire; bounded).  trail(k-2) never waits for this kernel, and everything it waits for
     //      completed before this grid could start (its stream predecessor, diag(k-1), was past its own dependency wait).
-    //  (2) LT | XT of block k-1 come from diag(k-1): griddepcontrol.wait.  The T tiles are fetched ahead of it.
+    //  (2) LT | XT of block k-1 come from diag(k-1), which is still RUNNING when this grid starts (programmatic launch: diag(k-1)
+    //      releases its dependents once it has all of its own inputs).  It publishes them block row by block row -- block row b of
+    //      L_{k-1,k-1} is final after block column 4b+3 of its factorization -- behind lxFlag[k-1][b] (release / acquire), so three of
+    //      the four substitution stages below, and three quarters of D = T_kk - P P^T, run beside the previous factorization.
     if (waitCnt > 0) {
         if (tid == 0) {
             int spins = 0, seen;
@@ -234,11 +239,18 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
             }
         }
     }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (*guard) return;
+    if (kblk == 0) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // the build kernel (and with it everything earlier on the stream)
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
+    if (*guard) {
+        // a guarded update: nothing will be published, the chain must still unwind
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        return;
+    }
     TL_MARK(tl, 0);
     BC_STAMP(1);
+    if (tid == 0 && kblk < 2) BC_GT(8 * kblk);
     const bool sGroup = tid < BC_S_THREADS;
     const int t = tid >> 1, h = tid & 1;  // S group: tile t (column-major over the lower triangle), rows 2h, 2h+1 of it
     const bool owner = sGroup && t < CH_TILES;
@@ -251,80 +263,111 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
         for (int c = 0; c < CH_T; ++c) a[r][c] = 0.0;
 
     if (kblk > 0) {
-        // ---- look-ahead products on the FP64 tensor pipe (16 warps):  P = T_{k,k-1} L^-T (block substitution),  D = T_kk - P P^T  ----
-        if (tid == 0) {
-            mbar_expect_tx(&sm.lxBar, (uint32_t)(BC_LX * 8));
-            bulk_g2s(&sm.LX[0][0][0], LxAll + (size_t)(kblk - 1) * BC_LX, (uint32_t)(BC_LX * 8), &sm.lxBar);
-        }
+        // ---- look-ahead products on the FP64 tensor pipe:  P = T_{k,k-1} L^-T (block substitution, one stage per published block
+        //      row),  D = T_kk - P P^T accumulated stage by stage  ----
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int q = tid + BC_DIAG_THREADS * u;
             *reinterpret_cast<double2*>(&sm.A[q >> 5][(q & 31) * 2]) = tpre[u];
         }
-        __syncthreads();
-        mbar_wait(&sm.lxBar, 0);
+        int fi2[3], fj2[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            fi2[u] = fj2[u] = 0;
+            if (warp + 16 * u < 36) tri_decode(warp + 16 * u, fi2[u], fj2[u]);
+        }
+        const int nf = warp < 4 ? 3 : 2;
+        const double* Lxg = LxAll + (size_t)(kblk - 1) * BC_LX;
+        const int* flagPrev = lxFlag + 8 * (kblk - 1);  // [0, 4): LT block row b published, [4, 8): XT block b published
+        auto wait_flag = [&](const int* fp) {
+            int spins = 0, seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(fp) : "memory");
+            } while (seen == 0 && ++spins < (1 << 24));
+            if (seen == 0) atomicOr(status, 8);
+        };
+        __syncthreads();  // T in shared memory
         BC_STAMP(2);
-        // four stages; warp fi < 8 owns rows 8 fi .. 8 fi + 7 of P through all of them (both 8-column fragments of a stage), so the
-        // stages only need warp-level synchronisation
-        if (warp < 8) {
-            const int fi = warp;
 #pragma unroll 1
-            for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < 4; ++b) {
+            // warp fi < 8 owns rows 8 fi .. 8 fi + 7 of P through all stages (both 8-column fragments of a stage).  Its operands from
+            // diag(k-1) -- fragments of LT block row b, then of XT block b -- come straight from global memory (L2) into registers
+            // behind the flag of each: no staging, no CTA-wide barrier between the flag and the products.
+            if (warp < 8) {
+                const int fi = warp;
                 double q[2][2];
 #pragma unroll
                 for (int fn = 0; fn < 2; ++fn) {
                     q[fn][0] = -sm.A[16 * b + 8 * fn + 2 * t4][8 * fi + g];
                     q[fn][1] = -sm.A[16 * b + 8 * fn + 2 * t4 + 1][8 * fi + g];
                 }
-                for (int k4 = 0; k4 < 16 * b; k4 += 4) {
-                    const double af = sm.A[k4 + t4][8 * fi + g];
+                if (b > 0) {
+                    wait_flag(flagPrev + b);
+                    double lf[3][4][2];  // every fragment of the block row in flight before the first product
 #pragma unroll
-                    for (int fn = 0; fn < 2; ++fn) dmma884(q[fn][0], q[fn][1], af, sm.LX[bc_lt_block(b, k4 >> 4)][(k4 & 15) + t4][8 * fn + g]);
+                    for (int jb = 0; jb < 3; ++jb)
+                        if (jb < b) {
+                            const double* Lb = Lxg + (size_t)bc_lt_block(b, jb) * BC_XBLK;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                                for (int fn = 0; fn < 2; ++fn) lf[jb][kk][fn] = Lb[(4 * kk + t4) * BC_XLD + 8 * fn + g];
+                        }
+#pragma unroll
+                    for (int jb = 0; jb < 3; ++jb)
+                        if (jb < b) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const double af = sm.A[16 * jb + 4 * kk + t4][8 * fi + g];
+#pragma unroll
+                                for (int fn = 0; fn < 2; ++fn) dmma884(q[fn][0], q[fn][1], af, lf[jb][kk][fn]);
+                            }
+                        }
                 }
 #pragma unroll
                 for (int fn = 0; fn < 2; ++fn) {
                     sm.Q[8 * fn + 2 * t4][8 * fi + g] = -q[fn][0];
                     sm.Q[8 * fn + 2 * t4 + 1][8 * fi + g] = -q[fn][1];
                 }
+                wait_flag(flagPrev + 4 + b);
+                if (tid == 0 && kblk == 1) BC_GT(16 + b);
+                const double* Xb = Lxg + (size_t)(6 + b) * BC_XBLK;
+                double xf[4][2];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                    for (int fn = 0; fn < 2; ++fn) xf[kk][fn] = Xb[(4 * kk + t4) * BC_XLD + 8 * fn + g];
                 __syncwarp();
                 double p[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
-                for (int k4 = 0; k4 < 16; k4 += 4) {
-                    const double af = sm.Q[k4 + t4][8 * fi + g];
-                    if (k4 < 8) dmma884(p[0][0], p[0][1], af, sm.LX[6 + b][k4 + t4][g]);
-                    dmma884(p[1][0], p[1][1], af, sm.LX[6 + b][k4 + t4][8 + g]);
+                for (int kk = 0; kk < 4; ++kk) {
+                    const double af = sm.Q[4 * kk + t4][8 * fi + g];
+                    if (kk < 2) dmma884(p[0][0], p[0][1], af, xf[kk][0]);
+                    dmma884(p[1][0], p[1][1], af, xf[kk][1]);
                 }
 #pragma unroll
                 for (int fn = 0; fn < 2; ++fn) {  // P_b takes the place of T's block column b
                     sm.A[16 * b + 8 * fn + 2 * t4][8 * fi + g] = p[fn][0];
                     sm.A[16 * b + 8 * fn + 2 * t4 + 1][8 * fi + g] = p[fn][1];
                 }
-                __syncwarp();
             }
-        }
-        __syncthreads();
-        BC_STAMP(3);
-        if (warp < 16) {
-            int fi[3], fj[3];
+            __syncthreads();
+            if (b == 3) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // diag(k-1) is done: let diag(k+1) in
+            // D -= P_b P_b^T on the 36 lower 8 x 8 fragments (round-robin over the 16 warps: 9 per SM sub-partition)
 #pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                fi[u] = fj[u] = 0;
-                if (warp + 16 * u < 36) tri_decode(warp + 16 * u, fi[u], fj[u]);
-            }
-            const int nf = warp < 4 ? 3 : 2;
-#pragma unroll 4
-            for (int c4 = 0; c4 < BC_T; c4 += 4) {
+            for (int c4 = 0; c4 < 16; c4 += 4) {
 #pragma unroll
                 for (int u = 0; u < 3; ++u)
-                    if (u < nf) dmma884(acc2[u][0], acc2[u][1], sm.A[c4 + t4][8 * fi[u] + g], sm.A[c4 + t4][8 * fj[u] + g]);
+                    if (u < nf) dmma884(acc2[u][0], acc2[u][1], sm.A[16 * b + c4 + t4][8 * fi2[u] + g], sm.A[16 * b + c4 + t4][8 * fj2[u] + g]);
             }
-#pragma unroll
-            for (int u = 0; u < 3; ++u)
-                if (u < nf) {
-                    sm.B[8 * fj[u] + 2 * t4][8 * fi[u] + g] = -acc2[u][0];
-                    sm.B[8 * fj[u] + 2 * t4 + 1][8 * fi[u] + g] = -acc2[u][1];
-                }
         }
+        BC_STAMP(3);
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+            if (u < nf) {
+                sm.B[8 * fj2[u] + 2 * t4][8 * fi2[u] + g] = -acc2[u][0];
+                sm.B[8 * fj2[u] + 2 * t4 + 1][8 * fi2[u] + g] = -acc2[u][1];
+            }
         __syncthreads();
         BC_STAMP(4);
         if (owner) {
@@ -386,6 +429,7 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
             }
         };
         const int myWarpFirstTile = (warp * 32) >> 1, myWarpLastTile = myWarpFirstTile + 15;
+        if (tid == 0 && kblk < 2) BC_GT(8 * kblk + 1);
         if (warp == 0) eliminate(0);
         for (int J = 0; J < CH_NT; ++J) {
             BC_FINE(4 * J);
@@ -463,35 +507,19 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
         }
         if (owner && TI == TK && h == 0) {
 #pragma unroll
-            for (int c = 0; c < CH_T; ++c) {
-                const double piv = pv[c];
-                const int k = CH_T * TK + c;
-                if (!(piv > 0.0)) {
-                    atomicOr(status, 1);
-                    sm.Inv[k] = 1.0;
-                } else {
-                    sm.Inv[k] = 1.0 / sqrt(piv);
-                }
-            }
+            for (int c = 0; c < CH_T; ++c)
+                if (!(pv[c] > 0.0)) atomicOr(status, 1);  // S is not positive definite
         }
         BC_STAMP(5);
-        __syncthreads();  // Inv published
-        // LT: the off-diagonal tiles are still in their owners' registers (unscaled columns: L_ij = v_ij / L_jj)
-        if (owner && (TI >> 2) > (TK >> 2)) {
-            double* Lt = LxAll + (size_t)kblk * BC_LX + (size_t)bc_lt_block(TI >> 2, TK >> 2) * BC_XBLK;
-#pragma unroll
-            for (int j = 0; j < CH_T; ++j) {
-                const double sc = sm.Inv[CH_T * TK + j];
-                *reinterpret_cast<double2*>(Lt + (CH_T * (TK & 3) + j) * BC_XLD + CH_T * (TI & 3) + 2 * h) = make_double2(a[0][j] * sc, a[1][j] * sc);
-            }
-        }
+        if (tid == 0 && kblk < 2) BC_GT(8 * kblk + 2);
     } else if (tid < BC_S_THREADS + BC_X_THREADS) {
         // ======== X group: the identity rides along inside each diagonal 16 x 16 block (4 steps per block): X_b = L_bb^-1 ========
-        const int q = tid - BC_S_THREADS;
-        const int blk = q >> 4, i = (q >> 2) & 3, tk = q & 3;
+        const int q = lane & 15;
+        const int blk = warp - BC_S_WARPS, i = (q >> 2) & 3, tk = q & 3;
+        if (lane >= 16) goto done;  // (the upper half of the warp only takes part in the final barrier)
         TI = 4 * blk + i;   // tile row: rows 4 TI .. 4 TI + 3 of the identity
         TK = 4 * blk + tk;  // tile column
-        const unsigned grp = 0xffffu << (16 * (blk & 1));  // the 16 lanes of this block: the two blocks of a warp run at their own pace
+        const unsigned grp = 0xffffu;
         double b[CH_T][CH_T];
 #pragma unroll
         for (int r = 0; r < CH_T; ++r)
@@ -544,22 +572,43 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
                 }
             }
         }
-        __syncthreads();  // Inv published
+        // 1 / L_jj = sqrt of the reciprocal pivot the diagonal thread published
         double* Xt = LxAll + (size_t)kblk * BC_LX + (size_t)(6 + blk) * BC_XBLK;
+        const double2* cq = reinterpret_cast<const double2*>(&sm.Dc[TK][0]);
+        const double2 e01 = cq[0], e23 = cq[1];
+        const double s0 = sqrt(e01.x), s1 = sqrt(e01.y), s2 = sqrt(e23.x), s3 = sqrt(e23.y);
 #pragma unroll
         for (int r = 0; r < CH_T; ++r) {
-            double2 lo, hi;
-            lo.x = b[r][0] * sm.Inv[CH_T * TK];
-            lo.y = b[r][1] * sm.Inv[CH_T * TK + 1];
-            hi.x = b[r][2] * sm.Inv[CH_T * TK + 2];
-            hi.y = b[r][3] * sm.Inv[CH_T * TK + 3];
             double* p = Xt + (CH_T * i + r) * BC_XLD + CH_T * tk;
-            *reinterpret_cast<double2*>(p) = lo;
-            *reinterpret_cast<double2*>(p + 2) = hi;
+            *reinterpret_cast<double2*>(p) = make_double2(b[r][0] * s0, b[r][1] * s1);
+            *reinterpret_cast<double2*>(p + 2) = make_double2(b[r][2] * s2, b[r][3] * s3);
         }
-    } else {
-        __syncthreads();  // the idle warps of the loop only take part in the barrier
+        __syncwarp(grp);
+        if (q == 0) {  // release at gpu scope: cumulative over the group's stores (ordered before it by the warp barrier)
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(lxFlag + 8 * kblk + 4 + blk), "r"(1) : "memory");
+            if (kblk == 0) BC_GT(3 + blk);
+        }
+    } else if (warp == (BC_S_THREADS + BC_X_THREADS) / 32) {
+        // ======== publisher (one of the warps that are idle during the loop): block row b of L_kk only has entries in block columns
+        // < b, final once block column 4b - 1 is finished: scaled, transposed, to global memory, then its flag ========
+        double* Ltg = LxAll + (size_t)kblk * BC_LX;
+#pragma unroll 1
+        for (int b = 1; b < 4; ++b) {
+            if (!mbar_wait_bounded(&sm.colBar[4 * b - 1], 0)) atomicOr(status, 8);
+            if (lane < 16) sm.Inv[16 * (b - 1) + lane] = sqrt(sm.Dc[4 * (b - 1) + (lane >> 2)][lane & 3]);  // 1 / L_jj of block b-1's columns
+            __syncwarp();
+            for (int idx = lane; idx < 256 * b; idx += 32) {
+                const int n = idx & 15, k = idx >> 4;  // row 16 b + n, column k of L
+                const double v = sm.Lp[k >> 2][4 * b + (n >> 2)][4 * (n & 3) + (k & 3)] * sm.Inv[k];
+                Ltg[(size_t)bc_lt_block(b, k >> 4) * BC_XBLK + (k & 15) * BC_XLD + n] = v;
+            }
+            __syncwarp();
+            if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(lxFlag + 8 * kblk + b), "r"(1) : "memory");
+        }
     }
+done:
+    __syncthreads();
+
 #ifdef EQVIO_CHUNK_TIMING
     if (kblk == 1 && tid < BC_S_WARPS * 32) {
         g_bc_warp[2 * tid] = bc_stamps[(2 * tid) / 64][(2 * tid) % 64];
@@ -602,11 +651,18 @@ __global__ void __launch_bounds__(128)
         bulk_g2s(&sm.LX[0][0][0], LxAll + (size_t)kblk * BC_LX, (uint32_t)(BC_LX * 8), &sm.bar);
     }
     const double* Tp = Z + (size_t)(kblk * BC_T) * ldz + (size_t)t * BC_T + 32 * half;
-    for (int q = tid; q < BC_T * 16; q += 128) {
-        const int j = q >> 4, r = (q & 15) * 2;
-        const double2 v = *reinterpret_cast<const double2*>(Tp + (size_t)j * ldz + r);
-        sm.A[j][r] = v.x;
-        sm.A[j][r + 1] = v.y;
+    {
+        double2 v[8];  // 1024 16-byte words, eight per thread, all in flight before the first store
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int q = tid + 128 * u;
+            v[u] = *reinterpret_cast<const double2*>(Tp + (size_t)(q >> 4) * ldz + (q & 15) * 2);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int q = tid + 128 * u;
+            *reinterpret_cast<double2*>(&sm.A[q >> 4][(q & 15) * 2]) = v[u];
+        }
     }
     __syncthreads();
     mbar_wait(&sm.bar, 0);
@@ -821,6 +877,162 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
                     *reinterpret_cast<double2*>(Sig + (size_t)R * ld + Cc) = tt;
                 }
             }
+    }
+    if (urgent) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(trailCnt + kblk, 1);
+        }
+    }
+    TL_MARK(tl, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// What the NEXT block column needs from step k, in one launch: for every tile of block column k+1 (S tiles (i, k+1), i >= k+2, the W
+// tiles (w, k+1)) and the diagonal tile (k+2, k+2), a CTA pair substitutes the two row panels it needs itself (P_a: its 32 rows, P_b:
+// the 64 rows of tile k+1 or k+2) and applies  T -= P_a P_b^T  -- panel(k) -> trail<next>(k) as two launches put ~11 us between the end
+// of diag(k) and the two tiles diag(k+2) reads; this puts ~5 us there, and panel(k) / trail<rest>(k) run beside it.
+// ------------------------------------------------------------------------------------------------
+constexpr int BC_NEXT_THREADS = 384;  // 12 warps: 8 row fragments of P_b, 4 of P_a
+constexpr int BC_QLD = 12;
+struct BcNextSmem {
+    double LX[10][16][BC_XLD];
+    double Pb[BC_T][YB_LD];
+    double Pa[BC_T][BC_PA_LD];
+    double Q[12][16][BC_QLD];
+    uint64_t bar;
+};
+constexpr int BC_NEXT_SMEM = (int)sizeof(BcNextSmem);
+
+// four substitution stages on the 8 rows r0 .. r0 + 7 of a panel held as P[c][r] (T on entry, P = T L^-T on exit); warp-local
+template <int LD>
+__device__ __forceinline__ void bc_substitute_rows(double (*P)[LD], int r0, const double (*LX)[16][BC_XLD], double (*Q)[BC_QLD], int g, int t4) {
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+        double q[2][2];
+#pragma unroll
+        for (int fn = 0; fn < 2; ++fn) {
+            q[fn][0] = -P[16 * b + 8 * fn + 2 * t4][r0 + g];
+            q[fn][1] = -P[16 * b + 8 * fn + 2 * t4 + 1][r0 + g];
+        }
+        for (int k4 = 0; k4 < 16 * b; k4 += 4) {
+            const double af = P[k4 + t4][r0 + g];
+#pragma unroll
+            for (int fn = 0; fn < 2; ++fn) dmma884(q[fn][0], q[fn][1], af, LX[bc_lt_block(b, k4 >> 4)][(k4 & 15) + t4][8 * fn + g]);
+        }
+#pragma unroll
+        for (int fn = 0; fn < 2; ++fn) {
+            Q[8 * fn + 2 * t4][g] = -q[fn][0];
+            Q[8 * fn + 2 * t4 + 1][g] = -q[fn][1];
+        }
+        __syncwarp();
+        double p[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int k4 = 0; k4 < 16; k4 += 4) {
+            const double af = Q[k4 + t4][g];
+            if (k4 < 8) dmma884(p[0][0], p[0][1], af, LX[6 + b][k4 + t4][g]);
+            dmma884(p[1][0], p[1][1], af, LX[6 + b][k4 + t4][8 + g]);
+        }
+#pragma unroll
+        for (int fn = 0; fn < 2; ++fn) {
+            P[16 * b + 8 * fn + 2 * t4][r0 + g] = p[fn][0];
+            P[16 * b + 8 * fn + 2 * t4 + 1][r0 + g] = p[fn][1];
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(BC_NEXT_THREADS)
+    bc_next_kernel(double* Z, int ldz, const double* __restrict__ LxAll, const int* __restrict__ guard, int kblk, int nT, int TW,
+                   int* __restrict__ trailCnt, int tl) {
+    pdl_wait();
+    const int bid = (int)(blockIdx.x >> 1), half = (int)(blockIdx.x & 1);
+    const int q = nT - kblk - 1;
+    const bool urgent = q >= 2 && (bid == 0 || bid == q - 1);  // T(k+2, k+1), T(k+2, k+2): what diag(k+2) waits for
+    if (*guard) {
+        if (urgent && threadIdx.x == 0) atomicAdd(trailCnt + kblk, 1);
+        return;
+    }
+    TL_MARK(tl, 0);
+    int ta, tb;
+    const int nSA = (q - 1) + (q >= 2 ? 1 : 0);
+    if (bid < q - 1) {
+        ta = kblk + 2 + bid;
+        tb = kblk + 1;
+    } else if (q >= 2 && bid == q - 1) {
+        ta = tb = kblk + 2;
+    } else {
+        ta = nT + (bid - nSA);
+        tb = kblk + 1;
+    }
+    extern __shared__ __align__(128) unsigned char bcn_smem_raw[];
+    BcNextSmem& sm = *reinterpret_cast<BcNextSmem*>(bcn_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    if (tid == 0) {
+        mbar_init(&sm.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&sm.bar, (uint32_t)(BC_LX * 8));
+        bulk_g2s(&sm.LX[0][0][0], LxAll + (size_t)kblk * BC_LX, (uint32_t)(BC_LX * 8), &sm.bar);
+    }
+    const double* Tb = Z + (size_t)(kblk * BC_T) * ldz + (size_t)tb * BC_T;
+    const double* Ta = Z + (size_t)(kblk * BC_T) * ldz + (size_t)ta * BC_T + 32 * half;
+    {
+        // 2048 + 1024 16-byte words: every load of a thread in flight before its first store (a load -> store loop pays one L2 round
+        // trip per iteration: 3 us of the launch)
+        double2 vb[6], va[3];
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+            const int w = tid + BC_NEXT_THREADS * u;
+            if (w < BC_T * 32) vb[u] = *reinterpret_cast<const double2*>(Tb + (size_t)(w >> 5) * ldz + (w & 31) * 2);
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int w = tid + BC_NEXT_THREADS * u;
+            if (w < BC_T * 16) va[u] = *reinterpret_cast<const double2*>(Ta + (size_t)(w >> 4) * ldz + (w & 15) * 2);
+        }
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+            const int w = tid + BC_NEXT_THREADS * u;
+            if (w < BC_T * 32) *reinterpret_cast<double2*>(&sm.Pb[w >> 5][(w & 31) * 2]) = vb[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int w = tid + BC_NEXT_THREADS * u;
+            if (w < BC_T * 16) *reinterpret_cast<double2*>(&sm.Pa[w >> 4][(w & 15) * 2]) = va[u];
+        }
+    }
+    // the tile itself, straight into the accumulator fragments of warps 0-7: rows wm .. wm+7 of this half, columns wn .. wn+31
+    const int wm = (warp >> 1) * 8, wn = (warp & 1) * 32;
+    double* cbase = Z + (size_t)((kblk + 1 + (tb - kblk - 1)) * BC_T + wn + 2 * t4) * ldz + (size_t)ta * BC_T + 32 * half + wm + g;
+    double acc[4][2];
+    if (warp < 8) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            acc[b][0] = -cbase[(size_t)(b * 8) * ldz];
+            acc[b][1] = -cbase[(size_t)(b * 8 + 1) * ldz];
+        }
+    }
+    __syncthreads();
+    mbar_wait(&sm.bar, 0);
+    if (warp < 8)
+        bc_substitute_rows<YB_LD>(sm.Pb, 8 * warp, sm.LX, sm.Q[warp], g, t4);
+    else
+        bc_substitute_rows<BC_PA_LD>(sm.Pa, 8 * (warp - 8), sm.LX, sm.Q[warp], g, t4);
+    __syncthreads();
+    if (warp < 8) {
+#pragma unroll 4
+        for (int k4 = 0; k4 < BC_T; k4 += 4) {
+            const double af = sm.Pa[k4 + t4][wm + g];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) dmma884(acc[b][0], acc[b][1], af, sm.Pb[k4 + t4][wn + 8 * b + g]);
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            cbase[(size_t)(b * 8) * ldz] = -acc[b][0];
+            cbase[(size_t)(b * 8 + 1) * ldz] = -acc[b][1];
+        }
     }
     if (urgent) {
         __syncthreads();

@@ -519,8 +519,8 @@ int alloc_device(eqvio_filter* f) {
         CUDA_TRY(f, cudaMalloc(&f->d_bcMt, mt * sizeof(double)));
         CUDA_TRY(f, cudaMemsetAsync(f->d_bcZp, 0, zp * sizeof(double), f->stream));  // the pad columns of the tiles travel with the bulk copies
         CUDA_TRY(f, cudaMemsetAsync(f->d_bcMt, 0, mt * sizeof(double), f->stream));
-        CUDA_TRY(f, cudaMalloc(&f->d_bcCnt, (mp / BC_T + 1) * sizeof(int)));
-        CUDA_TRY(f, cudaMemsetAsync(f->d_bcCnt, 0, (mp / BC_T + 1) * sizeof(int), f->stream));
+        CUDA_TRY(f, cudaMalloc(&f->d_bcCnt, (16 + 8 * (mp / BC_T) + 8) * sizeof(int)));  // counters [0, 16) | block-row flags
+        CUDA_TRY(f, cudaMemsetAsync(f->d_bcCnt, 0, (16 + 8 * (mp / BC_T) + 8) * sizeof(int), f->stream));
     }
     CUDA_TRY(f, cudaMalloc(&f->d_Cblk, c1 * 6 * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Gamma, (size_t)(dimpMax + 8) * sizeof(double)));
@@ -1425,7 +1425,7 @@ int enqueue_block_sweep(eqvio_filter* f, int nm, int dimp, double r2, const int*
         const int waitCnt = (!serial && k >= 2) ? BC_TRAIL_URGENT : 0;
         int pk = prof_begin(f, PROF_PANEL);
         launch_pdl(f, bc_diag_kernel, dim3(1), dim3(BC_DIAG_THREADS), (size_t)BC_DIAG_SMEM, sA, (const double*)f->d_bcZ, ldz, k, f->d_bcMt, f->d_status,
-                   (const int*)f->d_bcCnt, waitCnt, guard, TL_SLOT(f));
+                   (const int*)f->d_bcCnt, waitCnt, f->d_bcCnt + 16, guard, TL_SLOT(f));
         prof_end(f, pk);
         LAUNCH_CHECK(f, "bc_diag_kernel");
         if (!serial) {
@@ -1435,33 +1435,37 @@ int enqueue_block_sweep(eqvio_filter* f, int nm, int dimp, double r2, const int*
         double* Zp = f->d_bcZp + (size_t)(k & 1) * zpElems;
         const int below = nT + TW - k - 1;  // row tiles under the diagonal block (S, then W)
         const int q = nT - k - 1;
-        int tk = prof_begin(f, PROF_TRAIL);
-        bc_panel_kernel<<<2 * below, 128, BC_PANEL_SMEM, sB>>>(f->d_bcZ, ldz, k, f->d_bcMt, Zp, guard, TL_SLOT(f));
-        prof_end(f, tk);
-        LAUNCH_CHECK(f, "bc_panel_kernel");
-        int sk = prof_begin(f, PROF_SYRK);
         if (serial) {
+            int tk = prof_begin(f, PROF_TRAIL);
+            bc_panel_kernel<<<2 * below, 128, BC_PANEL_SMEM, sB>>>(f->d_bcZ, ldz, k, f->d_bcMt, Zp, guard, TL_SLOT(f));
+            prof_end(f, tk);
+            LAUNCH_CHECK(f, "bc_panel_kernel");
+            int sk = prof_begin(f, PROF_SYRK);
             bc_trail_kernel<<<2 * bc_trail_tiles(BC_PART_ALL, q, TW), DD_THREADS, DD_SMEM, sB>>>(f->d_bcZ, ldz, f->Sig[f->cur], f->ld, Zp, f->d_Gamma, guard, k,
                                                                                                nT, TW, dimp, k == nT - 1 ? 1 : 0, (int)BC_PART_ALL,
                                                                                                f->d_bcCnt, TL_SLOT(f));
+            prof_end(f, sk);
             LAUNCH_CHECK(f, "bc_trail_kernel");
         } else {
-            CUDA_TRY(f, cudaEventRecord(evPanel(k), sB));
-            CUDA_TRY(f, cudaStreamWaitEvent(sC, evPanel(k), 0));
-            if (k >= 1) CUDA_TRY(f, cudaStreamWaitEvent(sB, evRest(k - 1), 0));  // next(k) rewrites tiles rest(k-1) wrote; panel(k+1) reuses Zp(k-1)
+            // B: the tiles block column k+1 (and diag(k+2)) needs, panels substituted inside the launch
             const int nNext = bc_trail_tiles(BC_PART_NEXT, q, TW);
             if (nNext > 0) {
-                bc_trail_kernel<<<2 * nNext, DD_THREADS, DD_SMEM, sB>>>(f->d_bcZ, ldz, f->Sig[f->cur], f->ld, Zp, f->d_Gamma, guard, k, nT, TW, dimp, 0,
-                                                                      (int)BC_PART_NEXT, f->d_bcCnt, TL_SLOT(f));
-                LAUNCH_CHECK(f, "bc_trail_kernel<next>");
+                if (k >= 1) CUDA_TRY(f, cudaStreamWaitEvent(sB, evRest(k - 1), 0));  // rest(k-1) wrote the same tiles (step k-1)
+                bc_next_kernel<<<2 * nNext, BC_NEXT_THREADS, BC_NEXT_SMEM, sB>>>(f->d_bcZ, ldz, f->d_bcMt, guard, k, nT, TW, f->d_bcCnt, TL_SLOT(f));
+                LAUNCH_CHECK(f, "bc_next_kernel");
+                CUDA_TRY(f, cudaEventRecord(evPanel(k), sB));
             }
+            // C: panels of every row tile, then all the other trailing tiles
+            CUDA_TRY(f, cudaStreamWaitEvent(sC, evDiag(k), 0));
+            if (k >= 1) CUDA_TRY(f, cudaStreamWaitEvent(sC, evPanel(k - 1), 0));  // block column k is current through step k-1
+            bc_panel_kernel<<<2 * below, 128, BC_PANEL_SMEM, sC>>>(f->d_bcZ, ldz, k, f->d_bcMt, Zp, guard, TL_SLOT(f));
+            LAUNCH_CHECK(f, "bc_panel_kernel");
             bc_trail_kernel<<<2 * bc_trail_tiles(BC_PART_REST, q, TW), DD_THREADS, DD_SMEM, sC>>>(f->d_bcZ, ldz, f->Sig[f->cur], f->ld, Zp, f->d_Gamma, guard, k,
                                                                                                 nT, TW, dimp, k == nT - 1 ? 1 : 0, (int)BC_PART_REST,
                                                                                                 f->d_bcCnt, TL_SLOT(f));
             LAUNCH_CHECK(f, "bc_trail_kernel<rest>");
             CUDA_TRY(f, cudaEventRecord(evRest(k), sC));
         }
-        prof_end(f, sk);
     }
     if (!serial) {
         CUDA_TRY(f, cudaEventRecord(f->bcEv[3 * nT], sB));
@@ -1816,6 +1820,7 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
     if (e == cudaSuccess) e = cudaFuncSetAttribute(bc_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_DIAG_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(bc_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_PANEL_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(bc_trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(bc_next_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_NEXT_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ChunkSmem) > (size_t)CH_SMEM_STAGED ? sizeof(ChunkSmem) : (size_t)CH_SMEM_STAGED));
     if (e != cudaSuccess) {
         g_createError = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
@@ -2716,6 +2721,7 @@ int eqvio_debug_chunk_timing(long long out[16]) {
 int eqvio_debug_chunk_fine(long long out[128]) {
     return cudaMemcpyFromSymbol(out, g_chunk_fine, sizeof(long long) * 128) == cudaSuccess ? 0 : -2;
 }
+int eqvio_debug_bc_gt(unsigned long long out[32]) { return cudaMemcpyFromSymbol(out, g_bc_gt, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : -2; }
 int eqvio_debug_bc_timing(long long out[16], int warps[BC_S_WARPS * 64]) {
     if (cudaMemcpyFromSymbol(out, g_bc_t, sizeof(long long) * 16) != cudaSuccess) return -2;
     return cudaMemcpyFromSymbol(warps, g_bc_warp, sizeof(int) * BC_S_WARPS * 64) == cudaSuccess ? 0 : -2;

@@ -41,3 +41,16 @@ t0 = w[:, 0, 0].min()
 print("per S-group warp (lane 0), cycles since the loop start: loop top | after barrier 1 | after barrier 2")
 for J in range(16):
     print(f"  J={J:2d}  " + "   ".join(" ".join(f"{(w[q, J, i] - t0) & 0xffffffff:6d}" for i in (0, 2, 3)) for q in range(9)))
+
+gt = getattr(_capi.lib, "eqvio_debug_bc_gt", None)
+if gt is not None:
+    buf = (C.c_ulonglong * 32)()
+    if gt(buf) == 0:
+        v = np.array(list(buf), dtype=np.float64)
+        t0 = v[0]
+        lab = {0: "diag(0) start", 1: "diag(0) loop start", 2: "diag(0) loop end", 3: "diag(0) XT flag 0", 4: "diag(0) XT flag 1", 5: "diag(0) XT flag 2",
+               6: "diag(0) XT flag 3", 8: "diag(1) start (T fetched)", 9: "diag(1) loop start", 10: "diag(1) loop end", 16: "diag(1) saw XT flag 0",
+               17: "diag(1) saw XT flag 1", 18: "diag(1) saw XT flag 2", 19: "diag(1) saw XT flag 3"}
+        print("hand-over between the first two diagonal steps (globaltimer, us since diag(0) start):")
+        for i in sorted(lab, key=lambda i: v[i]):
+            print(f"  {lab[i]:>28s}: {(v[i] - t0) / 1e3:7.2f}")
