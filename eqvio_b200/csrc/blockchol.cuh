@@ -22,16 +22,38 @@ constexpr int BC_T = 64;                 // block width of the sweep
 constexpr int BC_YROW = 21;              // pad row of the state that carries ytilde / z
 constexpr int BC_MAX_ROWS = 768;         // largest m served by this form (beyond that the trailing work dominates: sequential chunks)
 
+// What a diagonal step hands to its consumers (the next diagonal step, the panel / next-column kernels), per block k:
+//   LT = L_kk transposed, the six 16 x 16 blocks below the diagonal blocks;  XT = X_b transposed, X_b = (b-th diagonal 16 x 16 block
+//   of L_kk)^-1, b = 0..3.   P = T L_kk^-T is then a 4-stage block substitution:  P_b = (T_b - sum_{j<b} P_j L_bj^T) X_b^T.
+// Stored compactly: ten 16 x 16 blocks of 16 x BC_XLD doubles -- LT block (b, j), j < b, at index b (b - 1) / 2 + j as [k][n] =
+// L[16 b + n][16 j + k]; XT block b at index 6 + b as [k][n] = X_b[n][k]  (25.6 KB: one TMA bulk copy for every consumer).
+constexpr int BC_XLD = 20;                          // row stride of a block: 20 mod 16 = 4 -> conflict-free fragment reads
+constexpr int BC_XBLK = 16 * BC_XLD;
+constexpr size_t BC_LX = 10 * BC_XBLK;
+// Hand-over of LT | XT from diag(k) to diag(k+1) while diag(k) is still running: the build kernel fills every block with a sentinel
+// (a NaN payload no computation produces), the producer overwrites it with plain 8-byte stores as block rows become final, and the
+// consumer simply loads the fragments it needs (L2, bypassing L1) until none of them is the sentinel -- ONE round trip when the data
+// is there; a flag would cost two dependent ones (flag, then data), ~0.4 us each, in every stage.
+constexpr unsigned long long BC_SENTINEL = 0x7FF8DEADBEEF0001ull;
+__device__ __forceinline__ double bc_ld_l2(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool bc_is_sentinel(double v) { return (unsigned long long)__double_as_longlong(v) == BC_SENTINEL; }
+
 // ------------------------------------------------------------------------------------------------
 // Z build.  Tile list: lower tiles of S (i >= j), then the W tiles (w, j).  256 threads per 64 x 64 tile.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     bc_build_kernel(const double* __restrict__ Sig, int ld, int dimp, const int* __restrict__ lmOf, const double* __restrict__ Cblk,
                     const double* __restrict__ ytilde, int nm, double r2, double* __restrict__ Z, int ldz, int nT, int TW,
-                    int* __restrict__ trailCnt, const int* __restrict__ guard, int tl) {
+                    int* __restrict__ trailCnt, double* __restrict__ LxAll, const int* __restrict__ guard, int tl) {
     pdl_wait();
-    // completion counters of the trailing steps and block-row flags of the diagonal steps (see bc_diag_kernel): trailCnt[0 .. 16) | flags
-    if (blockIdx.x == 0 && threadIdx.x < 16 + 8 * nT) trailCnt[threadIdx.x] = 0;
+    // completion counters of the urgent trailing launches; sentinels in the LT | XT blocks of every diagonal step (see BC_SENTINEL)
+    if (blockIdx.x == 0 && threadIdx.x < 32) trailCnt[threadIdx.x] = 0;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < (size_t)nT * BC_LX; w += (size_t)gridDim.x * blockDim.x)
+        LxAll[w] = __longlong_as_double((long long)BC_SENTINEL);
     if (*guard) return;
     TL_MARK(tl, 0);
     __shared__ double sC[32][6];
@@ -151,11 +173,6 @@ constexpr int BC_PLD = 18;                         // doubles per published tile
 // P = T L_kk^-T is then a 4-stage block substitution on the FP64 tensor pipe:  P_b = (T_b - sum_{j<b} P_j L_bj^T) X_b^T.
 // (An explicit 64 x 64 inverse riding along the whole factorization was measured first: its 256 threads made the loop fp64-pipe
 // bound, ~1200 clocks per block column instead of ~650.)
-// Stored compactly: ten 16 x 16 blocks of 16 x BC_XLD doubles -- LT block (b, j), j < b, at index b (b - 1) / 2 + j as [k][n] =
-// L[16 b + n][16 j + k]; XT block b at index 6 + b as [k][n] = X_b[n][k]  (25.6 KB: one TMA bulk copy for every consumer).
-constexpr int BC_XLD = 20;                          // row stride of a block: 20 mod 16 = 4 -> conflict-free fragment reads
-constexpr int BC_XBLK = 16 * BC_XLD;
-constexpr size_t BC_LX = 10 * BC_XBLK;
 __host__ __device__ __forceinline__ int bc_lt_block(int b, int j) { return b * (b - 1) / 2 + j; }
 
 struct BcDiagSmem {
@@ -188,7 +205,7 @@ __device__ __forceinline__ int bc_diag_tile(int J) { return CH_NT * J - J * (J -
 // Z: augmented matrix (ldz), kblk: block column.  LxAll: per block the LT | XT pair described above.
 __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
     bc_diag_kernel(const double* __restrict__ Z, int ldz, int kblk, double* __restrict__ LxAll, int* __restrict__ status,
-                   const int* trailCnt, int waitCnt, int* lxFlag, const int* __restrict__ guard, int tl) {
+                   const int* trailCnt, int waitCnt, const int* __restrict__ guard, int tl) {
     extern __shared__ __align__(128) unsigned char bc_smem_raw[];
     BcDiagSmem& sm = *reinterpret_cast<BcDiagSmem*>(bc_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -206,7 +223,7 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
     //      completed before this grid could start (its stream predecessor, diag(k-1), was past its own dependency wait).
     //  (2) LT | XT of block k-1 come from diag(k-1), which is still RUNNING when this grid starts (programmatic launch: diag(k-1)
     //      releases its dependents once it has all of its own inputs).  It publishes them block row by block row -- block row b of
-    //      L_{k-1,k-1} is final after block column 4b+3 of its factorization -- behind lxFlag[k-1][b] (release / acquire), so three of
+    //      L_{k-1,k-1} is final after block column 4b+3 of its factorization -- over sentinel-filled blocks (BC_SENTINEL), so three of
     //      the four substitution stages below, and three quarters of D = T_kk - P P^T, run beside the previous factorization.
     if (waitCnt > 0) {
         if (tid == 0) {
@@ -278,21 +295,13 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
         }
         const int nf = warp < 4 ? 3 : 2;
         const double* Lxg = LxAll + (size_t)(kblk - 1) * BC_LX;
-        const int* flagPrev = lxFlag + 8 * (kblk - 1);  // [0, 4): LT block row b published, [4, 8): XT block b published
-        auto wait_flag = [&](const int* fp) {
-            int spins = 0, seen;
-            do {
-                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(fp) : "memory");
-            } while (seen == 0 && ++spins < (1 << 24));
-            if (seen == 0) atomicOr(status, 8);
-        };
         __syncthreads();  // T in shared memory
         BC_STAMP(2);
 #pragma unroll 1
         for (int b = 0; b < 4; ++b) {
             // warp fi < 8 owns rows 8 fi .. 8 fi + 7 of P through all stages (both 8-column fragments of a stage).  Its operands from
-            // diag(k-1) -- fragments of LT block row b, then of XT block b -- come straight from global memory (L2) into registers
-            // behind the flag of each: no staging, no CTA-wide barrier between the flag and the products.
+            // diag(k-1) -- fragments of LT block row b, then of XT block b -- come straight from L2 into registers: no staging, no
+            // CTA-wide barrier between their arrival and the products.
             if (warp < 8) {
                 const int fi = warp;
                 double q[2][2];
@@ -301,18 +310,42 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
                     q[fn][0] = -sm.A[16 * b + 8 * fn + 2 * t4][8 * fi + g];
                     q[fn][1] = -sm.A[16 * b + 8 * fn + 2 * t4 + 1][8 * fi + g];
                 }
-                if (b > 0) {
-                    wait_flag(flagPrev + b);
-                    double lf[3][4][2];  // every fragment of the block row in flight before the first product
+                const double* Xb = Lxg + (size_t)(6 + b) * BC_XBLK;
+                double xf[4][2];
+                auto load_x = [&]() {
+                    bool bad = false;
 #pragma unroll
-                    for (int jb = 0; jb < 3; ++jb)
-                        if (jb < b) {
-                            const double* Lb = Lxg + (size_t)bc_lt_block(b, jb) * BC_XBLK;
+                    for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-                                for (int fn = 0; fn < 2; ++fn) lf[jb][kk][fn] = Lb[(4 * kk + t4) * BC_XLD + 8 * fn + g];
+                        for (int fn = 0; fn < 2; ++fn) {
+                            xf[kk][fn] = bc_ld_l2(Xb + (4 * kk + t4) * BC_XLD + 8 * fn + g);
+                            bad |= bc_is_sentinel(xf[kk][fn]);
                         }
+                    return bad;
+                };
+                bool xbad = true;
+                if (b > 0) {
+                    double lf[3][4][2];  // every fragment of the block row (and, optimistically, of XT block b) in flight at once
+                    int spins = 0;
+                    bool bad;
+                    do {
+                        bad = false;
+#pragma unroll
+                        for (int jb = 0; jb < 3; ++jb)
+                            if (jb < b) {
+                                const double* Lb = Lxg + (size_t)bc_lt_block(b, jb) * BC_XBLK;
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                                    for (int fn = 0; fn < 2; ++fn) {
+                                        lf[jb][kk][fn] = bc_ld_l2(Lb + (4 * kk + t4) * BC_XLD + 8 * fn + g);
+                                        bad |= bc_is_sentinel(lf[jb][kk][fn]);
+                                    }
+                            }
+                        if (spins == 0) xbad = load_x();
+                        bad = __any_sync(0xffffffffu, bad);
+                    } while (bad && ++spins < (1 << 22));
+                    if (bad) atomicOr(status, 8);
 #pragma unroll
                     for (int jb = 0; jb < 3; ++jb)
                         if (jb < b) {
@@ -329,14 +362,13 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
                     sm.Q[8 * fn + 2 * t4][8 * fi + g] = -q[fn][0];
                     sm.Q[8 * fn + 2 * t4 + 1][8 * fi + g] = -q[fn][1];
                 }
-                wait_flag(flagPrev + 4 + b);
+                {
+                    int spins = 0;
+                    xbad = __any_sync(0xffffffffu, xbad);
+                    while (xbad && ++spins < (1 << 22)) xbad = __any_sync(0xffffffffu, load_x());
+                    if (xbad) atomicOr(status, 8);
+                }
                 if (tid == 0 && kblk == 1) BC_GT(16 + b);
-                const double* Xb = Lxg + (size_t)(6 + b) * BC_XBLK;
-                double xf[4][2];
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-                    for (int fn = 0; fn < 2; ++fn) xf[kk][fn] = Xb[(4 * kk + t4) * BC_XLD + 8 * fn + g];
                 __syncwarp();
                 double p[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
@@ -583,11 +615,7 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
             *reinterpret_cast<double2*>(p) = make_double2(b[r][0] * s0, b[r][1] * s1);
             *reinterpret_cast<double2*>(p + 2) = make_double2(b[r][2] * s2, b[r][3] * s3);
         }
-        __syncwarp(grp);
-        if (q == 0) {  // release at gpu scope: cumulative over the group's stores (ordered before it by the warp barrier)
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(lxFlag + 8 * kblk + 4 + blk), "r"(1) : "memory");
-            if (kblk == 0) BC_GT(3 + blk);
-        }
+        if (q == 0 && kblk == 0) BC_GT(3 + blk);
     } else if (warp == (BC_S_THREADS + BC_X_THREADS) / 32) {
         // ======== publisher (one of the warps that are idle during the loop): block row b of L_kk only has entries in block columns
         // < b, final once block column 4b - 1 is finished: scaled, transposed, to global memory, then its flag ========
@@ -602,8 +630,6 @@ __global__ void __launch_bounds__(BC_DIAG_THREADS, 1)
                 const double v = sm.Lp[k >> 2][4 * b + (n >> 2)][4 * (n & 3) + (k & 3)] * sm.Inv[k];
                 Ltg[(size_t)bc_lt_block(b, k >> 4) * BC_XBLK + (k & 15) * BC_XLD + n] = v;
             }
-            __syncwarp();
-            if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(lxFlag + 8 * kblk + b), "r"(1) : "memory");
         }
     }
 done:
@@ -716,12 +742,19 @@ __global__ void __launch_bounds__(128)
 //   W tiles  (w, j > k)                                                                         in Z
 //   Sigma tiles (a >= b), mirrored on the last step; column BC_YROW of the product is -dGamma, row / column BC_YROW of Sigma stay zero
 // ------------------------------------------------------------------------------------------------
-enum { BC_PART_ALL = 0, BC_PART_NEXT = 1, BC_PART_REST = 2 };  // which tiles a launch covers (the split lets the next panel start early)
-constexpr int BC_TRAIL_URGENT = 4;
+// Which trailing tiles of step k a launch covers (local tile coordinates (li, lj) relative to block k+1, q = nT - k - 1):
+//   URGENT: (1,0), (1,1) = T(k+2,k+1), T(k+2,k+2), what diag(k+2) reads            -> bc_next_kernel<4> (16-row CTAs, its own stream)
+//   NEXT  : the rest of block column k+1 (S tiles (li >= 2, 0), W tiles (w, 0)) and (2,1), (2,2), the urgent pair of the NEXT step
+//           (so that urgent(k+1) only waits for this launch, not for the long one below)            -> bc_next_kernel<2>
+//   REST  : everything else, and the Sigma tiles                                                       -> bc_trail_kernel, after panel(k)
+//   ALL   : one launch (per-kernel profile runs)
+enum { BC_PART_ALL = 0, BC_PART_NEXT = 1, BC_PART_REST = 2, BC_PART_URGENT = 3 };
+constexpr int BC_TRAIL_URGENT = 8;  // CTAs of the urgent launch (2 tiles x 4 row quarters)
 __host__ __device__ __forceinline__ int bc_trail_tiles(int part, int q, int TW) {
     const int all = (q > 0 ? q * (q + 1) / 2 - 1 : 0) + TW * q + TW * (TW + 1) / 2;
-    const int next = q >= 1 ? (q - 1) + (q >= 2 ? 1 : 0) + TW : 0;
-    return part == BC_PART_ALL ? all : part == BC_PART_NEXT ? next : all - next;
+    const int urgent = q >= 2 ? 2 : 0;
+    const int next = (q >= 3 ? (q - 2) + 2 : 0) + (q >= 1 ? TW : 0);
+    return part == BC_PART_ALL ? all : part == BC_PART_URGENT ? urgent : part == BC_PART_NEXT ? next : all - urgent - next;
 }
 __global__ void __launch_bounds__(DD_THREADS, 3)
     bc_trail_kernel(double* Z, int ldz, double* Sig, int ld, const double* __restrict__ Zp, double* Gamma, const int* __restrict__ guard,
@@ -730,7 +763,7 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
     const int bid = (int)(blockIdx.x >> 1), half = (int)(blockIdx.x & 1);
     const int q = nT - kblk - 1;  // block columns to the right of this one
     // the two tiles diag(k+2) reads, T(k+2, k+1) and T(k+2, k+2): their four CTAs count themselves off (BC_TRAIL_URGENT of them)
-    const bool urgent = part != BC_PART_REST && q >= 2 && (part == BC_PART_ALL ? bid < 2 : (bid == 0 || bid == q - 1));
+    const bool urgent = part == BC_PART_ALL && q >= 2 && bid < 2;
     if (*guard) {
         if (urgent && threadIdx.x == 0) atomicAdd(trailCnt + kblk, 1);  // diag(k+2) counts them whatever they did
         return;
@@ -755,27 +788,13 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
             kind = 2;
             tri_decode(bid - nS - TW * q, li, lj);
         }
-    } else if (part == BC_PART_NEXT) {
-        // what the next block column needs: its own tiles (lj = 0) and the diagonal tile after it
-        const int nSA = (q - 1) + (q >= 2 ? 1 : 0);  // (q - 1) tiles (li, 0), li >= 1, plus (1, 1) when it exists
-        if (bid < q - 1) {
-            kind = 0;
-            li = bid + 1;
-            lj = 0;
-        } else if (q >= 2 && bid == q - 1) {
-            kind = 0;
-            li = lj = 1;
-        } else {
-            kind = 1;
-            li = bid - nSA;
-            lj = 0;
-        }
     } else {
-        const int nSB = q >= 2 ? (q - 1) * q / 2 - 1 : 0;
+        const int skipB = q >= 3 ? 3 : (q >= 2 ? 1 : 0);  // (1,1), (2,1), (2,2) belong to the urgent / next launches
+        const int nSB = q >= 2 ? (q - 1) * q / 2 - skipB : 0;
         const int nWB = q >= 2 ? TW * (q - 1) : 0;
         if (bid < nSB) {
             kind = 0;
-            tri_decode(bid + 1, li, lj);
+            tri_decode(bid + skipB, li, lj);
             ++li;
             ++lj;
         } else if (bid < nSB + nWB) {
@@ -943,43 +962,158 @@ __device__ __forceinline__ void bc_substitute_rows(double (*P)[LD], int r0, cons
     }
 }
 
+// The same four stages with the operands taken straight from global memory as the producer publishes them (BC_SENTINEL): for the
+// followers of a diagonal step that is still running.  Returns false when a bounded wait ran out.
+template <int LD>
+__device__ __forceinline__ bool bc_substitute_rows_staged(double (*P)[LD], int r0, const double* __restrict__ Lxg, double (*Q)[BC_QLD], int g, int t4) {
+    bool ok = true;
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+        double q[2][2];
+#pragma unroll
+        for (int fn = 0; fn < 2; ++fn) {
+            q[fn][0] = -P[16 * b + 8 * fn + 2 * t4][r0 + g];
+            q[fn][1] = -P[16 * b + 8 * fn + 2 * t4 + 1][r0 + g];
+        }
+        const double* Xb = Lxg + (size_t)(6 + b) * BC_XBLK;
+        double xf[4][2];
+        auto load_x = [&]() {
+            bool bad = false;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                for (int fn = 0; fn < 2; ++fn) {
+                    xf[kk][fn] = bc_ld_l2(Xb + (4 * kk + t4) * BC_XLD + 8 * fn + g);
+                    bad |= bc_is_sentinel(xf[kk][fn]);
+                }
+            return bad;
+        };
+        bool xbad = true;
+        if (b > 0) {
+            double lf[3][4][2];
+            int spins = 0;
+            bool bad;
+            do {
+                bad = false;
+#pragma unroll
+                for (int jb = 0; jb < 3; ++jb)
+                    if (jb < b) {
+                        const double* Lb = Lxg + (size_t)bc_lt_block(b, jb) * BC_XBLK;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                            for (int fn = 0; fn < 2; ++fn) {
+                                lf[jb][kk][fn] = bc_ld_l2(Lb + (4 * kk + t4) * BC_XLD + 8 * fn + g);
+                                bad |= bc_is_sentinel(lf[jb][kk][fn]);
+                            }
+                    }
+                if (spins == 0) xbad = load_x();
+                bad = __any_sync(0xffffffffu, bad);
+            } while (bad && ++spins < (1 << 22));
+            ok &= !bad;
+#pragma unroll
+            for (int jb = 0; jb < 3; ++jb)
+                if (jb < b) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const double af = P[16 * jb + 4 * kk + t4][r0 + g];
+#pragma unroll
+                        for (int fn = 0; fn < 2; ++fn) dmma884(q[fn][0], q[fn][1], af, lf[jb][kk][fn]);
+                    }
+                }
+        }
+#pragma unroll
+        for (int fn = 0; fn < 2; ++fn) {
+            Q[8 * fn + 2 * t4][g] = -q[fn][0];
+            Q[8 * fn + 2 * t4 + 1][g] = -q[fn][1];
+        }
+        {
+            int spins = 0;
+            xbad = __any_sync(0xffffffffu, xbad);
+            while (xbad && ++spins < (1 << 22)) xbad = __any_sync(0xffffffffu, load_x());
+            ok &= !xbad;
+        }
+        __syncwarp();
+        double p[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const double af = Q[4 * kk + t4][g];
+            if (kk < 2) dmma884(p[0][0], p[0][1], af, xf[kk][0]);
+            dmma884(p[1][0], p[1][1], af, xf[kk][1]);
+        }
+#pragma unroll
+        for (int fn = 0; fn < 2; ++fn) {
+            P[16 * b + 8 * fn + 2 * t4][r0 + g] = p[fn][0];
+            P[16 * b + 8 * fn + 2 * t4 + 1][r0 + g] = p[fn][1];
+        }
+        __syncwarp();
+    }
+    return ok;
+}
+
+template <int SPLIT>  // CTAs per tile: 2 (32 rows each) or 4 (16 rows: the urgent pair, where the launch is as long as one CTA)
 __global__ void __launch_bounds__(BC_NEXT_THREADS)
-    bc_next_kernel(double* Z, int ldz, const double* __restrict__ LxAll, const int* __restrict__ guard, int kblk, int nT, int TW,
-                   int* __restrict__ trailCnt, int tl) {
-    pdl_wait();
-    const int bid = (int)(blockIdx.x >> 1), half = (int)(blockIdx.x & 1);
+    bc_next_kernel(double* Z, int ldz, const double* __restrict__ LxAll, const int* __restrict__ guard, int kblk, int nT, int TW, int part,
+                   int* trailCnt, int waitNext, int* __restrict__ status, int tl) {
+    // The urgent launch (SPLIT = 4) sits on the chain stream behind diag(k) as a programmatic dependent: it starts while diag(k) is
+    // still factoring, lets diag(k+1) in at once, never waits for diag(k) to COMPLETE -- its T tiles are final before it is launched
+    // (next(k-1) counts its CTAs off in trailCnt[16 + k-1]; polled here), and L_kk arrives block row by block row over the
+    // sentinels, as for diag(k+1).
+    constexpr bool STAGED = SPLIT == 4;
+    if (STAGED)
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    else
+        pdl_wait();
+    constexpr int ROWS = BC_T / SPLIT, RF = ROWS / 8, CW = 8 / RF, NB = 8 / CW;
+    const int bid = (int)(blockIdx.x / SPLIT), half = (int)(blockIdx.x % SPLIT);
     const int q = nT - kblk - 1;
-    const bool urgent = q >= 2 && (bid == 0 || bid == q - 1);  // T(k+2, k+1), T(k+2, k+2): what diag(k+2) waits for
+    const bool urgent = part == BC_PART_URGENT;  // T(k+2, k+1), T(k+2, k+2): what diag(k+2) waits for
     if (*guard) {
-        if (urgent && threadIdx.x == 0) atomicAdd(trailCnt + kblk, 1);
+        if (threadIdx.x == 0) atomicAdd(trailCnt + (urgent ? 0 : 16) + kblk, 1);
         return;
+    }
+    if (STAGED && waitNext > 0) {
+        if (threadIdx.x == 0) {
+            int spins = 0, seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(trailCnt + 16 + (kblk - 1)) : "memory");
+            } while (seen < waitNext && ++spins < (1 << 24));
+            if (seen < waitNext) atomicOr(status, 8);
+        }
+        __syncthreads();
     }
     TL_MARK(tl, 0);
     int ta, tb;
-    const int nSA = (q - 1) + (q >= 2 ? 1 : 0);
-    if (bid < q - 1) {
-        ta = kblk + 2 + bid;
-        tb = kblk + 1;
-    } else if (q >= 2 && bid == q - 1) {
-        ta = tb = kblk + 2;
+    if (urgent) {
+        ta = kblk + 2;
+        tb = bid == 0 ? kblk + 1 : kblk + 2;
     } else {
-        ta = nT + (bid - nSA);
-        tb = kblk + 1;
+        const int nS1 = q >= 3 ? q - 2 : 0;
+        if (bid < nS1) {
+            ta = kblk + 3 + bid;
+            tb = kblk + 1;
+        } else if (q >= 3 && bid < nS1 + 2) {
+            ta = kblk + 3;
+            tb = bid == nS1 ? kblk + 2 : kblk + 3;
+        } else {
+            ta = nT + (bid - nS1 - (q >= 3 ? 2 : 0));
+            tb = kblk + 1;
+        }
     }
     extern __shared__ __align__(128) unsigned char bcn_smem_raw[];
     BcNextSmem& sm = *reinterpret_cast<BcNextSmem*>(bcn_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
-    if (tid == 0) {
+    if (!STAGED && tid == 0) {
         mbar_init(&sm.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(&sm.bar, (uint32_t)(BC_LX * 8));
         bulk_g2s(&sm.LX[0][0][0], LxAll + (size_t)kblk * BC_LX, (uint32_t)(BC_LX * 8), &sm.bar);
     }
     const double* Tb = Z + (size_t)(kblk * BC_T) * ldz + (size_t)tb * BC_T;
-    const double* Ta = Z + (size_t)(kblk * BC_T) * ldz + (size_t)ta * BC_T + 32 * half;
+    const double* Ta = Z + (size_t)(kblk * BC_T) * ldz + (size_t)ta * BC_T + ROWS * half;
     {
-        // 2048 + 1024 16-byte words: every load of a thread in flight before its first store (a load -> store loop pays one L2 round
+        // 2048 + 32 ROWS 16-byte words: every load of a thread in flight before its first store (a load -> store loop pays one L2 round
         // trip per iteration: 3 us of the launch)
         double2 vb[6], va[3];
 #pragma unroll
@@ -990,7 +1124,7 @@ __global__ void __launch_bounds__(BC_NEXT_THREADS)
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
             const int w = tid + BC_NEXT_THREADS * u;
-            if (w < BC_T * 16) va[u] = *reinterpret_cast<const double2*>(Ta + (size_t)(w >> 4) * ldz + (w & 15) * 2);
+            if (w < BC_T * (ROWS / 2)) va[u] = *reinterpret_cast<const double2*>(Ta + (size_t)(w / (ROWS / 2)) * ldz + (w % (ROWS / 2)) * 2);
         }
 #pragma unroll
         for (int u = 0; u < 6; ++u) {
@@ -1000,46 +1134,54 @@ __global__ void __launch_bounds__(BC_NEXT_THREADS)
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
             const int w = tid + BC_NEXT_THREADS * u;
-            if (w < BC_T * 16) *reinterpret_cast<double2*>(&sm.Pa[w >> 4][(w & 15) * 2]) = va[u];
+            if (w < BC_T * (ROWS / 2)) *reinterpret_cast<double2*>(&sm.Pa[w / (ROWS / 2)][(w % (ROWS / 2)) * 2]) = va[u];
         }
     }
     // the tile itself, straight into the accumulator fragments of warps 0-7: rows wm .. wm+7 of this half, columns wn .. wn+31
-    const int wm = (warp >> 1) * 8, wn = (warp & 1) * 32;
-    double* cbase = Z + (size_t)((kblk + 1 + (tb - kblk - 1)) * BC_T + wn + 2 * t4) * ldz + (size_t)ta * BC_T + 32 * half + wm + g;
-    double acc[4][2];
+    const int wm = (warp / CW) * 8, wn = (warp % CW) * (BC_T / CW);
+    double* cbase = Z + (size_t)(tb * BC_T + wn + 2 * t4) * ldz + (size_t)ta * BC_T + ROWS * half + wm + g;
+    double acc[NB][2];
     if (warp < 8) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < NB; ++b) {
             acc[b][0] = -cbase[(size_t)(b * 8) * ldz];
             acc[b][1] = -cbase[(size_t)(b * 8 + 1) * ldz];
         }
     }
     __syncthreads();
-    mbar_wait(&sm.bar, 0);
-    if (warp < 8)
-        bc_substitute_rows<YB_LD>(sm.Pb, 8 * warp, sm.LX, sm.Q[warp], g, t4);
-    else
-        bc_substitute_rows<BC_PA_LD>(sm.Pa, 8 * (warp - 8), sm.LX, sm.Q[warp], g, t4);
+    if (STAGED) {
+        const double* Lxg = LxAll + (size_t)kblk * BC_LX;
+        bool ok = true;
+        if (warp < 8)
+            ok = bc_substitute_rows_staged<YB_LD>(sm.Pb, 8 * warp, Lxg, sm.Q[warp], g, t4);
+        else if (warp < 8 + RF)
+            ok = bc_substitute_rows_staged<BC_PA_LD>(sm.Pa, 8 * (warp - 8), Lxg, sm.Q[warp], g, t4);
+        if (!ok) atomicOr(status, 8);
+    } else {
+        mbar_wait(&sm.bar, 0);
+        if (warp < 8)
+            bc_substitute_rows<YB_LD>(sm.Pb, 8 * warp, sm.LX, sm.Q[warp], g, t4);
+        else if (warp < 8 + RF)
+            bc_substitute_rows<BC_PA_LD>(sm.Pa, 8 * (warp - 8), sm.LX, sm.Q[warp], g, t4);
+    }
     __syncthreads();
     if (warp < 8) {
 #pragma unroll 4
         for (int k4 = 0; k4 < BC_T; k4 += 4) {
             const double af = sm.Pa[k4 + t4][wm + g];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) dmma884(acc[b][0], acc[b][1], af, sm.Pb[k4 + t4][wn + 8 * b + g]);
+            for (int b = 0; b < NB; ++b) dmma884(acc[b][0], acc[b][1], af, sm.Pb[k4 + t4][wn + 8 * b + g]);
         }
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < NB; ++b) {
             cbase[(size_t)(b * 8) * ldz] = -acc[b][0];
             cbase[(size_t)(b * 8 + 1) * ldz] = -acc[b][1];
         }
     }
-    if (urgent) {
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            atomicAdd(trailCnt + kblk, 1);
-        }
+    __syncthreads();
+    if (tid == 0) {  // urgent: diag(k+2) counts these; next: urgent(k+1) does
+        __threadfence();
+        atomicAdd(trailCnt + (urgent ? 0 : 16) + kblk, 1);
     }
     TL_MARK(tl, 1);
 }

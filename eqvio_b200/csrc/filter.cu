@@ -74,7 +74,7 @@ struct eqvio_filter {
     double* d_xi0s = nullptr;
     double* d_Xs[2] = {nullptr, nullptr};  // X sensor part, ping-pong across the observer integration
     int xcur = 0;
-    cudaStream_t stream4 = nullptr;  // block sweep: panel / next-column trailing tiles
+    cudaStream_t stream4 = nullptr, stream5 = nullptr;  // block sweep: next-column trailing tiles / the urgent pair
     cudaStream_t stream3 = nullptr;  // low priority: deferred downdate tiles of the look-ahead correction
     cudaStream_t stream2 = nullptr;  // observer chain of the propagation runs beside the Riccati chain
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
@@ -491,6 +491,7 @@ int alloc_device(eqvio_filter* f) {
         CUDA_TRY(f, cudaStreamCreateWithPriority(&f->stream2, cudaStreamNonBlocking, prGreatest));
         CUDA_TRY(f, cudaStreamCreateWithPriority(&f->stream3, cudaStreamNonBlocking, prLeast));
         CUDA_TRY(f, cudaStreamCreateWithPriority(&f->stream4, cudaStreamNonBlocking, prGreatest));
+        CUDA_TRY(f, cudaStreamCreateWithPriority(&f->stream5, cudaStreamNonBlocking, prGreatest));
     }
     CUDA_TRY(f, cudaEventCreateWithFlags(&f->evFork, cudaEventDisableTiming));
     CUDA_TRY(f, cudaEventCreateWithFlags(&f->evJoin, cudaEventDisableTiming));
@@ -1406,32 +1407,30 @@ int enqueue_block_sweep(eqvio_filter* f, int nm, int dimp, double r2, const int*
     const int ldy = (dimp + BC_T - 1) / BC_T * BC_T, TW = ldy / BC_T;
     const int ldz = nT * BC_T + ldy;
     const bool serial = f->profiling;
-    // A: build + diagonal chain; B: panel(k), then the trailing tiles the next block column needs; C: the other trailing tiles
+    // A: build + diagonal chain; D: the two tiles diag(k+2) reads; B: the other tiles of the next block column; C: panel(k), the rest
     cudaStream_t sA = f->stream, sB = serial ? f->stream : f->stream4, sC = serial ? f->stream : f->stream3;
-    while ((int)f->bcEv.size() < 3 * nT + 1) {
+    while ((int)f->bcEv.size() < 4 * nT + 1) {
         cudaEvent_t e;
         CUDA_TRY(f, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         f->bcEv.push_back(e);
     }
-    auto evDiag = [&](int k) { return f->bcEv[3 * k]; };
-    auto evPanel = [&](int k) { return f->bcEv[3 * k + 1]; };
-    auto evRest = [&](int k) { return f->bcEv[3 * k + 2]; };
+    auto evDiag = [&](int k) { return f->bcEv[4 * k]; };
+    auto evNext = [&](int k) { return f->bcEv[4 * k + 1]; };
+    auto evRest = [&](int k) { return f->bcEv[4 * k + 2]; };
+    auto evUrg = [&](int k) { return f->bcEv[4 * k + 3]; };
     const size_t zpElems = (size_t)(nT + TW) * YB_TILE;  // panels ping-pong: rest(k) still reads Zp(k) while panel(k+1) writes
     launch_pdl(f, bc_build_kernel, dim3(nT * (nT + 1) / 2 + TW * nT), dim3(256), (size_t)0, sA, (const double*)f->Sig[f->cur], f->ld, dimp,
-               (const int*)f->d_lmOf, (const double*)f->d_Cblk, (const double*)f->d_ytilde, nm, r2, f->d_bcZ, ldz, nT, TW, f->d_bcCnt, guard, TL_SLOT(f));
+               (const int*)f->d_lmOf, (const double*)f->d_Cblk, (const double*)f->d_ytilde, nm, r2, f->d_bcZ, ldz, nT, TW, f->d_bcCnt, f->d_bcMt, guard, TL_SLOT(f));
     LAUNCH_CHECK(f, "bc_build_kernel");
     for (int k = 0; k < nT; ++k) {
         // diag(k) needs two tiles of the trailing step k-2: counted off on the device (bc_diag_kernel), not an event edge into the chain
         const int waitCnt = (!serial && k >= 2) ? BC_TRAIL_URGENT : 0;
         int pk = prof_begin(f, PROF_PANEL);
         launch_pdl(f, bc_diag_kernel, dim3(1), dim3(BC_DIAG_THREADS), (size_t)BC_DIAG_SMEM, sA, (const double*)f->d_bcZ, ldz, k, f->d_bcMt, f->d_status,
-                   (const int*)f->d_bcCnt, waitCnt, f->d_bcCnt + 16, guard, TL_SLOT(f));
+                   (const int*)f->d_bcCnt, waitCnt, guard, TL_SLOT(f));
         prof_end(f, pk);
         LAUNCH_CHECK(f, "bc_diag_kernel");
-        if (!serial) {
-            CUDA_TRY(f, cudaEventRecord(evDiag(k), sA));
-            CUDA_TRY(f, cudaStreamWaitEvent(sB, evDiag(k), 0));
-        }
+        if (!serial) CUDA_TRY(f, cudaEventRecord(evDiag(k), sA));
         double* Zp = f->d_bcZp + (size_t)(k & 1) * zpElems;
         const int below = nT + TW - k - 1;  // row tiles under the diagonal block (S, then W)
         const int q = nT - k - 1;
@@ -1447,17 +1446,31 @@ int enqueue_block_sweep(eqvio_filter* f, int nm, int dimp, double r2, const int*
             prof_end(f, sk);
             LAUNCH_CHECK(f, "bc_trail_kernel");
         } else {
-            // B: the tiles block column k+1 (and diag(k+2)) needs, panels substituted inside the launch
-            const int nNext = bc_trail_tiles(BC_PART_NEXT, q, TW);
-            if (nNext > 0) {
-                if (k >= 1) CUDA_TRY(f, cudaStreamWaitEvent(sB, evRest(k - 1), 0));  // rest(k-1) wrote the same tiles (step k-1)
-                bc_next_kernel<<<2 * nNext, BC_NEXT_THREADS, BC_NEXT_SMEM, sB>>>(f->d_bcZ, ldz, f->d_bcMt, guard, k, nT, TW, f->d_bcCnt, TL_SLOT(f));
-                LAUNCH_CHECK(f, "bc_next_kernel");
-                CUDA_TRY(f, cudaEventRecord(evPanel(k), sB));
+            const int nUrg = bc_trail_tiles(BC_PART_URGENT, q, TW), nNext = bc_trail_tiles(BC_PART_NEXT, q, TW);
+            // chain stream, behind diag(k) as a programmatic dependent: T(k+2,k+1), T(k+2,k+2) -- their step k-1 came from next(k-1)
+            if (nUrg > 0) {
+                const int waitNext = k >= 1 ? 2 * bc_trail_tiles(BC_PART_NEXT, q + 1, TW) : 0;  // CTAs of next(k-1), counted off on the device
+                launch_pdl(f, bc_next_kernel<4>, dim3(4 * nUrg), dim3(BC_NEXT_THREADS), (size_t)BC_NEXT_SMEM, sA, f->d_bcZ, ldz, (const double*)f->d_bcMt, guard, k,
+                           nT, TW, (int)BC_PART_URGENT, f->d_bcCnt, waitNext, f->d_status, TL_SLOT(f));
+                LAUNCH_CHECK(f, "bc_next_kernel<urgent>");
+                CUDA_TRY(f, cudaEventRecord(evUrg(k), sA));
             }
-            // C: panels of every row tile, then all the other trailing tiles
+            // B: the rest of block column k+1 and the urgent pair of step k+1 -- their step k-1 came from rest(k-1)
+            if (nNext > 0) {
+                CUDA_TRY(f, cudaStreamWaitEvent(sB, evDiag(k), 0));
+                if (k >= 1) CUDA_TRY(f, cudaStreamWaitEvent(sB, evRest(k - 1), 0));
+                bc_next_kernel<2><<<2 * nNext, BC_NEXT_THREADS, BC_NEXT_SMEM, sB>>>(f->d_bcZ, ldz, f->d_bcMt, guard, k, nT, TW, (int)BC_PART_NEXT, f->d_bcCnt,
+                                                                                  0, f->d_status, TL_SLOT(f));
+                LAUNCH_CHECK(f, "bc_next_kernel");
+                CUDA_TRY(f, cudaEventRecord(evNext(k), sB));
+            }
+            // C: panels of every row tile (block column k is current through step k-1 after next(k-1) and urgent(k-1)), then all
+            // the other trailing tiles
             CUDA_TRY(f, cudaStreamWaitEvent(sC, evDiag(k), 0));
-            if (k >= 1) CUDA_TRY(f, cudaStreamWaitEvent(sC, evPanel(k - 1), 0));  // block column k is current through step k-1
+            if (k >= 1) {
+                if (bc_trail_tiles(BC_PART_NEXT, q + 1, TW) > 0) CUDA_TRY(f, cudaStreamWaitEvent(sC, evNext(k - 1), 0));
+                if (bc_trail_tiles(BC_PART_URGENT, q + 1, TW) > 0) CUDA_TRY(f, cudaStreamWaitEvent(sC, evUrg(k - 1), 0));
+            }
             bc_panel_kernel<<<2 * below, 128, BC_PANEL_SMEM, sC>>>(f->d_bcZ, ldz, k, f->d_bcMt, Zp, guard, TL_SLOT(f));
             LAUNCH_CHECK(f, "bc_panel_kernel");
             bc_trail_kernel<<<2 * bc_trail_tiles(BC_PART_REST, q, TW), DD_THREADS, DD_SMEM, sC>>>(f->d_bcZ, ldz, f->Sig[f->cur], f->ld, Zp, f->d_Gamma, guard, k,
@@ -1468,9 +1481,13 @@ int enqueue_block_sweep(eqvio_filter* f, int nm, int dimp, double r2, const int*
         }
     }
     if (!serial) {
-        CUDA_TRY(f, cudaEventRecord(f->bcEv[3 * nT], sB));
-        CUDA_TRY(f, cudaStreamWaitEvent(sA, f->bcEv[3 * nT], 0));
+        // everything joins the chain again: the last rest launch follows every next / urgent launch through the waits above, except
+        // the ones of the last two steps
         CUDA_TRY(f, cudaStreamWaitEvent(sA, evRest(nT - 1), 0));
+        for (int k = std::max(0, nT - 3); k < nT; ++k) {
+            const int q = nT - k - 1;
+            if (bc_trail_tiles(BC_PART_NEXT, q, TW) > 0) CUDA_TRY(f, cudaStreamWaitEvent(sA, evNext(k), 0));
+        }
     }
     return EQVIO_OK;
 }
@@ -1820,7 +1837,8 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
     if (e == cudaSuccess) e = cudaFuncSetAttribute(bc_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_DIAG_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(bc_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_PANEL_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(bc_trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(bc_next_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_NEXT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(bc_next_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_NEXT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(bc_next_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_NEXT_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ChunkSmem) > (size_t)CH_SMEM_STAGED ? sizeof(ChunkSmem) : (size_t)CH_SMEM_STAGED));
     if (e != cudaSuccess) {
         g_createError = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
@@ -2047,6 +2065,7 @@ void eqvio_destroy(eqvio_filter* f) {
     if (f->stream2) cudaStreamDestroy(f->stream2);
     if (f->stream3) cudaStreamDestroy(f->stream3);
     if (f->stream4) cudaStreamDestroy(f->stream4);
+    if (f->stream5) cudaStreamDestroy(f->stream5);
     if (f->evFork) cudaEventDestroy(f->evFork);
     if (f->evJoin) cudaEventDestroy(f->evJoin);
     cudaFree(f->d_ctx);
