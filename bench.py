@@ -116,13 +116,23 @@ def alg_counts(N, n, chunk_rows=64):
     dim, m = 21 + 3 * N, 2 * n
     chunks = [min(chunk_rows, m - r0) for r0 in range(0, m, chunk_rows)]
     factor_flops = sum(r ** 3 / 3.0 + float(r) * r * dim for r in chunks)
+    # block sweep (eqvio_b200/csrc/blockchol.cuh, the default up to 768 rows): 64-row blocks over [S; W^T], W padded to 64-row tiles.
+    # Per block k with q = nT - k - 1 blocks to its right and TW tiles of W: diagonal step 64^3 / 3 (factorization) + 2 * 64^3 / 2
+    # (look-ahead substitution + symmetric product); panels (q + TW) tiles x 64^3 (substitution, triangular: half of a full
+    # product); trailing tiles (q (q + 1) / 2 + TW q + TW (TW + 1) / 2) x 2 * 64^3.  Flops = 2 x FMA.
+    nT, TW, b3 = -(-m // 64), -(-(24 + 3 * N) // 64), 64.0 ** 3
+    bc_diag = sum(b3 / 3.0 + (b3 if k > 0 else 0.0) for k in range(nT))
+    bc_panel = sum((nT - k - 1 + TW) * b3 for k in range(nT))
+    bc_trail = sum(((nT - k - 1) * (nT - k) / 2.0 + TW * (nT - k - 1) + TW * (TW + 1) / 2.0) * 2.0 * b3 for k in range(nT))
+    block = m <= 768
     return dict(
+        block_sweep=block, bc_diag_flops=bc_diag, bc_panel_flops=bc_panel, bc_trail_flops=bc_trail, blocks=nT,
         dim=dim, m=m, chunks=len(chunks),
         syrk_flops=float(dim) * dim * m,
         factor_flops=factor_flops,
         trail_flops=float(m) * m * m / 3 + float(m) * m * dim,  # batch sweep only (Cholesky of S + trsm of W)
         prop_bytes=2.0 * 8 * dim * dim,  # read + write Sigma once
-        upd_flops=float(dim) * dim * m + 72.0 * dim * dim + factor_flops,
+        upd_flops=(bc_diag + bc_panel + bc_trail if block else float(dim) * dim * m + factor_flops) + 72.0 * dim * dim,
         upd_bytes=8.0 * (4 * dim * dim + 4 * m * dim))
 
 
@@ -284,6 +294,15 @@ def kernel_rooflines(prof, nprof, cnt, N, hbm_peak, f64_peak, traffic, tc=False,
         elif name == "chunk_factor":
             e.update(bound="tensor", achieved=cnt["factor_flops"] / (ms * 1e-3) / 1e12, peak=f64_peak, unit="TFLOP/s",
                      note="latency-bound: a chain of 64 dependent pivots per launch; the fraction is of the fp64 (DGEMM) peak")
+        elif name == "bc_diag":
+            e.update(bound="tensor", achieved=cnt["bc_diag_flops"] / (ms * 1e-3) / 1e12, peak=f64_peak, unit="TFLOP/s",
+                     note="latency-bound: the chain of 64 dependent pivots per block (plus the look-ahead products on one SM); the "
+                     "fraction is of the fp64 (DGEMM) peak.  Event-bracketed launches of the per-kernel profile run one after the "
+                     "other: in the timed steps consecutive diagonal steps overlap (see DESIGN.md 4)")
+        elif name == "bc_panel":
+            e.update(bound="tensor", achieved=cnt["bc_panel_flops"] / (ms * 1e-3) / 1e12, peak=f64_peak, unit="TFLOP/s")
+        elif name == "bc_trail":
+            e.update(bound="tensor", achieved=cnt["bc_trail_flops"] / (ms * 1e-3) / 1e12, peak=f64_peak, unit="TFLOP/s")
         elif name == "chol_trail":
             e.update(bound="tensor", achieved=cnt["trail_flops"] / (ms * 1e-3) / 1e12, peak=f64_peak, unit="TFLOP/s")
         elif name == "prop_ll":
@@ -644,8 +663,10 @@ def run_b200(args, rank, local_rank, world, guard):
                             dominant_by_time=dom, kernels=kern,
                             profile_stage_ms={k_: v / max(m["nprof"], 1) for k_, v in m["prof_stage"].items()},
                             update=dict(flops=cnt["upd_flops"], bytes=cnt["upd_bytes"], chunks=cnt["chunks"],
-                                        flops_note="flops the sequential-chunk algorithm executes: m dim^2 + 72 dim^2 + sum over chunks "
-                                        "(r^3 / 3 + r^2 dim)",
+                                        flops_note=("flops the block sweep executes (blockchol.cuh: diagonal steps + panels + trailing tiles of "
+                                                    "[S; W^T] and Sigma, 64-row tiles) + 72 dim^2 of the propagation" if cnt["block_sweep"] else
+                                                    "flops the sequential-chunk algorithm executes: m dim^2 + 72 dim^2 + sum over chunks "
+                                                    "(r^3 / 3 + r^2 dim)"),
                                         flops_frac=cnt["upd_flops"] * K * R / (dev_ms / 1e3) / 1e12 / f64_tflops,
                                         hbm_frac=cnt["upd_bytes"] * K * R / (dev_ms / 1e3) / 1e9 / hbm_peak))
         value = world * R * K / (dev_ms_max * 1e-3)

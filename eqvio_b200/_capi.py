@@ -30,8 +30,8 @@ ERROR_NAMES = {
     EQVIO_ERR_CAPACITY: "EQVIO_ERR_CAPACITY",
     EQVIO_ERR_UNSUPPORTED: "EQVIO_ERR_UNSUPPORTED",
 }
-PROF_CLASSES = 4
-PROF_NAMES = ("prop_ll", "chunk_factor", "chol_trail", "downdate")
+PROF_CLASSES = 7
+PROF_NAMES = ("prop_ll", "chunk_factor", "chol_trail", "downdate", "bc_diag", "bc_panel", "bc_trail")
 
 _D = C.c_double
 _I = C.c_int

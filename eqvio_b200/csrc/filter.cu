@@ -38,7 +38,8 @@ struct ImuSample {
     double v[12];  // gyr, acc, gyrBiasVel, accBiasVel
 };
 
-enum { PROF_PROP_LL = 0, PROF_PANEL, PROF_TRAIL, PROF_SYRK, PROF_CLASSES };
+enum { PROF_PROP_LL = 0, PROF_PANEL, PROF_TRAIL, PROF_SYRK, PROF_BC_DIAG, PROF_BC_PANEL, PROF_BC_TRAIL, PROF_CLASSES };
+static_assert(PROF_CLASSES == EQVIO_PROF_CLASSES, "profile classes of the header");
 
 struct EventPair {
     cudaEvent_t a, b;
@@ -176,8 +177,8 @@ struct eqvio_filter {
     bool profiling = false;
     std::vector<EventPair> evPool;
     size_t evUsed = 0;
-    double profMs[PROF_CLASSES] = {0, 0, 0, 0};
-    long long profLaunches[PROF_CLASSES] = {0, 0, 0, 0};
+    double profMs[PROF_CLASSES] = {};
+    long long profLaunches[PROF_CLASSES] = {};
 
     // scratch of a process_vision call split in phases (batch API)
     struct Pending {
@@ -1425,7 +1426,7 @@ int enqueue_block_sweep(eqvio_filter* f, int nm, int dimp, double r2, const int*
     for (int k = 0; k < nT; ++k) {
         // diag(k) needs two tiles of the trailing step k-2: counted off on the device (bc_diag_kernel), not an event edge into the chain
         const int waitCnt = (!serial && k >= 2) ? BC_TRAIL_URGENT : 0;
-        int pk = prof_begin(f, PROF_PANEL);
+        int pk = prof_begin(f, PROF_BC_DIAG);
         launch_pdl(f, bc_diag_kernel, dim3(1), dim3(BC_DIAG_THREADS), (size_t)BC_DIAG_SMEM, sA, (const double*)f->d_bcZ, ldz, k, f->d_bcMt, f->d_status,
                    (const int*)f->d_bcCnt, waitCnt, guard, TL_SLOT(f));
         prof_end(f, pk);
@@ -1435,11 +1436,11 @@ int enqueue_block_sweep(eqvio_filter* f, int nm, int dimp, double r2, const int*
         const int below = nT + TW - k - 1;  // row tiles under the diagonal block (S, then W)
         const int q = nT - k - 1;
         if (serial) {
-            int tk = prof_begin(f, PROF_TRAIL);
+            int tk = prof_begin(f, PROF_BC_PANEL);
             bc_panel_kernel<<<2 * below, 128, BC_PANEL_SMEM, sB>>>(f->d_bcZ, ldz, k, f->d_bcMt, Zp, guard, TL_SLOT(f));
             prof_end(f, tk);
             LAUNCH_CHECK(f, "bc_panel_kernel");
-            int sk = prof_begin(f, PROF_SYRK);
+            int sk = prof_begin(f, PROF_BC_TRAIL);
             bc_trail_kernel<<<2 * bc_trail_tiles(BC_PART_ALL, q, TW), DD_THREADS, DD_SMEM, sB>>>(f->d_bcZ, ldz, f->Sig[f->cur], f->ld, Zp, f->d_Gamma, guard, k,
                                                                                                nT, TW, dimp, k == nT - 1 ? 1 : 0, (int)BC_PART_ALL,
                                                                                                f->d_bcCnt, TL_SLOT(f));

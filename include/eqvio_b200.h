@@ -200,7 +200,10 @@ int eqvio_get_graph_stats(const eqvio_filter* f, long long* captures, long long*
 #define EQVIO_PROF_PANEL 1   /* chunk factorisation + solve (batch mode: panel of the Cholesky sweep) */
 #define EQVIO_PROF_TRAIL 2   /* batch mode only: trailing update of the sweep (FP64 tensor-core GEMM) */
 #define EQVIO_PROF_SYRK 3    /* Sigma downdate Sigma -= Y^T Y (FP64 tensor cores, DMMA) */
-#define EQVIO_PROF_CLASSES 4
+#define EQVIO_PROF_BC_DIAG 4  /* block sweep: diagonal step (look-ahead products + 64 x 64 factorization), the critical chain */
+#define EQVIO_PROF_BC_PANEL 5 /* block sweep: panels P = T L^-T (DMMA block substitution) */
+#define EQVIO_PROF_BC_TRAIL 6 /* block sweep: trailing tiles of S / W and the Sigma downdate (DMMA) */
+#define EQVIO_PROF_CLASSES 7
 int eqvio_enable_kernel_profile(eqvio_filter* f, int on);
 /* Accumulated ms and launch counts per class since the last reset. */
 int eqvio_get_kernel_profile(eqvio_filter* f, int reset, double ms[EQVIO_PROF_CLASSES],
