@@ -81,6 +81,10 @@ def parse():
     ap.add_argument("--landmarks", type=int, default=256)
     ap.add_argument("--coord", type=int, default=0)
     ap.add_argument("--sequences-per-gpu", type=int, default=1, help="independent sequences (replicas) run concurrently per GPU")
+    ap.add_argument("--batched-correction", type=int, default=0, choices=[0, 2],
+                    help="correction form of the batched leg's filters: 0 = sequential chunks (default there: with 16 sequences "
+                         "sharing one GPU the throughput is bound by SM occupancy, and the block sweep's followers hold SMs while they "
+                         "wait for their diagonal step), 2 = block sweep (the single-sequence default)")
     ap.add_argument("--batched-sequences", type=int, default=16,
                     help="extra leg: this many independent NOISY sequences per GPU replayed concurrently (BASELINE configs[4]: 16 "
                          "Monte-Carlo instances per GPU), reported as \"batched\"; 0 = skip")
@@ -471,6 +475,7 @@ def batched_leg(eb, args, N, B, Kb, Wb, device, first_instance):
                           0.0, capacity=N + 8, device=device)
         if args.no_graph:
             bf.setTuning(graph=0)
+        bf.setTuning(correction=args.batched_correction)
         filters.append(bf)
     eb.replayBatch(filters, [sm_.frames[:1 + Wb] for sm_ in streams], cam)  # t = 0 image + warm-up (graph capture)
     l0 = sum(f_.launchCount() for f_ in filters)
@@ -618,6 +623,7 @@ def run_b200(args, rank, local_rank, world, guard):
             assert bool(torch.isfinite(torch.stack(parts)).all())
         wall_max = float(tb[0])
         batched = dict(sequences_per_gpu=B, sequences=B * world, steps_per_sequence=Kb, noisy=True,
+                       correction=("sequential chunks (EQVIO_TUNE_CORRECTION=0)" if args.batched_correction == 0 else "block sweep"),
                        value=world * upd_b / ((wall_max + gather_ms) * 1e-3), unit="updates/s", ms_per_batch_step=wall_max / Kb,
                        pose_gather_ms=gather_ms, gpu_launches=launch_b,
                        timing="max over ranks of the host wall clock over the batch (host buffers in, state estimates out: the e2e "

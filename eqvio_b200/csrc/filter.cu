@@ -87,6 +87,10 @@ struct eqvio_filter {
     unsigned char* hd_frame = nullptr;  // device-side address of the pinned frame block (zero-copy upload kernel)
     unsigned char* hd_out = nullptr;    // ... of the pinned result block
     int zeroCopy = 1;                   // frame / result blocks move through block_copy_kernel instead of memcpy nodes
+    int prefetchSigma = 1;              // the frame upload kernel also prefetches the covariance into L2
+    int earlyRows = 1;                  // steady block-sweep frames: measurement rows right behind the observer, gate beside the sweep
+    int measHookNm = 0;                 // > 0: enqueue_propagation launches the measurement rows on the observer's stream
+    cudaEvent_t evG0 = nullptr, evGate = nullptr;
     int splitDowndate = 1;              // two CTAs per Sigma tile when the whole downdate is a single wave
     size_t frameBytes = 0, offImu = 0, offY = 0, offMeasIdx = 0, offLmOf = 0, offYIdx = 0;
     int* d_yIdx = nullptr;
@@ -496,6 +500,8 @@ int alloc_device(eqvio_filter* f) {
     }
     CUDA_TRY(f, cudaEventCreateWithFlags(&f->evFork, cudaEventDisableTiming));
     CUDA_TRY(f, cudaEventCreateWithFlags(&f->evJoin, cudaEventDisableTiming));
+    CUDA_TRY(f, cudaEventCreateWithFlags(&f->evG0, cudaEventDisableTiming));
+    CUDA_TRY(f, cudaEventCreateWithFlags(&f->evGate, cudaEventDisableTiming));
     CUDA_TRY(f, cudaMalloc(&f->d_ctx, sizeof(RiccatiCtx)));
     {
         int rcf = alloc_frame(f, 64, std::max(cap, 1));
@@ -760,6 +766,15 @@ int enqueue_propagation(eqvio_filter* f) {
             LAUNCH_CHECK(f, "observer_landmark_kernel");
         }
     }
+    if (f->measHookNm > 0 && N > 0) {
+        // C*, ytilde of the measured landmarks only read the landmarks the observer just integrated: right behind it on its stream,
+        // beside the Riccati chain (the gate, which also needs the propagated Sigma, runs beside the sweep: enqueue_correction)
+        const int nm = f->measHookNm;
+        meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream2>>>(f->lm[1 - f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
+                                                           s.useEquivariantOutput ? 1 : 0, f->d_Cblk, f->d_ytilde, 1, 0, (const int*)(f->d_spec + 1),
+                                                           f->d_yIdx, f->d_status, 1 + N, f->d_Gamma, dimp_of(N), (int*)nullptr, 0, TL_SLOT(f));
+        LAUNCH_CHECK(f, "meas_kernel");
+    }
     CUDA_TRY(f, cudaEventRecord(f->evJoin, f->stream2));
     {
         const double* Sin = f->Sig[f->cur];
@@ -922,7 +937,7 @@ int enqueue_gate(eqvio_filter* f, int N, bool clearFlag) {
     return EQVIO_OK;
 }
 
-int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate = false, bool fuseEst = false);
+int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate = false, bool fuseEst = false, bool lateGate = false);
 struct FramePlan;
 
 // The whole device side of a steady frame (no landmark enters or leaves before the gate): frame upload,
@@ -938,17 +953,25 @@ int enqueue_steady_update(eqvio_filter* f, int N, int nm, const FramePlan* plan)
     const eqvio_settings& s = f->st;
     const bool zc = f->zeroCopy && f->hd_frame && f->hd_out;
     if (zc) {
-        block_copy_kernel<<<2, 256, 0, f->stream>>>(reinterpret_cast<const double2*>(f->hd_frame), reinterpret_cast<double2*>(f->d_frame),
-                                                    (int)(f->frameBytes / 16), TL_SLOT(f));
+        // + prefetch of the covariance (the rows in use) into L2 beside the copy
+        const size_t pfBytes = f->prefetchSigma ? (size_t)f->ld * dimp_of(N) * sizeof(double) : 0;
+        block_copy_kernel<<<2 + (pfBytes ? 64 : 0), 256, 0, f->stream>>>(reinterpret_cast<const double2*>(f->hd_frame), reinterpret_cast<double2*>(f->d_frame),
+                                                                        (int)(f->frameBytes / 16), 2, reinterpret_cast<const char*>(f->Sig[f->cur]), pfBytes,
+                                                                        TL_SLOT(f));
         LAUNCH_CHECK(f, "block_copy_kernel<frame>");
     } else {
         CUDA_TRY(f, cudaMemcpyAsync(f->d_frame, f->h_frame, f->frameBytes, cudaMemcpyHostToDevice, f->stream));
     }
-    if ((rc = enqueue_propagation(f)) != EQVIO_OK) return rc;
-    f->steadySplit = !f->capturing;  // stage brackets inside the update exist only with plain launches (a replayed graph is one bracket)
-    if (f->steadySplit) stage_mark(f, 1);
     const bool fuseEst = f->fuseSmall && f->corrMode != 1;
     const bool fuseGate = fuseEst && !plan;  // with a landmark-set change the gate sees the OLD state, the rows the NEW one
+    // block sweep without a landmark-set change: rows early (observer stream), gate late (beside the sweep)
+    const bool lateGate = fuseGate && f->earlyRows && f->corrMode == 2 && 2 * nm <= BC_MAX_ROWS && !f->downdateTC && !f->profiling && nm > 0;
+    f->measHookNm = lateGate ? nm : 0;
+    rc = enqueue_propagation(f);
+    f->measHookNm = 0;
+    if (rc != EQVIO_OK) return rc;
+    f->steadySplit = !f->capturing;  // stage brackets inside the update exist only with plain launches (a replayed graph is one bracket)
+    if (f->steadySplit) stage_mark(f, 1);
     if (!fuseGate && (rc = enqueue_gate(f, N, false)) != EQVIO_OK) return rc;  // riccati_prep_kernel re-armed the flag
     int Nout = N;
     if (plan) {
@@ -967,7 +990,7 @@ int enqueue_steady_update(eqvio_filter* f, int N, int nm, const FramePlan* plan)
     if (f->steadySplit) stage_mark(f, 2);
     // maxOutliers == 0 (featureRetention = 1, or (1 - featureRetention) n < 1): removeOutliers removes nothing whatever the gate
     // says (VIOFilter.cpp:304-364), so the correction must not be guarded by the gate flag -- d_spec + 1 is a constant 0
-    if ((rc = enqueue_correction(f, nm, f->pend.ignoreGate ? f->d_spec + 1 : f->d_spec, fuseGate, fuseEst)) != EQVIO_OK) return rc;
+    if ((rc = enqueue_correction(f, nm, f->pend.ignoreGate ? f->d_spec + 1 : f->d_spec, fuseGate, fuseEst, lateGate)) != EQVIO_OK) return rc;
     // stateEstimate() is what every caller asks for next (main_opt.cpp:225, main_sim.cpp:146): produced here, by the lift itself
     // in the fused form
     if (!fuseEst) {
@@ -979,7 +1002,7 @@ int enqueue_steady_update(eqvio_filter* f, int N, int nm, const FramePlan* plan)
     const size_t outBytes = f->outOffEst + (23 + 3 * (size_t)Nout) * sizeof(double);
     if (zc) {
         launch_pdl(f, block_copy_kernel, dim3(2), dim3(256), (size_t)0, f->stream, reinterpret_cast<const double2*>(f->d_outblk),
-                   reinterpret_cast<double2*>(f->hd_out), (int)((outBytes + 15) / 16), TL_SLOT(f));
+                   reinterpret_cast<double2*>(f->hd_out), (int)((outBytes + 15) / 16), 2, (const char*)nullptr, (size_t)0, TL_SLOT(f));
         LAUNCH_CHECK(f, "block_copy_kernel<result>");
     } else {
         CUDA_TRY(f, cudaMemcpyAsync(f->h_out, f->d_outblk, outBytes, cudaMemcpyDeviceToHost, f->stream));
@@ -1402,7 +1425,10 @@ int launch_chunk_factor(eqvio_filter* f, int ldy, int dimp, int j0, int bc, doub
 // Block sweep with look-ahead (blockchol.cuh): stream A = f->stream carries the build and the chain of diagonal steps (programmatic
 // edges between them), stream B = f->stream3 the panel / trailing kernels; diag(k) -> panel(k) -> trail(k) -> diag(k+2).
 // While the per-kernel profile runs everything is issued on f->stream (event brackets around each class).
-int enqueue_block_sweep(eqvio_filter* f, int nm, int dimp, double r2, const int* guard) {
+int enqueue_block_sweep(eqvio_filter* f, int nm, int dimp, double r2, const int* stateGuard, bool lateGate) {
+    // lateGate: the gate flag is not known yet when the sweep starts (the gate runs beside it): kernels that only write scratch
+    // (Z, panels, LT | XT) run unguarded, the trailing launches -- which write Sigma and Gamma -- wait for the gate and honour it
+    const int* guard = lateGate ? f->d_spec + 1 : stateGuard;
     const int m = 2 * nm;
     const int nT = cdiv(m, BC_T);
     const int ldy = (dimp + BC_T - 1) / BC_T * BC_T, TW = ldy / BC_T;
@@ -1441,7 +1467,7 @@ int enqueue_block_sweep(eqvio_filter* f, int nm, int dimp, double r2, const int*
             prof_end(f, tk);
             LAUNCH_CHECK(f, "bc_panel_kernel");
             int sk = prof_begin(f, PROF_BC_TRAIL);
-            bc_trail_kernel<<<2 * bc_trail_tiles(BC_PART_ALL, q, TW), DD_THREADS, DD_SMEM, sB>>>(f->d_bcZ, ldz, f->Sig[f->cur], f->ld, Zp, f->d_Gamma, guard, k,
+            bc_trail_kernel<<<2 * bc_trail_tiles(BC_PART_ALL, q, TW), DD_THREADS, DD_SMEM, sB>>>(f->d_bcZ, ldz, f->Sig[f->cur], f->ld, Zp, f->d_Gamma, stateGuard, k,
                                                                                                nT, TW, dimp, k == nT - 1 ? 1 : 0, (int)BC_PART_ALL,
                                                                                                f->d_bcCnt, TL_SLOT(f));
             prof_end(f, sk);
@@ -1468,13 +1494,14 @@ int enqueue_block_sweep(eqvio_filter* f, int nm, int dimp, double r2, const int*
             // C: panels of every row tile (block column k is current through step k-1 after next(k-1) and urgent(k-1)), then all
             // the other trailing tiles
             CUDA_TRY(f, cudaStreamWaitEvent(sC, evDiag(k), 0));
+            if (k == 0 && lateGate) CUDA_TRY(f, cudaStreamWaitEvent(sC, f->evGate, 0));
             if (k >= 1) {
                 if (bc_trail_tiles(BC_PART_NEXT, q + 1, TW) > 0) CUDA_TRY(f, cudaStreamWaitEvent(sC, evNext(k - 1), 0));
                 if (bc_trail_tiles(BC_PART_URGENT, q + 1, TW) > 0) CUDA_TRY(f, cudaStreamWaitEvent(sC, evUrg(k - 1), 0));
             }
             bc_panel_kernel<<<2 * below, 128, BC_PANEL_SMEM, sC>>>(f->d_bcZ, ldz, k, f->d_bcMt, Zp, guard, TL_SLOT(f));
             LAUNCH_CHECK(f, "bc_panel_kernel");
-            bc_trail_kernel<<<2 * bc_trail_tiles(BC_PART_REST, q, TW), DD_THREADS, DD_SMEM, sC>>>(f->d_bcZ, ldz, f->Sig[f->cur], f->ld, Zp, f->d_Gamma, guard, k,
+            bc_trail_kernel<<<2 * bc_trail_tiles(BC_PART_REST, q, TW), DD_THREADS, DD_SMEM, sC>>>(f->d_bcZ, ldz, f->Sig[f->cur], f->ld, Zp, f->d_Gamma, stateGuard, k,
                                                                                                 nT, TW, dimp, k == nT - 1 ? 1 : 0, (int)BC_PART_REST,
                                                                                                 f->d_bcCnt, TL_SLOT(f));
             LAUNCH_CHECK(f, "bc_trail_kernel<rest>");
@@ -1496,7 +1523,7 @@ int enqueue_block_sweep(eqvio_filter* f, int nm, int dimp, double r2, const int*
 // performVisionUpdate (VIO_eqf.cpp:105-135) in the symmetric form, for the nm measured landmarks whose pixels are
 // in d_y and state indices in d_lmOf.  Every kernel returns at once when *guard != 0.
 // fuseGate: the gate launch carries the measurement rows (gate_meas_kernel); fuseEst: the lift also emits the state estimate.
-int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate, bool fuseEst) {
+int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate, bool fuseEst, bool lateGate) {
     auto& P = f->pend;
     (void)P;
     const eqvio_settings& s = f->st;
@@ -1520,7 +1547,17 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
         double* gin = f->d_Gamma;
         double* gout = f->d_Gamma2;
         // also clears the status words and Gamma (no memset nodes between the kernels of the update)
-        if (fuseGate) {
+        if (lateGate) {
+            // the rows were built behind the observer (enqueue_propagation); the gate runs on its own stream beside the sweep: only
+            // the kernels that touch the filter state (trailing tiles of Sigma / Gamma, lift) look at its flag
+            CUDA_TRY(f, cudaEventRecord(f->evG0, f->stream));
+            CUDA_TRY(f, cudaStreamWaitEvent(f->stream5, f->evG0, 0));
+            gate_kernel<<<cdiv(Nn, 128), 128, 0, f->stream5>>>(f->lm[f->lmcur], f->cap, Nn, f->Sig[f->cur], f->ld, f->d_measIdx, f->d_y, f->d_hdr,
+                                                               s.coordinateChoice, f->d_gate, s.outlierThresholdAbs, s.outlierThresholdProb, f->d_spec,
+                                                               TL_SLOT(f));
+            LAUNCH_CHECK(f, "gate_kernel");
+            CUDA_TRY(f, cudaEventRecord(f->evGate, f->stream5));
+        } else if (fuseGate) {
             // one launch: gate CTAs (per state landmark) | measurement-row CTAs (per measured landmark); the rows are built
             // whatever the gate says -- d_spec + 1 is a constant 0
             const int gb = cdiv(Nn, 128), mb = cdiv(nm, 128);
@@ -1537,8 +1574,9 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
         LAUNCH_CHECK(f, "meas_kernel");
         }
         if (blockSweep) {
-            const int rcb = enqueue_block_sweep(f, nm, dimp, r2, guard);
+            const int rcb = enqueue_block_sweep(f, nm, dimp, r2, guard, lateGate);
             if (rcb != EQVIO_OK) return rcb;
+            if (lateGate) CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->evGate, 0));
         } else {
         const int bcMax = std::max(1, std::min(f->chunkLm, CH_R / 2));
         const int nchunks = cdiv(nm, bcMax);
@@ -1849,6 +1887,8 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
     f->st = *s;
     f->device = device;
     f->cap = capacity;
+    if (const char* pf = std::getenv("EQVIO_B200_PREFETCH")) f->prefetchSigma = std::atoi(pf) != 0;
+    if (const char* er = std::getenv("EQVIO_B200_EARLY_ROWS")) f->earlyRows = std::atoi(er) != 0;
     if (const char* cm = std::getenv("EQVIO_B200_CORRECTION")) {  // A/B runs of whole test / bench commands
         const int v = std::atoi(cm);
         if (v >= 0 && v <= 2) f->corrMode = v;
@@ -2069,6 +2109,8 @@ void eqvio_destroy(eqvio_filter* f) {
     if (f->stream5) cudaStreamDestroy(f->stream5);
     if (f->evFork) cudaEventDestroy(f->evFork);
     if (f->evJoin) cudaEventDestroy(f->evJoin);
+    if (f->evG0) cudaEventDestroy(f->evG0);
+    if (f->evGate) cudaEventDestroy(f->evGate);
     cudaFree(f->d_ctx);
     cudaFree(f->d_steps);
     cudaFree(f->d_rows);

@@ -103,10 +103,21 @@ __device__ __forceinline__ void tl_mark(int slot, int end) {
 // runs on a copy engine, and the hand-over between the copy engine and the SMs at both ends of the update costs more than
 // moving ~13 KB through one CTA's loads / stores does.  n16 = number of 16-byte words.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) block_copy_kernel(const double2* __restrict__ src, double2* __restrict__ dst, int n16, int tl) {
+// The first copyBlocks CTAs copy; any further CTAs ask L2 for the lines of [pf, pf + pfBytes) (prefetch.global.L2, fire and forget): the
+// frame upload of a steady update carries a prefetch of the covariance, so that the latency-bound propagation kernels that follow
+// find it in L2 instead of paying an HBM round trip per dependent access (the step starts with a cold L2 in every deployment where
+// other work ran since the previous frame; bench.py flushes it).
+__global__ void __launch_bounds__(256) block_copy_kernel(const double2* __restrict__ src, double2* __restrict__ dst, int n16, int copyBlocks,
+                                                         const char* __restrict__ pf, size_t pfBytes, int tl) {
     pdl_wait();
     TL_MARK(tl, 0);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = src[i];
+    if ((int)blockIdx.x < copyBlocks) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += copyBlocks * blockDim.x) dst[i] = src[i];
+    } else {
+        const size_t nb = gridDim.x - copyBlocks;
+        for (size_t o = ((size_t)(blockIdx.x - copyBlocks) * blockDim.x + threadIdx.x) * 128; o < pfBytes; o += nb * blockDim.x * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + o));
+    }
     TL_MARK(tl, 1);
 }
 

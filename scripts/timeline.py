@@ -33,6 +33,16 @@ try:
         flt.augmentLandmarkStates(fr.ids, eb.VIOState(eb.VIOSensorState(), fr.provided_p, fr.ids))
         if k == len(sm.frames) - 1 or os.environ.get("EQVIO_TL_FIRST"):
             fn(flt._h, buf, 512, 1)
+            if os.environ.get("EQVIO_TL_FLUSH"):  # cold L2, as in bench.py: 256 MiB write (EQVIO_TL_FLUSH=2: followed by a read sweep)
+                import torch
+                scratch = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+                scratch.zero_()
+                if os.environ["EQVIO_TL_FLUSH"] == "2":
+                    scratch2 = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+                    scratch2.zero_()
+                    torch.cuda.synchronize()
+                    scratch.sum()
+                torch.cuda.synchronize()
         flt.processVisionArrays(fr.stamp, fr.ids, fr.y, cam)
 except Exception as e:  # timing-only kernel variants produce garbage: the stamps of the failing update are still there
     print("update failed:", e)
