@@ -21,7 +21,7 @@
 
 #include "../../include/eqvio_b200.h"
 #include "kernels.cuh"
-#include "dense_riccati.cuh"
+#include "structured_riccati.cuh"
 #include "blockchol.cuh"
 
 using namespace eqvio;
@@ -88,6 +88,8 @@ struct eqvio_filter {
     unsigned char* hd_out = nullptr;    // ... of the pinned result block
     int zeroCopy = 1;                   // frame / result blocks move through block_copy_kernel instead of memcpy nodes
     int prefetchSigma = 1;              // the frame upload kernel also prefetches the covariance into L2
+    int propFusion = 1;                 // fast Riccati step: prop_ll_kernel builds its own factors, the strip runs beside it
+    cudaEvent_t evStrip0 = nullptr, evStrip1 = nullptr;
     int earlyRows = 1;                  // steady block-sweep frames: measurement rows right behind the observer, gate beside the sweep
     int measHookNm = 0;                 // > 0: enqueue_propagation launches the measurement rows on the observer's stream
     cudaEvent_t evG0 = nullptr, evGate = nullptr;
@@ -95,7 +97,18 @@ struct eqvio_filter {
     size_t frameBytes = 0, offImu = 0, offY = 0, offMeasIdx = 0, offLmOf = 0, offYIdx = 0;
     int* d_yIdx = nullptr;
     FrameHeader* d_hdrSteps = nullptr;  // one header per IMU sample (per-sample Riccati variants)
-    dense::Workspace dense;
+    // compact blocks of the per-sample / Normal-chart Riccati variants (structured_riccati.cuh), allocated at first use
+    struct Sric {
+        double *Ts = nullptr, *Tl = nullptr, *Es = nullptr, *El = nullptr, *uv = nullptr, *ladder = nullptr, *dtBs = nullptr;
+        unsigned long long* norm = nullptr;
+        SE3* cc = nullptr;  // camera-frame changes of the 43 sensor evaluations of stateMatrixADiscrete
+        void release() {
+            cudaFree(Ts); cudaFree(Tl); cudaFree(Es); cudaFree(El); cudaFree(uv); cudaFree(ladder); cudaFree(dtBs); cudaFree(norm); cudaFree(cc);
+            Ts = Tl = Es = El = uv = ladder = dtBs = nullptr;
+            norm = nullptr;
+            cc = nullptr;
+        }
+    } sric;
     FrameHeader* d_hdr = nullptr;
     double* d_imu = nullptr;
     int maxSteps = 0;
@@ -134,6 +147,7 @@ struct eqvio_filter {
     int lazyMirror = 1;  // downdate refreshes the upper triangle only where the next chunk reads it
     std::vector<int> h_lmOfSorted;  // state indices of the correction rows (host copy of d_lmOf)
     double* d_normalM = nullptr;  // Normal chart: sensor block of the coordinate differential and its inverse (2 x 441)
+    bool normalMValid = false;    // ... which only depends on xi0's sensor part: recomputed when that is set
     int prLeast = 0, prGreatest = 0;  // stream priority range of the device
     int smCount = 148;                // SMs of the device (grid sizing)
     bool pdlHold = false;  // next launch_pdl is a plain launch (its predecessor produces what the kernel reads before its wait)
@@ -469,6 +483,7 @@ bool make_sigma_maps(eqvio_filter* f) {
     return true;
 }
 
+int alloc_sric(eqvio_filter* f);
 int alloc_device(eqvio_filter* f) {
     const int cap = f->cap;
     const int dimpMax = dimp_of(cap);
@@ -502,6 +517,8 @@ int alloc_device(eqvio_filter* f) {
     CUDA_TRY(f, cudaEventCreateWithFlags(&f->evJoin, cudaEventDisableTiming));
     CUDA_TRY(f, cudaEventCreateWithFlags(&f->evG0, cudaEventDisableTiming));
     CUDA_TRY(f, cudaEventCreateWithFlags(&f->evGate, cudaEventDisableTiming));
+    CUDA_TRY(f, cudaEventCreateWithFlags(&f->evStrip0, cudaEventDisableTiming));
+    CUDA_TRY(f, cudaEventCreateWithFlags(&f->evStrip1, cudaEventDisableTiming));
     CUDA_TRY(f, cudaMalloc(&f->d_ctx, sizeof(RiccatiCtx)));
     {
         int rcf = alloc_frame(f, 64, std::max(cap, 1));
@@ -552,6 +569,10 @@ int alloc_device(eqvio_filter* f) {
     f->d_status = reinterpret_cast<int*>(f->d_outblk + f->outOffStatus);
     f->d_out = reinterpret_cast<double*>(f->d_outblk + f->outOffEst);
     CUDA_TRY(f, cudaMalloc(&f->d_normalM, 2 * 441 * sizeof(double)));
+    if (!f->st.fastRiccati || f->st.coordinateChoice == EQVIO_COORD_NORMAL) {
+        int rcs = alloc_sric(f);
+        if (rcs != EQVIO_OK) return rcs;
+    }
     CUDA_TRY(f, cudaMalloc(&f->d_keepI, c1 * sizeof(int)));
     // landmark-set changes arrive as ONE block: new positions | old-index map | new ids  (a single upload per change)
     f->mapBlkBytes = c1 * (3 * sizeof(double) + 2 * sizeof(int));
@@ -581,6 +602,7 @@ int reset_state(eqvio_filter* f, const double sensor[23], int n, const int* ids,
     std::memcpy(f->xi0s, sensor, 23 * sizeof(double));
     int rc;
     if ((rc = upload(f, f->d_xi0s, sensor, 23)) != EQVIO_OK) return rc;
+    f->normalMValid = false;
     double gid[23];
     group_identity_flat(gid);
     if ((rc = upload(f, f->d_Xs[f->xcur], gid, 23)) != EQVIO_OK) return rc;
@@ -726,10 +748,8 @@ int plan_integration(eqvio_filter* f, double newTime, int* advanced) {
 // Two independent chains (VIOFilter.cpp:138 "the Riccati propagation ... does not affect the state propagation"):
 //   stream : Riccati  -- context + Sigma_ss, landmark rows, strips, landmark-landmark block (reads X, Q *before*)
 //   stream2: observer -- sensor part of every IMU segment, then the landmark part (writes the other X / lm buffers)
-int enqueue_propagation(eqvio_filter* f) {
+void fill_prep_args(eqvio_filter* f, PrepArgs& a) {
     const eqvio_settings& s = f->st;
-    const int N = (int)f->ids.size();
-    PrepArgs a;
     a.xi0s = f->d_xi0s;
     a.Xs = f->d_Xs[f->xcur];
     a.XsOut = f->d_Xs[1 - f->xcur];
@@ -750,6 +770,16 @@ int enqueue_propagation(eqvio_filter* f) {
     a.pdiag[5] = s.cameraAttitudeProcessVariance;
     a.pdiag[6] = s.cameraPositionProcessVariance;
     a.pdiag[7] = s.pointProcessVariance;
+}
+int enqueue_sric_step(eqvio_filter* f, const PrepArgs& a, int mode, const double* imuRow, int* clearFlag);
+
+// fastRiccati: ONE Riccati step over the frame with the time-weighted mean IMU (VIOFilter.cpp:140-158) beside the observer integration of
+// every buffered sample.  Euclid / InvDepth: the rank-27 structured kernels; Normal chart: the compact-block kernels (A = M A_euclid M^-1).
+int enqueue_propagation(eqvio_filter* f) {
+    const eqvio_settings& s = f->st;
+    const int N = (int)f->ids.size();
+    PrepArgs a;
+    fill_prep_args(f, a);
     CUDA_TRY(f, cudaEventRecord(f->evFork, f->stream));
     CUDA_TRY(f, cudaStreamWaitEvent(f->stream2, f->evFork, 0));
     const int nsteps = reinterpret_cast<const FrameHeader*>(f->h_frame)->fs.nsteps;
@@ -776,21 +806,36 @@ int enqueue_propagation(eqvio_filter* f) {
         LAUNCH_CHECK(f, "meas_kernel");
     }
     CUDA_TRY(f, cudaEventRecord(f->evJoin, f->stream2));
-    {
+    if (s.coordinateChoice == EQVIO_COORD_NORMAL) {
+        int rcs = enqueue_sric_step(f, a, 0, nullptr, f->d_spec);
+        if (rcs != EQVIO_OK) return rcs;
+    } else {
         const double* Sin = f->Sig[f->cur];
         double* Sout = f->Sig[1 - f->cur];
-        riccati_prep_kernel<<<1, 448, 0, f->stream>>>(a, Sin, Sout, f->ld, nullptr, f->d_spec, TL_SLOT(f));  // also re-arms the gate flag
+        // prologue + landmark rows in one launch; also re-arms the gate flag
+        riccati_prep_kernel<<<1 + cdiv(N, PREP_LM), PREP_THREADS, 0, f->stream>>>(a, Sin, Sout, f->ld, nullptr, f->d_spec, f->lm[f->lmcur], f->cap, N,
+                                                                                   s.coordinateChoice, f->d_rows, TL_SLOT(f));
         LAUNCH_CHECK(f, "riccati_prep_kernel");
         if (N > 0) {
-            launch_pdl(f, landmark_rows_kernel, dim3(cdiv(N, 64)), dim3(64), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, N, f->d_ctx, s.coordinateChoice, f->d_rows, TL_SLOT(f));
-            LAUNCH_CHECK(f, "landmark_rows_kernel");
-            launch_pdl(f, prop_strip_kernel, dim3(cdiv(N, PS_LM)), dim3(PS_LM * PS_TPL), (size_t)(0), f->stream, Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv, TL_SLOT(f));
-            LAUNCH_CHECK(f, "prop_strip_kernel");
             const int nt = cdiv(N, TP);
+            const bool fused = f->propFusion && !f->profiling;
+            if (fused) {
+                // the strip (sensor-landmark block only) beside the landmark-landmark kernel, which builds its own factors
+                CUDA_TRY(f, cudaEventRecord(f->evStrip0, f->stream));
+                CUDA_TRY(f, cudaStreamWaitEvent(f->stream5, f->evStrip0, 0));
+                prop_strip_kernel<<<cdiv(N, PS_LM), PS_LM * PS_TPL, 0, f->stream5>>>(Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, (double*)nullptr, TL_SLOT(f));
+                LAUNCH_CHECK(f, "prop_strip_kernel");
+                CUDA_TRY(f, cudaEventRecord(f->evStrip1, f->stream5));
+            } else {
+                launch_pdl(f, prop_strip_kernel, dim3(cdiv(N, PS_LM)), dim3(PS_LM * PS_TPL), (size_t)(0), f->stream, Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv, TL_SLOT(f));
+                LAUNCH_CHECK(f, "prop_strip_kernel");
+            }
             int pk = prof_begin(f, PROF_PROP_LL);
-            launch_pdl(f, prop_ll_kernel, dim3(dim3(nt, nt)), dim3(dim3(TP, TP)), (size_t)(0), f->stream, Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv, TL_SLOT(f));
+            launch_pdl(f, prop_ll_kernel, dim3(dim3(nt, nt)), dim3(dim3(TP, TP)), (size_t)(0), f->stream, Sin, Sout, f->ld, N, f->d_ctx, f->d_rows, f->d_uv,
+                       fused ? 1 : 0, TL_SLOT(f));
             prof_end(f, pk);
             LAUNCH_CHECK(f, "prop_ll_kernel");
+            if (fused) CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->evStrip1, 0));
         }
         f->cur = 1 - f->cur;
     }
@@ -800,21 +845,111 @@ int enqueue_propagation(eqvio_filter* f) {
     return EQVIO_OK;
 }
 
-// fastRiccati = false: per buffered IMU sample, integrateRiccatiStateAccurate (dense matrix exponential, see
-// dense_riccati.cuh) followed by that sample's integrateObserverState -- VIOFilter.cpp:160-178.  Synchronises once per
-// sample (the scaling of the exponential is decided from a norm); this is the slow, faithful variant.
-int enqueue_propagation_accurate(eqvio_filter* f) {
+// Normal chart: M_s and its inverse depend on xi0's sensor part only -- computed once per xi0, outside any graph capture.
+int ensure_normal_m(eqvio_filter* f) {
+    if (f->normalMValid || f->capturing) return EQVIO_OK;
+    sric::normal_m_sensor_kernel<<<1, 64, 0, f->stream>>>(f->d_xi0s, f->d_normalM, f->d_normalM + 441);
+    LAUNCH_CHECK(f, "sric::normal_m_sensor_kernel");
+    f->normalMValid = true;
+    return EQVIO_OK;
+}
+
+int alloc_sric(eqvio_filter* f) {
+    auto& w = f->sric;
+    if (w.Ts) return EQVIO_OK;
+    const size_t c1 = std::max(f->cap, 1);
+    CUDA_TRY(f, cudaMalloc(&w.Ts, sric::SSIZE * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&w.Es, sric::SSIZE * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&w.Tl, c1 * sric::LSTRIDE * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&w.El, c1 * sric::LSTRIDE * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&w.uv, c1 * sric::GUV_STRIDE * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&w.ladder, (size_t)(sric::EXP_MAX_SQ + 1) * sric::SSIZE * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&w.dtBs, 252 * sizeof(double)));
+    CUDA_TRY(f, cudaMalloc(&w.norm, sizeof(unsigned long long)));
+    CUDA_TRY(f, cudaMalloc(&w.cc, sric::DA_SENSOR_EVALS * sizeof(SE3)));
+    return EQVIO_OK;
+}
+
+// One Riccati step with the compact-block kernels (structured_riccati.cuh) on f->stream, Sig[cur] -> Sig[1 - cur]; the step's dt and mean
+// IMU are a.fr's.  mode 0: E = I + dt A (one step over the frame: Normal chart with fastRiccati);  1: integrateRiccatiStateDiscrete
+// (imuRow = the sample's row in d_imu);  2: integrateRiccatiStateAccurate.  No host synchronisation, nothing read from the host:
+// capturable.  clearFlag: the first kernel of a steady update re-arms the gate flag.
+int enqueue_sric_step(eqvio_filter* f, const PrepArgs& a, int mode, const double* imuRow, int* clearFlag) {
     const eqvio_settings& s = f->st;
     const int N = (int)f->ids.size();
-    const int dim = SENSOR_DIM + 3 * N, n = dim + 12;
+    auto& w = f->sric;
+    if (!w.Ts) {
+        int rca = alloc_sric(f);
+        if (rca != EQVIO_OK) return rca;
+    }
+    const bool normal = s.coordinateChoice == EQVIO_COORD_NORMAL;
+    const double* Sin = f->Sig[f->cur];
+    double* Sout = f->Sig[1 - f->cur];
+    // sensor blocks of A, B for this step (the fused Sigma'_ss it also writes is overwritten by gprop_sensor_kernel below)
+    riccati_prep_kernel<<<1 + cdiv(N, PREP_LM), PREP_THREADS, 0, f->stream>>>(a, Sin, Sout, f->ld, w.dtBs, clearFlag, f->lm[f->lmcur], f->cap, N,
+                                                                               s.coordinateChoice, f->d_rows, TL_SLOT(f));
+    LAUNCH_CHECK(f, "riccati_prep_kernel");
+    // integrateRiccatiStateAccurate: T = dt [A B; 0 0], E = exp(T).  integrateRiccatiStateDiscrete (VIO_eqf.cpp:93-103,
+    // useDiscreteStateMatrix): E = [A0tD, dt B] directly, with the numerically differentiated discrete state matrix
+    // -- the products and the noise term below are then the same expressions (dt B (Q / dt) (dt B)^T = dt B Q B^T).
+    const bool expo = mode == 2;
+    double* Ts = expo ? w.Ts : w.Es;  // only the exponential maps T to a different E
+    double* Tl = expo ? w.Tl : w.El;
+    sric::fill_kernel<<<1 + cdiv(N, 128), 128, 0, f->stream>>>(f->d_ctx, w.dtBs, f->d_rows, N, Ts, Tl, w.norm);
+    LAUNCH_CHECK(f, "sric::fill_kernel");
+    if (normal) {
+        int rcm = ensure_normal_m(f);  // a no-op inside a capture: vision_phase_a ran it before the capture began
+        if (rcm != EQVIO_OK) return rcm;
+        sric::normal_transform_kernel<<<1 + N, 128, 0, f->stream>>>(Ts, Tl, N, f->lm[f->lmcur], f->cap, f->d_normalM, f->d_normalM + 441);
+        LAUNCH_CHECK(f, "sric::normal_transform_kernel");
+    }
+    if (mode == 0) {
+        sric::add_identity_kernel<<<cdiv(std::max(3 * N, SENSOR_DIM), 128), 128, 0, f->stream>>>(w.Es, w.El, N);
+        LAUNCH_CHECK(f, "sric::add_identity_kernel");
+    } else if (mode == 1) {
+        sric::discrete_a_sensor_kernel<<<1, 64, 0, f->stream>>>(s.coordinateChoice, f->d_xi0s, a.Xs, imuRow, w.Es, w.cc);
+        LAUNCH_CHECK(f, "sric::discrete_a_sensor_kernel");
+        if (N > 0) {
+            sric::discrete_a_landmark_kernel<<<N, 64, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, s.coordinateChoice, imuRow, w.cc, w.El);
+            LAUNCH_CHECK(f, "sric::discrete_a_landmark_kernel");
+        }
+    } else {
+        sric::exp_norm_kernel<<<cdiv(SENSOR_DIM + 3 * N, 128), 128, 0, f->stream>>>(w.Ts, w.Tl, N, w.norm);
+        LAUNCH_CHECK(f, "sric::exp_norm_kernel");
+        sric::exp_sensor_kernel<<<1, sric::EXPS_THREADS, 0, f->stream>>>(w.Ts, w.norm, w.ladder, w.Es);
+        LAUNCH_CHECK(f, "sric::exp_sensor_kernel");
+        if (N > 0) {
+            sric::exp_landmark_kernel<<<N, 128, 0, f->stream>>>(w.Ts, w.Tl, w.norm, w.ladder, w.El, N);
+            LAUNCH_CHECK(f, "sric::exp_landmark_kernel");
+        }
+    }
+    sric::NoiseArgs nz;
+    for (int k = 0; k < 4; ++k) nz.q[k] = a.qdiag[k];
+    for (int k = 0; k < 8; ++k) nz.p[k] = a.pdiag[k];
+    sric::gprop_sensor_kernel<<<1, 448, 0, f->stream>>>(w.Es, nz, f->d_ctx, Sin, Sout, f->ld);
+    LAUNCH_CHECK(f, "sric::gprop_sensor_kernel");
+    if (N > 0) {
+        sric::gprop_strip_kernel<<<cdiv(N, sric::GS_LM), sric::GS_LM * 32, 0, f->stream>>>(w.Es, w.El, nz, f->d_ctx, Sin, Sout, f->ld, N, w.uv);
+        LAUNCH_CHECK(f, "sric::gprop_strip_kernel");
+        const int nt = cdiv(N, sric::GTP);
+        int pk = prof_begin(f, PROF_PROP_LL);
+        sric::gprop_ll_kernel<<<dim3(nt, nt), dim3(sric::GTP, sric::GTP), sric::GLL_SMEM, f->stream>>>(w.El, w.uv, f->d_ctx, Sin, Sout, f->ld, N);
+        prof_end(f, pk);
+        LAUNCH_CHECK(f, "sric::gprop_ll_kernel");
+    }
+    f->cur = 1 - f->cur;
+    return EQVIO_OK;
+}
+
+// fastRiccati = false: per buffered IMU sample, integrateRiccatiStateAccurate (or ...Discrete with useDiscreteStateMatrix) followed by
+// that sample's integrateObserverState -- VIOFilter.cpp:160-178.  Block-structured kernels of structured_riccati.cuh: no dense
+// matrix, no library call, no host synchronisation.
+int enqueue_propagation_per_sample(eqvio_filter* f) {
+    const eqvio_settings& s = f->st;
+    const int N = (int)f->ids.size();
     const FrameHeader* hh = reinterpret_cast<const FrameHeader*>(f->h_frame);
     const double* himu = reinterpret_cast<const double*>(f->h_frame + f->offImu);
     const int nsteps = hh->fs.nsteps;
-    const char* why = dense::ensure(f->dense, n, f->stream);
-    if (why) {
-        f->err = std::string("fastRiccati=false needs cuBLAS / cuSOLVER: ") + why;
-        return EQVIO_ERR_UNSUPPORTED;
-    }
     int rc;
     std::vector<FrameHeader> hdrs(nsteps);
     for (int i = 0; i < nsteps; ++i) {
@@ -824,102 +959,19 @@ int enqueue_propagation_accurate(eqvio_filter* f) {
         hdrs[i].fs.nsteps = 1;
     }
     if ((rc = upload(f, f->d_hdrSteps, hdrs.data(), (size_t)nsteps)) != EQVIO_OK) return rc;
-    const double pd[8] = {s.biasOmegaProcessVariance,      s.biasAccelProcessVariance,     s.attitudeProcessVariance,
-                          s.positionProcessVariance,       s.velocityProcessVariance,      s.cameraAttitudeProcessVariance,
-                          s.cameraPositionProcessVariance, s.pointProcessVariance};
-    if ((rc = upload(f, f->dense.pdiag, pd, 8)) != EQVIO_OK) return rc;
-    dense::Workspace& w = f->dense;
-    const bool normal = s.coordinateChoice == EQVIO_COORD_NORMAL;
-    // Normal coordinates with fastRiccati: ONE step over the frame with the time-weighted mean IMU (VIOFilter.cpp:140-158),
-    // Sigma <- (I + dt A) Sigma (I + dt A)^T + dt (B Q B^T + P) with the dense A_normal = M A_euclid M^-1, B_normal = M B_euclid;
-    // the observer then integrates every buffered sample.  Otherwise one Riccati step per sample.
-    const bool single = s.fastRiccati != 0;
-    if (normal) {
-        dense::normal_m_sensor_kernel<<<1, 64, 0, f->stream>>>(f->d_xi0s, f->d_normalM, f->d_normalM + 441);
-        LAUNCH_CHECK(f, "normal_m_sensor_kernel");
-    }
-    for (int i = 0; i < (single ? 1 : nsteps); ++i) {
-        const double dt = single ? hh->fs.dtTotal : himu[13 * i];
+    for (int i = 0; i < nsteps; ++i) {
+        const double dt = himu[13 * i];
         PrepArgs a;
-        a.xi0s = f->d_xi0s;
-        a.Xs = f->d_Xs[f->xcur];
-        a.XsOut = f->d_Xs[1 - f->xcur];
-        a.ctx = f->d_ctx;
-        a.steps = single ? f->d_steps : f->d_steps + i;
-        a.fr = single ? f->d_hdr : f->d_hdrSteps + i;
-        a.imu = single ? f->d_imu : f->d_imu + (size_t)13 * i;
-        a.discreteLift = s.useDiscreteVelocityLift ? 1 : 0;
-        a.qdiag[0] = s.velGyrNoise * s.velGyrNoise;
-        a.qdiag[1] = s.velAccNoise * s.velAccNoise;
-        a.qdiag[2] = s.velGyrBiasWalk * s.velGyrBiasWalk;
-        a.qdiag[3] = s.velAccBiasWalk * s.velAccBiasWalk;
-        for (int k = 0; k < 8; ++k) a.pdiag[k] = pd[k];
-        if (dt > 0) {
-            const double* Sin = f->Sig[f->cur];
-            double* Sout = f->Sig[1 - f->cur];
-            double *M = w.buf[0], *P0 = w.buf[1], *T = w.buf[2], *P1 = w.buf[3], *R = w.buf[8];
-            riccati_prep_kernel<<<1, 448, 0, f->stream>>>(a, Sin, Sout, f->ld, w.dtBs, nullptr, TL_SLOT(f));
-            LAUNCH_CHECK(f, "riccati_prep_kernel");
-            if (N > 0) {
-                launch_pdl(f, landmark_rows_kernel, dim3(cdiv(N, 64)), dim3(64), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, N, f->d_ctx, s.coordinateChoice, f->d_rows, TL_SLOT(f));
-                LAUNCH_CHECK(f, "landmark_rows_kernel");
-            }
-            // integrateRiccatiStateAccurate: M = dt [A B; 0 0], R = exp(M).  integrateRiccatiStateDiscrete (VIO_eqf.cpp:93-103,
-            // useDiscreteStateMatrix): R = [A0tD, dt B; 0 0] directly, with the numerically differentiated discrete state matrix
-            // -- the products and the noise term below are then the same expressions (dt B (Q / dt) (dt B)^T = dt B Q B^T).
-            const bool discreteA = !single && s.useDiscreteStateMatrix;
-            double* Tgt = discreteA ? R : M;
-            CUDA_TRY(f, cudaMemsetAsync(Tgt, 0, (size_t)n * n * sizeof(double), f->stream));
-            dense::dense_fill_sensor_kernel<<<2, 256, 0, f->stream>>>(Tgt, n, dim, f->d_ctx, w.dtBs);
-            LAUNCH_CHECK(f, "dense_fill_sensor_kernel");
-            if (N > 0) {
-                dense::dense_fill_landmark_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(Tgt, n, dim, N, f->d_rows, dt);
-                LAUNCH_CHECK(f, "dense_fill_landmark_kernel");
-            }
-            if (normal) {
-                dense::normal_transform_kernel<<<1 + N, 128, 0, f->stream>>>(Tgt, n, dim, N, f->lm[f->lmcur], f->cap, f->d_normalM,
-                                                                             f->d_normalM + 441);
-                LAUNCH_CHECK(f, "normal_transform_kernel");
-            }
-            if (single) {
-                dense::dense_lincomb_kernel<<<cdiv((size_t)n * n, 256), 256, 0, f->stream>>>(R, n, 1.0, M, 0.0, nullptr, 0.0, nullptr, 1.0);
-                LAUNCH_CHECK(f, "dense_lincomb_kernel");
-            } else if (discreteA) {
-                dense::discrete_a_sensor_kernel<<<1, 64, 0, f->stream>>>(s.coordinateChoice, f->d_xi0s, f->d_Xs[f->xcur], f->d_imu + (size_t)13 * i, R, n, w.cc);
-                LAUNCH_CHECK(f, "discrete_a_sensor_kernel");
-                if (N > 0) {
-                    dense::discrete_a_landmark_kernel<<<N, 64, 0, f->stream>>>(f->lm[f->lmcur], f->cap, N, s.coordinateChoice,
-                                                                               f->d_imu + (size_t)13 * i, w.cc, R, n);
-                    LAUNCH_CHECK(f, "discrete_a_landmark_kernel");
-                }
-            } else {
-                why = dense::expm(w, n, f->stream);
-                if (why) {
-                    f->err = std::string("matrix exponential: ") + why;
-                    return EQVIO_ERR_CUDA;
-                }
-            }
-            pack_sigma_kernel<<<dim3(cdiv(dim, 128), dim), 128, 0, f->stream>>>(Sin, f->ld, dim, P0, dim);
-            LAUNCH_CHECK(f, "pack_sigma_kernel");
-            if (dense::gemm(w, dense::OP_N, dense::OP_N, dim, dim, dim, 1.0, R, n, P0, dim, 0.0, T, dim) ||
-                dense::gemm(w, dense::OP_N, dense::OP_T, dim, dim, dim, 1.0, T, dim, R, n, 0.0, P1, dim)) {
-                f->err = "cublasDgemm failed";
-                return EQVIO_ERR_CUDA;
-            }
-            dense::dense_noise_kernel<<<dim3(cdiv(dim, 128), dim), 128, 0, f->stream>>>(P1, dim, R, n, a.qdiag[0], a.qdiag[1], a.qdiag[2],
-                                                                                       a.qdiag[3], 1.0 / dt, dt, w.pdiag);
-            LAUNCH_CHECK(f, "dense_noise_kernel");
-            CUDA_TRY(f, cudaMemsetAsync(Sout, 0, (size_t)f->ld * dimp_of(N) * sizeof(double), f->stream));
-            dense::dense_unpack_sigma_kernel<<<dim3(cdiv(dim, 128), dim), 128, 0, f->stream>>>(P1, dim, dim, Sout, f->ld);
-            LAUNCH_CHECK(f, "dense_unpack_sigma_kernel");
-            f->cur = 1 - f->cur;
-        }
+        fill_prep_args(f, a);
+        a.steps = f->d_steps + i;
+        a.fr = f->d_hdrSteps + i;
+        a.imu = f->d_imu + (size_t)13 * i;
+        if (dt > 0 && (rc = enqueue_sric_step(f, a, s.useDiscreteStateMatrix ? 1 : 2, f->d_imu + (size_t)13 * i, nullptr)) != EQVIO_OK) return rc;
         observer_sensor_kernel<<<1, 32, 0, f->stream>>>(a, TL_SLOT(f));
         LAUNCH_CHECK(f, "observer_sensor_kernel");
         if (N > 0) {
             observer_landmark_kernel<<<cdiv(N, 64), 64, 0, f->stream>>>(f->lm[f->lmcur], f->lm[1 - f->lmcur], f->dids[f->lmcur],
-                                                                        f->dids[1 - f->lmcur], f->cap, N, single ? f->d_steps : f->d_steps + i,
-                                                                        single ? f->d_hdr : f->d_hdrSteps + i, TL_SLOT(f));
+                                                                        f->dids[1 - f->lmcur], f->cap, N, f->d_steps + i, f->d_hdrSteps + i, TL_SLOT(f));
             LAUNCH_CHECK(f, "observer_landmark_kernel");
             f->lmcur = 1 - f->lmcur;
         }
@@ -955,9 +1007,20 @@ int enqueue_steady_update(eqvio_filter* f, int N, int nm, const FramePlan* plan)
     if (zc) {
         // + prefetch of the covariance (the rows in use) into L2 beside the copy
         const size_t pfBytes = f->prefetchSigma ? (size_t)f->ld * dimp_of(N) * sizeof(double) : 0;
+        PrefetchList small = {};
+        if (f->prefetchSigma) {
+            small.p[0] = reinterpret_cast<const char*>(f->d_xi0s);
+            small.bytes[0] = 23 * sizeof(double);
+            small.p[1] = reinterpret_cast<const char*>(f->d_Xs[f->xcur]);
+            small.bytes[1] = 23 * sizeof(double);
+            small.p[2] = reinterpret_cast<const char*>(f->lm[f->lmcur]);
+            small.bytes[2] = (unsigned)((size_t)LM_FIELDS * std::max(f->cap, 1) * sizeof(double));
+            small.p[3] = reinterpret_cast<const char*>(f->dids[f->lmcur]);
+            small.bytes[3] = (unsigned)(std::max(f->cap, 1) * sizeof(int));
+        }
         block_copy_kernel<<<2 + (pfBytes ? 64 : 0), 256, 0, f->stream>>>(reinterpret_cast<const double2*>(f->hd_frame), reinterpret_cast<double2*>(f->d_frame),
                                                                         (int)(f->frameBytes / 16), 2, reinterpret_cast<const char*>(f->Sig[f->cur]), pfBytes,
-                                                                        TL_SLOT(f));
+                                                                        small, TL_SLOT(f));
         LAUNCH_CHECK(f, "block_copy_kernel<frame>");
     } else {
         CUDA_TRY(f, cudaMemcpyAsync(f->d_frame, f->h_frame, f->frameBytes, cudaMemcpyHostToDevice, f->stream));
@@ -1002,7 +1065,7 @@ int enqueue_steady_update(eqvio_filter* f, int N, int nm, const FramePlan* plan)
     const size_t outBytes = f->outOffEst + (23 + 3 * (size_t)Nout) * sizeof(double);
     if (zc) {
         launch_pdl(f, block_copy_kernel, dim3(2), dim3(256), (size_t)0, f->stream, reinterpret_cast<const double2*>(f->d_outblk),
-                   reinterpret_cast<double2*>(f->hd_out), (int)((outBytes + 15) / 16), 2, (const char*)nullptr, (size_t)0, TL_SLOT(f));
+                   reinterpret_cast<double2*>(f->hd_out), (int)((outBytes + 15) / 16), 2, (const char*)nullptr, (size_t)0, PrefetchList{}, TL_SLOT(f));
         LAUNCH_CHECK(f, "block_copy_kernel<result>");
     } else {
         CUDA_TRY(f, cudaMemcpyAsync(f->h_out, f->d_outblk, outBytes, cudaMemcpyDeviceToHost, f->stream));
@@ -1080,7 +1143,7 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
     // leaves before the gate, and also when ids are lost (pruned, VIOFilter.cpp:203-205) or new (appended with bearing x median
     // depth, :258-278) -- those sets follow from the ids alone, and the new landmarks' positions are computed on the device under
     // the same "no gate trips" assumption the speculative correction makes (exact redo in phase C otherwise).
-    const bool densePath = !f->st.fastRiccati || f->st.coordinateChoice == EQVIO_COORD_NORMAL;  // cuBLAS products, not graph-captured
+    const bool densePath = !f->st.fastRiccati;  // per-sample Riccati variants: per-kernel launches (the Normal chart with fastRiccati is a steady path)
     int nLost = 0;
     for (int i = 0; i < N; ++i) nLost += P.keep[i] ? 0 : 1;
     const int nNewIds = n - matched;
@@ -1143,6 +1206,7 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
         P.h_spec = reinterpret_cast<int*>(f->h_out + f->outOffSpec);
         P.h_status = reinterpret_cast<int*>(f->h_out + f->outOffStatus);
         P.nStatus = 1 + Nout;
+        if (f->st.coordinateChoice == EQVIO_COORD_NORMAL && (rc = ensure_normal_m(f)) != EQVIO_OK) return rc;
         stage_mark(f, 0);
         // kernel arguments derived from the row -> landmark map are baked into a captured graph: replay only when that map
         // is the identity (every landmark of the updated state measured)
@@ -1215,7 +1279,7 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
     // general frame: upload, propagate, gate; decisions follow in phase B
     CUDA_TRY(f, cudaMemcpyAsync(f->d_frame, f->h_frame, f->frameBytes, cudaMemcpyHostToDevice, f->stream));
     stage_mark(f, 0);
-    if ((rc = densePath ? enqueue_propagation_accurate(f) : enqueue_propagation(f)) != EQVIO_OK) return rc;
+    if ((rc = densePath ? enqueue_propagation_per_sample(f) : enqueue_propagation(f)) != EQVIO_OK) return rc;
     stage_mark(f, 1);
     if (N > 0) {
         if ((rc = enqueue_gate(f, N, true)) != EQVIO_OK) return rc;
@@ -2111,6 +2175,8 @@ void eqvio_destroy(eqvio_filter* f) {
     if (f->evJoin) cudaEventDestroy(f->evJoin);
     if (f->evG0) cudaEventDestroy(f->evG0);
     if (f->evGate) cudaEventDestroy(f->evGate);
+    if (f->evStrip0) cudaEventDestroy(f->evStrip0);
+    if (f->evStrip1) cudaEventDestroy(f->evStrip1);
     cudaFree(f->d_ctx);
     cudaFree(f->d_steps);
     cudaFree(f->d_rows);
@@ -2131,7 +2197,7 @@ void eqvio_destroy(eqvio_filter* f) {
     cudaFree(f->d_ytilde);
     cudaFree(f->d_frame);
     cudaFree(f->d_hdrSteps);
-    f->dense.release();
+    f->sric.release();
     if (f->h_frame) cudaFreeHost(f->h_frame);
     if (f->h_out) cudaFreeHost(f->h_out);
     cudaFree(f->d_outblk);
@@ -2173,6 +2239,7 @@ int eqvio_initialise_from_imu(eqvio_filter* f, double stamp, const double gyr[3]
     f->xi0s[9] = q.z;
     for (int i = 10; i < 16; ++i) f->xi0s[i] = 0.0;
     int rc = upload(f, f->d_xi0s, f->xi0s, 23);
+    f->normalMValid = false;
     if (rc != EQVIO_OK) return rc;
     CUDA_TRY(f, cudaStreamSynchronize(f->stream));
     f->initialised = true;
@@ -2715,6 +2782,10 @@ int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
             return EQVIO_OK;
         case EQVIO_TUNE_ZERO_COPY:
             f->zeroCopy = value != 0;
+            clear_graphs(f);
+            return EQVIO_OK;
+        case EQVIO_TUNE_PROP_FUSION:
+            f->propFusion = value != 0;
             clear_graphs(f);
             return EQVIO_OK;
         case EQVIO_TUNE_FUSE_SMALL:

@@ -107,11 +107,20 @@ __device__ __forceinline__ void tl_mark(int slot, int end) {
 // frame upload of a steady update carries a prefetch of the covariance, so that the latency-bound propagation kernels that follow
 // find it in L2 instead of paying an HBM round trip per dependent access (the step starts with a cold L2 in every deployment where
 // other work ran since the previous frame; bench.py flushes it).
+struct PrefetchList {  // small state arrays the update reads first (group / origin sensor parts, landmark SoA, ids): a cold miss on each of
+    const char* p[4];  // them is a dependent HBM round trip in the one-thread Riccati prologue and the observer chain
+    unsigned bytes[4];
+};
 __global__ void __launch_bounds__(256) block_copy_kernel(const double2* __restrict__ src, double2* __restrict__ dst, int n16, int copyBlocks,
-                                                         const char* __restrict__ pf, size_t pfBytes, int tl) {
+                                                         const char* __restrict__ pf, size_t pfBytes, PrefetchList small, int tl) {
     pdl_wait();
     TL_MARK(tl, 0);
     if ((int)blockIdx.x < copyBlocks) {
+        if (blockIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                for (unsigned o = threadIdx.x * 128u; o < small.bytes[k]; o += blockDim.x * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(small.p[k] + o));
+        }
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += copyBlocks * blockDim.x) dst[i] = src[i];
     } else {
         const size_t nb = gridDim.x - copyBlocks;
@@ -126,64 +135,73 @@ __global__ void __launch_bounds__(256) block_copy_kernel(const double2* __restri
 // 186-233; identical for invdepth) from X *before* the observer integration, and the quantities the
 // landmark rows need.  As is 21x21, Bs 21x12, row-major.
 // ------------------------------------------------------------------------------------------------
-HD void riccati_small(const PrepArgs& a, double* As, double* Bs) {
+// Split into three independent parts (each starts from X, xi0 again: ~150 flops) so that three warps of the prologue CTA run them side
+// by side -- one thread of fp64 latency-bound work each -- instead of one thread running all of it.  As, Bs must be zero on entry.
+//   part 0: B sensor rows and the blocks of A that follow from them       -> As, Bs
+//   part 1: the adjoint chain  ad(Ad_{T0^-1} Ad_A U_I)                      -> As[15:21, 15:21], c.common
+//   part 2: what the landmark rows need beside `common`, and the scalars    -> c.RICt_RAt, RT_IC, vC, xIC, dt, cg, plDiag
+// Landmark rows need c.common (part 1) and part 2 only.
+HD void riccati_small_part(const PrepArgs& a, RiccatiCtx& c, double* As, double* Bs, int part) {
     SensorState xi0 = unpack_sensor(a.xi0s);
     GroupSensor X = unpack_group(a.Xs);
-    RiccatiCtx& c = *a.ctx;
     const double dt = a.fr->fs.dtTotal;
     const double* meanImu = a.fr->fs.meanImu;
     SensorState xh = sensor_group_action(X, xi0);
-    for (int i = 0; i < 21 * 21; ++i) As[i] = 0;
-    for (int i = 0; i < 21 * 12; ++i) Bs[i] = 0;
-    // B sensor rows (euclid.cpp:206-218)
-    for (int i = 0; i < 6; ++i) Bs[i * 12 + 6 + i] = 1.0;
-    M3 RA = qmat(X.A.q);
-    M3 xRA = skew(X.A.x) * RA;
-    M3 RAv = RA * skew(xh.vel);
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-            Bs[(6 + i) * 12 + j] = RA(i, j);
-            Bs[(9 + i) * 12 + j] = xRA(i, j);
-            Bs[(12 + i) * 12 + j] = RAv(i, j);
-            Bs[(12 + i) * 12 + 3 + j] = RA(i, j);
-        }
-    // A sensor block (euclid.cpp:111-131)
-    for (int i = 0; i < 21; ++i)
-        for (int j = 0; j < 6; ++j) As[i * 21 + j] = -Bs[i * 12 + j];
-    for (int i = 0; i < 3; ++i) As[(9 + i) * 21 + 12 + i] = 1.0;
-    V3 gdir = qrot(qinv(xi0.pose.q), V3{0, 0, 1});
-    M3 gsk = (-GRAVITY_CONSTANT) * skew(gdir);
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) As[(12 + i) * 21 + 6 + j] = gsk(i, j);
     double UI[6] = {meanImu[0] - xh.bias[0], meanImu[1] - xh.bias[1], meanImu[2] - xh.bias[2],
                     xh.vel.x, xh.vel.y, xh.vel.z};
-    double AdT0inv[36], AdA[36], t1[6], t2[6], adT[36];
-    se3_Adjoint(se3_inv(xi0.cam), AdT0inv);
-    se3_Adjoint(X.A, AdA);
-    mat6_vec(AdA, UI, t1);
-    mat6_vec(AdT0inv, t1, t2);
-    se3_adjoint(t2, adT);
-    for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 6; ++j) As[(15 + i) * 21 + 15 + j] = adT[6 * i + j];
-    // landmark-row context
-    double AdBinv[36];
-    se3_Adjoint(se3_inv(X.B), AdBinv);
-    mat6_mul(AdBinv, adT, c.common);
-    M3 RIC = qmat(xh.cam.q);
-    M3 t = transpose(RIC) * transpose(RA);
-    M3 RTIC = qmat(qinv(xh.cam.q));
-    for (int i = 0; i < 9; ++i) {
-        c.RICt_RAt[i] = t.m[i];
-        c.RT_IC[i] = RTIC.m[i];
+    if (part == 0) {
+        // B sensor rows (euclid.cpp:206-218)
+        for (int i = 0; i < 6; ++i) Bs[i * 12 + 6 + i] = 1.0;
+        M3 RA = qmat(X.A.q);
+        M3 xRA = skew(X.A.x) * RA;
+        M3 RAv = RA * skew(xh.vel);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                Bs[(6 + i) * 12 + j] = RA(i, j);
+                Bs[(9 + i) * 12 + j] = xRA(i, j);
+                Bs[(12 + i) * 12 + j] = RAv(i, j);
+                Bs[(12 + i) * 12 + 3 + j] = RA(i, j);
+            }
+        // A sensor block (euclid.cpp:111-131): the columns 0..5 are -B's (rows 6..14; the other rows of B's first six columns are zero)
+        for (int i = 6; i < 15; ++i)
+            for (int j = 0; j < 6; ++j) As[i * 21 + j] = -Bs[i * 12 + j];
+        for (int i = 0; i < 3; ++i) As[(9 + i) * 21 + 12 + i] = 1.0;
+        V3 gdir = qrot(qinv(xi0.pose.q), V3{0, 0, 1});
+        M3 gsk = (-GRAVITY_CONSTANT) * skew(gdir);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) As[(12 + i) * 21 + 6 + j] = gsk(i, j);
+    } else if (part == 1) {
+        double AdT0inv[36], AdA[36], t1[6], t2[6], adT[36];
+        se3_Adjoint(se3_inv(xi0.cam), AdT0inv);
+        se3_Adjoint(X.A, AdA);
+        mat6_vec(AdA, UI, t1);
+        mat6_vec(AdT0inv, t1, t2);
+        se3_adjoint(t2, adT);
+        if (As)
+            for (int i = 0; i < 6; ++i)
+                for (int j = 0; j < 6; ++j) As[(15 + i) * 21 + 15 + j] = adT[6 * i + j];
+        // landmark-row context
+        double AdBinv[36];
+        se3_Adjoint(se3_inv(X.B), AdBinv);
+        mat6_mul(AdBinv, adT, c.common);
+    } else {
+        M3 RA = qmat(X.A.q);
+        M3 RIC = qmat(xh.cam.q);
+        M3 t = transpose(RIC) * transpose(RA);
+        M3 RTIC = qmat(qinv(xh.cam.q));
+        for (int i = 0; i < 9; ++i) {
+            c.RICt_RAt[i] = t.m[i];
+            c.RT_IC[i] = RTIC.m[i];
+        }
+        double AdThinv[36], UC[6];
+        se3_Adjoint(se3_inv(xh.cam), AdThinv);
+        mat6_vec(AdThinv, UI, UC);
+        c.vC[0] = UC[3]; c.vC[1] = UC[4]; c.vC[2] = UC[5];
+        c.xIC[0] = xh.cam.x.x; c.xIC[1] = xh.cam.x.y; c.xIC[2] = xh.cam.x.z;
+        c.dt = dt;
+        c.cg = dt * a.qdiag[0];
+        c.plDiag = dt * a.pdiag[7];
     }
-    double AdThinv[36], UC[6];
-    se3_Adjoint(se3_inv(xh.cam), AdThinv);
-    mat6_vec(AdThinv, UI, UC);
-    c.vC[0] = UC[3]; c.vC[1] = UC[4]; c.vC[2] = UC[5];
-    c.xIC[0] = xh.cam.x.x; c.xIC[1] = xh.cam.x.y; c.xIC[2] = xh.cam.x.z;
-    c.dt = dt;
-    c.cg = dt * a.qdiag[0];
-    c.plDiag = dt * a.pdiag[7];
 }
 // part 2, one call per entry t = 21 i + j of the sensor block: F_s = I + dt A_s, N_s = dt (B_s Q B_s^T + P_s),
 // and dt q_gyr B_s[:, 0:3] for t < 63.
@@ -271,51 +289,6 @@ __global__ void observer_sensor_kernel(PrepArgs a, int tl) {
     TL_MARK(tl, 1);
 }
 
-// One CTA: Riccati context (thread 0 builds the sparse A_s, B_s; 441 threads fill F_s, N_s) and, fused, the
-// sensor-sensor block  Sigma'_ss = F_s Sigma_ss F_s^T + N_s  plus the zero pad rows/cols of the sensor block.
-__global__ void __launch_bounds__(448)
-    riccati_prep_kernel(PrepArgs a, const double* __restrict__ Sin, double* __restrict__ Sout, int ld, double* __restrict__ dtBsOut,
-                        int* __restrict__ clearFlag, int tl) {
-    pdl_wait();
-    TL_MARK(tl, 0);
-    __shared__ double sAs[441], sBs[252], sF[441], sS[441], sT[441];
-    const int t = threadIdx.x;
-    if (clearFlag && t == 447) *clearFlag = 0;  // first kernel of an update: re-arm the gate flag (no memset node)
-    if (t == 0) riccati_small(a, sAs, sBs);
-    if (t < 441) {
-        const int r = t / 21, c = t % 21;
-        sS[t] = Sin[(size_t)c * ld + r];  // sS[r*21+c] = Sigma[r,c]
-    }
-    __syncthreads();
-    double ns = 0.0;
-    if (t < 441) {
-        double fs;
-        riccati_entry(a, sAs, sBs, t, fs, ns);
-        sF[t] = fs;
-    }
-    if (dtBsOut && t < 252) dtBsOut[t] = a.fr->fs.dtTotal * sBs[t];  // dense (matrix-exponential) variant needs dt B_s itself
-    __syncthreads();
-    if (t < 441) {
-        const int r = t / 21, c = t % 21;
-        double s = 0;
-        for (int k = 0; k < 21; ++k) s += sF[r * 21 + k] * sS[k * 21 + c];
-        sT[t] = s;
-    }
-    __syncthreads();
-    if (t < 441) {
-        const int r = t / 21, c = t % 21;
-        double s = ns;
-        for (int k = 0; k < 21; ++k) s += sT[r * 21 + k] * sF[c * 21 + k];
-        Sout[(size_t)c * ld + r] = s;
-    }
-    if (t < 3 * SOFF) {
-        const int p = SENSOR_DIM + t / SOFF, q = t % SOFF;
-        Sout[(size_t)q * ld + p] = 0.0;
-        Sout[(size_t)p * ld + q] = 0.0;
-    }
-    TL_MARK(tl, 1);
-}
-
 // ------------------------------------------------------------------------------------------------
 // Per landmark, Riccati rows: the landmark rows of A and B (euclid.cpp:133-155,219-228; invdepth.cpp:83-118,
 // 170-178) condensed to D_i = I + dt A_qi (3x3), G_i = dt [ -B_l | A_vel | A_cam ] (3x12, columns c_sidx)
@@ -323,12 +296,8 @@ __global__ void __launch_bounds__(448)
 // ------------------------------------------------------------------------------------------------
 constexpr int ROWS_STRIDE = 54;
 
-__global__ void landmark_rows_kernel(const double* __restrict__ lm, int cap, int N, const RiccatiCtx* __restrict__ ctx, int coord,
-                                     double* __restrict__ rows, int tl) {
-    pdl_wait();
-    TL_MARK(tl, 0);
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) { TL_MARK(tl, 1); return; }
+__device__ __forceinline__ void landmark_rows_body(const double* __restrict__ lm, int cap, int i, const RiccatiCtx* ctx, int coord,
+                                                   double* __restrict__ rows) {
     V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
     Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
     double a = lm[F_QA * cap + i];
@@ -376,6 +345,66 @@ __global__ void landmark_rows_kernel(const double* __restrict__ lm, int cap, int
         for (int c = 0; c < 6; ++c) o[9 + 12 * r + 6 + c] = dt * camB[6 * r + c];
     }
     for (int k = 0; k < 9; ++k) o[45 + k] = Bl.m[k];
+}
+
+// Riccati prologue, one launch: CTA 0 builds the context (three threads on three warps run the independent parts of riccati_small_part,
+// 441 threads fill F_s, N_s) and, fused, the sensor-sensor block  Sigma'_ss = F_s Sigma_ss F_s^T + N_s  plus the zero pad rows / cols of
+// the sensor block;  CTA 1 + b computes the Riccati rows of landmarks 64 b .. 64 b + 63 from ITS OWN copy of the landmark-row context (parts
+// 1 and 2, in shared memory) -- redundant per CTA, but the rows no longer wait for a kernel boundary behind the serial prologue.
+constexpr int PREP_THREADS = 448, PREP_LM = 64;
+__global__ void __launch_bounds__(PREP_THREADS)
+    riccati_prep_kernel(PrepArgs a, const double* __restrict__ Sin, double* __restrict__ Sout, int ld, double* __restrict__ dtBsOut,
+                        int* __restrict__ clearFlag, const double* __restrict__ lm, int cap, int N, int coord, double* __restrict__ rows, int tl) {
+    pdl_wait();
+    TL_MARK(tl, 0);
+    const int t = threadIdx.x;
+    if (blockIdx.x > 0) {
+        __shared__ RiccatiCtx sCtx;
+        if (t == 32) riccati_small_part(a, sCtx, nullptr, nullptr, 1);
+        if (t == 64) riccati_small_part(a, sCtx, nullptr, nullptr, 2);
+        __syncthreads();
+        const int i = (blockIdx.x - 1) * PREP_LM + t;
+        if (t < PREP_LM && i < N) landmark_rows_body(lm, cap, i, &sCtx, coord, rows);
+        TL_MARK(tl, 1);
+        return;
+    }
+    __shared__ double sAs[441], sBs[252], sF[441], sS[441], sT[441];
+    if (clearFlag && t == 447) *clearFlag = 0;  // first kernel of an update: re-arm the gate flag (no memset node)
+    if (t < 441) {
+        const int r = t / 21, c = t % 21;
+        sAs[t] = 0.0;
+        if (t < 252) sBs[t] = 0.0;
+        sS[t] = Sin[(size_t)c * ld + r];  // sS[r*21+c] = Sigma[r,c]
+    }
+    __syncthreads();
+    if (t == 0 || t == 32 || t == 64) riccati_small_part(a, *a.ctx, sAs, sBs, t / 32);
+    __syncthreads();
+    double ns = 0.0;
+    if (t < 441) {
+        double fs;
+        riccati_entry(a, sAs, sBs, t, fs, ns);
+        sF[t] = fs;
+    }
+    if (dtBsOut && t < 252) dtBsOut[t] = a.fr->fs.dtTotal * sBs[t];  // the compact-block variants need dt B_s itself
+    __syncthreads();
+    if (t < 441) {
+        const int r = t / 21, c = t % 21;
+        double s = 0;
+        for (int k = 0; k < 21; ++k) s += sF[r * 21 + k] * sS[k * 21 + c];
+        sT[t] = s;
+    }
+    __syncthreads();
+    if (t < 441) {
+        const int r = t / 21, c = t % 21;
+        double s = ns;
+        for (int k = 0; k < 21; ++k) s += sT[r * 21 + k] * sF[c * 21 + k];
+        Sout[(size_t)c * ld + r] = s;
+    }
+    if (t < 3 * SOFF) {
+        const int p = SENSOR_DIM + t / SOFF, q = t % SOFF;
+        Sout[(size_t)q * ld + p] = 0.0;
+        Sout[(size_t)p * ld + q] = 0.0;
+    }
     TL_MARK(tl, 1);
 }
 
@@ -450,7 +479,7 @@ __global__ void observer_landmark_kernel(const double* __restrict__ lmIn, double
 // acquire counter; warps 1-2 (64 landmarks) consume segment s while the sensor thread is already on segment s + 1.
 // The update takes ~the sensor chain alone instead of sensor chain + landmark chain + a kernel boundary.
 // ------------------------------------------------------------------------------------------------
-constexpr int OBSF_LM = 64, OBSF_THREADS = 32 + OBSF_LM;
+constexpr int OBSF_LM = 64, OBSF_THREADS = 32 + OBSF_LM + 32;  // warp 0: sensor chain, warps 1-2: landmarks, warp 3: helper
 __device__ __forceinline__ void flag_release_cta(int* p, int v) {
     asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
@@ -472,17 +501,129 @@ struct PublishShared {
         if (writeGlobal) pack_group(X, a.XsOut);
     }
 };
+// Discrete velocity lift (VIOGroup.cpp:229-257), the default: what one thread has to run serially is only X_(s+1) = X_s Lambda_s(X_s).
+// The single-thread form spends ~6000 clocks per segment issuing ~1300 dependent fp64 instructions; two thirds of them do not sit on
+// that chain:
+//   * bias-corrected gyr / acc and  Lambda_A.q = exp(dt gyr)  depend on X only through X.beta, which grows by dt u_bias per segment
+//     whatever the state: the helper warp computes them for ALL segments at once (lane = segment, the prefix sum in the chain's order);
+//   * the camera-frame change the landmarks need,  T_hat^-1 Lambda_A^-1 T_hat,  is not an input of the next segment: the chain
+//     thread hands (T_hat, Lambda_A) to lane 0 of the helper warp, which publishes the ObsStep to the landmark warps.
+// Same functions on the same operands as observer_sensor_steps, so the two forms agree to rounding (test_fused_observer_...).
+struct ObsPre {
+    double dt;
+    V3 acc;
+    Quat LAq;
+};
+struct ObsChain {
+    SE3 cam, LA;
+};
+__device__ void observer_helper_discrete(const PrepArgs& a, int lane, ObsPre* s_pre, const ObsChain* s_chain, ObsStep* s_steps, int* preReady,
+                                         const int* chainReady, int* ready) {
+    const int nsteps = a.fr->fs.nsteps;
+    {
+        const SensorState xi0 = unpack_sensor(a.xi0s);
+        const GroupSensor X0 = unpack_group(a.Xs);
+        for (int base = 0; base < nsteps; base += 32) {
+            const int s = base + lane;
+            if (s < nsteps) {
+                double beta[6];
+                for (int i = 0; i < 6; ++i) beta[i] = X0.beta[i];
+                for (int k = 0; k < s; ++k) {  // X.beta after k segments, accumulated in the chain's order
+                    const double* uk = a.imu + 13 * k;
+                    for (int i = 0; i < 6; ++i) beta[i] = beta[i] + uk[0] * uk[7 + i];
+                }
+                const double* u = a.imu + 13 * s;
+                const double dt = u[0];
+                double bias[6];
+                for (int i = 0; i < 6; ++i) bias[i] = xi0.bias[i] + beta[i];
+                const V3 gyr = V3{u[1] - bias[0], u[2] - bias[1], u[3] - bias[2]};
+                ObsPre p;
+                p.dt = dt;
+                p.acc = V3{u[4] - bias[3], u[5] - bias[4], u[6] - bias[5]};
+                p.LAq = so3_exp(dt * gyr);
+                s_pre[s] = p;
+            }
+        }
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    flag_release_cta(preReady, 1);
+    for (int s = 0; s < nsteps; ++s) {
+        while (flag_acquire_cta(chainReady) <= s) {
+        }
+        const ObsChain c = s_chain[s];
+        ObsStep st;
+        st.discrete = 1;
+        st.dt = s_pre[s].dt;
+        st.camChangeInv = se3_mul(se3_mul(se3_inv(c.cam), se3_inv(c.LA)), c.cam);
+        st.omegaC = V3{0, 0, 0};
+        st.vC = V3{0, 0, 0};
+        s_steps[s] = st;
+        flag_release_cta(ready, s + 1);
+    }
+}
+__device__ void observer_chain_discrete(const PrepArgs& a, const ObsPre* s_pre, ObsChain* s_chain, const int* preReady, int* chainReady,
+                                        bool writeGlobal) {
+    const SensorState xi0 = unpack_sensor(a.xi0s);
+    GroupSensor X = unpack_group(a.Xs);
+    const int nsteps = a.fr->fs.nsteps;
+    while (flag_acquire_cta(preReady) == 0) {
+    }
+    for (int s = 0; s < nsteps; ++s) {
+        const double* u = a.imu + 13 * s;
+        const ObsPre p = s_pre[s];
+        const double dt = p.dt;
+        // the parts of xi_hat = phi_X(xi0) a segment uses (sensor_group_action)
+        const Quat poseq = qmul(xi0.pose.q, X.A.q);
+        const V3 vel = qrot(qinv(X.A.q), xi0.vel - X.w);
+        const SE3 cam = se3_mul(se3_mul(se3_inv(X.A), xi0.cam), X.B);
+        const V3 gdir = qrot(qinv(poseq), V3{0, 0, 1});
+        GroupSensor L;
+        for (int i = 0; i < 6; ++i) L.beta[i] = dt * u[7 + i];
+        L.A.q = p.LAq;
+        V3 x = dt * qrot(poseq, vel) + (0.5 * dt * dt) * (qrot(poseq, p.acc) + V3{0, 0, -GRAVITY_CONSTANT});
+        L.A.x = qrot(qinv(poseq), x);
+        s_chain[s] = ObsChain{cam, L.A};
+        flag_release_cta(chainReady, s + 1);
+        L.B = se3_mul(se3_mul(se3_inv(cam), L.A), cam);
+        V3 bvd = p.acc - GRAVITY_CONSTANT * gdir;
+        L.w = vel - (vel + dt * bvd);
+        // X <- X * Lambda (VIOGroup.cpp:71-92)
+        GroupSensor Xn;
+        for (int i = 0; i < 6; ++i) Xn.beta[i] = X.beta[i] + L.beta[i];
+        Xn.A = se3_mul(X.A, L.A);
+        Xn.B = se3_mul(X.B, L.B);
+        Xn.w = X.w + qrot(X.A.q, L.w);
+        X = Xn;
+    }
+    if (writeGlobal) pack_group(X, a.XsOut);
+}
 __global__ void __launch_bounds__(OBSF_THREADS)
     observer_fused_kernel(PrepArgs a, const double* __restrict__ lmIn, double* __restrict__ lmOut, const int* __restrict__ idsIn,
                           int* __restrict__ idsOut, int cap, int N, int tl) {
     TL_MARK(tl, 0);
     __shared__ ObsStep s_steps[OBS_STAGE];
-    __shared__ int s_ready;
-    if (threadIdx.x == 0) s_ready = 0;
+    __shared__ ObsPre s_pre[OBS_STAGE];
+    __shared__ ObsChain s_chain[OBS_STAGE];
+    __shared__ int s_ready, s_preReady, s_chainReady;
+    if (threadIdx.x == 0) {
+        s_ready = 0;
+        s_preReady = 0;
+        s_chainReady = 0;
+    }
     __syncthreads();
     if (threadIdx.x < 32) {
-        if (threadIdx.x == 0) observer_sensor_steps(a, PublishShared{a, s_steps, &s_ready, blockIdx.x == 0});
+        if (threadIdx.x == 0) {
+            if (a.discreteLift)
+                observer_chain_discrete(a, s_pre, s_chain, &s_preReady, &s_chainReady, blockIdx.x == 0);
+            else
+                observer_sensor_steps(a, PublishShared{a, s_steps, &s_ready, blockIdx.x == 0});
+        }
         { TL_MARK(tl, 1); return; }
+    }
+    if (threadIdx.x >= 32 + OBSF_LM) {
+        if (a.discreteLift) observer_helper_discrete(a, threadIdx.x - (32 + OBSF_LM), s_pre, s_chain, s_steps, &s_preReady, &s_chainReady, &s_ready);
+        return;
     }
     const int nsteps = a.fr->fs.nsteps;
     const int i = blockIdx.x * OBSF_LM + (threadIdx.x - 32);
@@ -570,7 +711,8 @@ __global__ void __launch_bounds__(PS_LM* PS_TPL)
     if (live) {
         double* U = uv + (size_t)i * UV_STRIDE;
         double* V = U + 81;
-        if (t < 12) {  // column t of E_i, H_i
+        if (!uv) {  // prop_ll_kernel builds the factors of its own tile rows / columns (ownFactors): only the sensor-landmark block here
+        } else if (t < 12) {  // column t of E_i, H_i
             const int sc = c_sidx[t];
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
@@ -634,23 +776,79 @@ constexpr int TP = 16;
 __global__ void __launch_bounds__(TP* TP)
     prop_ll_kernel(const double* __restrict__ Sin, double* __restrict__ Sout, int ld, int N,
                    const RiccatiCtx* __restrict__ ctx, const double* __restrict__ rows,
-                   const double* __restrict__ uv, int tl) {
+                   const double* __restrict__ uv, int ownFactors, int tl) {
     pdl_wait();
     TL_MARK(tl, 0);
     const int ti = blockIdx.y, tj = blockIdx.x;
     if (tj > ti) { TL_MARK(tl, 1); return; }
     __shared__ double sU[TP][82], sV[TP][82], sDi[TP][9], sDj[TP][9];
+    __shared__ double sRow[2][TP][ROWS_STRIDE];  // ownFactors: D(9) | G(36) | Bl(9) of the tile's row / column landmarks
+    __shared__ double sSS[144];                  // ownFactors: Sigma[sidx, sidx]
     const int tid = threadIdx.y * TP + threadIdx.x;
     const int i0 = ti * TP, j0 = tj * TP;
-    for (int t = tid; t < TP * 81; t += TP * TP) {
-        int l = t / 81, k = t % 81;
-        sU[l][k] = (i0 + l < N) ? uv[(size_t)(i0 + l) * UV_STRIDE + k] : 0.0;
-        sV[l][k] = (j0 + l < N) ? uv[(size_t)(j0 + l) * UV_STRIDE + 81 + k] : 0.0;
-    }
-    for (int t = tid; t < TP * 9; t += TP * TP) {
-        int l = t / 9, k = t % 9;
-        sDi[l][k] = (i0 + l < N) ? rows[(size_t)(i0 + l) * ROWS_STRIDE + k] : 0.0;
-        sDj[l][k] = (j0 + l < N) ? rows[(size_t)(j0 + l) * ROWS_STRIDE + k] : 0.0;
+    if (ownFactors) {
+        // U of the 16 row landmarks and V of the 16 column landmarks from the Riccati rows and Sigma's sensor strip -- the expressions of
+        // prop_strip_kernel (which then only writes the sensor-landmark block, beside this kernel on another stream): 480 work items of
+        // 3 loads + <= 45 FMAs instead of a kernel boundary on the chain prologue -> rows -> strip -> ll.
+        for (int t = tid; t < 2 * TP * ROWS_STRIDE; t += TP * TP) {
+            const int w = t / (TP * ROWS_STRIDE), l = (t / ROWS_STRIDE) % TP, k = t % ROWS_STRIDE;
+            const int lmk = (w ? j0 : i0) + l;
+            sRow[w][l][k] = lmk < N ? rows[(size_t)lmk * ROWS_STRIDE + k] : 0.0;
+        }
+        if (tid < 144) sSS[tid] = Sin[(size_t)c_sidx[tid % 12] * ld + c_sidx[tid / 12]];  // sSS[k * 12 + t] = Sigma[sidx[k], sidx[t]]
+        const double cg = ctx->cg;
+        __syncthreads();
+        for (int item = tid; item < 2 * TP * 15; item += TP * TP) {
+            const int w = item / (TP * 15), l = (item / 15) % TP, t = item % 15;
+            const int lmk = (w ? j0 : i0) + l;
+            const double* D = sRow[w][l];
+            const double* G = D + 9;
+            const double* Bl = D + 45;
+            double* out = w ? sV[l] : sU[l];
+            if (t < 12) {
+                const int sc = c_sidx[t];
+                const int r0 = SOFF + 3 * lmk;
+                double L0 = 0.0, L1 = 0.0, L2 = 0.0;
+                if (lmk < N) {
+                    L0 = Sin[(size_t)sc * ld + r0];
+                    L1 = Sin[(size_t)sc * ld + r0 + 1];
+                    L2 = Sin[(size_t)sc * ld + r0 + 2];
+                }
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const double e = D[3 * a] * L0 + D[3 * a + 1] * L1 + D[3 * a + 2] * L2;
+                    if (w == 0) {
+                        double h = e;
+#pragma unroll
+                        for (int k = 0; k < 12; ++k) h += G[12 * a + k] * sSS[k * 12 + t];
+                        out[27 * a + t] = G[12 * a + t];
+                        out[27 * a + 12 + t] = h;
+                    } else {
+                        out[27 * a + t] = e;
+                        out[27 * a + 12 + t] = G[12 * a + t];
+                    }
+                }
+            } else {
+                const int c = t - 12;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) out[27 * a + 24 + c] = w == 0 ? cg * Bl[3 * a + c] : Bl[3 * a + c];
+            }
+        }
+        if (tid < TP * 9) {
+            sDi[tid / 9][tid % 9] = sRow[0][tid / 9][tid % 9];
+            sDj[tid / 9][tid % 9] = sRow[1][tid / 9][tid % 9];
+        }
+    } else {
+        for (int t = tid; t < TP * 81; t += TP * TP) {
+            int l = t / 81, k = t % 81;
+            sU[l][k] = (i0 + l < N) ? uv[(size_t)(i0 + l) * UV_STRIDE + k] : 0.0;
+            sV[l][k] = (j0 + l < N) ? uv[(size_t)(j0 + l) * UV_STRIDE + 81 + k] : 0.0;
+        }
+        for (int t = tid; t < TP * 9; t += TP * TP) {
+            int l = t / 9, k = t % 9;
+            sDi[l][k] = (i0 + l < N) ? rows[(size_t)(i0 + l) * ROWS_STRIDE + k] : 0.0;
+            sDj[l][k] = (j0 + l < N) ? rows[(size_t)(j0 + l) * ROWS_STRIDE + k] : 0.0;
+        }
     }
     __syncthreads();
     const int li = threadIdx.x, lj = threadIdx.y;  // threadIdx.x walks rows (contiguous in memory)

@@ -84,6 +84,11 @@ class VIOWriter:
         "points.csv": "time, p1id, p1x, p1y, p1z, ...\n",
         "features.csv": "time, z1id, z1x, z1y, ...\n",
         "landmarkError.csv": "time, lm_err_1, lm_err_2, ...\n",
+        # VIOWriter.cpp:146-151 (the reference's literals concatenate without a comma between bias_acc_z and num_lm; kept as is)
+        "trueState.csv": "time, pose_tx, pose_ty, pose_tz, pose_qw, pose_qx, pose_qy, pose_qz,"
+                         "pose_vx, pose_vy, pose_vz, cam_tx, cam_ty, cam_tz, cam_qw, cam_qx, cam_qy, cam_qz,"
+                         "bias_gyr_x, bias_gyr_y, bias_gyr_z, bias_acc_x, bias_acc_y, bias_acc_z"
+                         "num_lm, lm_1_id, lm_1_x, lm_1_y, lm_1_z, lm_2_id, lm_2_x, lm_2_y, lm_2_z, ...\n",
         "nees.csv": "time, NEES, DoF, PoseNEES, AttitudeNEES\n",
         "poseConsistency.csv": "time, eps_rx, eps_ry, eps_rz, eps_px, eps_py, eps_pz,"
                                "Sigma2_rx, Sigma2_ry, Sigma2_rz, Sigma2_px, Sigma2_py, Sigma2_pz\n",
@@ -153,8 +158,14 @@ class VIOWriter:
             entries.append(float(np.linalg.norm(est[int(i)] - p)) if int(i) in est else float("nan"))
         self._file("landmarkError.csv").write(_line(stamp, entries))
 
-    # -- VIOWriter.cpp:142-228 (NEES and the per-block consistency files; the true-state dump is the caller's) ----------
+    # -- VIOWriter.cpp:142-228 (true-state dump, NEES and the per-block consistency files) -----------------------------
     def writeConsistency(self, stamp, trueState, flt):
+        # VIOState.cpp:80-92: sensor (pose, velocity, camera offset, bias), landmark count, then id, x, y, z per landmark
+        t = trueState.sensor
+        entries = [*t.pose_x, *t.pose_q, *t.velocity, *t.cameraOffset_x, *t.cameraOffset_q, *t.inputBias, int(len(trueState.ids))]
+        for pid, p in zip(trueState.ids, np.asarray(trueState.p).reshape(-1, 3)):
+            entries += [int(pid), *p]
+        self._file("trueState.csv").write(_line(stamp, entries))
         fs = flt.viewEqFState(withSigma=True)
         Sigma = fs.Sigma
         ts = trueState.sensor

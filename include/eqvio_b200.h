@@ -261,6 +261,10 @@ int eqvio_get_host_profile(eqvio_filter* f, int reset, double us[4], long long* 
 /*   EQVIO_TUNE_ZERO_COPY: 1 (default) = the per-frame input block and the result block of a steady update move through a copy
  *     KERNEL over host-mapped pinned memory; 0 = cudaMemcpyAsync (memcpy nodes on a copy engine inside the replayed graph). */
 #define EQVIO_TUNE_ZERO_COPY 13
+/*   EQVIO_TUNE_PROP_FUSION: 1 (default) = in the fast Riccati step the landmark-landmark kernel builds the rank-27 factors of its own
+ *     tile rows / columns and the sensor-landmark strip runs beside it on another stream (chain: prologue + rows -> ll);
+ *     0 = prologue + rows -> strip (writes the factors) -> ll.  Same expressions, bit-identical results. */
+#define EQVIO_TUNE_PROP_FUSION 14
 int eqvio_set_tuning(eqvio_filter* f, int key, int value);
 /* Version / build info string (arch the kernels were compiled for). */
 const char* eqvio_build_info(void);

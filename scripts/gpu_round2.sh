@@ -3,7 +3,7 @@
 # list + full captures, sanitizer.  Outputs under gpurun_out/r2f_*; summarise here with scripts/ncu_summary.py / ncu_traffic.py.
 set -u
 O=gpurun_out
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3 > $O/r2f_tests.txt
+timeout 1500 python -m pytest tests -m gpu -q -rf 2>&1 | tail -40 > $O/r2f_tests.txt
 python -c "import __graft_entry__ as g; g.smoke()" > $O/r2f_smoke.txt 2>&1
 timeout 600 python bench.py > $O/r2f_bench_n256.json 2> $O/r2f_bench_n256.err
 for n in 64 1024; do timeout 600 python bench.py --landmarks $n --no-sweep > $O/r2f_bench_n$n.json 2> $O/r2f_bench_n$n.err; done
@@ -25,6 +25,13 @@ timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"bc
   -o $O/r2f_prof_n256 -f python bench.py --steps 3 --warmup 3 --profile-steps 0 --no-cpu-baseline --no-graph --no-sweep --batched-sequences 0 > $O/r2f_ncu_full256.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"chunk_factor_kernel|chunk_downdate_kernel|prop_ll_kernel" -s 60 -c 9 \
   -o $O/r2f_prof_n1024 -f python bench.py --landmarks 1024 --steps 2 --warmup 3 --profile-steps 0 --no-cpu-baseline --no-graph --no-sweep --batched-sequences 0 > $O/r2f_ncu_full1024.log 2>&1
+# summaries on the box (gpurun brings back at most 64 MiB): per-launch table + DRAM traffic per kernel class, then drop the big reports
+python scripts/ncu_summary.py full $O/r2f_prof_n256.ncu-rep $O/r2f_ncu_full_n256.csv > /dev/null 2>&1
+python scripts/ncu_summary.py full $O/r2f_prof_n1024.ncu-rep $O/r2f_ncu_full_n1024.csv > /dev/null 2>&1
+python scripts/ncu_summary.py launches $O/r2f_launches_n256.csv $O/r2f_launches_n256.md > /dev/null 2>&1
+EQVIO_TRAFFIC_OUT=$O/r2f_traffic.json python scripts/ncu_traffic.py 256=$O/r2f_prof_n256.ncu-rep 1024=$O/r2f_prof_n1024.ncu-rep > /dev/null 2>&1
+for k in bc_diag_kernel bc_trail_kernel prop_ll_kernel observer_fused_kernel; do python scripts/ncu_lines.py $O/r2f_prof_n256.ncu-rep $k 30 > $O/r2f_lines_$k.txt 2>&1; done
+rm -f $O/r2f_prof_n256.ncu-rep $O/r2f_prof_n1024.ncu-rep
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "evaluation_orders or sequence_matches or steady_path or gating" > $O/r2f_sanitizer.txt 2>&1
 tail -5 $O/r2f_sanitizer.txt
 ls -la $O | grep r2f

@@ -13,7 +13,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLASSES = {"prop_ll_kernel": "prop_ll", "chunk_factor_kernel": "chunk_factor", "chunk_downdate_kernel": "downdate",
-           "chunk_downdate_tc_kernel": "downdate_tc", "gemm_nt_sub_kernel": "chol_trail", "observer_fused_kernel": "observer_fused"}
+           "chunk_downdate_tc_kernel": "downdate_tc", "gemm_nt_sub_kernel": "chol_trail", "observer_fused_kernel": "observer_fused",
+           "bc_diag_kernel": "bc_diag", "bc_panel_kernel": "bc_panel", "bc_trail_kernel": "bc_trail", "bc_next_kernel": "bc_next",
+           "bc_build_kernel": "bc_build"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
@@ -47,7 +49,7 @@ def main():
     traffic["_source"] = ("ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the "
                           "captured launches (counts: %s); reports: %s; summaries under profiles/ with the same stem"
                           % (json.dumps(sources), ", ".join(os.path.basename(a.split("=", 1)[1]) for a in sys.argv[1:])))
-    json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+    json.dump(traffic, open(os.environ.get("EQVIO_TRAFFIC_OUT", os.path.join(ROOT, "profiles", "traffic.json")), "w"), indent=1)
     print(json.dumps(traffic, indent=1))
 
 

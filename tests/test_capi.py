@@ -137,3 +137,17 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_library_has_no_blas_or_solver_dependency():
+    """Every Settings combination runs on the library's own kernels: no cuBLAS / cuSOLVER name anywhere in the shared object
+    (neither a link-time dependency nor a dlopen string), and libcudart is the only CUDA library it needs."""
+    import subprocess
+
+    from eqvio_b200 import _capi
+
+    blob = open(_capi.LIB_PATH, "rb").read()
+    for name in (b"cublas", b"cusolver", b"cusparse"):
+        assert name not in blob.lower(), name
+    needed = subprocess.run(["readelf", "-d", _capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "cublas" not in needed and "cusolver" not in needed

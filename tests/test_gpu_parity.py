@@ -73,7 +73,8 @@ def test_correction_evaluation_orders_agree(tuning):
     _check(run_gpu(stream, tuning=tuning), ref)
 
 
-@pytest.mark.parametrize("tuning", [dict(graph=0), dict(graph=0, speculate=0), dict(graph=1), dict(graph=1, pdl=0), dict(graph=0, pdl=0), dict(graph=1, fuseSmall=0), dict(graph=0, fuseSmall=0)])
+@pytest.mark.parametrize("tuning", [dict(graph=0), dict(graph=0, speculate=0), dict(graph=1), dict(graph=1, pdl=0), dict(graph=0, pdl=0), dict(graph=1, fuseSmall=0), dict(graph=0, fuseSmall=0),
+                                    dict(graph=1, propFusion=0), dict(graph=0, propFusion=0)])
 def test_steady_path_variants_agree(tuning):
     """CUDA-graph replay, plain speculative launches and the wait-for-the-gate path give identical results
     (same kernels, same order), over enough frames for graphs to be captured AND replayed."""
@@ -494,6 +495,10 @@ def test_writer_consistency_files(tmp_path):
     assert rows[-1, 2] == 21 + 3 * len(ref[-1]["ids"])
     imu = np.loadtxt(str(tmp_path / "IMUState.csv"), delimiter=",", skiprows=1, ndmin=2)
     np.testing.assert_allclose(imu[-1, 1:4], ref[-1]["sensor"][10:13], rtol=2e-5, atol=1e-6)  # six significant digits
+    tru = np.loadtxt(str(tmp_path / "trueState.csv"), delimiter=",", skiprows=1, ndmin=2)  # VIOWriter.cpp:144-156
+    n = len(ref[-1]["ids"])
+    assert tru.shape == (len(stream["frames"]), 1 + 23 + 1 + 4 * n) and tru[-1, 24] == n
+    np.testing.assert_array_equal(tru[-1, 25::4].astype(int), np.asarray(ref[-1]["ids"]))
     g.close()
 
 

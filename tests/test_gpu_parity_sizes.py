@@ -218,3 +218,52 @@ def test_zero_copy_blocks_agree_with_memcpy_nodes(N):
     for k, (g, r) in enumerate(zip(b, a)):
         e = compare_states(g, r)
         assert e["ids_equal"] and e["sigma"] == 0.0 and e["state"] == 0.0, f"update {k}: {e}"
+
+
+@pytest.mark.parametrize("coord", [0, 1])
+def test_n256_accurate_riccati(coord):
+    """fastRiccati = false (the reference's struct default, VIOFilterSettings.h:91-92) at BASELINE's N = 256: per IMU sample
+    integrateRiccatiStateAccurate (VIO_eqf.cpp:74-91).  The device takes the exponential block by block (one shared 33 x 33 sensor /
+    input block, one 3 x 33 row block per landmark, scaled Taylor series: structured_riccati.cuh); the oracle takes scipy's dense
+    Pade expm of the (dim + 12)-square matrix -- two independent algorithms, so the bound is the exponential's accuracy."""
+    stream = make_stream(N=256, frames=3, coord=coord, settings_overrides=dict(fastRiccati=False))
+    worst = _check(run_gpu(stream), run_oracle(stream), tol=1e-8)
+    print(f"N=256 accurate Riccati coord={coord}: worst {worst:.3e}")
+
+
+@pytest.mark.parametrize("N,overrides", [(256, dict()), (128, dict(fastRiccati=False)), (64, dict(fastRiccati=False, useDiscreteStateMatrix=True))])
+def test_normal_chart_at_size(N, overrides):
+    """Normal coordinates (coordinateSuite/normal.cpp:37-45) at size: fast (one step per frame), accurate and discrete per sample,
+    block-structured on the device (A = M A_euclid M^-1 applied to the compact blocks) against the oracle's dense matrices."""
+    stream = make_stream(N=N, frames=3, coord=2, settings_overrides=overrides)
+    worst = _check(run_gpu(stream), run_oracle(stream), tol=1e-7)
+    print(f"N={N} Normal {overrides}: worst {worst:.3e}")
+
+
+def test_n64_discrete_state_matrix():
+    """useDiscreteStateMatrix (VIO_eqf.cpp:93-103, EqFMatrices.cpp:24-41) at N = 64, Euclidean chart."""
+    stream = make_stream(N=64, frames=3, coord=0, settings_overrides=dict(fastRiccati=False, useDiscreteStateMatrix=True))
+    _check(run_gpu(stream), run_oracle(stream), tol=1e-7)
+
+
+def test_large_step_exponential_uses_squarings():
+    """IMU decimated to the camera rate (one 0.05 s segment per frame): |dt [A B; 0 0]|_inf exceeds the Taylor radius of 1/4 and the
+    scaled exponential has to square (sensor ladder + landmark rows) -- against scipy's expm in the oracle."""
+    import eqvio_b200 as eb
+    from oracle import eqf
+
+    stream = make_stream(N=24, frames=4, coord=0, settings_overrides=dict(fastRiccati=False))
+    o = eqf.VIOFilter(stream["settings"], stream["init"], 0.0)
+    g, cam = gpu_filter(stream)
+    for k, fr in enumerate(stream["frames"]):
+        imu = fr.imu[:1]
+        for row in imu:
+            o.processIMUData(eqf.IMUVelocity(row[0], row[1:4], row[4:7], row[7:10], row[10:13]))
+        g.processIMUArray(imu)
+        o.augmentLandmarkStates(list(fr.ids), eqf.VIOState(None, fr.provided_p, fr.ids))
+        g.augmentLandmarkStates(fr.ids, eb.VIOState(eb.VIOSensorState(), fr.provided_p, fr.ids))
+        o.processVisionData(eqf.VisionMeasurement.fromArrays(fr.stamp, fr.ids, fr.y, stream["cam"]))
+        g.processVisionArrays(fr.stamp, fr.ids, fr.y, cam)
+        e = compare_states(snapshot_gpu(g), snapshot_oracle(o))
+        assert e["ids_equal"] and e["sigma"] < 1e-8 and e["state"] < 1e-8, (k, e)
+    g.close()
