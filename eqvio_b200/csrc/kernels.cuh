@@ -94,8 +94,18 @@ __device__ __forceinline__ void tl_mark(int slot, int end) {
     }
 }
 #define TL_MARK(slot, end) tl_mark(slot, end)
+// end stamp from a thread other than thread 0 (kernels whose thread 0 is not the last to finish)
+#define TL_MARK_END_BY(slot, tid)                                       \
+    do {                                                                \
+        if (threadIdx.x == (tid) && (slot) >= 0 && (slot) < TL_MAX) {   \
+            unsigned long long t_;                                      \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));      \
+            atomicMax(&g_tl[2 * (slot) + 1], t_);                       \
+        }                                                               \
+    } while (0)
 #else
 #define TL_MARK(slot, end) do { } while (0)
+#define TL_MARK_END_BY(slot, tid) do { } while (0)
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -632,24 +642,43 @@ __global__ void __launch_bounds__(OBSF_THREADS)
     Quat Q = Quat{lmIn[F_QW * cap + i], lmIn[F_QX * cap + i], lmIn[F_QY * cap + i], lmIn[F_QZ * cap + i]};
     double a_ = lmIn[F_QA * cap + i];
     const int id = idsIn[i];
+    // Discrete lift: the landmark estimate after a segment IS the moved point (Q' a' acts on q0 as p1), so the point is carried instead
+    // of re-derived from Q, a in every segment, and one reciprocal norm per vector serves the direction, FromTwoVectors and the scale:
+    // 3 sqrt + 3 div per segment instead of 7 + ~15 (observer_landmark_kernel keeps the reference's operation order; the two forms
+    // differ by rounding only).  With the chain at ~1.2 us per segment these ~600 fp64 instructions per warp were the pipeline's slow stage.
+    V3 p0 = landmark_action(Q, a_, q0);
     for (int s = 0; s < nsteps; ++s) {
         while (flag_acquire_cta(&s_ready) <= s) __nanosleep(20);
         const ObsStep& st = s_steps[s];
-        V3 p0 = landmark_action(Q, a_, q0);
         Quat LQ;
         double La;
-        if (st.discrete) {  // same arithmetic as observer_landmark_kernel
-            V3 p1 = se3_apply(st.camChangeInv, p0);
-            LQ = quat_from_two_vectors(normalized(p1), normalized(p0));
-            La = norm(p0) / norm(p1);
+        if (st.discrete) {
+            const V3 p1 = se3_apply(st.camChangeInv, p0);
+            const double r0 = sqrt(dot(p0, p0)), r1 = sqrt(dot(p1, p1));
+            const double i0 = 1.0 / r0, i1 = 1.0 / r1;
+            const V3 v0 = i1 * p1, v1 = i0 * p0;
+            const double c = dot(v1, v0);
+            if (c < -1.0 + 1e-12) {
+                LQ = quat_from_two_vectors(v0, v1);  // antipodal directions: the general routine
+            } else {
+                const V3 axis = cross(v0, v1);
+                const double sn = sqrt((1.0 + c) * 2.0);
+                const double invs = 1.0 / sn;
+                LQ = Quat{sn * 0.5, axis.x * invs, axis.y * invs, axis.z * invs};
+            }
+            La = r0 * i1;
+            Q = qmul(Q, LQ);
+            a_ = a_ * La;
+            p0 = p1;
         } else {
             double n2 = norm2(p0);
             V3 wv = st.omegaC + cross(p0, st.vC) / n2;
             LQ = so3_exp(st.dt * wv);
             La = exp(st.dt * (dot(p0, st.vC) / n2));
+            Q = qmul(Q, LQ);
+            a_ = a_ * La;
+            p0 = landmark_action(Q, a_, q0);
         }
-        Q = qmul(Q, LQ);
-        a_ = a_ * La;
     }
     lmOut[F_Q0X * cap + i] = q0.x;
     lmOut[F_Q0Y * cap + i] = q0.y;
@@ -660,7 +689,7 @@ __global__ void __launch_bounds__(OBSF_THREADS)
     lmOut[F_QZ * cap + i] = Q.z;
     lmOut[F_QA * cap + i] = a_;
     idsOut[i] = id;
-    TL_MARK(tl, 1);
+    TL_MARK_END_BY(tl, 32);  // the landmark warps finish after the chain thread
 }
 
 // ------------------------------------------------------------------------------------------------

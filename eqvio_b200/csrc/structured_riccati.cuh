@@ -61,7 +61,7 @@ __device__ __forceinline__ int exp_squarings(double norm) {
 
 // ------------------------------------------------------------------------------------------------
 // Compact dt [A B; 0 0] from the Riccati context of the sample (ctx->Fs = I + dt A_ss, dtBs = dt B_s) and the landmark rows of
-// landmark_rows_kernel (rows[i] = D(9) | G(36) | Bl(9): D = I + dt A_ii, G = dt A_is on the columns c_sidx, Bl = B_i[:, 0:3]).
+// the landmark CTAs of riccati_prep_kernel (rows[i] = D(9) | G(36) | Bl(9): D = I + dt A_ii, G = dt A_is on the columns c_sidx, Bl = B_i[:, 0:3]).
 // Block 0: sensor rows and the norm reset; block 1 + b: 128 landmarks.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)

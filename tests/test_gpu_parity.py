@@ -30,15 +30,17 @@ def _check(gpu, ref, tol=TOL):
 
 @pytest.mark.parametrize("discrete", [1, 0])
 def test_fused_observer_matches_two_kernel_form(discrete):
-    """integrateObserverState as one software-pipelined kernel (sensor chain publishing segments to the landmark warps)
-    vs the sensor kernel followed by the landmark kernel: same arithmetic, checked against each other and the oracle."""
+    """integrateObserverState as one software-pipelined kernel (helper warp / sensor chain / landmark warps) vs the sensor kernel
+    followed by the landmark kernel, which keeps the reference's operation order: the pipelined form carries the moved point and shares
+    reciprocal norms, so the two agree to rounding (a few ulp per segment), and both are checked against the oracle."""
     stream = make_stream(N=70, frames=8, coord=0, settings_overrides=dict(useDiscreteVelocityLift=bool(discrete)))
     ref = run_gpu(stream, tuning=dict(fuseObserver=0))
     got = run_gpu(stream, tuning=dict(fuseObserver=1))
     for g, r in zip(got, ref):
         e = compare_states(g, r)
-        assert e["ids_equal"] and e["sigma"] < 1e-13 and e["state"] < 1e-13
+        assert e["ids_equal"] and e["sigma"] < 1e-11 and e["state"] < 1e-11
     _check(got, run_oracle(stream))
+    _check(ref, run_oracle(stream))
 
 
 @pytest.mark.parametrize("N,chunk", [(40, 8), (100, 32), (150, 32)])
