@@ -748,6 +748,34 @@ int plan_integration(eqvio_filter* f, double newTime, int* advanced) {
 // Two independent chains (VIOFilter.cpp:138 "the Riccati propagation ... does not affect the state propagation"):
 //   stream : Riccati  -- context + Sigma_ss, landmark rows, strips, landmark-landmark block (reads X, Q *before*)
 //   stream2: observer -- sensor part of every IMU segment, then the landmark part (writes the other X / lm buffers)
+// Instantiations of the one-pass kernels by camera model / chart / lift form (kernels.cuh, gate_body): picked on the host per launch.
+using MeasFn = decltype(&meas_kernel<-1, -1>);
+using GateFn = decltype(&gate_kernel<-1, -1>);
+using LiftFn = decltype(&lift_kernel<-1, -1>);
+#define EQ_CAM_ROW(K, c) {K<CAM_PINHOLE, c>, K<CAM_RADTAN, c>, K<CAM_EQUIDISTANT, c>}
+static MeasFn meas_fn(const eqvio_filter* f) {
+    static const MeasFn t[3][3] = {EQ_CAM_ROW(meas_kernel, 0), EQ_CAM_ROW(meas_kernel, 1), EQ_CAM_ROW(meas_kernel, 2)};
+    const int c = f->st.coordinateChoice, m = f->pend.cam.model;
+    return (c >= 0 && c < 3 && m >= 0 && m < 3) ? t[c][m] : meas_kernel<-1, -1>;
+}
+static GateFn gate_fn(const eqvio_filter* f) {
+    static const GateFn t[3][3] = {EQ_CAM_ROW(gate_kernel, 0), EQ_CAM_ROW(gate_kernel, 1), EQ_CAM_ROW(gate_kernel, 2)};
+    const int c = f->st.coordinateChoice, m = f->pend.cam.model;
+    return (c >= 0 && c < 3 && m >= 0 && m < 3) ? t[c][m] : gate_kernel<-1, -1>;
+}
+#undef EQ_CAM_ROW
+using PrepFn = decltype(&riccati_prep_kernel<-1>);
+static PrepFn prep_fn(const eqvio_filter* f) {
+    static const PrepFn t[3] = {riccati_prep_kernel<0>, riccati_prep_kernel<1>, riccati_prep_kernel<2>};
+    const int c = f->st.coordinateChoice;
+    return (c >= 0 && c < 3) ? t[c] : riccati_prep_kernel<-1>;
+}
+static LiftFn lift_fn(const eqvio_filter* f) {
+    static const LiftFn t[3][2] = {{lift_kernel<0, 0>, lift_kernel<0, 1>}, {lift_kernel<1, 0>, lift_kernel<1, 1>}, {lift_kernel<2, 0>, lift_kernel<2, 1>}};
+    const int c = f->st.coordinateChoice;
+    return (c >= 0 && c < 3) ? t[c][f->st.useDiscreteInnovationLift ? 1 : 0] : lift_kernel<-1, -1>;
+}
+
 void fill_prep_args(eqvio_filter* f, PrepArgs& a) {
     const eqvio_settings& s = f->st;
     a.xi0s = f->d_xi0s;
@@ -800,7 +828,7 @@ int enqueue_propagation(eqvio_filter* f) {
         // C*, ytilde of the measured landmarks only read the landmarks the observer just integrated: right behind it on its stream,
         // beside the Riccati chain (the gate, which also needs the propagated Sigma, runs beside the sweep: enqueue_correction)
         const int nm = f->measHookNm;
-        meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream2>>>(f->lm[1 - f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
+        meas_fn(f)<<<cdiv(nm, 128), 128, 0, f->stream2>>>(f->lm[1 - f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
                                                            s.useEquivariantOutput ? 1 : 0, f->d_Cblk, f->d_ytilde, 1, 0, (const int*)(f->d_spec + 1),
                                                            f->d_yIdx, f->d_status, 1 + N, f->d_Gamma, dimp_of(N), (int*)nullptr, 0, TL_SLOT(f));
         LAUNCH_CHECK(f, "meas_kernel");
@@ -813,7 +841,7 @@ int enqueue_propagation(eqvio_filter* f) {
         const double* Sin = f->Sig[f->cur];
         double* Sout = f->Sig[1 - f->cur];
         // prologue + landmark rows in one launch; also re-arms the gate flag
-        riccati_prep_kernel<<<1 + cdiv(N, PREP_LM), PREP_THREADS, 0, f->stream>>>(a, Sin, Sout, f->ld, nullptr, f->d_spec, f->lm[f->lmcur], f->cap, N,
+        prep_fn(f)<<<1 + cdiv(N, PREP_LM), PREP_THREADS, 0, f->stream>>>(a, Sin, Sout, f->ld, nullptr, f->d_spec, f->lm[f->lmcur], f->cap, N,
                                                                                    s.coordinateChoice, f->d_rows, TL_SLOT(f));
         LAUNCH_CHECK(f, "riccati_prep_kernel");
         if (N > 0) {
@@ -886,7 +914,7 @@ int enqueue_sric_step(eqvio_filter* f, const PrepArgs& a, int mode, const double
     const double* Sin = f->Sig[f->cur];
     double* Sout = f->Sig[1 - f->cur];
     // sensor blocks of A, B for this step (the fused Sigma'_ss it also writes is overwritten by gprop_sensor_kernel below)
-    riccati_prep_kernel<<<1 + cdiv(N, PREP_LM), PREP_THREADS, 0, f->stream>>>(a, Sin, Sout, f->ld, w.dtBs, clearFlag, f->lm[f->lmcur], f->cap, N,
+    prep_fn(f)<<<1 + cdiv(N, PREP_LM), PREP_THREADS, 0, f->stream>>>(a, Sin, Sout, f->ld, w.dtBs, clearFlag, f->lm[f->lmcur], f->cap, N,
                                                                                s.coordinateChoice, f->d_rows, TL_SLOT(f));
     LAUNCH_CHECK(f, "riccati_prep_kernel");
     // integrateRiccatiStateAccurate: T = dt [A B; 0 0], E = exp(T).  integrateRiccatiStateDiscrete (VIO_eqf.cpp:93-103,
@@ -982,7 +1010,7 @@ int enqueue_propagation_per_sample(eqvio_filter* f) {
 
 int enqueue_gate(eqvio_filter* f, int N, bool clearFlag) {
     if (clearFlag) CUDA_TRY(f, cudaMemsetAsync(f->d_spec, 0, sizeof(int), f->stream));
-    launch_pdl(f, gate_kernel, dim3(cdiv(N, 128)), dim3(128), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, N, f->Sig[f->cur], f->ld, f->d_measIdx, f->d_y,
+    launch_pdl(f, gate_fn(f), dim3(cdiv(N, 128)), dim3(128), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, N, f->Sig[f->cur], f->ld, f->d_measIdx, f->d_y,
                                                       f->d_hdr, f->st.coordinateChoice, f->d_gate, f->st.outlierThresholdAbs,
                                                       f->st.outlierThresholdProb, f->d_spec, TL_SLOT(f));
     LAUNCH_CHECK(f, "gate_kernel");
@@ -1009,14 +1037,22 @@ int enqueue_steady_update(eqvio_filter* f, int N, int nm, const FramePlan* plan)
         const size_t pfBytes = f->prefetchSigma ? (size_t)f->ld * dimp_of(N) * sizeof(double) : 0;
         PrefetchList small = {};
         if (f->prefetchSigma) {
-            small.p[0] = reinterpret_cast<const char*>(f->d_xi0s);
-            small.bytes[0] = 23 * sizeof(double);
-            small.p[1] = reinterpret_cast<const char*>(f->d_Xs[f->xcur]);
-            small.bytes[1] = 23 * sizeof(double);
-            small.p[2] = reinterpret_cast<const char*>(f->lm[f->lmcur]);
-            small.bytes[2] = (unsigned)((size_t)LM_FIELDS * std::max(f->cap, 1) * sizeof(double));
-            small.p[3] = reinterpret_cast<const char*>(f->dids[f->lmcur]);
-            small.bytes[3] = (unsigned)(std::max(f->cap, 1) * sizeof(int));
+            const size_t c1 = std::max(f->cap, 1);
+            auto add = [&](const void* p, size_t bytes, unsigned stride) {
+                if (p && bytes && small.n < PF_MAX) {
+                    small.p[small.n] = reinterpret_cast<const char*>(p);
+                    small.bytes[small.n] = (unsigned)std::min(bytes, (size_t)0xFFFFFFF0u);
+                    small.stride[small.n++] = stride;
+                }
+            };
+            // read first by the prologue / the observer chain: every line
+            add(f->d_xi0s, 23 * sizeof(double), 128);
+            add(f->d_Xs[f->xcur], 23 * sizeof(double), 128);
+            add(f->lm[f->lmcur], LM_FIELDS * c1 * sizeof(double), 128);
+            add(f->dids[f->lmcur], c1 * sizeof(int), 128);
+            // (touching every scratch / output buffer as well -- in case the first access to their pages paid a cold translation -- was
+            // measured and changes nothing: the cold-L2 penalty of the one-pass kernels, +8 us in the prologue, +4 us in the measurement
+            // rows, is not a data miss)
         }
         block_copy_kernel<<<2 + (pfBytes ? 64 : 0), 256, 0, f->stream>>>(reinterpret_cast<const double2*>(f->hd_frame), reinterpret_cast<double2*>(f->d_frame),
                                                                         (int)(f->frameBytes / 16), 2, reinterpret_cast<const char*>(f->Sig[f->cur]), pfBytes,
@@ -1218,7 +1254,7 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
             const eqvio_settings& st = f->st;
             std::vector<int> key = {N, n, f->cur, f->lmcur, f->xcur, f->chunkLm, f->corrMode, st.coordinateChoice, st.useDiscreteVelocityLift,
                                     st.useDiscreteInnovationLift, st.useEquivariantOutput, f->maxSteps, f->yCap,
-                                    change ? 1 : 0, Nout, plan.nNew > 0 ? 1 : 0, P.ignoreGate ? 1 : 0,
+                                    change ? 1 : 0, Nout, plan.nNew > 0 ? 1 : 0, P.ignoreGate ? 1 : 0, P.cam.model,
                                     // the observer kernel form is chosen on the host from the number of buffered IMU segments
                                     reinterpret_cast<const FrameHeader*>(f->h_frame)->fs.nsteps <= OBS_STAGE ? 1 : 0};
             auto it = f->graphs.find(key);
@@ -1616,7 +1652,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
             // the kernels that touch the filter state (trailing tiles of Sigma / Gamma, lift) look at its flag
             CUDA_TRY(f, cudaEventRecord(f->evG0, f->stream));
             CUDA_TRY(f, cudaStreamWaitEvent(f->stream5, f->evG0, 0));
-            gate_kernel<<<cdiv(Nn, 128), 128, 0, f->stream5>>>(f->lm[f->lmcur], f->cap, Nn, f->Sig[f->cur], f->ld, f->d_measIdx, f->d_y, f->d_hdr,
+            gate_fn(f)<<<cdiv(Nn, 128), 128, 0, f->stream5>>>(f->lm[f->lmcur], f->cap, Nn, f->Sig[f->cur], f->ld, f->d_measIdx, f->d_y, f->d_hdr,
                                                                s.coordinateChoice, f->d_gate, s.outlierThresholdAbs, s.outlierThresholdProb, f->d_spec,
                                                                TL_SLOT(f));
             LAUNCH_CHECK(f, "gate_kernel");
@@ -1632,7 +1668,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                        (const int*)f->d_yIdx, f->d_status, 1 + Nn, gin, dimp, (int*)nullptr, 0, TL_SLOT(f));
             LAUNCH_CHECK(f, "gate_meas_kernel");
         } else {
-        meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
+        meas_fn(f)<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
                                                           s.useEquivariantOutput ? 1 : 0, f->d_Cblk, f->d_ytilde, 1, 0, guard, f->d_yIdx,
                                                           f->d_status, 1 + Nn, gin, dimp, (int*)nullptr, 0, TL_SLOT(f));
         LAUNCH_CHECK(f, "meas_kernel");
@@ -1751,7 +1787,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
         gammaFinal = gin;
         }
     } else {
-    meas_kernel<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
+    meas_fn(f)<<<cdiv(nm, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
                                                       s.useEquivariantOutput ? 1 : 0, f->d_Cblk, Z, ldz, m + dimp, guard, f->d_yIdx,
                                                       nullptr, 0, nullptr, 0, nullptr, 0, TL_SLOT(f));
     LAUNCH_CHECK(f, "meas_kernel");
@@ -1787,7 +1823,7 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
     gamma_kernel<<<cdiv(dimp, 128), 128, m * sizeof(double), f->stream>>>(Z, ldz, m, dimp, f->d_Gamma);
     LAUNCH_CHECK(f, "gamma_kernel");
     }
-    launch_pdl(f, lift_kernel, dim3(cdiv(std::max(Nn, 1), 128)), dim3(128), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, Nn, f->d_xi0s, f->d_Xs[f->xcur], gammaFinal,
+    launch_pdl(f, lift_fn(f), dim3(cdiv(std::max(Nn, 1), 128)), dim3(128), (size_t)(0), f->stream, f->lm[f->lmcur], f->cap, Nn, f->d_xi0s, f->d_Xs[f->xcur], gammaFinal,
                                                                    s.useDiscreteInnovationLift ? 1 : 0, s.coordinateChoice,
                                                                    f->d_status, f->d_status + 1, guard, fuseEst ? f->d_out : (double*)nullptr,
                                                                    s.coordinateChoice == EQVIO_COORD_NORMAL ? (const double*)(f->d_normalM + 441) : (const double*)nullptr, TL_SLOT(f));

@@ -117,9 +117,14 @@ __device__ __forceinline__ void tl_mark(int slot, int end) {
 // frame upload of a steady update carries a prefetch of the covariance, so that the latency-bound propagation kernels that follow
 // find it in L2 instead of paying an HBM round trip per dependent access (the step starts with a cold L2 in every deployment where
 // other work ran since the previous frame; bench.py flushes it).
-struct PrefetchList {  // small state arrays the update reads first (group / origin sensor parts, landmark SoA, ids): a cold miss on each of
-    const char* p[4];  // them is a dependent HBM round trip in the one-thread Riccati prologue and the observer chain
-    unsigned bytes[4];
+// Small state arrays the update reads first (group / origin sensor parts, landmark SoA, ids): a cold miss on each of them is a dependent
+// HBM round trip in the one-thread Riccati prologue and the observer chain.
+constexpr int PF_MAX = 8;
+struct PrefetchList {
+    const char* p[PF_MAX];
+    unsigned bytes[PF_MAX];
+    unsigned stride[PF_MAX];  // 128 = every line
+    int n;
 };
 __global__ void __launch_bounds__(256) block_copy_kernel(const double2* __restrict__ src, double2* __restrict__ dst, int n16, int copyBlocks,
                                                          const char* __restrict__ pf, size_t pfBytes, PrefetchList small, int tl) {
@@ -127,9 +132,9 @@ __global__ void __launch_bounds__(256) block_copy_kernel(const double2* __restri
     TL_MARK(tl, 0);
     if ((int)blockIdx.x < copyBlocks) {
         if (blockIdx.x == 0) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                for (unsigned o = threadIdx.x * 128u; o < small.bytes[k]; o += blockDim.x * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(small.p[k] + o));
+            for (int k = 0; k < small.n; ++k)
+                for (unsigned o = threadIdx.x * small.stride[k]; o < small.bytes[k]; o += blockDim.x * small.stride[k])
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(small.p[k] + o));
         }
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += copyBlocks * blockDim.x) dst[i] = src[i];
     } else {
@@ -362,33 +367,39 @@ __device__ __forceinline__ void landmark_rows_body(const double* __restrict__ lm
 // the sensor block;  CTA 1 + b computes the Riccati rows of landmarks 64 b .. 64 b + 63 from ITS OWN copy of the landmark-row context (parts
 // 1 and 2, in shared memory) -- redundant per CTA, but the rows no longer wait for a kernel boundary behind the serial prologue.
 constexpr int PREP_THREADS = 448, PREP_LM = 64;
+template <int COORD>  // chart known at compile time on the launch sites (>= 0), see gate_body
 __global__ void __launch_bounds__(PREP_THREADS)
     riccati_prep_kernel(PrepArgs a, const double* __restrict__ Sin, double* __restrict__ Sout, int ld, double* __restrict__ dtBsOut,
-                        int* __restrict__ clearFlag, const double* __restrict__ lm, int cap, int N, int coord, double* __restrict__ rows, int tl) {
+                        int* __restrict__ clearFlag, const double* __restrict__ lm, int cap, int N, int coord_, double* __restrict__ rows, int tl) {
     pdl_wait();
     TL_MARK(tl, 0);
     const int t = threadIdx.x;
-    if (blockIdx.x > 0) {
-        __shared__ RiccatiCtx sCtx;
-        if (t == 32) riccati_small_part(a, sCtx, nullptr, nullptr, 1);
-        if (t == 64) riccati_small_part(a, sCtx, nullptr, nullptr, 2);
+    const int coord = COORD >= 0 ? COORD : coord_;
+    const bool lead = blockIdx.x == 0;
+    __shared__ RiccatiCtx sCtx;  // landmark CTAs: their own copy of the landmark-row context
+    __shared__ double sAs[441], sBs[252], sF[441], sS[441], sT[441];
+    RiccatiCtx& ctx = lead ? *a.ctx : sCtx;
+    if (lead) {
+        if (clearFlag && t == 447) *clearFlag = 0;  // first kernel of an update: re-arm the gate flag (no memset node)
+        if (t < 441) {
+            const int r = t / 21, c = t % 21;
+            sAs[t] = 0.0;
+            if (t < 252) sBs[t] = 0.0;
+            sS[t] = Sin[(size_t)c * ld + r];  // sS[r*21+c] = Sigma[r,c]
+        }
         __syncthreads();
+    }
+    // one inlined copy of each part serves the lead CTA and the landmark CTAs
+    if (t == 0 && lead) riccati_small_part(a, ctx, sAs, sBs, 0);
+    if (t == 32) riccati_small_part(a, ctx, lead ? sAs : nullptr, sBs, 1);
+    if (t == 64) riccati_small_part(a, ctx, sAs, sBs, 2);
+    __syncthreads();
+    if (!lead) {
         const int i = (blockIdx.x - 1) * PREP_LM + t;
         if (t < PREP_LM && i < N) landmark_rows_body(lm, cap, i, &sCtx, coord, rows);
         TL_MARK(tl, 1);
         return;
     }
-    __shared__ double sAs[441], sBs[252], sF[441], sS[441], sT[441];
-    if (clearFlag && t == 447) *clearFlag = 0;  // first kernel of an update: re-arm the gate flag (no memset node)
-    if (t < 441) {
-        const int r = t / 21, c = t % 21;
-        sAs[t] = 0.0;
-        if (t < 252) sBs[t] = 0.0;
-        sS[t] = Sin[(size_t)c * ld + r];  // sS[r*21+c] = Sigma[r,c]
-    }
-    __syncthreads();
-    if (t == 0 || t == 32 || t == 64) riccati_small_part(a, *a.ctx, sAs, sBs, t / 32);
-    __syncthreads();
     double ns = 0.0;
     if (t < 441) {
         double fs;
@@ -815,6 +826,18 @@ __global__ void __launch_bounds__(TP* TP)
     __shared__ double sSS[144];                  // ownFactors: Sigma[sidx, sidx]
     const int tid = threadIdx.y * TP + threadIdx.x;
     const int i0 = ti * TP, j0 = tj * TP;
+    // the thread's 3 x 3 block of Sigma first: its loads are in flight while the factors are built
+    const int li = threadIdx.x, lj = threadIdx.y;  // threadIdx.x walks rows (contiguous in memory)
+    const int i = i0 + li, j = j0 + lj;
+    const bool valid = i < N && j < N;
+    const int r0 = SOFF + 3 * i, c0 = SOFF + 3 * j;
+    double S[9];  // S[a*3+b] = Sigma[r0+a, c0+b]
+    if (valid) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) S[a * 3 + b] = Sin[(size_t)(c0 + b) * ld + r0 + a];
+    }
     if (ownFactors) {
         // U of the 16 row landmarks and V of the 16 column landmarks from the Riccati rows and Sigma's sensor strip -- the expressions of
         // prop_strip_kernel (which then only writes the sensor-landmark block, beside this kernel on another stream): 480 work items of
@@ -826,23 +849,33 @@ __global__ void __launch_bounds__(TP* TP)
         }
         if (tid < 144) sSS[tid] = Sin[(size_t)c_sidx[tid % 12] * ld + c_sidx[tid / 12]];  // sSS[k * 12 + t] = Sigma[sidx[k], sidx[t]]
         const double cg = ctx->cg;
-        __syncthreads();
-        for (int item = tid; item < 2 * TP * 15; item += TP * TP) {
+        // the Sigma entries of both rounds of work items, ahead of the barrier
+        double Lp[2][3];
+#pragma unroll
+        for (int rd = 0; rd < 2; ++rd) {
+            const int item = tid + rd * TP * TP;
             const int w = item / (TP * 15), l = (item / 15) % TP, t = item % 15;
             const int lmk = (w ? j0 : i0) + l;
+            Lp[rd][0] = Lp[rd][1] = Lp[rd][2] = 0.0;
+            if (item < 2 * TP * 15 && t < 12 && lmk < N) {
+                const size_t o = (size_t)c_sidx[t] * ld + SOFF + 3 * lmk;
+                Lp[rd][0] = Sin[o];
+                Lp[rd][1] = Sin[o + 1];
+                Lp[rd][2] = Sin[o + 2];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rd = 0; rd < 2; ++rd) {
+            const int item = tid + rd * TP * TP;
+            if (item >= 2 * TP * 15) break;
+            const int w = item / (TP * 15), l = (item / 15) % TP, t = item % 15;
             const double* D = sRow[w][l];
             const double* G = D + 9;
             const double* Bl = D + 45;
             double* out = w ? sV[l] : sU[l];
             if (t < 12) {
-                const int sc = c_sidx[t];
-                const int r0 = SOFF + 3 * lmk;
-                double L0 = 0.0, L1 = 0.0, L2 = 0.0;
-                if (lmk < N) {
-                    L0 = Sin[(size_t)sc * ld + r0];
-                    L1 = Sin[(size_t)sc * ld + r0 + 1];
-                    L2 = Sin[(size_t)sc * ld + r0 + 2];
-                }
+                const double L0 = Lp[rd][0], L1 = Lp[rd][1], L2 = Lp[rd][2];
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
                     const double e = D[3 * a] * L0 + D[3 * a + 1] * L1 + D[3 * a + 2] * L2;
@@ -880,13 +913,7 @@ __global__ void __launch_bounds__(TP* TP)
         }
     }
     __syncthreads();
-    const int li = threadIdx.x, lj = threadIdx.y;  // threadIdx.x walks rows (contiguous in memory)
-    const int i = i0 + li, j = j0 + lj;
-    if (i >= N || j >= N) { TL_MARK(tl, 1); return; }
-    const int r0 = SOFF + 3 * i, c0 = SOFF + 3 * j;
-    double S[9];  // S[a*3+b] = Sigma[r0+a, c0+b]
-    for (int b = 0; b < 3; ++b)
-        for (int a = 0; a < 3; ++a) S[a * 3 + b] = Sin[(size_t)(c0 + b) * ld + r0 + a];
+    if (!valid) { TL_MARK(tl, 1); return; }
     double T[9];
     for (int a = 0; a < 3; ++a)
         for (int b = 0; b < 3; ++b)
@@ -919,13 +946,20 @@ __global__ void __launch_bounds__(TP* TP)
 // (VIOFilter.cpp:304-336, VIO_eqf.cpp:196-211, VIOFilter.cpp:366-380).
 // measIdx[i] = index of landmark i's pixel in y, or -1.   out: errAbs[N] | errProb[N] | depth2[N]
 // ------------------------------------------------------------------------------------------------
+// MODEL / COORD >= 0: camera model and chart known at compile time (the host picks the instantiation from the frame's camera and the
+// settings): the one-pass kernels gate / meas / lift carry ~100-180 KB of SASS for all cameras, charts and lift forms, and after other
+// work ran on the GPU the executed path is fetched from HBM line by line (+3.6 ... +4.3 us per kernel with a cold L2) -- a specialised
+// instantiation runs a compact straight-line path.  -1 = decide at run time (same code, every site that is not on the steady path).
+template <int MODEL, int COORD>
 __device__ __forceinline__ void gate_body(int bid, const double* __restrict__ lm, int cap, int N, const double* __restrict__ Sig, int ld,
                                           const int* __restrict__ measIdx, const double* __restrict__ y, const FrameHeader* __restrict__ fr,
-                                          int coord, double* __restrict__ out, double thrAbs, double thrProb, int* __restrict__ tripped,
+                                          int coord_, double* __restrict__ out, double thrAbs, double thrProb, int* __restrict__ tripped,
                                           int tl) {
     int i = bid * blockDim.x + threadIdx.x;
     if (i >= N) { TL_MARK(tl, 1); return; }
-    const Camera cam = fr->cam;
+    Camera cam = fr->cam;
+    if (MODEL >= 0) cam.model = MODEL;
+    const int coord = COORD >= 0 ? COORD : coord_;
     V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
     Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
     double a = lm[F_QA * cap + i];
@@ -962,12 +996,13 @@ __device__ __forceinline__ void gate_body(int bid, const double* __restrict__ lm
     if (out[i] > thrAbs || eProb > thrProb) atomicOr(tripped, 1);  // same comparisons as the host decision
     TL_MARK(tl, 1);
 }
+template <int MODEL, int COORD>
 __global__ void gate_kernel(const double* __restrict__ lm, int cap, int N, const double* __restrict__ Sig, int ld,
                             const int* __restrict__ measIdx, const double* __restrict__ y, const FrameHeader* __restrict__ fr, int coord,
                             double* __restrict__ out, double thrAbs, double thrProb, int* __restrict__ tripped, int tl) {
     pdl_wait();
     TL_MARK(tl, 0);
-    gate_body(blockIdx.x, lm, cap, N, Sig, ld, measIdx, y, fr, coord, out, thrAbs, thrProb, tripped, tl);
+    gate_body<MODEL, COORD>(blockIdx.x, lm, cap, N, Sig, ld, measIdx, y, fr, coord, out, thrAbs, thrProb, tripped, tl);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1099,8 +1134,9 @@ __global__ void fill_ll_diag_kernel(double* __restrict__ S, int ld, int n3, doub
 // (VIOState.cpp:70-78, VisionMeasurement.cpp:60-79, EqFMatrices.cpp:43-82).
 // Writes Cblk[j] (2x3 row-major) and the ytilde row of Z.
 // ------------------------------------------------------------------------------------------------
+template <int MODEL, int COORD>
 __device__ __forceinline__ void meas_body(int bid, int nblk, const double* __restrict__ lm, int cap, const int* __restrict__ lmOf, int n,
-                            const double* __restrict__ y, const FrameHeader* __restrict__ fr, int coord, int useStar,
+                            const double* __restrict__ y, const FrameHeader* __restrict__ fr, int coord_, int useStar,
                             double* __restrict__ Cblk, double* __restrict__ Z, int ldz, int yrow,
                             const int* __restrict__ guard, const int* __restrict__ yIdx, int* __restrict__ zeroStatus, int nStatus,
                             double* __restrict__ zeroGamma, int nGamma, int* __restrict__ zeroCnt, int nCnt, int tl) {
@@ -1111,7 +1147,9 @@ __device__ __forceinline__ void meas_body(int bid, int nblk, const double* __res
     for (int t = j; t < nCnt; t += nblk * blockDim.x) zeroCnt[t] = 0;
     if (j >= n || *guard) { TL_MARK(tl, 1); return; }
     const int jm = yIdx ? yIdx[j] : j;  // row pair j of the correction takes the pixel of measurement jm
-    const Camera cam = fr->cam;
+    Camera cam = fr->cam;
+    if (MODEL >= 0) cam.model = MODEL;
+    const int coord = COORD >= 0 ? COORD : coord_;
     int i = lmOf[j];
     V3 q0 = V3{lm[F_Q0X * cap + i], lm[F_Q0Y * cap + i], lm[F_Q0Z * cap + i]};
     Quat Q = Quat{lm[F_QW * cap + i], lm[F_QX * cap + i], lm[F_QY * cap + i], lm[F_QZ * cap + i]};
@@ -1127,6 +1165,7 @@ __device__ __forceinline__ void meas_body(int bid, int nblk, const double* __res
     for (int k = 0; k < 6; ++k) Cblk[6 * j + k] = C[k];
     TL_MARK(tl, 1);
 }
+template <int MODEL, int COORD>
 __global__ void meas_kernel(const double* __restrict__ lm, int cap, const int* __restrict__ lmOf, int n,
                             const double* __restrict__ y, const FrameHeader* __restrict__ fr, int coord, int useStar,
                             double* __restrict__ Cblk, double* __restrict__ Z, int ldz, int yrow,
@@ -1134,7 +1173,7 @@ __global__ void meas_kernel(const double* __restrict__ lm, int cap, const int* _
                             double* __restrict__ zeroGamma, int nGamma, int* __restrict__ zeroCnt, int nCnt, int tl) {
     pdl_wait();
     TL_MARK(tl, 0);
-    meas_body(blockIdx.x, gridDim.x, lm, cap, lmOf, n, y, fr, coord, useStar, Cblk, Z, ldz, yrow, guard, yIdx, zeroStatus, nStatus, zeroGamma, nGamma, zeroCnt, nCnt, tl);
+    meas_body<MODEL, COORD>(blockIdx.x, gridDim.x, lm, cap, lmOf, n, y, fr, coord, useStar, Cblk, Z, ldz, yrow, guard, yIdx, zeroStatus, nStatus, zeroGamma, nGamma, zeroCnt, nCnt, tl);
 }
 // Steady update: the gate (per state landmark) and the measurement rows C*, ytilde (per measured landmark) only read the
 // propagated state, so they run as ONE launch -- the first gateBlocks CTAs gate, the others build the rows.  The rows are
@@ -1149,9 +1188,9 @@ __global__ void gate_meas_kernel(int gateBlocks, const double* __restrict__ lm, 
     pdl_wait();
     TL_MARK(tl, 0);
     if ((int)blockIdx.x < gateBlocks)
-        gate_body(blockIdx.x, lm, cap, N, Sig, ld, measIdx, yAll, fr, coord, gateOut, thrAbs, thrProb, tripped, tl);
+        gate_body<-1, -1>(blockIdx.x, lm, cap, N, Sig, ld, measIdx, yAll, fr, coord, gateOut, thrAbs, thrProb, tripped, tl);
     else
-        meas_body(blockIdx.x - gateBlocks, gridDim.x - gateBlocks, lm, cap, lmOf, n, y, fr, coord, useStar, Cblk, Z, ldz, yrow, zeroGuard,
+        meas_body<-1, -1>(blockIdx.x - gateBlocks, gridDim.x - gateBlocks, lm, cap, lmOf, n, y, fr, coord, useStar, Cblk, Z, ldz, yrow, zeroGuard,
                   yIdx, zeroStatus, nStatus, zeroGamma, nGamma, zeroCnt, nCnt, tl);
 }
 
@@ -2155,8 +2194,9 @@ __global__ void gamma_kernel(const double* __restrict__ Z, int ldz, int m, int d
 // (VIO_eqf.cpp:213-223).  status: bit0 = non-SPD S, bit1 = NaN, invalidFlag[i] = 1 if Q.a is out of
 // (1e-8, 1e8].  Gamma uses the internal index (landmark i at SOFF + 3 i).
 // ------------------------------------------------------------------------------------------------
+template <int COORD, int DISCRETE>
 __global__ void lift_kernel(double* __restrict__ lm, int cap, int N, const double* __restrict__ xi0s,
-                            double* __restrict__ Xs, const double* __restrict__ Gamma, int discrete, int coord,
+                            double* __restrict__ Xs, const double* __restrict__ Gamma, int discrete_, int coord_,
                             int* __restrict__ status, int* __restrict__ invalidFlag, const int* __restrict__ guard,
                             double* __restrict__ estOut /* may be null: sensor(23) | p(3N) of the corrected state */,
                             const double* __restrict__ MsInv /* Normal chart: inverse sensor block of the coordinate differential */,
@@ -2164,6 +2204,8 @@ __global__ void lift_kernel(double* __restrict__ lm, int cap, int N, const doubl
     pdl_wait();
     TL_MARK(tl, 0);
     if (*guard) { TL_MARK(tl, 1); return; }
+    const int coord = COORD >= 0 ? COORD : coord_;      // compile-time chart / lift form on the steady path (see gate_body)
+    const int discrete = DISCRETE >= 0 ? DISCRETE : discrete_;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         SensorState xi0 = unpack_sensor(xi0s);
