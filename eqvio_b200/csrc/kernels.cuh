@@ -817,16 +817,19 @@ __global__ void __launch_bounds__(TP* TP)
     prop_ll_kernel(const double* __restrict__ Sin, double* __restrict__ Sout, int ld, int N,
                    const RiccatiCtx* __restrict__ ctx, const double* __restrict__ rows,
                    const double* __restrict__ uv, int ownFactors, int tl) {
-    pdl_wait();
-    TL_MARK(tl, 0);
     const int ti = blockIdx.y, tj = blockIdx.x;
-    if (tj > ti) { TL_MARK(tl, 1); return; }
+    if (tj > ti) {
+        pdl_wait();
+        return;
+    }
     __shared__ double sU[TP][82], sV[TP][82], sDi[TP][9], sDj[TP][9];
     __shared__ double sRow[2][TP][ROWS_STRIDE];  // ownFactors: D(9) | G(36) | Bl(9) of the tile's row / column landmarks
     __shared__ double sSS[144];                  // ownFactors: Sigma[sidx, sidx]
     const int tid = threadIdx.y * TP + threadIdx.x;
     const int i0 = ti * TP, j0 = tj * TP;
-    // the thread's 3 x 3 block of Sigma first: its loads are in flight while the factors are built
+    // Everything this kernel reads from Sigma_in is issued AHEAD of the dependency wait: the preceding grid (the Riccati prologue) does
+    // not write Sigma_in, and under programmatic dependent launch these CTAs are resident while it runs -- the loads (the thread's
+    // 3 x 3 block, the sensor strip entries of the factor work items, Sigma[sidx, sidx]) are then off the chain prologue -> ll.
     const int li = threadIdx.x, lj = threadIdx.y;  // threadIdx.x walks rows (contiguous in memory)
     const int i = i0 + li, j = j0 + lj;
     const bool valid = i < N && j < N;
@@ -838,19 +841,9 @@ __global__ void __launch_bounds__(TP* TP)
 #pragma unroll
             for (int a = 0; a < 3; ++a) S[a * 3 + b] = Sin[(size_t)(c0 + b) * ld + r0 + a];
     }
+    double Lp[2][3];  // ownFactors: the Sigma entries of both rounds of work items
     if (ownFactors) {
-        // U of the 16 row landmarks and V of the 16 column landmarks from the Riccati rows and Sigma's sensor strip -- the expressions of
-        // prop_strip_kernel (which then only writes the sensor-landmark block, beside this kernel on another stream): 480 work items of
-        // 3 loads + <= 45 FMAs instead of a kernel boundary on the chain prologue -> rows -> strip -> ll.
-        for (int t = tid; t < 2 * TP * ROWS_STRIDE; t += TP * TP) {
-            const int w = t / (TP * ROWS_STRIDE), l = (t / ROWS_STRIDE) % TP, k = t % ROWS_STRIDE;
-            const int lmk = (w ? j0 : i0) + l;
-            sRow[w][l][k] = lmk < N ? rows[(size_t)lmk * ROWS_STRIDE + k] : 0.0;
-        }
         if (tid < 144) sSS[tid] = Sin[(size_t)c_sidx[tid % 12] * ld + c_sidx[tid / 12]];  // sSS[k * 12 + t] = Sigma[sidx[k], sidx[t]]
-        const double cg = ctx->cg;
-        // the Sigma entries of both rounds of work items, ahead of the barrier
-        double Lp[2][3];
 #pragma unroll
         for (int rd = 0; rd < 2; ++rd) {
             const int item = tid + rd * TP * TP;
@@ -864,6 +857,19 @@ __global__ void __launch_bounds__(TP* TP)
                 Lp[rd][2] = Sin[o + 2];
             }
         }
+    }
+    pdl_wait();
+    TL_MARK(tl, 0);
+    if (ownFactors) {
+        // U of the 16 row landmarks and V of the 16 column landmarks from the Riccati rows and Sigma's sensor strip -- the expressions of
+        // prop_strip_kernel (which then only writes the sensor-landmark block, beside this kernel on another stream): 480 work items of
+        // 3 loads + <= 45 FMAs instead of a kernel boundary on the chain prologue -> rows -> strip -> ll.
+        for (int t = tid; t < 2 * TP * ROWS_STRIDE; t += TP * TP) {
+            const int w = t / (TP * ROWS_STRIDE), l = (t / ROWS_STRIDE) % TP, k = t % ROWS_STRIDE;
+            const int lmk = (w ? j0 : i0) + l;
+            sRow[w][l][k] = lmk < N ? rows[(size_t)lmk * ROWS_STRIDE + k] : 0.0;
+        }
+        const double cg = ctx->cg;
         __syncthreads();
 #pragma unroll
         for (int rd = 0; rd < 2; ++rd) {

@@ -28,8 +28,8 @@ int hook_sensor_prep(const double* xi0s, double* Xs, const double* imu, int nste
     for (int k = 0; k < 8; ++k) a.pdiag[k] = pdiag[k];
     double XsOut[23];
     a.XsOut = XsOut;
-    double As[441], Bs[252];
-    riccati_small(a, As, Bs);
+    double As[441] = {0.0}, Bs[252] = {0.0};  // zero on entry, as the kernel's shared arrays are
+    for (int part = 0; part < 3; ++part) riccati_small_part(a, ctx, As, Bs, part);
     for (int t = 0; t < 441; ++t) {
         double fs, ns;
         riccati_entry(a, As, Bs, t, fs, ns);
