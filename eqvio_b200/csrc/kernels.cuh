@@ -864,10 +864,14 @@ __global__ void __launch_bounds__(TP* TP)
         // U of the 16 row landmarks and V of the 16 column landmarks from the Riccati rows and Sigma's sensor strip -- the expressions of
         // prop_strip_kernel (which then only writes the sensor-landmark block, beside this kernel on another stream): 480 work items of
         // 3 loads + <= 45 FMAs instead of a kernel boundary on the chain prologue -> rows -> strip -> ll.
-        for (int t = tid; t < 2 * TP * ROWS_STRIDE; t += TP * TP) {
-            const int w = t / (TP * ROWS_STRIDE), l = (t / ROWS_STRIDE) % TP, k = t % ROWS_STRIDE;
-            const int lmk = (w ? j0 : i0) + l;
-            sRow[w][l][k] = lmk < N ? rows[(size_t)lmk * ROWS_STRIDE + k] : 0.0;
+        {  // the rows of 16 consecutive landmarks are one contiguous run: flat coalesced copies, no index arithmetic
+            double* fr0 = &sRow[0][0][0];
+            double* fr1 = &sRow[1][0][0];
+            const size_t lim = (size_t)N * ROWS_STRIDE, o0 = (size_t)i0 * ROWS_STRIDE, o1 = (size_t)j0 * ROWS_STRIDE;
+            for (int t = tid; t < TP * ROWS_STRIDE; t += TP * TP) {
+                fr0[t] = o0 + t < lim ? rows[o0 + t] : 0.0;
+                fr1[t] = o1 + t < lim ? rows[o1 + t] : 0.0;
+            }
         }
         const double cg = ctx->cg;
         __syncthreads();
