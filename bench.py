@@ -80,6 +80,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--landmarks", type=int, default=256)
     ap.add_argument("--coord", type=int, default=0)
+    ap.add_argument("--riccati", choices=["fast", "accurate", "discrete"], default="fast",
+                    help="Riccati variant of the filters (default fast = the benchmark workload; the others are side measurements, "
+                    "use with --no-cpu-baseline --no-sweep --batched-sequences 0)")
     ap.add_argument("--sequences-per-gpu", type=int, default=1, help="independent sequences (replicas) run concurrently per GPU")
     ap.add_argument("--batched-correction", type=int, default=0, choices=[0, 2],
                     help="correction form of the batched leg's filters: 0 = sequential chunks (default there: with 16 sequences "
@@ -102,14 +105,22 @@ def parse():
     return ap.parse_args()
 
 
+RICCATI = "fast"  # --riccati: side measurements of the per-sample Riccati variants (not the headline workload)
+
+
 def settings_dict(coord):
     """Benchmark filter settings (SURVEY.md 8d): struct defaults of VIOFilter::Settings with fastRiccati on."""
+    if RICCATI == "accurate":  # the struct default: integrateRiccatiStateAccurate per IMU sample
+        return dict(fastRiccati=0, coordinateChoice=coord)
+    if RICCATI == "discrete":
+        return dict(fastRiccati=0, useDiscreteStateMatrix=1, coordinateChoice=coord)
     return dict(fastRiccati=1, coordinateChoice=coord)
 
 
 def workload_name(N, coord):
     return (f"VIOSimulator wave, N={N} landmarks, fp64 Sigma (dim {21 + 3 * N}), {('Euclidean', 'InvDepth', 'Normal')[coord]} chart, "
-            "fastRiccati, 10 IMU samples per update")
+            + {"fast": "fastRiccati", "accurate": "fastRiccati=false (matrix exponential per IMU sample)",
+               "discrete": "fastRiccati=false, useDiscreteStateMatrix (per IMU sample)"}[RICCATI] + ", 10 IMU samples per update")
 
 
 # ---- algorithmic work per update (DESIGN.md "Roofline bookkeeping", SURVEY.md 8d) -------------------------
@@ -745,7 +756,9 @@ def run_b200(args, rank, local_rank, world, guard):
 
 
 def main():
+    global RICCATI
     args = parse()
+    RICCATI = args.riccati
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -44,11 +44,11 @@ extern "C" {
 #define EQVIO_ERR_NUMERIC (-3)     /* NaN / non-SPD innovation covariance detected on device */
 #define EQVIO_ERR_CAPACITY (-4)    /* more landmarks than the handle was created for */
 #define EQVIO_ERR_UNSUPPORTED (-5) /* something this build has no CUDA path for (an unknown coordinateChoice, a camera model other
-                                      than pinhole / radtan / equidistant, cuBLAS / cuSOLVER missing for the dense variants) */
+                                      than pinhole / radtan / equidistant) */
 
 #define EQVIO_COORD_EUCLIDEAN 0
 #define EQVIO_COORD_INVDEPTH 1
-#define EQVIO_COORD_NORMAL 2 /* normal.cpp: dense propagation (M A_euclid M^-1 with the numerically differentiated chart change M) */
+#define EQVIO_COORD_NORMAL 2 /* normal.cpp: A = M A_euclid M^-1 with the numerically differentiated, block-diagonal chart change M, applied block by block */
 
 #define EQVIO_CAMERA_PINHOLE 0
 #define EQVIO_CAMERA_RADTAN 1
