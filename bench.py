@@ -521,7 +521,7 @@ def run_b200(args, rank, local_rank, world, guard):
     N, K, W, P, R = args.landmarks, args.steps, args.warmup, args.profile_steps, args.sequences_per_gpu
     dev = torch.device("cuda", local_rank)
     host_cores = None
-    if world > 1:
+    if world > 1 and os.environ.get("EQVIO_BENCH_PIN", "1") != "0":
         # one disjoint block of host cores per rank: the e2e figure is a max over ranks of HOST wall clock, and ranks whose driver
         # threads share or migrate between cores pay for it (round 1: e2e efficiency 0.80 at 8 GPUs with every rank on cores 0-31)
         try:
@@ -641,7 +641,11 @@ def run_b200(args, rank, local_rank, world, guard):
                        "contract) + the all-gather of the final poses")
 
     t = torch.tensor([dev_ms, py_ms, cpp_ms, real_ms, collective_ms], dtype=torch.float64, device="cuda")
+    per_rank = None
     if dist:
+        allr = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)  # per-rank figures beside the max (a slow rank is a host-side finding, not a kernel one)
+        per_rank = [[float(x) for x in r] for r in allr]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max, py_ms_max, cpp_ms_max, real_ms_max, coll_ms_max = (float(x) for x in t)
 
@@ -705,6 +709,8 @@ def run_b200(args, rank, local_rank, world, guard):
                                 host_cores_rank0=host_cores),
                     e2e=dict(value=world * R * K / (e2e_ms * 1e-3), unit="updates/s", h2d_bytes_per_step=m["h2d"], d2h_bytes_per_step=m["d2h"],
                              ms_per_step=e2e_ms / K, collective_ms=coll_ms_max, collective_charged_ms=coll_share,
+                             per_rank_ms_per_step=([dict(value=r[0] / K, python_driver=r[1] / K, e2e=r[2] / K) for r in per_rank]
+                                                   if per_rank else None),
                              collective_note=(f"one all-gather of the trajectories per simulated lap ({LAP_UPDATES} updates); "
                                               f"{K} updates timed -> {K}/{LAP_UPDATES} of it is charged to e2e") if world > 1
                              else "single GPU: no collective",

@@ -643,9 +643,11 @@ int launch_compaction(eqvio_filter* f, int newN, const int* d_map, const int* d_
                       double newDepthVar) {
     if (newN > 0) {
         compact_landmarks_kernel<<<cdiv(newN, 128), 128, 0, f->stream>>>(f->lm[f->lmcur], f->lm[1 - f->lmcur], f->cap, f->dids[f->lmcur],
-                                                                          f->dids[1 - f->lmcur], d_map, newN, d_newP, d_newIds);
+                                                                          f->dids[1 - f->lmcur], d_map, newN, d_newP, d_newIds,
+                                                                          (const double*)f->d_Xs[f->xcur], f->d_Xs[1 - f->xcur]);
         LAUNCH_CHECK(f, "compact_landmarks_kernel");
         f->lmcur = 1 - f->lmcur;
+        f->xcur = 1 - f->xcur;  // Sigma, landmarks and X flip together (see the kernel)
     }
     const int nb = 8 + newN;
     dim3 block(32, 8);
@@ -828,9 +830,9 @@ int enqueue_propagation(eqvio_filter* f) {
         // C*, ytilde of the measured landmarks only read the landmarks the observer just integrated: right behind it on its stream,
         // beside the Riccati chain (the gate, which also needs the propagated Sigma, runs beside the sweep: enqueue_correction)
         const int nm = f->measHookNm;
-        meas_fn(f)<<<cdiv(nm, 128), 128, 0, f->stream2>>>(f->lm[1 - f->lmcur], f->cap, f->d_lmOf, nm, f->d_y, f->d_hdr, s.coordinateChoice,
-                                                           s.useEquivariantOutput ? 1 : 0, f->d_Cblk, f->d_ytilde, 1, 0, (const int*)(f->d_spec + 1),
-                                                           f->d_yIdx, f->d_status, 1 + N, f->d_Gamma, dimp_of(N), (int*)nullptr, 0, TL_SLOT(f));
+        launch_pdl(f, meas_fn(f), dim3(cdiv(nm, 128)), dim3(128), (size_t)0, f->stream2, (const double*)f->lm[1 - f->lmcur], f->cap, (const int*)f->d_lmOf, nm,
+                   (const double*)f->d_y, (const FrameHeader*)f->d_hdr, (int)s.coordinateChoice, s.useEquivariantOutput ? 1 : 0, f->d_Cblk, f->d_ytilde, 1, 0,
+                   (const int*)(f->d_spec + 1), (const int*)f->d_yIdx, f->d_status, 1 + N, f->d_Gamma, dimp_of(N), (int*)nullptr, 0, TL_SLOT(f));
         LAUNCH_CHECK(f, "meas_kernel");
     }
     CUDA_TRY(f, cudaEventRecord(f->evJoin, f->stream2));
@@ -841,8 +843,9 @@ int enqueue_propagation(eqvio_filter* f) {
         const double* Sin = f->Sig[f->cur];
         double* Sout = f->Sig[1 - f->cur];
         // prologue + landmark rows in one launch; also re-arms the gate flag
-        prep_fn(f)<<<1 + cdiv(N, PREP_LM), PREP_THREADS, 0, f->stream>>>(a, Sin, Sout, f->ld, nullptr, f->d_spec, f->lm[f->lmcur], f->cap, N,
-                                                                                   s.coordinateChoice, f->d_rows, TL_SLOT(f));
+        // (a programmatic dependent of the frame upload: its CTAs are resident when the upload's last store lands)
+        launch_pdl(f, prep_fn(f), dim3(1 + cdiv(N, PREP_LM)), dim3(PREP_THREADS), (size_t)0, f->stream, a, Sin, Sout, f->ld, (double*)nullptr, f->d_spec,
+                   (const double*)f->lm[f->lmcur], f->cap, N, (int)s.coordinateChoice, f->d_rows, TL_SLOT(f));
         LAUNCH_CHECK(f, "riccati_prep_kernel");
         if (N > 0) {
             const int nt = cdiv(N, TP);

@@ -622,6 +622,8 @@ __device__ void observer_chain_discrete(const PrepArgs& a, const ObsPre* s_pre, 
 __global__ void __launch_bounds__(OBSF_THREADS)
     observer_fused_kernel(PrepArgs a, const double* __restrict__ lmIn, double* __restrict__ lmOut, const int* __restrict__ idsIn,
                           int* __restrict__ idsOut, int cap, int N, int tl) {
+    // a programmatic dependent (the measurement rows, which wait for this grid's completion) may become resident right away
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     TL_MARK(tl, 0);
     __shared__ ObsStep s_steps[OBS_STAGE];
     __shared__ ObsPre s_pre[OBS_STAGE];
@@ -1078,8 +1080,11 @@ __global__ void new_landmark_kernel(const double* __restrict__ gate, const int* 
 __global__ void compact_landmarks_kernel(const double* __restrict__ src, double* __restrict__ dst, int cap,
                                          const int* __restrict__ srcIds, int* __restrict__ dstIds,
                                          const int* __restrict__ map, int newN, const double* __restrict__ newP,
-                                         const int* __restrict__ newIds) {
+                                         const int* __restrict__ newIds, const double* __restrict__ XsSrc, double* __restrict__ XsDst) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
+    // the sensor part of X moves to its other buffer as well: the three ping-pong indices (Sigma, landmarks, X) then always flip
+    // together, and a landmark-set change does not open a new family of CUDA-graph keys (a capture costs ~3 ms)
+    if (XsSrc && p < 23) XsDst[p] = XsSrc[p];
     if (p >= newN) return;
     int s = map[p];
     if (s >= 0) {
