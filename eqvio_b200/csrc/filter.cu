@@ -1269,38 +1269,66 @@ int vision_phase_a(eqvio_filter* f, double stamp, int n, const int* ids, const d
                     cudaGraphExecDestroy(victim->second.exec);
                     f->graphs.erase(victim);
                 }
-                const int c0 = f->cur, l0 = f->lmcur, x0 = f->xcur;
-                const long long launches0 = f->launches;
-                cudaGraph_t graph = nullptr;
-                CUDA_TRY(f, cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal));
-                std::vector<int> ids0 = f->ids;  // a captured landmark-set change assigns f->ids: the replay below does it for real
-                f->capturing = true;
-                rc = enqueue_steady_update(f, N, nm, change ? &plan : nullptr);
-                f->capturing = false;
-                cudaError_t ce = cudaStreamEndCapture(f->stream, &graph);
-                f->ids.swap(ids0);
+                // capture for the ping-pong indices (c, l, x); nothing executes, the indices are restored afterwards
+                auto capture = [&](int c, int l, int x, eqvio_filter::GraphEntry& ge) -> int {
+                    const int c0 = f->cur, l0 = f->lmcur, x0 = f->xcur;
+                    const long long launches0 = f->launches;
+                    f->cur = c;
+                    f->lmcur = l;
+                    f->xcur = x;
+                    cudaGraph_t graph = nullptr;
+                    cudaError_t cb = cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal);
+                    if (cb != cudaSuccess) {
+                        f->cur = c0; f->lmcur = l0; f->xcur = x0;
+                        f->err = std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(cb);
+                        return EQVIO_ERR_CUDA;
+                    }
+                    std::vector<int> ids0 = f->ids;  // a captured landmark-set change assigns f->ids: the replay below does it for real
+                    f->capturing = true;
+                    int rcc = enqueue_steady_update(f, N, nm, change ? &plan : nullptr);
+                    f->capturing = false;
+                    cudaError_t ce = cudaStreamEndCapture(f->stream, &graph);
+                    f->ids.swap(ids0);
+                    ge.cur2 = f->cur;
+                    ge.lmcur2 = f->lmcur;
+                    ge.xcur2 = f->xcur;
+                    ge.launches = f->launches - launches0;
+                    f->cur = c0;  // capture only records: the state flips when the graph is launched below
+                    f->lmcur = l0;
+                    f->xcur = x0;
+                    f->launches = launches0;
+                    if (rcc != EQVIO_OK) return rcc;
+                    if (ce != cudaSuccess || !graph) {
+                        f->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce);
+                        return EQVIO_ERR_CUDA;
+                    }
+                    ce = cudaGraphInstantiate(&ge.exec, graph, 0);
+                    cudaGraphDestroy(graph);
+                    if (ce != cudaSuccess) {
+                        f->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce);
+                        return EQVIO_ERR_CUDA;
+                    }
+                    ++f->graphCaptures;
+                    return EQVIO_OK;
+                };
                 eqvio_filter::GraphEntry ge;
-                ge.cur2 = f->cur;
-                ge.lmcur2 = f->lmcur;
-                ge.xcur2 = f->xcur;
-                ge.launches = f->launches - launches0;
-                f->cur = c0;  // capture only records: the state flips when the graph is launched below
-                f->lmcur = l0;
-                f->xcur = x0;
-                f->launches = launches0;
-                if (rc != EQVIO_OK) return rc;
-                if (ce != cudaSuccess || !graph) {
-                    f->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce);
-                    return EQVIO_ERR_CUDA;
-                }
-                ce = cudaGraphInstantiate(&ge.exec, graph, 0);
-                cudaGraphDestroy(graph);
-                if (ce != cudaSuccess) {
-                    f->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce);
-                    return EQVIO_ERR_CUDA;
-                }
-                ++f->graphCaptures;
+                if ((rc = capture(f->cur, f->lmcur, f->xcur, ge)) != EQVIO_OK) return rc;
                 it = f->graphs.emplace(key, ge).first;
+                // ... and its twin with every index flipped: a frame that flips the buffers an odd number of times (a landmark-set change
+                // in augmentLandmarkStates) would otherwise meet this shape again as a NEW key later, ~3 ms of capture + instantiation in
+                // the middle of a run instead of beside the first one
+                if (f->graphs.size() < 32) {
+                    std::vector<int> twin = key;
+                    twin[2] = 1 - f->cur;
+                    twin[3] = 1 - f->lmcur;
+                    twin[4] = 1 - f->xcur;
+                    if (f->graphs.find(twin) == f->graphs.end()) {
+                        eqvio_filter::GraphEntry gt;
+                        if ((rc = capture(1 - f->cur, 1 - f->lmcur, 1 - f->xcur, gt)) != EQVIO_OK) return rc;
+                        f->graphs.emplace(twin, gt);
+                        it = f->graphs.find(key);
+                    }
+                }
             }
             it->second.lastUse = ++f->graphClock;
             CUDA_TRY(f, cudaGraphLaunch(it->second.exec, f->stream));
