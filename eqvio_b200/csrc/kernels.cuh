@@ -622,8 +622,6 @@ __device__ void observer_chain_discrete(const PrepArgs& a, const ObsPre* s_pre, 
 __global__ void __launch_bounds__(OBSF_THREADS)
     observer_fused_kernel(PrepArgs a, const double* __restrict__ lmIn, double* __restrict__ lmOut, const int* __restrict__ idsIn,
                           int* __restrict__ idsOut, int cap, int N, int tl) {
-    // a programmatic dependent (the measurement rows, which wait for this grid's completion) may become resident right away
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     TL_MARK(tl, 0);
     __shared__ ObsStep s_steps[OBS_STAGE];
     __shared__ ObsPre s_pre[OBS_STAGE];
