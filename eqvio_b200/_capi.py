@@ -14,11 +14,11 @@ LIB_PATH = os.environ.get("EQVIO_B200_LIB", LIB_PATH)  # debug builds (-DEQVIO_T
 EQVIO_OK = 0
 # eqvio_set_tuning keys (include/eqvio_b200.h: EQVIO_TUNE_*), keyed by the keyword VIOFilter.setTuning takes
 TUNE = dict(correction=0, chunkLandmarks=1, speculate=2, graph=3, downdate=5, lookahead=6, fuseObserver=7, pdl=8,
-            fuseSmall=10, speculateNew=11, stageS=12, zeroCopy=13, propFusion=14)
+            fuseSmall=10, speculateNew=11, stageS=12, zeroCopy=13, propFusion=14, lazyDowndate=15)
 TUNE_HEADER_NAMES = dict(correction="CORRECTION", chunkLandmarks="CHUNK_LANDMARKS", speculate="SPECULATE", graph="GRAPH",
                          downdate="DOWNDATE", lookahead="LOOKAHEAD", fuseObserver="FUSE_OBSERVER", pdl="PDL",
                          fuseSmall="FUSE_SMALL", speculateNew="SPECULATE_NEW", stageS="STAGE_S", zeroCopy="ZERO_COPY",
-                         propFusion="PROP_FUSION")
+                         propFusion="PROP_FUSION", lazyDowndate="LAZY_DOWNDATE")
 EQVIO_ERR_INVALID_ARG = -1
 EQVIO_ERR_CUDA = -2
 EQVIO_ERR_NUMERIC = -3

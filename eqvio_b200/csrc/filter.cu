@@ -165,6 +165,14 @@ struct eqvio_filter {
     double hostWaitUs = 0;
     int lookahead = 2;   // 2 = automatic (on when the tile grid spans more than one wave, T >= 24), 1 = on, 0 = off: split each downdate into the tiles the next chunk gathers (urgent) and the rest (beside the next factor)
     double* d_Y2 = nullptr;
+    // lazy trailing updates of the look-ahead correction (EQVIO_TUNE_LAZY_DOWNDATE = M >= 1): the panels of every chunk stay in d_Z, the
+    // deferred tiles are visited once per M chunks (K = 64 M rows of Y per visit), d_lvl says through which chunk a tile is current
+    int lazyMerge = 1;
+    int bandSplit = 1;   // urgent tiles of the lazy form: two CTAs per tile
+    int restPersist = 0;    // 2 = deferred launch of the lazy form as a persistent kernel (two CTAs per SM drawing tiles from a counter)
+    int restAfterBand = 1;  // the deferred launch waits for the urgent one: the next factor (a programmatic dependent of the urgent
+                            // launch) is resident before the deferred tiles fill the SMs
+    int* d_lvl = nullptr;
     std::vector<cudaEvent_t> chunkEv;
     int* d_spec = nullptr;  // [0] set by the gate kernel when any measured landmark exceeds a threshold, [1] constant 0
     cudaEvent_t augEv[2] = {nullptr, nullptr};
@@ -533,6 +541,11 @@ int alloc_device(eqvio_filter* f) {
     CUDA_TRY(f, cudaMalloc(&f->d_Z, f->zElems * sizeof(double)));
     CUDA_TRY(f, cudaMalloc(&f->d_Ysplit, (size_t)(f->ld / TC_T) * TC_BLOCK_BYTES));
     CUDA_TRY(f, cudaMalloc(&f->d_Y2, (size_t)(f->ld / YB_T) * YB_TILE * sizeof(double)));
+    {
+        const size_t Tm = f->ld / YB_T + 1;  // level words | one tile counter per chunk (persistent deferred launches)
+        CUDA_TRY(f, cudaMalloc(&f->d_lvl, (Tm * (Tm + 1) + c1 + 8) * sizeof(int)));
+        CUDA_TRY(f, cudaMemsetAsync(f->d_lvl, 0, (Tm * (Tm + 1) + c1 + 8) * sizeof(int), f->stream));
+    }
     CUDA_TRY(f, cudaMalloc(&f->d_Lout, ((size_t)dimpMax + mMax + NB) * NB * sizeof(double)));
     {
         // block sweep (mode 2): Z = [S; W^T] for at most BC_MAX_ROWS measurement rows, tile-blocked panels, one inverse per block
@@ -1726,6 +1739,84 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
             }
             double* Ybuf[2] = {f->d_Z, f->d_Y2};
             const int* lo = f->h_lmOfSorted.data();
+            const size_t chunkStride = (size_t)T * YB_TILE;
+            const int M = f->lazyMerge;
+            if (M >= 1 && nchunks > 2 && (size_t)nchunks * chunkStride <= f->zElems) {
+                // Lazy trailing updates.  The panels of every chunk stay in d_Z; d_lvl[tile] = number of chunks applied to the tile.
+                //   band(c)  [f->stream, after factor(c)]: the tiles chunk c+1 gathers from, brought up to chunk c (K = 64 .. 64 (M+1))
+                //   rest(r)  [f->stream3, after factor(r)], r = M-1, 2M-1, ...: every other lower tile up to chunk r, EXCEPT the tile rows /
+                //            columns of the bands r .. r+M, which the band launches beside it own; band(r+M+1) waits for rest(r)
+                // so a deferred tile is read and written once per M chunks and the chain factor -> band -> factor never waits for a
+                // rest launch that was issued less than M+1 chunks ago.
+                std::vector<int> blo(nchunks, 0), bhi(nchunks, 0);
+                for (int c = 0; c + 1 < nchunks; ++c) {
+                    const int j1 = (c + 1) * bcMax;
+                    const int nb = std::min(bcMax, nm - j1);
+                    int rmin = lo[j1], rmax = rmin;
+                    for (int q = 1; q < nb; ++q) {
+                        rmin = std::min(rmin, lo[j1 + q]);
+                        rmax = std::max(rmax, lo[j1 + q]);
+                    }
+                    blo[c] = (SOFF + 3 * rmin) / DD_T;
+                    bhi[c] = (SOFF + 3 * rmax + 2) / DD_T;
+                }
+                CUDA_TRY(f, cudaMemsetAsync(f->d_lvl, 0, ((size_t)T * (T + 1) + nchunks) * sizeof(int), f->stream));
+                int lastRest = -1;
+                for (int c = 0; c < nchunks; ++c) {
+                    const int j0 = c * bcMax;
+                    const int bc = std::min(bcMax, nm - j0);
+                    double* Yc = f->d_Z + (size_t)c * chunkStride;
+                    cudaEvent_t evF = f->chunkEv[2 * c], evR = f->chunkEv[2 * c + 1];
+                    f->pdlHold = (j0 == 0);
+                    const int rc = launch_chunk_factor(f, ldy, dimp, j0, bc, r2, gin, gout, Yc, guard);
+                    f->pdlHold = false;
+                    if (rc != EQVIO_OK) return rc;
+                    std::swap(gin, gout);
+                    if (c == nchunks - 1) {  // last chunk: every tile up to date, full symmetric storage again
+                        if (lastRest >= 0) CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * lastRest + 1], 0));
+                        chunk_downdate_kernel<false><<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream>>>(
+                            f->Sig[f->cur], f->Sig[f->cur], f->ld, f->d_Z, guard, 0, T, DD_ALL, T, TL_SLOT(f), f->d_lvl, nchunks, chunkStride);
+                        LAUNCH_CHECK(f, "chunk_downdate_kernel");
+                        break;
+                    }
+                    {  // the newest rest launch this band's tiles were not excluded from
+                        const int r = ((c - M - 1 + 1) / M) * M - 1;  // largest r = kM - 1 <= c - M - 1
+                        if (c - M - 1 >= M - 1 && r >= 0) CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * r + 1], 0));
+                    }
+                    const int mlo = blo[c], mhi = bhi[c];
+                    const int w = mhi - mlo + 1;
+                    int nBand = w * (T - 1 - mhi);
+                    for (int ti = mlo; ti <= mhi; ++ti) nBand += ti + 1;
+                    CUDA_TRY(f, cudaEventRecord(evF, f->stream));
+                    if (f->bandSplit)
+                        chunk_downdate_kernel<true><<<2 * nBand, DD_THREADS, DD_SMEM, f->stream>>>(
+                            f->Sig[f->cur], f->Sig[f->cur], f->ld, f->d_Z, guard, mlo, mhi, DD_BAND, T, TL_SLOT(f), f->d_lvl, c + 1, chunkStride);
+                    else
+                        chunk_downdate_kernel<false><<<nBand, DD_THREADS, DD_SMEM, f->stream>>>(
+                            f->Sig[f->cur], f->Sig[f->cur], f->ld, f->d_Z, guard, mlo, mhi, DD_BAND, T, TL_SLOT(f), f->d_lvl, c + 1, chunkStride);
+                    LAUNCH_CHECK(f, "chunk_downdate_kernel");
+                    if ((c + 1) % M == 0) {
+                        const int xlo = mlo, xhi = bhi[std::min(c + M, nchunks - 2)];
+                        const int xw = xhi - xlo + 1;
+                        const int nRest = (T - xw) * (T - xw + 1) / 2;
+                        if (f->restAfterBand) CUDA_TRY(f, cudaEventRecord(evF, f->stream));
+                        CUDA_TRY(f, cudaStreamWaitEvent(f->stream3, evF, 0));
+                        if (nRest > 0) {
+                            f->pdlHold = true;
+                            const int perSm = f->restPersist;  // 0: one CTA per tile
+                            const int grid = perSm ? std::min(nRest, perSm * f->smCount) : nRest;
+                            launch_pdl(f, chunk_downdate_kernel<false>, dim3(grid), dim3(DD_THREADS), (size_t)(perSm ? DD_SMEM_PERSIST : DD_SMEM),
+                                       f->stream3, (const double*)f->Sig[f->cur], f->Sig[f->cur], f->ld, (const double*)f->d_Z, guard, xlo, xhi,
+                                       (int)DD_REST, T, TL_SLOT(f), f->d_lvl, c + 1, chunkStride,
+                                       perSm ? f->d_lvl + (size_t)T * (T + 1) + c : (int*)nullptr, nRest);
+                            f->pdlHold = false;
+                            LAUNCH_CHECK(f, "chunk_downdate_kernel");
+                        }
+                        CUDA_TRY(f, cudaEventRecord(evR, f->stream3));
+                        lastRest = c;
+                    }
+                }
+            } else
             for (int c = 0; c < nchunks; ++c) {
                 const int j0 = c * bcMax;
                 const int bc = std::min(bcMax, nm - j0);
@@ -1758,11 +1849,12 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                 chunk_downdate_kernel<false><<<nBand, DD_THREADS, DD_SMEM, f->stream>>>(f->Sig[f->cur], f->Sig[f->cur], f->ld, Yc, guard, mlo, mhi,
                                                                                  DD_BAND, T, TL_SLOT(f));
                 LAUNCH_CHECK(f, "chunk_downdate_kernel");
+                if (f->restAfterBand) CUDA_TRY(f, cudaEventRecord(evF, f->stream));
                 CUDA_TRY(f, cudaStreamWaitEvent(f->stream3, evF, 0));
                 if (nRest > 0) {
                     f->pdlHold = true;
                     launch_pdl(f, chunk_downdate_kernel<false>, dim3(nRest), dim3(DD_THREADS), (size_t)DD_SMEM, f->stream3, (const double*)f->Sig[f->cur],
-                               f->Sig[f->cur], f->ld, (const double*)Yc, guard, mlo, mhi, (int)DD_REST, T, TL_SLOT(f));
+                               f->Sig[f->cur], f->ld, (const double*)Yc, guard, mlo, mhi, (int)DD_REST, T, TL_SLOT(f), (int*)nullptr, 1, (size_t)0, (int*)nullptr, 0);
                     f->pdlHold = false;
                     LAUNCH_CHECK(f, "chunk_downdate_kernel");
                 }
@@ -1806,10 +1898,10 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                     // one wave with SMs to spare: two CTAs per tile (the launch lasts as long as its slowest CTA)
                     if (f->splitDowndate && T * (T + 1) / 2 <= f->smCount)
                         launch_pdl(f, chunk_downdate_kernel<true>, dim3(T * (T + 1)), dim3(DD_THREADS), DD_SMEM, f->stream, f->Sig[f->cur],
-                                   f->Sig[f->cur], f->ld, Y, guard, mlo, mhi, (int)DD_ALL, T, TL_SLOT(f));
+                                   f->Sig[f->cur], f->ld, Y, guard, mlo, mhi, (int)DD_ALL, T, TL_SLOT(f), (int*)nullptr, 1, (size_t)0, (int*)nullptr, 0);
                     else
                         launch_pdl(f, chunk_downdate_kernel<false>, dim3(T * (T + 1) / 2), dim3(DD_THREADS), DD_SMEM, f->stream, f->Sig[f->cur],
-                                   f->Sig[f->cur], f->ld, Y, guard, mlo, mhi, (int)DD_ALL, T, TL_SLOT(f));
+                                   f->Sig[f->cur], f->ld, Y, guard, mlo, mhi, (int)DD_ALL, T, TL_SLOT(f), (int*)nullptr, 1, (size_t)0, (int*)nullptr, 0);
                     LAUNCH_CHECK(f, "chunk_downdate_kernel");
                 }
                 prof_end(f, sk);
@@ -1998,7 +2090,7 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
         g_createError = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
         return EQVIO_ERR_CUDA;
     }
-    e = cudaFuncSetAttribute(chunk_downdate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM);
+    e = cudaFuncSetAttribute(chunk_downdate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM_PERSIST);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(chunk_downdate_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     // factor CTAs of the next chunk must fit beside the deferred downdate CTAs: keep the shared-memory carve-out at its maximum
@@ -2021,6 +2113,10 @@ int make_filter(const eqvio_settings* s, int device, int capacity, void* stream,
     f->cap = capacity;
     if (const char* pf = std::getenv("EQVIO_B200_PREFETCH")) f->prefetchSigma = std::atoi(pf) != 0;
     if (const char* er = std::getenv("EQVIO_B200_EARLY_ROWS")) f->earlyRows = std::atoi(er) != 0;
+    if (const char* lz = std::getenv("EQVIO_B200_LAZY")) f->lazyMerge = std::max(0, std::min(8, std::atoi(lz)));
+    if (const char* bs = std::getenv("EQVIO_B200_BAND_SPLIT")) f->bandSplit = std::atoi(bs) != 0;
+    if (const char* rb = std::getenv("EQVIO_B200_REST_AFTER_BAND")) f->restAfterBand = std::atoi(rb) != 0;
+    if (const char* rp = std::getenv("EQVIO_B200_REST_PERSIST")) f->restPersist = std::max(0, std::min(4, std::atoi(rp)));
     if (const char* cm = std::getenv("EQVIO_B200_CORRECTION")) {  // A/B runs of whole test / bench commands
         const int v = std::atoi(cm);
         if (v >= 0 && v <= 2) f->corrMode = v;
@@ -2257,6 +2353,7 @@ void eqvio_destroy(eqvio_filter* f) {
     cudaFree(f->d_bcCnt);
     for (auto& e : f->bcEv) cudaEventDestroy(e);
     cudaFree(f->d_Y2);
+    cudaFree(f->d_lvl);
     cudaFree(f->d_Ysplit);
     for (auto& e : f->chunkEv) cudaEventDestroy(e);
     cudaFree(f->d_Cblk);
@@ -2871,6 +2968,11 @@ int eqvio_set_tuning(eqvio_filter* f, int key, int value) {
         case EQVIO_TUNE_LOOKAHEAD:
             if (value < 0 || value > 2) return EQVIO_ERR_INVALID_ARG;
             f->lookahead = value;
+            clear_graphs(f);
+            return EQVIO_OK;
+        case EQVIO_TUNE_LAZY_DOWNDATE:
+            if (value < 0 || value > 8) return EQVIO_ERR_INVALID_ARG;
+            f->lazyMerge = value;
             clear_graphs(f);
             return EQVIO_OK;
         case EQVIO_TUNE_GRAPH:

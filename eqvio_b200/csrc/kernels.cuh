@@ -1939,6 +1939,9 @@ __global__ void __launch_bounds__(CH_THREADS)
 // ------------------------------------------------------------------------------------------------
 constexpr int DD_T = 64, DD_LD = YB_LD, DD_THREADS = 128;
 constexpr int DD_SMEM = 2 * DD_T * DD_LD * 8 + 16;
+// persistent deferred launch: padded so that exactly two of its CTAs fit on an SM (3 x (76.5 + 1) KB > 228 KB) and one CTA of an urgent
+// launch (69.6 + 1 KB) still fits beside them
+constexpr int DD_SMEM_PERSIST = 78336;
 enum { DD_ALL = 0, DD_BAND = 1, DD_REST = 2 };  // which tiles a launch of chunk_downdate_kernel covers
 
 // SPLIT: two CTAs per tile (32 of its 64 rows each).  When all lower tiles fit in one wave with SMs to spare (N <= 256: 91
@@ -1947,12 +1950,39 @@ enum { DD_ALL = 0, DD_BAND = 1, DD_REST = 2 };  // which tiles a launch of chunk
 template <bool SPLIT>
 __global__ void __launch_bounds__(DD_THREADS, 3)
     chunk_downdate_kernel(const double* SigIn, double* SigOut, int ld, const double* __restrict__ Y,
-                          const int* __restrict__ guard, int mirrorLo, int mirrorHi, int mode, int T, int tl) {
+                          const int* __restrict__ guard, int mirrorLo, int mirrorHi, int mode, int T, int tl,
+                          int* __restrict__ level = nullptr, int upto = 1, size_t chunkStride = 0, int* __restrict__ tileCtr = nullptr,
+                          int nTiles = 0) {
     pdl_wait();
     if (*guard) return;
     TL_MARK(tl, 0);
+    extern __shared__ __align__(16) unsigned char dd_smem_raw[];
+    double(*sA)[DD_LD] = reinterpret_cast<double(*)[DD_LD]>(dd_smem_raw);
+    double(*sB)[DD_LD] = sA + DD_T;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dd_smem_raw + 2 * DD_T * DD_LD * 8);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr uint32_t PANEL_BYTES = DD_T * DD_LD * 8;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // Persistent form (tileCtr != nullptr): the launch has fewer CTAs than tiles (at most two per SM, see DD_SMEM_PERSIST) and each
+    // CTA draws tile after tile from a counter, so the launch never has CTAs queued in front of the urgent launches beside it.
+    __shared__ int sTile;
+    uint32_t phase = 0;
+    bool firstTile = true;
+    for (;;) {
     int ti, tj;
-    const int bid = SPLIT ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    int bid = SPLIT ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    if (tileCtr) {
+        if (!firstTile) __syncthreads();  // every warp is done with the panels (and sTile) of the previous tile
+        if (tid == 0) sTile = atomicAdd(tileCtr, 1);
+        __syncthreads();
+        bid = sTile;
+        if (bid >= nTiles) break;
+    } else if (!firstTile) {
+        break;
+    }
     const int half = SPLIT ? (int)(blockIdx.x & 1) : 0;
     constexpr int NA = SPLIT ? 2 : 4;  // 8-row fragments per warp
     if (mode == DD_ALL) {
@@ -1979,20 +2009,26 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
         ti = ci < mirrorLo ? ci : ci + w;
         tj = cj < mirrorLo ? cj : cj + w;
     }
-    extern __shared__ __align__(16) unsigned char dd_smem_raw[];
-    double(*sA)[DD_LD] = reinterpret_cast<double(*)[DD_LD]>(dd_smem_raw);
-    double(*sB)[DD_LD] = sA + DD_T;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(dd_smem_raw + 2 * DD_T * DD_LD * 8);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i0 = ti * DD_T, j0 = tj * DD_T;
     const bool diag = ti == tj;
-    constexpr uint32_t PANEL_BYTES = DD_T * DD_LD * 8;
+    // Lazy form (level != nullptr): Y holds the panels of EVERY chunk of this update (chunk q at Y + q * chunkStride) and level[]
+    // says through which chunk a (half) tile is current; the launch brings its tiles up to chunk `upto` in one visit -- the tile
+    // is read and written once for K = 64 (upto - level) rows of Y.  Two words per lower tile (one per 32-row half): an unsplit
+    // launch reads the first and writes both, a split one keeps each CTA on its own word.
+    int q0 = 0, q1 = 1;
+    int* lv = nullptr;
+    if (level) {
+        lv = level + 2 * (ti * (ti + 1) / 2 + tj) + half;
+        q0 = *lv;
+        q1 = upto;
+    }
     if (tid == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(bar, diag ? PANEL_BYTES : 2 * PANEL_BYTES);
-        bulk_g2s(&sA[0][0], Y + (size_t)ti * YB_TILE, PANEL_BYTES, bar);
-        if (!diag) bulk_g2s(&sB[0][0], Y + (size_t)tj * YB_TILE, PANEL_BYTES, bar);
+        if (q0 < q1) {
+            const double* Yq = Y + (size_t)q0 * chunkStride;
+            mbar_expect_tx(bar, diag ? PANEL_BYTES : 2 * PANEL_BYTES);
+            bulk_g2s(&sA[0][0], Yq + (size_t)ti * YB_TILE, PANEL_BYTES, bar);
+            if (!diag) bulk_g2s(&sB[0][0], Yq + (size_t)tj * YB_TILE, PANEL_BYTES, bar);
+        }
     }
     // The Sigma tile goes straight into the accumulator fragment layout: element (r, c) of the tile is
     // Sigma[i0 + r, j0 + c]; for one (a, b, e) a warp touches 4 columns x 8 consecutive rows = whole sectors.
@@ -2008,20 +2044,37 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
             acc[a][b][0] = -cin[(size_t)(b * 8) * ld + a * 8];
             acc[a][b][1] = -cin[(size_t)(b * 8 + 1) * ld + a * 8];
         }
-    __syncthreads();  // barrier initialised for everyone
-    mbar_wait(bar, 0);
+    if (firstTile) __syncthreads();  // barrier initialised for everyone
+    firstTile = false;
     double(*sBB)[DD_LD] = diag ? sA : sB;
+    for (int q = q0; q < q1; ++q) {
+        if (q > q0) {
+            __syncthreads();  // every warp is done with the panels of chunk q - 1
+            if (tid == 0) {
+                const double* Yq = Y + (size_t)q * chunkStride;
+                mbar_expect_tx(bar, diag ? PANEL_BYTES : 2 * PANEL_BYTES);
+                bulk_g2s(&sA[0][0], Yq + (size_t)ti * YB_TILE, PANEL_BYTES, bar);
+                if (!diag) bulk_g2s(&sB[0][0], Yq + (size_t)tj * YB_TILE, PANEL_BYTES, bar);
+            }
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
 #pragma unroll 4
-    for (int k4 = 0; k4 < DD_T; k4 += 4) {
-        double af[NA], bf[4];
+        for (int k4 = 0; k4 < DD_T; k4 += 4) {
+            double af[NA], bf[4];
 #pragma unroll
-        for (int a = 0; a < NA; ++a) af[a] = sA[k4 + (lane & 3)][wm + a * 8 + (lane >> 2)];
+            for (int a = 0; a < NA; ++a) af[a] = sA[k4 + (lane & 3)][wm + a * 8 + (lane >> 2)];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) bf[b] = sBB[k4 + (lane & 3)][wn + b * 8 + (lane >> 2)];
+            for (int b = 0; b < 4; ++b) bf[b] = sBB[k4 + (lane & 3)][wn + b * 8 + (lane >> 2)];
 #pragma unroll
-        for (int a = 0; a < NA; ++a)
+            for (int a = 0; a < NA; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+                for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+    }
+    if (lv && tid == 0) {
+        lv[0] = upto;
+        if (!SPLIT) lv[1] = upto;
     }
     // acc = -(Sigma - Y^T Y): store negated.  Mirror tile: (c, c+1) are adjacent in memory -> 16-byte stores.  Between
     // chunks only the lower triangle has to be current, except for the columns the NEXT chunk gathers (its landmarks'
@@ -2041,6 +2094,7 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
                 *reinterpret_cast<double2*>(SigOut + (size_t)(i0 + fr + a * 8) * ld + j0 + fc + b * 8) = t;
             }
         }
+    }  // tile loop
     TL_MARK(tl, 1);
 }
 

@@ -353,7 +353,7 @@ class VIOFilter:
         """Evaluation-order knobs (eqvio_set_tuning, include/eqvio_b200.h EQVIO_TUNE_*): correction (0 = sequential chunks, 1 = batch
         sweep), chunkLandmarks, speculate, graph, downdate (0 = fp64 DMMA, 1 = tcgen05 split-bf16), lookahead (split
         downdates beside the next factor kernel), fuseObserver, pdl, fuseSmall, speculateNew, stageS (S blocks through one TMA
-        tensor copy).  Results agree across every knob (tests/test_gpu_parity.py)."""
+        tensor copy), lazyDowndate (M = deferred Sigma tiles visited once per M chunks in the look-ahead form, 0 = every chunk).  Results agree across every knob (tests/test_gpu_parity.py)."""
         for name, value in knobs.items():
             if value is None:
                 continue

@@ -265,6 +265,14 @@ int eqvio_get_host_profile(eqvio_filter* f, int reset, double us[4], long long* 
  *     tile rows / columns and the sensor-landmark strip runs beside it on another stream (chain: prologue + rows -> ll);
  *     0 = prologue + rows -> strip (writes the factors) -> ll.  Same expressions, bit-identical results. */
 #define EQVIO_TUNE_PROP_FUSION 14
+/*   EQVIO_TUNE_LAZY_DOWNDATE: M = 1 (default): in the look-ahead form of the sequential chunks (more than 768 measurement rows) the
+ *     panels Y_c of every chunk are kept, a per-tile word says through which chunk a tile of Sigma is current, the deferred launch
+ *     of every M-th chunk leaves out the tile rows / columns the next M + 1 chunks gather from, and the urgent launch of a chunk brings
+ *     its tiles up to date from wherever they stand (K = 64 .. 64 (M + 1) rows of Y per visit) -- so the chain factor -> urgent tiles
+ *     -> factor only waits for a deferred launch issued M + 1 chunks earlier;  0 = every chunk downdates every lower tile (K = 64)
+ *     and the urgent launch of chunk c waits for the deferred one of chunk c - 1.  Per tile the same products in the same order:
+ *     bit-identical results for every M. */
+#define EQVIO_TUNE_LAZY_DOWNDATE 15
 int eqvio_set_tuning(eqvio_filter* f, int key, int value);
 /* Version / build info string (arch the kernels were compiled for). */
 const char* eqvio_build_info(void);

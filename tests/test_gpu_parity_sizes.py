@@ -267,3 +267,23 @@ def test_large_step_exponential_uses_squarings():
         e = compare_states(snapshot_gpu(g), snapshot_oracle(o))
         assert e["ids_equal"] and e["sigma"] < 1e-8 and e["state"] < 1e-8, (k, e)
     g.close()
+
+
+@pytest.mark.parametrize("N,frames", [(300, 3), (1024, 2)])
+def test_lazy_downdate_orders_bit_identical(N, frames, monkeypatch):
+    """Look-ahead form of the sequential chunks with lazy trailing updates (EQVIO_TUNE_LAZY_DOWNDATE = M): deferred tiles visited once
+    per M chunks, urgent tiles split over two CTAs or not, deferred launch one CTA per tile or persistent -- per tile the same
+    products in the same order, so every variant must reproduce the every-chunk form (M = 0) bit for bit; M = 0 against the oracle."""
+    stream = make_stream(N=N, frames=frames, coord=0)
+    base = dict(correction=0, lookahead=1)
+    ref = run_gpu(stream, tuning=dict(base, lazyDowndate=0))
+    if N <= 300:
+        _check(ref, run_oracle(stream, structured=True))
+    for M, split, persist, after in ((1, 1, 0, 1), (1, 0, 0, 0), (2, 1, 0, 1), (2, 1, 2, 1), (3, 0, 2, 1), (5, 1, 1, 0)):
+        monkeypatch.setenv("EQVIO_B200_BAND_SPLIT", str(split))
+        monkeypatch.setenv("EQVIO_B200_REST_PERSIST", str(persist))
+        monkeypatch.setenv("EQVIO_B200_REST_AFTER_BAND", str(after))
+        got = run_gpu(stream, tuning=dict(base, lazyDowndate=M))
+        for k, (g, r) in enumerate(zip(got, ref)):
+            assert np.array_equal(g["Sigma"], r["Sigma"]), f"M={M} split={split} persist={persist}: Sigma differs at update {k}"
+            assert np.array_equal(g["sensor"], r["sensor"]) and np.array_equal(g["p"], r["p"]), f"M={M}: state differs at update {k}"
