@@ -1954,7 +1954,8 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
                           int* __restrict__ level = nullptr, int upto = 1, size_t chunkStride = 0, int* __restrict__ tileCtr = nullptr,
                           int nTiles = 0) {
     pdl_wait();
-    if (*guard) return;
+    // the gate flag is looked at only once the panel copies and the tile loads are in flight: its L2 round trip rides beside theirs
+    const int gateSet = *reinterpret_cast<const volatile int*>(guard);
     TL_MARK(tl, 0);
     extern __shared__ __align__(16) unsigned char dd_smem_raw[];
     double(*sA)[DD_LD] = reinterpret_cast<double(*)[DD_LD]>(dd_smem_raw);
@@ -2044,6 +2045,10 @@ __global__ void __launch_bounds__(DD_THREADS, 3)
             acc[a][b][0] = -cin[(size_t)(b * 8) * ld + a * 8];
             acc[a][b][1] = -cin[(size_t)(b * 8 + 1) * ld + a * 8];
         }
+    if (gateSet) {  // uniform; a bulk copy in flight must land before the CTA may leave
+        if (tid == 0 && q0 < q1) mbar_wait(bar, phase);
+        return;
+    }
     if (firstTile) __syncthreads();  // barrier initialised for everyone
     firstTile = false;
     double(*sBB)[DD_LD] = diag ? sA : sB;
