@@ -10,6 +10,7 @@ from .filter import (  # noqa: F401
     COORD_EUCLIDEAN, COORD_INVDEPTH, COORD_NORMAL, Camera, EqFState, IMUVelocity, Settings, VIOFilter, VIOSensorState,
     VIOState, VisionMeasurement, batchProcessVision, replayBatch)
 from .writer import VIOWriter, trajectory_errors  # noqa: F401
+from .stream import FeatureStream, run_stream, settings_from_yaml  # noqa: F401
 
 
 def build_info():

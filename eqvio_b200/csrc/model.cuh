@@ -211,7 +211,9 @@ HD V3 cam_undistort(const Camera& c, double u, double v) {
     V3 b = normalized(V3{(u - c.cx) / c.fx, (v - c.cy) / c.fy, 1.0});  // PinholeCamera.cpp:57-61
     if (c.model == CAM_RADTAN) {                                        // StandardCamera.cpp:50-56
         double dx, dy;
-        distort_homogeneous(b.x / b.z, b.y / b.z, c.inv_dist, c.ndist, dx, dy);
+        // invDist ALWAYS has five entries (the least-squares fit of StandardCamera.cpp:117-147 solves for five whatever the length of
+        // the forward model), so a four-coefficient camera -- EuRoC's sensor.yaml -- still undistorts with the r^6 term
+        distort_homogeneous(b.x / b.z, b.y / b.z, c.inv_dist, 5, dx, dy);
         b = normalized(V3{dx, dy, 1.0});
     } else if (c.model == CAM_EQUIDISTANT) {  // EquidistantCamera.cpp:48-68: damped Gauss-Newton on the sphere
         for (int iter = 0; iter < 30; ++iter) {

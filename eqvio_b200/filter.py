@@ -119,7 +119,7 @@ class Camera:
                 if rc != 0:
                     raise EqvioError(rc, "inverse distortion fit failed")
             else:
-                for i in range(len(dist)):
+                for i in range(min(5, len(inv_dist))):  # invDist always has five entries (StandardCamera.cpp:117-147)
                     pod.inv_dist[i] = float(inv_dist[i])
         self.pod = pod
 
@@ -128,7 +128,7 @@ class Camera:
         """From the dict produced by the oracle cameras' ``pod()`` (tests) or any mapping with the same keys."""
         nd = d["ndist"]
         return Camera(d["width"], d["height"], d["fx"], d["fy"], d["cx"], d["cy"], d["dist"][:nd],
-                      d["inv_dist"][:nd] if (nd and d["model"] == CAMERA_RADTAN) else None, model=d["model"])
+                      d["inv_dist"][:5] if (nd and d["model"] == CAMERA_RADTAN) else None, model=d["model"])
 
 
 @dataclass

@@ -78,7 +78,7 @@ typedef struct eqvio_settings {
 typedef struct eqvio_camera {
     int model; /* EQVIO_CAMERA_* */
     int width, height;
-    int ndist; /* number of valid entries of dist / inv_dist: 0, 2, 4 or 5 */
+    int ndist; /* number of valid entries of dist: 0, 2, 4 or 5 (inv_dist always holds the five entries of StandardCamera::invDist) */
     double fx, fy, cx, cy;
     double dist[5];
     double inv_dist[5];

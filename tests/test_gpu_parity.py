@@ -207,11 +207,14 @@ def test_keep_lost_landmarks():
     g.close()
 
 
-def test_radtan_camera():
+@pytest.mark.parametrize("ncoef", [5, 4])
+def test_radtan_camera(ncoef):
+    """Radtan camera with five and with FOUR distortion coefficients (EuRoC's sensor.yaml gives four): the inverse model always has
+    five (StandardCamera.cpp:117-147), so the undistortion of a four-coefficient camera must still apply the r^6 term."""
     from oracle.camera import StandardCamera
 
     stream = make_stream(N=24, frames=1, coord=1)
-    dist = [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0]
+    dist = [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0][:ncoef]
     cam = StandardCamera(752, 480, 458.654, 457.296, 367.215, 248.375, dist)
     stream["cam"] = cam
     # re-project the recorded measurements through the distorted camera
