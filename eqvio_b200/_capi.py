@@ -107,6 +107,7 @@ SIGNATURES = {
     "eqvio_replay": (_I, [_H, _I, C.c_void_p, C.c_void_p, C.c_size_t, _PD, _PD]),
     "eqvio_get_host_profile": (_I, [_H, _I, _PD, C.POINTER(C.c_longlong)]),
     "eqvio_set_tuning": (_I, [_H, _I, _I]),
+    "eqvio_plan_lazy_downdates": (_I, [_I, _I, _PI, _PI, _I, _PI, _I]),
     "eqvio_build_info": (C.c_char_p, []),
 }
 

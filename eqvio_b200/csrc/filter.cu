@@ -1556,6 +1556,47 @@ int launch_correction(eqvio_filter* f, const int* guard) {
     return EQVIO_OK;
 }
 
+// Launch plan of the lazy trailing updates (sequential chunks with look-ahead, EQVIO_TUNE_LAZY_DOWNDATE = M >= 1).  Pure host logic,
+// exported as eqvio_plan_lazy_downdates so that the CPU tests can check its invariants without a GPU (tests/test_lazy_plan.py):
+//   chunk c < nchunks-1:  factor(c);  [wait for the deferred launch of chunk waitRest];  urgent launch over the band [blo, bhi] of tile
+//                         rows / columns chunk c+1 gathers from, up to chunk c;  if hasRest: deferred launch on the side stream over
+//                         every lower tile with neither index in [xlo, xhi] (the bands of chunks c .. c+M), up to chunk c
+//   chunk nchunks-1:      factor;  wait for the last deferred launch;  every lower tile up to chunk nchunks-1, mirrored.
+struct LazyStep {
+    int blo, bhi, nBand;  // urgent launch
+    int waitRest;         // chunk whose deferred launch must have finished before this chunk's urgent / final launch (-1: none)
+    int hasRest, xlo, xhi, nRest;
+};
+static void plan_lazy_downdates(int T, int nchunks, const int* blo, const int* bhi, int M, std::vector<LazyStep>& plan) {
+    plan.assign(nchunks, LazyStep{0, 0, 0, -1, 0, 0, 0, 0});
+    int lastRest = -1;
+    for (int c = 0; c < nchunks; ++c) {
+        LazyStep& s = plan[c];
+        if (c == nchunks - 1) {
+            s.blo = 0;
+            s.bhi = T;
+            s.nBand = T * (T + 1) / 2;
+            s.waitRest = lastRest;
+            break;
+        }
+        // the newest deferred launch this band's tiles were not left out of: largest r = kM - 1 <= c - M - 1
+        if (c >= 2 * M) s.waitRest = ((c - M) / M) * M - 1;
+        s.blo = blo[c];
+        s.bhi = bhi[c];
+        const int w = s.bhi - s.blo + 1;
+        s.nBand = w * (T - 1 - s.bhi);
+        for (int ti = s.blo; ti <= s.bhi; ++ti) s.nBand += ti + 1;
+        if ((c + 1) % M == 0) {
+            s.hasRest = 1;
+            s.xlo = s.blo;
+            s.xhi = bhi[std::min(c + M, nchunks - 2)];
+            const int xw = s.xhi - s.xlo + 1;
+            s.nRest = (T - xw) * (T - xw + 1) / 2;
+            lastRest = c;
+        }
+    }
+}
+
 // One chunk factor launch (S_c, its elimination, Y_c, Gamma).
 int launch_chunk_factor(eqvio_filter* f, int ldy, int dimp, int j0, int bc, double r2, const double* gin, double* gout, double* Yc,
                         const int* guard) {
@@ -1761,8 +1802,10 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                     bhi[c] = (SOFF + 3 * rmax + 2) / DD_T;
                 }
                 CUDA_TRY(f, cudaMemsetAsync(f->d_lvl, 0, ((size_t)T * (T + 1) + nchunks) * sizeof(int), f->stream));
-                int lastRest = -1;
+                std::vector<LazyStep> plan;
+                plan_lazy_downdates(T, nchunks, blo.data(), bhi.data(), M, plan);
                 for (int c = 0; c < nchunks; ++c) {
+                    const LazyStep& st = plan[c];
                     const int j0 = c * bcMax;
                     const int bc = std::min(bcMax, nm - j0);
                     double* Yc = f->d_Z + (size_t)c * chunkStride;
@@ -1772,48 +1815,36 @@ int enqueue_correction(eqvio_filter* f, int nm, const int* guard, bool fuseGate,
                     f->pdlHold = false;
                     if (rc != EQVIO_OK) return rc;
                     std::swap(gin, gout);
+                    if (st.waitRest >= 0) CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * st.waitRest + 1], 0));
                     if (c == nchunks - 1) {  // last chunk: every tile up to date, full symmetric storage again
-                        if (lastRest >= 0) CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * lastRest + 1], 0));
-                        chunk_downdate_kernel<false><<<T * (T + 1) / 2, DD_THREADS, DD_SMEM, f->stream>>>(
+                        chunk_downdate_kernel<false><<<st.nBand, DD_THREADS, DD_SMEM, f->stream>>>(
                             f->Sig[f->cur], f->Sig[f->cur], f->ld, f->d_Z, guard, 0, T, DD_ALL, T, TL_SLOT(f), f->d_lvl, nchunks, chunkStride);
                         LAUNCH_CHECK(f, "chunk_downdate_kernel");
                         break;
                     }
-                    {  // the newest rest launch this band's tiles were not excluded from
-                        const int r = ((c - M - 1 + 1) / M) * M - 1;  // largest r = kM - 1 <= c - M - 1
-                        if (c - M - 1 >= M - 1 && r >= 0) CUDA_TRY(f, cudaStreamWaitEvent(f->stream, f->chunkEv[2 * r + 1], 0));
-                    }
-                    const int mlo = blo[c], mhi = bhi[c];
-                    const int w = mhi - mlo + 1;
-                    int nBand = w * (T - 1 - mhi);
-                    for (int ti = mlo; ti <= mhi; ++ti) nBand += ti + 1;
                     CUDA_TRY(f, cudaEventRecord(evF, f->stream));
                     if (f->bandSplit)
-                        chunk_downdate_kernel<true><<<2 * nBand, DD_THREADS, DD_SMEM, f->stream>>>(
-                            f->Sig[f->cur], f->Sig[f->cur], f->ld, f->d_Z, guard, mlo, mhi, DD_BAND, T, TL_SLOT(f), f->d_lvl, c + 1, chunkStride);
+                        chunk_downdate_kernel<true><<<2 * st.nBand, DD_THREADS, DD_SMEM, f->stream>>>(
+                            f->Sig[f->cur], f->Sig[f->cur], f->ld, f->d_Z, guard, st.blo, st.bhi, DD_BAND, T, TL_SLOT(f), f->d_lvl, c + 1, chunkStride);
                     else
-                        chunk_downdate_kernel<false><<<nBand, DD_THREADS, DD_SMEM, f->stream>>>(
-                            f->Sig[f->cur], f->Sig[f->cur], f->ld, f->d_Z, guard, mlo, mhi, DD_BAND, T, TL_SLOT(f), f->d_lvl, c + 1, chunkStride);
+                        chunk_downdate_kernel<false><<<st.nBand, DD_THREADS, DD_SMEM, f->stream>>>(
+                            f->Sig[f->cur], f->Sig[f->cur], f->ld, f->d_Z, guard, st.blo, st.bhi, DD_BAND, T, TL_SLOT(f), f->d_lvl, c + 1, chunkStride);
                     LAUNCH_CHECK(f, "chunk_downdate_kernel");
-                    if ((c + 1) % M == 0) {
-                        const int xlo = mlo, xhi = bhi[std::min(c + M, nchunks - 2)];
-                        const int xw = xhi - xlo + 1;
-                        const int nRest = (T - xw) * (T - xw + 1) / 2;
+                    if (st.hasRest) {
                         if (f->restAfterBand) CUDA_TRY(f, cudaEventRecord(evF, f->stream));
                         CUDA_TRY(f, cudaStreamWaitEvent(f->stream3, evF, 0));
-                        if (nRest > 0) {
+                        if (st.nRest > 0) {
                             f->pdlHold = true;
                             const int perSm = f->restPersist;  // 0: one CTA per tile
-                            const int grid = perSm ? std::min(nRest, perSm * f->smCount) : nRest;
+                            const int grid = perSm ? std::min(st.nRest, perSm * f->smCount) : st.nRest;
                             launch_pdl(f, chunk_downdate_kernel<false>, dim3(grid), dim3(DD_THREADS), (size_t)(perSm ? DD_SMEM_PERSIST : DD_SMEM),
-                                       f->stream3, (const double*)f->Sig[f->cur], f->Sig[f->cur], f->ld, (const double*)f->d_Z, guard, xlo, xhi,
+                                       f->stream3, (const double*)f->Sig[f->cur], f->Sig[f->cur], f->ld, (const double*)f->d_Z, guard, st.xlo, st.xhi,
                                        (int)DD_REST, T, TL_SLOT(f), f->d_lvl, c + 1, chunkStride,
-                                       perSm ? f->d_lvl + (size_t)T * (T + 1) + c : (int*)nullptr, nRest);
+                                       perSm ? f->d_lvl + (size_t)T * (T + 1) + c : (int*)nullptr, st.nRest);
                             f->pdlHold = false;
                             LAUNCH_CHECK(f, "chunk_downdate_kernel");
                         }
                         CUDA_TRY(f, cudaEventRecord(evR, f->stream3));
-                        lastRest = c;
                     }
                 }
             } else
@@ -3030,6 +3061,18 @@ int eqvio_debug_bc_timing(long long out[16], int warps[BC_S_WARPS * 64]) {
     return cudaMemcpyFromSymbol(warps, g_bc_warp, sizeof(int) * BC_S_WARPS * 64) == cudaSuccess ? 0 : -2;
 }
 #endif
+
+int eqvio_plan_lazy_downdates(int T, int nchunks, const int* band_lo, const int* band_hi, int M, int* out, int max_steps) {
+    if (T < 1 || nchunks < 1 || M < 1 || !band_lo || !band_hi || !out || max_steps < nchunks) return EQVIO_ERR_INVALID_ARG;
+    std::vector<LazyStep> plan;
+    plan_lazy_downdates(T, nchunks, band_lo, band_hi, M, plan);
+    for (int c = 0; c < nchunks; ++c) {
+        const LazyStep& s = plan[c];
+        const int v[8] = {s.blo, s.bhi, s.nBand, s.waitRest, s.hasRest, s.xlo, s.xhi, s.nRest};
+        for (int k = 0; k < 8; ++k) out[8 * c + k] = v[k];
+    }
+    return nchunks;
+}
 
 const char* eqvio_build_info(void) { return "eqvio_b200 sm_100a fp64 (CUDA " EQVIO_STR(__CUDACC_VER_MAJOR__) "." EQVIO_STR(__CUDACC_VER_MINOR__) ")"; }
 

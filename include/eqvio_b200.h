@@ -274,6 +274,13 @@ int eqvio_get_host_profile(eqvio_filter* f, int reset, double us[4], long long* 
  *     bit-identical results for every M. */
 #define EQVIO_TUNE_LAZY_DOWNDATE 15
 int eqvio_set_tuning(eqvio_filter* f, int key, int value);
+/* Launch plan of the lazy trailing updates (EQVIO_TUNE_LAZY_DOWNDATE = M) for T x T tiles of Sigma and nchunks landmark chunks;
+ * band_lo[c] .. band_hi[c] (c < nchunks - 1) = the tile rows / columns chunk c + 1 gathers from.  Host logic only (no GPU
+ * needed): out[8 c ..] = band lo, band hi, urgent tiles, chunk whose deferred launch the urgent launch waits for (-1: none), deferred
+ * launch issued (0 / 1), its left-out tile range lo, hi, its tile count.  Returns nchunks, or EQVIO_ERR_INVALID_ARG.  This is the
+ * plan eqvio_process_vision executes; tests/test_lazy_plan.py checks its invariants (no tile shared by launches that may overlap,
+ * every tile current at the end). */
+int eqvio_plan_lazy_downdates(int T, int nchunks, const int* band_lo, const int* band_hi, int M, int* out, int max_steps);
 /* Version / build info string (arch the kernels were compiled for). */
 const char* eqvio_build_info(void);
 
